@@ -1,0 +1,233 @@
+/*
+ * lh264_b200.h — C ABI of the B200-native hot path of losslessh264.
+ *
+ * This is the flat shim between the host decoder (NAL/slice/CAVLC parse, which stays on the
+ * CPU) and the sm_100a CUDA kernels that do macroblock reconstruction.  Plain pointers and
+ * sizes only: no C++ types, no torch types.  Everything here replaces a specific piece of the
+ * reference (paths relative to the reference root, OpenH264 v1.4 fork "losslessh264"):
+ *
+ *   lh264_mb_rec / lh264_slice_rec    <- SDqLayer per-MB SoA hand-off record
+ *                                        (codec/decoder/core/inc/dec_frame.h:61-127,
+ *                                         allocated at decoder_core.cpp:1226-1348) and the
+ *                                        slice-header fields the reconstruction reads
+ *                                        (slice.h: SSliceHeader; deblocking.cpp:872-905).
+ *   lh264_recon_submit()              <- WelsTargetSliceConstruction  decode_slice.cpp:110-206
+ *                                        (= per MB WelsTargetMbConstruction :353-373, then
+ *                                        WelsDeblockingFilterSlice deblocking.cpp:872-933),
+ *                                        for ALL slices of one picture, for a BATCH of pictures
+ *                                        belonging to independent streams.
+ *   lh264_stream_open()/pictures      <- PPicture pool / DPB storage (pic_queue.cpp:60-107);
+ *                                        border handling replaces ExpandReferencingPicture
+ *                                        (expand_pic.cpp:37-174) by clamp-at-read.
+ *   lh264_picture_read()              <- DecodeFrameConstruction output pointers
+ *                                        (decoder_core.cpp:56-217): cropped I420 to host.
+ *   lh264_k_*()                       <- the function-pointer kernel tables of
+ *                                        SWelsDecoderContext (decoder_context.h:391-407):
+ *                                        pIdctResAddPredFunc, sMcFunc, sDeblockingFunc,
+ *                                        pGetI*PredFunc, sExpandPicFunc.  Batched, for
+ *                                        kernel-level parity tests.
+ *
+ * Error convention: every function returns LH264_OK (0) or a negative LH264_E_* code; no
+ * exceptions cross this boundary.  There is NO CPU fallback: with no usable CUDA device
+ * lh264_ctx_create() fails with LH264_E_NO_DEVICE.
+ */
+#ifndef LH264_B200_H_
+#define LH264_B200_H_
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LH264_ABI_VERSION 1
+
+/* ---- error codes ------------------------------------------------------------------------ */
+#define LH264_OK             0
+#define LH264_E_INVALID     -1   /* bad argument / malformed record                         */
+#define LH264_E_NO_DEVICE   -2   /* no CUDA device / driver; there is no CPU fallback        */
+#define LH264_E_CUDA        -3   /* a CUDA call failed; see lh264_last_error()               */
+#define LH264_E_NOMEM       -4
+#define LH264_E_UNSUPPORTED -5
+
+/* ---- macroblock record -------------------------------------------------------------------- */
+/* mb_type (reference bitmask values wels_common_defs.h:264-276 are folded into an enum)     */
+enum {
+  LH264_MB_NONE   = 0,  /* not decoded in this picture: samples left untouched               */
+  LH264_MB_I4x4   = 1,
+  LH264_MB_I8x8   = 2,
+  LH264_MB_I16x16 = 3,
+  LH264_MB_IPCM   = 4,  /* 384 samples carried as int16 in the coefficient pool              */
+  LH264_MB_P16x16 = 5,
+  LH264_MB_P16x8  = 6,
+  LH264_MB_P8x16  = 7,
+  LH264_MB_P8x8   = 8,  /* also P_8x8ref0                                                    */
+  LH264_MB_PSKIP  = 9
+};
+#define LH264_MB_IS_INTRA(t) ((t) >= LH264_MB_I4x4 && (t) <= LH264_MB_IPCM)
+#define LH264_MB_IS_INTER(t) ((t) >= LH264_MB_P16x16)
+
+enum { LH264_SUB_8x8 = 0, LH264_SUB_8x4 = 1, LH264_SUB_4x8 = 2, LH264_SUB_4x4 = 3 };
+
+/* Resolved intra 4x4 / 8x8 predictor index.  0..8 are the H.264 modes; 9..13 are the
+ * availability variants the reference resolves at parse time (pIntra4x4FinalMode,
+ * wels_common_defs.h:314-331).                                                              */
+enum {
+  LH264_I4_V = 0, LH264_I4_H = 1, LH264_I4_DC = 2, LH264_I4_DDL = 3, LH264_I4_DDR = 4,
+  LH264_I4_VR = 5, LH264_I4_HD = 6, LH264_I4_VL = 7, LH264_I4_HU = 8,
+  LH264_I4_DC_L = 9, LH264_I4_DC_T = 10, LH264_I4_DC_128 = 11,
+  LH264_I4_DDL_TOP = 12, /* top-right unavailable: replicate top[3] (top[7] for 8x8)       */
+  LH264_I4_VL_TOP = 13
+};
+/* Resolved intra 16x16 luma predictor (wels_common_defs.h:302-311).                          */
+enum { LH264_I16_V = 0, LH264_I16_H = 1, LH264_I16_DC = 2, LH264_I16_P = 3,
+       LH264_I16_DC_L = 4, LH264_I16_DC_T = 5, LH264_I16_DC_128 = 6 };
+/* Resolved intra chroma predictor (wels_common_defs.h:334-343).                              */
+enum { LH264_C_DC = 0, LH264_C_H = 1, LH264_C_V = 2, LH264_C_P = 3,
+       LH264_C_DC_L = 4, LH264_C_DC_T = 5, LH264_C_DC_128 = 6 };
+
+#define LH264_MBF_TRANSFORM8x8 0x01
+
+/* One macroblock, 128 bytes, 128-byte aligned in the batch (one L2 line / one warp-wide
+ * 128-bit-per-lane... load).  Raster MB order inside a picture.
+ *
+ * Block index conventions: "z" = H.264 4x4 block decode order (8x8 quadrant major);
+ * "r" = raster order of the 4x4 blocks inside the MB (r = 4*by + bx).                       */
+typedef struct lh264_mb_rec {
+  uint8_t  mb_type;           /* LH264_MB_*                                                  */
+  uint8_t  flags;             /* LH264_MBF_*                                                 */
+  uint8_t  cbp;               /* coded_block_pattern: luma bits 0..3, chroma bits 4..5       */
+  uint8_t  qp_y;              /* luma QP (pLumaQp)                                           */
+  uint8_t  qp_c[2];           /* Cb, Cr QP (pChromaQp[2])                                    */
+  uint8_t  i16_mode;          /* LH264_I16_* (pIntraPredMode[7])                             */
+  uint8_t  chroma_mode;       /* LH264_C_*   (pChromaPredMode)                               */
+  uint16_t slice_idx;         /* index into the picture's slice table (pSliceIdc)            */
+  uint8_t  nxn_avail;         /* I8x8 neighbour flags, bit0 top, bit1 left, bit2 top-left,
+                                 bit3 top-right  (pIntraNxNAvailFlag, rec_mb.cpp:88-97)      */
+  uint8_t  reserved0;
+  uint32_t nz_mask;           /* bit r (r<16): luma 4x4 block r has non-zero count (pNzc);
+                                 bits 16..19 Cb 2x2 raster, 20..23 Cr.  Used for bS.         */
+  uint32_t coded_mask;        /* bit z (z<16 luma in z order; 16..19 Cb; 20..23 Cr): the
+                                 16-coefficient block is present in the coefficient pool     */
+  uint32_t coef_off;          /* index (in 16-coefficient blocks) of this MB's first present
+                                 block in the picture's coefficient pool                     */
+  int8_t   ref_idx[4];        /* ref_idx_l0 per 8x8 quadrant (raw index: bS compares these)  */
+  uint8_t  sub_mb_type[4];    /* LH264_SUB_* per 8x8 quadrant (P8x8 only)                    */
+  uint8_t  intra_mode[16];    /* LH264_I4_* per 4x4 block in z order; I8x8 uses [0,4,8,12]   */
+  int16_t  mv[16][2];         /* final motion vectors (quarter-pel) per 4x4 block, r order   */
+  uint8_t  reserved1[16];
+} lh264_mb_rec;
+
+/* Coefficient pool: int16 *quantised levels* (the reference's pScaledTCoeffQuant,
+ * decoder_core.cpp:1226+; dequantisation moves to the GPU).  Present blocks of one MB are
+ * consecutive, ordered by increasing bit index of coded_mask; each is 16 int16 in raster order
+ * of the 4x4 block.  With LH264_MBF_TRANSFORM8x8 the four bits of a luma quadrant are set or
+ * clear together and their 64 int16 are one raster 8x8 block.  Intra16x16 luma DC and chroma DC
+ * levels sit in slot 0 of their block (same as the reference).  IPCM: coded_mask = 0xFFFFFF and
+ * the 384 int16 are the samples: Y 16x16 raster, Cb 8x8 raster, Cr 8x8 raster.               */
+
+#define LH264_MAX_REFS 16
+
+typedef struct lh264_slice_rec {
+  int32_t  first_mb;
+  int32_t  num_mbs;
+  uint8_t  slice_type;              /* 0 = P, 2 = I (H.264 slice_type % 5)                    */
+  uint8_t  disable_deblocking_idc;  /* 0, 1 or 2                                              */
+  int8_t   alpha_c0_offset;         /* already doubled (slice_alpha_c0_offset_div2 * 2)       */
+  int8_t   beta_offset;             /* already doubled                                        */
+  uint8_t  num_ref_idx_l0;
+  uint8_t  weighted_pred;           /* explicit WP on (rec_mb.cpp:276-341)                    */
+  uint8_t  luma_log2_denom;
+  uint8_t  chroma_log2_denom;
+  int16_t  ref_slot[LH264_MAX_REFS];/* picture slot of RefPicList0[i] after reordering; the
+                                       host has already applied the "missing reference ->
+                                       list entry 0" fallback (rec_mb.cpp:229-233)            */
+  int16_t  luma_weight[LH264_MAX_REFS];
+  int16_t  luma_offset[LH264_MAX_REFS];
+  int16_t  chroma_weight[LH264_MAX_REFS][2];
+  int16_t  chroma_offset[LH264_MAX_REFS][2];
+} lh264_slice_rec;
+
+/* One picture to reconstruct (all of its slices).  All pointers are HOST pointers for
+ * lh264_recon_submit(); the library copies what it needs before returning only if
+ * LH264_SUBMIT_COPY is set, otherwise the memory must stay valid until lh264_sync().        */
+typedef struct lh264_picture_desc {
+  int32_t  stream;                  /* handle from lh264_stream_open                          */
+  int32_t  cur_slot;                /* picture slot to reconstruct into                       */
+  int32_t  n_slices;
+  int32_t  n_coef_blocks;           /* blocks of 16 int16 in coefs                            */
+  const lh264_slice_rec* slices;
+  const lh264_mb_rec*    mbs;       /* mb_w*mb_h records, raster order                        */
+  const int16_t*         coefs;
+} lh264_picture_desc;
+
+typedef struct lh264_ctx lh264_ctx;
+
+/* ---- context / streams ---------------------------------------------------------------------- */
+int  lh264_abi_version(void);
+const char* lh264_last_error(void);
+
+/* device: CUDA ordinal.  cuda_stream: a cudaStream_t to run on (e.g. the torch current
+ * stream), or NULL for a library-owned stream.                                              */
+int  lh264_ctx_create(lh264_ctx** out, int device, void* cuda_stream);
+void lh264_ctx_destroy(lh264_ctx* ctx);
+
+/* Opens a stream: allocates n_slots pictures of mb_w x mb_h macroblocks in HBM, pre-filled
+ * with 128 (pic_queue.cpp:96).  Returns the stream handle (>= 0) or an error.               */
+int  lh264_stream_open(lh264_ctx* ctx, int mb_w, int mb_h, int n_slots);
+int  lh264_stream_close(lh264_ctx* ctx, int stream);
+
+/* ---- the hot path ----------------------------------------------------------------------------- */
+/* Reconstructs a batch of pictures (at most one per stream per call; streams are
+ * independent).  Host buffers in, asynchronous on the context's CUDA stream:
+ * H2D of records + coefficient pools, then the reconstruction kernels.                      */
+int  lh264_recon_submit(lh264_ctx* ctx, const lh264_picture_desc* pics, int n_pics);
+
+/* Resident variant used by the roofline bench: stage a batch in HBM once, replay it.        */
+typedef struct lh264_resident_batch lh264_resident_batch;
+int  lh264_batch_upload(lh264_ctx* ctx, const lh264_picture_desc* pics, int n_pics,
+                        lh264_resident_batch** out);
+int  lh264_batch_recon(lh264_ctx* ctx, lh264_resident_batch* batch);
+void lh264_batch_free(lh264_ctx* ctx, lh264_resident_batch* batch);
+/* number of kernel launches issued by this context so far                                   */
+uint64_t lh264_kernel_launches(const lh264_ctx* ctx);
+/* accumulated device time (ms, CUDA events on the context stream) of one kernel family
+ * since the last reset: 0 inter, 1 intra, 2 deblock, 3 all; reset with family = -1           */
+float lh264_kernel_ms(lh264_ctx* ctx, int family);
+
+/* Copies the cropped I420 picture to host memory (asynchronous unless sync != 0).
+ * crop_* in luma samples, even.  Strides in bytes.                                          */
+int  lh264_picture_read(lh264_ctx* ctx, int stream, int slot,
+                        int crop_x, int crop_y, int width, int height,
+                        uint8_t* dst_y, int stride_y,
+                        uint8_t* dst_u, uint8_t* dst_v, int stride_c, int sync);
+/* Uploads a full (uncropped, mb_w*16 x mb_h*16) I420 picture into a slot — used by tests and
+ * by host-side error concealment.                                                           */
+int  lh264_picture_write(lh264_ctx* ctx, int stream, int slot,
+                         const uint8_t* src_y, int stride_y,
+                         const uint8_t* src_u, const uint8_t* src_v, int stride_c);
+/* Device pointers of a slot (for zero-copy consumers such as torch); pitch in bytes.        */
+int  lh264_picture_device_ptrs(lh264_ctx* ctx, int stream, int slot,
+                               void** y, void** u, void** v, int* pitch_y, int* pitch_c);
+int  lh264_sync(lh264_ctx* ctx);
+
+/* ---- kernel-level entry points (parity tests against the reference kernel tables) ---------- */
+/* n independent 4x4 blocks: pred/out u8[n][16], levels int16[n][16] already dequantised.
+ * = IdctResAddPred_c (decode_mb_aux.cpp:42-77).                                              */
+int  lh264_k_idct4x4_add(lh264_ctx* ctx, uint8_t* pix /*[n][16] in/out*/, const int16_t* coef, int n);
+/* = IdctResAddPred8x8_c (decode_mb_aux.cpp:79-167): pix u8[n][64], coef int16[n][64].       */
+int  lh264_k_idct8x8_add(lh264_ctx* ctx, uint8_t* pix, const int16_t* coef, int n);
+/* = McLuma_c (mc.cpp:334-346) on a w x h reference plane (border replicated by clamping);
+ * n blocks: x,y (integer position of the block), mvx,mvy (quarter-pel), bw,bh in
+ * int32[n][6]; out u8[n][256] (row stride 16).                                              */
+int  lh264_k_mc_luma(lh264_ctx* ctx, const uint8_t* ref, int w, int h, const int32_t* blocks, int n, uint8_t* out);
+/* = McChroma_c (mc.cpp:368-378); blocks as above in chroma samples with 1/8-pel mv.        */
+int  lh264_k_mc_chroma(lh264_ctx* ctx, const uint8_t* ref, int w, int h, const int32_t* blocks, int n, uint8_t* out);
+/* = ExpandPictureLuma_c/Chroma_c (expand_pic.cpp:37-115): in w x h, out (w+2p) x (h+2p).    */
+int  lh264_k_expand_plane(lh264_ctx* ctx, const uint8_t* in, int w, int h, int pad, uint8_t* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LH264_B200_H_ */

@@ -1,0 +1,182 @@
+"""numpy mirrors of the C-ABI records in include/lh264_b200.h and the .lhfb fixture container.
+
+The record layouts replace the reference's SDqLayer per-MB SoA hand-off
+(codec/decoder/core/inc/dec_frame.h:61-127).  `.lhfb` files are written by
+oracle/ref_dump_hook.cpp (test infrastructure) and by the host decoder's --dump mode; they hold
+one record per slice and are merged into pictures here.
+"""
+from __future__ import annotations
+
+import struct
+from dataclasses import dataclass, field
+
+import numpy as np
+
+MAX_REFS = 16
+
+MB_NONE, MB_I4x4, MB_I8x8, MB_I16x16, MB_IPCM, MB_P16x16, MB_P16x8, MB_P8x16, MB_P8x8, MB_PSKIP = range(10)
+MBF_TRANSFORM8x8 = 1
+
+MB_REC = np.dtype(
+    [
+        ("mb_type", "u1"),
+        ("flags", "u1"),
+        ("cbp", "u1"),
+        ("qp_y", "u1"),
+        ("qp_c", "u1", (2,)),
+        ("i16_mode", "u1"),
+        ("chroma_mode", "u1"),
+        ("slice_idx", "<u2"),
+        ("nxn_avail", "u1"),
+        ("reserved0", "u1"),
+        ("nz_mask", "<u4"),
+        ("coded_mask", "<u4"),
+        ("coef_off", "<u4"),
+        ("ref_idx", "i1", (4,)),
+        ("sub_mb_type", "u1", (4,)),
+        ("intra_mode", "u1", (16,)),
+        ("mv", "<i2", (16, 2)),
+        ("reserved1", "u1", (16,)),
+    ]
+)
+assert MB_REC.itemsize == 128
+
+SLICE_REC = np.dtype(
+    [
+        ("first_mb", "<i4"),
+        ("num_mbs", "<i4"),
+        ("slice_type", "u1"),
+        ("disable_deblocking_idc", "u1"),
+        ("alpha_c0_offset", "i1"),
+        ("beta_offset", "i1"),
+        ("num_ref_idx_l0", "u1"),
+        ("weighted_pred", "u1"),
+        ("luma_log2_denom", "u1"),
+        ("chroma_log2_denom", "u1"),
+        ("ref_slot", "<i2", (MAX_REFS,)),
+        ("luma_weight", "<i2", (MAX_REFS,)),
+        ("luma_offset", "<i2", (MAX_REFS,)),
+        ("chroma_weight", "<i2", (MAX_REFS, 2)),
+        ("chroma_offset", "<i2", (MAX_REFS, 2)),
+    ]
+)
+assert SLICE_REC.itemsize == 16 + 2 * MAX_REFS * 7
+
+
+@dataclass
+class Picture:
+    """All slices of one coded picture in hand-off form."""
+
+    mb_w: int
+    mb_h: int
+    cur_slot: int
+    frame_num: int = 0
+    poc_lsb: int = 0
+    idr_pic_id: int = 0
+    nal_ref_idc: int = 0
+    serial: int = 0
+    slices: np.ndarray = field(default_factory=lambda: np.zeros(0, SLICE_REC))
+    mbs: np.ndarray = field(default_factory=lambda: np.zeros(0, MB_REC))
+    coefs: np.ndarray = field(default_factory=lambda: np.zeros((0, 16), np.int16))
+    scaled: np.ndarray | None = None  # reference-dequantised coefficients (dump only)
+    pix_pre: list | None = None  # per slice: picture before that slice's deblocking
+    pix_post: list | None = None  # per slice: picture after it
+
+    @property
+    def n_mbs(self) -> int:
+        return self.mb_w * self.mb_h
+
+    def final_yuv(self) -> np.ndarray | None:
+        return self.pix_post[-1] if self.pix_post else None
+
+
+def _read(f, fmt):
+    size = struct.calcsize(fmt)
+    b = f.read(size)
+    if len(b) < size:
+        raise EOFError
+    return struct.unpack(fmt, b)
+
+
+def read_lhfb(path, max_pictures=None):
+    """Parses a .lhfb dump into a list of Picture (slices of one picture merged)."""
+    pics: list[Picture] = []
+    cur = None
+    cur_key = None
+    with open(path, "rb") as f:
+        while True:
+            try:
+                magic, ver = _read(f, "<II")
+            except EOFError:
+                break
+            if magic != 0x4246484C or ver != 1:
+                raise ValueError("bad lhfb record")
+            mb_w, mb_h, slot, frame_num, poc, idr_id, ref_idc, serial = _read(f, "<8i")
+            srec = np.frombuffer(f.read(SLICE_REC.itemsize), SLICE_REC, 1).copy()
+            (n_mbs,) = _read(f, "<i")
+            raw = np.frombuffer(f.read(n_mbs * (4 + MB_REC.itemsize)), np.dtype([("xy", "<i4"), ("rec", MB_REC)]), n_mbs)
+            (n_blk,) = _read(f, "<i")
+            quant = np.frombuffer(f.read(n_blk * 32), "<i2").reshape(n_blk, 16).copy()
+            scaled = np.frombuffer(f.read(n_blk * 32), "<i2").reshape(n_blk, 16).copy()
+            (has_pix,) = _read(f, "<i")
+            pre = post = None
+            if has_pix:
+                sz = mb_w * mb_h * 384
+                pre = np.frombuffer(f.read(sz), np.uint8).copy()
+                post = np.frombuffer(f.read(sz), np.uint8).copy()
+            key = (serial, slot, frame_num, poc, idr_id, mb_w, mb_h)
+            if cur is None or key != cur_key:
+                if max_pictures is not None and len(pics) >= max_pictures:
+                    break
+                cur = Picture(mb_w, mb_h, slot, frame_num, poc, idr_id, ref_idc, serial)
+                cur.mbs = np.zeros(mb_w * mb_h, MB_REC)
+                cur.scaled = np.zeros((0, 16), np.int16)
+                cur.pix_pre, cur.pix_post = [], []
+                cur_key = key
+                pics.append(cur)
+            sidx = len(cur.slices)
+            cur.slices = np.concatenate([cur.slices, srec])
+            base = len(cur.coefs)
+            recs = raw["rec"].copy()
+            recs["slice_idx"] = sidx
+            recs["coef_off"] += base
+            cur.mbs[raw["xy"]] = recs
+            cur.coefs = np.concatenate([cur.coefs, quant])
+            cur.scaled = np.concatenate([cur.scaled, scaled])
+            if has_pix:
+                cur.pix_pre.append(pre)
+                cur.pix_post.append(post)
+    return pics
+
+
+def write_lhfb(path, pics, with_pix=True):
+    """Writes pictures back as one record per slice (used to trim fixtures)."""
+    with open(path, "wb") as f:
+        for p in pics:
+            for s in range(len(p.slices)):
+                sl = p.slices[s]
+                f.write(struct.pack("<II", 0x4246484C, 1))
+                f.write(struct.pack("<8i", p.mb_w, p.mb_h, p.cur_slot, p.frame_num, p.poc_lsb, p.idr_pic_id, p.nal_ref_idc, p.serial))
+                f.write(sl.tobytes())
+                xy = np.nonzero((p.mbs["slice_idx"] == s) & (np.arange(p.n_mbs) >= sl["first_mb"]) & (np.arange(p.n_mbs) < sl["first_mb"] + sl["num_mbs"]))[0]
+                recs = p.mbs[xy].copy()
+                nblk = np.array([bin(int(m)).count("1") for m in recs["coded_mask"]], np.int64)
+                lo = int(recs["coef_off"][0]) if len(recs) else 0
+                hi = int(recs["coef_off"][-1] + nblk[-1]) if len(recs) else 0
+                recs["coef_off"] -= lo
+                recs["slice_idx"] = 0
+                f.write(struct.pack("<i", len(xy)))
+                out = np.zeros(len(xy), np.dtype([("xy", "<i4"), ("rec", MB_REC)]))
+                out["xy"] = xy
+                out["rec"] = recs
+                f.write(out.tobytes())
+                f.write(struct.pack("<i", hi - lo))
+                f.write(p.coefs[lo:hi].tobytes())
+                sc = p.scaled[lo:hi] if p.scaled is not None and len(p.scaled) >= hi else np.zeros((hi - lo, 16), np.int16)
+                f.write(sc.tobytes())
+                if with_pix and p.pix_post:
+                    f.write(struct.pack("<i", 1))
+                    f.write(p.pix_pre[s].tobytes())
+                    f.write(p.pix_post[s].tobytes())
+                else:
+                    f.write(struct.pack("<i", 0))
