@@ -103,7 +103,7 @@ typedef struct lh264_mb_rec {
   uint8_t  i16_mode;          /* LH264_I16_* (pIntraPredMode[7])                             */
   uint8_t  chroma_mode;       /* LH264_C_*   (pChromaPredMode)                               */
   uint16_t slice_idx;         /* index into the picture's slice table (pSliceIdc)            */
-  uint8_t  nxn_avail;         /* I8x8 neighbour flags, bit0 top, bit1 left, bit2 top-left,
+  uint8_t  nxn_avail;         /* I8x8 neighbour flags, bit0 top, bit1 top-left, bit2 left,
                                  bit3 top-right  (pIntraNxNAvailFlag, rec_mb.cpp:88-97)      */
   uint8_t  reserved0;
   uint32_t nz_mask;           /* bit r (r<16): luma 4x4 block r has non-zero count (pNzc);
@@ -211,6 +211,15 @@ int  lh264_picture_write(lh264_ctx* ctx, int stream, int slot,
 int  lh264_picture_device_ptrs(lh264_ctx* ctx, int stream, int slot,
                                void** y, void** u, void** v, int* pitch_y, int* pitch_c);
 int  lh264_sync(lh264_ctx* ctx);
+/* Gathers the cropped I420 pictures of n (stream, slot) pairs on the device and brings them to
+ * the host with ONE copy: for each picture Y (width x height) then U, V ((w+1)/2 x (h+1)/2),
+ * tightly packed, pictures back to back.  dst should be pinned (lh264_host_alloc).           */
+int  lh264_pictures_read_packed(lh264_ctx* ctx, const int* streams, const int* slots, int n,
+                                int crop_x, int crop_y, int width, int height,
+                                uint8_t* dst, size_t dst_bytes, int sync);
+/* Pinned host memory for hand-off records and output pictures (async copies need it).       */
+void* lh264_host_alloc(size_t bytes);
+void  lh264_host_free(void* p);
 
 /* ---- kernel-level entry points (parity tests against the reference kernel tables) ---------- */
 /* n independent 4x4 blocks: pred/out u8[n][16], levels int16[n][16] already dequantised.

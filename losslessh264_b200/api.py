@@ -1,0 +1,228 @@
+"""ctypes host layer over the C ABI (include/lh264_b200.h).
+
+Mirrors the reference's decoder-side operator interface for the hot path: a `Context` owns a
+CUDA stream, `open_stream` allocates the picture pool of one decoder instance (the reference's
+PPicture pool, pic_queue.cpp:60-107), `recon` runs what WelsTargetSliceConstruction
+(decode_slice.cpp:110-206) does for every picture of a batch.  No CPU fallback: if the CUDA
+library or a device is missing this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+from .build import library_path
+from .records import MB_REC, SLICE_REC, Picture
+
+_LIB = None
+
+EXPORTS = [
+    "lh264_abi_version", "lh264_last_error", "lh264_ctx_create", "lh264_ctx_destroy",
+    "lh264_stream_open", "lh264_stream_close", "lh264_recon_submit", "lh264_batch_upload",
+    "lh264_batch_recon", "lh264_batch_free", "lh264_kernel_launches", "lh264_kernel_ms",
+    "lh264_picture_read", "lh264_picture_write", "lh264_picture_device_ptrs", "lh264_sync",
+    "lh264_pictures_read_packed", "lh264_host_alloc", "lh264_host_free",
+    "lh264_k_idct4x4_add", "lh264_k_idct8x8_add", "lh264_k_mc_luma", "lh264_k_mc_chroma",
+    "lh264_k_expand_plane",
+]
+
+
+class PictureDesc(C.Structure):
+    _fields_ = [
+        ("stream", C.c_int32),
+        ("cur_slot", C.c_int32),
+        ("n_slices", C.c_int32),
+        ("n_coef_blocks", C.c_int32),
+        ("slices", C.c_void_p),
+        ("mbs", C.c_void_p),
+        ("coefs", C.c_void_p),
+    ]
+
+
+class LibraryMissing(RuntimeError):
+    pass
+
+
+def load_library():
+    """Loads liblh264_b200.so (built in-tree by losslessh264_b200.build).  Never falls back."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise LibraryMissing(f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)")
+    lib = C.CDLL(path)
+    lib.lh264_last_error.restype = C.c_char_p
+    lib.lh264_kernel_launches.restype = C.c_uint64
+    lib.lh264_kernel_ms.restype = C.c_float
+    lib.lh264_host_alloc.restype = C.c_void_p
+    lib.lh264_host_alloc.argtypes = [C.c_size_t]
+    lib.lh264_host_free.argtypes = [C.c_void_p]
+    lib.lh264_ctx_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_void_p]
+    lib.lh264_ctx_destroy.argtypes = [C.c_void_p]
+    lib.lh264_stream_open.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int]
+    lib.lh264_stream_close.argtypes = [C.c_void_p, C.c_int]
+    lib.lh264_recon_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.lh264_batch_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    lib.lh264_batch_recon.argtypes = [C.c_void_p, C.c_void_p]
+    lib.lh264_batch_free.argtypes = [C.c_void_p, C.c_void_p]
+    lib.lh264_kernel_launches.argtypes = [C.c_void_p]
+    lib.lh264_kernel_ms.argtypes = [C.c_void_p, C.c_int]
+    lib.lh264_sync.argtypes = [C.c_void_p]
+    lib.lh264_picture_read.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+    lib.lh264_picture_write.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    lib.lh264_pictures_read_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
+    lib.lh264_k_idct4x4_add.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    lib.lh264_k_idct8x8_add.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    lib.lh264_k_mc_luma.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    lib.lh264_k_mc_chroma.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    lib.lh264_k_expand_plane.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    _LIB = lib
+    return lib
+
+
+class Lh264Error(RuntimeError):
+    pass
+
+
+def _check(lib, rc):
+    if rc < 0:
+        raise Lh264Error(f"lh264 error {rc}: {lib.lh264_last_error().decode()}")
+    return rc
+
+
+class PinnedArray:
+    """numpy view over pinned host memory from lh264_host_alloc."""
+
+    def __init__(self, nbytes):
+        self.lib = load_library()
+        self.ptr = self.lib.lh264_host_alloc(nbytes)
+        if not self.ptr:
+            raise MemoryError("lh264_host_alloc failed")
+        self.nbytes = nbytes
+        self.array = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(self.ptr))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self.lib.lh264_host_free(self.ptr)
+            self.ptr = None
+
+
+class Context:
+    def __init__(self, device=0, cuda_stream=None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        _check(self.lib, self.lib.lh264_ctx_create(C.byref(h), device, cuda_stream))
+        self.h = h
+        self._keep = []
+
+    def close(self):
+        if self.h:
+            self.lib.lh264_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- streams / pictures -------------------------------------------------------------------
+    def open_stream(self, mb_w, mb_h, n_slots):
+        return _check(self.lib, self.lib.lh264_stream_open(self.h, mb_w, mb_h, n_slots))
+
+    def close_stream(self, s):
+        _check(self.lib, self.lib.lh264_stream_close(self.h, s))
+
+    def _descs(self, pics, streams):
+        arr = (PictureDesc * len(pics))()
+        keep = []
+        for i, (p, s) in enumerate(zip(pics, streams)):
+            slices = np.ascontiguousarray(p.slices, SLICE_REC)
+            mbs = np.ascontiguousarray(p.mbs, MB_REC)
+            coefs = np.ascontiguousarray(p.coefs, np.int16)
+            keep += [slices, mbs, coefs]
+            arr[i] = PictureDesc(s, p.cur_slot, len(slices), len(coefs), slices.ctypes.data, mbs.ctypes.data, coefs.ctypes.data if len(coefs) else None)
+        return arr, keep
+
+    def recon(self, pics, streams, sync=True):
+        """Reconstructs `pics` (records.Picture) into their streams' cur_slot.  Host buffers in."""
+        arr, keep = self._descs(pics, streams)
+        self._keep = keep
+        _check(self.lib, self.lib.lh264_recon_submit(self.h, arr, len(pics)))
+        if sync:
+            self.sync()
+
+    def upload_batch(self, pics, streams):
+        arr, keep = self._descs(pics, streams)
+        h = C.c_void_p()
+        _check(self.lib, self.lib.lh264_batch_upload(self.h, arr, len(pics), C.byref(h)))
+        return h
+
+    def recon_resident(self, batch):
+        _check(self.lib, self.lib.lh264_batch_recon(self.h, batch))
+
+    def free_batch(self, batch):
+        self.lib.lh264_batch_free(self.h, batch)
+
+    def sync(self):
+        _check(self.lib, self.lib.lh264_sync(self.h))
+        self._keep = []
+
+    def read_picture(self, stream, slot, mb_w, mb_h, crop=None):
+        """Returns the (cropped) I420 picture as a flat uint8 array Y|U|V."""
+        x, y, w, h = crop if crop else (0, 0, mb_w * 16, mb_h * 16)
+        cw, ch = (w + 1) // 2, (h + 1) // 2
+        out = np.empty(w * h + 2 * cw * ch, np.uint8)
+        base = out.ctypes.data
+        _check(self.lib, self.lib.lh264_picture_read(self.h, stream, slot, x, y, w, h, base, w, base + w * h, base + w * h + cw * ch, cw, 1))
+        return out
+
+    def write_picture(self, stream, slot, mb_w, mb_h, yuv):
+        yuv = np.ascontiguousarray(yuv, np.uint8)
+        w, h = mb_w * 16, mb_h * 16
+        base = yuv.ctypes.data
+        _check(self.lib, self.lib.lh264_picture_write(self.h, stream, slot, base, w, base + w * h, base + w * h + w * h // 4, w // 2))
+
+    def read_packed(self, streams, slots, crop, dst: "PinnedArray"):
+        s = np.ascontiguousarray(streams, np.int32)
+        sl = np.ascontiguousarray(slots, np.int32)
+        x, y, w, h = crop
+        _check(self.lib, self.lib.lh264_pictures_read_packed(self.h, s.ctypes.data, sl.ctypes.data, len(s), x, y, w, h, dst.ptr, dst.nbytes, 1))
+
+    def kernel_launches(self):
+        return int(self.lib.lh264_kernel_launches(self.h))
+
+    def kernel_ms(self, family):
+        return float(self.lib.lh264_kernel_ms(self.h, family))
+
+    # ---- kernel-level entry points ---------------------------------------------------------------
+    def k_idct4x4_add(self, pix, coef):
+        pix = np.ascontiguousarray(pix, np.uint8).copy()
+        coef = np.ascontiguousarray(coef, np.int16)
+        _check(self.lib, self.lib.lh264_k_idct4x4_add(self.h, pix.ctypes.data, coef.ctypes.data, len(pix)))
+        return pix
+
+    def k_idct8x8_add(self, pix, coef):
+        pix = np.ascontiguousarray(pix, np.uint8).copy()
+        coef = np.ascontiguousarray(coef, np.int16)
+        _check(self.lib, self.lib.lh264_k_idct8x8_add(self.h, pix.ctypes.data, coef.ctypes.data, len(pix)))
+        return pix
+
+    def k_mc(self, ref, blocks, luma=True):
+        ref = np.ascontiguousarray(ref, np.uint8)
+        blocks = np.ascontiguousarray(blocks, np.int32)
+        out = np.zeros((len(blocks), 16, 16), np.uint8)
+        f = self.lib.lh264_k_mc_luma if luma else self.lib.lh264_k_mc_chroma
+        _check(self.lib, f(self.h, ref.ctypes.data, ref.shape[1], ref.shape[0], blocks.ctypes.data, len(blocks), out.ctypes.data))
+        return out
+
+    def k_expand_plane(self, plane, pad):
+        plane = np.ascontiguousarray(plane, np.uint8)
+        h, w = plane.shape
+        out = np.zeros((h + 2 * pad, w + 2 * pad), np.uint8)
+        _check(self.lib, self.lib.lh264_k_expand_plane(self.h, plane.ctypes.data, w, h, pad, out.ctypes.data))
+        return out

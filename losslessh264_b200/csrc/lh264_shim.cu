@@ -1,0 +1,436 @@
+// lh264_shim.cu — the C-ABI of include/lh264_b200.h over the sm_100a kernels.
+//
+// Host side of the hot-path boundary: owns the per-stream picture pools in HBM (the reference's
+// PPicture pool, codec/decoder/core/src/pic_queue.cpp:60-107), stages a batch of hand-off records
+// (SDqLayer, dec_frame.h:61-127) into HBM and issues the reconstruction launches that replace
+// WelsTargetSliceConstruction (decode_slice.cpp:110-206) for every picture of the batch.
+// There is no CPU fallback in this file: without a CUDA device every entry point fails.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdarg.h>
+#include <vector>
+#include <algorithm>
+#include <new>
+
+#include "recon_kernels.cuh"
+
+using namespace lh264;
+
+static thread_local char g_err[512] = "";
+static int fail (int code, const char* fmt, ...) {
+  va_list ap; va_start (ap, fmt); vsnprintf (g_err, sizeof (g_err), fmt, ap); va_end (ap);
+  return code;
+}
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) return fail (LH264_E_CUDA, "%s: %s (%s:%d)", #call, cudaGetErrorString (e_), __FILE__, __LINE__); } while (0)
+
+namespace {
+
+struct StreamRec {
+  bool open = false;
+  int mb_w = 0, mb_h = 0, n_slots = 0;
+  uint8_t* base = nullptr;
+  size_t slot_stride = 0;
+};
+
+template <typename T> struct DevBuf {       // grow-only device buffer
+  T* p = nullptr; size_t cap = 0;
+  cudaError_t reserve (size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFree (p);
+    p = nullptr; cap = 0;
+    size_t want = std::max (n, (size_t)1024);
+    want += want / 4;
+    cudaError_t e = cudaMalloc (&p, want * sizeof (T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFree (p); p = nullptr; cap = 0; }
+};
+template <typename T> struct PinBuf {       // grow-only pinned host buffer
+  T* p = nullptr; size_t cap = 0;
+  cudaError_t reserve (size_t n) {
+    if (n <= cap) return cudaSuccess;
+    if (p) cudaFreeHost (p);
+    p = nullptr; cap = 0;
+    size_t want = std::max (n, (size_t)256);
+    want += want / 4;
+    cudaError_t e = cudaMallocHost (&p, want * sizeof (T));
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() { if (p) cudaFreeHost (p); p = nullptr; cap = 0; }
+};
+
+struct BatchDev {                            // device-resident batch
+  DevBuf<lh264_mb_rec> mbs;
+  DevBuf<int16_t> coefs;
+  DevBuf<lh264_slice_rec> slices;
+  DevBuf<PicDev> pics;
+  DevBuf<int> intra_ids;
+  int n_pics = 0, n_intra_pics = 0;
+  int max_mbs = 0, max_diag = 0, n_waves = 0;
+  void release() { mbs.release(); coefs.release(); slices.release(); pics.release(); intra_ids.release(); }
+};
+
+} // namespace
+
+struct lh264_resident_batch { BatchDev dev; };
+
+struct lh264_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::vector<StreamRec> streams;
+  BatchDev batch;                            // staging for lh264_recon_submit
+  PinBuf<PicDev> h_pics;
+  PinBuf<int> h_intra_ids;
+  cudaEvent_t staged = nullptr;              // h_pics/h_intra_ids consumed by the H2D copy
+  bool staged_pending = false;
+  DevBuf<PackDev> pack_jobs; PinBuf<PackDev> h_pack_jobs; DevBuf<uint8_t> pack_out;
+  DevBuf<uint8_t> scratch_a, scratch_b, scratch_c;
+  uint64_t launches = 0;
+  // per-family device timing
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float ms[3] = {0, 0, 0};
+  bool timing = false;
+};
+
+extern "C" {
+
+int lh264_abi_version (void) { return LH264_ABI_VERSION; }
+const char* lh264_last_error (void) { return g_err; }
+
+int lh264_ctx_create (lh264_ctx** out, int device, void* cuda_stream) {
+  if (!out) return fail (LH264_E_INVALID, "null out");
+  *out = nullptr;
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount (&n);
+  if (e != cudaSuccess || n <= 0) return fail (LH264_E_NO_DEVICE, "no CUDA device (%s); this library has no CPU fallback", cudaGetErrorString (e));
+  if (device < 0 || device >= n) return fail (LH264_E_INVALID, "device %d out of range (%d devices)", device, n);
+  CK (cudaSetDevice (device));
+  lh264_ctx* c = new (std::nothrow) lh264_ctx();
+  if (!c) return fail (LH264_E_NOMEM, "out of host memory");
+  c->device = device;
+  if (cuda_stream) c->stream = (cudaStream_t)cuda_stream;
+  else { CK (cudaStreamCreateWithFlags (&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
+  CK (cudaEventCreateWithFlags (&c->staged, cudaEventDisableTiming));
+  for (int i = 0; i < 4; i++) CK (cudaEventCreate (&c->ev[i]));
+  *out = c;
+  return LH264_OK;
+}
+
+void lh264_ctx_destroy (lh264_ctx* c) {
+  if (!c) return;
+  cudaSetDevice (c->device);
+  cudaStreamSynchronize (c->stream);
+  for (auto& s : c->streams) if (s.base) cudaFree (s.base);
+  c->batch.release(); c->h_pics.release(); c->h_intra_ids.release();
+  c->pack_jobs.release(); c->h_pack_jobs.release(); c->pack_out.release();
+  c->scratch_a.release(); c->scratch_b.release(); c->scratch_c.release();
+  if (c->staged) cudaEventDestroy (c->staged);
+  for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy (c->ev[i]);
+  if (c->own_stream) cudaStreamDestroy (c->stream);
+  delete c;
+}
+
+int lh264_stream_open (lh264_ctx* c, int mb_w, int mb_h, int n_slots) {
+  if (!c || mb_w <= 0 || mb_h <= 0 || n_slots <= 0 || n_slots > 64) return fail (LH264_E_INVALID, "bad stream geometry");
+  CK (cudaSetDevice (c->device));
+  StreamRec s;
+  s.open = true; s.mb_w = mb_w; s.mb_h = mb_h; s.n_slots = n_slots;
+  s.slot_stride = (size_t)mb_w * mb_h * 384;
+  CK (cudaMalloc (&s.base, s.slot_stride * n_slots));
+  CK (cudaMemsetAsync (s.base, 128, s.slot_stride * n_slots, c->stream));   // pic_queue.cpp:96
+  for (size_t i = 0; i < c->streams.size(); i++) if (!c->streams[i].open) { c->streams[i] = s; return (int)i; }
+  c->streams.push_back (s);
+  return (int)c->streams.size() - 1;
+}
+
+int lh264_stream_close (lh264_ctx* c, int stream) {
+  if (!c || stream < 0 || stream >= (int)c->streams.size() || !c->streams[stream].open) return fail (LH264_E_INVALID, "bad stream");
+  CK (cudaStreamSynchronize (c->stream));
+  cudaFree (c->streams[stream].base);
+  c->streams[stream] = StreamRec();
+  return LH264_OK;
+}
+
+static int check_pic (lh264_ctx* c, const lh264_picture_desc& p) {
+  if (p.stream < 0 || p.stream >= (int)c->streams.size() || !c->streams[p.stream].open) return fail (LH264_E_INVALID, "picture names a closed stream");
+  const StreamRec& s = c->streams[p.stream];
+  if (p.cur_slot < 0 || p.cur_slot >= s.n_slots) return fail (LH264_E_INVALID, "cur_slot out of range");
+  if (p.n_slices <= 0 || !p.slices || !p.mbs || (p.n_coef_blocks > 0 && !p.coefs) || p.n_coef_blocks < 0) return fail (LH264_E_INVALID, "malformed picture_desc");
+  return LH264_OK;
+}
+
+// Copies the records of a batch into HBM (async) and fills the device picture table.
+static int stage_batch (lh264_ctx* c, BatchDev& b, PinBuf<PicDev>& h_pics, PinBuf<int>& h_ids, const lh264_picture_desc* pics, int n) {
+  size_t tot_mbs = 0, tot_blk = 0, tot_sl = 0;
+  for (int i = 0; i < n; i++) {
+    int rc = check_pic (c, pics[i]);
+    if (rc) return rc;
+    const StreamRec& s = c->streams[pics[i].stream];
+    tot_mbs += (size_t)s.mb_w * s.mb_h; tot_blk += pics[i].n_coef_blocks; tot_sl += pics[i].n_slices;
+  }
+  CK (b.mbs.reserve (tot_mbs)); CK (b.coefs.reserve (tot_blk * 16 + 16)); CK (b.slices.reserve (tot_sl));
+  CK (b.pics.reserve (n)); CK (b.intra_ids.reserve (n));
+  if (c->staged_pending) { CK (cudaEventSynchronize (c->staged)); c->staged_pending = false; }
+  CK (h_pics.reserve (n)); CK (h_ids.reserve (n));
+  size_t o_mb = 0, o_blk = 0, o_sl = 0;
+  b.n_pics = n; b.n_intra_pics = 0; b.max_mbs = 0; b.max_diag = 0; b.n_waves = 0;
+  for (int i = 0; i < n; i++) {
+    const lh264_picture_desc& p = pics[i];
+    const StreamRec& s = c->streams[p.stream];
+    const size_t nmb = (size_t)s.mb_w * s.mb_h;
+    CK (cudaMemcpyAsync (b.mbs.p + o_mb, p.mbs, nmb * sizeof (lh264_mb_rec), cudaMemcpyHostToDevice, c->stream));
+    if (p.n_coef_blocks) CK (cudaMemcpyAsync (b.coefs.p + o_blk * 16, p.coefs, (size_t)p.n_coef_blocks * 32, cudaMemcpyHostToDevice, c->stream));
+    CK (cudaMemcpyAsync (b.slices.p + o_sl, p.slices, (size_t)p.n_slices * sizeof (lh264_slice_rec), cudaMemcpyHostToDevice, c->stream));
+    PicDev& d = h_pics.p[i];
+    d.mbs = b.mbs.p + o_mb; d.coefs = b.coefs.p + o_blk * 16; d.slices = b.slices.p + o_sl;
+    d.base = s.base; d.slot_stride = s.slot_stride; d.cur_slot = p.cur_slot; d.n_slots = s.n_slots; d.mb_w = s.mb_w; d.mb_h = s.mb_h;
+    // pictures whose every slice is P may still hold intra MBs; a picture takes part in the intra
+    // wavefront unless the producer marks all its slices as "no intra MB" (slice_type 0 and n_intra==0
+    // cannot be told from the records cheaply), so only I/P mix is decided here: always include.
+    h_ids.p[b.n_intra_pics++] = i;
+    b.max_mbs = std::max (b.max_mbs, (int)nmb);
+    b.max_diag = std::max (b.max_diag, std::min (s.mb_h, (s.mb_w + 1) / 2 + 1));
+    b.n_waves = std::max (b.n_waves, (s.mb_w - 1) + 2 * (s.mb_h - 1) + 1);
+    o_mb += nmb; o_blk += p.n_coef_blocks; o_sl += p.n_slices;
+  }
+  CK (cudaMemcpyAsync (b.pics.p, h_pics.p, n * sizeof (PicDev), cudaMemcpyHostToDevice, c->stream));
+  CK (cudaMemcpyAsync (b.intra_ids.p, h_ids.p, b.n_intra_pics * sizeof (int), cudaMemcpyHostToDevice, c->stream));
+  CK (cudaEventRecord (c->staged, c->stream));
+  c->staged_pending = true;
+  return LH264_OK;
+}
+
+static int launch_recon (lh264_ctx* c, BatchDev& b) {
+  if (b.n_pics == 0) return LH264_OK;
+  if (c->timing) CK (cudaEventRecord (c->ev[0], c->stream));
+  k_inter<<<dim3 (b.max_mbs, b.n_pics), 128, 0, c->stream>>> (b.pics.p);
+  c->launches++;
+  if (c->timing) CK (cudaEventRecord (c->ev[1], c->stream));
+  for (int w = 0; w < b.n_waves && b.n_intra_pics; w++) {
+    k_intra<<<dim3 (b.max_diag, b.n_intra_pics), 128, 0, c->stream>>> (b.pics.p, b.intra_ids.p, w);
+    c->launches++;
+  }
+  if (c->timing) CK (cudaEventRecord (c->ev[2], c->stream));
+  for (int w = 0; w < b.n_waves; w++) {
+    k_deblock<<<dim3 ((b.max_diag + 3) / 4, b.n_pics), 128, 0, c->stream>>> (b.pics.p, w);
+    c->launches++;
+  }
+  if (c->timing) {
+    CK (cudaEventRecord (c->ev[3], c->stream));
+    CK (cudaEventSynchronize (c->ev[3]));
+    for (int i = 0; i < 3; i++) { float t = 0; cudaEventElapsedTime (&t, c->ev[i], c->ev[i + 1]); c->ms[i] += t; }
+  }
+  CK (cudaGetLastError());
+  return LH264_OK;
+}
+
+int lh264_recon_submit (lh264_ctx* c, const lh264_picture_desc* pics, int n_pics) {
+  if (!c || (n_pics > 0 && !pics) || n_pics < 0) return fail (LH264_E_INVALID, "bad arguments");
+  CK (cudaSetDevice (c->device));
+  for (int i = 0; i < n_pics; i++) for (int j = i + 1; j < n_pics; j++)
+      if (n_pics <= 64 && pics[i].stream == pics[j].stream) return fail (LH264_E_INVALID, "two pictures of one stream in a batch");
+  int rc = stage_batch (c, c->batch, c->h_pics, c->h_intra_ids, pics, n_pics);
+  if (rc) return rc;
+  return launch_recon (c, c->batch);
+}
+
+int lh264_batch_upload (lh264_ctx* c, const lh264_picture_desc* pics, int n_pics, lh264_resident_batch** out) {
+  if (!c || !pics || n_pics <= 0 || !out) return fail (LH264_E_INVALID, "bad arguments");
+  CK (cudaSetDevice (c->device));
+  lh264_resident_batch* rb = new (std::nothrow) lh264_resident_batch();
+  if (!rb) return fail (LH264_E_NOMEM, "out of host memory");
+  int rc = stage_batch (c, rb->dev, c->h_pics, c->h_intra_ids, pics, n_pics);
+  if (rc) { rb->dev.release(); delete rb; return rc; }
+  CK (cudaStreamSynchronize (c->stream));
+  c->staged_pending = false;
+  *out = rb;
+  return LH264_OK;
+}
+int lh264_batch_recon (lh264_ctx* c, lh264_resident_batch* b) {
+  if (!c || !b) return fail (LH264_E_INVALID, "bad arguments");
+  CK (cudaSetDevice (c->device));
+  return launch_recon (c, b->dev);
+}
+void lh264_batch_free (lh264_ctx* c, lh264_resident_batch* b) {
+  if (!b) return;
+  if (c) { cudaSetDevice (c->device); cudaStreamSynchronize (c->stream); }
+  b->dev.release();
+  delete b;
+}
+
+uint64_t lh264_kernel_launches (const lh264_ctx* c) { return c ? c->launches : 0; }
+float lh264_kernel_ms (lh264_ctx* c, int family) {
+  if (!c) return 0.f;
+  if (family < 0) { c->ms[0] = c->ms[1] = c->ms[2] = 0.f; c->timing = true; return 0.f; }
+  if (family < 3) return c->ms[family];
+  return c->ms[0] + c->ms[1] + c->ms[2];
+}
+
+static int plane_geom (lh264_ctx* c, int stream, int slot, const StreamRec** sp) {
+  if (!c || stream < 0 || stream >= (int)c->streams.size() || !c->streams[stream].open) return fail (LH264_E_INVALID, "bad stream");
+  if (slot < 0 || slot >= c->streams[stream].n_slots) return fail (LH264_E_INVALID, "bad slot");
+  *sp = &c->streams[stream];
+  return LH264_OK;
+}
+
+int lh264_picture_read (lh264_ctx* c, int stream, int slot, int crop_x, int crop_y, int width, int height,
+                        uint8_t* dst_y, int stride_y, uint8_t* dst_u, uint8_t* dst_v, int stride_c, int sync) {
+  const StreamRec* s;
+  int rc = plane_geom (c, stream, slot, &s);
+  if (rc) return rc;
+  const int W = s->mb_w * 16, H = s->mb_h * 16;
+  if (crop_x < 0 || crop_y < 0 || width <= 0 || height <= 0 || crop_x + width > W || crop_y + height > H || (crop_x & 1) || (crop_y & 1))
+    return fail (LH264_E_INVALID, "bad crop window");
+  CK (cudaSetDevice (c->device));
+  const uint8_t* y = s->base + (size_t)slot * s->slot_stride;
+  const uint8_t* u = y + (size_t)W * H;
+  const uint8_t* v = u + (size_t)W * H / 4;
+  const int cw = (width + 1) >> 1, ch = (height + 1) >> 1;
+  CK (cudaMemcpy2DAsync (dst_y, stride_y, y + (size_t)crop_y * W + crop_x, W, width, height, cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaMemcpy2DAsync (dst_u, stride_c, u + (size_t) (crop_y >> 1) * (W >> 1) + (crop_x >> 1), W >> 1, cw, ch, cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaMemcpy2DAsync (dst_v, stride_c, v + (size_t) (crop_y >> 1) * (W >> 1) + (crop_x >> 1), W >> 1, cw, ch, cudaMemcpyDeviceToHost, c->stream));
+  if (sync) CK (cudaStreamSynchronize (c->stream));
+  return LH264_OK;
+}
+
+int lh264_picture_write (lh264_ctx* c, int stream, int slot, const uint8_t* src_y, int stride_y,
+                         const uint8_t* src_u, const uint8_t* src_v, int stride_c) {
+  const StreamRec* s;
+  int rc = plane_geom (c, stream, slot, &s);
+  if (rc) return rc;
+  const int W = s->mb_w * 16, H = s->mb_h * 16;
+  CK (cudaSetDevice (c->device));
+  uint8_t* y = s->base + (size_t)slot * s->slot_stride;
+  uint8_t* u = y + (size_t)W * H;
+  uint8_t* v = u + (size_t)W * H / 4;
+  CK (cudaMemcpy2DAsync (y, W, src_y, stride_y, W, H, cudaMemcpyHostToDevice, c->stream));
+  CK (cudaMemcpy2DAsync (u, W >> 1, src_u, stride_c, W >> 1, H >> 1, cudaMemcpyHostToDevice, c->stream));
+  CK (cudaMemcpy2DAsync (v, W >> 1, src_v, stride_c, W >> 1, H >> 1, cudaMemcpyHostToDevice, c->stream));
+  CK (cudaStreamSynchronize (c->stream));
+  return LH264_OK;
+}
+
+int lh264_picture_device_ptrs (lh264_ctx* c, int stream, int slot, void** y, void** u, void** v, int* pitch_y, int* pitch_c) {
+  const StreamRec* s;
+  int rc = plane_geom (c, stream, slot, &s);
+  if (rc) return rc;
+  const int W = s->mb_w * 16, H = s->mb_h * 16;
+  uint8_t* py = s->base + (size_t)slot * s->slot_stride;
+  if (y) *y = py;
+  if (u) *u = py + (size_t)W * H;
+  if (v) *v = py + (size_t)W * H + (size_t)W * H / 4;
+  if (pitch_y) *pitch_y = W;
+  if (pitch_c) *pitch_c = W >> 1;
+  return LH264_OK;
+}
+
+// Gathers the cropped I420 pictures of n (stream, slot) pairs into one pinned host buffer with a
+// single D2H copy: dst layout = for each picture Y (width x height), U, V ((w+1)/2 x (h+1)/2).
+int lh264_pictures_read_packed (lh264_ctx* c, const int* streams, const int* slots, int n, int crop_x, int crop_y,
+                                int width, int height, uint8_t* dst, size_t dst_bytes, int sync) {
+  if (!c || !streams || !slots || n <= 0 || !dst) return fail (LH264_E_INVALID, "bad arguments");
+  CK (cudaSetDevice (c->device));
+  const int cw = (width + 1) >> 1, ch = (height + 1) >> 1;
+  const size_t per = (size_t)width * height + 2 * (size_t)cw * ch;
+  if (dst_bytes < per * n) return fail (LH264_E_INVALID, "destination too small");
+  CK (c->pack_jobs.reserve (3 * n)); CK (c->h_pack_jobs.reserve (3 * n)); CK (c->pack_out.reserve (per * n));
+  for (int i = 0; i < n; i++) {
+    const StreamRec* s;
+    int rc = plane_geom (c, streams[i], slots[i], &s);
+    if (rc) return rc;
+    const int W = s->mb_w * 16, H = s->mb_h * 16;
+    if (crop_x < 0 || crop_y < 0 || crop_x + width > W || crop_y + height > H || (crop_x & 1) || (crop_y & 1)) return fail (LH264_E_INVALID, "bad crop window");
+    const uint8_t* y = s->base + (size_t)slots[i] * s->slot_stride;
+    const uint8_t* u = y + (size_t)W * H;
+    const uint8_t* v = u + (size_t)W * H / 4;
+    PackDev* j = c->h_pack_jobs.p + 3 * i;
+    j[0] = PackDev{ y + (size_t)crop_y * W + crop_x, W, width, height, per * i };
+    j[1] = PackDev{ u + (size_t) (crop_y >> 1) * (W >> 1) + (crop_x >> 1), W >> 1, cw, ch, per * i + (size_t)width * height };
+    j[2] = PackDev{ v + (size_t) (crop_y >> 1) * (W >> 1) + (crop_x >> 1), W >> 1, cw, ch, per * i + (size_t)width * height + (size_t)cw * ch };
+  }
+  CK (cudaMemcpyAsync (c->pack_jobs.p, c->h_pack_jobs.p, 3 * n * sizeof (PackDev), cudaMemcpyHostToDevice, c->stream));
+  k_pack<<<dim3 (std::min (height, 64), 3 * n), 128, 0, c->stream>>> (c->pack_jobs.p, c->pack_out.p);
+  c->launches++;
+  CK (cudaMemcpyAsync (dst, c->pack_out.p, per * n, cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaStreamSynchronize (c->stream));     // h_pack_jobs is reused by the next call
+  (void)sync;
+  return LH264_OK;
+}
+
+int lh264_sync (lh264_ctx* c) {
+  if (!c) return fail (LH264_E_INVALID, "null ctx");
+  CK (cudaSetDevice (c->device));
+  CK (cudaStreamSynchronize (c->stream));
+  c->staged_pending = false;
+  return LH264_OK;
+}
+
+void* lh264_host_alloc (size_t bytes) { void* p = nullptr; return cudaMallocHost (&p, bytes) == cudaSuccess ? p : nullptr; }
+void lh264_host_free (void* p) { if (p) cudaFreeHost (p); }
+
+// ---- kernel-level entry points ---------------------------------------------------------------------------
+static int up (lh264_ctx* c, DevBuf<uint8_t>& b, const void* src, size_t bytes) {
+  CK (b.reserve (bytes + 16));
+  if (src) CK (cudaMemcpyAsync (b.p, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  return LH264_OK;
+}
+int lh264_k_idct4x4_add (lh264_ctx* c, uint8_t* pix, const int16_t* coef, int n) {
+  if (!c || !pix || !coef || n <= 0) return fail (LH264_E_INVALID, "bad arguments");
+  CK (cudaSetDevice (c->device));
+  int rc;
+  if ((rc = up (c, c->scratch_a, pix, (size_t)n * 16))) return rc;
+  if ((rc = up (c, c->scratch_b, coef, (size_t)n * 32))) return rc;
+  k_test_idct4<<<(n + 127) / 128, 128, 0, c->stream>>> (c->scratch_a.p, (const int16_t*)c->scratch_b.p, n);
+  c->launches++;
+  CK (cudaMemcpyAsync (pix, c->scratch_a.p, (size_t)n * 16, cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaStreamSynchronize (c->stream));
+  return LH264_OK;
+}
+int lh264_k_idct8x8_add (lh264_ctx* c, uint8_t* pix, const int16_t* coef, int n) {
+  if (!c || !pix || !coef || n <= 0) return fail (LH264_E_INVALID, "bad arguments");
+  CK (cudaSetDevice (c->device));
+  int rc;
+  if ((rc = up (c, c->scratch_a, pix, (size_t)n * 64))) return rc;
+  if ((rc = up (c, c->scratch_b, coef, (size_t)n * 128))) return rc;
+  k_test_idct8<<<(n + 63) / 64, 64, 0, c->stream>>> (c->scratch_a.p, (const int16_t*)c->scratch_b.p, n);
+  c->launches++;
+  CK (cudaMemcpyAsync (pix, c->scratch_a.p, (size_t)n * 64, cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaStreamSynchronize (c->stream));
+  return LH264_OK;
+}
+static int mc_common (lh264_ctx* c, const uint8_t* ref, int w, int h, const int32_t* blocks, int n, uint8_t* out, bool luma) {
+  if (!c || !ref || !blocks || !out || n <= 0 || w <= 0 || h <= 0) return fail (LH264_E_INVALID, "bad arguments");
+  CK (cudaSetDevice (c->device));
+  int rc;
+  if ((rc = up (c, c->scratch_a, ref, (size_t)w * h))) return rc;
+  if ((rc = up (c, c->scratch_b, blocks, (size_t)n * 24))) return rc;
+  if ((rc = up (c, c->scratch_c, nullptr, (size_t)n * 256))) return rc;
+  CK (cudaMemsetAsync (c->scratch_c.p, 0, (size_t)n * 256, c->stream));
+  if (luma) k_test_mc_luma<<<n, 256, 0, c->stream>>> (c->scratch_a.p, w, h, (const int32_t*)c->scratch_b.p, c->scratch_c.p);
+  else k_test_mc_chroma<<<n, 256, 0, c->stream>>> (c->scratch_a.p, w, h, (const int32_t*)c->scratch_b.p, c->scratch_c.p);
+  c->launches++;
+  CK (cudaMemcpyAsync (out, c->scratch_c.p, (size_t)n * 256, cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaStreamSynchronize (c->stream));
+  return LH264_OK;
+}
+int lh264_k_mc_luma (lh264_ctx* c, const uint8_t* ref, int w, int h, const int32_t* blocks, int n, uint8_t* out) { return mc_common (c, ref, w, h, blocks, n, out, true); }
+int lh264_k_mc_chroma (lh264_ctx* c, const uint8_t* ref, int w, int h, const int32_t* blocks, int n, uint8_t* out) { return mc_common (c, ref, w, h, blocks, n, out, false); }
+int lh264_k_expand_plane (lh264_ctx* c, const uint8_t* in, int w, int h, int pad, uint8_t* out) {
+  if (!c || !in || !out || w <= 0 || h <= 0 || pad < 0) return fail (LH264_E_INVALID, "bad arguments");
+  CK (cudaSetDevice (c->device));
+  int rc;
+  const size_t ob = (size_t) (w + 2 * pad) * (h + 2 * pad);
+  if ((rc = up (c, c->scratch_a, in, (size_t)w * h))) return rc;
+  if ((rc = up (c, c->scratch_c, nullptr, ob))) return rc;
+  k_test_expand<<<148 * 4, 256, 0, c->stream>>> (c->scratch_a.p, w, h, pad, c->scratch_c.p);
+  c->launches++;
+  CK (cudaMemcpyAsync (out, c->scratch_c.p, ob, cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaStreamSynchronize (c->stream));
+  return LH264_OK;
+}
+
+} // extern "C"

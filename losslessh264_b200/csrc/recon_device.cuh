@@ -1,0 +1,157 @@
+// recon_device.cuh — device-side arithmetic of the sm_100a macroblock-reconstruction kernels.
+//
+// Each routine names the reference code whose results it must reproduce bit-exactly (paths
+// relative to the reference root).  The decomposition is GPU-first: per-4x4-block reference
+// windows staged in shared memory, one thread per 4-pixel row for motion compensation, one
+// thread per coefficient block for dequant+IDCT, warp-lane-per-line deblocking.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "../../include/lh264_b200.h"
+
+namespace lh264 {
+
+__device__ __forceinline__ int clip3i (int v, int lo, int hi) { return min (max (v, lo), hi); }
+__device__ __forceinline__ int clip255 (int v) { return min (max (v, 0), 255); }
+
+// ---- tables ---------------------------------------------------------------------------------------
+// LevelScale4x4 (g_kuiDequantCoeff = this << qp/6, codec/common/src/common_tables.cpp:208-235)
+__constant__ uint8_t c_scale4[6][3] = { {10, 16, 13}, {11, 18, 14}, {13, 20, 16}, {14, 23, 18}, {16, 25, 20}, {18, 29, 23} };
+// normAdjust8x8 (g_kuiDequantCoeff8x8 = 16 * this, common_tables.cpp:237+)
+__constant__ uint8_t c_scale8[6][6] = { {20, 18, 32, 19, 25, 24}, {22, 19, 35, 21, 28, 26}, {26, 23, 42, 24, 33, 31},
+  {28, 25, 45, 26, 35, 33}, {32, 28, 51, 30, 40, 38}, {36, 32, 58, 34, 46, 43} };
+// alpha / beta / tc0 of the loop filter (codec/decoder/core/src/deblocking.cpp:89-125, without the +12 guard band)
+__constant__ uint8_t c_alpha[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 4, 4, 5, 6, 7, 8, 9, 10, 12, 13, 15, 17, 20, 22,
+                                    25, 28, 32, 36, 40, 45, 50, 56, 63, 71, 80, 90, 101, 113, 127, 144, 162, 182, 203, 226, 255, 255
+                                   };
+__constant__ uint8_t c_beta[52] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 6, 6, 7, 7,
+                                   8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13, 14, 14, 15, 15, 16, 16, 17, 17, 18, 18
+                                  };
+__constant__ int8_t c_tc0[52][4] = {
+  { -1, 0, 0, 0}, { -1, 0, 0, 0}, { -1, 0, 0, 0}, { -1, 0, 0, 0}, { -1, 0, 0, 0}, { -1, 0, 0, 0}, { -1, 0, 0, 0}, { -1, 0, 0, 0},
+  { -1, 0, 0, 0}, { -1, 0, 0, 0}, { -1, 0, 0, 0}, { -1, 0, 0, 0}, { -1, 0, 0, 0}, { -1, 0, 0, 0}, { -1, 0, 0, 0}, { -1, 0, 0, 0},
+  { -1, 0, 0, 0}, { -1, 0, 0, 1}, { -1, 0, 0, 1}, { -1, 0, 0, 1}, { -1, 0, 0, 1}, { -1, 0, 1, 1}, { -1, 0, 1, 1}, { -1, 1, 1, 1},
+  { -1, 1, 1, 1}, { -1, 1, 1, 1}, { -1, 1, 1, 1}, { -1, 1, 1, 2}, { -1, 1, 1, 2}, { -1, 1, 1, 2}, { -1, 1, 1, 2}, { -1, 1, 2, 3},
+  { -1, 1, 2, 3}, { -1, 2, 2, 3}, { -1, 2, 2, 4}, { -1, 2, 3, 4}, { -1, 2, 3, 4}, { -1, 3, 3, 5}, { -1, 3, 4, 6}, { -1, 3, 4, 6},
+  { -1, 4, 5, 7}, { -1, 4, 5, 8}, { -1, 4, 6, 9}, { -1, 5, 7, 10}, { -1, 6, 8, 11}, { -1, 6, 8, 13}, { -1, 7, 10, 14}, { -1, 8, 11, 16},
+  { -1, 9, 12, 18}, { -1, 10, 13, 20}, { -1, 11, 15, 23}, { -1, 13, 17, 25}
+};
+
+// 4x4 block z (decode order) -> pixel offset inside the MB
+__device__ __forceinline__ int blk_x (int z) { return ((z & 1) << 2) | ((z & 4) << 1); }
+__device__ __forceinline__ int blk_y (int z) { return ((z & 2) << 1) | ((z & 8)); }
+
+__device__ __forceinline__ int dq4 (int qp, int pos) {
+  // class by (pos & 7): a c a c / c b c b
+  const int cls = (0x12122020 >> ((pos & 7) * 4)) & 3;
+  return (int)c_scale4[qp % 6][cls] << (qp / 6);
+}
+__device__ __forceinline__ int dq8 (int qp, int pos) {
+  const int i = pos >> 3, j = pos & 7;
+  int c;
+  if ((i & 3) == 0 && (j & 3) == 0) c = 0;
+  else if ((i & 1) && (j & 1)) c = 1;
+  else if ((i & 3) == 2 && (j & 3) == 2) c = 2;
+  else if (((i & 3) == 0 && (j & 1)) || ((i & 1) && (j & 3) == 0)) c = 3;
+  else if (((i & 3) == 0 && (j & 3) == 2) || ((i & 3) == 2 && (j & 3) == 0)) c = 4;
+  else c = 5;
+  return 16 * (int)c_scale8[qp % 6][c];
+}
+
+// ---- inverse transforms ------------------------------------------------------------------------------
+// IdctResAddPred_c (codec/decoder/core/src/decode_mb_aux.cpp:42-77): c[16] dequantised (int16
+// values), row pass stored as int16, residual = (x + 32) >> 6.  Writes the 16 residuals to res[].
+__device__ __forceinline__ void idct4x4_res (const int c[16], int16_t* res, int rstride) {
+  int t[16];
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int a = c[4 * i], b = c[4 * i + 1], d = c[4 * i + 2], e = c[4 * i + 3];
+    const int e0 = a + d, e1 = a - d, e2 = (b >> 1) - e, e3 = b + (e >> 1);
+    t[4 * i] = (int16_t) (e0 + e3); t[4 * i + 1] = (int16_t) (e1 + e2);
+    t[4 * i + 2] = (int16_t) (e1 - e2); t[4 * i + 3] = (int16_t) (e0 - e3);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int e0 = t[i] + t[i + 8], e1 = t[i] - t[i + 8], e2 = (t[i + 4] >> 1) - t[i + 12], e3 = t[i + 4] + (t[i + 12] >> 1);
+    res[i] = (int16_t) ((32 + e0 + e3) >> 6);
+    res[i + rstride] = (int16_t) ((32 + e1 + e2) >> 6);
+    res[i + 2 * rstride] = (int16_t) ((32 + e1 - e2) >> 6);
+    res[i + 3 * rstride] = (int16_t) ((32 + e0 - e3) >> 6);
+  }
+}
+
+// one 8-point pass of IdctResAddPred8x8_c (decode_mb_aux.cpp:79-167); every intermediate is int16
+#define S16(x) ((int)(int16_t)(x))
+__device__ __forceinline__ void idct8_1d (const int p[8], int o[8]) {
+  int a0 = S16 (p[0] + p[4]), a1 = S16 (p[0] - p[4]), a2 = S16 (p[6] - (p[2] >> 1)), a3 = S16 (p[2] + (p[6] >> 1));
+  const int b0 = S16 (a0 + a3), b2 = S16 (a1 - a2), b4 = S16 (a1 + a2), b6 = S16 (a0 - a3);
+  a0 = S16 (-p[3] + p[5] - p[7] - (p[7] >> 1));
+  a1 = S16 (p[1] + p[7] - p[3] - (p[3] >> 1));
+  a2 = S16 (-p[1] + p[7] + p[5] + (p[5] >> 1));
+  a3 = S16 (p[3] + p[5] + p[1] + (p[1] >> 1));
+  const int b1 = S16 (a0 + (a3 >> 2)), b3 = S16 (a1 + (a2 >> 2)), b5 = S16 (a2 - (a1 >> 2)), b7 = S16 (a3 - (a0 >> 2));
+  o[0] = S16 (b0 + b7); o[1] = S16 (b2 - b5); o[2] = S16 (b4 + b3); o[3] = S16 (b6 + b1);
+  o[4] = S16 (b6 - b1); o[5] = S16 (b4 - b3); o[6] = S16 (b2 + b5); o[7] = S16 (b0 - b7);
+}
+
+// ---- luma / chroma interpolation on a shared-memory window ----------------------------------------------
+// McLuma_c family, codec/common/src/mc.cpp:142-346.  w points at the sample co-located with the
+// output pixel inside a window of row stride ws that holds 2 extra samples left/above and 4
+// right/below.
+__device__ __forceinline__ int tap6 (int a, int b, int c, int d, int e, int f) { return a + f - 5 * (b + e) + 20 * (c + d); }
+__device__ __forceinline__ int mc_h (const uint8_t* w) { return clip255 ((tap6 (w[-2], w[-1], w[0], w[1], w[2], w[3]) + 16) >> 5); }
+__device__ __forceinline__ int mc_vraw (const uint8_t* w, int ws) { return tap6 (w[-2 * ws], w[-ws], w[0], w[ws], w[2 * ws], w[3 * ws]); }
+__device__ __forceinline__ int mc_v (const uint8_t* w, int ws) { return clip255 ((mc_vraw (w, ws) + 16) >> 5); }
+__device__ __forceinline__ int mc_c (const uint8_t* w, int ws) {
+  // McHorVer22_c: vertical 6-tap first (int16 intermediates), then horizontal, (x + 512) >> 10
+  return clip255 ((tap6 (mc_vraw (w - 2, ws), mc_vraw (w - 1, ws), mc_vraw (w, ws), mc_vraw (w + 1, ws), mc_vraw (w + 2, ws),
+                         mc_vraw (w + 3, ws)) + 512) >> 10);
+}
+__device__ __forceinline__ int mc_luma_sample (const uint8_t* w, int ws, int frac /* fx*4+fy */) {
+#define AVG2(a, b) (((a) + (b) + 1) >> 1)
+  switch (frac) {            // pWelsMcFunc[x][y], mc.cpp:337-343
+  case 0: return w[0];
+  case 1: return AVG2 (w[0], mc_v (w, ws));
+  case 2: return mc_v (w, ws);
+  case 3: return AVG2 (w[ws], mc_v (w, ws));
+  case 4: return AVG2 (w[0], mc_h (w));
+  case 5: return AVG2 (mc_h (w), mc_v (w, ws));
+  case 6: return AVG2 (mc_v (w, ws), mc_c (w, ws));
+  case 7: return AVG2 (mc_h (w + ws), mc_v (w, ws));
+  case 8: return mc_h (w);
+  case 9: return AVG2 (mc_h (w), mc_c (w, ws));
+  case 10: return mc_c (w, ws);
+  case 11: return AVG2 (mc_h (w + ws), mc_c (w, ws));
+  case 12: return AVG2 (w[1], mc_h (w));
+  case 13: return AVG2 (mc_h (w), mc_v (w + 1, ws));
+  case 14: return AVG2 (mc_v (w + 1, ws), mc_c (w, ws));
+  default: return AVG2 (mc_h (w + ws), mc_v (w + 1, ws));
+  }
+#undef AVG2
+}
+
+// partition geometry of the 4x4 block (bx,by) (block units) inside an inter MB — GetInterPred's
+// partition walk, codec/decoder/core/src/rec_mb.cpp:344-545
+__device__ __forceinline__ void part_geom (int mb_type, int sub, int bx, int by, int& ox, int& oy, int& bw, int& bh) {
+  const int qx = (bx >> 1) << 3, qy = (by >> 1) << 3;
+  switch (mb_type) {
+  case LH264_MB_P16x8: ox = 0; oy = qy; bw = 16; bh = 8; break;
+  case LH264_MB_P8x16: ox = qx; oy = 0; bw = 8; bh = 16; break;
+  case LH264_MB_P8x8:
+    switch (sub) {
+    case LH264_SUB_8x8: ox = qx; oy = qy; bw = 8; bh = 8; break;
+    case LH264_SUB_8x4: ox = qx; oy = by << 2; bw = 8; bh = 4; break;
+    case LH264_SUB_4x8: ox = bx << 2; oy = qy; bw = 4; bh = 8; break;
+    default: ox = bx << 2; oy = by << 2; bw = 4; bh = 4; break;
+    }
+    break;
+  default: ox = 0; oy = 0; bw = 16; bh = 16; break;
+  }
+}
+
+// WeightPrediction sample op, rec_mb.cpp:291-300
+__device__ __forceinline__ int wp_sample (int v, int w, int o, int ld) {
+  return clip255 (ld >= 1 ? (((v * w + (1 << (ld - 1))) >> ld) + o) : (v * w + o));
+}
+
+} // namespace lh264

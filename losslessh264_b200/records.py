@@ -180,3 +180,40 @@ def write_lhfb(path, pics, with_pix=True):
                     f.write(p.pix_post[s].tobytes())
                 else:
                     f.write(struct.pack("<i", 0))
+
+
+def save_fixture(path, pics):
+    """Compact .npz form of a picture sequence (hand-off records + the reference's final pictures)."""
+    meta = np.array([[p.mb_w, p.mb_h, p.cur_slot, p.frame_num, p.poc_lsb, p.idr_pic_id, p.nal_ref_idc, p.serial, len(p.slices), len(p.coefs)] for p in pics], np.int32)
+    np.savez_compressed(
+        path,
+        meta=meta,
+        slices=np.concatenate([p.slices for p in pics]),
+        mbs=np.concatenate([p.mbs for p in pics]),
+        coefs=np.concatenate([p.coefs for p in pics]) if sum(len(p.coefs) for p in pics) else np.zeros((0, 16), np.int16),
+        yuv=np.concatenate([p.final_yuv() for p in pics]),
+    )
+
+
+def load_fixture(path):
+    z = np.load(path)
+    pics = []
+    o_s = o_m = o_c = o_y = 0
+    for row in z["meta"]:
+        mb_w, mb_h, slot, fn, poc, idr, ref_idc, serial, n_sl, n_co = (int(v) for v in row)
+        p = Picture(mb_w, mb_h, slot, fn, poc, idr, ref_idc, serial)
+        p.slices = z["slices"][o_s : o_s + n_sl].copy()
+        p.mbs = z["mbs"][o_m : o_m + mb_w * mb_h].copy()
+        p.coefs = z["coefs"][o_c : o_c + n_co].copy()
+        ysz = mb_w * mb_h * 384
+        p.pix_post = [z["yuv"][o_y : o_y + ysz].copy()]
+        o_s += n_sl
+        o_m += mb_w * mb_h
+        o_c += n_co
+        o_y += ysz
+        pics.append(p)
+    return pics
+
+
+def n_slots_needed(pics):
+    return max(max(p.cur_slot for p in pics), max(int(p.slices["ref_slot"].max()) for p in pics)) + 1
