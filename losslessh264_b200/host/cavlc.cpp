@@ -1,0 +1,231 @@
+// cavlc.cpp — see cavlc.h.
+#include "cavlc.h"
+#include <string.h>
+#include <vector>
+#include <mutex>
+
+namespace lh264host {
+
+const uint8_t kZigzag4x4[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
+const uint8_t kZigzag8x8[64] = {
+  0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+  35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63
+};
+
+// ---- Table 9-5: coeff_token, [table][trailing_ones][total_coeff] -----------------------------------
+static const uint8_t kTokLen[3][4][17] = {
+  { { 1, 6, 8, 9, 10, 11, 13, 13, 13, 14, 14, 15, 15, 16, 16, 16, 16},
+    { 0, 2, 6, 8, 9, 10, 11, 13, 13, 14, 14, 15, 15, 15, 16, 16, 16},
+    { 0, 0, 3, 7, 8, 9, 10, 11, 13, 13, 14, 14, 15, 15, 16, 16, 16},
+    { 0, 0, 0, 5, 6, 7, 8, 9, 10, 11, 13, 14, 14, 15, 15, 16, 16} },
+  { { 2, 6, 6, 7, 8, 8, 9, 11, 11, 12, 12, 12, 13, 13, 13, 14, 14},
+    { 0, 2, 5, 6, 6, 7, 8, 9, 11, 11, 12, 12, 13, 13, 14, 14, 14},
+    { 0, 0, 3, 6, 6, 7, 8, 9, 11, 11, 12, 12, 13, 13, 13, 14, 14},
+    { 0, 0, 0, 4, 4, 5, 6, 6, 7, 9, 11, 11, 12, 13, 13, 13, 14} },
+  { { 4, 6, 6, 6, 7, 7, 7, 7, 8, 8, 9, 9, 9, 10, 10, 10, 10},
+    { 0, 4, 5, 5, 5, 5, 6, 6, 7, 8, 8, 9, 9, 9, 10, 10, 10},
+    { 0, 0, 4, 5, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 10},
+    { 0, 0, 0, 4, 4, 4, 4, 4, 5, 6, 7, 8, 8, 9, 10, 10, 10} },
+};
+static const uint8_t kTokCode[3][4][17] = {
+  { { 1, 5, 7, 7, 7, 7, 15, 11, 8, 15, 11, 15, 11, 15, 11, 7, 4},
+    { 0, 1, 4, 6, 6, 6, 6, 14, 10, 14, 10, 14, 10, 1, 14, 10, 6},
+    { 0, 0, 1, 5, 5, 5, 5, 5, 13, 9, 13, 9, 13, 9, 13, 9, 5},
+    { 0, 0, 0, 3, 3, 4, 4, 4, 4, 4, 12, 12, 8, 12, 8, 12, 8} },
+  { { 3, 11, 7, 7, 7, 4, 7, 15, 11, 15, 11, 8, 15, 11, 7, 9, 7},
+    { 0, 2, 7, 10, 6, 6, 6, 6, 14, 10, 14, 10, 14, 10, 11, 8, 6},
+    { 0, 0, 3, 9, 5, 5, 5, 5, 13, 9, 13, 9, 13, 9, 6, 10, 5},
+    { 0, 0, 0, 5, 4, 6, 8, 4, 4, 4, 12, 8, 12, 12, 8, 1, 4} },
+  { { 15, 15, 11, 8, 15, 11, 9, 8, 15, 11, 15, 11, 8, 13, 9, 5, 1},
+    { 0, 14, 15, 12, 10, 8, 14, 10, 14, 14, 10, 14, 10, 7, 12, 8, 4},
+    { 0, 0, 13, 14, 11, 9, 13, 9, 13, 10, 13, 9, 13, 9, 11, 7, 3},
+    { 0, 0, 0, 12, 11, 10, 9, 8, 13, 12, 12, 12, 8, 12, 10, 6, 2} },
+};
+// chroma DC (4:2:0) coeff_token, [trailing_ones][total_coeff]
+static const uint8_t kTokLenC[4][5] = { {2, 6, 6, 6, 6}, {0, 1, 6, 7, 8}, {0, 0, 3, 7, 8}, {0, 0, 0, 6, 7} };
+static const uint8_t kTokCodeC[4][5] = { {1, 7, 4, 3, 2}, {0, 1, 6, 3, 3}, {0, 0, 1, 2, 2}, {0, 0, 0, 5, 0} };
+
+// ---- Tables 9-7 / 9-8: total_zeros, [total_coeff-1][total_zeros] ------------------------------------------
+static const uint8_t kTzLen[15][16] = {
+  {1, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 9},
+  {3, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 6, 6, 6, 6},
+  {4, 3, 3, 3, 4, 4, 3, 3, 4, 5, 5, 6, 5, 6},
+  {5, 3, 4, 4, 3, 3, 3, 4, 3, 4, 5, 5, 5},
+  {4, 4, 4, 3, 3, 3, 3, 3, 4, 5, 4, 5},
+  {6, 5, 3, 3, 3, 3, 3, 3, 4, 3, 6},
+  {6, 5, 3, 3, 3, 2, 3, 4, 3, 6},
+  {6, 4, 5, 3, 2, 2, 3, 3, 6},
+  {6, 6, 4, 2, 2, 3, 2, 5},
+  {5, 5, 3, 2, 2, 2, 4},
+  {4, 4, 3, 3, 1, 3},
+  {4, 4, 2, 1, 3},
+  {3, 3, 1, 2},
+  {2, 2, 1},
+  {1, 1},
+};
+static const uint8_t kTzCode[15][16] = {
+  {1, 3, 2, 3, 2, 3, 2, 3, 2, 3, 2, 3, 2, 3, 2, 1},
+  {7, 6, 5, 4, 3, 5, 4, 3, 2, 3, 2, 3, 2, 1, 0},
+  {5, 7, 6, 5, 4, 3, 4, 3, 2, 3, 2, 1, 1, 0},
+  {3, 7, 5, 4, 6, 5, 4, 3, 3, 2, 2, 1, 0},
+  {5, 4, 3, 7, 6, 5, 4, 3, 2, 1, 1, 0},
+  {1, 1, 7, 6, 5, 4, 3, 2, 1, 1, 0},
+  {1, 1, 5, 4, 3, 3, 2, 1, 1, 0},
+  {1, 1, 1, 3, 3, 2, 2, 1, 0},
+  {1, 0, 1, 3, 2, 1, 1, 1},
+  {1, 0, 1, 3, 2, 1, 1},
+  {0, 1, 1, 2, 1, 3},
+  {0, 1, 1, 1, 1},
+  {0, 1, 1, 1},
+  {0, 1, 1},
+  {0, 1},
+};
+static const uint8_t kTzLenC[3][4] = { {1, 2, 3, 3}, {1, 2, 2, 0}, {1, 1, 0, 0} };
+static const uint8_t kTzCodeC[3][4] = { {1, 1, 1, 0}, {1, 1, 0, 0}, {1, 0, 0, 0} };
+// ---- Table 9-10: run_before, [min(zeros_left,7)-1][run_before] ------------------------------------------------
+static const uint8_t kRunLen[7][15] = {
+  {1, 1}, {1, 2, 2}, {2, 2, 2, 2}, {2, 2, 2, 3, 3}, {2, 2, 3, 3, 3, 3}, {2, 3, 3, 3, 3, 3, 3},
+  {3, 3, 3, 3, 3, 3, 3, 4, 5, 6, 7, 8, 9, 10, 11},
+};
+static const uint8_t kRunCode[7][15] = {
+  {1, 0}, {1, 1, 0}, {3, 2, 1, 0}, {3, 2, 1, 1, 0}, {3, 2, 3, 2, 1, 0}, {3, 0, 1, 3, 2, 5, 4},
+  {7, 6, 5, 4, 3, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1},
+};
+
+// ---- generic prefix-code LUT ------------------------------------------------------------------------------------
+struct Lut {
+  int bits = 0;                         // index width
+  std::vector<uint8_t> sym, len;        // len == 0 -> invalid code
+  void build (int nbits, const uint8_t* lens, const uint8_t* codes, int n) {
+    bits = nbits;
+    sym.assign ((size_t)1 << nbits, 0);
+    len.assign ((size_t)1 << nbits, 0);
+    for (int s = 0; s < n; s++) {
+      const int l = lens[s];
+      if (!l) continue;
+      const uint32_t first = (uint32_t)codes[s] << (nbits - l), cnt = 1u << (nbits - l);
+      for (uint32_t k = 0; k < cnt; k++) { sym[first + k] = (uint8_t)s; len[first + k] = (uint8_t)l; }
+    }
+  }
+  inline int get (BitReader& br) const {
+    const uint32_t idx = br.peek (bits);
+    const int l = len[idx];
+    if (!l) return -1;
+    br.skip (l);
+    return sym[idx];
+  }
+};
+
+static Lut g_tok[3], g_tokc, g_tz[15], g_tzc[3], g_run[7];
+static std::once_flag g_once;
+
+static void do_init() {
+  for (int t = 0; t < 3; t++) {
+    uint8_t lens[68], codes[68];
+    for (int t1 = 0; t1 < 4; t1++) for (int tc = 0; tc < 17; tc++) { lens[tc * 4 + t1] = kTokLen[t][t1][tc]; codes[tc * 4 + t1] = kTokCode[t][t1][tc]; }
+    g_tok[t].build (16, lens, codes, 68);
+  }
+  {
+    uint8_t lens[20], codes[20];
+    for (int t1 = 0; t1 < 4; t1++) for (int tc = 0; tc < 5; tc++) { lens[tc * 4 + t1] = kTokLenC[t1][tc]; codes[tc * 4 + t1] = kTokCodeC[t1][tc]; }
+    g_tokc.build (8, lens, codes, 20);
+  }
+  for (int i = 0; i < 15; i++) g_tz[i].build (9, kTzLen[i], kTzCode[i], 16 - i);
+  for (int i = 0; i < 3; i++) g_tzc[i].build (3, kTzLenC[i], kTzCodeC[i], 4 - i);
+  for (int i = 0; i < 7; i++) g_run[i].build (11, kRunLen[i], kRunCode[i], i < 6 ? i + 2 : 15);
+}
+void cavlc_init() { std::call_once (g_once, do_init); }
+
+static bool kraft_ok (const uint8_t* lens, const uint8_t* codes, int n, bool complete) {
+  // prefix-free and (optionally) complete
+  double sum = 0;
+  for (int a = 0; a < n; a++) {
+    if (!lens[a]) continue;
+    sum += 1.0 / (double) (1u << lens[a]);
+    for (int b = 0; b < n; b++) {
+      if (a == b || !lens[b] || lens[b] < lens[a]) continue;
+      if ((uint32_t) (codes[b] >> (lens[b] - lens[a])) == codes[a]) return false;
+    }
+  }
+  return complete ? (sum > 0.999999 && sum < 1.000001) : sum <= 1.000001;
+}
+bool cavlc_selfcheck() {
+  bool ok = true;
+  for (int t = 0; t < 3; t++) {
+    uint8_t lens[68], codes[68];
+    for (int t1 = 0; t1 < 4; t1++) for (int tc = 0; tc < 17; tc++) { lens[tc * 4 + t1] = kTokLen[t][t1][tc]; codes[tc * 4 + t1] = kTokCode[t][t1][tc]; }
+    ok &= kraft_ok (lens, codes, 68, false);
+  }
+  { uint8_t lens[20], codes[20];
+    for (int t1 = 0; t1 < 4; t1++) for (int tc = 0; tc < 5; tc++) { lens[tc * 4 + t1] = kTokLenC[t1][tc]; codes[tc * 4 + t1] = kTokCodeC[t1][tc]; }
+    ok &= kraft_ok (lens, codes, 20, false); }
+  for (int i = 0; i < 15; i++) ok &= kraft_ok (kTzLen[i], kTzCode[i], 16 - i, i != 0 ? true : false);
+  for (int i = 0; i < 3; i++) ok &= kraft_ok (kTzLenC[i], kTzCodeC[i], 4 - i, true);
+  for (int i = 0; i < 7; i++) ok &= kraft_ok (kRunLen[i], kRunCode[i], i < 6 ? i + 2 : 15, i < 6);
+  return ok;
+}
+
+int cavlc_residual_block (BitReader& br, int nC, int max_coeff, const uint8_t* scan, int scan_step, int scan_off, int16_t* out) {
+  int total, t1;
+  if (nC < 0) {
+    const int s = g_tokc.get (br);
+    if (s < 0) return -1;
+    total = s >> 2; t1 = s & 3;
+  } else if (nC >= 8) {                      // 6-bit FLC: xxxxyy, 000011 = no coefficients
+    const uint32_t v = br.u (6);
+    if (v == 3) { total = 0; t1 = 0; }
+    else { total = (v >> 2) + 1; t1 = v & 3; }
+  } else {
+    const int s = g_tok[nC < 2 ? 0 : (nC < 4 ? 1 : 2)].get (br);
+    if (s < 0) return -1;
+    total = s >> 2; t1 = s & 3;
+  }
+  if (total == 0) return 0;
+  if (total > max_coeff || t1 > total) return -1;
+  int level[16];
+  // 9.2.2: trailing ones then levels, highest frequency first
+  for (int i = 0; i < t1; i++) level[i] = br.u1() ? -1 : 1;
+  int suffix_len = (total > 10 && t1 < 3) ? 1 : 0;
+  for (int i = t1; i < total; i++) {
+    const uint32_t w = br.peek (32);
+    if (w == 0) return -1;
+    const int prefix = __builtin_clz (w);
+    br.skip (prefix + 1);
+    int code = (prefix < 15 ? prefix : 15) << suffix_len;
+    int suffix_size = suffix_len;
+    if (prefix == 14 && suffix_len == 0) suffix_size = 4;
+    else if (prefix >= 15) suffix_size = prefix - 3;
+    if (suffix_size > 0) code += (int)br.u (suffix_size);
+    if (prefix >= 15 && suffix_len == 0) code += 15;
+    if (prefix >= 16) code += (1 << (prefix - 3)) - 4096;
+    if (i == t1 && t1 < 3) code += 2;
+    const int lv = (code & 1) ? (-code - 1) >> 1 : (code + 2) >> 1;
+    level[i] = lv;
+    if (suffix_len == 0) suffix_len = 1;
+    if ((lv < 0 ? -lv : lv) > (3 << (suffix_len - 1)) && suffix_len < 6) suffix_len++;
+  }
+  int zeros_left = 0;
+  if (total < max_coeff) {
+    int tz;
+    if (nC < 0) tz = g_tzc[total - 1].get (br);
+    else tz = g_tz[total - 1].get (br);
+    if (tz < 0) return -1;
+    zeros_left = tz;
+  }
+  if (zeros_left + total > max_coeff) return -1;
+  // place coefficients: level[0] is the highest-frequency one
+  int pos = zeros_left + total - 1;
+  for (int i = 0; i < total; i++) {
+    out[scan[scan_off + pos * scan_step]] = (int16_t)level[i];
+    if (i + 1 < total && zeros_left > 0) {
+      const int run = g_run[(zeros_left > 7 ? 7 : zeros_left) - 1].get (br);
+      if (run < 0 || run > zeros_left) return -1;
+      zeros_left -= run;
+      pos -= run;
+    }
+    pos--;
+  }
+  return total;
+}
+
+} // namespace lh264host

@@ -1,0 +1,722 @@
+// decoder.cpp — see decoder.h.  Clause numbers refer to ITU-T H.264.
+#include "decoder.h"
+#include "cavlc.h"
+#include <string.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <algorithm>
+
+namespace lh264host {
+
+namespace {
+
+// Table 9-4: coded_block_pattern me(v) mapping for ChromaArrayType 1/2
+const uint8_t kCbpIntra[48] = {47, 31, 15, 0, 23, 27, 29, 30, 7, 11, 13, 14, 39, 43, 45, 46, 16, 3, 5, 10, 12, 19, 21, 26, 28, 35, 37, 42, 44, 1, 2, 4,
+                               8, 17, 18, 20, 24, 6, 9, 22, 25, 32, 33, 34, 36, 40, 38, 41
+                              };
+const uint8_t kCbpInter[48] = {0, 16, 1, 2, 4, 8, 32, 3, 5, 10, 12, 15, 47, 7, 11, 13, 14, 6, 9, 31, 35, 37, 42, 44, 33, 34, 36, 40, 39, 43, 45, 46,
+                               17, 18, 20, 24, 19, 21, 26, 28, 23, 27, 29, 30, 22, 25, 38, 41
+                              };
+// Table 8-15: QPc as a function of qPI
+const uint8_t kChromaQp[52] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29,
+                               29, 30, 31, 32, 32, 33, 34, 34, 35, 35, 36, 36, 37, 37, 37, 38, 38, 38, 39, 39, 39, 39
+                              };
+// z (decode order) <-> raster index of the 4x4 luma blocks
+const uint8_t kZtoR[16] = {0, 1, 4, 5, 2, 3, 6, 7, 8, 9, 12, 13, 10, 11, 14, 15};
+const uint8_t kRtoZ[16] = {0, 1, 4, 5, 2, 3, 6, 7, 8, 9, 12, 13, 10, 11, 14, 15};
+const uint8_t kChromaDcScan[4] = {0, 16, 32, 48};   // DC k -> slot 0 of block k
+
+struct RefPic {
+  int slot = -1, frame_num = 0, pic_num = 0, long_idx = -1;
+  bool is_long = false, exists = true;
+};
+
+struct Nb { bool avail; int ref; int mvx, mvy; };
+
+inline int median3 (int a, int b, int c) { return a > b ? (b > c ? b : (a > c ? c : a)) : (a > c ? a : (b > c ? c : b)); }
+
+} // namespace
+
+struct Decoder::Impl {
+  PictureSink* sink = nullptr;
+  Sps sps[32];
+  Pps pps[256];
+  int active_sps = -1;
+  int mb_w = 0, mb_h = 0, n_mbs = 0, n_slots = 0;
+  std::vector<uint8_t> rbsp;
+
+  // decoded picture buffer (reference marking, 8.2.5)
+  std::vector<RefPic> refs;
+  int max_long_idx = -1;                 // "no long-term frame indices" = -1
+  int prev_ref_frame_num = 0;
+  int serial = 0;
+
+  // picture being decoded
+  bool open = false;
+  SliceHeader sh0;                       // first slice header of the picture
+  int cur_slot = 0, decoded = 0;
+  unsigned long long ts = 0;
+  std::vector<lh264_mb_rec> mbs;
+  std::vector<int16_t> coefs;
+  std::vector<lh264_slice_rec> slices;
+  std::vector<uint8_t> nzc;              // [mb][24] total_coeff (luma raster 0..15, Cb 16..19, Cr 20..23)
+  std::vector<int8_t> ipm;               // [mb][16] Intra4x4/8x8PredMode per raster block; 2 for other MB types
+  std::vector<int16_t> mb_slice;         // slice number of each MB, -1 = not decoded in this picture
+  std::vector<ModelMbSide> side;
+
+  // slice being parsed
+  const Sps* S = nullptr;
+  const Pps* P = nullptr;
+  SliceHeader sh;
+  int slice_no = 0, qp = 26;
+  RefPic* list0[33];
+  bool cur_done[16];                     // per raster 4x4 block of the current MB: MV already derived
+  int cur_mb = 0;
+
+  // ---------------------------------------------------------------------------------------------
+  bool mb_avail (int mb) const { return mb >= 0 && mb < n_mbs && mb_slice[mb] == slice_no; }
+  bool mb_avail_intra (int mb) const {   // usable for intra prediction samples / mode prediction
+    return mb_avail (mb) && (!P->constrained_intra_pred || LH264_MB_IS_INTRA (mbs[mb].mb_type));
+  }
+  int nb_mb (int mbx, int mby, int dx, int dy) const {
+    const int x = mbx + dx, y = mby + dy;
+    if (x < 0 || x >= mb_w || y < 0 || y >= mb_h) return -1;
+    return y * mb_w + x;
+  }
+  // neighbouring 4x4 block at block coordinates (bx,by) relative to the current MB's origin; may be
+  // negative / >= 4.  Returns motion data as 6.4.11.7 + 8.4.1.3.2 want it.
+  Nb nb_block (int bx, int by) const {
+    Nb r{false, -2, 0, 0};
+    const int mbx = cur_mb % mb_w, mby = cur_mb / mb_w;
+    int tx = mbx, ty = mby;
+    if (bx < 0) { tx--; bx += 4; } else if (bx > 3) { tx++; bx -= 4; }
+    if (by < 0) { ty--; by += 4; } else if (by > 3) return r;
+    if (tx < 0 || tx >= mb_w || ty < 0) return r;
+    const int t = ty * mb_w + tx;
+    const int rr = by * 4 + bx;
+    if (t == cur_mb) {
+      if (!cur_done[rr]) return r;
+    } else {
+      if (t > cur_mb || !mb_avail (t)) return r;
+    }
+    const lh264_mb_rec& m = mbs[t];
+    r.avail = true;
+    if (!LH264_MB_IS_INTER (m.mb_type)) { r.ref = -1; return r; }
+    r.ref = m.ref_idx[(by >> 1) * 2 + (bx >> 1)];
+    r.mvx = m.mv[rr][0]; r.mvy = m.mv[rr][1];
+    return r;
+  }
+  // 8.4.1.3: luma motion vector prediction for the partition at block (bx,by), size (bw,bh) blocks
+  void pred_mv (int bx, int by, int bw, int bh, int ref, int shape /*0 general, 1 16x8, 2 8x16*/, int& px, int& py) const {
+    const Nb A = nb_block (bx - 1, by), B = nb_block (bx, by - 1);
+    Nb C = nb_block (bx + bw, by - 1);
+    if (!C.avail) C = nb_block (bx - 1, by - 1);
+    if (shape == 1) {                                   // 16x8: upper uses B, lower uses A when refs match
+      if (by == 0) { if (B.ref == ref) { px = B.mvx; py = B.mvy; return; } }
+      else if (A.ref == ref) { px = A.mvx; py = A.mvy; return; }
+    } else if (shape == 2) {                            // 8x16: left uses A, right uses C
+      if (bx == 0) { if (A.ref == ref) { px = A.mvx; py = A.mvy; return; } }
+      else if (C.ref == ref) { px = C.mvx; py = C.mvy; return; }
+    }
+    // 8.4.1.3.1 median
+    if (!B.avail && !C.avail && A.avail) { px = A.mvx; py = A.mvy; return; }
+    const int match = (A.ref == ref) + (B.ref == ref) + (C.ref == ref);
+    if (match == 1) {
+      const Nb& n = A.ref == ref ? A : (B.ref == ref ? B : C);
+      px = n.mvx; py = n.mvy;
+      return;
+    }
+    px = median3 (A.mvx, B.mvx, C.mvx);
+    py = median3 (A.mvy, B.mvy, C.mvy);
+  }
+
+  // ---- reference lists / marking -----------------------------------------------------------------
+  int free_slot() const {
+    for (int s = 0; s < n_slots; s++) {
+      bool used = false;
+      for (const RefPic& r : refs) if (r.slot == s) used = true;
+      if (!used) return s;
+    }
+    return 0;
+  }
+  void build_list0() {
+    const int max_fn = 1 << S->log2_max_frame_num;
+    std::vector<RefPic*> sh_refs, lg_refs;
+    for (RefPic& r : refs) {
+      if (r.is_long) { r.pic_num = r.long_idx; lg_refs.push_back (&r); }
+      else { r.pic_num = r.frame_num > sh.frame_num ? r.frame_num - max_fn : r.frame_num; sh_refs.push_back (&r); }
+    }
+    std::sort (sh_refs.begin(), sh_refs.end(), [] (RefPic * a, RefPic * b) { return a->pic_num > b->pic_num; });
+    std::sort (lg_refs.begin(), lg_refs.end(), [] (RefPic * a, RefPic * b) { return a->pic_num < b->pic_num; });
+    const int n = sh.num_ref_idx_l0;
+    for (int i = 0; i < 33; i++) list0[i] = nullptr;
+    int k = 0;
+    for (RefPic* r : sh_refs) if (k < 32) list0[k++] = r;
+    for (RefPic* r : lg_refs) if (k < 32) list0[k++] = r;
+    // Reordering exactly as the reference performs it (WelsReorderRefList, manage_dec_ref.cpp:174-252):
+    // the picture is searched from the END of the whole initial list down to the current
+    // reordering index (by frame_num modulo MaxFrameNum, or long-term index) and rotated into
+    // place; when it is not found the remaining commands are dropped and the list keeps its
+    // current order.  This differs from 8.2.4.3 for streams that list one picture twice
+    // (x264 weightp duplicates, roundtriptest/tibby8x8cavlc.264) and must be mirrored for parity.
+    const int ref_count = k;
+    int pred = sh.frame_num, idx = 0;
+    for (const RefPicListMod& m : sh.mods) {
+      int i = -1;
+      if (m.op == 0 || m.op == 1) {
+        const int abs_diff = (int)m.val + 1;
+        pred = (m.op == 0 ? pred - abs_diff : pred + abs_diff) & (max_fn - 1);
+        for (i = ref_count - 1; i >= idx; i--) if (list0[i]->frame_num == pred && !list0[i]->is_long) break;
+      } else {
+        for (i = ref_count - 1; i >= idx; i--) if (list0[i]->is_long && list0[i]->long_idx == (int)m.val) break;
+      }
+      if (i < idx) break;
+      RefPic* pic = list0[i];
+      for (int c = i; c > idx; c--) list0[c] = list0[c - 1];
+      list0[idx++] = pic;
+    }
+    (void)n;
+  }
+  void mark_current() {                                  // 8.2.5 after the picture is decoded
+    if (sh0.nal_ref_idc == 0) return;
+    const int max_fn = 1 << S->log2_max_frame_num;
+    RefPic cur;
+    cur.slot = cur_slot; cur.frame_num = sh0.frame_num;
+    if (sh0.idr) {
+      refs.clear();
+      if (sh0.long_term_reference_flag) { cur.is_long = true; cur.long_idx = 0; max_long_idx = 0; }
+      else max_long_idx = -1;
+      refs.push_back (cur);
+      prev_ref_frame_num = sh0.frame_num;
+      return;
+    }
+    bool cur_long = false, had5 = false;
+    if (sh0.adaptive_marking) {
+      auto pic_num_of = [&] (const RefPic & r) { return r.frame_num > sh0.frame_num ? r.frame_num - max_fn : r.frame_num; };
+      for (const Mmco& m : sh0.mmcos) {
+        switch (m.op) {
+        case 1: {
+          const int pn = sh0.frame_num - ((int)m.a + 1);
+          for (size_t i = 0; i < refs.size(); i++) if (!refs[i].is_long && pic_num_of (refs[i]) == pn) { refs.erase (refs.begin() + i); break; }
+          break;
+        }
+        case 2:
+          for (size_t i = 0; i < refs.size(); i++) if (refs[i].is_long && refs[i].long_idx == (int)m.a) { refs.erase (refs.begin() + i); break; }
+          break;
+        case 3: {
+          const int pn = sh0.frame_num - ((int)m.a + 1);
+          for (size_t i = 0; i < refs.size(); i++) if (refs[i].is_long && refs[i].long_idx == (int)m.b) { refs.erase (refs.begin() + i); break; }
+          for (RefPic& r : refs) if (!r.is_long && pic_num_of (r) == pn) { r.is_long = true; r.long_idx = (int)m.b; break; }
+          break;
+        }
+        case 4:
+          max_long_idx = (int)m.a - 1;
+          for (size_t i = 0; i < refs.size();) { if (refs[i].is_long && refs[i].long_idx > max_long_idx) refs.erase (refs.begin() + i); else i++; }
+          break;
+        case 5: refs.clear(); max_long_idx = -1; had5 = true; break;
+        case 6:
+          for (size_t i = 0; i < refs.size(); i++) if (refs[i].is_long && refs[i].long_idx == (int)m.b) { refs.erase (refs.begin() + i); break; }
+          cur.is_long = true; cur.long_idx = (int)m.b; cur_long = true;
+          break;
+        }
+      }
+    } else {
+      sliding_window();
+    }
+    (void)cur_long;
+    if (had5) cur.frame_num = 0;
+    refs.push_back (cur);
+    prev_ref_frame_num = had5 ? 0 : sh0.frame_num;
+  }
+  void sliding_window() {
+    const int max_refs = std::max (S->max_num_ref_frames, 1);
+    while ((int)refs.size() >= max_refs) {
+      int best = -1, best_num = 0;
+      const int max_fn = 1 << S->log2_max_frame_num;
+      for (size_t i = 0; i < refs.size(); i++) {
+        if (refs[i].is_long) continue;
+        const int w = refs[i].frame_num > sh0.frame_num ? refs[i].frame_num - max_fn : refs[i].frame_num;
+        if (best < 0 || w < best_num) { best = (int)i; best_num = w; }
+      }
+      if (best < 0) break;
+      refs.erase (refs.begin() + best);
+    }
+  }
+
+  // ---- picture life cycle --------------------------------------------------------------------------
+  int activate (const Sps& s) {
+    if (active_sps == s.id && mb_w == s.mb_w && mb_h == s.mb_h && n_slots >= s.max_num_ref_frames + 2) return 0;
+    active_sps = s.id;
+    mb_w = s.mb_w; mb_h = s.mb_h; n_mbs = mb_w * mb_h;
+    n_slots = std::max (3, s.max_num_ref_frames + 2);
+    refs.clear(); max_long_idx = -1;
+    mbs.assign (n_mbs, lh264_mb_rec());
+    nzc.assign ((size_t)n_mbs * 24, 0);
+    ipm.assign ((size_t)n_mbs * 16, 2);
+    mb_slice.assign (n_mbs, -1);
+    side.assign (n_mbs, ModelMbSide());
+    coefs.reserve ((size_t)n_mbs * 64);
+    return sink->configure (mb_w, mb_h, n_slots);
+  }
+  bool is_new_picture (const SliceHeader& a, const SliceHeader& b) const {   // 7.4.1.2.4
+    return a.frame_num != b.frame_num || a.pps_id != b.pps_id || (a.nal_ref_idc == 0) != (b.nal_ref_idc == 0) ||
+           a.idr != b.idr || (a.idr && a.idr_pic_id != b.idr_pic_id) || a.poc_lsb != b.poc_lsb ||
+           a.delta_poc_bottom != b.delta_poc_bottom || a.delta_poc[0] != b.delta_poc[0] || a.delta_poc[1] != b.delta_poc[1];
+  }
+  void start_picture (Decoder* self) {
+    (void)self;
+    open = true; sh0 = sh; decoded = 0; slice_no = 0;
+    if (sh.idr) { /* refs dropped at marking time; lists are empty for an I picture anyway */ }
+    else if (S->gaps_in_frame_num_allowed) {
+      // 8.2.5.2: fill frame_num gaps with non-existing short-term frames
+      const int max_fn = 1 << S->log2_max_frame_num;
+      if (sh.frame_num != prev_ref_frame_num && sh.frame_num != (prev_ref_frame_num + 1) % max_fn) {
+        int fn = (prev_ref_frame_num + 1) % max_fn, guard = 0;
+        const SliceHeader keep = sh0;
+        while (fn != sh.frame_num && guard++ < max_fn) {
+          sh0.frame_num = fn;
+          sliding_window();
+          RefPic r; r.slot = refs.empty() ? 0 : refs.back().slot; r.frame_num = fn; r.exists = false;
+          refs.push_back (r);
+          prev_ref_frame_num = fn;
+          fn = (fn + 1) % max_fn;
+        }
+        sh0 = keep;
+      }
+    }
+    cur_slot = free_slot();
+    slices.clear(); coefs.clear();
+    for (int i = 0; i < n_mbs; i++) { mbs[i].mb_type = LH264_MB_NONE; mb_slice[i] = -1; }
+  }
+  int finish_picture (Decoder* self) {
+    if (!open) return 0;
+    open = false;
+    lh264_picture_desc d;
+    d.stream = 0; d.cur_slot = cur_slot; d.n_slices = (int)slices.size(); d.n_coef_blocks = (int) (coefs.size() / 16);
+    d.slices = slices.data(); d.mbs = mbs.data(); d.coefs = coefs.data();
+    DecodedPictureInfo info;
+    info.mb_w = mb_w; info.mb_h = mb_h;
+    info.crop_x = S->crop_left; info.crop_y = S->crop_top;
+    info.width = mb_w * 16 - S->crop_left - S->crop_right; info.height = mb_h * 16 - S->crop_top - S->crop_bottom;
+    info.frame_num = sh0.frame_num; info.poc_lsb = sh0.poc_lsb; info.idr_pic_id = sh0.idr_pic_id; info.nal_ref_idc = sh0.nal_ref_idc;
+    info.slot = cur_slot; info.serial = serial++; info.complete = decoded >= n_mbs; info.timestamp = ts;
+    int rc = 0;
+    if (!slices.empty()) rc = sink->submit (d, info);
+    mark_current();
+    self->stats_.pictures++;
+    self->stats_.coef_blocks += coefs.size() / 16;
+    self->out_.push_back (info);
+    return rc;
+  }
+
+  // ---- slice data ------------------------------------------------------------------------------------
+  int parse_slice_data (BitReader& br, Decoder* self);
+  int parse_mb (BitReader& br, int mb_addr, bool skipped);
+  int parse_residual (BitReader& br, lh264_mb_rec& m, int mb_addr, int16_t* lev, uint32_t& coded, bool i16, int cbp);
+  void resolve_intra (lh264_mb_rec& m, int mb_addr, const int8_t* modes, bool i8x8);
+  int nC_luma (int mb_addr, int r) const;
+  int nC_chroma (int mb_addr, int plane, int b) const;
+};
+
+// ---- nC derivation (9.2.1) -----------------------------------------------------------------------------
+int Decoder::Impl::nC_luma (int mb_addr, int r) const {
+  const int mbx = mb_addr % mb_w, mby = mb_addr / mb_w, bx = r & 3, by = r >> 2;
+  int nA = -1, nB = -1;
+  if (bx > 0) nA = nzc[(size_t)mb_addr * 24 + r - 1];
+  else { const int n = nb_mb (mbx, mby, -1, 0); if (mb_avail (n)) nA = nzc[(size_t)n * 24 + r + 3]; }
+  if (by > 0) nB = nzc[(size_t)mb_addr * 24 + r - 4];
+  else { const int n = nb_mb (mbx, mby, 0, -1); if (mb_avail (n)) nB = nzc[(size_t)n * 24 + r + 12]; }
+  if (nA >= 0 && nB >= 0) return (nA + nB + 1) >> 1;
+  return nA >= 0 ? nA : (nB >= 0 ? nB : 0);
+}
+int Decoder::Impl::nC_chroma (int mb_addr, int plane, int b) const {
+  const int mbx = mb_addr % mb_w, mby = mb_addr / mb_w, bx = b & 1, by = b >> 1, base = 16 + 4 * plane;
+  int nA = -1, nB = -1;
+  if (bx > 0) nA = nzc[(size_t)mb_addr * 24 + base + b - 1];
+  else { const int n = nb_mb (mbx, mby, -1, 0); if (mb_avail (n)) nA = nzc[(size_t)n * 24 + base + b + 1]; }
+  if (by > 0) nB = nzc[(size_t)mb_addr * 24 + base + b - 2];
+  else { const int n = nb_mb (mbx, mby, 0, -1); if (mb_avail (n)) nB = nzc[(size_t)n * 24 + base + b + 2]; }
+  if (nA >= 0 && nB >= 0) return (nA + nB + 1) >> 1;
+  return nA >= 0 ? nA : (nB >= 0 ? nB : 0);
+}
+
+// ---- intra mode resolution: what the reference does at parse time (CheckIntraNxNPredMode etc.,
+// parse_mb_syn_cavlc.cpp:519-612) expressed on neighbour availability -----------------------------------
+void Decoder::Impl::resolve_intra (lh264_mb_rec& m, int mb_addr, const int8_t* modes, bool i8x8) {
+  const int mbx = mb_addr % mb_w, mby = mb_addr / mb_w;
+  const bool L = mb_avail_intra (nb_mb (mbx, mby, -1, 0)), T = mb_avail_intra (nb_mb (mbx, mby, 0, -1));
+  const bool TL = mb_avail_intra (nb_mb (mbx, mby, -1, -1)), TR = mb_avail_intra (nb_mb (mbx, mby, 1, -1));
+  m.nxn_avail = (uint8_t) ((T ? 1 : 0) | (TL ? 2 : 0) | (L ? 4 : 0) | (TR ? 8 : 0));
+  auto fix = [] (int mode, bool l, bool t, bool tr) -> uint8_t {
+    if (mode == LH264_I4_DC) return (uint8_t) (l && t ? LH264_I4_DC : (l ? LH264_I4_DC_L : (t ? LH264_I4_DC_T : LH264_I4_DC_128)));
+    if (mode == LH264_I4_DDL && !tr) return LH264_I4_DDL_TOP;
+    if (mode == LH264_I4_VL && !tr) return LH264_I4_VL_TOP;
+    return (uint8_t)mode;
+  };
+  if (modes) {
+    if (i8x8) {
+      for (int q = 0; q < 4; q++) {
+        const bool l = (q & 1) ? true : L, t = (q >> 1) ? true : T;
+        const bool tr = q == 0 ? T : (q == 1 ? TR : (q == 2));
+        const uint8_t f = fix (modes[q], l, t, tr);
+        for (int k = 0; k < 4; k++) m.intra_mode[4 * q + k] = f;
+      }
+    } else {
+      for (int z = 0; z < 16; z++) {
+        const int r = kZtoR[z], bx = r & 3, by = r >> 2;
+        const bool l = bx > 0 ? true : L, t = by > 0 ? true : T;
+        bool tr;
+        if (by == 0) tr = bx < 3 ? T : TR;
+        else tr = bx < 3 && kRtoZ[r - 3] < z;          // block (bx+1, by-1) decoded earlier?
+        m.intra_mode[z] = fix (modes[z], l, t, tr);
+      }
+    }
+  }
+  // Intra16x16 / chroma DC variants (CheckIntra16x16PredMode / CheckIntraChromaPredMode)
+  if (m.mb_type == LH264_MB_I16x16 && m.i16_mode == LH264_I16_DC)
+    m.i16_mode = (uint8_t) (L && T ? LH264_I16_DC : (L ? LH264_I16_DC_L : (T ? LH264_I16_DC_T : LH264_I16_DC_128)));
+  if (m.chroma_mode == LH264_C_DC)
+    m.chroma_mode = (uint8_t) (L && T ? LH264_C_DC : (L ? LH264_C_DC_L : (T ? LH264_C_DC_T : LH264_C_DC_128)));
+}
+
+// ---- residual( ) for CAVLC (7.3.5.3) --------------------------------------------------------------------
+int Decoder::Impl::parse_residual (BitReader& br, lh264_mb_rec& m, int mb_addr, int16_t* lev, uint32_t& coded, bool i16, int cbp) {
+  uint8_t* nz = &nzc[(size_t)mb_addr * 24];
+  const bool t8 = m.flags & LH264_MBF_TRANSFORM8x8;
+  if (i16) {                                        // Intra16x16DCLevel: 16 DC levels, zig-zag over the 4x4 DC matrix
+    int16_t dc[16];
+    memset (dc, 0, sizeof (dc));
+    const int tc = cavlc_residual_block (br, nC_luma (mb_addr, 0), 16, kZigzag4x4, 1, 0, dc);
+    if (tc < 0) return -1;
+    for (int r = 0; r < 16; r++) if (dc[r]) { const int z = kRtoZ[r]; lev[16 * z] = dc[r]; coded |= 1u << z; }
+  }
+  for (int q = 0; q < 4; q++) {
+    if (! (cbp & (1 << q))) { for (int k = 0; k < 4; k++) nz[kZtoR[4 * q + k]] = 0; continue; }
+    for (int k = 0; k < 4; k++) {
+      const int z = 4 * q + k, r = kZtoR[z];
+      int tc;
+      if (t8) tc = cavlc_residual_block (br, nC_luma (mb_addr, r), 16, kZigzag8x8, 4, k, lev + 64 * q);
+      else if (i16) tc = cavlc_residual_block (br, nC_luma (mb_addr, r), 15, kZigzag4x4, 1, 1, lev + 16 * z);
+      else tc = cavlc_residual_block (br, nC_luma (mb_addr, r), 16, kZigzag4x4, 1, 0, lev + 16 * z);
+      if (tc < 0) return -1;
+      nz[r] = (uint8_t)tc;
+      if (tc) coded |= t8 ? (0xFu << (4 * q)) : (1u << z);
+    }
+  }
+  const int cc = cbp >> 4;
+  if (cc) {
+    for (int p = 0; p < 2; p++) {                   // ChromaDCLevel
+      int16_t dc[64];
+      memset (dc, 0, sizeof (dc));
+      const int tc = cavlc_residual_block (br, -1, 4, kChromaDcScan, 1, 0, dc);
+      if (tc < 0) return -1;
+      for (int b = 0; b < 4; b++) if (dc[16 * b]) { lev[16 * (16 + 4 * p + b)] = dc[16 * b]; coded |= 1u << (16 + 4 * p + b); }
+    }
+  }
+  for (int p = 0; p < 2; p++) for (int b = 0; b < 4; b++) {
+      if (cc & 2) {                                 // ChromaACLevel
+        const int tc = cavlc_residual_block (br, nC_chroma (mb_addr, p, b), 15, kZigzag4x4, 1, 1, lev + 16 * (16 + 4 * p + b));
+        if (tc < 0) return -1;
+        nz[16 + 4 * p + b] = (uint8_t)tc;
+        if (tc) coded |= 1u << (16 + 4 * p + b);
+      } else nz[16 + 4 * p + b] = 0;
+    }
+  return 0;
+}
+
+// ---- macroblock_layer( ) (7.3.5) -----------------------------------------------------------------------
+int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped) {
+  lh264_mb_rec& m = mbs[mb_addr];
+  memset (&m, 0, sizeof (m));
+  cur_mb = mb_addr;
+  m.slice_idx = (uint16_t)slice_no;
+  uint8_t* nz = &nzc[(size_t)mb_addr * 24];
+  int8_t* pm = &ipm[(size_t)mb_addr * 16];
+  memset (pm, 2, 16);
+  const int mbx = mb_addr % mb_w, mby = mb_addr / mb_w;
+  auto set_qp = [&] (lh264_mb_rec & mm) {
+    mm.qp_y = (uint8_t)qp;
+    mm.qp_c[0] = kChromaQp[std::min (51, std::max (0, qp + P->chroma_qp_index_offset))];
+    mm.qp_c[1] = kChromaQp[std::min (51, std::max (0, qp + P->second_chroma_qp_index_offset))];
+  };
+  memset (cur_done, 0, sizeof (cur_done));
+  memset (m.ref_idx, -1, 4);
+
+  if (skipped) {                                    // P_Skip: 8.4.1.1
+    m.mb_type = LH264_MB_PSKIP;
+    set_qp (m);
+    memset (nz, 0, 24);
+    memset (m.ref_idx, 0, 4);
+    int px = 0, py = 0;
+    const Nb A = nb_block (-1, 0), B = nb_block (0, -1);
+    if (A.avail && B.avail && ! (A.ref == 0 && A.mvx == 0 && A.mvy == 0) && ! (B.ref == 0 && B.mvx == 0 && B.mvy == 0))
+      pred_mv (0, 0, 4, 4, 0, 0, px, py);
+    for (int r = 0; r < 16; r++) { m.mv[r][0] = (int16_t)px; m.mv[r][1] = (int16_t)py; }
+    mb_slice[mb_addr] = (int16_t)slice_no;
+    return 0;
+  }
+
+  uint32_t t = br.ue();
+  const bool p_slice = sh.slice_type == SLICE_P;
+  bool intra = true;
+  if (p_slice) {
+    if (t < 5) intra = false;
+    else t -= 5;
+  }
+  if (intra && t > 25) return -1;
+  int16_t lev[384];
+  uint32_t coded = 0;
+  int cbp = 0;
+  bool i16 = false;
+
+  if (!intra) {
+    static const uint8_t kind[5] = {LH264_MB_P16x16, LH264_MB_P16x8, LH264_MB_P8x16, LH264_MB_P8x8, LH264_MB_P8x8};
+    m.mb_type = kind[t];
+    const int nref = sh.num_ref_idx_l0;
+    bool sub_lt8 = false;
+    auto put_mv = [&] (int bx, int by, int bw, int bh, int mvx, int mvy) {
+      for (int y = by; y < by + bh; y++) for (int x = bx; x < bx + bw; x++) { m.mv[y * 4 + x][0] = (int16_t)mvx; m.mv[y * 4 + x][1] = (int16_t)mvy; cur_done[y * 4 + x] = true; }
+    };
+    if (m.mb_type == LH264_MB_P8x8) {
+      for (int q = 0; q < 4; q++) {
+        const uint32_t s = br.ue();
+        if (s > 3) return -1;
+        m.sub_mb_type[q] = (uint8_t)s;
+        if (s) sub_lt8 = true;
+      }
+      for (int q = 0; q < 4; q++) {
+        int ref = 0;
+        if (t != 4 && nref > 1) { ref = (int)br.te (nref - 1); if (ref >= nref) return -1; }
+        m.ref_idx[q] = (int8_t)ref;
+      }
+      // the standard makes a block "available" only once its motion has been derived; the ref_idx of
+      // later quadrants must therefore stay hidden from nb_block(): cur_done gates them.
+      for (int q = 0; q < 4; q++) {
+        const int bx0 = (q & 1) * 2, by0 = (q >> 1) * 2, ref = m.ref_idx[q];
+        static const uint8_t npart[4] = {1, 2, 2, 4};
+        for (int s = 0; s < npart[m.sub_mb_type[q]]; s++) {
+          int bx = bx0, by = by0, bw = 2, bh = 2;
+          switch (m.sub_mb_type[q]) {
+          case LH264_SUB_8x4: bh = 1; by += s; break;
+          case LH264_SUB_4x8: bw = 1; bx += s; break;
+          case LH264_SUB_4x4: bw = bh = 1; bx += s & 1; by += s >> 1; break;
+          default: break;
+          }
+          int px, py;
+          pred_mv (bx, by, bw, bh, ref, 0, px, py);
+          const int dx = br.se(), dy = br.se();
+          put_mv (bx, by, bw, bh, px + dx, py + dy);
+        }
+      }
+    } else {
+      const int nparts = m.mb_type == LH264_MB_P16x16 ? 1 : 2;
+      int refs_[2] = {0, 0};
+      for (int p = 0; p < nparts; p++) if (nref > 1) { refs_[p] = (int)br.te (nref - 1); if (refs_[p] >= nref) return -1; }
+      for (int p = 0; p < nparts; p++) {
+        int bx = 0, by = 0, bw = 4, bh = 4, shape = 0;
+        if (m.mb_type == LH264_MB_P16x8) { bh = 2; by = 2 * p; shape = 1; }
+        else if (m.mb_type == LH264_MB_P8x16) { bw = 2; bx = 2 * p; shape = 2; }
+        // ref_idx of this partition becomes visible together with its MV
+        for (int y = by; y < by + bh; y += 2) for (int x = bx; x < bx + bw; x += 2) m.ref_idx[(y >> 1) * 2 + (x >> 1)] = (int8_t)refs_[p];
+        int px, py;
+        pred_mv (bx, by, bw, bh, refs_[p], shape, px, py);
+        const int dx = br.se(), dy = br.se();
+        put_mv (bx, by, bw, bh, px + dx, py + dy);
+      }
+    }
+    const uint32_t c = br.ue();
+    if (c > 47) return -1;
+    cbp = kCbpInter[c];
+    if ((cbp & 15) && P->transform_8x8_mode && ! (m.mb_type == LH264_MB_P8x8 && sub_lt8)) {
+      if (br.u1()) m.flags |= LH264_MBF_TRANSFORM8x8;
+    }
+  } else if (t == 25) {                               // I_PCM
+    m.mb_type = LH264_MB_IPCM;
+    br.align();
+    const size_t at = coefs.size();
+    coefs.resize (at + 384);
+    int16_t* o = coefs.data() + at;
+    const uint8_t* src = br.data() + (br.pos() >> 3);
+    for (int i = 0; i < 384; i++) o[i] = src[i];
+    br.skip (384 * 8);
+    m.coded_mask = 0xFFFFFF; m.coef_off = (uint32_t) (at / 16);
+    m.nz_mask = 0xFFFFFF;
+    memset (nz, 16, 24);
+    m.qp_y = 0; m.qp_c[0] = m.qp_c[1] = 0;          // decode_slice.cpp:3258-3259
+    mb_slice[mb_addr] = (int16_t)slice_no;
+    return br.overrun() ? -1 : 0;
+  } else if (t == 0) {                                // I_NxN
+    bool i8 = false;
+    if (P->transform_8x8_mode) i8 = br.u1();
+    m.mb_type = i8 ? LH264_MB_I8x8 : LH264_MB_I4x4;
+    if (i8) m.flags |= LH264_MBF_TRANSFORM8x8;
+    int8_t modes[16];
+    const int nL = nb_mb (mbx, mby, -1, 0), nT = nb_mb (mbx, mby, 0, -1);
+    const bool aL = mb_avail_intra (nL), aT = mb_avail_intra (nT);
+    const int n = i8 ? 4 : 16;
+    for (int i = 0; i < n; i++) {
+      // 8.3.1.1 / 8.3.2.1: predicted mode = min(left, top), 2 when either neighbour is unavailable
+      const int r = i8 ? kZtoR[4 * i] : kZtoR[i], bx = r & 3, by = r >> 2;
+      int a, b;
+      bool okA = true, okB = true;
+      if (bx > 0) a = pm[r - 1]; else if (aL) a = ipm[(size_t)nL * 16 + r + 3]; else { a = 2; okA = false; }
+      if (by > 0) b = pm[r - 4]; else if (aT) b = ipm[(size_t)nT * 16 + r + 12]; else { b = 2; okB = false; }
+      if (i8 && bx == 0 && aL && mbs[nL].mb_type == LH264_MB_I4x4) a = ipm[(size_t)nL * 16 + r + 3];          // 4x4 block 8x8idxA*4+1 = (x=3, y=by)
+      if (i8 && by == 0 && aT && mbs[nT].mb_type == LH264_MB_I4x4) b = ipm[(size_t)nT * 16 + 12 + bx];        // 4x4 block 8x8idxB*4+2 = (x=bx, y=3)
+      int pred = (!okA || !okB) ? 2 : std::min (a, b);
+      int mode = pred;
+      if (!br.u1()) { const int rem = (int)br.u (3); mode = rem < pred ? rem : rem + 1; }
+      modes[i] = (int8_t)mode;
+      if (i8) { pm[r] = pm[r + 1] = pm[r + 4] = pm[r + 5] = (int8_t)mode; }
+      else pm[r] = (int8_t)mode;
+    }
+    const uint32_t cm = br.ue();
+    if (cm > 3) return -1;
+    m.chroma_mode = (uint8_t)cm;
+    resolve_intra (m, mb_addr, modes, i8);
+    const uint32_t c = br.ue();
+    if (c > 47) return -1;
+    cbp = kCbpIntra[c];
+  } else {                                            // Intra16x16
+    m.mb_type = LH264_MB_I16x16;
+    i16 = true;
+    m.i16_mode = (uint8_t) ((t - 1) & 3);
+    cbp = (((t - 1) >> 2) % 3) << 4 | ((t - 1) >= 12 ? 15 : 0);
+    const uint32_t cm = br.ue();
+    if (cm > 3) return -1;
+    m.chroma_mode = (uint8_t)cm;
+    resolve_intra (m, mb_addr, nullptr, false);
+  }
+  m.cbp = (uint8_t)cbp;
+  if (cbp > 0 || i16) {
+    const int dqp = br.se();
+    if (dqp < -26 || dqp > 25) return -1;
+    qp = (qp + dqp + 52) % 52;
+    set_qp (m);
+    memset (lev, 0, sizeof (lev));
+    if (parse_residual (br, m, mb_addr, lev, coded, i16, cbp) < 0) return -1;
+    if (coded) {
+      m.coded_mask = coded;
+      m.coef_off = (uint32_t) (coefs.size() / 16);
+      size_t at = coefs.size();
+      coefs.resize (at + 16 * (size_t)__builtin_popcount (coded));
+      int16_t* o = coefs.data() + at;
+      for (uint32_t mk = coded; mk; mk &= mk - 1) { const int k = __builtin_ctz (mk); memcpy (o, lev + 16 * k, 32); o += 16; }
+    }
+  } else {
+    set_qp (m);
+    memset (nz, 0, 24);
+  }
+  uint32_t nzm = 0;
+  for (int r = 0; r < 24; r++) if (nz[r]) nzm |= 1u << r;
+  m.nz_mask = nzm;
+  mb_slice[mb_addr] = (int16_t)slice_no;
+  return br.overrun() ? -1 : 0;
+}
+
+// ---- slice_data( ) (7.3.4), CAVLC --------------------------------------------------------------------------
+int Decoder::Impl::parse_slice_data (BitReader& br, Decoder* self) {
+  int mb_addr = sh.first_mb;
+  qp = sh.slice_qp;
+  const int first = mb_addr;
+  bool more = true;
+  int rc = 0;
+  while (more && mb_addr < n_mbs) {
+    if (sh.slice_type != SLICE_I) {
+      const uint32_t run = br.ue();
+      if (run > (uint32_t) (n_mbs - mb_addr)) { rc = -1; break; }
+      for (uint32_t i = 0; i < run; i++) { parse_mb (br, mb_addr, true); mb_addr++; }
+      if (run > 0) more = br.more_rbsp_data();
+      if (!more || mb_addr >= n_mbs) break;
+    }
+    if (parse_mb (br, mb_addr, false) < 0) { rc = -1; self->stats_.errors++; break; }
+    mb_addr++;
+    more = br.more_rbsp_data();
+  }
+  lh264_slice_rec& sr = slices.back();
+  sr.num_mbs = mb_addr - first;
+  decoded += mb_addr - first;
+  self->stats_.mbs += mb_addr - first;
+  return rc;
+}
+
+// ---- Decoder ---------------------------------------------------------------------------------------------------
+Decoder::Decoder (PictureSink* sink) : d_ (new Impl()) { d_->sink = sink; cavlc_init(); }
+Decoder::~Decoder() {}
+const std::vector<ModelMbSide>& Decoder::model_side() const { return d_->side; }
+
+int Decoder::flush() { return d_->finish_picture (this); }
+
+int Decoder::decode (const uint8_t* data, size_t len, unsigned long long timestamp) {
+  Impl& D = *d_;
+  std::vector<NalSpan> nals;
+  split_annexb (data, len, nals);
+  int last_err = 0;
+  for (const NalSpan& n : nals) {
+    stats_.nals++;
+    if (n.len < 1) continue;
+    const int ref_idc = (n.p[0] >> 5) & 3, type = n.p[0] & 31;
+    const size_t plen = unescape_nal (n.p + 1, n.len - 1, D.rbsp);
+    BitReader br (D.rbsp.data(), plen);
+    if (type == NAL_SPS) {
+      Sps s;
+      if (parse_sps (br, s)) {
+        if (D.open && D.active_sps == s.id) D.finish_picture (this);
+        D.sps[s.id] = s;
+      } else { last_err = -10; stats_.errors++; }
+    } else if (type == NAL_PPS) {
+      Pps p;
+      if (parse_pps (br, p, D.sps)) D.pps[p.id] = p; else { last_err = -11; stats_.errors++; }
+    } else if (type == NAL_SLICE || type == NAL_IDR) {
+      SliceHeader sh;
+      const int rc = parse_slice_header (br, ref_idc, type, D.sps, D.pps, sh);
+      if (rc < 0) { last_err = rc; stats_.errors++; continue; }
+      const Pps& pps = D.pps[sh.pps_id];
+      const Sps& sps = D.sps[pps.sps_id];
+      if (pps.cabac) { last_err = -20; stats_.errors++; continue; }      // CABAC parse: not built yet
+      if (sps.scaling_matrix_present || pps.scaling_matrix_present) { last_err = -21; stats_.errors++; continue; }
+      if (D.open && D.is_new_picture (D.sh0, sh)) D.finish_picture (this);
+      if (!D.open) {
+        if (D.activate (sps) < 0) { last_err = -30; continue; }
+        D.S = &D.sps[pps.sps_id]; D.P = &D.pps[sh.pps_id]; D.sh = sh; D.ts = timestamp;
+        D.start_picture (this);
+      } else { D.S = &D.sps[pps.sps_id]; D.P = &D.pps[sh.pps_id]; D.sh = sh; }
+      if (sh.first_mb >= D.n_mbs) { last_err = -1; stats_.errors++; continue; }
+      D.slice_no = (int)D.slices.size();
+      // slice record
+      lh264_slice_rec sr;
+      memset (&sr, 0, sizeof (sr));
+      sr.first_mb = sh.first_mb;
+      sr.slice_type = (uint8_t)sh.slice_type;
+      sr.disable_deblocking_idc = (uint8_t)sh.disable_deblocking_idc;
+      sr.alpha_c0_offset = (int8_t)sh.alpha_c0_offset; sr.beta_offset = (int8_t)sh.beta_offset;
+      sr.num_ref_idx_l0 = (uint8_t)sh.num_ref_idx_l0;
+      if (sh.slice_type == SLICE_P) {
+        D.build_list0();
+        if (getenv("LH264_DEBUG")) { fprintf(stderr, "slice fn=%d nref=%d refs=%zu mods:", sh.frame_num, sh.num_ref_idx_l0, D.refs.size()); for (auto& mm : sh.mods) fprintf(stderr, " (%d,%u)", mm.op, mm.val); fprintf(stderr, " | refs:"); for (auto& r : D.refs) fprintf(stderr, " [slot %d fn %d long %d idx %d]", r.slot, r.frame_num, r.is_long, r.long_idx); fprintf(stderr, " | mmco:"); for (auto& mm : sh.mmcos) fprintf(stderr, " (%d,%u,%u)", mm.op, mm.a, mm.b); fprintf(stderr, "\n"); }
+        const int fallback = D.list0[0] ? D.list0[0]->slot : (D.refs.empty() ? 0 : D.refs.back().slot);
+        for (int i = 0; i < LH264_MAX_REFS; i++) sr.ref_slot[i] = (int16_t) (D.list0[i] ? D.list0[i]->slot : fallback);
+        // explicit WP is "on" in the reference only when some weight differs from the default
+        // (bUseWeightPredictionFlag); identical results either way, so keep it simple: on iff signalled
+        if (sh.has_wp) {
+          sr.weighted_pred = 1;
+          sr.luma_log2_denom = (uint8_t)sh.luma_log2_denom; sr.chroma_log2_denom = (uint8_t)sh.chroma_log2_denom;
+          for (int i = 0; i < LH264_MAX_REFS && i < sh.num_ref_idx_l0; i++) {
+            sr.luma_weight[i] = (int16_t)sh.luma_weight[i]; sr.luma_offset[i] = (int16_t)sh.luma_offset[i];
+            for (int c = 0; c < 2; c++) { sr.chroma_weight[i][c] = (int16_t)sh.chroma_weight[i][c]; sr.chroma_offset[i][c] = (int16_t)sh.chroma_offset[i][c]; }
+          }
+        }
+      }
+      D.slices.push_back (sr);
+      stats_.slices++;
+      br.seek (sh.header_bits);
+      if (D.parse_slice_data (br, this) < 0) last_err = -40;
+      if (D.decoded >= D.n_mbs) D.finish_picture (this);
+    } else if (type == NAL_END_SEQ || type == NAL_END_STREAM) {
+      D.finish_picture (this);
+    }
+  }
+  return last_err;
+}
+
+} // namespace lh264host

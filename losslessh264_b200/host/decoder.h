@@ -1,0 +1,81 @@
+// decoder.h — host decoder core: NAL -> parameter sets / slices -> per-picture hand-off records.
+//
+// This is the HOST side of the hot path (it stays on the CPU by design; one instance per
+// stream, instances are independent so N host threads can each own one).  It plays the role of
+// the reference's decoder framework + MB parse:
+//   WelsDecodeBs            codec/decoder/core/src/decoder.cpp:656-859
+//   DecodeCurrentAccessUnit codec/decoder/core/src/decoder_core.cpp:2118-2417
+//   WelsDecodeSlice / WelsActualDecodeMbCavlc{I,P}Slice  decode_slice.cpp:2959-3171, :3173-3984
+//   parse_mb_syn_cavlc.cpp, mv_pred.cpp (PredMv :46, PredPSkipMvFromNeighbor :197, 16x8 :244, 8x16 :267)
+//   manage_dec_ref.cpp (WelsInitRefList :112, WelsReorderRefList :174, WelsMarkAsRef :254)
+// and produces, instead of calling WelsTargetSliceConstruction per slice, one
+// lh264_picture_desc per coded picture that a PictureSink consumes (GPU sink = the product;
+// dump sink = tests).  Written from the H.264 specification, not from the reference sources.
+#pragma once
+#include <stdint.h>
+#include <vector>
+#include <memory>
+#include "../../include/lh264_b200.h"
+#include "h264_syntax.h"
+
+namespace lh264host {
+
+struct DecodedPictureInfo {
+  int mb_w, mb_h;
+  int crop_x, crop_y, width, height;    // cropped output window (luma samples)
+  int frame_num, poc_lsb, idr_pic_id, nal_ref_idc;
+  int slot;
+  int serial;
+  bool complete;                         // every macroblock was decoded
+  unsigned long long timestamp;
+};
+
+// Per-MB side record for the recompression model (filled by the parser; reference:
+// DecodedMacroblock, codec/decoder/core/inc/decoded_macroblock.h:4-104).
+struct ModelMbSide {
+  int16_t mvd[16][2];        // as parsed, per 4x4 block in raster order (partition's first block and replicated)
+  int8_t  pred_mode[16];     // signalled intra 4x4/8x8 modes (z order), before availability resolution
+  int8_t  pred_mode_pred[16];// predicted mode for each block
+  int16_t skip_run;          // mb_skip_run read before this MB (-1 if none)
+  int8_t  qp_delta;
+  uint8_t i16_mode_raw, chroma_mode_raw;
+  uint8_t reserved;
+};
+
+class PictureSink {
+ public:
+  virtual ~PictureSink() {}
+  // geometry changed (new SPS activated): (re)allocate picture storage with n_slots slots
+  virtual int configure (int mb_w, int mb_h, int n_slots) = 0;
+  // one complete coded picture in hand-off form; pointers valid until the call returns
+  virtual int submit (const lh264_picture_desc& pic, const DecodedPictureInfo& info) = 0;
+  // host-side error concealment: copy slot src -> dst (whole picture)
+  virtual int copy_slot (int dst, int src) { (void)dst; (void)src; return 0; }
+};
+
+struct DecoderStats { uint64_t nals = 0, slices = 0, pictures = 0, mbs = 0, coef_blocks = 0, errors = 0; };
+
+class Decoder {
+ public:
+  explicit Decoder (PictureSink* sink);
+  ~Decoder();
+  // Feeds bytes holding zero or more complete Annex-B NAL units.  Returns 0 or a negative error
+  // for the LAST failing NAL (decoding continues with the next NAL).
+  int decode (const uint8_t* data, size_t len, unsigned long long timestamp = 0);
+  // Flushes a picture still pending (end of stream).
+  int flush();
+  const DecoderStats& stats() const { return stats_; }
+  // pictures completed by the last decode()/flush() call, in output order
+  const std::vector<DecodedPictureInfo>& output() const { return out_; }
+  void clear_output() { out_.clear(); }
+  bool keep_model_side = false;          // fill ModelMbSide records
+  const std::vector<ModelMbSide>& model_side() const;
+
+ private:
+  struct Impl;
+  std::unique_ptr<Impl> d_;
+  DecoderStats stats_;
+  std::vector<DecodedPictureInfo> out_;
+};
+
+} // namespace lh264host

@@ -1,0 +1,227 @@
+// h264_syntax.cpp — see h264_syntax.h.  H.264 clauses 7.3.1 (NAL), 7.3.2.1 (SPS), 7.3.2.2 (PPS),
+// 7.3.3 (slice header), B.1 (byte stream).
+#include "h264_syntax.h"
+#include <string.h>
+
+namespace lh264host {
+
+void split_annexb (const uint8_t* d, size_t len, std::vector<NalSpan>& out) {
+  out.clear();
+  size_t i = 0;
+  // find first start code
+  auto find_sc = [&] (size_t from, size_t& sc_len) -> size_t {
+    for (size_t k = from; k + 3 <= len; k++) {
+      if (d[k] == 0 && d[k + 1] == 0) {
+        if (d[k + 2] == 1) { sc_len = 3; return k; }
+        if (k + 4 <= len && d[k + 2] == 0 && d[k + 3] == 1) { sc_len = 4; return k; }
+      }
+    }
+    sc_len = 0;
+    return len;
+  };
+  size_t scl = 0;
+  i = find_sc (0, scl);
+  while (i < len) {
+    const size_t start = i + scl;
+    size_t nscl = 0;
+    const size_t next = find_sc (start, nscl);
+    size_t end = next;
+    while (end > start && d[end - 1] == 0) end--;       // trailing_zero_8bits
+    if (end > start) out.push_back (NalSpan{d + start, end - start});
+    i = next; scl = nscl;
+  }
+}
+
+size_t unescape_nal (const uint8_t* p, size_t len, std::vector<uint8_t>& out) {
+  out.resize (len + 8);
+  size_t o = 0;
+  int zeros = 0;
+  for (size_t i = 0; i < len; i++) {
+    const uint8_t b = p[i];
+    if (zeros >= 2 && b == 3) { zeros = 0; continue; }   // emulation_prevention_three_byte
+    out[o++] = b;
+    zeros = b == 0 ? zeros + 1 : 0;
+  }
+  memset (out.data() + o, 0, 8);
+  out.resize (o + 8);
+  return o;
+}
+
+static void skip_scaling_list (BitReader& br, int size) {
+  int last = 8, next = 8;
+  for (int j = 0; j < size; j++) {
+    if (next != 0) next = (last + br.se() + 256) % 256;
+    last = next == 0 ? last : next;
+  }
+}
+
+bool parse_sps (BitReader& br, Sps& s) {
+  s = Sps();
+  s.profile_idc = br.u (8);
+  s.constraint_flags = br.u (8);
+  s.level_idc = br.u (8);
+  s.id = br.ue();
+  if (s.id < 0 || s.id > 31) return false;
+  const int p = s.profile_idc;
+  if (p == 100 || p == 110 || p == 122 || p == 244 || p == 44 || p == 83 || p == 86 || p == 118 || p == 128) {
+    s.chroma_format_idc = br.ue();
+    if (s.chroma_format_idc == 3) br.u1();
+    const int bdl = br.ue(), bdc = br.ue();
+    br.u1();                                       // qpprime_y_zero_transform_bypass_flag
+    if (br.u1()) {                                 // seq_scaling_matrix_present_flag
+      s.scaling_matrix_present = true;
+      for (int i = 0; i < (s.chroma_format_idc != 3 ? 8 : 12); i++) if (br.u1()) skip_scaling_list (br, i < 6 ? 16 : 64);
+    }
+    if (s.chroma_format_idc != 1 || bdl != 0 || bdc != 0) return false;   // 4:2:0 8-bit only
+  }
+  s.log2_max_frame_num = br.ue() + 4;
+  s.poc_type = br.ue();
+  if (s.poc_type == 0) s.log2_max_poc_lsb = br.ue() + 4;
+  else if (s.poc_type == 1) {
+    s.delta_pic_order_always_zero = br.u1();
+    s.offset_for_non_ref_pic = br.se();
+    s.offset_for_top_to_bottom = br.se();
+    s.num_ref_frames_in_poc_cycle = br.ue();
+    if (s.num_ref_frames_in_poc_cycle > 255) return false;
+    for (int i = 0; i < s.num_ref_frames_in_poc_cycle; i++) s.offset_for_ref_frame[i] = br.se();
+  } else if (s.poc_type != 2) return false;
+  s.max_num_ref_frames = br.ue();
+  s.gaps_in_frame_num_allowed = br.u1();
+  s.mb_w = br.ue() + 1;
+  s.mb_h = br.ue() + 1;
+  s.frame_mbs_only = br.u1();
+  if (!s.frame_mbs_only) { br.u1(); return false; }   // interlace is outside the reference decoder's scope too
+  s.direct_8x8_inference = br.u1();
+  if (br.u1()) {                                      // frame_cropping_flag (4:2:0: units of 2 samples)
+    s.crop_left = 2 * br.ue(); s.crop_right = 2 * br.ue(); s.crop_top = 2 * br.ue(); s.crop_bottom = 2 * br.ue();
+  }
+  // vui_parameters: nothing the reconstruction path needs
+  if (br.overrun() || s.mb_w <= 0 || s.mb_h <= 0 || s.mb_w > 1024 || s.mb_h > 1024 || s.max_num_ref_frames > 16) return false;
+  s.valid = true;
+  return true;
+}
+
+bool parse_pps (BitReader& br, Pps& p, const Sps* sps_table) {
+  p = Pps();
+  p.id = br.ue();
+  p.sps_id = br.ue();
+  if (p.id < 0 || p.id > 255 || p.sps_id < 0 || p.sps_id > 31) return false;
+  p.cabac = br.u1();
+  p.bottom_field_pic_order = br.u1();
+  p.num_slice_groups = br.ue() + 1;
+  if (p.num_slice_groups > 1) {
+    // slice groups (FMO) are parsed so the rest of the PPS stays aligned; decoding them is a "next" row
+    const int type = br.ue();
+    if (type == 0) for (int i = 0; i < p.num_slice_groups; i++) br.ue();
+    else if (type == 2) for (int i = 0; i < p.num_slice_groups - 1; i++) { br.ue(); br.ue(); }
+    else if (type >= 3 && type <= 5) { br.u1(); br.ue(); }
+    else if (type == 6) {
+      const int n = br.ue() + 1;
+      int bits = 0;
+      while ((1 << bits) < p.num_slice_groups) bits++;
+      for (int i = 0; i < n; i++) br.u (bits);
+    }
+  }
+  p.num_ref_idx_l0_default = br.ue() + 1;
+  p.num_ref_idx_l1_default = br.ue() + 1;
+  p.weighted_pred = br.u1();
+  p.weighted_bipred_idc = br.u (2);
+  p.pic_init_qp = 26 + br.se();
+  p.pic_init_qs = 26 + br.se();
+  p.chroma_qp_index_offset = br.se();
+  p.second_chroma_qp_index_offset = p.chroma_qp_index_offset;
+  p.deblocking_filter_control_present = br.u1();
+  p.constrained_intra_pred = br.u1();
+  p.redundant_pic_cnt_present = br.u1();
+  if (br.more_rbsp_data()) {
+    p.transform_8x8_mode = br.u1();
+    if (br.u1()) {                                    // pic_scaling_matrix_present_flag
+      p.scaling_matrix_present = true;
+      for (int i = 0; i < 6 + (p.transform_8x8_mode ? 2 : 0); i++) if (br.u1()) skip_scaling_list (br, i < 6 ? 16 : 64);
+    }
+    p.second_chroma_qp_index_offset = br.se();
+  }
+  (void)sps_table;
+  if (br.overrun()) return false;
+  p.valid = true;
+  return true;
+}
+
+int parse_slice_header (BitReader& br, int nal_ref_idc, int nal_type, const Sps* sps_table, const Pps* pps_table, SliceHeader& sh) {
+  sh = SliceHeader();
+  sh.nal_ref_idc = nal_ref_idc; sh.nal_type = nal_type; sh.idr = nal_type == NAL_IDR;
+  sh.first_mb = br.ue();
+  int st = br.ue();
+  if (st > 9) return -1;
+  sh.slice_type = st % 5;
+  sh.pps_id = br.ue();
+  if (sh.pps_id < 0 || sh.pps_id > 255 || !pps_table[sh.pps_id].valid) return -2;
+  const Pps& pps = pps_table[sh.pps_id];
+  if (!sps_table[pps.sps_id].valid) return -2;
+  const Sps& sps = sps_table[pps.sps_id];
+  if (sh.slice_type != SLICE_P && sh.slice_type != SLICE_I) return -3;     // B/SP/SI: not in the reference decoder either
+  sh.frame_num = br.u (sps.log2_max_frame_num);
+  if (sh.idr) sh.idr_pic_id = br.ue();
+  if (sps.poc_type == 0) {
+    sh.poc_lsb = br.u (sps.log2_max_poc_lsb);
+    if (pps.bottom_field_pic_order) sh.delta_poc_bottom = br.se();
+  } else if (sps.poc_type == 1 && !sps.delta_pic_order_always_zero) {
+    sh.delta_poc[0] = br.se();
+    if (pps.bottom_field_pic_order) sh.delta_poc[1] = br.se();
+  }
+  if (pps.redundant_pic_cnt_present) sh.redundant_pic_cnt = br.ue();
+  sh.num_ref_idx_l0 = pps.num_ref_idx_l0_default;
+  if (sh.slice_type == SLICE_P) {
+    if (br.u1()) sh.num_ref_idx_l0 = br.ue() + 1;     // num_ref_idx_active_override_flag
+    if (sh.num_ref_idx_l0 < 1 || sh.num_ref_idx_l0 > 32) return -1;
+    if (br.u1()) {                                    // ref_pic_list_modification_flag_l0
+      for (;;) {
+        const int op = br.ue();
+        if (op == 3) break;
+        if (op > 3 || sh.mods.size() > 64) return -1;
+        sh.mods.push_back (RefPicListMod{op, br.ue()});
+      }
+    }
+    if (pps.weighted_pred) {
+      sh.has_wp = true;
+      sh.luma_log2_denom = br.ue();
+      sh.chroma_log2_denom = br.ue();
+      for (int i = 0; i < sh.num_ref_idx_l0; i++) {
+        sh.luma_weight[i] = 1 << sh.luma_log2_denom; sh.luma_offset[i] = 0;
+        for (int c = 0; c < 2; c++) { sh.chroma_weight[i][c] = 1 << sh.chroma_log2_denom; sh.chroma_offset[i][c] = 0; }
+        if (br.u1()) { sh.luma_weight[i] = br.se(); sh.luma_offset[i] = br.se(); }
+        if (br.u1()) for (int c = 0; c < 2; c++) { sh.chroma_weight[i][c] = br.se(); sh.chroma_offset[i][c] = br.se(); }
+      }
+    }
+  } else sh.num_ref_idx_l0 = 0;
+  if (nal_ref_idc != 0) {                             // dec_ref_pic_marking()
+    if (sh.idr) { sh.no_output_of_prior_pics = br.u1(); sh.long_term_reference_flag = br.u1(); }
+    else if ((sh.adaptive_marking = br.u1())) {
+      for (;;) {
+        const int op = br.ue();
+        if (op == 0) break;
+        if (op > 6 || sh.mmcos.size() > 64) return -1;
+        Mmco m{op, 0, 0};
+        if (op == 1 || op == 3) m.a = br.ue();        // difference_of_pic_nums_minus1
+        if (op == 2) m.a = br.ue();                   // long_term_pic_num
+        if (op == 3 || op == 6) m.b = br.ue();        // long_term_frame_idx
+        if (op == 4) m.a = br.ue();                   // max_long_term_frame_idx_plus1
+        sh.mmcos.push_back (m);
+      }
+    }
+  }
+  if (pps.cabac && sh.slice_type != SLICE_I) sh.cabac_init_idc = br.ue();
+  sh.slice_qp = pps.pic_init_qp + br.se();
+  if (sh.slice_qp < 0 || sh.slice_qp > 51) return -1;
+  if (pps.deblocking_filter_control_present) {
+    sh.disable_deblocking_idc = br.ue();
+    if (sh.disable_deblocking_idc > 2) return -1;
+    if (sh.disable_deblocking_idc != 1) { sh.alpha_c0_offset = 2 * br.se(); sh.beta_offset = 2 * br.se(); }
+  }
+  if (pps.num_slice_groups > 1) return -4;            // FMO: "next" row N3
+  if (br.overrun()) return -1;
+  sh.header_bits = br.pos();
+  return 0;
+}
+
+} // namespace lh264host

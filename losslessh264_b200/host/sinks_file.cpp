@@ -1,0 +1,43 @@
+// sinks_file.cpp — LhfbSink, see sinks.h.
+#include "sinks.h"
+#include <string.h>
+
+namespace lh264host {
+
+LhfbSink::LhfbSink (const char* path) : f_ (fopen (path, "wb")) {}
+LhfbSink::~LhfbSink() { if (f_) fclose (f_); }
+int LhfbSink::configure (int mb_w, int mb_h, int) { mb_w_ = mb_w; mb_h_ = mb_h; return 0; }
+int LhfbSink::submit (const lh264_picture_desc& pic, const DecodedPictureInfo& info) {
+  if (!f_) return -1;
+  auto w32 = [&] (int32_t v) { fwrite (&v, 4, 1, f_); };
+  for (int s = 0; s < pic.n_slices; s++) {
+    const lh264_slice_rec& sl = pic.slices[s];
+    w32 (0x4246484c); w32 (1);
+    w32 (mb_w_); w32 (mb_h_); w32 (pic.cur_slot); w32 (info.frame_num); w32 (info.poc_lsb); w32 (info.idr_pic_id); w32 (info.nal_ref_idc); w32 (info.serial);
+    fwrite (&sl, sizeof (sl), 1, f_);
+    w32 (sl.num_mbs);
+    uint32_t lo = 0xffffffffu, hi = 0;
+    for (int i = 0; i < sl.num_mbs; i++) {
+      const lh264_mb_rec& m = pic.mbs[sl.first_mb + i];
+      if (m.coded_mask) { lo = lo < m.coef_off ? lo : m.coef_off; const uint32_t e = m.coef_off + __builtin_popcount (m.coded_mask); hi = hi > e ? hi : e; }
+    }
+    if (lo == 0xffffffffu) lo = hi = 0;
+    for (int i = 0; i < sl.num_mbs; i++) {
+      lh264_mb_rec m = pic.mbs[sl.first_mb + i];
+      m.slice_idx = 0;
+      if (m.coded_mask) m.coef_off -= lo; else m.coef_off = 0;
+      w32 (sl.first_mb + i);
+      fwrite (&m, sizeof (m), 1, f_);
+    }
+    w32 ((int32_t) (hi - lo));
+    if (hi > lo) {
+      fwrite (pic.coefs + (size_t)lo * 16, 32, hi - lo, f_);
+      std::vector<int16_t> z ((size_t) (hi - lo) * 16, 0);
+      fwrite (z.data(), 32, hi - lo, f_);
+    }
+    w32 (0);
+  }
+  return 0;
+}
+
+} // namespace lh264host

@@ -1,0 +1,46 @@
+// tool_parse_dump.cpp — CPU-only tool: parses an Annex-B stream with the host decoder and writes
+// the hand-off records as .lhfb (no reconstruction).  Used by the CPU tests to compare the host
+// parser with the reference's own records and to feed the oracle.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <chrono>
+#include <vector>
+#include "decoder.h"
+#include "sinks.h"
+#include "cavlc.h"
+
+using namespace lh264host;
+
+int main (int argc, char** argv) {
+  if (argc < 3) { fprintf (stderr, "usage: %s in.264 out.lhfb [repeat]\n", argv[0]); return 2; }
+  if (!cavlc_selfcheck()) { fprintf (stderr, "CAVLC tables failed the Kraft/prefix self-check\n"); return 3; }
+  FILE* f = fopen (argv[1], "rb");
+  if (!f) { perror (argv[1]); return 1; }
+  std::vector<uint8_t> buf;
+  uint8_t tmp[65536];
+  size_t n;
+  while ((n = fread (tmp, 1, sizeof (tmp), f)) > 0) buf.insert (buf.end(), tmp, tmp + n);
+  fclose (f);
+  const int repeat = argc > 3 ? atoi (argv[3]) : 1;
+  double best = 1e30;
+  DecoderStats st;
+  for (int it = 0; it < repeat; it++) {
+    LhfbSink sink (it == 0 ? argv[2] : "/dev/null");
+    Decoder dec (&sink);
+    const auto t0 = std::chrono::steady_clock::now();
+    dec.decode (buf.data(), buf.size());
+    dec.flush();
+    const double dt = std::chrono::duration<double> (std::chrono::steady_clock::now() - t0).count();
+    if (dt < best) best = dt;
+    st = dec.stats();
+    if (it == 0 && !dec.output().empty()) {
+      const DecodedPictureInfo& o = dec.output().front();
+      fprintf (stderr, "crop %d %d %d %d\n", o.crop_x, o.crop_y, o.width, o.height);
+    }
+  }
+  fprintf (stderr, "nals %llu slices %llu pictures %llu mbs %llu coef_blocks %llu errors %llu  parse %.4f s (%.1f pictures/s)\n",
+           (unsigned long long)st.nals, (unsigned long long)st.slices, (unsigned long long)st.pictures, (unsigned long long)st.mbs,
+           (unsigned long long)st.coef_blocks, (unsigned long long)st.errors, best, st.pictures / best);
+  return st.errors ? 4 : 0;
+}
