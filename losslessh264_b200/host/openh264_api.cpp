@@ -1,0 +1,169 @@
+// openh264_api.cpp — libopenh264_lh264.so: the OpenH264 decoder API (include/lh264_codec_api.h)
+// over the host decoder + GPU reconstruction.  Mirrors CWelsDecoder
+// (codec/decoder/plus/src/welsDecoderExt.cpp:189-708): same entry points, argument meaning and
+// return-code conventions; the macroblock reconstruction behind it runs on the B200 through the
+// C ABI of include/lh264_b200.h (no CPU fallback: Initialize fails without a CUDA device).
+#include <string.h>
+#include <stdlib.h>
+#include <deque>
+#include <new>
+#include "../../include/lh264_codec_api.h"
+#include "decoder.h"
+#include "sinks.h"
+
+using namespace lh264host;
+
+namespace {
+
+class CLh264Decoder : public ISVCDecoder {
+ public:
+  CLh264Decoder() {}
+  ~CLh264Decoder() override { Uninitialize(); }
+
+  long Initialize (const SDecodingParam* p) override {
+    if (!p) return cmInitParaError;
+    if (p->bParseOnly) return cmUnsupportedData;
+    Uninitialize();
+    ec_idc_ = p->eEcActiveIdc;
+    sink_ = new (std::nothrow) GpuSink (nullptr, device_);
+    if (!sink_ || !sink_->ctx()) { delete sink_; sink_ = nullptr; return cmInitParaError; }   // no device: fail loudly
+    dec_ = new (std::nothrow) Decoder (sink_);
+    if (!dec_) return cmMallocMemeError;
+    memset (&stat_, 0, sizeof (stat_));
+    return cmResultSuccess;
+  }
+  long Uninitialize() override {
+    delete dec_; dec_ = nullptr;
+    delete sink_; sink_ = nullptr;
+    if (out_) { lh264_host_free (out_); out_ = nullptr; out_cap_ = 0; }
+    queue_.clear();
+    return cmResultSuccess;
+  }
+
+  DECODING_STATE DecodeFrame2 (const unsigned char* src, const int len, unsigned char** ppDst, SBufferInfo* info) override {
+    return decode (src, len, ppDst, info, false);
+  }
+  // welsDecoderExt.cpp:408-430: DecodeFrame2(src) then DecodeFrame2(NULL, 0), return codes OR-ed
+  DECODING_STATE DecodeFrameNoDelay (const unsigned char* src, const int len, unsigned char** ppDst, SBufferInfo* info) override {
+    return decode (src, len, ppDst, info, true);
+  }
+  // welsDecoderExt.cpp:618-642
+  DECODING_STATE DecodeFrame (const unsigned char* src, const int len, unsigned char** ppDst, int* stride, int& w, int& h) override {
+    SBufferInfo bi;
+    memset (&bi, 0, sizeof (bi));
+    DECODING_STATE st = DecodeFrame2 (src, len, ppDst, &bi);
+    if (bi.iBufferStatus == 1) {
+      stride[0] = bi.UsrData.sSystemBuffer.iStride[0]; stride[1] = bi.UsrData.sSystemBuffer.iStride[1];
+      w = bi.UsrData.sSystemBuffer.iWidth; h = bi.UsrData.sSystemBuffer.iHeight;
+    }
+    return st;
+  }
+  DECODING_STATE DecodeParser (const unsigned char*, const int, SParserBsInfo*) override { return dsInitialOptExpected; }
+  DECODING_STATE DecodeFrameEx (const unsigned char*, const int, unsigned char*, int, int& iDstLen, int&, int&, int&) override { iDstLen = 0; return dsErrorFree; }
+
+  long SetOption (DECODER_OPTION id, void* opt) override {
+    if (!opt) return cmInitParaError;
+    switch (id) {
+    case DECODER_OPTION_DATAFORMAT: return * (int*)opt == videoFormatI420 ? cmResultSuccess : cmInitParaError;
+    case DECODER_OPTION_END_OF_STREAM: eos_ = * (bool*)opt; return cmResultSuccess;
+    case DECODER_OPTION_ERROR_CON_IDC: ec_idc_ = * (int*)opt; return cmResultSuccess;
+    case DECODER_OPTION_TRACE_LEVEL: trace_level_ = * (int*)opt; return cmResultSuccess;
+    case DECODER_OPTION_TRACE_CALLBACK: case DECODER_OPTION_TRACE_CALLBACK_CONTEXT: return cmResultSuccess;
+    default: return cmInitParaError;
+    }
+  }
+  long GetOption (DECODER_OPTION id, void* opt) override {
+    if (!opt) return cmInitParaError;
+    switch (id) {
+    case DECODER_OPTION_DATAFORMAT: * (int*)opt = videoFormatI420; return cmResultSuccess;
+    case DECODER_OPTION_END_OF_STREAM: * (int*)opt = eos_; return cmResultSuccess;
+    case DECODER_OPTION_VCL_NAL: * (int*)opt = last_vcl_; return cmResultSuccess;
+    case DECODER_OPTION_TEMPORAL_ID: * (int*)opt = 0; return cmResultSuccess;
+    case DECODER_OPTION_FRAME_NUM: * (int*)opt = last_frame_num_; return cmResultSuccess;
+    case DECODER_OPTION_IDR_PIC_ID: * (int*)opt = last_idr_pic_id_; return cmResultSuccess;
+    case DECODER_OPTION_LTR_MARKING_FLAG: * (bool*)opt = false; return cmResultSuccess;
+    case DECODER_OPTION_LTR_MARKED_FRAME_NUM: * (int*)opt = 0; return cmResultSuccess;
+    case DECODER_OPTION_ERROR_CON_IDC: * (int*)opt = ec_idc_; return cmResultSuccess;
+    case DECODER_OPTION_GET_STATISTICS: memcpy (opt, &stat_, sizeof (stat_)); return cmResultSuccess;
+    default: return cmInitParaError;
+    }
+  }
+
+ private:
+  DECODING_STATE decode (const unsigned char* src, int len, unsigned char** ppDst, SBufferInfo* info, bool no_delay) {
+    if (!dec_ || !sink_) return dsInitialOptExpected;
+    if (!ppDst || !info) return dsInvalidArgument;
+    const unsigned long long ts = info->uiInBsTimeStamp;       // welsDecoderExt.cpp:463-465
+    memset (info, 0, sizeof (*info));
+    info->uiInBsTimeStamp = ts;
+    ppDst[0] = ppDst[1] = ppDst[2] = nullptr;
+    int state = dsErrorFree;
+    dec_->clear_output();
+    if (src && len > 0) {
+      const int rc = dec_->decode (src, (size_t)len, ts);
+      if (rc == -2) state |= dsNoParamSets;
+      else if (rc < 0) state |= dsBitstreamError;
+      last_vcl_ = 1;
+    } else if (eos_ || !no_delay) {
+      if (eos_) dec_->flush();                                   // end of stream: emit what is pending
+    }
+    for (const DecodedPictureInfo& o : dec_->output()) queue_.push_back (o);
+    if (!queue_.empty()) {
+      const DecodedPictureInfo o = queue_.front();
+      queue_.pop_front();
+      const int cw = (o.width + 1) >> 1, ch = (o.height + 1) >> 1;
+      const size_t need = (size_t)o.width * o.height + 2 * (size_t)cw * ch;
+      if (need > out_cap_) {
+        if (out_) lh264_host_free (out_);
+        out_ = (unsigned char*)lh264_host_alloc (need);
+        out_cap_ = out_ ? need : 0;
+        if (!out_) return (DECODING_STATE) (state | dsOutOfMemory);
+      }
+      unsigned char* y = out_, *u = y + (size_t)o.width * o.height, *v = u + (size_t)cw * ch;
+      if (sink_->read (o, y, o.width, u, v, cw) != LH264_OK) return (DECODING_STATE) (state | dsOutOfMemory);
+      ppDst[0] = y; ppDst[1] = u; ppDst[2] = v;
+      info->iBufferStatus = 1;
+      info->uiOutYuvTimeStamp = o.timestamp;
+      info->UsrData.sSystemBuffer.iWidth = o.width; info->UsrData.sSystemBuffer.iHeight = o.height;
+      info->UsrData.sSystemBuffer.iFormat = videoFormatI420;
+      info->UsrData.sSystemBuffer.iStride[0] = o.width; info->UsrData.sSystemBuffer.iStride[1] = cw;
+      last_frame_num_ = o.frame_num; last_idr_pic_id_ = o.idr_pic_id;
+      stat_.uiDecodedFrameCount++;
+      if (stat_.uiWidth != (unsigned)o.width || stat_.uiHeight != (unsigned)o.height) { stat_.uiResolutionChangeTimes++; stat_.uiWidth = o.width; stat_.uiHeight = o.height; }
+      if (!o.complete) state |= dsDataErrorConcealed;
+    }
+    return (DECODING_STATE)state;
+  }
+
+  Decoder* dec_ = nullptr;
+  GpuSink* sink_ = nullptr;
+  std::deque<DecodedPictureInfo> queue_;
+  unsigned char* out_ = nullptr;
+  size_t out_cap_ = 0;
+  bool eos_ = false;
+  int ec_idc_ = ERROR_CON_SLICE_COPY, trace_level_ = 0, device_ = 0;
+  int last_vcl_ = 0, last_frame_num_ = -1, last_idr_pic_id_ = 0;
+  SDecoderStatistics stat_;
+};
+
+} // namespace
+
+extern "C" {
+
+long WelsCreateDecoder (ISVCDecoder** pp) {
+  if (!pp) return 1;                                  // ERR_INVALID_PARAMETERS
+  *pp = new (std::nothrow) CLh264Decoder();
+  return *pp ? 0 : 2;
+}
+void WelsDestroyDecoder (ISVCDecoder* p) { delete static_cast<CLh264Decoder*> (p); }
+int WelsGetDecoderCapability (SDecoderCapability* c) {   // fixed values, welsDecoderExt.cpp:666-679
+  if (!c) return 1;
+  memset (c, 0, sizeof (*c));
+  c->iProfileIdc = 66; c->iProfileIop = 0xE0; c->iLevelIdc = 32; c->iMaxMbps = 216000; c->iMaxFs = 5120;
+  c->iMaxCpb = 20000; c->iMaxDpb = 20480; c->iMaxBr = 20000; c->bRedPicCap = 0;
+  return 0;
+}
+OpenH264Version WelsGetCodecVersion (void) { OpenH264Version v = {1, 4, 0, 0}; return v; }
+void WelsGetCodecVersionEx (OpenH264Version* v) { if (v) *v = WelsGetCodecVersion(); }
+
+} // extern "C"

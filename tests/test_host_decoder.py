@@ -1,0 +1,64 @@
+"""CPU: the host decoder (NAL/slice/CAVLC parse -> hand-off records) checked end to end through the
+oracle: parsed records -> oracle reconstruction -> SHA1 of the cropped I420 == the reference's SHA1
+(tests/golden/stream_sha1.json: 36 of them are the constants of the reference's
+test/api/decoder_test.cpp:90-128, the rest were measured from the compiled reference)."""
+import hashlib
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from losslessh264_b200.records import n_slots_needed, read_lhfb
+from oracle import oracle
+from streams import LIB_DIR, NOT_YET, SHA1, STREAM_DIR, cavlc_streams
+
+TOOL = os.path.join(LIB_DIR, "lh264_parse_dump")
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _built():
+    subprocess.check_call(["make", "-s", "-C", os.path.join(os.path.dirname(LIB_DIR), "host"), "../_lib/lh264_parse_dump"])
+
+
+def decode_with_oracle(stream, tmp_path):
+    out = os.path.join(tmp_path, "d.lhfb")
+    r = subprocess.run([TOOL, stream, out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    crop = tuple(int(v) for v in re.search(r"crop (\d+) (\d+) (\d+) (\d+)", r.stderr).groups())
+    pics = read_lhfb(out)
+    mb_w, mb_h = pics[0].mb_w, pics[0].mb_h
+    W, H = mb_w * 16, mb_h * 16
+    cx, cy, cw, ch = crop
+    st = oracle.OracleStream(mb_w, mb_h, n_slots_needed(pics))
+    h = hashlib.sha1()
+    for p in pics:
+        o = st.recon(p)
+        h.update(np.ascontiguousarray(o[: W * H].reshape(H, W)[cy : cy + ch, cx : cx + cw]).tobytes())
+        for k in (0, 1):
+            pl = o[W * H + k * W * H // 4 : W * H + (k + 1) * W * H // 4].reshape(H // 2, W // 2)
+            h.update(np.ascontiguousarray(pl[cy // 2 : cy // 2 + ch // 2, cx // 2 : cx // 2 + cw // 2]).tobytes())
+    return h.hexdigest(), len(pics)
+
+
+# the long streams are left to the GPU suite to keep the CPU suite within a few minutes
+CPU_SET = [s for s in cavlc_streams() if s not in ("LS_SVA_D.264", "BA1_FT_C.264", "CI1_FT_B.264", "syn1080p_cbp_ippp_16f.264", "CVPCMNL1_SVA_C.264")]
+
+
+@pytest.mark.parametrize("name", CPU_SET)
+def test_host_parse_plus_oracle_matches_reference_sha1(name, tmp_path):
+    sha, n = decode_with_oracle(os.path.join(STREAM_DIR, name), str(tmp_path))
+    assert sha == SHA1[name]["sha1"], f"{name}: {n} pictures decoded, SHA1 differs from the reference"
+
+
+def test_cavlc_tables_are_prefix_codes(tmp_path):
+    # the tool refuses to run when the Kraft/prefix self-check of its VLC tables fails (exit code 3)
+    r = subprocess.run([TOOL, os.path.join(STREAM_DIR, "SVA_BA2_D.264"), os.path.join(str(tmp_path), "x.lhfb")], capture_output=True)
+    assert r.returncode == 0
+
+
+def test_unsupported_streams_fail_loudly(tmp_path):
+    for name in ("tibbycabac.264",):
+        r = subprocess.run([TOOL, os.path.join(STREAM_DIR, name), os.path.join(str(tmp_path), "x.lhfb")], capture_output=True)
+        assert r.returncode != 0, f"{name} ({NOT_YET[name]}) must be reported as an error, not decoded silently"
