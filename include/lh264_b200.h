@@ -193,7 +193,8 @@ void lh264_batch_free(lh264_ctx* ctx, lh264_resident_batch* batch);
 /* number of kernel launches issued by this context so far                                   */
 uint64_t lh264_kernel_launches(const lh264_ctx* ctx);
 /* accumulated device time (ms, CUDA events on the context stream) of one kernel family
- * since the last reset: 0 inter, 1 intra, 2 deblock, 3 all; reset with family = -1           */
+ * since the last reset: 0 k_recon_rows (inter + intra), 1 unused, 2 k_deblock_rows, 3 all; family = -1 resets and switches the
+ * (synchronising) per-family timing on, family = -2 switches it off                          */
 float lh264_kernel_ms(lh264_ctx* ctx, int family);
 
 /* Copies the cropped I420 picture to host memory (asynchronous unless sync != 0).

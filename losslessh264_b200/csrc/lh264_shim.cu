@@ -14,6 +14,7 @@
 #include <new>
 
 #include "recon_kernels.cuh"
+#include "recon_rows.cuh"
 
 using namespace lh264;
 
@@ -67,10 +68,9 @@ struct BatchDev {                            // device-resident batch
   DevBuf<int16_t> coefs;
   DevBuf<lh264_slice_rec> slices;
   DevBuf<PicDev> pics;
-  DevBuf<int> intra_ids;
-  int n_pics = 0, n_intra_pics = 0;
-  int max_mbs = 0, max_diag = 0, n_waves = 0;
-  void release() { mbs.release(); coefs.release(); slices.release(); pics.release(); intra_ids.release(); }
+  DevBuf<int> row_sync;                      // RowSync header + progress[2][n_pics][max_rows]
+  int n_pics = 0, max_rows = 0;
+  void release() { mbs.release(); coefs.release(); slices.release(); pics.release(); row_sync.release(); }
 };
 
 } // namespace
@@ -78,14 +78,13 @@ struct BatchDev {                            // device-resident batch
 struct lh264_resident_batch { BatchDev dev; };
 
 struct lh264_ctx {
-  int device = 0;
+  int device = 0, n_sm = 148, occ_recon = 2, occ_deblock = 4;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   std::vector<StreamRec> streams;
   BatchDev batch;                            // staging for lh264_recon_submit
   PinBuf<PicDev> h_pics;
-  PinBuf<int> h_intra_ids;
-  cudaEvent_t staged = nullptr;              // h_pics/h_intra_ids consumed by the H2D copy
+  cudaEvent_t staged = nullptr;              // h_pics consumed by the H2D copy
   bool staged_pending = false;
   DevBuf<PackDev> pack_jobs; PinBuf<PackDev> h_pack_jobs; DevBuf<uint8_t> pack_out;
   DevBuf<uint8_t> scratch_a, scratch_b, scratch_c;
@@ -112,6 +111,11 @@ int lh264_ctx_create (lh264_ctx** out, int device, void* cuda_stream) {
   lh264_ctx* c = new (std::nothrow) lh264_ctx();
   if (!c) return fail (LH264_E_NOMEM, "out of host memory");
   c->device = device;
+  cudaDeviceGetAttribute (&c->n_sm, cudaDevAttrMultiProcessorCount, device);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor (&c->occ_recon, k_recon_rows, ROWS_WARPS * 32, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor (&c->occ_deblock, k_deblock_rows, ROWS_WARPS * 32, 0);
+  if (c->occ_recon < 1) c->occ_recon = 1;
+  if (c->occ_deblock < 1) c->occ_deblock = 1;
   if (cuda_stream) c->stream = (cudaStream_t)cuda_stream;
   else { CK (cudaStreamCreateWithFlags (&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
   CK (cudaEventCreateWithFlags (&c->staged, cudaEventDisableTiming));
@@ -125,7 +129,7 @@ void lh264_ctx_destroy (lh264_ctx* c) {
   cudaSetDevice (c->device);
   cudaStreamSynchronize (c->stream);
   for (auto& s : c->streams) if (s.base) cudaFree (s.base);
-  c->batch.release(); c->h_pics.release(); c->h_intra_ids.release();
+  c->batch.release(); c->h_pics.release();
   c->pack_jobs.release(); c->h_pack_jobs.release(); c->pack_out.release();
   c->scratch_a.release(); c->scratch_b.release(); c->scratch_c.release();
   if (c->staged) cudaEventDestroy (c->staged);
@@ -164,7 +168,7 @@ static int check_pic (lh264_ctx* c, const lh264_picture_desc& p) {
 }
 
 // Copies the records of a batch into HBM (async) and fills the device picture table.
-static int stage_batch (lh264_ctx* c, BatchDev& b, PinBuf<PicDev>& h_pics, PinBuf<int>& h_ids, const lh264_picture_desc* pics, int n) {
+static int stage_batch (lh264_ctx* c, BatchDev& b, PinBuf<PicDev>& h_pics, const lh264_picture_desc* pics, int n) {
   size_t tot_mbs = 0, tot_blk = 0, tot_sl = 0;
   for (int i = 0; i < n; i++) {
     int rc = check_pic (c, pics[i]);
@@ -173,11 +177,11 @@ static int stage_batch (lh264_ctx* c, BatchDev& b, PinBuf<PicDev>& h_pics, PinBu
     tot_mbs += (size_t)s.mb_w * s.mb_h; tot_blk += pics[i].n_coef_blocks; tot_sl += pics[i].n_slices;
   }
   CK (b.mbs.reserve (tot_mbs)); CK (b.coefs.reserve (tot_blk * 16 + 16)); CK (b.slices.reserve (tot_sl));
-  CK (b.pics.reserve (n)); CK (b.intra_ids.reserve (n));
+  CK (b.pics.reserve (n));
   if (c->staged_pending) { CK (cudaEventSynchronize (c->staged)); c->staged_pending = false; }
-  CK (h_pics.reserve (n)); CK (h_ids.reserve (n));
+  CK (h_pics.reserve (n));
   size_t o_mb = 0, o_blk = 0, o_sl = 0;
-  b.n_pics = n; b.n_intra_pics = 0; b.max_mbs = 0; b.max_diag = 0; b.n_waves = 0;
+  b.n_pics = n; b.max_rows = 0;
   for (int i = 0; i < n; i++) {
     const lh264_picture_desc& p = pics[i];
     const StreamRec& s = c->streams[p.stream];
@@ -188,37 +192,30 @@ static int stage_batch (lh264_ctx* c, BatchDev& b, PinBuf<PicDev>& h_pics, PinBu
     PicDev& d = h_pics.p[i];
     d.mbs = b.mbs.p + o_mb; d.coefs = b.coefs.p + o_blk * 16; d.slices = b.slices.p + o_sl;
     d.base = s.base; d.slot_stride = s.slot_stride; d.cur_slot = p.cur_slot; d.n_slots = s.n_slots; d.mb_w = s.mb_w; d.mb_h = s.mb_h;
-    // pictures whose every slice is P may still hold intra MBs; a picture takes part in the intra
-    // wavefront unless the producer marks all its slices as "no intra MB" (slice_type 0 and n_intra==0
-    // cannot be told from the records cheaply), so only I/P mix is decided here: always include.
-    h_ids.p[b.n_intra_pics++] = i;
-    b.max_mbs = std::max (b.max_mbs, (int)nmb);
-    b.max_diag = std::max (b.max_diag, std::min (s.mb_h, (s.mb_w + 1) / 2 + 1));
-    b.n_waves = std::max (b.n_waves, (s.mb_w - 1) + 2 * (s.mb_h - 1) + 1);
+    b.max_rows = std::max (b.max_rows, s.mb_h);
     o_mb += nmb; o_blk += p.n_coef_blocks; o_sl += p.n_slices;
   }
   CK (cudaMemcpyAsync (b.pics.p, h_pics.p, n * sizeof (PicDev), cudaMemcpyHostToDevice, c->stream));
-  CK (cudaMemcpyAsync (b.intra_ids.p, h_ids.p, b.n_intra_pics * sizeof (int), cudaMemcpyHostToDevice, c->stream));
   CK (cudaEventRecord (c->staged, c->stream));
   c->staged_pending = true;
+  CK (b.row_sync.reserve (4 + 2 * (size_t)n * b.max_rows));
   return LH264_OK;
 }
 
 static int launch_recon (lh264_ctx* c, BatchDev& b) {
   if (b.n_pics == 0) return LH264_OK;
+  // persistent row kernels: enough warps to fill the machine, never more than there are rows
+  const size_t sync_bytes = (4 + 2 * (size_t)b.n_pics * b.max_rows) * sizeof (int);
+  const long long rows = (long long)b.n_pics * b.max_rows;
+  const int blocks = (int)std::max (1LL, std::min ((long long)c->n_sm * c->occ_recon, (rows + ROWS_WARPS - 1) / ROWS_WARPS));
+  const int dblocks = (int)std::max (1LL, std::min ((long long)c->n_sm * c->occ_deblock, (rows + ROWS_WARPS - 1) / ROWS_WARPS));
   if (c->timing) CK (cudaEventRecord (c->ev[0], c->stream));
-  k_inter<<<dim3 (b.max_mbs, b.n_pics), 128, 0, c->stream>>> (b.pics.p);
+  CK (cudaMemsetAsync (b.row_sync.p, 0, sync_bytes, c->stream));
+  k_recon_rows<<<blocks, ROWS_WARPS * 32, 0, c->stream>>> (b.pics.p, b.n_pics, b.max_rows, reinterpret_cast<RowSync*> (b.row_sync.p));
   c->launches++;
-  if (c->timing) CK (cudaEventRecord (c->ev[1], c->stream));
-  for (int w = 0; w < b.n_waves && b.n_intra_pics; w++) {
-    k_intra<<<dim3 (b.max_diag, b.n_intra_pics), 128, 0, c->stream>>> (b.pics.p, b.intra_ids.p, w);
-    c->launches++;
-  }
-  if (c->timing) CK (cudaEventRecord (c->ev[2], c->stream));
-  for (int w = 0; w < b.n_waves; w++) {
-    k_deblock<<<dim3 ((b.max_diag + 3) / 4, b.n_pics), 128, 0, c->stream>>> (b.pics.p, w);
-    c->launches++;
-  }
+  if (c->timing) { CK (cudaEventRecord (c->ev[1], c->stream)); CK (cudaEventRecord (c->ev[2], c->stream)); }
+  k_deblock_rows<<<dblocks, ROWS_WARPS * 32, 0, c->stream>>> (b.pics.p, b.n_pics, b.max_rows, reinterpret_cast<RowSync*> (b.row_sync.p));
+  c->launches++;
   if (c->timing) {
     CK (cudaEventRecord (c->ev[3], c->stream));
     CK (cudaEventSynchronize (c->ev[3]));
@@ -233,7 +230,7 @@ int lh264_recon_submit (lh264_ctx* c, const lh264_picture_desc* pics, int n_pics
   CK (cudaSetDevice (c->device));
   for (int i = 0; i < n_pics; i++) for (int j = i + 1; j < n_pics; j++)
       if (n_pics <= 64 && pics[i].stream == pics[j].stream) return fail (LH264_E_INVALID, "two pictures of one stream in a batch");
-  int rc = stage_batch (c, c->batch, c->h_pics, c->h_intra_ids, pics, n_pics);
+  int rc = stage_batch (c, c->batch, c->h_pics, pics, n_pics);
   if (rc) return rc;
   return launch_recon (c, c->batch);
 }
@@ -243,7 +240,7 @@ int lh264_batch_upload (lh264_ctx* c, const lh264_picture_desc* pics, int n_pics
   CK (cudaSetDevice (c->device));
   lh264_resident_batch* rb = new (std::nothrow) lh264_resident_batch();
   if (!rb) return fail (LH264_E_NOMEM, "out of host memory");
-  int rc = stage_batch (c, rb->dev, c->h_pics, c->h_intra_ids, pics, n_pics);
+  int rc = stage_batch (c, rb->dev, c->h_pics, pics, n_pics);
   if (rc) { rb->dev.release(); delete rb; return rc; }
   CK (cudaStreamSynchronize (c->stream));
   c->staged_pending = false;
@@ -265,6 +262,7 @@ void lh264_batch_free (lh264_ctx* c, lh264_resident_batch* b) {
 uint64_t lh264_kernel_launches (const lh264_ctx* c) { return c ? c->launches : 0; }
 float lh264_kernel_ms (lh264_ctx* c, int family) {
   if (!c) return 0.f;
+  if (family == -2) { c->timing = false; return 0.f; }
   if (family < 0) { c->ms[0] = c->ms[1] = c->ms[2] = 0.f; c->timing = true; return 0.f; }
   if (family < 3) return c->ms[family];
   return c->ms[0] + c->ms[1] + c->ms[2];

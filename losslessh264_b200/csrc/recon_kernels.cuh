@@ -1,15 +1,9 @@
-// recon_kernels.cuh — the sm_100a reconstruction kernels (inter pass, intra wavefront, deblocking
-// wavefront, output packing).  Included by lh264_shim.cu.
+// recon_kernels.cuh — building blocks of the sm_100a reconstruction kernels.  Included by lh264_shim.cu.
 //
-// Work decomposition per picture batch (one picture per independent stream):
-//   k_inter    all inter MBs of all pictures, fully parallel, one 128-thread CTA per MB:
-//              64 threads = 16 4x4 luma blocks x 4 rows (9x9 reference window per block staged in
-//              shared memory with clamp-at-read borders), 32 threads = chroma 2x2 blocks,
-//              24 threads = dequant + inverse transform of the 24 coefficient blocks.
-//   k_intra    anti-diagonal wave d = x + 2y (left, top, top-left and top-right neighbours are
-//              complete), one launch per wave over all pictures of the batch.
-//   k_deblock  same wave order (the top-right MB filters before the current one in raster
-//              order), one warp per MB: lanes 0-15 = luma lines, 16-31 = Cb/Cr lines.
+// Shared device code of the reconstruction kernels: the MB staging record, dequant + inverse
+// transforms of one coefficient block, the intra 4x4 / 8x8 predictors, the deblocking line filters,
+// output packing and the kernel-level test entry points.  The persistent row kernels that drive
+// them are in recon_rows.cuh.
 #pragma once
 #include "recon_device.cuh"
 
@@ -29,14 +23,6 @@ __device__ __forceinline__ uint8_t* plane_ptr (const PicDev& p, int slot, int pl
   return p.base + (size_t)slot * p.slot_stride + (plane == 0 ? 0 : (plane == 1 ? ysz : ysz + (ysz >> 2)));
 }
 
-// wave d -> k-th MB on the anti-diagonal x + 2y = d; returns false when k is past its end
-__device__ __forceinline__ bool wave_mb (int d, int k, int mb_w, int mb_h, int& x, int& y) {
-  const int y_min = max (0, (d - (mb_w - 1) + 1) >> 1), y_max = min (mb_h - 1, d >> 1);
-  y = y_min + k;
-  x = d - 2 * y;
-  return y <= y_max;
-}
-
 // ---- shared staging of the MB record and its coefficient levels ------------------------------------------
 struct MbShared {
   lh264_mb_rec mb;          // 128 B
@@ -44,20 +30,6 @@ struct MbShared {
   int16_t res[384];         // residual: luma 16x16 raster, then Cb 8x8, Cr 8x8
   uint8_t pred[384];        // prediction (same layout)
 };
-
-__device__ __forceinline__ void load_mb_and_levels (MbShared& s, const lh264_mb_rec* m, const int16_t* coefs, int tid, int nthreads) {
-  if (tid < 32) reinterpret_cast<uint32_t*> (&s.mb)[tid] = __ldg (reinterpret_cast<const uint32_t*> (m) + tid);
-  __syncthreads();
-  const uint32_t mask = s.mb.coded_mask;
-  const uint32_t* src = reinterpret_cast<const uint32_t*> (coefs) + (size_t)s.mb.coef_off * 8;
-  for (int w = tid; w < 192; w += nthreads) {
-    const int blk = w >> 3;
-    uint32_t v = 0;
-    if ((mask >> blk) & 1) v = __ldg (src + __popc (mask & ((1u << blk) - 1)) * 8 + (w & 7));
-    reinterpret_cast<uint32_t*> (s.lev)[w] = v;
-  }
-  __syncthreads();
-}
 
 // Residual of coefficient block k (0..15 luma in z order, 16..19 Cb, 20..23 Cr) into s.res.
 // Dequantisation as fused into the reference parse (parse_mb_syn_cavlc.cpp:938-1005,:1088-1095),
@@ -134,115 +106,6 @@ __device__ void residual_block (MbShared& s, int k) {
     c[0] = S16 (b == 0 ? (a + cc) >> 1 : (b == 1 ? (e + bb) >> 1 : (b == 2 ? (a - cc) >> 1 : (e - bb) >> 1)));
     idct4x4_res (c, s.res + 256 + 64 * p + (b >> 1) * 32 + (b & 1) * 4, 8);
   }
-}
-
-// final add + clip + store of 4 horizontally adjacent samples (thread t < 96)
-__device__ __forceinline__ void store_quad (const MbShared& s, const PicDev& pic, int mbx, int mby, int t, bool add_res) {
-  const int W = pic.mb_w * 16;
-  int idx;
-  uint8_t* dst;
-  if (t < 64) {
-    const int y = t >> 2, x4 = (t & 3) << 2;
-    idx = y * 16 + x4;
-    dst = plane_ptr (pic, pic.cur_slot, 0) + (size_t) (mby * 16 + y) * W + mbx * 16 + x4;
-  } else {
-    const int c = t - 64, p = c >> 4, y = (c & 15) >> 1, x4 = (c & 1) << 2;
-    idx = 256 + 64 * p + y * 8 + x4;
-    dst = plane_ptr (pic, pic.cur_slot, 1 + p) + (size_t) (mby * 8 + y) * (W >> 1) + mbx * 8 + x4;
-  }
-  uchar4 o;
-  if (add_res) {
-    o.x = (uint8_t)clip255 (s.pred[idx] + s.res[idx]); o.y = (uint8_t)clip255 (s.pred[idx + 1] + s.res[idx + 1]);
-    o.z = (uint8_t)clip255 (s.pred[idx + 2] + s.res[idx + 2]); o.w = (uint8_t)clip255 (s.pred[idx + 3] + s.res[idx + 3]);
-  } else {
-    o.x = s.pred[idx]; o.y = s.pred[idx + 1]; o.z = s.pred[idx + 2]; o.w = s.pred[idx + 3];
-  }
-  *reinterpret_cast<uchar4*> (dst) = o;
-}
-
-// =====================================================================================================
-// Inter pass.  GetInterPred/BaseMC/WeightPrediction (rec_mb.cpp:247-545) + WelsMbInterSampleConstruction
-// (decode_slice.cpp:208-250).  grid = (mbs of the largest picture, pictures).
-// =====================================================================================================
-#define WIN_STRIDE 12
-__global__ void __launch_bounds__ (128) k_inter (const PicDev* __restrict__ pics) {
-  __shared__ MbShared s;
-  __shared__ uint8_t s_win[16][9 * WIN_STRIDE];
-  const PicDev pic = pics[blockIdx.y];
-  const int mb = blockIdx.x;
-  if (mb >= pic.mb_w * pic.mb_h) return;
-  const int mb_type = __ldg (&pic.mbs[mb].mb_type);
-  if (!LH264_MB_IS_INTER (mb_type)) return;
-  const int tid = threadIdx.x;
-  load_mb_and_levels (s, pic.mbs + mb, pic.coefs, tid, 128);
-  const int mbx = mb % pic.mb_w, mby = mb / pic.mb_w;
-  const int W = pic.mb_w * 16, H = pic.mb_h * 16;
-  const lh264_slice_rec* sl = pic.slices + s.mb.slice_idx;
-  const bool has_res = s.mb.cbp != 0;
-
-  if (tid < 96) {
-    const bool luma = tid < 64;
-    const int c = tid - 64;
-    const int r = luma ? (tid >> 2) : (c & 15);            // raster 4x4 block this thread predicts for
-    const int bx = r & 3, by = r >> 2, q = (by >> 1) * 2 + (bx >> 1);
-    int ox, oy, bw, bh;
-    part_geom (mb_type, s.mb.sub_mb_type[q], bx, by, ox, oy, bw, bh);
-    const int refidx = s.mb.ref_idx[q] & 15;
-    const int slot = clip3i (__ldg (&sl->ref_slot[refidx]), 0, pic.n_slots - 1);
-    // BaseMC: clamp the partition's full-sample MV into the (virtual) 32-pixel border
-    const int fx = clip3i (((mbx * 16 + ox) << 2) + s.mb.mv[r][0], (-32 + 2) * 4, (W + 32 - 19) << 2);
-    const int fy = clip3i (((mby * 16 + oy) << 2) + s.mb.mv[r][1], (-32 + 2) * 4, (H + 32 - 19) << 2);
-    const int wp = __ldg (&sl->weighted_pred);
-    if (luma) {
-      const int row = tid & 3;
-      const uint8_t* ref = plane_ptr (pic, slot, 0);
-      const int ix = (fx >> 2) + (bx * 4 - ox) - 2, iy = (fy >> 2) + (by * 4 - oy) - 2;
-      uint8_t* win = s_win[r];
-      for (int k = row; k < 81; k += 4) {
-        const int wy = k / 9, wx = k - wy * 9;
-        win[wy * WIN_STRIDE + wx] = __ldg (ref + (size_t)clip3i (iy + wy, 0, H - 1) * W + clip3i (ix + wx, 0, W - 1));
-      }
-      __syncwarp();
-      const int frac = ((fx & 3) << 2) | (fy & 3);
-      const uint8_t* w0 = win + (2 + row) * WIN_STRIDE + 2;
-      uint8_t* out = s.pred + (by * 4 + row) * 16 + bx * 4;
-      int lw = 0, lo = 0, ld = 0;
-      if (wp) { lw = __ldg (&sl->luma_weight[refidx]); lo = __ldg (&sl->luma_offset[refidx]); ld = __ldg (&sl->luma_log2_denom); }
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        int v = mc_luma_sample (w0 + i, WIN_STRIDE, frac);
-        if (wp) v = wp_sample (v, lw, lo, ld);
-        out[i] = (uint8_t)v;
-      }
-    } else {
-      // McChroma_c on the 2x2 chroma block that belongs to luma block r
-      const int p = c >> 4, CW = W >> 1, CH = H >> 1;
-      const uint8_t* ref = plane_ptr (pic, slot, 1 + p);
-      const int cx = (fx >> 3) + ((bx * 4 - ox) >> 1), cy = (fy >> 3) + ((by * 4 - oy) >> 1);
-      const int dx = fx & 7, dy = fy & 7;
-      int v[3][3];
-#pragma unroll
-      for (int j = 0; j < 3; j++)
-#pragma unroll
-        for (int i = 0; i < 3; i++) v[j][i] = __ldg (ref + (size_t)clip3i (cy + j, 0, CH - 1) * CW + clip3i (cx + i, 0, CW - 1));
-      const int A = (8 - dx) * (8 - dy), B = dx * (8 - dy), C = (8 - dx) * dy, D = dx * dy;
-      int cw = 0, co = 0, cd = 0;
-      // the reference weights only the top-left (bw>>2) x (bh>>2) samples of a partition's chroma (rec_mb.cpp:309-311)
-      if (wp) { cw = __ldg (&sl->chroma_weight[refidx][p]); co = __ldg (&sl->chroma_offset[refidx][p]); cd = __ldg (&sl->chroma_log2_denom); }
-#pragma unroll
-      for (int j = 0; j < 2; j++)
-#pragma unroll
-        for (int i = 0; i < 2; i++) {
-          int o = (A * v[j][i] + B * v[j][i + 1] + C * v[j + 1][i] + D * v[j + 1][i + 1] + 32) >> 6;
-          if (wp && ((bx * 4 - ox) >> 1) + i < (bw >> 2) && ((by * 4 - oy) >> 1) + j < (bh >> 2)) o = wp_sample (o, cw, co, cd);
-          s.pred[256 + 64 * p + (by * 2 + j) * 8 + bx * 2 + i] = (uint8_t)o;
-        }
-    }
-  } else if (tid < 120 && has_res) {
-    residual_block (s, tid - 96);
-  }
-  __syncthreads();
-  if (tid < 96) store_quad (s, pic, mbx, mby, tid, has_res);
 }
 
 // =====================================================================================================
@@ -382,141 +245,6 @@ __device__ int pred8x8_sample (const uint8_t* tile, int X0, int Y0, int mode, in
 #undef E8
 }
 
-__global__ void __launch_bounds__ (128) k_intra (const PicDev* __restrict__ pics, const int* __restrict__ pic_ids, int wave) {
-  __shared__ MbShared s;
-  __shared__ uint8_t tile[17 * TS];
-  __shared__ uint8_t cedge[2][2][9];      // [plane][0 = top incl. top-left at [0], 1 = left incl. top-left][9]
-  const PicDev pic = pics[pic_ids[blockIdx.y]];
-  int mbx, mby;
-  if (!wave_mb (wave, blockIdx.x, pic.mb_w, pic.mb_h, mbx, mby)) return;
-  const int mb = mby * pic.mb_w + mbx;
-  const int mb_type = __ldg (&pic.mbs[mb].mb_type);
-  if (!LH264_MB_IS_INTRA (mb_type)) return;
-  const int tid = threadIdx.x;
-  load_mb_and_levels (s, pic.mbs + mb, pic.coefs, tid, 128);
-  const int W = pic.mb_w * 16, H = pic.mb_h * 16, CW = W >> 1;
-  uint8_t* Y = plane_ptr (pic, pic.cur_slot, 0);
-
-  if (mb_type == LH264_MB_IPCM) {           // samples travel in the coefficient pool
-    for (int i = tid; i < 384; i += 128) s.pred[i] = (uint8_t)s.lev[i];
-    __syncthreads();
-    if (tid < 96) store_quad (s, pic, mbx, mby, tid, false);
-    return;
-  }
-
-  // phase A: neighbour samples -> shared, residuals of all 24 blocks
-  if (tid < 96) {
-    // luma: top row x = -1..23 (25 samples), left column y = 0..15; coordinates clamped (unavailable
-    // neighbours are never used by a resolved mode)
-    if (tid < 25) {
-      const int x = mbx * 16 - 1 + tid, y = mby * 16 - 1;
-      tile[tid] = Y[(size_t)max (y, 0) * W + clip3i (x, 0, W - 1)];
-    } else if (tid < 41) {
-      const int y = mby * 16 + tid - 25, x = mbx * 16 - 1;
-      tile[(tid - 25 + 1) * TS] = Y[(size_t)y * W + max (x, 0)];
-    } else if (tid < 41 + 36) {
-      const int c = tid - 41, p = c / 18, k = c % 18;        // k 0..8 top (x=-1..7), 9..17 left (y=-1..7)
-      const uint8_t* C = plane_ptr (pic, pic.cur_slot, 1 + p);
-      int x, y;
-      if (k < 9) { x = mbx * 8 - 1 + k; y = mby * 8 - 1; } else { x = mbx * 8 - 1; y = mby * 8 - 1 + (k - 9); }
-      cedge[p][k < 9 ? 0 : 1][k < 9 ? k : k - 9] = C[(size_t)max (y, 0) * CW + clip3i (x, 0, CW - 1)];
-    }
-  } else if (tid < 120) {
-    residual_block (s, tid - 96);
-  }
-  __syncthreads();
-  (void)H;
-
-  // chroma prediction (threads 64..95), WelsIChromaPred*_c
-  if (tid >= 64 && tid < 96) {
-    const int c = tid - 64, p = c >> 4, y = (c & 15) >> 1, x4 = (c & 1) << 2;
-    const uint8_t* top = &cedge[p][0][1];   // top[-1] = top-left
-    const uint8_t* left = &cedge[p][1][1];
-    const int mode = s.mb.chroma_mode;
-    int v[4];
-    if (mode == LH264_C_V) { for (int i = 0; i < 4; i++) v[i] = top[x4 + i]; }
-    else if (mode == LH264_C_H) { for (int i = 0; i < 4; i++) v[i] = left[y]; }
-    else if (mode == LH264_C_P) {
-      int Hs = 0, Vs = 0;
-#pragma unroll
-      for (int i = 0; i < 4; i++) { Hs += (i + 1) * (top[4 + i] - top[2 - i]); Vs += (i + 1) * (left[4 + i] - left[2 - i]); }
-      const int a = (left[7] + top[7]) << 4, b = (17 * Hs + 16) >> 5, cc = (17 * Vs + 16) >> 5;
-      for (int i = 0; i < 4; i++) v[i] = clip255 ((a + b * (x4 + i - 3) + cc * (y - 3) + 16) >> 5);
-    } else {
-      int t0 = 0, t1 = 0, l0 = 0, l1 = 0, dc = 128;
-#pragma unroll
-      for (int i = 0; i < 4; i++) { t0 += top[i]; t1 += top[4 + i]; l0 += left[i]; l1 += left[4 + i]; }
-      const int quad = (y >> 2) * 2 + (x4 >> 2);
-      if (mode == LH264_C_DC) dc = quad == 0 ? (t0 + l0 + 4) >> 3 : (quad == 1 ? (t1 + 2) >> 2 : (quad == 2 ? (l1 + 2) >> 2 : (t1 + l1 + 4) >> 3));
-      else if (mode == LH264_C_DC_T) dc = ((x4 ? t1 : t0) + 2) >> 2;
-      else if (mode == LH264_C_DC_L) dc = ((y >> 2 ? l1 : l0) + 2) >> 2;
-      for (int i = 0; i < 4; i++) v[i] = dc;
-    }
-    for (int i = 0; i < 4; i++) s.pred[256 + 64 * p + y * 8 + x4 + i] = (uint8_t)v[i];
-  }
-
-  if (mb_type == LH264_MB_I16x16) {
-    if (tid < 64) {
-      const int y = tid >> 2, x4 = (tid & 3) << 2, mode = s.mb.i16_mode;
-      int v[4];
-      if (mode == LH264_I16_V) { for (int i = 0; i < 4; i++) v[i] = TILE (x4 + i, -1); }
-      else if (mode == LH264_I16_H) { for (int i = 0; i < 4; i++) v[i] = TILE (-1, y); }
-      else if (mode == LH264_I16_P) {
-        int Hs = 0, Vs = 0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) { Hs += (i + 1) * (TILE (8 + i, -1) - TILE (6 - i, -1)); Vs += (i + 1) * (TILE (-1, 8 + i) - TILE (-1, 6 - i)); }
-        const int a = (TILE (-1, 15) + TILE (15, -1)) << 4, b = (5 * Hs + 32) >> 6, cc = (5 * Vs + 32) >> 6;
-        for (int i = 0; i < 4; i++) v[i] = clip255 ((a + b * (x4 + i - 7) + cc * (y - 7) + 16) >> 5);
-      } else {
-        int st = 0, sl = 0, dc = 128;
-#pragma unroll
-        for (int i = 0; i < 16; i++) { st += TILE (i, -1); sl += TILE (-1, i); }
-        if (mode == LH264_I16_DC) dc = (st + sl + 16) >> 5;
-        else if (mode == LH264_I16_DC_T) dc = (st + 8) >> 4;
-        else if (mode == LH264_I16_DC_L) dc = (sl + 8) >> 4;
-        for (int i = 0; i < 4; i++) v[i] = dc;
-      }
-      for (int i = 0; i < 4; i++) s.pred[y * 16 + x4 + i] = (uint8_t)v[i];
-    }
-    __syncthreads();
-    if (tid < 96) store_quad (s, pic, mbx, mby, tid, true);
-    return;
-  }
-
-  if (mb_type == LH264_MB_I4x4) {
-    if (tid < 16) {                          // 16 dependent 4x4 steps, one lane per sample
-      const int x = tid & 3, y = tid >> 2;
-      for (int z = 0; z < 16; z++) {
-        const int X0 = blk_x (z), Y0 = blk_y (z);
-        const int v = pred4x4_sample (tile, X0, Y0, s.mb.intra_mode[z], x, y);
-        __syncwarp (0xffff);
-        TILE (X0 + x, Y0 + y) = (uint8_t)clip255 (v + s.res[(Y0 + y) * 16 + X0 + x]);
-        __syncwarp (0xffff);
-      }
-    }
-  } else {                                    // I8x8: 4 dependent 8x8 steps, one thread per sample
-    const int f = s.mb.nxn_avail;
-    for (int q = 0; q < 4; q++) {
-      const int X0 = (q & 1) * 8, Y0 = (q >> 1) * 8;
-      const int tl = q == 0 ? (f >> 1) & 1 : (q == 1 ? f & 1 : (q == 2 ? (f >> 2) & 1 : 1));
-      const int tr = q == 0 ? f & 1 : (q == 1 ? (f >> 3) & 1 : (q == 2 ? 1 : 0));
-      int v = 0;
-      if (tid < 64) v = pred8x8_sample (tile, X0, Y0, s.mb.intra_mode[4 * q], tl, tr, tid & 7, tid >> 3);
-      __syncthreads();
-      if (tid < 64) TILE (X0 + (tid & 7), Y0 + (tid >> 3)) = (uint8_t)clip255 (v + s.res[(Y0 + (tid >> 3)) * 16 + X0 + (tid & 7)]);
-      __syncthreads();
-    }
-  }
-  __syncthreads();
-  if (tid < 64) {                            // luma: the tile already holds pred + residual
-    const int y = tid >> 2, x4 = (tid & 3) << 2;
-    uchar4 o = make_uchar4 (TILE (x4, y), TILE (x4 + 1, y), TILE (x4 + 2, y), TILE (x4 + 3, y));
-    *reinterpret_cast<uchar4*> (Y + (size_t) (mby * 16 + y) * W + mbx * 16 + x4) = o;
-  } else if (tid < 96) {
-    const int cc = s.mb.cbp >> 4;
-    store_quad (s, pic, mbx, mby, tid, cc == 1 || cc == 2);
-  }
-}
 #undef F2
 #undef F3
 
@@ -572,99 +300,6 @@ __device__ __forceinline__ void chroma_line (uint8_t* p, int sx, int bS, int ia,
     const int tc = c_tc0[ia][bS] + 1;
     const int dl = clip3i ((((q0 - p0) << 2) + (p1 - q1) + 4) >> 3, -tc, tc);
     p[-sx] = (uint8_t)clip255 (p0 + dl); p[0] = (uint8_t)clip255 (q0 - dl);
-  }
-}
-
-__global__ void __launch_bounds__ (128) k_deblock (const PicDev* __restrict__ pics, int wave) {
-  const PicDev pic = pics[blockIdx.y];
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  int mbx, mby;
-  if (!wave_mb (wave, blockIdx.x * 4 + warp, pic.mb_w, pic.mb_h, mbx, mby)) return;
-  const int mb_w = pic.mb_w, mbi = mby * mb_w + mbx;
-  const lh264_mb_rec* m = pic.mbs + mbi;
-  const int mb_type = m->mb_type;
-  if (mb_type == LH264_MB_NONE) return;
-  const lh264_slice_rec* sl = pic.slices + m->slice_idx;
-  const int idc = sl->disable_deblocking_idc;
-  if (idc == 1) return;
-  const int aoff = sl->alpha_c0_offset, boff = sl->beta_offset;
-  // DeblockingAvailableNoInterlayer, deblocking.cpp:354-369
-  bool left = mbx > 0, top = mby > 0;
-  if (idc == 2) { left = left && m[-1].slice_idx == m->slice_idx; top = top && m[-mb_w].slice_idx == m->slice_idx; }
-  const bool t8 = m->flags & LH264_MBF_TRANSFORM8x8;
-  const bool intra = LH264_MB_IS_INTRA (mb_type);
-
-  // ---- boundary strength: lane = dir*16 + edge*4 + segment ----
-  const int dir = lane >> 4, e = (lane >> 2) & 3, i = lane & 3;
-  int bs = 0;
-  if (intra) bs = e == 0 ? 4 : 3;
-  else if (e == 0) {
-    const bool avail = dir ? top : left;
-    if (avail) {
-      const lh264_mb_rec* nb = dir ? m - mb_w : m - 1;
-      if (LH264_MB_IS_INTRA (nb->mb_type)) bs = 4;
-      else {                                  // DeblockingBsMarginalMBAvcbase
-        const uint32_t nzc = m->nz_mask, nzn = nb->nz_mask;
-        const bool n8 = nb->flags & LH264_MBF_TRANSFORM8x8;
-        const int rc = dir ? i : 4 * i, rn = dir ? 12 + i : 4 * i + 3;
-        const int rc8 = dir ? (i & 2) : 4 * (i & 2), rn8 = dir ? 8 + (i & 2) : 4 * (i & 2) + 2;
-        const int nz = (t8 ? nz8 (nzc, rc) : nzb (nzc, rc)) | (n8 ? nz8 (nzn, rn) : nzb (nzn, rn));
-        bs = nz ? 2 : mv_differs (m, t8 ? rc8 : rc, nb, n8 ? rn8 : rn);
-      }
-    }
-  } else if (mb_type != LH264_MB_PSKIP && ! (t8 && e != 2)) {
-    const uint32_t nzc = m->nz_mask;
-    const int a = dir ? 4 * e + i : 4 * i + e, b = dir ? a - 4 : a - 1;
-    const int nz = t8 ? (nz8 (nzc, a) | nz8 (nzc, b)) : (nzb (nzc, a) | nzb (nzc, b));
-    if (nz) bs = 2;
-    else if (mb_type != LH264_MB_P16x16) {
-      const int ma = t8 ? ((a & 8) + (a & 2)) : a, mb2 = t8 ? ((b & 8) + (b & 2)) : b;
-      bs = mv_differs (m, ma, m, mb2);
-    }
-  }
-
-  const int W = mb_w * 16, CW = W >> 1;
-  uint8_t* Y = plane_ptr (pic, pic.cur_slot, 0) + (size_t)mby * 16 * W + mbx * 16;
-  const int qp_cur = m->qp_y;
-  const int cplane = (lane - 16) >> 3;         // chroma lanes: 16..23 Cb, 24..31 Cr
-  uint8_t* C = nullptr;
-  int qpc_cur = 0;
-  if (lane >= 16) { C = plane_ptr (pic, pic.cur_slot, 1 + cplane) + (size_t)mby * 8 * CW + mbx * 8; qpc_cur = m->qp_c[cplane]; }
-
-#pragma unroll 1
-  for (int d = 0; d < 2; d++) {
-    const bool avail = d ? top : left;
-    const lh264_mb_rec* nb = d ? m - mb_w : m - 1;
-#pragma unroll 1
-    for (int ed = 0; ed < 4; ed++) {
-      // bS of this lane's line: luma line l -> segment l>>2 ; chroma line l -> segment l>>1
-      const int seg = lane < 16 ? (lane >> 2) : ((lane & 7) >> 1);
-      const int my_bs = __shfl_sync (0xffffffffu, bs, d * 16 + ed * 4 + seg);
-      const unsigned any = __ballot_sync (0xffffffffu, my_bs != 0);
-      if (ed == 0 && !avail) continue;
-      if ((ed & 1) && t8) continue;
-      if (!any) continue;
-      if (lane < 16) {
-        int qp = qp_cur;
-        if (ed == 0) qp = (qp + nb->qp_y + 1) >> 1;
-        const int ia = clip3i (qp + aoff, 0, 51), alpha = c_alpha[ia], beta = c_beta[clip3i (qp + boff, 0, 51)];
-        if ((alpha | beta) && my_bs) {
-          uint8_t* p = d ? Y + (size_t)4 * ed * W + lane : Y + (size_t)lane * W + 4 * ed;
-          luma_line (p, d ? W : 1, my_bs, ia, alpha, beta);
-        }
-      } else if (! (ed & 1)) {
-        int qp = qpc_cur;
-        if (ed == 0) qp = (qp + nb->qp_c[cplane] + 1) >> 1;
-        const int ia = clip3i (qp + aoff, 0, 51), alpha = c_alpha[ia], beta = c_beta[clip3i (qp + boff, 0, 51)];
-        if ((alpha | beta) && my_bs) {
-          const int l = lane & 7;
-          uint8_t* p = d ? C + (size_t)2 * ed * CW + l : C + (size_t)l * CW + 2 * ed;
-          chroma_line (p, d ? CW : 1, my_bs, ia, alpha, beta);
-        }
-      }
-      __syncwarp();
-    }
-    __syncwarp();
   }
 }
 
