@@ -237,6 +237,104 @@ int  lh264_k_mc_chroma(lh264_ctx* ctx, const uint8_t* ref, int w, int h, const i
 /* = ExpandPictureLuma_c/Chroma_c (expand_pic.cpp:37-115): in w x h, out (w+2p) x (h+2p).    */
 int  lh264_k_expand_plane(lh264_ctx* ctx, const uint8_t* in, int w, int h, int pad, uint8_t* out);
 
+/* ==== recompression model ("Pied Piper" layer) ================================================
+ * Replaces, for the compress direction, the per-macroblock modelling of the reference:
+ *   lh264_model_mb / lh264_model_slice  <- DecodedMacroblock + the emission decisions that
+ *                                          WelsDecodeSliceForNonRecoding takes from decoder state
+ *                                          (decoded_macroblock.h:4-104, decode_slice.cpp:2174-2474)
+ *   lh264_model_submit()                <- WelsDecodeSlice's MB loop for every slice of a picture
+ *                                          (decode_slice.cpp:2959-3171): FreqImage neighbour
+ *                                          contexts (decoded_macroblock.h:106-191, macroblock_model.cpp:9-44),
+ *                                          prior selection (macroblock_model.cpp:375-645), the
+ *                                          binarisations (compression_stream.h:441-591), DynProb
+ *                                          adaptation (:87-115) and the VP8 bool coder (bitwriter.h:35-105),
+ *                                          for a BATCH of pictures of independent streams.
+ *   lh264_model_finish()                <- vpx_stop_encode + ArithmeticCodedOutput::flushToWriter
+ *                                          (bitwriter.cpp:28-38, compression_stream.cpp:211-234): the
+ *                                          bytes of one `x.pip.<tag>` side stream.
+ * Model state (priors, previous-frame contexts, coder states) lives in HBM per model stream.       */
+
+/* tag ids = the reference's billing enum (billing.h:7-58); file suffix of the side stream          */
+enum {
+  LH264_TAG_SKIP = 1, LH264_TAG_SKIP_END = 2, LH264_TAG_CBPL = 4, LH264_TAG_QPL = 6, LH264_TAG_MB_TYPE = 7,
+  LH264_TAG_TRANSFORM_8x8 = 8, LH264_TAG_REF = 9, LH264_TAG_8x8 = 10, LH264_TAG_16x16 = 11,
+  LH264_TAG_PRED_MODE = 13, LH264_TAG_SUB_MB = 14, LH264_TAG_MVX = 15, LH264_TAG_MVY = 16,
+  LH264_TAG_LDC = 17, LH264_TAG_CRDC = 18,
+  LH264_TAG_LAC_0_EOB = 19, LH264_TAG_LAC_0_BITMASK = 20, LH264_TAG_LAC_0_EXP = 21, LH264_TAG_LAC_0_RES = 22, LH264_TAG_LAC_0_SIGN = 23,
+  LH264_TAG_LAC_N_BITMASK = 25, LH264_TAG_LAC_N_EXP = 26, LH264_TAG_LAC_N_RES = 27, LH264_TAG_LAC_N_SIGN = 28,
+  LH264_TAG_CRAC_EOB = 29, LH264_TAG_CRAC_BITMASK = 30, LH264_TAG_CRAC_EXP = 31, LH264_TAG_CRAC_RES = 32, LH264_TAG_CRAC_SIGN = 33,
+  LH264_TAG_PADBYTE = 69,
+  LH264_NUM_TAGS = 70
+};
+
+#define LH264_MM_EMIT_SKIP_RUN 0x01  /* an mb_skip_run was read in front of this MB: code skip_run (decode_slice.cpp:2210-2217) */
+#define LH264_MM_STOP_IN_SKIP  0x02  /* last MB of a skip run: code the stop bit (:2223-2226)                                  */
+#define LH264_MM_WRITE_BLOCK   0x04  /* a coded macroblock (not skipped): code the whole record (:2244-2434)                     */
+#define LH264_MM_STOP_BIT      0x08  /* value of the stop bit: the slice data ends right after this MB (:2200-2201)            */
+#define LH264_MM_T8_CODED      0x10  /* transform_size_8x8_flag is part of the MB syntax (needParseTransformSize8x8)            */
+#define LH264_MM_T8            0x20  /* its value                                                                               */
+
+/* One macroblock in slice-data order (skipped MBs included), 128 bytes.                                                       */
+typedef struct lh264_model_mb {
+  uint32_t mb_addr;          /* raster address in the picture                                                                   */
+  uint16_t flags;            /* LH264_MM_*                                                                                      */
+  uint16_t skip_run;         /* value coded when LH264_MM_EMIT_SKIP_RUN                                                         */
+  uint16_t mb_in_slice;      /* macroblockIndexInSlice (decode_slice.cpp:3063)                                                  */
+  uint8_t  type_code;        /* MacroblockModel::encodeMacroblockType: 0 I4x4 1 I16x16 2 I8x8 3 16x16 4 16x8 5 8x16 6 8x8
+                                7 8x8ref0 8 I_PCM 11 skip (macroblock_model.cpp:647-679)                                        */
+  uint8_t  cbp;              /* pCbp[mb] as the reference holds it: luma bits 0-3, chroma bits 4-5                              */
+  uint8_t  luma_qp;          /* pLumaQp[mb]                                                                                     */
+  uint8_t  chroma_mode;      /* pChromaPredMode[mb] (availability-resolved; retained from an earlier picture for inter MBs)    */
+  uint8_t  i16_mode;         /* pIntraPredMode[mb][7] (likewise)                                                                */
+  uint8_t  reserved;
+  uint8_t  sub_mb_type[4];   /* pSubMbType[mb][]: 1 8x8, 2 8x4, 4 4x8, 8 4x4 (retained values for I8x8)                          */
+  int8_t   ref_idx[4];       /* rtd.iRefIdx[]: per partition (16x8 / 8x16: [0],[1]) or per 8x8 quadrant                           */
+  uint8_t  pred_mode[16];    /* I4x4: low nibble = coded mode (iBestIntra4x4PredMode), high nibble = predicted mode;
+                                I8x8: entries 0..3, low nibble only                                                            */
+  uint8_t  pred_avail[16];   /* I4x4: (left << 2) | (top << 1) | top-left sample availability of each block (:2310-2316)       */
+  uint32_t coded_mask;       /* as lh264_mb_rec (0 for I_PCM: the reference models no coefficients there)                       */
+  uint32_t coef_off;
+  int16_t  mvd[16][2];       /* motion vector differences as parsed, at the raster index of each partition's first 4x4 block   */
+} lh264_model_mb;
+
+typedef struct lh264_model_slice {
+  int32_t  first_rec;        /* index of the slice's first lh264_model_mb in the picture's array                                */
+  int32_t  n_recs;
+  int32_t  frame_num;        /* FreqImage::updateFrame key (decode_slice.cpp:3034)                                              */
+  uint8_t  slice_type;       /* eSliceType: 0 P, 2 I                                                                            */
+  uint8_t  num_ref_idx_l0;   /* uiRefCount[0]                                                                                   */
+  uint8_t  n_pad_bits;       /* slice trailing alignment bits coded into the PADBYTE tag (:3133-3147)                            */
+  uint8_t  pad_bits;
+  uint8_t  chroma_format_idc;
+  uint8_t  reserved[3];
+} lh264_model_slice;
+
+typedef struct lh264_model_picture {
+  int32_t  model_stream;     /* handle from lh264_model_open                                                                    */
+  int32_t  mb_w, mb_h;
+  int32_t  n_slices;
+  int32_t  n_recs;
+  int32_t  n_coef_blocks;
+  const lh264_model_slice* slices;
+  const lh264_model_mb*    recs;
+  const int16_t*           coefs;   /* the picture's coefficient pool (same pool as lh264_picture_desc.coefs)                   */
+} lh264_model_picture;
+
+/* Opens the model state of one stream in HBM.  max_mbs bounds the picture size; with_8x8 != 0 also allocates the 8x8
+ * coefficient priors (High profile streams).  Returns a handle >= 0 or an error.                                             */
+int  lh264_model_open(lh264_ctx* ctx, int max_mbs, int with_8x8);
+int  lh264_model_close(lh264_ctx* ctx, int model_stream);
+/* Codes one picture per stream for a batch of independent streams (host buffers in, asynchronous).  Output bytes
+ * accumulate on the device and are drained by lh264_model_drain / lh264_model_finish.                                         */
+int  lh264_model_submit(lh264_ctx* ctx, const lh264_model_picture* pics, int n_pics);
+/* Ends every tag stream of a model stream (32 trailing zero decisions etc.) and makes all bytes available.                  */
+int  lh264_model_finish(lh264_ctx* ctx, int model_stream);
+/* Bytes produced so far for one tag: copies up to cap bytes starting at offset into dst (host), returns the total
+ * number of bytes available for that tag (>= 0) or an error; a tag never used returns 0 and has no side file.               */
+long long lh264_model_read(lh264_ctx* ctx, int model_stream, int tag, uint8_t* dst, size_t offset, size_t cap);
+/* decisions coded so far by a model stream (for throughput reporting)                                                         */
+unsigned long long lh264_model_decisions(lh264_ctx* ctx, int model_stream);
+
 #ifdef __cplusplus
 }
 #endif

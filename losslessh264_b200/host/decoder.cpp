@@ -63,6 +63,14 @@ struct Decoder::Impl {
   std::vector<int8_t> ipm;               // [mb][16] Intra4x4/8x8PredMode per raster block; 2 for other MB types
   std::vector<int16_t> mb_slice;         // slice number of each MB, -1 = not decoded in this picture
   std::vector<ModelMbSide> side;
+  // recompression-model hand-off (include/lh264_b200.h, lh264_model_*): records in slice-data order
+  bool want_model = false;
+  std::vector<lh264_model_mb> mrecs;
+  std::vector<lh264_model_slice> mslices;
+  // per-position decoder state the reference keeps across pictures and reads back when it fills its
+  // DecodedMacroblock (initRTDFromDecoderState, decode_slice.cpp:81-108): pCbp, pChromaPredMode,
+  // pIntraPredMode[][7], pSubMbType are only written by the MB types that carry them
+  std::vector<uint8_t> st_cbp, st_chroma, st_i16, st_sub;
 
   // slice being parsed
   const Sps* S = nullptr;
@@ -255,6 +263,7 @@ struct Decoder::Impl {
     ipm.assign ((size_t)n_mbs * 16, 2);
     mb_slice.assign (n_mbs, -1);
     side.assign (n_mbs, ModelMbSide());
+    st_cbp.assign (n_mbs, 0); st_chroma.assign (n_mbs, 0); st_i16.assign (n_mbs, 0); st_sub.assign ((size_t)n_mbs * 4, 0);
     coefs.reserve ((size_t)n_mbs * 64);
     return sink->configure (mb_w, mb_h, n_slots);
   }
@@ -285,7 +294,7 @@ struct Decoder::Impl {
       }
     }
     cur_slot = free_slot();
-    slices.clear(); coefs.clear();
+    slices.clear(); coefs.clear(); mrecs.clear(); mslices.clear();
     for (int i = 0; i < n_mbs; i++) { mbs[i].mb_type = LH264_MB_NONE; mb_slice[i] = -1; }
   }
   int finish_picture (Decoder* self) {
@@ -302,6 +311,13 @@ struct Decoder::Impl {
     info.slot = cur_slot; info.serial = serial++; info.complete = decoded >= n_mbs; info.timestamp = ts;
     int rc = 0;
     if (!slices.empty()) rc = sink->submit (d, info);
+    if (want_model && !mslices.empty()) {
+      lh264_model_picture mp;
+      mp.model_stream = 0; mp.mb_w = mb_w; mp.mb_h = mb_h; mp.n_slices = (int)mslices.size(); mp.n_recs = (int)mrecs.size();
+      mp.n_coef_blocks = d.n_coef_blocks; mp.slices = mslices.data(); mp.recs = mrecs.data(); mp.coefs = coefs.data();
+      const int rm = sink->submit_model (mp, info);
+      if (!rc) rc = rm;
+    }
     mark_current();
     self->stats_.pictures++;
     self->stats_.coef_blocks += coefs.size() / 16;
@@ -311,7 +327,7 @@ struct Decoder::Impl {
 
   // ---- slice data ------------------------------------------------------------------------------------
   int parse_slice_data (BitReader& br, Decoder* self);
-  int parse_mb (BitReader& br, int mb_addr, bool skipped);
+  int parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_model_mb* mr);
   int parse_residual (BitReader& br, lh264_mb_rec& m, int mb_addr, int16_t* lev, uint32_t& coded, bool i16, int cbp);
   void resolve_intra (lh264_mb_rec& m, int mb_addr, const int8_t* modes, bool i8x8);
   int nC_luma (int mb_addr, int r) const;
@@ -425,7 +441,7 @@ int Decoder::Impl::parse_residual (BitReader& br, lh264_mb_rec& m, int mb_addr, 
 }
 
 // ---- macroblock_layer( ) (7.3.5) -----------------------------------------------------------------------
-int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped) {
+int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_model_mb* mr) {
   lh264_mb_rec& m = mbs[mb_addr];
   memset (&m, 0, sizeof (m));
   cur_mb = mb_addr;
@@ -453,6 +469,8 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped) {
       pred_mv (0, 0, 4, 4, 0, 0, px, py);
     for (int r = 0; r < 16; r++) { m.mv[r][0] = (int16_t)px; m.mv[r][1] = (int16_t)py; }
     mb_slice[mb_addr] = (int16_t)slice_no;
+    st_cbp[mb_addr] = 0;                             // pCbp[iMbXy] = 0, decode_slice.cpp:3945
+    if (mr) { mr->type_code = 11; mr->luma_qp = (uint8_t)qp; }
     return 0;
   }
 
@@ -483,11 +501,13 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped) {
         if (s > 3) return -1;
         m.sub_mb_type[q] = (uint8_t)s;
         if (s) sub_lt8 = true;
+        st_sub[(size_t)mb_addr * 4 + q] = (uint8_t) (1u << s);   // g_ksInterSubMbTypeInfo[].iType
       }
       for (int q = 0; q < 4; q++) {
         int ref = 0;
         if (t != 4 && nref > 1) { ref = (int)br.te (nref - 1); if (ref >= nref) return -1; }
         m.ref_idx[q] = (int8_t)ref;
+        if (mr) mr->ref_idx[q] = (int8_t)ref;
       }
       // the standard makes a block "available" only once its motion has been derived; the ref_idx of
       // later quadrants must therefore stay hidden from nb_block(): cur_done gates them.
@@ -505,6 +525,7 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped) {
           int px, py;
           pred_mv (bx, by, bw, bh, ref, 0, px, py);
           const int dx = br.se(), dy = br.se();
+          if (mr) { mr->mvd[by * 4 + bx][0] = (int16_t)dx; mr->mvd[by * 4 + bx][1] = (int16_t)dy; }
           put_mv (bx, by, bw, bh, px + dx, py + dy);
         }
       }
@@ -521,14 +542,17 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped) {
         int px, py;
         pred_mv (bx, by, bw, bh, refs_[p], shape, px, py);
         const int dx = br.se(), dy = br.se();
+        if (mr) { mr->ref_idx[p] = (int8_t)refs_[p]; mr->mvd[by * 4 + bx][0] = (int16_t)dx; mr->mvd[by * 4 + bx][1] = (int16_t)dy; }
         put_mv (bx, by, bw, bh, px + dx, py + dy);
       }
     }
+    if (mr) mr->type_code = (uint8_t) (3 + t);          // 16x16 3, 16x8 4, 8x16 5, 8x8 6, 8x8ref0 7
     const uint32_t c = br.ue();
     if (c > 47) return -1;
     cbp = kCbpInter[c];
     if ((cbp & 15) && P->transform_8x8_mode && ! (m.mb_type == LH264_MB_P8x8 && sub_lt8)) {
       if (br.u1()) m.flags |= LH264_MBF_TRANSFORM8x8;
+      if (mr) mr->flags |= LH264_MM_T8_CODED;
     }
   } else if (t == 25) {                               // I_PCM
     m.mb_type = LH264_MB_IPCM;
@@ -544,6 +568,10 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped) {
     memset (nz, 16, 24);
     m.qp_y = 0; m.qp_c[0] = m.qp_c[1] = 0;          // decode_slice.cpp:3258-3259
     mb_slice[mb_addr] = (int16_t)slice_no;
+    if (mr) {                                         // the reference models no coefficients for I_PCM and reads back retained state
+      mr->type_code = 8; mr->luma_qp = 0; mr->cbp = st_cbp[mb_addr]; mr->chroma_mode = st_chroma[mb_addr]; mr->i16_mode = st_i16[mb_addr];
+      mr->coded_mask = 0; mr->coef_off = 0;
+    }
     return br.overrun() ? -1 : 0;
   } else if (t == 0) {                                // I_NxN
     bool i8 = false;
@@ -567,6 +595,15 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped) {
       int mode = pred;
       if (!br.u1()) { const int rem = (int)br.u (3); mode = rem < pred ? rem : rem + 1; }
       modes[i] = (int8_t)mode;
+      if (mr) {
+        mr->pred_mode[i] = (uint8_t) (mode | (pred << 4));
+        if (!i8) {                                    // sample availability as CheckIntraNxNPredMode sees it (iSampleAvail grid)
+          const int nTL = nb_mb (mbx, mby, -1, -1);
+          const bool l = bx > 0 ? true : aL, tp = by > 0 ? true : aT;
+          const bool tl = (bx > 0 && by > 0) ? true : (bx > 0 ? aT : (by > 0 ? aL : mb_avail_intra (nTL)));
+          mr->pred_avail[i] = (uint8_t) ((l ? 4 : 0) | (tp ? 2 : 0) | (tl ? 1 : 0));
+        }
+      }
       if (i8) { pm[r] = pm[r + 1] = pm[r + 4] = pm[r + 5] = (int8_t)mode; }
       else pm[r] = (int8_t)mode;
     }
@@ -574,6 +611,8 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped) {
     if (cm > 3) return -1;
     m.chroma_mode = (uint8_t)cm;
     resolve_intra (m, mb_addr, modes, i8);
+    st_chroma[mb_addr] = m.chroma_mode;
+    if (mr) mr->type_code = i8 ? 2 : 0;
     const uint32_t c = br.ue();
     if (c > 47) return -1;
     cbp = kCbpIntra[c];
@@ -586,8 +625,11 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped) {
     if (cm > 3) return -1;
     m.chroma_mode = (uint8_t)cm;
     resolve_intra (m, mb_addr, nullptr, false);
+    st_chroma[mb_addr] = m.chroma_mode; st_i16[mb_addr] = m.i16_mode;
+    if (mr) mr->type_code = 1;
   }
   m.cbp = (uint8_t)cbp;
+  st_cbp[mb_addr] = (uint8_t)cbp;
   if (cbp > 0 || i16) {
     const int dqp = br.se();
     if (dqp < -26 || dqp > 25) return -1;
@@ -611,6 +653,13 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped) {
   for (int r = 0; r < 24; r++) if (nz[r]) nzm |= 1u << r;
   m.nz_mask = nzm;
   mb_slice[mb_addr] = (int16_t)slice_no;
+  if (mr) {
+    mr->cbp = (uint8_t)cbp; mr->luma_qp = m.qp_y;
+    mr->chroma_mode = st_chroma[mb_addr]; mr->i16_mode = st_i16[mb_addr];
+    for (int q = 0; q < 4; q++) mr->sub_mb_type[q] = st_sub[(size_t)mb_addr * 4 + q];
+    if (m.flags & LH264_MBF_TRANSFORM8x8) mr->flags |= LH264_MM_T8;
+    mr->coded_mask = m.coded_mask; mr->coef_off = m.coef_off;
+  }
   return br.overrun() ? -1 : 0;
 }
 
@@ -621,22 +670,64 @@ int Decoder::Impl::parse_slice_data (BitReader& br, Decoder* self) {
   const int first = mb_addr;
   bool more = true;
   int rc = 0;
+  // model records: one per MB in slice-data order, with the reference's skip-run / stop-bit bookkeeping
+  // (WelsDecodeMbCavlcPSlice decode_slice.cpp:3880-3960, WelsDecodeSliceForNonRecoding :2192-2252)
+  const size_t rec0 = mrecs.size();
+  auto new_rec = [&] (int addr) -> lh264_model_mb* {
+    if (!want_model) return nullptr;
+    mrecs.emplace_back ();
+    lh264_model_mb* r = &mrecs.back();
+    memset (r, 0, sizeof (*r));
+    r->mb_addr = (uint32_t)addr; r->mb_in_slice = (uint16_t)std::min<size_t> (mrecs.size() - 1 - rec0, 65535);
+    return r;
+  };
   while (more && mb_addr < n_mbs) {
+    bool run_read = false;
     if (sh.slice_type != SLICE_I) {
       const uint32_t run = br.ue();
       if (run > (uint32_t) (n_mbs - mb_addr)) { rc = -1; break; }
-      for (uint32_t i = 0; i < run; i++) { parse_mb (br, mb_addr, true); mb_addr++; }
-      if (run > 0) more = br.more_rbsp_data();
+      run_read = true;
+      for (uint32_t i = 0; i < run; i++) {
+        lh264_model_mb* mr = new_rec (mb_addr);
+        parse_mb (br, mb_addr, true, mr);
+        if (mr) {
+          if (i == 0) { mr->flags |= LH264_MM_EMIT_SKIP_RUN; mr->skip_run = (uint16_t)std::min<uint32_t> (run, 65535); }
+          if (i + 1 == run) { mr->flags |= LH264_MM_STOP_IN_SKIP; if (!br.more_rbsp_data()) mr->flags |= LH264_MM_STOP_BIT; }
+        }
+        mb_addr++;
+      }
+      if (run > 0) { more = br.more_rbsp_data(); run_read = false; }
       if (!more || mb_addr >= n_mbs) break;
     }
-    if (parse_mb (br, mb_addr, false) < 0) { rc = -1; self->stats_.errors++; break; }
+    lh264_model_mb* mr = new_rec (mb_addr);
+    if (mr) {
+      mr->flags |= LH264_MM_WRITE_BLOCK;
+      if (run_read || sh.slice_type == SLICE_I) mr->flags |= LH264_MM_EMIT_SKIP_RUN;   // value 0
+    }
+    if (parse_mb (br, mb_addr, false, mr) < 0) { rc = -1; self->stats_.errors++; if (mr) mrecs.pop_back(); break; }
     mb_addr++;
     more = br.more_rbsp_data();
+    if (mr && !more) mr->flags |= LH264_MM_STOP_BIT;
   }
   lh264_slice_rec& sr = slices.back();
   sr.num_mbs = mb_addr - first;
   decoded += mb_addr - first;
   self->stats_.mbs += mb_addr - first;
+  if (want_model) {
+    lh264_model_slice ms;
+    memset (&ms, 0, sizeof (ms));
+    ms.first_rec = (int32_t)rec0; ms.n_recs = (int32_t) (mrecs.size() - rec0);
+    ms.frame_num = sh.frame_num;
+    ms.slice_type = (uint8_t) (sh.slice_type == SLICE_I ? 2 : 0);
+    ms.num_ref_idx_l0 = (uint8_t) (sh.slice_type == SLICE_P ? sh.num_ref_idx_l0 : P->num_ref_idx_l0_default);
+    // alignment bits after the stop bit (decode_slice.cpp:3133-3147): 7 - (bits used & 7), taken from the byte that
+    // holds the stop bit
+    const size_t used = br.pos();
+    ms.n_pad_bits = (uint8_t) (7 - (used & 7));
+    ms.pad_bits = (uint8_t) (br.size_bits() ? (br.data()[br.payload_end() >> 3] & ((1u << ms.n_pad_bits) - 1)) : 0);
+    ms.chroma_format_idc = 1;
+    mslices.push_back (ms);
+  }
   return rc;
 }
 
@@ -644,6 +735,7 @@ int Decoder::Impl::parse_slice_data (BitReader& br, Decoder* self) {
 Decoder::Decoder (PictureSink* sink) : d_ (new Impl()) { d_->sink = sink; cavlc_init(); }
 Decoder::~Decoder() {}
 const std::vector<ModelMbSide>& Decoder::model_side() const { return d_->side; }
+void Decoder::enable_model (bool on) { d_->want_model = on; }
 
 int Decoder::flush() { return d_->finish_picture (this); }
 

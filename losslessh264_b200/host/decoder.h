@@ -51,6 +51,8 @@ class PictureSink {
   virtual int submit (const lh264_picture_desc& pic, const DecodedPictureInfo& info) = 0;
   // host-side error concealment: copy slot src -> dst (whole picture)
   virtual int copy_slot (int dst, int src) { (void)dst; (void)src; return 0; }
+  // the picture's recompression-model records (only when Decoder::enable_model(true)); pointers valid until return
+  virtual int submit_model (const lh264_model_picture& pic, const DecodedPictureInfo& info) { (void)pic; (void)info; return 0; }
 };
 
 struct DecoderStats { uint64_t nals = 0, slices = 0, pictures = 0, mbs = 0, coef_blocks = 0, errors = 0; };
@@ -68,6 +70,7 @@ class Decoder {
   // pictures completed by the last decode()/flush() call, in output order
   const std::vector<DecodedPictureInfo>& output() const { return out_; }
   void clear_output() { out_.clear(); }
+  void enable_model (bool on);           // produce lh264_model_picture hand-offs (PictureSink::submit_model)
   bool keep_model_side = false;          // fill ModelMbSide records
   const std::vector<ModelMbSide>& model_side() const;
 

@@ -16,9 +16,15 @@ class LhfbSink : public PictureSink {
   ~LhfbSink() override;
   int configure (int mb_w, int mb_h, int n_slots) override;
   int submit (const lh264_picture_desc& pic, const DecodedPictureInfo& info) override;
+  // optional second file: the recompression-model hand-off, one 'LHMD' record per picture:
+  //   u32 magic 'LHMD'; i32 mb_w, mb_h, n_slices, n_recs, n_coef_blocks; lh264_model_slice[n_slices];
+  //   lh264_model_mb[n_recs]; int16[n_coef_blocks][16]
+  void set_model_path (const char* path);
+  int submit_model (const lh264_model_picture& pic, const DecodedPictureInfo& info) override;
   bool ok() const { return f_ != nullptr; }
  private:
   FILE* f_;
+  FILE* fm_ = nullptr;
   int mb_w_ = 0, mb_h_ = 0;
 };
 

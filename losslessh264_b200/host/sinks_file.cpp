@@ -5,7 +5,17 @@
 namespace lh264host {
 
 LhfbSink::LhfbSink (const char* path) : f_ (fopen (path, "wb")) {}
-LhfbSink::~LhfbSink() { if (f_) fclose (f_); }
+LhfbSink::~LhfbSink() { if (f_) fclose (f_); if (fm_) fclose (fm_); }
+void LhfbSink::set_model_path (const char* path) { if (fm_) fclose (fm_); fm_ = path ? fopen (path, "wb") : nullptr; }
+int LhfbSink::submit_model (const lh264_model_picture& pic, const DecodedPictureInfo&) {
+  if (!fm_) return 0;
+  const int32_t hdr[6] = {0x444d484c, pic.mb_w, pic.mb_h, pic.n_slices, pic.n_recs, pic.n_coef_blocks};
+  fwrite (hdr, 4, 6, fm_);
+  fwrite (pic.slices, sizeof (lh264_model_slice), pic.n_slices, fm_);
+  fwrite (pic.recs, sizeof (lh264_model_mb), pic.n_recs, fm_);
+  if (pic.n_coef_blocks) fwrite (pic.coefs, 32, pic.n_coef_blocks, fm_);
+  return 0;
+}
 int LhfbSink::configure (int mb_w, int mb_h, int) { mb_w_ = mb_w; mb_h_ = mb_h; return 0; }
 int LhfbSink::submit (const lh264_picture_desc& pic, const DecodedPictureInfo& info) {
   if (!f_) return -1;

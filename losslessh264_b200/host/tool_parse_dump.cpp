@@ -13,7 +13,7 @@
 using namespace lh264host;
 
 int main (int argc, char** argv) {
-  if (argc < 3) { fprintf (stderr, "usage: %s in.264 out.lhfb [repeat]\n", argv[0]); return 2; }
+  if (argc < 3) { fprintf (stderr, "usage: %s in.264 out.lhfb [repeat] [out.lhmd]\n", argv[0]); return 2; }
   if (!cavlc_selfcheck()) { fprintf (stderr, "CAVLC tables failed the Kraft/prefix self-check\n"); return 3; }
   FILE* f = fopen (argv[1], "rb");
   if (!f) { perror (argv[1]); return 1; }
@@ -28,6 +28,7 @@ int main (int argc, char** argv) {
   for (int it = 0; it < repeat; it++) {
     LhfbSink sink (it == 0 ? argv[2] : "/dev/null");
     Decoder dec (&sink);
+    if (argc > 4 && it == 0) { sink.set_model_path (argv[4]); dec.enable_model (true); }
     const auto t0 = std::chrono::steady_clock::now();
     dec.decode (buf.data(), buf.size());
     dec.flush();
