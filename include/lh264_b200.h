@@ -193,7 +193,8 @@ void lh264_batch_free(lh264_ctx* ctx, lh264_resident_batch* batch);
 /* number of kernel launches issued by this context so far                                   */
 uint64_t lh264_kernel_launches(const lh264_ctx* ctx);
 /* accumulated device time (ms, CUDA events on the context stream) of one kernel family
- * since the last reset: 0 k_recon_rows (inter + intra), 1 unused, 2 k_deblock_rows, 3 all; family = -1 resets and switches the
+ * since the last reset: 0 k_recon_rows (inter + intra), 1 unused, 2 k_deblock_rows, 3 all reconstruction, 4 model generation
+ * kernels (k_model_frame/count/scan/emit), 5 k_model_code; family = -1 resets and switches the
  * (synchronising) per-family timing on, family = -2 switches it off                          */
 float lh264_kernel_ms(lh264_ctx* ctx, int family);
 
@@ -273,6 +274,8 @@ enum {
 #define LH264_MM_STOP_BIT      0x08  /* value of the stop bit: the slice data ends right after this MB (:2200-2201)            */
 #define LH264_MM_T8_CODED      0x10  /* transform_size_8x8_flag is part of the MB syntax (needParseTransformSize8x8)            */
 #define LH264_MM_T8            0x20  /* its value                                                                               */
+#define LH264_MM_LASTDQP_SHIFT 6     /* bits 6-7: sign class of the last non-zero luma QP delta of the slice before this MB
+                                        (0 negative, 1 none yet, 2 positive): getQPLPrior, macroblock_model.cpp:441-444          */
 
 /* One macroblock in slice-data order (skipped MBs included), 128 bytes.                                                       */
 typedef struct lh264_model_mb {
@@ -286,7 +289,8 @@ typedef struct lh264_model_mb {
   uint8_t  luma_qp;          /* pLumaQp[mb]                                                                                     */
   uint8_t  chroma_mode;      /* pChromaPredMode[mb] (availability-resolved; retained from an earlier picture for inter MBs)    */
   uint8_t  i16_mode;         /* pIntraPredMode[mb][7] (likewise)                                                                */
-  uint8_t  reserved;
+  int8_t   qp_delta;         /* luma_qp minus the luma_qp of the previous coded MB of the slice (0 before the first one):
+                                deltaLumaQp, decode_slice.cpp:2267-2274                                                         */
   uint8_t  sub_mb_type[4];   /* pSubMbType[mb][]: 1 8x8, 2 8x4, 4 4x8, 8 4x4 (retained values for I8x8)                          */
   int8_t   ref_idx[4];       /* rtd.iRefIdx[]: per partition (16x8 / 8x16: [0],[1]) or per 8x8 quadrant                           */
   uint8_t  pred_mode[16];    /* I4x4: low nibble = coded mode (iBestIntra4x4PredMode), high nibble = predicted mode;

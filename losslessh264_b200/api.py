@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 from .build import library_path
-from .records import MB_REC, SLICE_REC, Picture
+from .records import MB_REC, MODEL_MB, MODEL_SLICE, NUM_TAGS, SLICE_REC, Picture
 
 _LIB = None
 
@@ -26,6 +26,8 @@ EXPORTS = [
     "lh264_pictures_read_packed", "lh264_host_alloc", "lh264_host_free",
     "lh264_k_idct4x4_add", "lh264_k_idct8x8_add", "lh264_k_mc_luma", "lh264_k_mc_chroma",
     "lh264_k_expand_plane",
+    "lh264_model_open", "lh264_model_close", "lh264_model_submit", "lh264_model_finish", "lh264_model_read",
+    "lh264_model_decisions",
 ]
 
 
@@ -37,6 +39,20 @@ class PictureDesc(C.Structure):
         ("n_coef_blocks", C.c_int32),
         ("slices", C.c_void_p),
         ("mbs", C.c_void_p),
+        ("coefs", C.c_void_p),
+    ]
+
+
+class ModelPictureDesc(C.Structure):
+    _fields_ = [
+        ("model_stream", C.c_int32),
+        ("mb_w", C.c_int32),
+        ("mb_h", C.c_int32),
+        ("n_slices", C.c_int32),
+        ("n_recs", C.c_int32),
+        ("n_coef_blocks", C.c_int32),
+        ("slices", C.c_void_p),
+        ("recs", C.c_void_p),
         ("coefs", C.c_void_p),
     ]
 
@@ -79,6 +95,14 @@ def load_library():
     lib.lh264_k_mc_luma.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     lib.lh264_k_mc_chroma.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     lib.lh264_k_expand_plane.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+    lib.lh264_model_open.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    lib.lh264_model_close.argtypes = [C.c_void_p, C.c_int]
+    lib.lh264_model_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+    lib.lh264_model_finish.argtypes = [C.c_void_p, C.c_int]
+    lib.lh264_model_read.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t]
+    lib.lh264_model_read.restype = C.c_longlong
+    lib.lh264_model_decisions.argtypes = [C.c_void_p, C.c_int]
+    lib.lh264_model_decisions.restype = C.c_ulonglong
     _LIB = lib
     return lib
 
@@ -198,6 +222,42 @@ class Context:
 
     def kernel_ms(self, family):
         return float(self.lib.lh264_kernel_ms(self.h, family))
+
+    # ---- recompression model (compress direction) -------------------------------------------------------
+    def model_open(self, max_mbs, with_8x8=False):
+        """Model state of one stream in HBM (the reference's MacroblockModel + FreqImage + tagged bool coders)."""
+        return _check(self.lib, self.lib.lh264_model_open(self.h, max_mbs, 1 if with_8x8 else 0))
+
+    def model_close(self, ms):
+        _check(self.lib, self.lib.lh264_model_close(self.h, ms))
+
+    def model_submit(self, mpics, model_streams):
+        """Codes one picture (records.ModelPicture) per stream; what WelsDecodeSlice's MB loop does in the reference."""
+        arr = (ModelPictureDesc * len(mpics))()
+        keep = []
+        for i, (p, ms) in enumerate(zip(mpics, model_streams)):
+            sl = np.ascontiguousarray(p.slices, MODEL_SLICE)
+            rc = np.ascontiguousarray(p.recs, MODEL_MB)
+            co = np.ascontiguousarray(p.coefs, np.int16)
+            keep += [sl, rc, co]
+            arr[i] = ModelPictureDesc(ms, p.mb_w, p.mb_h, len(sl), len(rc), len(co), sl.ctypes.data, rc.ctypes.data, co.ctypes.data if len(co) else None)
+        _check(self.lib, self.lib.lh264_model_submit(self.h, arr, len(mpics)))
+        self.sync()
+
+    def model_finish(self, ms):
+        """Ends all tag streams; returns {tag id: bytes} = the contents of the `.pip.<tag>` side files."""
+        _check(self.lib, self.lib.lh264_model_finish(self.h, ms))
+        out = {}
+        for tag in range(NUM_TAGS):
+            n = _check(self.lib, self.lib.lh264_model_read(self.h, ms, tag, None, 0, 0))
+            if n > 0:
+                buf = np.empty(n, np.uint8)
+                _check(self.lib, self.lib.lh264_model_read(self.h, ms, tag, buf.ctypes.data, 0, n))
+                out[tag] = buf.tobytes()
+        return out
+
+    def model_decisions(self, ms):
+        return int(self.lib.lh264_model_decisions(self.h, ms))
 
     # ---- kernel-level entry points ---------------------------------------------------------------
     def k_idct4x4_add(self, pix, coef):

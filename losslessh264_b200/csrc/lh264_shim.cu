@@ -15,6 +15,7 @@
 
 #include "recon_kernels.cuh"
 #include "recon_rows.cuh"
+#include "model_kernels.cuh"
 
 using namespace lh264;
 
@@ -93,7 +94,10 @@ struct lh264_ctx {
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float ms[3] = {0, 0, 0};
   bool timing = false;
+  void* model = nullptr;                     // ModelCtx (model_host.inl), created by the first lh264_model_open
 };
+static void model_destroy (lh264_ctx* c);
+static float model_ms (lh264_ctx* c, int which, bool reset);
 
 extern "C" {
 
@@ -128,6 +132,7 @@ void lh264_ctx_destroy (lh264_ctx* c) {
   if (!c) return;
   cudaSetDevice (c->device);
   cudaStreamSynchronize (c->stream);
+  model_destroy (c);
   for (auto& s : c->streams) if (s.base) cudaFree (s.base);
   c->batch.release(); c->h_pics.release();
   c->pack_jobs.release(); c->h_pack_jobs.release(); c->pack_out.release();
@@ -263,8 +268,9 @@ uint64_t lh264_kernel_launches (const lh264_ctx* c) { return c ? c->launches : 0
 float lh264_kernel_ms (lh264_ctx* c, int family) {
   if (!c) return 0.f;
   if (family == -2) { c->timing = false; return 0.f; }
-  if (family < 0) { c->ms[0] = c->ms[1] = c->ms[2] = 0.f; c->timing = true; return 0.f; }
+  if (family < 0) { c->ms[0] = c->ms[1] = c->ms[2] = 0.f; model_ms (c, 0, true); c->timing = true; return 0.f; }
   if (family < 3) return c->ms[family];
+  if (family == 4 || family == 5) return model_ms (c, family - 4, false);
   return c->ms[0] + c->ms[1] + c->ms[2];
 }
 
@@ -432,3 +438,12 @@ int lh264_k_expand_plane (lh264_ctx* c, const uint8_t* in, int w, int h, int pad
 }
 
 } // extern "C"
+
+#include "model_host.inl"
+
+static float model_ms (lh264_ctx* c, int which, bool reset) {
+  ModelCtx* m = static_cast<ModelCtx*> (c->model);
+  if (!m) return 0.f;
+  if (reset) { m->ms_gen = m->ms_code = 0.f; return 0.f; }
+  return which == 0 ? m->ms_gen : m->ms_code;
+}

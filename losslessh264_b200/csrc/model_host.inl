@@ -1,0 +1,286 @@
+// model_host.inl — host side of the lh264_model_* entry points (included by lh264_shim.cu).
+// Owns the per-stream model state in HBM (prior table, two frames of context records, coder states,
+// output page lists), the output page arena and the staging of a batch of model pictures.
+
+namespace {
+
+using namespace lh264m;
+
+struct MStreamHost {
+  bool open = false;
+  int max_mbs = 0, with_8x8 = 0;
+  MState* d_state = nullptr;
+  uint32_t* d_priors = nullptr;
+  CtxRec* d_frames = nullptr;      // frame[0], frame[1], newrec
+  int* d_order = nullptr;
+  uint32_t* d_pagelist = nullptr;
+  unsigned long long decisions = 0;
+};
+
+struct ModelCtx {
+  std::vector<MStreamHost> streams;
+  // output arena
+  std::vector<uint8_t*> segments;
+  std::vector<uint8_t*> h_page_ptrs;
+  uint8_t** d_page_ptrs = nullptr; size_t page_ptr_cap = 0;
+  unsigned int* d_next = nullptr;
+  unsigned int n_pages = 0, reserved_pages = 0;
+  // batch staging
+  DevBuf<lh264_model_mb> recs; DevBuf<lh264_model_slice> slices; DevBuf<int16_t> coefs;
+  DevBuf<MPicDev> pics; PinBuf<MPicDev> h_pics;
+  DevBuf<uint16_t> lane_cnt; DevBuf<uint32_t> rec_off; DevBuf<uint32_t> pic_total; DevBuf<unsigned long long> dec_base;
+  PinBuf<uint32_t> h_total; PinBuf<unsigned long long> h_base;
+  DevBuf<uint32_t> dec;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  float ms_gen = 0, ms_code = 0;
+};
+
+constexpr unsigned int SEG_PAGES = 2048;         // 32 MB arena segments
+constexpr size_t MAX_ARENA_PAGES = 1u << 18;     // 4 GB of output pages
+
+int model_grow_arena (lh264_ctx* c, ModelCtx* m, unsigned int need_pages);
+
+} // namespace
+
+static ModelCtx* model_ctx (lh264_ctx* c) {
+  if (!c->model) {
+    ModelCtx* m = new (std::nothrow) ModelCtx();
+    if (!m) return nullptr;
+    for (int i = 0; i < 4; i++) cudaEventCreate (&m->ev[i]);
+    c->model = m;
+  }
+  return static_cast<ModelCtx*> (c->model);
+}
+
+static void model_free_stream (MStreamHost& s) {
+  if (s.d_state) cudaFree (s.d_state);
+  if (s.d_priors) cudaFree (s.d_priors);
+  if (s.d_frames) cudaFree (s.d_frames);
+  if (s.d_order) cudaFree (s.d_order);
+  if (s.d_pagelist) cudaFree (s.d_pagelist);
+  s = MStreamHost();
+}
+
+static void model_destroy (lh264_ctx* c) {
+  ModelCtx* m = static_cast<ModelCtx*> (c->model);
+  if (!m) return;
+  for (auto& s : m->streams) if (s.open) model_free_stream (s);
+  for (uint8_t* p : m->segments) cudaFree (p);
+  if (m->d_page_ptrs) cudaFree (m->d_page_ptrs);
+  if (m->d_next) cudaFree (m->d_next);
+  m->recs.release(); m->slices.release(); m->coefs.release(); m->pics.release(); m->h_pics.release();
+  m->lane_cnt.release(); m->rec_off.release(); m->pic_total.release(); m->dec_base.release(); m->h_total.release(); m->h_base.release();
+  m->dec.release();
+  for (int i = 0; i < 4; i++) if (m->ev[i]) cudaEventDestroy (m->ev[i]);
+  delete m;
+  c->model = nullptr;
+}
+
+namespace {
+int model_grow_arena (lh264_ctx* c, ModelCtx* m, unsigned int need_pages) {
+  if (!m->d_page_ptrs) {
+    CK (cudaMalloc (&m->d_page_ptrs, MAX_ARENA_PAGES * sizeof (uint8_t*)));
+    CK (cudaMalloc (&m->d_next, sizeof (unsigned int)));
+    CK (cudaMemsetAsync (m->d_next, 0, sizeof (unsigned int), c->stream));
+  }
+  while (m->n_pages < need_pages) {
+    if (m->n_pages + SEG_PAGES > MAX_ARENA_PAGES) return fail (LH264_E_NOMEM, "model output arena exhausted");
+    uint8_t* seg = nullptr;
+    CK (cudaMalloc (&seg, (size_t)SEG_PAGES * PAGE_SIZE));
+    m->segments.push_back (seg);
+    const size_t first = m->h_page_ptrs.size();
+    for (unsigned int i = 0; i < SEG_PAGES; i++) m->h_page_ptrs.push_back (seg + (size_t)i * PAGE_SIZE);
+    CK (cudaMemcpyAsync (m->d_page_ptrs + first, m->h_page_ptrs.data() + first, SEG_PAGES * sizeof (uint8_t*), cudaMemcpyHostToDevice, c->stream));
+    CK (cudaStreamSynchronize (c->stream));
+    m->n_pages += SEG_PAGES;
+  }
+  return LH264_OK;
+}
+} // namespace
+
+extern "C" {
+
+int lh264_model_open (lh264_ctx* c, int max_mbs, int with_8x8) {
+  if (!c || max_mbs <= 0 || max_mbs > (1 << 20)) return fail (LH264_E_INVALID, "bad model stream geometry");
+  CK (cudaSetDevice (c->device));
+  ModelCtx* m = model_ctx (c);
+  if (!m) return fail (LH264_E_NOMEM, "out of host memory");
+  MStreamHost s;
+  s.open = true; s.max_mbs = max_mbs; s.with_8x8 = with_8x8 ? 1 : 0;
+  const size_t n_priors = with_8x8 ? P_END : P_END_NO8;
+  CK (cudaMalloc (&s.d_state, sizeof (MState)));
+  CK (cudaMalloc (&s.d_priors, n_priors * sizeof (uint32_t)));
+  CK (cudaMalloc (&s.d_frames, (size_t)3 * max_mbs * sizeof (CtxRec)));
+  CK (cudaMalloc (&s.d_order, (size_t)max_mbs * sizeof (int)));
+  CK (cudaMalloc (&s.d_pagelist, (size_t)CT_COUNT * MAX_PAGES_PER_TAG * sizeof (uint32_t)));
+  CK (cudaMemsetAsync (s.d_priors, 0, n_priors * sizeof (uint32_t), c->stream));          // fresh DynProb = all zero bits
+  CK (cudaMemsetAsync (s.d_frames, 0, (size_t)3 * max_mbs * sizeof (CtxRec), c->stream));
+  CK (cudaMemsetAsync (s.d_pagelist, 0, (size_t)CT_COUNT * MAX_PAGES_PER_TAG * sizeof (uint32_t), c->stream));
+  MState h;
+  memset (&h, 0, sizeof (h));
+  h.priors = s.d_priors; h.frame[0] = s.d_frames; h.frame[1] = s.d_frames + max_mbs; h.newrec = s.d_frames + 2 * (size_t)max_mbs;
+  h.order = s.d_order; h.pagelist = s.d_pagelist; h.max_mbs = max_mbs;
+  CK (cudaMemcpyAsync (s.d_state, &h, sizeof (h), cudaMemcpyHostToDevice, c->stream));
+  k_model_init_state<<<1, 32, 0, c->stream>>> (s.d_state);
+  CK (cudaStreamSynchronize (c->stream));                                                  // h is on the stack
+  for (size_t i = 0; i < m->streams.size(); i++) if (!m->streams[i].open) { m->streams[i] = s; return (int)i; }
+  m->streams.push_back (s);
+  return (int)m->streams.size() - 1;
+}
+
+static int model_stream_ok (lh264_ctx* c, int ms, ModelCtx** pm) {
+  if (!c || !c->model) return fail (LH264_E_INVALID, "no model stream is open");
+  ModelCtx* m = static_cast<ModelCtx*> (c->model);
+  if (ms < 0 || ms >= (int)m->streams.size() || !m->streams[ms].open) return fail (LH264_E_INVALID, "bad model stream");
+  *pm = m;
+  return LH264_OK;
+}
+
+int lh264_model_close (lh264_ctx* c, int ms) {
+  ModelCtx* m;
+  int rc = model_stream_ok (c, ms, &m);
+  if (rc) return rc;
+  CK (cudaSetDevice (c->device));
+  CK (cudaStreamSynchronize (c->stream));
+  // the stream's output pages stay in the arena until the context is destroyed (bump allocator)
+  model_free_stream (m->streams[ms]);
+  return LH264_OK;
+}
+
+int lh264_model_submit (lh264_ctx* c, const lh264_model_picture* pics, int n) {
+  if (!c || (n > 0 && !pics) || n < 0) return fail (LH264_E_INVALID, "bad arguments");
+  if (n == 0) return LH264_OK;
+  CK (cudaSetDevice (c->device));
+  ModelCtx* m = model_ctx (c);
+  if (!m) return fail (LH264_E_NOMEM, "out of host memory");
+  size_t tot_rec = 0, tot_sl = 0, tot_blk = 0;
+  for (int i = 0; i < n; i++) {
+    const lh264_model_picture& p = pics[i];
+    ModelCtx* mm;
+    int rc = model_stream_ok (c, p.model_stream, &mm);
+    if (rc) return rc;
+    const MStreamHost& s = m->streams[p.model_stream];
+    if (p.mb_w <= 0 || p.mb_h <= 0 || (long long)p.mb_w * p.mb_h > s.max_mbs) return fail (LH264_E_INVALID, "picture larger than the model stream was opened for");
+    if (p.n_slices <= 0 || p.n_recs <= 0 || !p.slices || !p.recs || p.n_coef_blocks < 0 || (p.n_coef_blocks > 0 && !p.coefs)) return fail (LH264_E_INVALID, "malformed model picture");
+    for (int k = 0; k < p.n_slices; k++) {
+      const lh264_model_slice& sl = p.slices[k];
+      if (sl.first_rec < 0 || sl.n_recs < 0 || sl.first_rec + sl.n_recs > p.n_recs) return fail (LH264_E_INVALID, "slice record range out of bounds");
+      if (sl.slice_type != 0 && sl.slice_type != 2) return fail (LH264_E_UNSUPPORTED, "only P and I slices are modelled");
+    }
+    for (int j = 0; j < i; j++) if (n <= 64 && pics[j].model_stream == p.model_stream) return fail (LH264_E_INVALID, "two pictures of one model stream in a batch");
+    tot_rec += p.n_recs; tot_sl += p.n_slices; tot_blk += p.n_coef_blocks;
+  }
+  CK (m->recs.reserve (tot_rec)); CK (m->slices.reserve (tot_sl)); CK (m->coefs.reserve (tot_blk * 16 + 16));
+  CK (m->pics.reserve (n)); CK (m->lane_cnt.reserve (tot_rec * 32)); CK (m->rec_off.reserve (tot_rec));
+  CK (m->pic_total.reserve (n)); CK (m->dec_base.reserve (n));
+  CK (cudaStreamSynchronize (c->stream));          // pinned staging of the previous batch is free again
+  CK (m->h_pics.reserve (n)); CK (m->h_total.reserve (n)); CK (m->h_base.reserve (n));
+  size_t o_rec = 0, o_sl = 0, o_blk = 0;
+  for (int i = 0; i < n; i++) {
+    const lh264_model_picture& p = pics[i];
+    const MStreamHost& s = m->streams[p.model_stream];
+    CK (cudaMemcpyAsync (m->recs.p + o_rec, p.recs, (size_t)p.n_recs * sizeof (lh264_model_mb), cudaMemcpyHostToDevice, c->stream));
+    CK (cudaMemcpyAsync (m->slices.p + o_sl, p.slices, (size_t)p.n_slices * sizeof (lh264_model_slice), cudaMemcpyHostToDevice, c->stream));
+    if (p.n_coef_blocks) CK (cudaMemcpyAsync (m->coefs.p + o_blk * 16, p.coefs, (size_t)p.n_coef_blocks * 32, cudaMemcpyHostToDevice, c->stream));
+    MPicDev& d = m->h_pics.p[i];
+    d.recs = m->recs.p + o_rec; d.slices = m->slices.p + o_sl; d.coefs = m->coefs.p + o_blk * 16;
+    d.st = s.d_state; d.lane_cnt = m->lane_cnt.p + o_rec * 32; d.rec_off = m->rec_off.p + o_rec;
+    d.n_recs = p.n_recs; d.n_slices = p.n_slices; d.mb_w = p.mb_w; d.mb_h = p.mb_h; d.rec_base = (int)o_rec; d.pad = 0;
+    o_rec += p.n_recs; o_sl += p.n_slices; o_blk += p.n_coef_blocks;
+  }
+  CK (cudaMemcpyAsync (m->pics.p, m->h_pics.p, n * sizeof (MPicDev), cudaMemcpyHostToDevice, c->stream));
+  const int total_recs = (int)tot_rec;
+  const int mb_blocks = (total_recs + MB_WARPS - 1) / MB_WARPS;
+  if (c->timing) CK (cudaEventRecord (m->ev[0], c->stream));
+  k_model_frame<<<n, 32, 0, c->stream>>> (m->pics.p, n);
+  k_model_count<<<mb_blocks, MB_WARPS * 32, 0, c->stream>>> (m->pics.p, n, total_recs);
+  k_model_scan<<<n, 1024, 0, c->stream>>> (m->pics.p, n, m->pic_total.p);
+  c->launches += 3;
+  CK (cudaMemcpyAsync (m->h_total.p, m->pic_total.p, n * sizeof (uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaStreamSynchronize (c->stream));
+  unsigned long long total = 0;
+  for (int i = 0; i < n; i++) { m->h_base.p[i] = total; total += m->h_total.p[i]; m->streams[pics[i].model_stream].decisions += m->h_total.p[i]; }
+  CK (m->dec.reserve ((size_t)total + 32));
+  // every decision shifts out at most 7 bits; a tag needs at most one partly filled page more than its bytes
+  m->reserved_pages += (unsigned int) (total * 7 / 8 / PAGE_SIZE) + (unsigned int)n * CT_COUNT + 1;
+  int rc = model_grow_arena (c, m, m->reserved_pages);
+  if (rc) return rc;
+  CK (cudaMemcpyAsync (m->dec_base.p, m->h_base.p, n * sizeof (unsigned long long), cudaMemcpyHostToDevice, c->stream));
+  ArenaDev ar{ m->d_page_ptrs, m->d_next, m->n_pages };
+  k_model_emit<<<mb_blocks, MB_WARPS * 32, 0, c->stream>>> (m->pics.p, n, total_recs, m->dec.p, m->dec_base.p);
+  if (c->timing) { CK (cudaEventRecord (m->ev[1], c->stream)); CK (cudaEventRecord (m->ev[2], c->stream)); }
+  k_model_code<<<n, 32, 0, c->stream>>> (m->pics.p, n, m->dec.p, m->dec_base.p, m->pic_total.p, ar);
+  c->launches += 2;
+  if (c->timing) {
+    CK (cudaEventRecord (m->ev[3], c->stream));
+    CK (cudaEventSynchronize (m->ev[3]));
+    float t = 0;
+    cudaEventElapsedTime (&t, m->ev[0], m->ev[1]); m->ms_gen += t;
+    cudaEventElapsedTime (&t, m->ev[2], m->ev[3]); m->ms_code += t;
+  }
+  CK (cudaGetLastError());
+  return LH264_OK;
+}
+
+static int model_check_error (lh264_ctx* c, MStreamHost& s) {
+  int err = 0;
+  CK (cudaMemcpyAsync (&err, &s.d_state->error, sizeof (int), cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaStreamSynchronize (c->stream));
+  if (err == 1) return fail (LH264_E_UNSUPPORTED, "a context index left the reference's prior tables (the reference asserts on this input)");
+  if (err == 2) return fail (LH264_E_NOMEM, "model output pages exhausted");
+  return LH264_OK;
+}
+
+int lh264_model_finish (lh264_ctx* c, int ms) {
+  ModelCtx* m;
+  int rc = model_stream_ok (c, ms, &m);
+  if (rc) return rc;
+  CK (cudaSetDevice (c->device));
+  m->reserved_pages += CT_COUNT;
+  if ((rc = model_grow_arena (c, m, m->reserved_pages))) return rc;
+  ArenaDev ar{ m->d_page_ptrs, m->d_next, m->n_pages };
+  k_model_finish<<<1, 32, 0, c->stream>>> (m->streams[ms].d_state, ar);
+  c->launches++;
+  CK (cudaGetLastError());
+  return model_check_error (c, m->streams[ms]);
+}
+
+long long lh264_model_read (lh264_ctx* c, int ms, int tag, uint8_t* dst, size_t offset, size_t cap) {
+  ModelCtx* m;
+  int rc = model_stream_ok (c, ms, &m);
+  if (rc) return rc;
+  int ct = -1;
+  for (int i = 0; i < CT_COUNT; i++) if (kTagOfCompact[i] == tag) ct = i;
+  if (ct < 0) return 0;                              // a tag the model never writes: no side stream
+  CK (cudaSetDevice (c->device));
+  MStreamHost& s = m->streams[ms];
+  if ((rc = model_check_error (c, s))) return rc;
+  struct { uint32_t used; uint32_t finished; } uf;
+  Coder cd;
+  CK (cudaMemcpy (&uf, &s.d_state->used, sizeof (uf), cudaMemcpyDeviceToHost));
+  CK (cudaMemcpy (&cd, &s.d_state->coder[ct], sizeof (cd), cudaMemcpyDeviceToHost));
+  if (!((uf.used >> ct) & 1u)) return 0;
+  const size_t total = cd.pos;
+  if (!dst || cap == 0 || offset >= total) return (long long)total;
+  const size_t end = std::min (total, offset + cap);
+  const size_t p0 = offset >> PAGE_SHIFT, p1 = (end - 1) >> PAGE_SHIFT;
+  std::vector<uint32_t> pl (p1 - p0 + 1);
+  CK (cudaMemcpy (pl.data(), s.d_pagelist + (size_t)ct * MAX_PAGES_PER_TAG + p0, pl.size() * sizeof (uint32_t), cudaMemcpyDeviceToHost));
+  size_t at = offset;
+  while (at < end) {
+    const size_t pg = at >> PAGE_SHIFT, in = at & (PAGE_SIZE - 1), nb = std::min ((size_t)PAGE_SIZE - in, end - at);
+    const uint32_t idx = pl[pg - p0];
+    if (idx == 0 || idx > m->h_page_ptrs.size()) return fail (LH264_E_CUDA, "model output page list is inconsistent");
+    CK (cudaMemcpy (dst + (at - offset), m->h_page_ptrs[idx - 1] + in, nb, cudaMemcpyDeviceToHost));
+    at += nb;
+  }
+  return (long long)total;
+}
+
+unsigned long long lh264_model_decisions (lh264_ctx* c, int ms) {
+  ModelCtx* m;
+  if (model_stream_ok (c, ms, &m)) return 0;
+  return m->streams[ms].decisions;
+}
+
+} // extern "C"

@@ -1,0 +1,788 @@
+// model_kernels.cuh — the recompression model ("Pied Piper" layer) of losslessh264 on sm_100a,
+// compress direction.  Replaces, for a batch of pictures of independent streams, the per-macroblock
+// modelling of WelsDecodeSlice / WelsDecodeSliceForNonRecoding (codec/decoder/core/src/decode_slice.cpp
+// :2959-3171, :2174-2474), the prior selection of MacroblockModel (src/macroblock_model.cpp:375-645),
+// the binarisations of CompressionStream (inc/compression_stream.h:441-591), DynProb adaptation
+// (:87-115) and the VP8 bool coder (inc/bitwriter.h:35-105).
+//
+// Decomposition (B200-first, not the reference's serial per-MB loop).  The reference interleaves three
+// things per binary decision: (1) binarise a symbol and pick a prior from neighbour context, (2) read and
+// adapt that prior's probability, (3) push (bit, probability) through the tag's bool coder.  Only (2) and
+// (3) are serial, and they are serial along different axes: (2) per prior, (3) per tag.  (1) depends on
+// data alone.  So:
+//
+//   k_model_frame   one warp per stream: FreqImage::updateFrame (inc/decoded_macroblock.h:120-165) on the
+//                   previous frame's context records, frame flip / resolution change.
+//   k_model_count   one warp per macroblock record, all streams at once: context record of the MB
+//                   (what the reference stores in FreqImage) + number of decisions per lane role.
+//   k_model_scan    exclusive scan of the decision counts -> position of every MB in its stream's
+//                   decision list.
+//   k_model_emit    one warp per macroblock record: lanes = {MB header, luma DC, chroma DC, 16 luma
+//                   blocks, 8 chroma blocks, slice tail}; each lane binarises its symbols and writes
+//                   32-bit decision words (prior index | tag | bit) in the reference's decision order.
+//   k_model_code    one warp per stream walks the stream's decision list 32 decisions at a time:
+//                   lanes gather the 32 priors, resolve same-prior chains inside the chunk in order,
+//                   write the adapted priors back; then lanes turn into tag owners (<= 30 live tags)
+//                   and each owner pushes its tag's (bit, probability) pairs through its bool coder.
+//
+// Model state per stream lives in HBM: a pruned prior table of 32-bit DynProbs (the reference's 9.4 GB
+// dense table, inc/macroblock_model.h:36-136, restricted to the index ranges that can occur; a fresh
+// DynProb is all zero bits), two frames of 32-byte context records, 32 coder states and paged output.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/lh264_b200.h"
+
+namespace lh264m {
+
+// ---- compact tag ids (lane = tag owner in k_model_code) ---------------------------------------------------
+enum {
+  CT_SKIP = 0, CT_SKIP_END, CT_CBPL, CT_QPL, CT_MB_TYPE, CT_T8, CT_REF, CT_8x8, CT_16x16, CT_PRED_MODE, CT_SUB_MB,
+  CT_MVX, CT_MVY, CT_LDC, CT_CRDC,
+  CT_L0_EOB, CT_L0_BITMASK, CT_L0_EXP, CT_L0_RES, CT_L0_SIGN,
+  CT_LN_BITMASK, CT_LN_EXP, CT_LN_RES, CT_LN_SIGN,
+  CT_C_EOB, CT_C_BITMASK, CT_C_EXP, CT_C_RES, CT_C_SIGN, CT_PAD, CT_COUNT
+};
+static const int kTagOfCompact[CT_COUNT] = {   // billing.h:7-58
+  LH264_TAG_SKIP, LH264_TAG_SKIP_END, LH264_TAG_CBPL, LH264_TAG_QPL, LH264_TAG_MB_TYPE, LH264_TAG_TRANSFORM_8x8, LH264_TAG_REF,
+  LH264_TAG_8x8, LH264_TAG_16x16, LH264_TAG_PRED_MODE, LH264_TAG_SUB_MB, LH264_TAG_MVX, LH264_TAG_MVY, LH264_TAG_LDC, LH264_TAG_CRDC,
+  LH264_TAG_LAC_0_EOB, LH264_TAG_LAC_0_BITMASK, LH264_TAG_LAC_0_EXP, LH264_TAG_LAC_0_RES, LH264_TAG_LAC_0_SIGN,
+  LH264_TAG_LAC_N_BITMASK, LH264_TAG_LAC_N_EXP, LH264_TAG_LAC_N_RES, LH264_TAG_LAC_N_SIGN,
+  LH264_TAG_CRAC_EOB, LH264_TAG_CRAC_BITMASK, LH264_TAG_CRAC_EXP, LH264_TAG_CRAC_RES, LH264_TAG_CRAC_SIGN, LH264_TAG_PADBYTE };
+
+// ---- prior table layout (units: one 32-bit DynProb) ---------------------------------------------------------
+// DynProb word: bits 0-9 counts[0], bits 10-19 counts[1], bits 24-31 prob ^ 0x80 (compression_stream.h:87-115).
+constexpr uint32_t NT = 12;                                  // mb type codes 0..11 (macroblock_model.cpp:647-679)
+constexpr uint32_t P_TEST = 0;                               // ArithmeticCodedOutput::TEST_PROB (shared by all tags)
+constexpr uint32_t P_MBTYPE = 16;                            // [32][2][16]        mbTypePriors
+constexpr uint32_t P_CBPC = P_MBTYPE + 32 * 2 * 16;          // [4][NT][4]         CbpCPrior
+constexpr uint32_t P_CBPL = P_CBPC + 4 * NT * 4;             // [16][NT][16]       CbpLPrior
+constexpr uint32_t P_QPL = P_CBPL + 16 * NT * 16;            // [2][3][128]        mbQPLPrior
+constexpr uint32_t P_NUMREF = P_QPL + 2 * 3 * 128;           // [16][NT][16]       numRefIdxL0ActivePrior
+constexpr uint32_t P_CMODE = P_NUMREF + 16 * NT * 16;        // [8][8]             chromaI8x8ModePriors
+constexpr uint32_t P_PREDMODE = P_CMODE + 64;                // [NT][8][9][16]     predictionModePriors
+constexpr uint32_t P_SUBMB = P_PREDMODE + NT * 8 * 9 * 16;   // [NT][256]          subMbPriors
+constexpr uint32_t P_STOP = P_SUBMB + NT * 256;              // [2048]             stopBitPriors
+constexpr uint32_t P_T8 = P_STOP + 2048;                     // [NT][64]           transform8x8FlagPriors
+constexpr uint32_t P_LDC = P_T8 + NT * 64;                   // [16][2][NT][16]    lumaDCIntPriors   (IntPrior<3,4>)
+constexpr uint32_t P_CDC = P_LDC + 16 * 2 * NT * 16;         // [8][2][NT][16]     chromaDCIntPriors
+constexpr uint32_t P_MVD = P_CDC + 8 * 2 * NT * 16;          // [5][16][16]        motionVectorDifferencePriors (types 3..7)
+constexpr uint32_t P_NZ = P_MVD + 5 * 16 * 16;               // [2][NT][3][27][8]  nonzerosPriors    (UnsignedIntPrior<3,4>)
+constexpr uint32_t P_NZ8 = P_NZ + 2 * NT * 3 * 27 * 8;       // [2][NT][27][8]     nonzerosPriors8x8
+constexpr uint32_t P_SKIP = P_NZ8 + 2 * NT * 27 * 8;         // [512][512]         mbSkipRunPrior (type code 11 only)
+constexpr uint32_t P_AC = P_SKIP + 512 * 512;                // [2][8][3][16][125][16]  acPriors (UEGkIntPrior<14,4,2,4,0>)
+constexpr uint32_t P_AC8 = P_AC + 2 * 8 * 3 * 16 * 125 * 16; // [2][8][64][125][16]     acPriors8x8
+constexpr uint32_t P_END_NO8 = P_AC8;
+constexpr uint32_t P_END = P_AC8 + 2 * 8 * 64 * 125 * 16;
+// slots inside the integer priors
+enum { I_EXP = 0, I_MANT = 3, I_ZERO = 7, I_SIGN = 8 };                      // UnsignedIntPrior<3,4> / IntPrior<3,4>
+enum { U_SIGN = 0, U_FIRST = 1, U_EXP = 5, U_ZERO = 13 };                    // UEGkIntPrior<.,4,.,4,.>: mantissa follows exponent
+#define NO_PRIOR 0xffffffffu
+
+// ---- device structures -----------------------------------------------------------------------------------
+struct __align__ (16) CtxRec {      // what the priors read from a DecodedMacroblock (decoded_macroblock.h:4-104), 32 bytes
+  uint8_t flags;                    // bit0 odata.initialized, bit1 isSkipped
+  uint8_t type_code, cbp, num_ref, chroma_mode, i16_mode;
+  uint16_t cachedSkips;
+  uint8_t cnt[24];                  // non-zero levels per 16-coefficient chunk (16 luma, 4 Cb, 4 Cr), DC slot included
+};
+static_assert (sizeof (CtxRec) == 32, "CtxRec");
+
+struct Coder { uint32_t lowvalue, range; int32_t count; uint32_t pos; };   // vpx_writer, bitwriter.h:22-28
+
+constexpr int PAGE_SHIFT = 14;                          // 16 KB output pages
+constexpr uint32_t PAGE_SIZE = 1u << PAGE_SHIFT;
+constexpr int MAX_PAGES_PER_TAG = 1024;                 // 16 MB per tag per stream
+
+struct MState {                       // per model stream, device resident
+  uint32_t* priors;
+  CtxRec* frame[2];
+  CtxRec* newrec;                     // records of the picture being coded, committed to frame[cur] at its end
+  int* order;                         // slice-data position of every MB address in the picture being coded
+  uint32_t* pagelist;                 // [CT_COUNT][MAX_PAGES_PER_TAG] page index + 1
+  int width, height, frame_len, cur, lastFrameId, max_mbs;
+  int no_past_slice0;
+  int error;                          // 1 prior index outside the reference's tables, 2 out of output pages
+  uint32_t used;                      // compact tags that have a stream (CompressionStream::tag creates it)
+  uint32_t finished;
+  unsigned long long decisions;
+  Coder coder[32];
+};
+
+struct MPicDev {                      // one picture of the batch
+  const lh264_model_mb* recs;
+  const lh264_model_slice* slices;
+  const int16_t* coefs;
+  MState* st;
+  uint16_t* lane_cnt;                 // [n_recs][32]
+  uint32_t* rec_off;                  // [n_recs] position of the record's first decision inside the picture
+  int n_recs, n_slices, mb_w, mb_h;
+  int rec_base;                       // index of the picture's first record in the batch-wide record numbering
+  int pad;
+};
+
+struct ArenaDev { uint8_t** page_ptrs; unsigned int* next; unsigned int n_pages; };
+
+// ---- binarisation: identical decision sequences to the reference, prior = index into the table ---------
+template <bool W> struct Em {
+  uint32_t* out; uint32_t n;
+  __device__ __forceinline__ void put (uint32_t tag, uint32_t prior, uint32_t bit) {
+    if (W) out[n] = (prior << 6) | (tag << 1) | (bit & 1u);
+    n++;
+  }
+};
+// emitBits(data, Branch<n>): compression_stream.h:477-487; pre-order tree layout of Branch<n>::selectBranch :131-139
+template <bool W> __device__ __forceinline__ void e_branch (Em<W>& e, uint32_t tag, uint32_t data, int nbits, uint32_t tree) {
+  for (int n = nbits; n >= 1; n--) {
+    const uint32_t bit = (data >> (n - 1)) & 1u;
+    e.put (tag, tree, bit);
+    tree += bit ? (1u << (n - 1)) : 1u;
+  }
+}
+// emitBits(data, nBits) through TEST_PROB: :441-448
+template <bool W> __device__ __forceinline__ void e_raw (Em<W>& e, uint32_t tag, uint32_t data, int nbits) {
+  for (int i = 0; i < nbits; i++) e.put (tag, P_TEST, (data >> (nbits - 1 - i)) & 1u);
+}
+// emitBitsZeroToPow2Inclusive<n>: :455-463
+template <bool W> __device__ __forceinline__ void e_zero_to_pow2 (Em<W>& e, uint32_t tag, uint32_t data, int nbits, uint32_t priors, uint32_t preferred) {
+  e.put (tag, priors, data != preferred);
+  if (data != preferred) e_branch (e, tag, data > preferred ? data - 1 : data, nbits, priors + 1);
+}
+// emitUnary: :465-474, UnaryIntPrior<N>::at :175-177
+template <bool W> __device__ __forceinline__ void e_unary (Em<W>& e, uint32_t tag, int data, uint32_t base, int n, int early) {
+  for (int i = 0; i < data; i++) {
+    e.put (tag, base + min (i, n - 1), 1);
+    if (i == early - 1) return;
+  }
+  e.put (tag, base + min (data, n - 1), 0);
+}
+// CompressionStream::emitInt: :523-572 (mantissa size 4)
+template <bool W> __device__ __forceinline__ void e_int (Em<W>& e, int data, uint32_t expo, int n_exp, uint32_t mant, int order, uint32_t zero, uint32_t sign,
+                                                         uint32_t tagExp, uint32_t tagMant, uint32_t tagZero, uint32_t tagSign) {
+  if (zero != NO_PRIOR) { e.put (tagZero, zero, data == 0); if (data == 0) return; }
+  if (sign != NO_PRIOR) { e.put (tagSign, sign, data > 0); if (data < 0) data = -data; }
+  data--;
+  const int data_high = 1 + (data >> order);
+  const int log2 = 31 - __clz (data_high);
+  e_unary (e, tagExp, log2, expo, n_exp, -1);
+  int lo = 0, hi = 4;
+  for (int k = 0; k < log2 + order; k++) {
+    const uint32_t bit = k < log2 ? (uint32_t) (data_high >> (log2 - 1 - k)) & 1u : (uint32_t) (data >> (order - 1 - (k - log2))) & 1u;
+    if (hi > lo) {
+      const int mid = (hi + lo) >> 1;
+      e.put (tagMant, mant + mid, bit);
+      if (bit) lo = mid + 1; else hi = mid;
+    } else e.put (tagMant, P_TEST, bit);
+  }
+}
+// CompressionStream::emitUEGkInt: :575-591; p = base of a UEGk prior with n_exp exponent slots
+template <bool W> __device__ __forceinline__ void e_uegk (Em<W>& e, int data, int threshold, uint32_t p, int n_exp, int order,
+                                                          uint32_t tagExp, uint32_t tagMant, uint32_t tagZero, uint32_t tagSign) {
+  e.put (tagZero, p + U_ZERO, data == 0);
+  if (data == 0) return;
+  e.put (tagSign, p + U_SIGN, data < 0);
+  if (data < 0) data = -data;
+  e_unary (e, tagMant, data - 1, p + U_FIRST, 4, threshold);
+  if (data - 1 >= threshold)
+    e_int (e, data - 1 - threshold, p + U_EXP, n_exp, p + U_EXP + n_exp, order, p + U_EXP + n_exp + 4, NO_PRIOR, tagExp, tagMant, tagZero, tagSign);
+}
+
+__constant__ uint8_t c_zz16[16] = { 0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15 };     // decode_slice.cpp:2035-2040
+__constant__ uint8_t c_zz64[64] = {                                                              // decode_slice.cpp:2041-2050
+  0, 1, 5, 6, 14, 15, 27, 28, 2, 4, 7, 13, 16, 26, 29, 42, 3, 8, 12, 17, 25, 30, 41, 43, 9, 11, 18, 24, 31, 40, 44, 53,
+  10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38, 46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63 };
+__constant__ uint8_t c_scan4[16] = { 0, 1, 4, 5, 2, 3, 6, 7, 8, 9, 12, 13, 10, 11, 14, 15 };    // g_kuiScan4
+
+// encode4x4<n>: decode_slice.cpp:2060-2094 with getACPrior4x4/8x8 (macroblock_model.cpp:562-604; the neighbour terms of
+// the index are the constant 2 because priorCoef only fills `past`, :196-262).  nzp = nonzeros prior base.
+template <bool W> __device__ void gen_block (Em<W>& e, const int16_t* ac, int n, bool emit_dc, int color, uint32_t nzp, uint32_t acbase) {
+  const uint8_t* zz = n == 16 ? c_zz16 : c_zz64;
+  int nonzeros = 0;
+  for (int i = emit_dc ? 0 : 1; i < n; i++) nonzeros += ac[zz[i]] != 0;
+  const uint32_t tEob = color ? CT_C_EOB : CT_L0_EOB;
+  e_int (e, nonzeros, nzp + I_EXP, 3, nzp + I_MANT, 0, nzp + I_ZERO, NO_PRIOR, tEob, tEob, tEob, tEob);
+  int left = nonzeros, emitted = 0, prev = 0, prev2 = 0;
+  for (int i = emit_dc ? 0 : 1; i < n && left > 0; i++) {
+    const int c = ac[zz[i]];
+    const uint32_t tb = color ? CT_C_BITMASK : (i == 0 ? CT_L0_BITMASK : CT_LN_BITMASK);
+    const uint32_t p = acbase + ((uint32_t) (emitted * 5 + min (4, left)) * 25u + (uint32_t)min (4, max (0, prev + 2)) * 5u + (uint32_t)min (4, max (0, prev2 + 2))) * 16u;
+    e_uegk (e, c, 14, p, 2, 0, tb + 1, tb + 2, tb, tb + 3);
+    prev2 = prev; prev = c; emitted++;
+    if (c) left--;
+  }
+}
+// which EXP tag streams a block creates without necessarily coding into them (tag().billTo(), decode_slice.cpp:2081-2083)
+__device__ __forceinline__ uint32_t block_touch (const int16_t* ac, int n, bool emit_dc, int color) {
+  const uint8_t* zz = n == 16 ? c_zz16 : c_zz64;
+  int nonzeros = 0;
+  for (int i = emit_dc ? 0 : 1; i < n; i++) nonzeros += ac[zz[i]] != 0;
+  if (!nonzeros) return 0;
+  if (color) return 1u << CT_C_EXP;
+  uint32_t m = emit_dc ? 1u << CT_L0_EXP : 0;
+  // a second coded position exists unless the only non-zero level is the first one coded
+  if (!emit_dc || nonzeros > 1 || ac[0] == 0) m |= 1u << CT_LN_EXP;
+  return m;
+}
+
+struct WarpMb {                       // per-warp staging in shared memory
+  lh264_model_mb rec;                 // 128 B
+  int16_t lev[384];                   // dense levels, 24 chunks of 16
+  CtxRec L, A, P;
+  uint32_t flagsLAP;                  // bit0 L, bit1 A, bit2 P present
+};
+
+__device__ __forceinline__ void load_rec (WarpMb& s, const lh264_model_mb* r, const int16_t* coefs, int lane) {
+  reinterpret_cast<uint32_t*> (&s.rec)[lane] = __ldg (reinterpret_cast<const uint32_t*> (r) + lane);
+  __syncwarp();
+  const uint32_t mask = (s.rec.flags & LH264_MM_WRITE_BLOCK) ? s.rec.coded_mask : 0u;
+  const uint32_t* src = reinterpret_cast<const uint32_t*> (coefs) + (size_t)s.rec.coef_off * 8;
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    const int w = lane + 32 * i, blk = w >> 3;
+    uint32_t v = 0;
+    if ((mask >> blk) & 1) v = __ldg (src + __popc (mask & ((1u << blk) - 1)) * 8 + (w & 7));
+    reinterpret_cast<uint32_t*> (s.lev)[w] = v;
+  }
+  __syncwarp();
+}
+__device__ __forceinline__ int chunk_count (const int16_t* a) {
+  int n = 0;
+#pragma unroll
+  for (int i = 0; i < 16; i++) n += a[i] != 0;
+  return n;
+}
+
+// lane roles of a macroblock warp, in the reference's emission order
+enum { ROLE_HEADER = 0, ROLE_LDC = 1, ROLE_CDC = 2, ROLE_LUMA0 = 3, ROLE_CHROMA0 = 19, ROLE_TAIL = 27 };
+
+// Decisions of one lane role.  Returns through e; touch = EXP tags created.
+template <bool W> __device__ void gen_lane (Em<W>& e, const WarpMb& s, const lh264_model_slice& sl, int lane, bool last_of_slice,
+                                            const uint8_t* own_cnt, uint32_t* touch, int* error) {
+  const lh264_model_mb& r = s.rec;
+  const int tc = r.type_code;
+  const uint32_t st = sl.slice_type == 0 ? 0u : 1u;
+  const bool write = r.flags & LH264_MM_WRITE_BLOCK;
+  const bool hasL = s.flagsLAP & 1, hasA = s.flagsLAP & 2, hasP = s.flagsLAP & 4;
+  const int cbpL = r.cbp & 15, cbpC = r.cbp >> 4;
+  if (lane == ROLE_HEADER) {
+    const uint32_t stop_idx = P_STOP + min ((int)r.mb_in_slice, 2047);
+    if (r.flags & LH264_MM_EMIT_SKIP_RUN) {         // decode_slice.cpp:2210-2217; getSkipRunPrior macroblock_model.cpp:375-390
+      const int cs = hasP ? s.P.cachedSkips : 0;
+      const int prior = cs / 8 + (cs % 8 ? 1 : 0);
+      if (prior >= 512) { *error = 1; return; }
+      e_branch (e, CT_SKIP, r.skip_run, 9, P_SKIP + (uint32_t)prior * 512u);
+    }
+    if (r.flags & LH264_MM_STOP_IN_SKIP) e.put (CT_SKIP_END, stop_idx, (r.flags & LH264_MM_STOP_BIT) != 0);
+    if (!write) return;
+    e.put (CT_SKIP_END, stop_idx, (r.flags & LH264_MM_STOP_BIT) != 0);                     // :2252
+    {                                                 // getMacroblockTypePrior macroblock_model.cpp:415-438
+      int prior = 15, prevType = 15;
+      if (hasA) prior = s.A.type_code;
+      if (hasL) prior = s.L.type_code;
+      if (hasP) prevType = s.P.type_code;
+      e_branch (e, CT_MB_TYPE, (uint32_t)tc, 4, P_MBTYPE + ((uint32_t) (prior + prevType) * 2u + (st == 0)) * 16u);
+    }
+    if (sl.chroma_format_idc != 0) e_branch (e, CT_CBPL, (uint32_t)cbpC, 2, P_CBPC + ((uint32_t) (hasP ? s.P.cbp >> 4 : 0) * NT + tc) * 4u);
+    e_branch (e, CT_CBPL, (uint32_t)cbpL, 4, P_CBPL + ((uint32_t) (hasP ? s.P.cbp & 15 : 0) * NT + tc) * 16u);
+    {                                                 // :2267-2270, swizzle_sign macroblock_model.cpp:715-721
+      const int d = r.qp_delta;
+      const uint32_t sw = d >= 0 ? (uint32_t)d << 1 : (((uint32_t) (-d - 1)) << 1) | 1u;
+      e_zero_to_pow2 (e, CT_QPL, sw, 7, P_QPL + ((r.mb_in_slice == 0 ? 3u : 0u) + ((r.flags >> LH264_MM_LASTDQP_SHIFT) & 3u)) * 128u, 0);
+    }
+    const int num_ref = sl.num_ref_idx_l0;
+    {
+      const int pr = hasP ? s.P.num_ref : 0;
+      if (pr >= 16) { *error = 1; return; }
+      e_branch (e, CT_REF, (uint32_t)num_ref, 4, P_NUMREF + ((uint32_t)pr * NT + tc) * 16u);
+    }
+    int refBits = 0;
+    while ((1 << refBits) < num_ref) refBits++;
+    {
+      const uint32_t pc = hasP ? min ((int)s.P.chroma_mode, 6) : 7;
+      e_zero_to_pow2 (e, CT_8x8, r.chroma_mode, 3, P_CMODE + pc * 8u, pc);
+      const uint32_t pl = hasP ? min ((int)s.P.i16_mode, 6) : 7;       // the CHROMA table: macroblock_model.cpp:632
+      e_zero_to_pow2 (e, CT_16x16, r.i16_mode, 3, P_CMODE + pl * 8u, pl);
+    }
+    if (tc == 0)
+      for (int i = 0; i < 16; i++)
+        e_branch (e, CT_PRED_MODE, r.pred_mode[i] & 15u, 4, P_PREDMODE + (((uint32_t)tc * 8u + (r.pred_avail[i] & 7u)) * 9u + min (r.pred_mode[i] >> 4, 8)) * 16u);
+    if (tc == 2) {
+      for (int i = 0; i < 4; i++) e_branch (e, CT_PRED_MODE, r.pred_mode[i] & 15u, 4, P_PREDMODE + (((uint32_t)tc * 8u + 6u) * 9u + 1u) * 16u);
+      for (int i = 0; i < 4; i++) e_branch (e, CT_SUB_MB, r.sub_mb_type[i], 8, P_SUBMB + (uint32_t)tc * 256u);
+      for (int i = 0; i < 4; i++) e_raw (e, CT_REF, (uint8_t)r.ref_idx[i], refBits);
+    } else if (tc == 6 || tc == 7) {
+      for (int i = 0; i < 4; i++) e_branch (e, CT_SUB_MB, r.sub_mb_type[i], 8, P_SUBMB + (uint32_t)tc * 256u);
+      if (tc == 6) for (int i = 0; i < 4; i++) e_raw (e, CT_REF, (uint8_t)r.ref_idx[i], refBits);
+      for (int i = 0; i < 4; i++) {
+        const int sub = r.sub_mb_type[i];
+        const int cnt = sub == 1 ? 1 : (sub == 8 ? 4 : 2), step = sub == 2 ? 2 : 1;
+        if (sub != 1 && sub != 2 && sub != 4 && sub != 8) { *error = 1; return; }
+        for (int j = 0; j < cnt; j++) {
+          const int b = c_scan4[(i << 2) + j * step];
+          const uint32_t p = P_MVD + ((uint32_t) (tc - 3) * 16u + b) * 16u;
+          e_uegk (e, r.mvd[b][0], 9, p, 3, 3, CT_MVX, CT_MVX, CT_MVX, CT_MVX);
+          e_uegk (e, r.mvd[b][1], 9, p, 3, 3, CT_MVY, CT_MVY, CT_MVY, CT_MVY);
+        }
+      }
+    } else if (tc == 4 || tc == 5) {
+      for (int i = 0; i < 2; i++) e_raw (e, CT_REF, (uint32_t) (int)r.ref_idx[i], refBits);
+      for (int i = 0; i < 2; i++) {
+        const int b = tc == 4 ? i * 8 : i * 2;
+        const uint32_t p = P_MVD + ((uint32_t) (tc - 3) * 16u + b) * 16u;
+        e_uegk (e, r.mvd[b][0], 9, p, 3, 3, CT_MVX, CT_MVX, CT_MVX, CT_MVX);
+        e_uegk (e, r.mvd[b][1], 9, p, 3, 3, CT_MVY, CT_MVY, CT_MVY, CT_MVY);
+      }
+    } else if (tc == 3) {
+      e_raw (e, CT_REF, (uint32_t) (int)r.ref_idx[0], refBits);
+      const uint32_t p = P_MVD;
+      e_uegk (e, r.mvd[0][0], 9, p, 3, 3, CT_MVX, CT_MVX, CT_MVX, CT_MVX);
+      e_uegk (e, r.mvd[0][1], 9, p, 3, 3, CT_MVY, CT_MVY, CT_MVY, CT_MVY);
+    }
+    if (r.flags & LH264_MM_T8_CODED) e.put (CT_T8, P_T8 + (uint32_t)tc * 64u + min ((int)r.luma_qp, 63), (r.flags & LH264_MM_T8) != 0);
+    return;
+  }
+  if (lane == ROLE_TAIL) {                            // slice trailing bits, decode_slice.cpp:3133-3147
+    if (last_of_slice && sl.n_pad_bits) e_raw (e, CT_PAD, sl.pad_bits, sl.n_pad_bits);
+    return;
+  }
+  if (!write) return;
+  if (lane == ROLE_LDC) {                             // :2396-2402
+    if (tc != 1) return;
+    for (int i = 0; i < 16; i++) {
+      const uint32_t p = P_LDC + (((uint32_t)i * 2u + st) * NT + tc) * 16u;
+      e_int (e, s.lev[16 * i], p + I_EXP, 3, p + I_MANT, 0, p + I_ZERO, p + I_SIGN, CT_LDC, CT_LDC, CT_LDC, CT_LDC);
+    }
+    return;
+  }
+  if (lane == ROLE_CDC) {                             // :2403-2409
+    if (cbpC != 1 && cbpC != 2) return;
+    for (int i = 0; i < 8; i++) {
+      const uint32_t p = P_CDC + (((uint32_t)i * 2u + st) * NT + tc) * 16u;
+      e_int (e, s.lev[256 + 16 * i], p + I_EXP, 3, p + I_MANT, 0, p + I_ZERO, p + I_SIGN, CT_CRDC, CT_CRDC, CT_CRDC, CT_CRDC);
+    }
+    return;
+  }
+  const bool t8 = r.flags & LH264_MM_T8;
+  if (lane >= ROLE_LUMA0 && lane < ROLE_CHROMA0) {    // :2410-2426
+    const int idx = lane - ROLE_LUMA0;
+    if (!(cbpL & (1 << (idx >> 2)))) return;
+    if (tc > 7 && !t8) {                              // I_PCM with retained cbp: all levels are zero, only the non-zero count is coded
+    }
+    const bool emit_dc = tc != 1;
+    if (t8) {
+      if (idx & 3) return;
+      // getNonzerosPrior8x8 macroblock_model.cpp:529-560
+      const int q = idx >> 2;
+      int past = 0, left = 0, above = 0;
+      if (hasP) past = s.P.cnt[idx] + s.P.cnt[idx + 1] + s.P.cnt[idx + 2] + s.P.cnt[idx + 3];
+      if ((q & 1) == 0) { if (hasL) { const int k = (q + 1) * 4; left = s.L.cnt[k] + s.L.cnt[k + 1] + s.L.cnt[k + 2] + s.L.cnt[k + 3]; } }
+      else { const int k = (q - 1) * 4; left = own_cnt[k] + own_cnt[k + 1] + own_cnt[k + 2] + own_cnt[k + 3]; }
+      if ((q & 2) == 0) { if (hasA) { const int k = (q + 2) * 4; above = s.A.cnt[k] + s.A.cnt[k + 1] + s.A.cnt[k + 2] + s.A.cnt[k + 3]; } }
+      else { const int k = (q - 2) * 4; above = own_cnt[k] + own_cnt[k + 1] + own_cnt[k + 2] + own_cnt[k + 3]; }
+      const uint32_t nzp = P_NZ8 + (((st * NT + tc) * 3u + min (2, past)) * 3u + min (2, left)) * 3u * 8u + (uint32_t)min (2, above) * 8u;
+      if (tc > 7) { *error = 1; return; }
+      const uint32_t acb = P_AC8 + ((st * 8u + tc) * 64u) * 125u * 16u;
+      if (touch) *touch |= block_touch (&s.lev[idx * 16], 64, emit_dc, 0);
+      gen_block (e, &s.lev[idx * 16], 64, emit_dc, 0, nzp, acb);
+    } else {
+      // getNonzerosPrior4x4 macroblock_model.cpp:478-527 (colour 0)
+      int past = 0, left = 0, above = 0;
+      if (hasP) past = s.P.cnt[idx];
+      if ((idx & 3) == 0) { if (hasL) left = s.L.cnt[idx + 3]; } else left = own_cnt[idx - 1];
+      if (idx < 4) { if (hasA) above = s.A.cnt[idx + 12]; } else above = own_cnt[idx - 4];
+      const uint32_t nzp = P_NZ + ((((st * NT + tc) * 3u + 0u) * 3u + min (2, past)) * 3u + min (2, left)) * 3u * 8u + (uint32_t)min (2, above) * 8u;
+      const uint32_t acb = P_AC + (((st * 8u + min (tc, 7)) * 3u + 0u) * 16u) * 125u * 16u;
+      if (touch) *touch |= block_touch (&s.lev[idx * 16], 16, emit_dc, 0);
+      gen_block (e, &s.lev[idx * 16], 16, emit_dc, 0, nzp, acb);
+    }
+    return;
+  }
+  if (lane >= ROLE_CHROMA0 && lane < ROLE_TAIL) {     // :2427-2435
+    if (cbpC != 2) return;
+    const int i = lane - ROLE_CHROMA0;                // 0..7: Cb 0-3, Cr 4-7
+    const int color = i < 4 ? 1 : 2;
+    const bool emit_dc = !(cbpC == 1 || cbpC == 2);
+    int past = 0, left = 0, above = 0;
+    if (hasP) past = s.P.cnt[16 + i];
+    if ((i & 1) == 0) { if (hasL) left = s.L.cnt[16 + i + 1]; } else left = own_cnt[16 + i - 1];
+    if ((i & 2) == 0) { if (hasA) above = s.A.cnt[16 + i + 2]; } else above = own_cnt[16 + i - 2];
+    const uint32_t nzp = P_NZ + ((((st * NT + tc) * 3u + color) * 3u + min (2, past)) * 3u + min (2, left)) * 3u * 8u + (uint32_t)min (2, above) * 8u;
+    const uint32_t acb = P_AC + (((st * 8u + min (tc, 7)) * 3u + color) * 16u) * 125u * 16u;
+    if (touch) *touch |= block_touch (&s.lev[256 + i * 16], 16, emit_dc, color);
+    gen_block (e, &s.lev[256 + i * 16], 16, emit_dc, color, nzp, acb);
+    return;
+  }
+}
+
+// ---- k_model_frame: per-stream frame bookkeeping -------------------------------------------------------------
+// WelsDecodeSlice decode_slice.cpp:3032-3046 for the first slice of the picture (later slices of the same picture repeat
+// the same updateFrame on unchanged data) and FreqImage::updateFrame decoded_macroblock.h:120-165.
+__global__ void __launch_bounds__ (32) k_model_frame (const MPicDev* pics, int n_pics) {
+  const int p = blockIdx.x, lane = threadIdx.x;
+  if (p >= n_pics) return;
+  const MPicDev& pic = pics[p];
+  MState* st = pic.st;
+  int cur = st->cur, len = st->frame_len;
+  const int frame = pic.slices[0].frame_num;
+  if (frame != st->lastFrameId) cur ^= 1;
+  CtxRec* f = st->frame[1 - cur];
+  // isSkipped / cachedSkips of the other frame: run of all-zero MBs followed by a non-zero one gets its length written into
+  // the LAST `run` records ending at the non-zero one (the reference's off-by-one is kept)
+  int run_start = 0;                                 // first index of the current zero run
+  for (int base = 0; base < len; base += 32) {
+    const int i = base + lane;
+    bool zeroed = false, valid = i < len;
+    if (valid) {
+      const uint4* q = reinterpret_cast<const uint4*> (&f[i]);
+      const uint4 a = q[0], b = q[1];
+      zeroed = ((a.z | a.w | b.x | b.y | b.z | b.w) == 0);
+      uint8_t fl = (uint8_t) (a.x & 0xff);
+      fl = zeroed ? (fl | 2) : (fl & ~2);
+      f[i].flags = fl;
+    }
+    unsigned nzmask = __ballot_sync (0xffffffffu, valid && !zeroed);
+    while (nzmask) {
+      const int l = __ffs (nzmask) - 1;
+      nzmask &= nzmask - 1;
+      const int at = base + l, run = at - run_start;
+      if (run > 0) for (int j = at - run + 1 + lane; j <= at; j += 32) f[j].cachedSkips = (uint16_t)run;
+      run_start = at + 1;
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+    st->cur = cur; st->lastFrameId = frame;
+    st->no_past_slice0 = 0;
+  }
+  if (st->width != pic.mb_w || st->height != pic.mb_h) {     // std::vector::resize semantics, decode_slice.cpp:3036-3045
+    const int n = pic.mb_w * pic.mb_h;
+    for (int k = 0; k < 2; k++)
+      for (int j = len + lane; j < n; j += 32) { uint4* q = reinterpret_cast<uint4*> (&st->frame[k][j]); q[0] = make_uint4 (0, 0, 0, 0); q[1] = make_uint4 (0, 0, 0, 0); }
+    __syncwarp();
+    if (lane == 0) { st->no_past_slice0 = 1; st->width = pic.mb_w; st->height = pic.mb_h; st->frame_len = n; }
+  }
+  for (int j = lane; j < pic.mb_w * pic.mb_h; j += 32) st->order[j] = 0x7fffffff;
+}
+
+// ---- k_model_count -------------------------------------------------------------------------------------------------
+constexpr int MB_WARPS = 4;
+
+__device__ __forceinline__ const lh264_model_slice* find_slice (const MPicDev& pic, int rec, int lane, int* sidx) {
+  int found = -1;
+  for (int b = 0; b < pic.n_slices && found < 0; b += 32) {
+    const int i = b + lane;
+    bool hit = false;
+    if (i < pic.n_slices) { const int f = pic.slices[i].first_rec; hit = rec >= f && rec < f + pic.slices[i].n_recs; }
+    const unsigned m = __ballot_sync (0xffffffffu, hit);
+    if (m) found = b + __ffs (m) - 1;
+  }
+  *sidx = found;
+  return found >= 0 ? &pic.slices[found] : nullptr;
+}
+
+// batch-wide record numbering -> (picture, record): binary search over MPicDev::rec_base
+__device__ __forceinline__ int find_pic (const MPicDev* pics, int n_pics, int g) {
+  int lo = 0, hi = n_pics - 1;
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (pics[mid].rec_base <= g) lo = mid; else hi = mid - 1; }
+  return lo;
+}
+
+__global__ void __launch_bounds__ (MB_WARPS * 32) k_model_count (const MPicDev* pics, int n_pics, int total_recs) {
+  __shared__ WarpMb sm[MB_WARPS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x * MB_WARPS + warp;
+  if (g >= total_recs) return;
+  const int p = find_pic (pics, n_pics, g);
+  const MPicDev& pic = pics[p];
+  const int ri = g - pic.rec_base;
+  WarpMb& s = sm[warp];
+  load_rec (s, &pic.recs[ri], pic.coefs, lane);
+  int sidx;
+  const lh264_model_slice* sl = find_slice (pic, ri, lane, &sidx);
+  if (!sl) { pic.lane_cnt[(size_t)ri * 32 + lane] = 0; return; }
+  MState* st = pic.st;
+  const lh264_model_mb& r = s.rec;
+  const bool write = r.flags & LH264_MM_WRITE_BLOCK;
+  // context record of this MB: a coded MB stores its own data, a skipped one copies the co-located record of the other frame
+  // (decode_slice.cpp:3098-3109)
+  const int mycnt = lane < 24 ? chunk_count (&s.lev[lane * 16]) : 0;
+  const bool in_range = (int)r.mb_addr < pic.mb_w * pic.mb_h;
+  if (in_range) {
+    CtxRec* dst = &st->newrec[r.mb_addr];
+    if (write) {
+      if (lane < 24) dst->cnt[lane] = (uint8_t)mycnt;
+      if (lane == 24) {
+        dst->flags = 1; dst->type_code = r.type_code; dst->cbp = r.cbp; dst->num_ref = sl->num_ref_idx_l0;
+        dst->chroma_mode = r.chroma_mode; dst->i16_mode = r.i16_mode; dst->cachedSkips = 0;
+      }
+    } else if (lane < 8) {
+      reinterpret_cast<uint32_t*> (dst)[lane] = reinterpret_cast<const uint32_t*> (&st->frame[1 - st->cur][r.mb_addr])[lane];
+    }
+    if (lane == 0) st->order[r.mb_addr] = ri;
+  }
+  // decision counts per lane role (the binarisation is context free, so neighbours are not needed here)
+  __shared__ uint8_t own[MB_WARPS][24];
+  if (lane < 24) own[warp][lane] = (uint8_t)mycnt;
+  if (lane == 0) s.flagsLAP = 0;
+  __syncwarp();
+  Em<false> e; e.out = nullptr; e.n = 0;
+  int err = 0;
+  uint32_t touch = 0;
+  const bool last = ri == sl->first_rec + sl->n_recs - 1;
+  if (in_range) gen_lane<false> (e, s, *sl, lane, last, own[warp], &touch, &err);
+  pic.lane_cnt[(size_t)ri * 32 + lane] = (uint16_t)min (e.n, 65535u);
+  if (e.n > 65535u) err = 1;
+  touch = __reduce_or_sync (0xffffffffu, touch);
+  if (lane == 0 && touch) atomicOr (&st->used, touch);
+  if (err) st->error = 1;
+}
+
+// ---- k_model_scan: one block per picture ---------------------------------------------------------------------------------
+__global__ void __launch_bounds__ (1024) k_model_scan (const MPicDev* pics, int n_pics, uint32_t* pic_total) {
+  __shared__ uint32_t wsum[32];
+  __shared__ uint32_t carry_s;
+  const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (p >= n_pics) return;
+  const MPicDev& pic = pics[p];
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < pic.n_recs; base += 1024) {
+    const int i = base + tid;
+    uint32_t v = 0;
+    if (i < pic.n_recs) {
+      const uint4* q = reinterpret_cast<const uint4*> (pic.lane_cnt + (size_t)i * 32);
+#pragma unroll
+      for (int k = 0; k < 4; k++) {
+        const uint4 a = q[k];
+        v += (a.x & 0xffff) + (a.x >> 16) + (a.y & 0xffff) + (a.y >> 16) + (a.z & 0xffff) + (a.z >> 16) + (a.w & 0xffff) + (a.w >> 16);
+      }
+    }
+    uint32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync (0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      uint32_t w = wsum[lane], z = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync (0xffffffffu, z, o); if (lane >= o) z += y; }
+      wsum[lane] = z - w;
+    }
+    __syncthreads();
+    const uint32_t excl = carry_s + wsum[warp] + x - v;
+    if (i < pic.n_recs) pic.rec_off[i] = excl;
+    __syncthreads();
+    if (tid == 1023) carry_s = excl + v;
+    __syncthreads();
+  }
+  if (tid == 0) pic_total[p] = carry_s;
+}
+
+// ---- k_model_emit ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__ (MB_WARPS * 32) k_model_emit (const MPicDev* pics, int n_pics, int total_recs, uint32_t* dec, const unsigned long long* dec_base) {
+  __shared__ WarpMb sm[MB_WARPS];
+  __shared__ uint8_t own[MB_WARPS][24];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = blockIdx.x * MB_WARPS + warp;
+  if (g >= total_recs) return;
+  const int p = find_pic (pics, n_pics, g);
+  const MPicDev& pic = pics[p];
+  const int ri = g - pic.rec_base;
+  WarpMb& s = sm[warp];
+  load_rec (s, &pic.recs[ri], pic.coefs, lane);
+  int sidx;
+  const lh264_model_slice* sl = find_slice (pic, ri, lane, &sidx);
+  if (!sl) return;
+  MState* st = pic.st;
+  const lh264_model_mb& r = s.rec;
+  if ((int)r.mb_addr >= pic.mb_w * pic.mb_h) return;
+  const int mbx = (int) (r.mb_addr % (unsigned)pic.mb_w), mby = (int) (r.mb_addr / (unsigned)pic.mb_w);
+  // Neighbors::init macroblock_model.cpp:9-44.  LEFT/ABOVE come from the frame being written: the record of this picture if
+  // that MB precedes this one in slice-data order, else whatever the buffer still holds from two frames ago.
+  if (lane < 24) {
+    const int which = lane >> 3, w = lane & 7;         // 0 L, 1 A, 2 P
+    uint32_t v = 0;
+    if (which == 0 && mbx > 0) {
+      const int nb = (int)r.mb_addr - 1;
+      const CtxRec* src = st->order[nb] < ri ? &st->newrec[nb] : &st->frame[st->cur][nb];
+      v = reinterpret_cast<const uint32_t*> (src)[w];
+    } else if (which == 1 && mby > 0) {
+      const int nb = (int)r.mb_addr - pic.mb_w;
+      const CtxRec* src = st->order[nb] < ri ? &st->newrec[nb] : &st->frame[st->cur][nb];
+      v = reinterpret_cast<const uint32_t*> (src)[w];
+    } else if (which == 2 && !(st->no_past_slice0 && sidx == 0)) {
+      v = reinterpret_cast<const uint32_t*> (&st->frame[1 - st->cur][r.mb_addr])[w];
+    }
+    reinterpret_cast<uint32_t*> (&s.L)[lane] = v;      // L, A, P are contiguous
+  }
+  if (lane < 24) own[warp][lane] = (uint8_t)chunk_count (&s.lev[lane * 16]);
+  __syncwarp();
+  if (lane == 0) s.flagsLAP = (s.L.flags & 1u) | ((s.A.flags & 1u) << 1) | ((s.P.flags & 1u) << 2);
+  __syncwarp();
+  // position of this lane's decisions
+  const uint32_t cnt = pic.lane_cnt[(size_t)ri * 32 + lane];
+  uint32_t x = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync (0xffffffffu, x, o); if (lane >= o) x += y; }
+  Em<true> e;
+  e.out = dec + dec_base[p] + pic.rec_off[ri] + (x - cnt);
+  e.n = 0;
+  int err = 0;
+  const bool last = ri == sl->first_rec + sl->n_recs - 1;
+  if (cnt) gen_lane<true> (e, s, *sl, lane, last, own[warp], nullptr, &err);
+  if (err || e.n != cnt) st->error = 1;
+}
+
+// ---- k_model_code ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t dp_prob (uint32_t w) { return (w >> 24) ^ 0x80u; }
+__device__ __forceinline__ uint32_t dp_update (uint32_t w, uint32_t bit) {   // DynProb::updateProb compression_stream.h:101-110
+  uint32_t c0 = w & 0x3ffu, c1 = (w >> 10) & 0x3ffu;
+  if (bit) c1++; else c0++;
+  const uint32_t prob = (256u * (c0 + 1u)) / (c0 + c1 + 2u);
+  if (c0 + c1 > 512u) { c0 = (c0 + 1u) >> 1; c1 = (c1 + 1u) >> 1; }
+  return c0 | (c1 << 10) | ((prob ^ 0x80u) << 24);
+}
+
+struct OutCursor { uint8_t* page; };
+
+__device__ __forceinline__ uint8_t* out_ptr (MState* st, const ArenaDev& ar, int tag, uint32_t pos, bool alloc) {
+  uint32_t* slot = &st->pagelist[tag * MAX_PAGES_PER_TAG + (pos >> PAGE_SHIFT)];
+  uint32_t pg = *slot;
+  if (pg == 0) {
+    if (!alloc || (pos >> PAGE_SHIFT) >= (uint32_t)MAX_PAGES_PER_TAG) return nullptr;
+    const unsigned int idx = atomicAdd (ar.next, 1u);
+    if (idx >= ar.n_pages) return nullptr;
+    pg = idx + 1;
+    *slot = pg;
+  }
+  return ar.page_ptrs[pg - 1] + (pos & (PAGE_SIZE - 1));
+}
+
+// vpx_write, bitwriter.h:35-105
+__device__ __forceinline__ void coder_write (Coder& c, uint8_t*& page, MState* st, const ArenaDev& ar, int tag, uint32_t bit, uint32_t prob, int* error) {
+  const uint32_t split = 1u + (((c.range - 1u) * prob) >> 8);
+  uint32_t range = split, low = c.lowvalue;
+  if (bit) { low += split; range = c.range - split; }
+  int shift = __clz (range) - 24;
+  range <<= shift;
+  int count = c.count + shift;
+  if (count >= 0) {
+    const int offset = shift - count;
+    if ((low << (offset - 1)) & 0x80000000u) {      // carry into the bytes already written
+      int x = (int)c.pos - 1;
+      while (x >= 0) {
+        uint8_t* q = out_ptr (st, ar, tag, (uint32_t)x, false);
+        if (!q) break;
+        if (*q == 0xff) { *q = 0; x--; } else { *q += 1; break; }
+      }
+    }
+    if ((c.pos & (PAGE_SIZE - 1)) == 0 || !page) {
+      uint8_t* q = out_ptr (st, ar, tag, c.pos, true);
+      if (!q) { *error = 2; return; }
+      page = q - (c.pos & (PAGE_SIZE - 1));
+    }
+    page[c.pos & (PAGE_SIZE - 1)] = (uint8_t) (low >> (24 - offset));
+    c.pos++;
+    low <<= offset;
+    shift = count;
+    low &= 0xffffffu;
+    count -= 8;
+  }
+  low <<= shift;
+  c.count = count; c.lowvalue = low; c.range = range;
+}
+
+// one warp per stream; blockDim = 32
+__global__ void __launch_bounds__ (32) k_model_code (const MPicDev* pics, int n_pics, const uint32_t* dec, const unsigned long long* dec_base,
+                                                     const uint32_t* pic_total, ArenaDev ar) {
+  __shared__ uint32_t smask[32];
+  const int p = blockIdx.x, lane = threadIdx.x;
+  if (p >= n_pics) return;
+  const MPicDev& pic = pics[p];
+  MState* st = pic.st;
+  if (st->error) return;
+  uint32_t* priors = st->priors;
+  const uint32_t n = pic_total[p];
+  const uint32_t* d = dec + dec_base[p];
+  Coder c = st->coder[lane];
+  uint8_t* page = nullptr;
+  int err = 0;
+  bool coded = false;
+  const uint32_t lt = (1u << lane) - 1u;
+  for (uint32_t k = 0; k < n; k += 32) {
+    const bool valid = k + lane < n;
+    const uint32_t w = valid ? d[k + lane] : 0xffffffffu;
+    const uint32_t idx = w >> 6, tag = valid ? (w >> 1) & 31u : 31u, bit = w & 1u;
+    // (2) priors: gather, resolve same-prior chains in decision order, scatter
+    uint32_t sv = valid ? priors[idx] : 0u;
+    const unsigned peers = __match_any_sync (0xffffffffu, idx);
+    const unsigned bits = __ballot_sync (0xffffffffu, bit);
+    unsigned m = peers & lt;
+    while (m) { const int j = __ffs (m) - 1; m &= m - 1; sv = dp_update (sv, (bits >> j) & 1u); }
+    const uint32_t prob = dp_prob (sv);
+    sv = dp_update (sv, bit);
+    if (valid && (peers >> lane) <= 1u) priors[idx] = sv;      // the last decision of the chain stores
+    // (3) bool coders: lane t owns compact tag t
+    const unsigned tpeers = __match_any_sync (0xffffffffu, tag);
+    smask[lane] = 0;
+    __syncwarp();
+    if (valid && (tpeers & lt) == 0) smask[tag] = tpeers;
+    __syncwarp();
+    unsigned mine = smask[lane];
+    const uint32_t pb = (prob << 1) | bit;
+    const int iters = __reduce_max_sync (0xffffffffu, (unsigned)__popc (mine));
+    for (int it = 0; it < iters; it++) {
+      const int src = mine ? __ffs (mine) - 1 : 0;
+      const uint32_t v = __shfl_sync (0xffffffffu, pb, src);
+      if (mine && !err) { coder_write (c, page, st, ar, lane, v & 1u, v >> 1, &err); coded = true; mine &= mine - 1; }
+    }
+    __syncwarp();
+  }
+  st->coder[lane] = c;
+  const unsigned usedm = __ballot_sync (0xffffffffu, coded);
+  const unsigned errm = __ballot_sync (0xffffffffu, err != 0);
+  if (lane == 0) {
+    if (usedm) atomicOr (&st->used, usedm);
+    st->decisions += n;
+    if (errm) st->error = 2;
+  }
+  // commit the picture's context records (decode_slice.cpp:3104-3108)
+  for (int i = lane; i < pic.n_recs; i += 32) {
+    const uint32_t a = pic.recs[i].mb_addr;
+    if ((int)a < pic.mb_w * pic.mb_h) {
+      const uint4* q = reinterpret_cast<const uint4*> (&st->newrec[a]);
+      uint4* o = reinterpret_cast<uint4*> (&st->frame[st->cur][a]);
+      o[0] = q[0]; o[1] = q[1];
+    }
+  }
+}
+
+// vpx_stop_encode (bitwriter.cpp:28-38) for every tag stream that exists; one warp per stream
+__global__ void __launch_bounds__ (32) k_model_finish (MState* st, ArenaDev ar) {
+  const int lane = threadIdx.x;
+  if (st->finished) return;
+  Coder c = st->coder[lane];
+  uint8_t* page = nullptr;
+  int err = 0;
+  if ((st->used >> lane) & 1u) {
+    for (int i = 0; i < 32; i++) coder_write (c, page, st, ar, lane, 0, 128, &err);
+    if (c.pos > 0 && !err) {
+      const uint8_t* lastb = out_ptr (st, ar, lane, c.pos - 1, false);
+      if (lastb && (*lastb & 0xe0) == 0xc0) {
+        uint8_t* q = out_ptr (st, ar, lane, c.pos, true);
+        if (q) { *q = 0; c.pos++; } else err = 2;
+      }
+    }
+  }
+  st->coder[lane] = c;
+  const unsigned errm = __ballot_sync (0xffffffffu, err != 0);
+  __syncwarp();
+  if (lane == 0) { st->finished = 1; if (errm) st->error = 2; }
+}
+
+__global__ void k_model_init_state (MState* st) {
+  const int lane = threadIdx.x;
+  if (lane < 32) { st->coder[lane].lowvalue = 0; st->coder[lane].range = 255; st->coder[lane].count = -24; st->coder[lane].pos = 0; }
+}
+
+} // namespace lh264m

@@ -681,6 +681,7 @@ int Decoder::Impl::parse_slice_data (BitReader& br, Decoder* self) {
     r->mb_addr = (uint32_t)addr; r->mb_in_slice = (uint16_t)std::min<size_t> (mrecs.size() - 1 - rec0, 65535);
     return r;
   };
+  int m_cached_qp = 0, m_last_dqp = 0;                // uiCachedLumaQp / uiLastNonzeroDeltaLumaQp, decode_slice.cpp:3061-3062
   while (more && mb_addr < n_mbs) {
     bool run_read = false;
     if (sh.slice_type != SLICE_I) {
@@ -705,6 +706,13 @@ int Decoder::Impl::parse_slice_data (BitReader& br, Decoder* self) {
       if (run_read || sh.slice_type == SLICE_I) mr->flags |= LH264_MM_EMIT_SKIP_RUN;   // value 0
     }
     if (parse_mb (br, mb_addr, false, mr) < 0) { rc = -1; self->stats_.errors++; if (mr) mrecs.pop_back(); break; }
+    if (mr) {                                         // decode_slice.cpp:2267-2274
+      const int d = (int)mr->luma_qp - m_cached_qp;
+      mr->qp_delta = (int8_t)d;
+      mr->flags |= (uint16_t) ((m_last_dqp < 0 ? 0 : (m_last_dqp == 0 ? 1 : 2)) << LH264_MM_LASTDQP_SHIFT);
+      m_cached_qp = mr->luma_qp;
+      if (d) m_last_dqp = d;
+    }
     mb_addr++;
     more = br.more_rbsp_data();
     if (mr && !more) mr->flags |= LH264_MM_STOP_BIT;

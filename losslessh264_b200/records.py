@@ -217,3 +217,75 @@ def load_fixture(path):
 
 def n_slots_needed(pics):
     return max(max(p.cur_slot for p in pics), max(int(p.slices["ref_slot"].max()) for p in pics)) + 1
+
+
+# ---- recompression-model hand-off (lh264_model_mb / lh264_model_slice, include/lh264_b200.h) -----------
+MM_EMIT_SKIP_RUN, MM_STOP_IN_SKIP, MM_WRITE_BLOCK, MM_STOP_BIT, MM_T8_CODED, MM_T8 = 1, 2, 4, 8, 16, 32
+NUM_TAGS = 70
+
+MODEL_MB = np.dtype(
+    [
+        ("mb_addr", "<u4"),
+        ("flags", "<u2"),
+        ("skip_run", "<u2"),
+        ("mb_in_slice", "<u2"),
+        ("type_code", "u1"),
+        ("cbp", "u1"),
+        ("luma_qp", "u1"),
+        ("chroma_mode", "u1"),
+        ("i16_mode", "u1"),
+        ("qp_delta", "i1"),
+        ("sub_mb_type", "u1", (4,)),
+        ("ref_idx", "i1", (4,)),
+        ("pred_mode", "u1", (16,)),
+        ("pred_avail", "u1", (16,)),
+        ("coded_mask", "<u4"),
+        ("coef_off", "<u4"),
+        ("mvd", "<i2", (16, 2)),
+    ]
+)
+assert MODEL_MB.itemsize == 128
+
+MODEL_SLICE = np.dtype(
+    [
+        ("first_rec", "<i4"),
+        ("n_recs", "<i4"),
+        ("frame_num", "<i4"),
+        ("slice_type", "u1"),
+        ("num_ref_idx_l0", "u1"),
+        ("n_pad_bits", "u1"),
+        ("pad_bits", "u1"),
+        ("chroma_format_idc", "u1"),
+        ("reserved", "u1", (3,)),
+    ]
+)
+assert MODEL_SLICE.itemsize == 20
+
+
+@dataclass
+class ModelPicture:
+    """The recompression-model records of one coded picture (all slices, slice-data order)."""
+
+    mb_w: int
+    mb_h: int
+    slices: np.ndarray
+    recs: np.ndarray
+    coefs: np.ndarray  # (n_blocks, 16) int16 quantised levels, the picture's coefficient pool
+
+
+def read_lhmd(path, max_pictures=None):
+    """Parses the 'LHMD' dump written by the host decoder (LhfbSink::submit_model)."""
+    pics = []
+    with open(path, "rb") as f:
+        while max_pictures is None or len(pics) < max_pictures:
+            try:
+                magic, mb_w, mb_h, n_sl, n_rec, n_blk = _read(f, "<6i")
+            except EOFError:
+                break
+            if magic != 0x444D484C:
+                raise ValueError("bad lhmd record")
+            sl = np.frombuffer(f.read(n_sl * MODEL_SLICE.itemsize), MODEL_SLICE, n_sl).copy()
+            rc = np.frombuffer(f.read(n_rec * MODEL_MB.itemsize), MODEL_MB, n_rec).copy()
+            co = np.frombuffer(f.read(n_blk * 32), "<i2").reshape(n_blk, 16).copy()
+            pics.append(ModelPicture(mb_w, mb_h, sl, rc, co))
+    return pics

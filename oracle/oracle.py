@@ -17,9 +17,10 @@ _LIB = None
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    src = os.path.join(_HERE, "recon_oracle.c")
-    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-        subprocess.check_call(["gcc", "-O2", "-std=c99", "-fPIC", "-shared", "-o", so, src])
+    srcs = [os.path.join(_HERE, "recon_oracle.c"), os.path.join(_HERE, "model_oracle.c")]
+    dep = max(os.path.getmtime(p) for p in srcs + [os.path.join(os.path.dirname(_HERE), "include", "lh264_b200.h")])
+    if force or not os.path.exists(so) or os.path.getmtime(so) < dep:
+        subprocess.check_call(["gcc", "-O2", "-std=c99", "-fPIC", "-shared", "-o", so] + srcs)
     return so
 
 
@@ -44,6 +45,14 @@ def lib():
     if _LIB is None:
         _LIB = C.CDLL(build())
         _LIB.ora_recon_picture.restype = C.c_int
+        _LIB.mo_open.restype = C.c_void_p
+        _LIB.mo_close.argtypes = [C.c_void_p]
+        _LIB.mo_picture.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _LIB.mo_finish.argtypes = [C.c_void_p]
+        _LIB.mo_tag_bytes.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+        _LIB.mo_tag_bytes.restype = C.c_long
+        _LIB.mo_decisions.argtypes = [C.c_void_p]
+        _LIB.mo_decisions.restype = C.c_ulonglong
     return _LIB
 
 
@@ -113,3 +122,41 @@ def expand_plane(plane, pad):
     out = np.zeros((h + 2 * pad, w + 2 * pad), np.uint8)
     lib().ora_expand_plane(C.c_void_p(plane.ctypes.data), w, h, pad, C.c_void_p(out.ctypes.data))
     return out
+
+
+class ModelOracle:
+    """Sequential CPU restatement of the recompression model for one stream (oracle/model_oracle.c)."""
+
+    def __init__(self):
+        self._h = lib().mo_open()
+
+    def picture(self, mp):
+        """mp: losslessh264_b200.records.ModelPicture."""
+        sl = np.ascontiguousarray(mp.slices)
+        rc = np.ascontiguousarray(mp.recs)
+        co = np.ascontiguousarray(mp.coefs)
+        r = lib().mo_picture(self._h, mp.mb_w, mp.mb_h, len(sl), sl.ctypes.data, rc.ctypes.data, co.ctypes.data)
+        if r != 0:
+            raise RuntimeError("mo_picture: index outside the reference's prior tables (the reference asserts here)")
+
+    def finish(self):
+        """Ends every tag stream; returns {tag: bytes} for the tags that were used."""
+        lib().mo_finish(self._h)
+        out = {}
+        for t in range(70):
+            p = C.c_void_p()
+            n = lib().mo_tag_bytes(self._h, t, C.byref(p))
+            if n >= 0:
+                out[t] = C.string_at(p, n)
+        return out
+
+    def decisions(self):
+        return int(lib().mo_decisions(self._h))
+
+    def close(self):
+        if self._h:
+            lib().mo_close(self._h)
+            self._h = None
+
+    def __del__(self):
+        self.close()
