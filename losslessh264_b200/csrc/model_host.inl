@@ -226,7 +226,8 @@ static int model_check_error (lh264_ctx* c, MStreamHost& s) {
   int err = 0;
   CK (cudaMemcpyAsync (&err, &s.d_state->error, sizeof (int), cudaMemcpyDeviceToHost, c->stream));
   CK (cudaStreamSynchronize (c->stream));
-  if (err == 1) return fail (LH264_E_UNSUPPORTED, "a context index left the reference's prior tables (the reference asserts on this input)");
+  if (err >= 11 && err <= 14) return fail (LH264_E_UNSUPPORTED, "a context index left the reference's prior tables (the reference asserts on this input; site %d)", err);
+  if (err) { if (err != 2) return fail (LH264_E_CUDA, "model kernels: internal inconsistency %d", err); }
   if (err == 2) return fail (LH264_E_NOMEM, "model output pages exhausted");
   return LH264_OK;
 }

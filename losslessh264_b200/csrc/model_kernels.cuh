@@ -102,7 +102,7 @@ struct MState {                       // per model stream, device resident
   uint32_t* pagelist;                 // [CT_COUNT][MAX_PAGES_PER_TAG] page index + 1
   int width, height, frame_len, cur, lastFrameId, max_mbs;
   int no_past_slice0;
-  int error;                          // 1 prior index outside the reference's tables, 2 out of output pages
+  int error;                          // 11-14 a context index outside the reference's prior tables, 15-16 internal, 2 out of output pages
   uint32_t used;                      // compact tags that have a stream (CompressionStream::tag creates it)
   uint32_t finished;
   unsigned long long decisions;
@@ -269,7 +269,7 @@ template <bool W> __device__ void gen_lane (Em<W>& e, const WarpMb& s, const lh2
     if (r.flags & LH264_MM_EMIT_SKIP_RUN) {         // decode_slice.cpp:2210-2217; getSkipRunPrior macroblock_model.cpp:375-390
       const int cs = hasP ? s.P.cachedSkips : 0;
       const int prior = cs / 8 + (cs % 8 ? 1 : 0);
-      if (prior >= 512) { *error = 1; return; }
+      if (prior >= 512) { *error = 11; return; }
       e_branch (e, CT_SKIP, r.skip_run, 9, P_SKIP + (uint32_t)prior * 512u);
     }
     if (r.flags & LH264_MM_STOP_IN_SKIP) e.put (CT_SKIP_END, stop_idx, (r.flags & LH264_MM_STOP_BIT) != 0);
@@ -292,7 +292,7 @@ template <bool W> __device__ void gen_lane (Em<W>& e, const WarpMb& s, const lh2
     const int num_ref = sl.num_ref_idx_l0;
     {
       const int pr = hasP ? s.P.num_ref : 0;
-      if (pr >= 16) { *error = 1; return; }
+      if (pr >= 16) { *error = 12; return; }
       e_branch (e, CT_REF, (uint32_t)num_ref, 4, P_NUMREF + ((uint32_t)pr * NT + tc) * 16u);
     }
     int refBits = 0;
@@ -316,7 +316,7 @@ template <bool W> __device__ void gen_lane (Em<W>& e, const WarpMb& s, const lh2
       for (int i = 0; i < 4; i++) {
         const int sub = r.sub_mb_type[i];
         const int cnt = sub == 1 ? 1 : (sub == 8 ? 4 : 2), step = sub == 2 ? 2 : 1;
-        if (sub != 1 && sub != 2 && sub != 4 && sub != 8) { *error = 1; return; }
+        if (sub != 1 && sub != 2 && sub != 4 && sub != 8) { *error = 13; return; }
         for (int j = 0; j < cnt; j++) {
           const int b = c_scan4[(i << 2) + j * step];
           const uint32_t p = P_MVD + ((uint32_t) (tc - 3) * 16u + b) * 16u;
@@ -380,7 +380,7 @@ template <bool W> __device__ void gen_lane (Em<W>& e, const WarpMb& s, const lh2
       if ((q & 2) == 0) { if (hasA) { const int k = (q + 2) * 4; above = s.A.cnt[k] + s.A.cnt[k + 1] + s.A.cnt[k + 2] + s.A.cnt[k + 3]; } }
       else { const int k = (q - 2) * 4; above = own_cnt[k] + own_cnt[k + 1] + own_cnt[k + 2] + own_cnt[k + 3]; }
       const uint32_t nzp = P_NZ8 + (((st * NT + tc) * 3u + min (2, past)) * 3u + min (2, left)) * 3u * 8u + (uint32_t)min (2, above) * 8u;
-      if (tc > 7) { *error = 1; return; }
+      if (tc > 7) { *error = 14; return; }
       const uint32_t acb = P_AC8 + ((st * 8u + tc) * 64u) * 125u * 16u;
       if (touch) *touch |= block_touch (&s.lev[idx * 16], 64, emit_dc, 0);
       gen_block (e, &s.lev[idx * 16], 64, emit_dc, 0, nzp, acb);
@@ -520,10 +520,17 @@ __global__ void __launch_bounds__ (MB_WARPS * 32) k_model_count (const MPicDev* 
     }
     if (lane == 0) st->order[r.mb_addr] = ri;
   }
-  // decision counts per lane role (the binarisation is context free, so neighbours are not needed here)
+  // decision counts per lane role.  The binarisation is context free except for the two intra mode symbols, whose
+  // "preferred" value comes from the co-located record of the other frame (PAST), so only that neighbour is loaded here.
   __shared__ uint8_t own[MB_WARPS][24];
   if (lane < 24) own[warp][lane] = (uint8_t)mycnt;
-  if (lane == 0) s.flagsLAP = 0;
+  if (lane < 24) {
+    uint32_t v = 0;
+    if (lane >= 16 && in_range && !(st->no_past_slice0 && sidx == 0)) v = reinterpret_cast<const uint32_t*> (&st->frame[1 - st->cur][r.mb_addr])[lane & 7];
+    reinterpret_cast<uint32_t*> (&s.L)[lane] = v;
+  }
+  __syncwarp();
+  if (lane == 0) s.flagsLAP = (s.P.flags & 1u) << 2;
   __syncwarp();
   Em<false> e; e.out = nullptr; e.n = 0;
   int err = 0;
@@ -531,10 +538,10 @@ __global__ void __launch_bounds__ (MB_WARPS * 32) k_model_count (const MPicDev* 
   const bool last = ri == sl->first_rec + sl->n_recs - 1;
   if (in_range) gen_lane<false> (e, s, *sl, lane, last, own[warp], &touch, &err);
   pic.lane_cnt[(size_t)ri * 32 + lane] = (uint16_t)min (e.n, 65535u);
-  if (e.n > 65535u) err = 1;
+  if (e.n > 65535u) err = 15;
   touch = __reduce_or_sync (0xffffffffu, touch);
   if (lane == 0 && touch) atomicOr (&st->used, touch);
-  if (err) st->error = 1;
+  if (err) st->error = err;
 }
 
 // ---- k_model_scan: one block per picture ---------------------------------------------------------------------------------
@@ -630,7 +637,7 @@ __global__ void __launch_bounds__ (MB_WARPS * 32) k_model_emit (const MPicDev* p
   int err = 0;
   const bool last = ri == sl->first_rec + sl->n_recs - 1;
   if (cnt) gen_lane<true> (e, s, *sl, lane, last, own[warp], nullptr, &err);
-  if (err || e.n != cnt) st->error = 1;
+  if (err) st->error = err; else if (e.n != cnt) st->error = 16;
 }
 
 // ---- k_model_code ------------------------------------------------------------------------------------------------------
