@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 STREAM = os.path.join(ROOT, "tests", "golden", "streams", "syn1080p_cbp_ippp_16f.264")
 PARSE_TOOL = os.path.join(ROOT, "losslessh264_b200", "_lib", "lh264_parse_dump")
 REF_DEC = os.path.join(ROOT, "oracle", "_ref", "h264dec")
-METRIC, UNIT = "1080p decode frames/s", "frames/s"
+METRIC, UNIT = "1080p decode + recompress frames/s", "frames/s"
 WORKLOAD = "syn1080p_cbp_ippp_16f x S independent streams (BASELINE config 4), 1 picture per stream per step"
 MB_PER_PIC = 120 * 68
 PIC_BYTES = 1920 * 1088 * 3 // 2
@@ -141,15 +141,30 @@ def bench_reference(args):
 
 
 def parse_stream():
-    from losslessh264_b200.records import read_lhfb
+    from losslessh264_b200.records import read_lhfb, read_lhmd
 
     with tempfile.TemporaryDirectory() as tmp:
-        out = os.path.join(tmp, "s.lhfb")
-        r = subprocess.run([PARSE_TOOL, STREAM, out, "3"], capture_output=True, text=True)
+        out, md = os.path.join(tmp, "s.lhfb"), os.path.join(tmp, "s.lhmd")
+        r = subprocess.run([PARSE_TOOL, STREAM, out, "3", md], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("host parser failed: " + r.stderr[-300:])
         m = re.search(r"\(([\d.]+) pictures/s\)", r.stderr)
-        return read_lhfb(out), float(m.group(1)) if m else None
+        return read_lhfb(out), read_lhmd(md), float(m.group(1)) if m else None
+
+
+def pinned_copy(arr, keep):
+    """Copy of a numpy array in pinned host memory (lh264_host_alloc), so that H2D copies are real async DMA."""
+    import numpy as np
+    from losslessh264_b200.api import PinnedArray
+
+    a = np.ascontiguousarray(arr)
+    if a.nbytes == 0:
+        return a
+    pin = PinnedArray(a.nbytes)
+    keep.append(pin)
+    v = pin.array.view(a.dtype).reshape(a.shape)
+    v[...] = a
+    return v
 
 
 def main():
@@ -163,6 +178,8 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         return bench_reference(args)
+
+    import copy
 
     import numpy as np
     import torch
@@ -181,13 +198,17 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     S, K, W = args.streams, args.steps, max(args.warmup, 3)
 
-    pics, parse_pps = parse_stream()
+    pics, mpics, parse_pps = parse_stream()
     n_frames = len(pics)
+    assert len(mpics) == n_frames
     mb_w, mb_h = pics[0].mb_w, pics[0].mb_h
+    stream_bytes = os.path.getsize(STREAM)
     tstream = torch.cuda.Stream()
     ctx = Context(local, tstream.cuda_stream)
     streams = [ctx.open_stream(mb_w, mb_h, n_slots_needed(pics)) for _ in range(S)]
+    mstreams = [ctx.model_open(mb_w * mb_h) for _ in range(S)]
     batches = [ctx.upload_batch([p] * S, streams) for p in pics]   # S independent copies of every picture's records
+    mbatches = [ctx.model_upload_batch([p] * S, mstreams) for p in mpics]
     ctx.sync()
 
     def barrier():
@@ -203,66 +224,90 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- value: records resident in HBM -------------------------------------------------------
-    # every step touches S x (records + 2-4 picture planes) = S x ~14 MB >> 126 MB L2: inputs larger than L2
+    # ---- value: records resident in HBM; a step = reconstruction + recompression model of one picture per stream -----
+    # every step touches S x (records + 2-4 picture planes + decision list) = S x ~16 MB >> 126 MB L2: inputs larger than L2
     step_no = 0
 
-    def resident_steps(n):
+    def resident_steps(n, model=True):
         nonlocal step_no
         for _ in range(n):
             ctx.recon_resident(batches[step_no % n_frames])
+            if model:
+                ctx.model_run_resident(mbatches[step_no % n_frames])
             step_no += 1
+
+    def timed(n, model):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(tstream)
+        resident_steps(n, model)
+        e1.record(tstream)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
 
     with torch.cuda.stream(tstream):
         resident_steps(W + (-W) % n_frames)            # warm-up ends on a sequence boundary
-        barrier()
         sampler = ClockSampler(local)
         sampler.start()
         l0 = ctx.kernel_launches()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(tstream)
-        resident_steps(K)
-        e1.record(tstream)
-        barrier()
-        ms = max_over_ranks(e0.elapsed_time(e1))
+        ms = timed(K, True)
         launches = ctx.kernel_launches() - l0
         sampler.stop_flag = True
+        step_no = 0
+        ms_dec = timed(K, False)                       # reconstruction alone (decode without the recompression model)
     value = world * S * K / (ms / 1000.0)
+    value_dec = world * S * K / (ms_dec / 1000.0)
 
-    # ---- roofline of the dominant kernel family (CUDA events on the launching stream) ------------
+    # ---- roofline per kernel family (CUDA events on the launching stream) ---------------------------------------------
     step_no = 0
+    d0 = ctx.model_decisions(mstreams[0])
     ctx.kernel_ms(-1)                                   # reset + enable per-family event timing
     resident_steps(n_frames)
-    fam = [ctx.kernel_ms(i) for i in range(3)]
+    fam = [ctx.kernel_ms(i) for i in (0, 2, 4, 5)]
     ctx.kernel_ms(-2)
-    fam_names = ["k_recon_rows", "(unused)", "k_deblock_rows"]
+    dec_seq = ctx.model_decisions(mstreams[0]) - d0     # decisions of one pass over the sequence, per stream
+    fam_names = ["k_recon_rows", "k_deblock_rows", "k_model_frame+count+scan+emit", "k_model_code"]
     dom = int(np.argmax(fam))
     n_p = sum(1 for p in pics if int(p.slices["slice_type"][0]) == 0)
-    alg_seq = S * (n_p * algorithmic_bytes(True) + (n_frames - n_p) * algorithmic_bytes(False))
     peak, peak_kind = measured_peak()
-    # whole reconstruction (all three families) against the whole-picture algorithmic bytes
-    ach_all = alg_seq / (sum(fam) / 1000.0) / 1e9
-    # dominant family: its own share of the algorithmic bytes: k_recon_rows = reference read (P pictures) +
-    # reconstruction write + records and coefficients; k_deblock_rows = picture read + write + MB metadata
-    share = [S * (n_p * PIC_BYTES + n_frames * (PIC_BYTES + MB_PER_PIC * 896)), 0, S * n_frames * (2 * PIC_BYTES + MB_PER_PIC * 128)]
-    ach_dom = share[dom] / (fam[dom] / 1000.0) / 1e9
-    roofline = {"bound": "hbm", "kernel": fam_names[dom], "achieved": round(ach_dom, 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                "frac": round(ach_dom / peak, 4), "traffic": None,
+    pip_bytes_seq = 175638                               # .pip side-stream bytes of one pass (reference output size)
+    n_rec_seq = sum(len(p.recs) for p in mpics)
+    # algorithmic bytes of each family over one pass of the sequence, all S streams (DESIGN.md "Algorithmic bytes"):
+    #   k_recon_rows   reference read (P pictures) + reconstruction write + records and coefficients (896 B / MB)
+    #   k_deblock_rows picture read + write + MB metadata (128 B / MB)
+    #   model gen      MB record + coefficients (896 B) + three neighbour context records (SURVEY 8d charges 3 x 896)
+    #   k_model_code   24 B per decision (one DynProb read + write at the reference's 12 B) + output bytes
+    share = [S * (n_p * PIC_BYTES + n_frames * (PIC_BYTES + MB_PER_PIC * 896)), S * n_frames * (2 * PIC_BYTES + MB_PER_PIC * 128),
+             S * n_rec_seq * 3584, S * (dec_seq * 24 + pip_bytes_seq)]
+    ach = [share[i] / (fam[i] / 1000.0) / 1e9 if fam[i] > 0 else 0.0 for i in range(4)]
+    ach_all = sum(share) / (sum(fam) / 1000.0) / 1e9
+    roofline = {"bound": "hbm", "kernel": fam_names[dom], "achieved": round(ach[dom], 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                "frac": round(ach[dom] / peak, 4), "traffic": None,
                 "whole_step": {"achieved": round(ach_all, 1), "frac": round(ach_all / peak, 4)},
-                "family_ms_per_16_steps": {n: round(v, 3) for n, v in zip(fam_names, fam) if n[0] != "("}}
+                "families": {n: {"ms_per_16_steps": round(t, 3), "achieved": round(a, 1), "frac": round(a / peak, 4)} for n, t, a in zip(fam_names, fam, ach)},
+                "model_decisions_per_s": round(S * dec_seq / (fam[3] / 1000.0)) if fam[3] > 0 else None}
 
-    # ---- e2e: host buffers in, decoded pictures back to the host ---------------------------------
+    # ---- e2e: pinned host records in, decoded pictures back to pinned host memory, .pip side streams read at the end ----
     Se = min(S, 64)                                    # pictures per submit on the host-buffer path
     out_pin = PinnedArray(Se * 1920 * 1080 * 3 // 2)
-    e_streams = streams[:Se]
-    h2d = Se * int(pics[1].mbs.nbytes + pics[1].coefs.nbytes + pics[1].slices.nbytes)
+    e_streams, e_mstreams = streams[:Se], mstreams[:Se]
+    keep = []
+    hp, hm = [], []
+    for p, q in zip(pics, mpics):
+        p2, q2 = copy.copy(p), copy.copy(q)
+        p2.mbs, p2.coefs, p2.slices = pinned_copy(p.mbs, keep), pinned_copy(p.coefs, keep), pinned_copy(p.slices, keep)
+        q2.recs, q2.slices, q2.coefs = pinned_copy(q.recs, keep), pinned_copy(q.slices, keep), p2.coefs   # same coefficient pool
+        hp.append(p2)
+        hm.append(q2)
+    h2d = Se * int(pics[1].mbs.nbytes + 2 * pics[1].coefs.nbytes + pics[1].slices.nbytes + mpics[1].recs.nbytes + mpics[1].slices.nbytes)
     d2h = Se * 1920 * 1080 * 3 // 2
 
     def e2e_steps(n, start):
         for i in range(n):
-            p = pics[(start + i) % n_frames]
-            ctx.recon([p] * Se, e_streams, sync=False)
-            ctx.read_packed(e_streams, [p.cur_slot] * Se, (0, 0, 1920, 1080), out_pin)
+            t = (start + i) % n_frames
+            ctx.recon([hp[t]] * Se, e_streams, sync=False)
+            ctx.model_submit([hm[t]] * Se, e_mstreams, sync=False)
+            ctx.read_packed(e_streams, [hp[t].cur_slot] * Se, (0, 0, 1920, 1080), out_pin)
 
     e2e_steps(n_frames, 0)
     barrier()
@@ -272,15 +317,20 @@ def main():
     barrier()
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1000.0)
     e2e_value = world * Se * Ke / (e2e_ms / 1000.0)
+    mb_per_frame = stream_bytes / n_frames / 1e6
 
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms / K, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOAD, "streams_per_gpu": S, "pictures_per_step_per_gpu": S, "resolution": "1920x1080 (coded 1920x1088)",
-                   "l2": "inputs larger than L2 (each step touches > 1 GB of records and pictures)", "host_parse_pictures_per_s_per_core": parse_pps},
+                   "step": "reconstruction (decode) + recompression model of one picture per stream, i.e. the whole `h264dec in.264 out.pip` hot path",
+                   "l2": "inputs larger than L2 (each step touches > 1 GB of records, pictures and decisions)", "host_parse_pictures_per_s_per_core": parse_pps},
+        "recompress": {"value": round(value * mb_per_frame, 2), "unit": "MB/s of input .264", "pip_out_mb_s": round(value * pip_bytes_seq / n_frames / 1e6, 2)},
+        "decode_only": {"value": round(value_dec, 1), "unit": UNIT, "ms_per_step": round(ms_dec / K, 4)},
         "roofline": roofline,
         "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "pictures_per_step": Se,
-                "path": "lh264_recon_submit (host records) + lh264_pictures_read_packed (I420 to pinned host)"},
+                "recompress_mb_s": round(e2e_value * mb_per_frame, 2),
+                "path": "lh264_recon_submit + lh264_model_submit (pinned host records) + lh264_pictures_read_packed (I420 to pinned host)"},
         "gpu_launches": int(launches), "clocks": sampler.summary(),
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(REF_DEC):
@@ -291,6 +341,8 @@ def main():
                                 "sample": f"{k} concurrent oracle/_ref/h264dec processes x 16 frames of the workload stream (parse + model + reconstruction, tool-reported decode time; {wall:.2f} frames/s including the ~8 s start-up per process)"}
     for b in batches:
         ctx.free_batch(b)
+    for b in mbatches:
+        ctx.model_free_batch(b)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

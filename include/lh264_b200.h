@@ -331,6 +331,11 @@ int  lh264_model_close(lh264_ctx* ctx, int model_stream);
 /* Codes one picture per stream for a batch of independent streams (host buffers in, asynchronous).  Output bytes
  * accumulate on the device and are drained by lh264_model_drain / lh264_model_finish.                                         */
 int  lh264_model_submit(lh264_ctx* ctx, const lh264_model_picture* pics, int n_pics);
+/* Resident variant used by the roofline bench: stage a batch of model pictures in HBM once, code it (again) later.   */
+typedef struct lh264_model_batch lh264_model_batch;
+int  lh264_model_batch_upload(lh264_ctx* ctx, const lh264_model_picture* pics, int n_pics, lh264_model_batch** out);
+int  lh264_model_batch_run(lh264_ctx* ctx, lh264_model_batch* batch);
+void lh264_model_batch_free(lh264_ctx* ctx, lh264_model_batch* batch);
 /* Ends every tag stream of a model stream (32 trailing zero decisions etc.) and makes all bytes available.                  */
 int  lh264_model_finish(lh264_ctx* ctx, int model_stream);
 /* Bytes produced so far for one tag: copies up to cap bytes starting at offset into dst (host), returns the total

@@ -27,7 +27,7 @@ EXPORTS = [
     "lh264_k_idct4x4_add", "lh264_k_idct8x8_add", "lh264_k_mc_luma", "lh264_k_mc_chroma",
     "lh264_k_expand_plane",
     "lh264_model_open", "lh264_model_close", "lh264_model_submit", "lh264_model_finish", "lh264_model_read",
-    "lh264_model_decisions",
+    "lh264_model_decisions", "lh264_model_batch_upload", "lh264_model_batch_run", "lh264_model_batch_free",
 ]
 
 
@@ -101,6 +101,9 @@ def load_library():
     lib.lh264_model_finish.argtypes = [C.c_void_p, C.c_int]
     lib.lh264_model_read.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_size_t]
     lib.lh264_model_read.restype = C.c_longlong
+    lib.lh264_model_batch_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_void_p)]
+    lib.lh264_model_batch_run.argtypes = [C.c_void_p, C.c_void_p]
+    lib.lh264_model_batch_free.argtypes = [C.c_void_p, C.c_void_p]
     lib.lh264_model_decisions.argtypes = [C.c_void_p, C.c_int]
     lib.lh264_model_decisions.restype = C.c_ulonglong
     _LIB = lib
@@ -231,8 +234,7 @@ class Context:
     def model_close(self, ms):
         _check(self.lib, self.lib.lh264_model_close(self.h, ms))
 
-    def model_submit(self, mpics, model_streams):
-        """Codes one picture (records.ModelPicture) per stream; what WelsDecodeSlice's MB loop does in the reference."""
+    def _model_descs(self, mpics, model_streams):
         arr = (ModelPictureDesc * len(mpics))()
         keep = []
         for i, (p, ms) in enumerate(zip(mpics, model_streams)):
@@ -241,8 +243,27 @@ class Context:
             co = np.ascontiguousarray(p.coefs, np.int16)
             keep += [sl, rc, co]
             arr[i] = ModelPictureDesc(ms, p.mb_w, p.mb_h, len(sl), len(rc), len(co), sl.ctypes.data, rc.ctypes.data, co.ctypes.data if len(co) else None)
+        return arr, keep
+
+    def model_submit(self, mpics, model_streams, sync=True):
+        """Codes one picture (records.ModelPicture) per stream; what WelsDecodeSlice's MB loop does in the reference."""
+        arr, keep = self._model_descs(mpics, model_streams)
+        self._keep_model = keep
         _check(self.lib, self.lib.lh264_model_submit(self.h, arr, len(mpics)))
-        self.sync()
+        if sync:
+            self.sync()
+
+    def model_upload_batch(self, mpics, model_streams):
+        arr, keep = self._model_descs(mpics, model_streams)
+        h = C.c_void_p()
+        _check(self.lib, self.lib.lh264_model_batch_upload(self.h, arr, len(mpics), C.byref(h)))
+        return h
+
+    def model_run_resident(self, batch):
+        _check(self.lib, self.lib.lh264_model_batch_run(self.h, batch))
+
+    def model_free_batch(self, batch):
+        self.lib.lh264_model_batch_free(self.h, batch)
 
     def model_finish(self, ms):
         """Ends all tag streams; returns {tag id: bytes} = the contents of the `.pip.<tag>` side files."""

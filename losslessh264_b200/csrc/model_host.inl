@@ -17,6 +17,17 @@ struct MStreamHost {
   unsigned long long decisions = 0;
 };
 
+struct MBatch {                    // one batch of model pictures in HBM
+  DevBuf<lh264_model_mb> recs; DevBuf<lh264_model_slice> slices; DevBuf<int16_t> coefs;
+  DevBuf<MPicDev> pics; PinBuf<MPicDev> h_pics;
+  DevBuf<uint16_t> lane_cnt; DevBuf<uint32_t> rec_off; DevBuf<uint32_t> pic_total; DevBuf<unsigned long long> dec_base;
+  PinBuf<uint32_t> h_total; PinBuf<unsigned long long> h_base;
+  std::vector<int> stream_of;
+  int n = 0, total_recs = 0;
+  void release() { recs.release(); slices.release(); coefs.release(); pics.release(); h_pics.release(); lane_cnt.release(); rec_off.release();
+                   pic_total.release(); dec_base.release(); h_total.release(); h_base.release(); }
+};
+
 struct ModelCtx {
   std::vector<MStreamHost> streams;
   // output arena
@@ -25,12 +36,8 @@ struct ModelCtx {
   uint8_t** d_page_ptrs = nullptr; size_t page_ptr_cap = 0;
   unsigned int* d_next = nullptr;
   unsigned int n_pages = 0, reserved_pages = 0;
-  // batch staging
-  DevBuf<lh264_model_mb> recs; DevBuf<lh264_model_slice> slices; DevBuf<int16_t> coefs;
-  DevBuf<MPicDev> pics; PinBuf<MPicDev> h_pics;
-  DevBuf<uint16_t> lane_cnt; DevBuf<uint32_t> rec_off; DevBuf<uint32_t> pic_total; DevBuf<unsigned long long> dec_base;
-  PinBuf<uint32_t> h_total; PinBuf<unsigned long long> h_base;
-  DevBuf<uint32_t> dec;
+  MBatch batch;                    // staging of lh264_model_submit
+  DevBuf<uint32_t> dec;            // decision list of the batch being coded
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float ms_gen = 0, ms_code = 0;
 };
@@ -41,6 +48,8 @@ constexpr size_t MAX_ARENA_PAGES = 1u << 18;     // 4 GB of output pages
 int model_grow_arena (lh264_ctx* c, ModelCtx* m, unsigned int need_pages);
 
 } // namespace
+
+struct lh264_model_batch { MBatch b; };
 
 static ModelCtx* model_ctx (lh264_ctx* c) {
   if (!c->model) {
@@ -68,8 +77,7 @@ static void model_destroy (lh264_ctx* c) {
   for (uint8_t* p : m->segments) cudaFree (p);
   if (m->d_page_ptrs) cudaFree (m->d_page_ptrs);
   if (m->d_next) cudaFree (m->d_next);
-  m->recs.release(); m->slices.release(); m->coefs.release(); m->pics.release(); m->h_pics.release();
-  m->lane_cnt.release(); m->rec_off.release(); m->pic_total.release(); m->dec_base.release(); m->h_total.release(); m->h_base.release();
+  m->batch.release();
   m->dec.release();
   for (int i = 0; i < 4; i++) if (m->ev[i]) cudaEventDestroy (m->ev[i]);
   delete m;
@@ -147,12 +155,8 @@ int lh264_model_close (lh264_ctx* c, int ms) {
   return LH264_OK;
 }
 
-int lh264_model_submit (lh264_ctx* c, const lh264_model_picture* pics, int n) {
-  if (!c || (n > 0 && !pics) || n < 0) return fail (LH264_E_INVALID, "bad arguments");
-  if (n == 0) return LH264_OK;
-  CK (cudaSetDevice (c->device));
-  ModelCtx* m = model_ctx (c);
-  if (!m) return fail (LH264_E_NOMEM, "out of host memory");
+// Validates a batch and copies its records into HBM (async); fills the device picture table.
+static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_picture* pics, int n) {
   size_t tot_rec = 0, tot_sl = 0, tot_blk = 0;
   for (int i = 0; i < n; i++) {
     const lh264_model_picture& p = pics[i];
@@ -170,46 +174,60 @@ int lh264_model_submit (lh264_ctx* c, const lh264_model_picture* pics, int n) {
     for (int j = 0; j < i; j++) if (n <= 64 && pics[j].model_stream == p.model_stream) return fail (LH264_E_INVALID, "two pictures of one model stream in a batch");
     tot_rec += p.n_recs; tot_sl += p.n_slices; tot_blk += p.n_coef_blocks;
   }
-  CK (m->recs.reserve (tot_rec)); CK (m->slices.reserve (tot_sl)); CK (m->coefs.reserve (tot_blk * 16 + 16));
-  CK (m->pics.reserve (n)); CK (m->lane_cnt.reserve (tot_rec * 32)); CK (m->rec_off.reserve (tot_rec));
-  CK (m->pic_total.reserve (n)); CK (m->dec_base.reserve (n));
+  CK (b.recs.reserve (tot_rec)); CK (b.slices.reserve (tot_sl)); CK (b.coefs.reserve (tot_blk * 16 + 16));
+  CK (b.pics.reserve (n)); CK (b.lane_cnt.reserve (tot_rec * 32)); CK (b.rec_off.reserve (tot_rec));
+  CK (b.pic_total.reserve (n)); CK (b.dec_base.reserve (n));
   CK (cudaStreamSynchronize (c->stream));          // pinned staging of the previous batch is free again
-  CK (m->h_pics.reserve (n)); CK (m->h_total.reserve (n)); CK (m->h_base.reserve (n));
+  CK (b.h_pics.reserve (n)); CK (b.h_total.reserve (n + 1)); CK (b.h_base.reserve (n));
+  b.stream_of.assign (n, 0);
   size_t o_rec = 0, o_sl = 0, o_blk = 0;
   for (int i = 0; i < n; i++) {
     const lh264_model_picture& p = pics[i];
     const MStreamHost& s = m->streams[p.model_stream];
-    CK (cudaMemcpyAsync (m->recs.p + o_rec, p.recs, (size_t)p.n_recs * sizeof (lh264_model_mb), cudaMemcpyHostToDevice, c->stream));
-    CK (cudaMemcpyAsync (m->slices.p + o_sl, p.slices, (size_t)p.n_slices * sizeof (lh264_model_slice), cudaMemcpyHostToDevice, c->stream));
-    if (p.n_coef_blocks) CK (cudaMemcpyAsync (m->coefs.p + o_blk * 16, p.coefs, (size_t)p.n_coef_blocks * 32, cudaMemcpyHostToDevice, c->stream));
-    MPicDev& d = m->h_pics.p[i];
-    d.recs = m->recs.p + o_rec; d.slices = m->slices.p + o_sl; d.coefs = m->coefs.p + o_blk * 16;
-    d.st = s.d_state; d.lane_cnt = m->lane_cnt.p + o_rec * 32; d.rec_off = m->rec_off.p + o_rec;
+    CK (cudaMemcpyAsync (b.recs.p + o_rec, p.recs, (size_t)p.n_recs * sizeof (lh264_model_mb), cudaMemcpyHostToDevice, c->stream));
+    CK (cudaMemcpyAsync (b.slices.p + o_sl, p.slices, (size_t)p.n_slices * sizeof (lh264_model_slice), cudaMemcpyHostToDevice, c->stream));
+    if (p.n_coef_blocks) CK (cudaMemcpyAsync (b.coefs.p + o_blk * 16, p.coefs, (size_t)p.n_coef_blocks * 32, cudaMemcpyHostToDevice, c->stream));
+    MPicDev& d = b.h_pics.p[i];
+    d.recs = b.recs.p + o_rec; d.slices = b.slices.p + o_sl; d.coefs = b.coefs.p + o_blk * 16;
+    d.st = s.d_state; d.lane_cnt = b.lane_cnt.p + o_rec * 32; d.rec_off = b.rec_off.p + o_rec;
     d.n_recs = p.n_recs; d.n_slices = p.n_slices; d.mb_w = p.mb_w; d.mb_h = p.mb_h; d.rec_base = (int)o_rec; d.pad = 0;
+    b.stream_of[i] = p.model_stream;
     o_rec += p.n_recs; o_sl += p.n_slices; o_blk += p.n_coef_blocks;
   }
-  CK (cudaMemcpyAsync (m->pics.p, m->h_pics.p, n * sizeof (MPicDev), cudaMemcpyHostToDevice, c->stream));
-  const int total_recs = (int)tot_rec;
+  CK (cudaMemcpyAsync (b.pics.p, b.h_pics.p, n * sizeof (MPicDev), cudaMemcpyHostToDevice, c->stream));
+  b.n = n; b.total_recs = (int)tot_rec;
+  return LH264_OK;
+}
+
+// The five launches of one batch.  The host waits once in the middle for the decision totals (they size the decision
+// list and bound the output pages the coder may take).
+static int model_run (lh264_ctx* c, ModelCtx* m, MBatch& b) {
+  const int n = b.n, total_recs = b.total_recs;
+  if (n == 0) return LH264_OK;
+  for (int i = 0; i < n; i++) if (!m->streams[b.stream_of[i]].open) return fail (LH264_E_INVALID, "batch names a closed model stream");
   const int mb_blocks = (total_recs + MB_WARPS - 1) / MB_WARPS;
   if (c->timing) CK (cudaEventRecord (m->ev[0], c->stream));
-  k_model_frame<<<n, 32, 0, c->stream>>> (m->pics.p, n);
-  k_model_count<<<mb_blocks, MB_WARPS * 32, 0, c->stream>>> (m->pics.p, n, total_recs);
-  k_model_scan<<<n, 1024, 0, c->stream>>> (m->pics.p, n, m->pic_total.p);
+  k_model_frame<<<n, 32, 0, c->stream>>> (b.pics.p, n);
+  k_model_count<<<mb_blocks, MB_WARPS * 32, 0, c->stream>>> (b.pics.p, n, total_recs);
+  k_model_scan<<<n, 1024, 0, c->stream>>> (b.pics.p, n, b.pic_total.p);
   c->launches += 3;
-  CK (cudaMemcpyAsync (m->h_total.p, m->pic_total.p, n * sizeof (uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaMemcpyAsync (b.h_total.p, b.pic_total.p, n * sizeof (uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  if (m->d_next) CK (cudaMemcpyAsync (b.h_total.p + n, m->d_next, sizeof (unsigned int), cudaMemcpyDeviceToHost, c->stream));
+  else b.h_total.p[n] = 0;
   CK (cudaStreamSynchronize (c->stream));
   unsigned long long total = 0;
-  for (int i = 0; i < n; i++) { m->h_base.p[i] = total; total += m->h_total.p[i]; m->streams[pics[i].model_stream].decisions += m->h_total.p[i]; }
+  for (int i = 0; i < n; i++) { b.h_base.p[i] = total; total += b.h_total.p[i]; m->streams[b.stream_of[i]].decisions += b.h_total.p[i]; }
   CK (m->dec.reserve ((size_t)total + 32));
-  // every decision shifts out at most 7 bits; a tag needs at most one partly filled page more than its bytes
-  m->reserved_pages += (unsigned int) (total * 7 / 8 / PAGE_SIZE) + (unsigned int)n * CT_COUNT + 1;
+  // pages in use + what this batch can add at most: every decision shifts out at most 7 bits, and a tag needs at most one
+  // partly filled page more than its bytes
+  m->reserved_pages = b.h_total.p[n] + (unsigned int) (total * 7 / 8 / PAGE_SIZE) + (unsigned int)n * CT_COUNT + 1;
   int rc = model_grow_arena (c, m, m->reserved_pages);
   if (rc) return rc;
-  CK (cudaMemcpyAsync (m->dec_base.p, m->h_base.p, n * sizeof (unsigned long long), cudaMemcpyHostToDevice, c->stream));
+  CK (cudaMemcpyAsync (b.dec_base.p, b.h_base.p, n * sizeof (unsigned long long), cudaMemcpyHostToDevice, c->stream));
   ArenaDev ar{ m->d_page_ptrs, m->d_next, m->n_pages };
-  k_model_emit<<<mb_blocks, MB_WARPS * 32, 0, c->stream>>> (m->pics.p, n, total_recs, m->dec.p, m->dec_base.p);
+  k_model_emit<<<mb_blocks, MB_WARPS * 32, 0, c->stream>>> (b.pics.p, n, total_recs, m->dec.p, b.dec_base.p);
   if (c->timing) { CK (cudaEventRecord (m->ev[1], c->stream)); CK (cudaEventRecord (m->ev[2], c->stream)); }
-  k_model_code<<<n, 32, 0, c->stream>>> (m->pics.p, n, m->dec.p, m->dec_base.p, m->pic_total.p, ar);
+  k_model_code<<<n, 32, 0, c->stream>>> (b.pics.p, n, m->dec.p, b.dec_base.p, b.pic_total.p, ar);
   c->launches += 2;
   if (c->timing) {
     CK (cudaEventRecord (m->ev[3], c->stream));
@@ -220,6 +238,42 @@ int lh264_model_submit (lh264_ctx* c, const lh264_model_picture* pics, int n) {
   }
   CK (cudaGetLastError());
   return LH264_OK;
+}
+
+int lh264_model_submit (lh264_ctx* c, const lh264_model_picture* pics, int n) {
+  if (!c || (n > 0 && !pics) || n < 0) return fail (LH264_E_INVALID, "bad arguments");
+  if (n == 0) return LH264_OK;
+  CK (cudaSetDevice (c->device));
+  ModelCtx* m = model_ctx (c);
+  if (!m) return fail (LH264_E_NOMEM, "out of host memory");
+  int rc = model_stage (c, m, m->batch, pics, n);
+  if (rc) return rc;
+  return model_run (c, m, m->batch);
+}
+
+int lh264_model_batch_upload (lh264_ctx* c, const lh264_model_picture* pics, int n, lh264_model_batch** out) {
+  if (!c || !pics || n <= 0 || !out) return fail (LH264_E_INVALID, "bad arguments");
+  CK (cudaSetDevice (c->device));
+  ModelCtx* m = model_ctx (c);
+  if (!m) return fail (LH264_E_NOMEM, "out of host memory");
+  lh264_model_batch* rb = new (std::nothrow) lh264_model_batch();
+  if (!rb) return fail (LH264_E_NOMEM, "out of host memory");
+  int rc = model_stage (c, m, rb->b, pics, n);
+  if (rc) { rb->b.release(); delete rb; return rc; }
+  CK (cudaStreamSynchronize (c->stream));
+  *out = rb;
+  return LH264_OK;
+}
+int lh264_model_batch_run (lh264_ctx* c, lh264_model_batch* b) {
+  if (!c || !b || !c->model) return fail (LH264_E_INVALID, "bad arguments");
+  CK (cudaSetDevice (c->device));
+  return model_run (c, static_cast<ModelCtx*> (c->model), b->b);
+}
+void lh264_model_batch_free (lh264_ctx* c, lh264_model_batch* b) {
+  if (!b) return;
+  if (c) { cudaSetDevice (c->device); cudaStreamSynchronize (c->stream); }
+  b->b.release();
+  delete b;
 }
 
 static int model_check_error (lh264_ctx* c, MStreamHost& s) {
@@ -237,8 +291,9 @@ int lh264_model_finish (lh264_ctx* c, int ms) {
   int rc = model_stream_ok (c, ms, &m);
   if (rc) return rc;
   CK (cudaSetDevice (c->device));
-  m->reserved_pages += CT_COUNT;
-  if ((rc = model_grow_arena (c, m, m->reserved_pages))) return rc;
+  unsigned int used = 0;
+  if (m->d_next) { CK (cudaMemcpyAsync (&used, m->d_next, sizeof (used), cudaMemcpyDeviceToHost, c->stream)); CK (cudaStreamSynchronize (c->stream)); }
+  if ((rc = model_grow_arena (c, m, used + CT_COUNT))) return rc;
   ArenaDev ar{ m->d_page_ptrs, m->d_next, m->n_pages };
   k_model_finish<<<1, 32, 0, c->stream>>> (m->streams[ms].d_state, ar);
   c->launches++;

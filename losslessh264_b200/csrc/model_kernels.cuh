@@ -716,12 +716,19 @@ __global__ void __launch_bounds__ (32) k_model_code (const MPicDev* pics, int n_
   int err = 0;
   bool coded = false;
   const uint32_t lt = (1u << lane) - 1u;
+  // software pipeline: decision words are loaded two chunks ahead and the priors of chunk k+1 are gathered before the
+  // coder phase of chunk k, so both global latencies hide behind the serial coder work
+  uint32_t w1 = lane < n ? __ldg (d + lane) : 0xffffffffu;
+  uint32_t w2 = 32u + lane < n ? __ldg (d + 32 + lane) : 0xffffffffu;
+  uint32_t sv1 = w1 != 0xffffffffu ? priors[w1 >> 6] : 0u;
   for (uint32_t k = 0; k < n; k += 32) {
-    const bool valid = k + lane < n;
-    const uint32_t w = valid ? d[k + lane] : 0xffffffffu;
+    const uint32_t w = w1;
+    uint32_t sv = sv1;
+    w1 = w2;
+    w2 = k + 64u + lane < n ? __ldg (d + k + 64 + lane) : 0xffffffffu;
+    const bool valid = w != 0xffffffffu;
     const uint32_t idx = w >> 6, tag = valid ? (w >> 1) & 31u : 31u, bit = w & 1u;
-    // (2) priors: gather, resolve same-prior chains in decision order, scatter
-    uint32_t sv = valid ? priors[idx] : 0u;
+    // (2) priors: resolve same-prior chains in decision order, scatter
     const unsigned peers = __match_any_sync (0xffffffffu, idx);
     const unsigned bits = __ballot_sync (0xffffffffu, bit);
     unsigned m = peers & lt;
@@ -729,6 +736,8 @@ __global__ void __launch_bounds__ (32) k_model_code (const MPicDev* pics, int n_
     const uint32_t prob = dp_prob (sv);
     sv = dp_update (sv, bit);
     if (valid && (peers >> lane) <= 1u) priors[idx] = sv;      // the last decision of the chain stores
+    __syncwarp();                                                // orders the scatter before the next chunk's gather
+    sv1 = w1 != 0xffffffffu ? priors[w1 >> 6] : 0u;
     // (3) bool coders: lane t owns compact tag t
     const unsigned tpeers = __match_any_sync (0xffffffffu, tag);
     smask[lane] = 0;
