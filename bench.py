@@ -35,7 +35,7 @@ sys.path.insert(0, ROOT)
 STREAM = os.path.join(ROOT, "tests", "golden", "streams", "syn1080p_cbp_ippp_16f.264")
 PARSE_TOOL = os.path.join(ROOT, "losslessh264_b200", "_lib", "lh264_parse_dump")
 REF_DEC = os.path.join(ROOT, "oracle", "_ref", "h264dec")
-METRIC, UNIT = "1080p decode + recompress frames/s", "frames/s"
+METRIC, UNIT = "1080p decode frames/s + recompress MB/s", "frames/s"
 WORKLOAD = "syn1080p_cbp_ippp_16f x S independent streams (BASELINE config 4), 1 picture per stream per step"
 MB_PER_PIC = 120 * 68
 PIC_BYTES = 1920 * 1088 * 3 // 2

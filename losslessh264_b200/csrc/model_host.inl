@@ -227,7 +227,7 @@ static int model_run (lh264_ctx* c, ModelCtx* m, MBatch& b) {
   ArenaDev ar{ m->d_page_ptrs, m->d_next, m->n_pages };
   k_model_emit<<<mb_blocks, MB_WARPS * 32, 0, c->stream>>> (b.pics.p, n, total_recs, m->dec.p, b.dec_base.p);
   if (c->timing) { CK (cudaEventRecord (m->ev[1], c->stream)); CK (cudaEventRecord (m->ev[2], c->stream)); }
-  k_model_code<<<n, 32, 0, c->stream>>> (b.pics.p, n, m->dec.p, b.dec_base.p, b.pic_total.p, ar);
+  k_model_code<<<n, 64, 0, c->stream>>> (b.pics.p, n, m->dec.p, b.dec_base.p, b.pic_total.p, ar);
   c->launches += 2;
   if (c->timing) {
     CK (cudaEventRecord (m->ev[3], c->stream));

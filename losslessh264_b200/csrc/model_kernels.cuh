@@ -645,7 +645,12 @@ __device__ __forceinline__ uint32_t dp_prob (uint32_t w) { return (w >> 24) ^ 0x
 __device__ __forceinline__ uint32_t dp_update (uint32_t w, uint32_t bit) {   // DynProb::updateProb compression_stream.h:101-110
   uint32_t c0 = w & 0x3ffu, c1 = (w >> 10) & 0x3ffu;
   if (bit) c1++; else c0++;
-  const uint32_t prob = (256u * (c0 + 1u)) / (c0 + c1 + 2u);
+  // (256 * (c0 + 1)) / (c0 + c1 + 2), exactly: numerator < 2^18, so the float quotient is off by at most one
+  const uint32_t num = 256u * (c0 + 1u), den = c0 + c1 + 2u;
+  uint32_t prob = (uint32_t)__fdividef ((float)num, (float)den);
+  const int rem = (int)num - (int) (prob * den);
+  prob += rem >= (int)den ? 1u : 0u;
+  prob -= rem < 0 ? 1u : 0u;
   if (c0 + c1 > 512u) { c0 = (c0 + 1u) >> 1; c1 = (c1 + 1u) >> 1; }
   return c0 | (c1 << 10) | ((prob ^ 0x80u) << 24);
 }
@@ -699,76 +704,137 @@ __device__ __forceinline__ void coder_write (Coder& c, uint8_t*& page, MState* s
   c.count = count; c.lowvalue = low; c.range = range;
 }
 
-// one warp per stream; blockDim = 32
-__global__ void __launch_bounds__ (32) k_model_code (const MPicDev* pics, int n_pics, const uint32_t* dec, const unsigned long long* dec_base,
+// One block of two warps per stream.  Warp 0 (producer) walks the decision list 32 decisions at a time: gathers the
+// priors, resolves same-prior chains inside the chunk in decision order, scatters the adapted priors, and appends
+// (probability, bit) to the shared-memory ring of the decision's tag.  Warp 1 (consumer): lane t owns compact tag t and
+// drains ring t through its bool coder.  The two serial chains (per prior, per tag) thus run concurrently and the coder
+// lanes never wait for each other.
+constexpr int CODE_RING = 256;               // entries per tag ring (power of two)
+struct CodeShared {
+  uint16_t ring[32][CODE_RING];
+  volatile uint32_t prod[32];               // entries ever appended to ring t (producer writes)
+  volatile uint32_t cons[32];               // entries consumed from ring t (consumer lane t writes)
+  volatile int done;
+};
+
+__global__ void __launch_bounds__ (64) k_model_code (const MPicDev* pics, int n_pics, const uint32_t* dec, const unsigned long long* dec_base,
                                                      const uint32_t* pic_total, ArenaDev ar) {
-  __shared__ uint32_t smask[32];
-  const int p = blockIdx.x, lane = threadIdx.x;
+  __shared__ CodeShared sh;
+  const int p = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (p >= n_pics) return;
   const MPicDev& pic = pics[p];
   MState* st = pic.st;
   if (st->error) return;
-  uint32_t* priors = st->priors;
+  if (threadIdx.x < 32) { sh.prod[threadIdx.x] = 0; sh.cons[threadIdx.x] = 0; }
+  if (threadIdx.x == 0) sh.done = 0;
+  __syncthreads();
   const uint32_t n = pic_total[p];
-  const uint32_t* d = dec + dec_base[p];
-  Coder c = st->coder[lane];
-  uint8_t* page = nullptr;
-  int err = 0;
-  bool coded = false;
-  const uint32_t lt = (1u << lane) - 1u;
-  // software pipeline: decision words are loaded two chunks ahead and the priors of chunk k+1 are gathered before the
-  // coder phase of chunk k, so both global latencies hide behind the serial coder work
-  uint32_t w1 = lane < n ? __ldg (d + lane) : 0xffffffffu;
-  uint32_t w2 = 32u + lane < n ? __ldg (d + 32 + lane) : 0xffffffffu;
-  uint32_t sv1 = w1 != 0xffffffffu ? priors[w1 >> 6] : 0u;
-  for (uint32_t k = 0; k < n; k += 32) {
-    const uint32_t w = w1;
-    uint32_t sv = sv1;
-    w1 = w2;
-    w2 = k + 64u + lane < n ? __ldg (d + k + 64 + lane) : 0xffffffffu;
-    const bool valid = w != 0xffffffffu;
-    const uint32_t idx = w >> 6, tag = valid ? (w >> 1) & 31u : 31u, bit = w & 1u;
-    // (2) priors: resolve same-prior chains in decision order, scatter
-    const unsigned peers = __match_any_sync (0xffffffffu, idx);
-    const unsigned bits = __ballot_sync (0xffffffffu, bit);
-    unsigned m = peers & lt;
-    while (m) { const int j = __ffs (m) - 1; m &= m - 1; sv = dp_update (sv, (bits >> j) & 1u); }
-    const uint32_t prob = dp_prob (sv);
-    sv = dp_update (sv, bit);
-    if (valid && (peers >> lane) <= 1u) priors[idx] = sv;      // the last decision of the chain stores
-    __syncwarp();                                                // orders the scatter before the next chunk's gather
-    sv1 = w1 != 0xffffffffu ? priors[w1 >> 6] : 0u;
-    // (3) bool coders: lane t owns compact tag t
-    const unsigned tpeers = __match_any_sync (0xffffffffu, tag);
-    smask[lane] = 0;
-    __syncwarp();
-    if (valid && (tpeers & lt) == 0) smask[tag] = tpeers;
-    __syncwarp();
-    unsigned mine = smask[lane];
-    const uint32_t pb = (prob << 1) | bit;
-    const int iters = __reduce_max_sync (0xffffffffu, (unsigned)__popc (mine));
-    for (int it = 0; it < iters; it++) {
-      const int src = mine ? __ffs (mine) - 1 : 0;
-      const uint32_t v = __shfl_sync (0xffffffffu, pb, src);
-      if (mine && !err) { coder_write (c, page, st, ar, lane, v & 1u, v >> 1, &err); coded = true; mine &= mine - 1; }
+  if (warp == 0) {
+    // ---- producer ---------------------------------------------------------------------------------------------------
+    uint32_t* priors = st->priors;
+    const uint32_t* d = dec + dec_base[p];
+    const uint32_t lt = (1u << lane) - 1u;
+    // software pipeline: decision words are loaded two chunks ahead and the priors of chunk k+1 are gathered right after
+    // the scatter of chunk k
+    uint32_t w1 = lane < n ? __ldg (d + lane) : 0xffffffffu;
+    uint32_t w2 = 32u + lane < n ? __ldg (d + 32 + lane) : 0xffffffffu;
+    uint32_t sv1 = w1 != 0xffffffffu ? priors[w1 >> 6] : 0u;
+    for (uint32_t k = 0; k < n; k += 32) {
+      const uint32_t w = w1;
+      uint32_t sv = sv1;
+      w1 = w2;
+      w2 = k + 64u + lane < n ? __ldg (d + k + 64 + lane) : 0xffffffffu;
+      const bool valid = w != 0xffffffffu;
+      const uint32_t idx = w >> 6, tag = valid ? (w >> 1) & 31u : 31u, bit = w & 1u;
+      const unsigned peers = __match_any_sync (0xffffffffu, idx);
+      const unsigned bits = __ballot_sync (0xffffffffu, bit);
+      unsigned m = peers & lt;
+      while (m) { const int j = __ffs (m) - 1; m &= m - 1; sv = dp_update (sv, (bits >> j) & 1u); }
+      const uint32_t prob = dp_prob (sv);
+      sv = dp_update (sv, bit);
+      if (valid && (peers >> lane) <= 1u) priors[idx] = sv;      // the last decision of the chain stores
+      __syncwarp();                                                // orders the scatter before the next chunk's gather
+      sv1 = w1 != 0xffffffffu ? priors[w1 >> 6] : 0u;
+      // append to the tag rings in decision order
+      const unsigned tpeers = __match_any_sync (0xffffffffu, tag);
+      if (valid) {
+        const uint32_t pos = sh.prod[tag] + (uint32_t)__popc (tpeers & lt);
+        while (pos - sh.cons[tag] >= (uint32_t)CODE_RING) { }
+        sh.ring[tag][pos & (CODE_RING - 1)] = (uint16_t) ((prob << 1) | bit);
+      }
+      __threadfence_block();
+      __syncwarp();
+      if (valid && (tpeers >> lane) <= 1u) sh.prod[tag] = sh.prod[tag] + (uint32_t)__popc (tpeers);
+      __syncwarp();
     }
-    __syncwarp();
-  }
-  st->coder[lane] = c;
-  const unsigned usedm = __ballot_sync (0xffffffffu, coded);
-  const unsigned errm = __ballot_sync (0xffffffffu, err != 0);
-  if (lane == 0) {
-    if (usedm) atomicOr (&st->used, usedm);
-    st->decisions += n;
-    if (errm) st->error = 2;
-  }
-  // commit the picture's context records (decode_slice.cpp:3104-3108)
-  for (int i = lane; i < pic.n_recs; i += 32) {
-    const uint32_t a = pic.recs[i].mb_addr;
-    if ((int)a < pic.mb_w * pic.mb_h) {
-      const uint4* q = reinterpret_cast<const uint4*> (&st->newrec[a]);
-      uint4* o = reinterpret_cast<uint4*> (&st->frame[st->cur][a]);
-      o[0] = q[0]; o[1] = q[1];
+    __threadfence_block();
+    if (lane == 0) { sh.done = 1; st->decisions += n; }
+    // commit the picture's context records (decode_slice.cpp:3104-3108)
+    for (int i = lane; i < pic.n_recs; i += 32) {
+      const uint32_t a = pic.recs[i].mb_addr;
+      if ((int)a < pic.mb_w * pic.mb_h) {
+        const uint4* q = reinterpret_cast<const uint4*> (&st->newrec[a]);
+        uint4* o = reinterpret_cast<uint4*> (&st->frame[st->cur][a]);
+        o[0] = q[0]; o[1] = q[1];
+      }
+    }
+  } else {
+    // ---- consumer: lane t = bool coder of compact tag t -----------------------------------------------------------------
+    Coder c = st->coder[lane];
+    uint8_t* page = nullptr;
+    int err = 0;
+    uint32_t consumed = 0, avail = 0;
+    const uint16_t* myring = sh.ring[lane];
+    // The loop body is the bare vpx_write dependency chain, predicated instead of branched: with one warp per scheduler
+    // every taken branch costs more than the arithmetic it skips.  Only the byte-output path (once per 8 shifted bits)
+    // branches.
+    while (true) {
+      const bool has = consumed != avail;
+      const uint32_t v = myring[consumed & (CODE_RING - 1)];
+      const uint32_t prob = v >> 1, bit = v & 1u;
+      const uint32_t split = 1u + (((c.range - 1u) * prob) >> 8);
+      uint32_t range = bit ? c.range - split : split;
+      uint32_t low = c.lowvalue + (bit ? split : 0u);
+      int shift = __clz (range) - 24;
+      range <<= shift;
+      int count = c.count + shift;
+      if (has && count >= 0) {
+        const int offset = shift - count;
+        if ((low << (offset - 1)) & 0x80000000u) {      // carry into the bytes already written
+          int x = (int)c.pos - 1;
+          while (x >= 0) {
+            uint8_t* q = out_ptr (st, ar, lane, (uint32_t)x, false);
+            if (!q) break;
+            if (*q == 0xff) { *q = 0; x--; } else { *q += 1; break; }
+          }
+        }
+        if (((c.pos & (PAGE_SIZE - 1)) == 0 || !page) && !err) {
+          uint8_t* q = out_ptr (st, ar, lane, c.pos, true);
+          if (!q) err = 2; else page = q - (c.pos & (PAGE_SIZE - 1));
+        }
+        if (!err) page[c.pos & (PAGE_SIZE - 1)] = (uint8_t) (low >> (24 - offset));
+        c.pos++;
+        low <<= offset;
+        shift = count;
+        low &= 0xffffffu;
+        count -= 8;
+      }
+      low <<= shift;
+      if (has) { c.range = range; c.lowvalue = low; c.count = count; consumed++; }
+      sh.cons[lane] = consumed;
+      if (!has) avail = sh.prod[lane];
+      if (!__any_sync (0xffffffffu, has)) {
+        const int dn = sh.done;
+        avail = sh.prod[lane];
+        if (dn && __all_sync (0xffffffffu, avail == consumed)) break;
+      }
+    }
+    st->coder[lane] = c;
+    const unsigned usedm = __ballot_sync (0xffffffffu, consumed != 0);
+    const unsigned errm = __ballot_sync (0xffffffffu, err != 0);
+    if (lane == 0) {
+      if (usedm) atomicOr (&st->used, usedm);
+      if (errm) st->error = 2;
     }
   }
 }
