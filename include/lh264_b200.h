@@ -328,8 +328,12 @@ typedef struct lh264_model_picture {
  * coefficient priors (High profile streams).  Returns a handle >= 0 or an error.                                             */
 int  lh264_model_open(lh264_ctx* ctx, int max_mbs, int with_8x8);
 int  lh264_model_close(lh264_ctx* ctx, int model_stream);
-/* Codes one picture per stream for a batch of independent streams (host buffers in, asynchronous).  Output bytes
- * accumulate on the device and are drained by lh264_model_drain / lh264_model_finish.                                         */
+/* Codes one picture per stream for a batch of independent streams (host buffers in; the buffers may be reused when the
+ * call returns).  Runs on a CUDA stream of its own, concurrently with reconstruction work queued on the context stream;
+ * work queued on the context stream AFTER this call is ordered after it, and lh264_sync() waits for both.  A picture
+ * whose `coefs` pointer equals that of a picture of the immediately preceding lh264_recon_submit() (the same pool, as the
+ * host decoder hands it over) reads that batch's device copy instead of being copied again.  Output bytes accumulate on
+ * the device and are read with lh264_model_read().                                                                          */
 int  lh264_model_submit(lh264_ctx* ctx, const lh264_model_picture* pics, int n_pics);
 /* Resident variant used by the roofline bench: stage a batch of model pictures in HBM once, code it (again) later.   */
 typedef struct lh264_model_batch lh264_model_batch;

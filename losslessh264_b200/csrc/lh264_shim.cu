@@ -11,6 +11,7 @@
 #include <stdarg.h>
 #include <vector>
 #include <algorithm>
+#include <utility>
 #include <new>
 
 #include "recon_kernels.cuh"
@@ -95,9 +96,14 @@ struct lh264_ctx {
   float ms[3] = {0, 0, 0};
   bool timing = false;
   void* model = nullptr;                     // ModelCtx (model_host.inl), created by the first lh264_model_open
+  // host pointer -> device copy of the coefficient pools staged by the last lh264_recon_submit: a model picture that names
+  // the same pool (it is the same data) reads the device copy instead of crossing PCIe twice
+  std::vector<std::pair<const int16_t*, const int16_t*> > staged_coefs;
+  cudaEvent_t recon_staged = nullptr;        // the H2D copies of that batch are done
 };
 static void model_destroy (lh264_ctx* c);
 static float model_ms (lh264_ctx* c, int which, bool reset);
+static cudaError_t model_sync (lh264_ctx* c);
 
 extern "C" {
 
@@ -123,6 +129,7 @@ int lh264_ctx_create (lh264_ctx** out, int device, void* cuda_stream) {
   if (cuda_stream) c->stream = (cudaStream_t)cuda_stream;
   else { CK (cudaStreamCreateWithFlags (&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
   CK (cudaEventCreateWithFlags (&c->staged, cudaEventDisableTiming));
+  CK (cudaEventCreateWithFlags (&c->recon_staged, cudaEventDisableTiming));
   for (int i = 0; i < 4; i++) CK (cudaEventCreate (&c->ev[i]));
   *out = c;
   return LH264_OK;
@@ -138,6 +145,7 @@ void lh264_ctx_destroy (lh264_ctx* c) {
   c->pack_jobs.release(); c->h_pack_jobs.release(); c->pack_out.release();
   c->scratch_a.release(); c->scratch_b.release(); c->scratch_c.release();
   if (c->staged) cudaEventDestroy (c->staged);
+  if (c->recon_staged) cudaEventDestroy (c->recon_staged);
   for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy (c->ev[i]);
   if (c->own_stream) cudaStreamDestroy (c->stream);
   delete c;
@@ -235,8 +243,11 @@ int lh264_recon_submit (lh264_ctx* c, const lh264_picture_desc* pics, int n_pics
   CK (cudaSetDevice (c->device));
   for (int i = 0; i < n_pics; i++) for (int j = i + 1; j < n_pics; j++)
       if (n_pics <= 64 && pics[i].stream == pics[j].stream) return fail (LH264_E_INVALID, "two pictures of one stream in a batch");
+  c->staged_coefs.clear();
   int rc = stage_batch (c, c->batch, c->h_pics, pics, n_pics);
   if (rc) return rc;
+  for (int i = 0; i < n_pics; i++) if (pics[i].n_coef_blocks) c->staged_coefs.push_back (std::make_pair (pics[i].coefs, c->h_pics.p[i].coefs));
+  CK (cudaEventRecord (c->recon_staged, c->stream));
   return launch_recon (c, c->batch);
 }
 
@@ -368,6 +379,7 @@ int lh264_pictures_read_packed (lh264_ctx* c, const int* streams, const int* slo
 int lh264_sync (lh264_ctx* c) {
   if (!c) return fail (LH264_E_INVALID, "null ctx");
   CK (cudaSetDevice (c->device));
+  CK (model_sync (c));
   CK (cudaStreamSynchronize (c->stream));
   c->staged_pending = false;
   return LH264_OK;

@@ -40,6 +40,10 @@ struct ModelCtx {
   DevBuf<uint32_t> dec;            // decision list of the batch being coded
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float ms_gen = 0, ms_code = 0;
+  // The model runs on its own CUDA stream: it consumes syntax elements, not samples, so the model of picture t overlaps
+  // the reconstruction of picture t.  `done` makes the context stream (and whoever records events on it) wait for it.
+  cudaStream_t stream = nullptr;
+  cudaEvent_t done = nullptr;
 };
 
 constexpr unsigned int SEG_PAGES = 2048;         // 32 MB arena segments
@@ -56,6 +60,8 @@ static ModelCtx* model_ctx (lh264_ctx* c) {
     ModelCtx* m = new (std::nothrow) ModelCtx();
     if (!m) return nullptr;
     for (int i = 0; i < 4; i++) cudaEventCreate (&m->ev[i]);
+    cudaStreamCreateWithFlags (&m->stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags (&m->done, cudaEventDisableTiming);
     c->model = m;
   }
   return static_cast<ModelCtx*> (c->model);
@@ -80,6 +86,8 @@ static void model_destroy (lh264_ctx* c) {
   m->batch.release();
   m->dec.release();
   for (int i = 0; i < 4; i++) if (m->ev[i]) cudaEventDestroy (m->ev[i]);
+  if (m->stream) { cudaStreamSynchronize (m->stream); cudaStreamDestroy (m->stream); }
+  if (m->done) cudaEventDestroy (m->done);
   delete m;
   c->model = nullptr;
 }
@@ -89,7 +97,7 @@ int model_grow_arena (lh264_ctx* c, ModelCtx* m, unsigned int need_pages) {
   if (!m->d_page_ptrs) {
     CK (cudaMalloc (&m->d_page_ptrs, MAX_ARENA_PAGES * sizeof (uint8_t*)));
     CK (cudaMalloc (&m->d_next, sizeof (unsigned int)));
-    CK (cudaMemsetAsync (m->d_next, 0, sizeof (unsigned int), c->stream));
+    CK (cudaMemsetAsync (m->d_next, 0, sizeof (unsigned int), m->stream));
   }
   while (m->n_pages < need_pages) {
     if (m->n_pages + SEG_PAGES > MAX_ARENA_PAGES) return fail (LH264_E_NOMEM, "model output arena exhausted");
@@ -98,8 +106,8 @@ int model_grow_arena (lh264_ctx* c, ModelCtx* m, unsigned int need_pages) {
     m->segments.push_back (seg);
     const size_t first = m->h_page_ptrs.size();
     for (unsigned int i = 0; i < SEG_PAGES; i++) m->h_page_ptrs.push_back (seg + (size_t)i * PAGE_SIZE);
-    CK (cudaMemcpyAsync (m->d_page_ptrs + first, m->h_page_ptrs.data() + first, SEG_PAGES * sizeof (uint8_t*), cudaMemcpyHostToDevice, c->stream));
-    CK (cudaStreamSynchronize (c->stream));
+    CK (cudaMemcpyAsync (m->d_page_ptrs + first, m->h_page_ptrs.data() + first, SEG_PAGES * sizeof (uint8_t*), cudaMemcpyHostToDevice, m->stream));
+    CK (cudaStreamSynchronize (m->stream));
     m->n_pages += SEG_PAGES;
   }
   return LH264_OK;
@@ -121,16 +129,16 @@ int lh264_model_open (lh264_ctx* c, int max_mbs, int with_8x8) {
   CK (cudaMalloc (&s.d_frames, (size_t)3 * max_mbs * sizeof (CtxRec)));
   CK (cudaMalloc (&s.d_order, (size_t)max_mbs * sizeof (int)));
   CK (cudaMalloc (&s.d_pagelist, (size_t)CT_COUNT * MAX_PAGES_PER_TAG * sizeof (uint32_t)));
-  CK (cudaMemsetAsync (s.d_priors, 0, n_priors * sizeof (uint32_t), c->stream));          // fresh DynProb = all zero bits
-  CK (cudaMemsetAsync (s.d_frames, 0, (size_t)3 * max_mbs * sizeof (CtxRec), c->stream));
-  CK (cudaMemsetAsync (s.d_pagelist, 0, (size_t)CT_COUNT * MAX_PAGES_PER_TAG * sizeof (uint32_t), c->stream));
+  CK (cudaMemsetAsync (s.d_priors, 0, n_priors * sizeof (uint32_t), m->stream));          // fresh DynProb = all zero bits
+  CK (cudaMemsetAsync (s.d_frames, 0, (size_t)3 * max_mbs * sizeof (CtxRec), m->stream));
+  CK (cudaMemsetAsync (s.d_pagelist, 0, (size_t)CT_COUNT * MAX_PAGES_PER_TAG * sizeof (uint32_t), m->stream));
   MState h;
   memset (&h, 0, sizeof (h));
   h.priors = s.d_priors; h.frame[0] = s.d_frames; h.frame[1] = s.d_frames + max_mbs; h.newrec = s.d_frames + 2 * (size_t)max_mbs;
   h.order = s.d_order; h.pagelist = s.d_pagelist; h.max_mbs = max_mbs;
-  CK (cudaMemcpyAsync (s.d_state, &h, sizeof (h), cudaMemcpyHostToDevice, c->stream));
-  k_model_init_state<<<1, 32, 0, c->stream>>> (s.d_state);
-  CK (cudaStreamSynchronize (c->stream));                                                  // h is on the stack
+  CK (cudaMemcpyAsync (s.d_state, &h, sizeof (h), cudaMemcpyHostToDevice, m->stream));
+  k_model_init_state<<<1, 32, 0, m->stream>>> (s.d_state);
+  CK (cudaStreamSynchronize (m->stream));                                                  // h is on the stack
   for (size_t i = 0; i < m->streams.size(); i++) if (!m->streams[i].open) { m->streams[i] = s; return (int)i; }
   m->streams.push_back (s);
   return (int)m->streams.size() - 1;
@@ -149,14 +157,14 @@ int lh264_model_close (lh264_ctx* c, int ms) {
   int rc = model_stream_ok (c, ms, &m);
   if (rc) return rc;
   CK (cudaSetDevice (c->device));
-  CK (cudaStreamSynchronize (c->stream));
+  CK (cudaStreamSynchronize (m->stream));
   // the stream's output pages stay in the arena until the context is destroyed (bump allocator)
   model_free_stream (m->streams[ms]);
   return LH264_OK;
 }
 
 // Validates a batch and copies its records into HBM (async); fills the device picture table.
-static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_picture* pics, int n) {
+static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_picture* pics, int n, bool share_coefs) {
   size_t tot_rec = 0, tot_sl = 0, tot_blk = 0;
   for (int i = 0; i < n; i++) {
     const lh264_model_picture& p = pics[i];
@@ -177,24 +185,28 @@ static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_
   CK (b.recs.reserve (tot_rec)); CK (b.slices.reserve (tot_sl)); CK (b.coefs.reserve (tot_blk * 16 + 16));
   CK (b.pics.reserve (n)); CK (b.lane_cnt.reserve (tot_rec * 32)); CK (b.rec_off.reserve (tot_rec));
   CK (b.pic_total.reserve (n)); CK (b.dec_base.reserve (n));
-  CK (cudaStreamSynchronize (c->stream));          // pinned staging of the previous batch is free again
+  CK (cudaStreamSynchronize (m->stream));          // pinned staging of the previous batch is free again
   CK (b.h_pics.reserve (n)); CK (b.h_total.reserve (n + 1)); CK (b.h_base.reserve (n));
   b.stream_of.assign (n, 0);
   size_t o_rec = 0, o_sl = 0, o_blk = 0;
   for (int i = 0; i < n; i++) {
     const lh264_model_picture& p = pics[i];
     const MStreamHost& s = m->streams[p.model_stream];
-    CK (cudaMemcpyAsync (b.recs.p + o_rec, p.recs, (size_t)p.n_recs * sizeof (lh264_model_mb), cudaMemcpyHostToDevice, c->stream));
-    CK (cudaMemcpyAsync (b.slices.p + o_sl, p.slices, (size_t)p.n_slices * sizeof (lh264_model_slice), cudaMemcpyHostToDevice, c->stream));
-    if (p.n_coef_blocks) CK (cudaMemcpyAsync (b.coefs.p + o_blk * 16, p.coefs, (size_t)p.n_coef_blocks * 32, cudaMemcpyHostToDevice, c->stream));
+    CK (cudaMemcpyAsync (b.recs.p + o_rec, p.recs, (size_t)p.n_recs * sizeof (lh264_model_mb), cudaMemcpyHostToDevice, m->stream));
+    CK (cudaMemcpyAsync (b.slices.p + o_sl, p.slices, (size_t)p.n_slices * sizeof (lh264_model_slice), cudaMemcpyHostToDevice, m->stream));
+    const int16_t* dev_coefs = nullptr;
+    if (share_coefs && p.n_coef_blocks)
+      for (const auto& sc : c->staged_coefs) if (sc.first == p.coefs) { dev_coefs = sc.second; break; }
+    if (p.n_coef_blocks && !dev_coefs) CK (cudaMemcpyAsync (b.coefs.p + o_blk * 16, p.coefs, (size_t)p.n_coef_blocks * 32, cudaMemcpyHostToDevice, m->stream));
     MPicDev& d = b.h_pics.p[i];
-    d.recs = b.recs.p + o_rec; d.slices = b.slices.p + o_sl; d.coefs = b.coefs.p + o_blk * 16;
+    d.recs = b.recs.p + o_rec; d.slices = b.slices.p + o_sl; d.coefs = dev_coefs ? dev_coefs : b.coefs.p + o_blk * 16;
     d.st = s.d_state; d.lane_cnt = b.lane_cnt.p + o_rec * 32; d.rec_off = b.rec_off.p + o_rec;
     d.n_recs = p.n_recs; d.n_slices = p.n_slices; d.mb_w = p.mb_w; d.mb_h = p.mb_h; d.rec_base = (int)o_rec; d.pad = 0;
     b.stream_of[i] = p.model_stream;
     o_rec += p.n_recs; o_sl += p.n_slices; o_blk += p.n_coef_blocks;
   }
-  CK (cudaMemcpyAsync (b.pics.p, b.h_pics.p, n * sizeof (MPicDev), cudaMemcpyHostToDevice, c->stream));
+  CK (cudaMemcpyAsync (b.pics.p, b.h_pics.p, n * sizeof (MPicDev), cudaMemcpyHostToDevice, m->stream));
+  if (share_coefs) CK (cudaStreamWaitEvent (m->stream, c->recon_staged, 0));     // the shared pools are in HBM
   b.n = n; b.total_recs = (int)tot_rec;
   return LH264_OK;
 }
@@ -206,15 +218,15 @@ static int model_run (lh264_ctx* c, ModelCtx* m, MBatch& b) {
   if (n == 0) return LH264_OK;
   for (int i = 0; i < n; i++) if (!m->streams[b.stream_of[i]].open) return fail (LH264_E_INVALID, "batch names a closed model stream");
   const int mb_blocks = (total_recs + MB_WARPS - 1) / MB_WARPS;
-  if (c->timing) CK (cudaEventRecord (m->ev[0], c->stream));
-  k_model_frame<<<n, 32, 0, c->stream>>> (b.pics.p, n);
-  k_model_count<<<mb_blocks, MB_WARPS * 32, 0, c->stream>>> (b.pics.p, n, total_recs);
-  k_model_scan<<<n, 1024, 0, c->stream>>> (b.pics.p, n, b.pic_total.p);
+  if (c->timing) CK (cudaEventRecord (m->ev[0], m->stream));
+  k_model_frame<<<n, 32, 0, m->stream>>> (b.pics.p, n);
+  k_model_count<<<mb_blocks, MB_WARPS * 32, 0, m->stream>>> (b.pics.p, n, total_recs);
+  k_model_scan<<<n, 1024, 0, m->stream>>> (b.pics.p, n, b.pic_total.p);
   c->launches += 3;
-  CK (cudaMemcpyAsync (b.h_total.p, b.pic_total.p, n * sizeof (uint32_t), cudaMemcpyDeviceToHost, c->stream));
-  if (m->d_next) CK (cudaMemcpyAsync (b.h_total.p + n, m->d_next, sizeof (unsigned int), cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaMemcpyAsync (b.h_total.p, b.pic_total.p, n * sizeof (uint32_t), cudaMemcpyDeviceToHost, m->stream));
+  if (m->d_next) CK (cudaMemcpyAsync (b.h_total.p + n, m->d_next, sizeof (unsigned int), cudaMemcpyDeviceToHost, m->stream));
   else b.h_total.p[n] = 0;
-  CK (cudaStreamSynchronize (c->stream));
+  CK (cudaStreamSynchronize (m->stream));
   unsigned long long total = 0;
   for (int i = 0; i < n; i++) { b.h_base.p[i] = total; total += b.h_total.p[i]; m->streams[b.stream_of[i]].decisions += b.h_total.p[i]; }
   CK (m->dec.reserve ((size_t)total + 32));
@@ -223,19 +235,23 @@ static int model_run (lh264_ctx* c, ModelCtx* m, MBatch& b) {
   m->reserved_pages = b.h_total.p[n] + (unsigned int) (total * 7 / 8 / PAGE_SIZE) + (unsigned int)n * CT_COUNT + 1;
   int rc = model_grow_arena (c, m, m->reserved_pages);
   if (rc) return rc;
-  CK (cudaMemcpyAsync (b.dec_base.p, b.h_base.p, n * sizeof (unsigned long long), cudaMemcpyHostToDevice, c->stream));
+  CK (cudaMemcpyAsync (b.dec_base.p, b.h_base.p, n * sizeof (unsigned long long), cudaMemcpyHostToDevice, m->stream));
   ArenaDev ar{ m->d_page_ptrs, m->d_next, m->n_pages };
-  k_model_emit<<<mb_blocks, MB_WARPS * 32, 0, c->stream>>> (b.pics.p, n, total_recs, m->dec.p, b.dec_base.p);
-  if (c->timing) { CK (cudaEventRecord (m->ev[1], c->stream)); CK (cudaEventRecord (m->ev[2], c->stream)); }
-  k_model_code<<<n, 64, 0, c->stream>>> (b.pics.p, n, m->dec.p, b.dec_base.p, b.pic_total.p, ar);
+  k_model_emit<<<mb_blocks, MB_WARPS * 32, 0, m->stream>>> (b.pics.p, n, total_recs, m->dec.p, b.dec_base.p);
+  if (c->timing) { CK (cudaEventRecord (m->ev[1], m->stream)); CK (cudaEventRecord (m->ev[2], m->stream)); }
+  k_model_code<<<n, 64, 0, m->stream>>> (b.pics.p, n, m->dec.p, b.dec_base.p, b.pic_total.p, ar);
   c->launches += 2;
   if (c->timing) {
-    CK (cudaEventRecord (m->ev[3], c->stream));
+    CK (cudaEventRecord (m->ev[3], m->stream));
     CK (cudaEventSynchronize (m->ev[3]));
     float t = 0;
     cudaEventElapsedTime (&t, m->ev[0], m->ev[1]); m->ms_gen += t;
     cudaEventElapsedTime (&t, m->ev[2], m->ev[3]); m->ms_code += t;
   }
+  // later work on the context stream (the next batch's staging overwrites shared pools; callers time with events on it)
+  // is ordered after this batch's model
+  CK (cudaEventRecord (m->done, m->stream));
+  CK (cudaStreamWaitEvent (c->stream, m->done, 0));
   CK (cudaGetLastError());
   return LH264_OK;
 }
@@ -246,7 +262,7 @@ int lh264_model_submit (lh264_ctx* c, const lh264_model_picture* pics, int n) {
   CK (cudaSetDevice (c->device));
   ModelCtx* m = model_ctx (c);
   if (!m) return fail (LH264_E_NOMEM, "out of host memory");
-  int rc = model_stage (c, m, m->batch, pics, n);
+  int rc = model_stage (c, m, m->batch, pics, n, true);
   if (rc) return rc;
   return model_run (c, m, m->batch);
 }
@@ -258,9 +274,9 @@ int lh264_model_batch_upload (lh264_ctx* c, const lh264_model_picture* pics, int
   if (!m) return fail (LH264_E_NOMEM, "out of host memory");
   lh264_model_batch* rb = new (std::nothrow) lh264_model_batch();
   if (!rb) return fail (LH264_E_NOMEM, "out of host memory");
-  int rc = model_stage (c, m, rb->b, pics, n);
+  int rc = model_stage (c, m, rb->b, pics, n, false);
   if (rc) { rb->b.release(); delete rb; return rc; }
-  CK (cudaStreamSynchronize (c->stream));
+  CK (cudaStreamSynchronize (m->stream));
   *out = rb;
   return LH264_OK;
 }
@@ -271,15 +287,16 @@ int lh264_model_batch_run (lh264_ctx* c, lh264_model_batch* b) {
 }
 void lh264_model_batch_free (lh264_ctx* c, lh264_model_batch* b) {
   if (!b) return;
-  if (c) { cudaSetDevice (c->device); cudaStreamSynchronize (c->stream); }
+  if (c) { cudaSetDevice (c->device); model_sync (c); }
   b->b.release();
   delete b;
 }
 
 static int model_check_error (lh264_ctx* c, MStreamHost& s) {
+  ModelCtx* m = static_cast<ModelCtx*> (c->model);
   int err = 0;
-  CK (cudaMemcpyAsync (&err, &s.d_state->error, sizeof (int), cudaMemcpyDeviceToHost, c->stream));
-  CK (cudaStreamSynchronize (c->stream));
+  CK (cudaMemcpyAsync (&err, &s.d_state->error, sizeof (int), cudaMemcpyDeviceToHost, m->stream));
+  CK (cudaStreamSynchronize (m->stream));
   if (err >= 11 && err <= 14) return fail (LH264_E_UNSUPPORTED, "a context index left the reference's prior tables (the reference asserts on this input; site %d)", err);
   if (err) { if (err != 2) return fail (LH264_E_CUDA, "model kernels: internal inconsistency %d", err); }
   if (err == 2) return fail (LH264_E_NOMEM, "model output pages exhausted");
@@ -292,10 +309,10 @@ int lh264_model_finish (lh264_ctx* c, int ms) {
   if (rc) return rc;
   CK (cudaSetDevice (c->device));
   unsigned int used = 0;
-  if (m->d_next) { CK (cudaMemcpyAsync (&used, m->d_next, sizeof (used), cudaMemcpyDeviceToHost, c->stream)); CK (cudaStreamSynchronize (c->stream)); }
+  if (m->d_next) { CK (cudaMemcpyAsync (&used, m->d_next, sizeof (used), cudaMemcpyDeviceToHost, m->stream)); CK (cudaStreamSynchronize (m->stream)); }
   if ((rc = model_grow_arena (c, m, used + CT_COUNT))) return rc;
   ArenaDev ar{ m->d_page_ptrs, m->d_next, m->n_pages };
-  k_model_finish<<<1, 32, 0, c->stream>>> (m->streams[ms].d_state, ar);
+  k_model_finish<<<1, 32, 0, m->stream>>> (m->streams[ms].d_state, ar);
   c->launches++;
   CK (cudaGetLastError());
   return model_check_error (c, m->streams[ms]);
@@ -340,3 +357,8 @@ unsigned long long lh264_model_decisions (lh264_ctx* c, int ms) {
 }
 
 } // extern "C"
+
+static cudaError_t model_sync (lh264_ctx* c) {
+  ModelCtx* m = static_cast<ModelCtx*> (c->model);
+  return m && m->stream ? cudaStreamSynchronize (m->stream) : cudaSuccess;
+}
