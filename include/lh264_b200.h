@@ -213,6 +213,9 @@ int  lh264_picture_write(lh264_ctx* ctx, int stream, int slot,
 int  lh264_picture_device_ptrs(lh264_ctx* ctx, int stream, int slot,
                                void** y, void** u, void** v, int* pitch_y, int* pitch_c);
 int  lh264_sync(lh264_ctx* ctx);
+/* Orders the context stream after all model work submitted so far (the model runs on its own CUDA stream); for callers
+ * that time or chain work with events on the stream they passed to lh264_ctx_create.                         */
+int  lh264_join(lh264_ctx* ctx);
 /* Gathers the cropped I420 pictures of n (stream, slot) pairs on the device and brings them to
  * the host with ONE copy: for each picture Y (width x height) then U, V ((w+1)/2 x (h+1)/2),
  * tightly packed, pictures back to back.  dst should be pinned (lh264_host_alloc).           */
@@ -329,8 +332,8 @@ typedef struct lh264_model_picture {
 int  lh264_model_open(lh264_ctx* ctx, int max_mbs, int with_8x8);
 int  lh264_model_close(lh264_ctx* ctx, int model_stream);
 /* Codes one picture per stream for a batch of independent streams (host buffers in; the buffers may be reused when the
- * call returns).  Runs on a CUDA stream of its own, concurrently with reconstruction work queued on the context stream;
- * work queued on the context stream AFTER this call is ordered after it, and lh264_sync() waits for both.  A picture
+ * call returns).  Runs on a CUDA stream of its own, concurrently with reconstruction work on the context stream;
+ * lh264_sync() waits for both, lh264_join() orders the context stream after it.  A picture
  * whose `coefs` pointer equals that of a picture of the immediately preceding lh264_recon_submit() (the same pool, as the
  * host decoder hands it over) reads that batch's device copy instead of being copied again.  Output bytes accumulate on
  * the device and are read with lh264_model_read().                                                                          */

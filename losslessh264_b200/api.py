@@ -22,7 +22,7 @@ EXPORTS = [
     "lh264_abi_version", "lh264_last_error", "lh264_ctx_create", "lh264_ctx_destroy",
     "lh264_stream_open", "lh264_stream_close", "lh264_recon_submit", "lh264_batch_upload",
     "lh264_batch_recon", "lh264_batch_free", "lh264_kernel_launches", "lh264_kernel_ms",
-    "lh264_picture_read", "lh264_picture_write", "lh264_picture_device_ptrs", "lh264_sync",
+    "lh264_picture_read", "lh264_picture_write", "lh264_picture_device_ptrs", "lh264_sync", "lh264_join",
     "lh264_pictures_read_packed", "lh264_host_alloc", "lh264_host_free",
     "lh264_k_idct4x4_add", "lh264_k_idct8x8_add", "lh264_k_mc_luma", "lh264_k_mc_chroma",
     "lh264_k_expand_plane",
@@ -87,6 +87,7 @@ def load_library():
     lib.lh264_kernel_launches.argtypes = [C.c_void_p]
     lib.lh264_kernel_ms.argtypes = [C.c_void_p, C.c_int]
     lib.lh264_sync.argtypes = [C.c_void_p]
+    lib.lh264_join.argtypes = [C.c_void_p]
     lib.lh264_picture_read.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     lib.lh264_picture_write.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     lib.lh264_pictures_read_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
@@ -198,6 +199,10 @@ class Context:
     def sync(self):
         _check(self.lib, self.lib.lh264_sync(self.h))
         self._keep = []
+
+    def join(self):
+        """Orders the context's CUDA stream after the model work submitted so far."""
+        _check(self.lib, self.lib.lh264_join(self.h))
 
     def read_picture(self, stream, slot, mb_w, mb_h, crop=None):
         """Returns the (cropped) I420 picture as a flat uint8 array Y|U|V."""

@@ -84,7 +84,11 @@ struct lh264_ctx {
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   std::vector<StreamRec> streams;
-  BatchDev batch;                            // staging for lh264_recon_submit
+  BatchDev batch[2];                         // staging for lh264_recon_submit, alternating: the model may still read the
+                                             // coefficient pools of the previous batch (shared, see staged_coefs)
+  int batch_cur = 0;
+  cudaEvent_t batch_free[2] = {nullptr, nullptr};   // recorded on the model stream after the model run that shared batch[k]
+  bool batch_shared[2] = {false, false};
   PinBuf<PicDev> h_pics;
   cudaEvent_t staged = nullptr;              // h_pics consumed by the H2D copy
   bool staged_pending = false;
@@ -104,6 +108,7 @@ struct lh264_ctx {
 static void model_destroy (lh264_ctx* c);
 static float model_ms (lh264_ctx* c, int which, bool reset);
 static cudaError_t model_sync (lh264_ctx* c);
+static cudaError_t model_join (lh264_ctx* c);
 
 extern "C" {
 
@@ -130,6 +135,7 @@ int lh264_ctx_create (lh264_ctx** out, int device, void* cuda_stream) {
   else { CK (cudaStreamCreateWithFlags (&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
   CK (cudaEventCreateWithFlags (&c->staged, cudaEventDisableTiming));
   CK (cudaEventCreateWithFlags (&c->recon_staged, cudaEventDisableTiming));
+  for (int i = 0; i < 2; i++) CK (cudaEventCreateWithFlags (&c->batch_free[i], cudaEventDisableTiming));
   for (int i = 0; i < 4; i++) CK (cudaEventCreate (&c->ev[i]));
   *out = c;
   return LH264_OK;
@@ -141,7 +147,8 @@ void lh264_ctx_destroy (lh264_ctx* c) {
   cudaStreamSynchronize (c->stream);
   model_destroy (c);
   for (auto& s : c->streams) if (s.base) cudaFree (s.base);
-  c->batch.release(); c->h_pics.release();
+  c->batch[0].release(); c->batch[1].release(); c->h_pics.release();
+  for (int i = 0; i < 2; i++) if (c->batch_free[i]) cudaEventDestroy (c->batch_free[i]);
   c->pack_jobs.release(); c->h_pack_jobs.release(); c->pack_out.release();
   c->scratch_a.release(); c->scratch_b.release(); c->scratch_c.release();
   if (c->staged) cudaEventDestroy (c->staged);
@@ -244,11 +251,14 @@ int lh264_recon_submit (lh264_ctx* c, const lh264_picture_desc* pics, int n_pics
   for (int i = 0; i < n_pics; i++) for (int j = i + 1; j < n_pics; j++)
       if (n_pics <= 64 && pics[i].stream == pics[j].stream) return fail (LH264_E_INVALID, "two pictures of one stream in a batch");
   c->staged_coefs.clear();
-  int rc = stage_batch (c, c->batch, c->h_pics, pics, n_pics);
+  c->batch_cur ^= 1;
+  const int k = c->batch_cur;
+  if (c->batch_shared[k]) { CK (cudaStreamWaitEvent (c->stream, c->batch_free[k], 0)); c->batch_shared[k] = false; }
+  int rc = stage_batch (c, c->batch[k], c->h_pics, pics, n_pics);
   if (rc) return rc;
   for (int i = 0; i < n_pics; i++) if (pics[i].n_coef_blocks) c->staged_coefs.push_back (std::make_pair (pics[i].coefs, c->h_pics.p[i].coefs));
   CK (cudaEventRecord (c->recon_staged, c->stream));
-  return launch_recon (c, c->batch);
+  return launch_recon (c, c->batch[k]);
 }
 
 int lh264_batch_upload (lh264_ctx* c, const lh264_picture_desc* pics, int n_pics, lh264_resident_batch** out) {
@@ -373,6 +383,13 @@ int lh264_pictures_read_packed (lh264_ctx* c, const int* streams, const int* slo
   CK (cudaMemcpyAsync (dst, c->pack_out.p, per * n, cudaMemcpyDeviceToHost, c->stream));
   CK (cudaStreamSynchronize (c->stream));     // h_pack_jobs is reused by the next call
   (void)sync;
+  return LH264_OK;
+}
+
+int lh264_join (lh264_ctx* c) {
+  if (!c) return fail (LH264_E_INVALID, "null ctx");
+  CK (cudaSetDevice (c->device));
+  CK (model_join (c));
   return LH264_OK;
 }
 

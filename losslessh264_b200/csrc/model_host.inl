@@ -20,11 +20,12 @@ struct MStreamHost {
 struct MBatch {                    // one batch of model pictures in HBM
   DevBuf<lh264_model_mb> recs; DevBuf<lh264_model_slice> slices; DevBuf<int16_t> coefs;
   DevBuf<MPicDev> pics; PinBuf<MPicDev> h_pics;
-  DevBuf<uint16_t> lane_cnt; DevBuf<uint32_t> rec_off; DevBuf<uint32_t> pic_total; DevBuf<unsigned long long> dec_base;
+  DevBuf<uint32_t> rec_cnt; DevBuf<uint32_t> rec_off; DevBuf<uint32_t> pic_total; DevBuf<unsigned long long> dec_base;
   PinBuf<uint32_t> h_total; PinBuf<unsigned long long> h_base;
   std::vector<int> stream_of;
   int n = 0, total_recs = 0;
-  void release() { recs.release(); slices.release(); coefs.release(); pics.release(); h_pics.release(); lane_cnt.release(); rec_off.release();
+  int shares_recon_batch = -1;     // index of the recon staging batch whose coefficient pools this batch reads
+  void release() { recs.release(); slices.release(); coefs.release(); pics.release(); h_pics.release(); rec_cnt.release(); rec_off.release();
                    pic_total.release(); dec_base.release(); h_total.release(); h_base.release(); }
 };
 
@@ -61,6 +62,8 @@ static ModelCtx* model_ctx (lh264_ctx* c) {
     if (!m) return nullptr;
     for (int i = 0; i < 4; i++) cudaEventCreate (&m->ev[i]);
     cudaStreamCreateWithFlags (&m->stream, cudaStreamNonBlocking);
+    cudaFuncSetAttribute (k_model_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (GEN_THREADS * sizeof (ThreadMb)));
+    cudaFuncSetAttribute (k_model_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (GEN_THREADS * sizeof (ThreadMb)));
     cudaEventCreateWithFlags (&m->done, cudaEventDisableTiming);
     c->model = m;
   }
@@ -183,11 +186,12 @@ static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_
     tot_rec += p.n_recs; tot_sl += p.n_slices; tot_blk += p.n_coef_blocks;
   }
   CK (b.recs.reserve (tot_rec)); CK (b.slices.reserve (tot_sl)); CK (b.coefs.reserve (tot_blk * 16 + 16));
-  CK (b.pics.reserve (n)); CK (b.lane_cnt.reserve (tot_rec * 32)); CK (b.rec_off.reserve (tot_rec));
+  CK (b.pics.reserve (n)); CK (b.rec_cnt.reserve (tot_rec)); CK (b.rec_off.reserve (tot_rec));
   CK (b.pic_total.reserve (n)); CK (b.dec_base.reserve (n));
   CK (cudaStreamSynchronize (m->stream));          // pinned staging of the previous batch is free again
   CK (b.h_pics.reserve (n)); CK (b.h_total.reserve (n + 1)); CK (b.h_base.reserve (n));
   b.stream_of.assign (n, 0);
+  bool any_shared = false;
   size_t o_rec = 0, o_sl = 0, o_blk = 0;
   for (int i = 0; i < n; i++) {
     const lh264_model_picture& p = pics[i];
@@ -196,17 +200,18 @@ static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_
     CK (cudaMemcpyAsync (b.slices.p + o_sl, p.slices, (size_t)p.n_slices * sizeof (lh264_model_slice), cudaMemcpyHostToDevice, m->stream));
     const int16_t* dev_coefs = nullptr;
     if (share_coefs && p.n_coef_blocks)
-      for (const auto& sc : c->staged_coefs) if (sc.first == p.coefs) { dev_coefs = sc.second; break; }
+      for (const auto& sc : c->staged_coefs) if (sc.first == p.coefs) { dev_coefs = sc.second; any_shared = true; break; }
     if (p.n_coef_blocks && !dev_coefs) CK (cudaMemcpyAsync (b.coefs.p + o_blk * 16, p.coefs, (size_t)p.n_coef_blocks * 32, cudaMemcpyHostToDevice, m->stream));
     MPicDev& d = b.h_pics.p[i];
     d.recs = b.recs.p + o_rec; d.slices = b.slices.p + o_sl; d.coefs = dev_coefs ? dev_coefs : b.coefs.p + o_blk * 16;
-    d.st = s.d_state; d.lane_cnt = b.lane_cnt.p + o_rec * 32; d.rec_off = b.rec_off.p + o_rec;
+    d.st = s.d_state; d.rec_cnt = b.rec_cnt.p + o_rec; d.rec_off = b.rec_off.p + o_rec;
     d.n_recs = p.n_recs; d.n_slices = p.n_slices; d.mb_w = p.mb_w; d.mb_h = p.mb_h; d.rec_base = (int)o_rec; d.pad = 0;
     b.stream_of[i] = p.model_stream;
     o_rec += p.n_recs; o_sl += p.n_slices; o_blk += p.n_coef_blocks;
   }
   CK (cudaMemcpyAsync (b.pics.p, b.h_pics.p, n * sizeof (MPicDev), cudaMemcpyHostToDevice, m->stream));
-  if (share_coefs) CK (cudaStreamWaitEvent (m->stream, c->recon_staged, 0));     // the shared pools are in HBM
+  b.shares_recon_batch = any_shared ? c->batch_cur : -1;
+  if (any_shared) CK (cudaStreamWaitEvent (m->stream, c->recon_staged, 0));      // the shared pools are in HBM
   b.n = n; b.total_recs = (int)tot_rec;
   return LH264_OK;
 }
@@ -217,10 +222,11 @@ static int model_run (lh264_ctx* c, ModelCtx* m, MBatch& b) {
   const int n = b.n, total_recs = b.total_recs;
   if (n == 0) return LH264_OK;
   for (int i = 0; i < n; i++) if (!m->streams[b.stream_of[i]].open) return fail (LH264_E_INVALID, "batch names a closed model stream");
-  const int mb_blocks = (total_recs + MB_WARPS - 1) / MB_WARPS;
+  const int mb_blocks = (total_recs + GEN_THREADS - 1) / GEN_THREADS;
+  const size_t gen_smem = (size_t)GEN_THREADS * sizeof (ThreadMb);
   if (c->timing) CK (cudaEventRecord (m->ev[0], m->stream));
   k_model_frame<<<n, 32, 0, m->stream>>> (b.pics.p, n);
-  k_model_count<<<mb_blocks, MB_WARPS * 32, 0, m->stream>>> (b.pics.p, n, total_recs);
+  k_model_count<<<mb_blocks, GEN_THREADS, gen_smem, m->stream>>> (b.pics.p, n, total_recs);
   k_model_scan<<<n, 1024, 0, m->stream>>> (b.pics.p, n, b.pic_total.p);
   c->launches += 3;
   CK (cudaMemcpyAsync (b.h_total.p, b.pic_total.p, n * sizeof (uint32_t), cudaMemcpyDeviceToHost, m->stream));
@@ -237,7 +243,7 @@ static int model_run (lh264_ctx* c, ModelCtx* m, MBatch& b) {
   if (rc) return rc;
   CK (cudaMemcpyAsync (b.dec_base.p, b.h_base.p, n * sizeof (unsigned long long), cudaMemcpyHostToDevice, m->stream));
   ArenaDev ar{ m->d_page_ptrs, m->d_next, m->n_pages };
-  k_model_emit<<<mb_blocks, MB_WARPS * 32, 0, m->stream>>> (b.pics.p, n, total_recs, m->dec.p, b.dec_base.p);
+  k_model_emit<<<mb_blocks, GEN_THREADS, gen_smem, m->stream>>> (b.pics.p, n, total_recs, m->dec.p, b.dec_base.p);
   if (c->timing) { CK (cudaEventRecord (m->ev[1], m->stream)); CK (cudaEventRecord (m->ev[2], m->stream)); }
   k_model_code<<<n, 64, 0, m->stream>>> (b.pics.p, n, m->dec.p, b.dec_base.p, b.pic_total.p, ar);
   c->launches += 2;
@@ -248,10 +254,11 @@ static int model_run (lh264_ctx* c, ModelCtx* m, MBatch& b) {
     cudaEventElapsedTime (&t, m->ev[0], m->ev[1]); m->ms_gen += t;
     cudaEventElapsedTime (&t, m->ev[2], m->ev[3]); m->ms_code += t;
   }
-  // later work on the context stream (the next batch's staging overwrites shared pools; callers time with events on it)
-  // is ordered after this batch's model
   CK (cudaEventRecord (m->done, m->stream));
-  CK (cudaStreamWaitEvent (c->stream, m->done, 0));
+  if (b.shares_recon_batch >= 0) {                 // that staging batch may be overwritten once this run is over
+    CK (cudaEventRecord (c->batch_free[b.shares_recon_batch], m->stream));
+    c->batch_shared[b.shares_recon_batch] = true;
+  }
   CK (cudaGetLastError());
   return LH264_OK;
 }
@@ -361,4 +368,12 @@ unsigned long long lh264_model_decisions (lh264_ctx* c, int ms) {
 static cudaError_t model_sync (lh264_ctx* c) {
   ModelCtx* m = static_cast<ModelCtx*> (c->model);
   return m && m->stream ? cudaStreamSynchronize (m->stream) : cudaSuccess;
+}
+
+// the context stream waits for everything submitted to the model stream so far
+static cudaError_t model_join (lh264_ctx* c) {
+  ModelCtx* m = static_cast<ModelCtx*> (c->model);
+  if (!m || !m->stream) return cudaSuccess;
+  cudaError_t e = cudaEventRecord (m->done, m->stream);
+  return e != cudaSuccess ? e : cudaStreamWaitEvent (c->stream, m->done, 0);
 }

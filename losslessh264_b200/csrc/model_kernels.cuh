@@ -114,7 +114,7 @@ struct MPicDev {                      // one picture of the batch
   const lh264_model_slice* slices;
   const int16_t* coefs;
   MState* st;
-  uint16_t* lane_cnt;                 // [n_recs][32]
+  uint32_t* rec_cnt;                  // [n_recs] decisions of the record
   uint32_t* rec_off;                  // [n_recs] position of the record's first decision inside the picture
   int n_recs, n_slices, mb_w, mb_h;
   int rec_base;                       // index of the picture's first record in the batch-wide record numbering
@@ -195,10 +195,10 @@ __constant__ uint8_t c_scan4[16] = { 0, 1, 4, 5, 2, 3, 6, 7, 8, 9, 12, 13, 10, 1
 
 // encode4x4<n>: decode_slice.cpp:2060-2094 with getACPrior4x4/8x8 (macroblock_model.cpp:562-604; the neighbour terms of
 // the index are the constant 2 because priorCoef only fills `past`, :196-262).  nzp = nonzeros prior base.
-template <bool W> __device__ void gen_block (Em<W>& e, const int16_t* ac, int n, bool emit_dc, int color, uint32_t nzp, uint32_t acbase) {
+// cnt_all = non-zero levels of the block including position 0 (from the chunk counts); ac may be nullptr when it is 0.
+template <bool W> __device__ void gen_block (Em<W>& e, const int16_t* ac, int cnt_all, int n, bool emit_dc, int color, uint32_t nzp, uint32_t acbase) {
   const uint8_t* zz = n == 16 ? c_zz16 : c_zz64;
-  int nonzeros = 0;
-  for (int i = emit_dc ? 0 : 1; i < n; i++) nonzeros += ac[zz[i]] != 0;
+  const int nonzeros = cnt_all - ((!emit_dc && cnt_all && ac[0] != 0) ? 1 : 0);
   const uint32_t tEob = color ? CT_C_EOB : CT_L0_EOB;
   e_int (e, nonzeros, nzp + I_EXP, 3, nzp + I_MANT, 0, nzp + I_ZERO, NO_PRIOR, tEob, tEob, tEob, tEob);
   int left = nonzeros, emitted = 0, prev = 0, prev2 = 0;
@@ -212,10 +212,8 @@ template <bool W> __device__ void gen_block (Em<W>& e, const int16_t* ac, int n,
   }
 }
 // which EXP tag streams a block creates without necessarily coding into them (tag().billTo(), decode_slice.cpp:2081-2083)
-__device__ __forceinline__ uint32_t block_touch (const int16_t* ac, int n, bool emit_dc, int color) {
-  const uint8_t* zz = n == 16 ? c_zz16 : c_zz64;
-  int nonzeros = 0;
-  for (int i = emit_dc ? 0 : 1; i < n; i++) nonzeros += ac[zz[i]] != 0;
+__device__ __forceinline__ uint32_t block_touch (const int16_t* ac, int cnt_all, bool emit_dc, int color) {
+  const int nonzeros = cnt_all - ((!emit_dc && cnt_all && ac[0] != 0) ? 1 : 0);
   if (!nonzeros) return 0;
   if (color) return 1u << CT_C_EXP;
   uint32_t m = emit_dc ? 1u << CT_L0_EXP : 0;
@@ -224,27 +222,25 @@ __device__ __forceinline__ uint32_t block_touch (const int16_t* ac, int n, bool 
   return m;
 }
 
-struct WarpMb {                       // per-warp staging in shared memory
+struct CtxRecS {                      // CtxRec without the 16-byte alignment, for the shared-memory staging
+  uint8_t flags, type_code, cbp, num_ref, chroma_mode, i16_mode;
+  uint16_t cachedSkips;
+  uint8_t cnt[24];
+};
+struct WarpMb {                       // staging of one macroblock in shared memory
   lh264_model_mb rec;                 // 128 B
-  int16_t lev[384];                   // dense levels, 24 chunks of 16
-  CtxRec L, A, P;
+  CtxRecS L, A, P;
   uint32_t flagsLAP;                  // bit0 L, bit1 A, bit2 P present
 };
-
-__device__ __forceinline__ void load_rec (WarpMb& s, const lh264_model_mb* r, const int16_t* coefs, int lane) {
-  reinterpret_cast<uint32_t*> (&s.rec)[lane] = __ldg (reinterpret_cast<const uint32_t*> (r) + lane);
-  __syncwarp();
-  const uint32_t mask = (s.rec.flags & LH264_MM_WRITE_BLOCK) ? s.rec.coded_mask : 0u;
-  const uint32_t* src = reinterpret_cast<const uint32_t*> (coefs) + (size_t)s.rec.coef_off * 8;
-#pragma unroll
-  for (int i = 0; i < 6; i++) {
-    const int w = lane + 32 * i, blk = w >> 3;
-    uint32_t v = 0;
-    if ((mask >> blk) & 1) v = __ldg (src + __popc (mask & ((1u << blk) - 1)) * 8 + (w & 7));
-    reinterpret_cast<uint32_t*> (s.lev)[w] = v;
-  }
-  __syncwarp();
+// 16-coefficient chunk b of the macroblock in the picture's coefficient pool (present chunks are consecutive, ordered by
+// bit index of coded_mask); nullptr = not coded = all zero.  The levels are read in place: a chunk is one 32-byte sector
+// that stays in L1 while its thread walks it.
+__device__ __forceinline__ const int16_t* chunk_ptr (const lh264_model_mb& r, const int16_t* pool, int b) {
+  const uint32_t mask = (r.flags & LH264_MM_WRITE_BLOCK) ? r.coded_mask : 0u;
+  if (!((mask >> b) & 1u)) return nullptr;
+  return pool + ((size_t)r.coef_off + __popc (mask & ((1u << b) - 1u))) * 16;
 }
+
 __device__ __forceinline__ int chunk_count (const int16_t* a) {
   int n = 0;
 #pragma unroll
@@ -256,7 +252,7 @@ __device__ __forceinline__ int chunk_count (const int16_t* a) {
 enum { ROLE_HEADER = 0, ROLE_LDC = 1, ROLE_CDC = 2, ROLE_LUMA0 = 3, ROLE_CHROMA0 = 19, ROLE_TAIL = 27 };
 
 // Decisions of one lane role.  Returns through e; touch = EXP tags created.
-template <bool W> __device__ void gen_lane (Em<W>& e, const WarpMb& s, const lh264_model_slice& sl, int lane, bool last_of_slice,
+template <bool W> __device__ void gen_lane (Em<W>& e, const WarpMb& s, const int16_t* pool, const lh264_model_slice& sl, int lane, bool last_of_slice,
                                             const uint8_t* own_cnt, uint32_t* touch, int* error) {
   const lh264_model_mb& r = s.rec;
   const int tc = r.type_code;
@@ -350,7 +346,8 @@ template <bool W> __device__ void gen_lane (Em<W>& e, const WarpMb& s, const lh2
     if (tc != 1) return;
     for (int i = 0; i < 16; i++) {
       const uint32_t p = P_LDC + (((uint32_t)i * 2u + st) * NT + tc) * 16u;
-      e_int (e, s.lev[16 * i], p + I_EXP, 3, p + I_MANT, 0, p + I_ZERO, p + I_SIGN, CT_LDC, CT_LDC, CT_LDC, CT_LDC);
+      const int16_t* dcp = chunk_ptr (r, pool, i);
+      e_int (e, dcp ? dcp[0] : 0, p + I_EXP, 3, p + I_MANT, 0, p + I_ZERO, p + I_SIGN, CT_LDC, CT_LDC, CT_LDC, CT_LDC);
     }
     return;
   }
@@ -358,7 +355,8 @@ template <bool W> __device__ void gen_lane (Em<W>& e, const WarpMb& s, const lh2
     if (cbpC != 1 && cbpC != 2) return;
     for (int i = 0; i < 8; i++) {
       const uint32_t p = P_CDC + (((uint32_t)i * 2u + st) * NT + tc) * 16u;
-      e_int (e, s.lev[256 + 16 * i], p + I_EXP, 3, p + I_MANT, 0, p + I_ZERO, p + I_SIGN, CT_CRDC, CT_CRDC, CT_CRDC, CT_CRDC);
+      const int16_t* dcp = chunk_ptr (r, pool, 16 + i);
+      e_int (e, dcp ? dcp[0] : 0, p + I_EXP, 3, p + I_MANT, 0, p + I_ZERO, p + I_SIGN, CT_CRDC, CT_CRDC, CT_CRDC, CT_CRDC);
     }
     return;
   }
@@ -382,8 +380,10 @@ template <bool W> __device__ void gen_lane (Em<W>& e, const WarpMb& s, const lh2
       const uint32_t nzp = P_NZ8 + (((st * NT + tc) * 3u + min (2, past)) * 3u + min (2, left)) * 3u * 8u + (uint32_t)min (2, above) * 8u;
       if (tc > 7) { *error = 14; return; }
       const uint32_t acb = P_AC8 + ((st * 8u + tc) * 64u) * 125u * 16u;
-      if (touch) *touch |= block_touch (&s.lev[idx * 16], 64, emit_dc, 0);
-      gen_block (e, &s.lev[idx * 16], 64, emit_dc, 0, nzp, acb);
+      const int16_t* ac = chunk_ptr (r, pool, idx);
+      const int call = own_cnt[idx] + own_cnt[idx + 1] + own_cnt[idx + 2] + own_cnt[idx + 3];
+      if (touch) *touch |= block_touch (ac, call, emit_dc, 0);
+      gen_block (e, ac, call, 64, emit_dc, 0, nzp, acb);
     } else {
       // getNonzerosPrior4x4 macroblock_model.cpp:478-527 (colour 0)
       int past = 0, left = 0, above = 0;
@@ -392,8 +392,9 @@ template <bool W> __device__ void gen_lane (Em<W>& e, const WarpMb& s, const lh2
       if (idx < 4) { if (hasA) above = s.A.cnt[idx + 12]; } else above = own_cnt[idx - 4];
       const uint32_t nzp = P_NZ + ((((st * NT + tc) * 3u + 0u) * 3u + min (2, past)) * 3u + min (2, left)) * 3u * 8u + (uint32_t)min (2, above) * 8u;
       const uint32_t acb = P_AC + (((st * 8u + min (tc, 7)) * 3u + 0u) * 16u) * 125u * 16u;
-      if (touch) *touch |= block_touch (&s.lev[idx * 16], 16, emit_dc, 0);
-      gen_block (e, &s.lev[idx * 16], 16, emit_dc, 0, nzp, acb);
+      const int16_t* ac = chunk_ptr (r, pool, idx);
+      if (touch) *touch |= block_touch (ac, own_cnt[idx], emit_dc, 0);
+      gen_block (e, ac, own_cnt[idx], 16, emit_dc, 0, nzp, acb);
     }
     return;
   }
@@ -408,8 +409,9 @@ template <bool W> __device__ void gen_lane (Em<W>& e, const WarpMb& s, const lh2
     if ((i & 2) == 0) { if (hasA) above = s.A.cnt[16 + i + 2]; } else above = own_cnt[16 + i - 2];
     const uint32_t nzp = P_NZ + ((((st * NT + tc) * 3u + color) * 3u + min (2, past)) * 3u + min (2, left)) * 3u * 8u + (uint32_t)min (2, above) * 8u;
     const uint32_t acb = P_AC + (((st * 8u + min (tc, 7)) * 3u + color) * 16u) * 125u * 16u;
-    if (touch) *touch |= block_touch (&s.lev[256 + i * 16], 16, emit_dc, color);
-    gen_block (e, &s.lev[256 + i * 16], 16, emit_dc, color, nzp, acb);
+    const int16_t* ac = chunk_ptr (r, pool, 16 + i);
+    if (touch) *touch |= block_touch (ac, own_cnt[16 + i], emit_dc, color);
+    gen_block (e, ac, own_cnt[16 + i], 16, emit_dc, color, nzp, acb);
     return;
   }
 }
@@ -464,22 +466,22 @@ __global__ void __launch_bounds__ (32) k_model_frame (const MPicDev* pics, int n
   for (int j = lane; j < pic.mb_w * pic.mb_h; j += 32) st->order[j] = 0x7fffffff;
 }
 
-// ---- k_model_count -------------------------------------------------------------------------------------------------
-constexpr int MB_WARPS = 4;
+// ---- k_model_count / k_model_emit: ONE THREAD per macroblock record ---------------------------------------------------
+// A typical inter macroblock produces ~25 header decisions and a handful of block decisions; a warp per macroblock left
+// 31 lanes idle most of the time.  Here every thread owns one record: it stages the record and its three context records
+// in a private slice of shared memory (stride 63 words: odd, so equal-field accesses of the 32 lanes hit 32 different
+// banks), reads coefficient chunks in place, and walks the lane roles of gen_lane() in the reference's emission order.
+constexpr int GEN_THREADS = 256;
+struct ThreadMb { WarpMb m; uint8_t own[24]; };
+static_assert (sizeof (ThreadMb) == 252, "ThreadMb stride must stay an odd number of words");
 
-__device__ __forceinline__ const lh264_model_slice* find_slice (const MPicDev& pic, int rec, int lane, int* sidx) {
-  int found = -1;
-  for (int b = 0; b < pic.n_slices && found < 0; b += 32) {
-    const int i = b + lane;
-    bool hit = false;
-    if (i < pic.n_slices) { const int f = pic.slices[i].first_rec; hit = rec >= f && rec < f + pic.slices[i].n_recs; }
-    const unsigned m = __ballot_sync (0xffffffffu, hit);
-    if (m) found = b + __ffs (m) - 1;
-  }
-  *sidx = found;
-  return found >= 0 ? &pic.slices[found] : nullptr;
+// slices of a picture are in arrival order, first_rec increasing
+__device__ __forceinline__ int find_slice (const MPicDev& pic, int rec) {
+  int lo = 0, hi = pic.n_slices - 1;
+  while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (pic.slices[mid].first_rec <= rec) lo = mid; else hi = mid - 1; }
+  const lh264_model_slice& sl = pic.slices[lo];
+  return rec >= sl.first_rec && rec < sl.first_rec + sl.n_recs ? lo : -1;
 }
-
 // batch-wide record numbering -> (picture, record): binary search over MPicDev::rec_base
 __device__ __forceinline__ int find_pic (const MPicDev* pics, int n_pics, int g) {
   int lo = 0, hi = n_pics - 1;
@@ -487,60 +489,104 @@ __device__ __forceinline__ int find_pic (const MPicDev* pics, int n_pics, int g)
   return lo;
 }
 
-__global__ void __launch_bounds__ (MB_WARPS * 32) k_model_count (const MPicDev* pics, int n_pics, int total_recs) {
-  __shared__ WarpMb sm[MB_WARPS];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = blockIdx.x * MB_WARPS + warp;
-  if (g >= total_recs) return;
-  const int p = find_pic (pics, n_pics, g);
+// Which picture / record every thread of the block owns.  The block's records are consecutive in the batch-wide numbering,
+// so the binary search runs once per block (thread 0) and the other threads only step over picture boundaries.
+__device__ __forceinline__ bool block_locate (const MPicDev* pics, int n_pics, int total_recs, int* p_out, int* ri_out) {
+  __shared__ int s_first_pic;
+  const int g = blockIdx.x * GEN_THREADS + threadIdx.x;
+  if (threadIdx.x == 0) s_first_pic = find_pic (pics, n_pics, blockIdx.x * GEN_THREADS);
+  __syncthreads();
+  if (g >= total_recs) return false;
+  int p = s_first_pic;
+  while (p + 1 < n_pics && pics[p + 1].rec_base <= g) p++;
+  *p_out = p; *ri_out = g - pics[p].rec_base;
+  return true;
+}
+// The warp copies its 32 records (4 KB, contiguous unless a picture boundary intervenes) with coalesced loads.
+__device__ __forceinline__ void warp_stage_recs (ThreadMb* tm, const lh264_model_mb* my_rec, bool active) {
+  const int lane = threadIdx.x & 31, w0 = threadIdx.x & ~31;
+  for (int i = 0; i < 32; i++) {
+    const unsigned long long a = __shfl_sync (0xffffffffu, (unsigned long long)my_rec, i);
+    const int on = __shfl_sync (0xffffffffu, (int)active, i);
+    if (on) reinterpret_cast<uint32_t*> (&tm[w0 + i].m.rec)[lane] = __ldg (reinterpret_cast<const uint32_t*> (a) + lane);
+  }
+  __syncwarp();
+}
+// non-zero levels per 16-coefficient chunk (DC slot included): what the neighbour contexts and FreqImage::updateFrame need
+__device__ __forceinline__ void t_count_chunks (ThreadMb& t, const int16_t* coefs) {
+  const uint32_t mask = (t.m.rec.flags & LH264_MM_WRITE_BLOCK) ? t.m.rec.coded_mask : 0u;
+  const uint4* pool = reinterpret_cast<const uint4*> (coefs) + (size_t)t.m.rec.coef_off * 2;
+  int k = 0;
+  for (int b = 0; b < 24; b++) {
+    int n = 0;
+    if ((mask >> b) & 1u) {
+      const uint4 x = __ldg (pool + 2 * k), y = __ldg (pool + 2 * k + 1);
+      k++;
+      const uint32_t w[8] = { x.x, x.y, x.z, x.w, y.x, y.y, y.z, y.w };
+#pragma unroll
+      for (int i = 0; i < 8; i++) n += ((w[i] & 0xffffu) != 0) + ((w[i] >> 16) != 0);
+    }
+    t.own[b] = (uint8_t)n;
+  }
+}
+__device__ __forceinline__ void t_load_ctx (CtxRecS& dst, const CtxRec* src) {
+  uint32_t* d = reinterpret_cast<uint32_t*> (&dst);
+  if (src) {
+    const uint4 a = reinterpret_cast<const uint4*> (src)[0], b = reinterpret_cast<const uint4*> (src)[1];
+    d[0] = a.x; d[1] = a.y; d[2] = a.z; d[3] = a.w; d[4] = b.x; d[5] = b.y; d[6] = b.z; d[7] = b.w;
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; i++) d[i] = 0;
+  }
+}
+
+__global__ void __launch_bounds__ (GEN_THREADS) k_model_count (const MPicDev* pics, int n_pics, int total_recs) {
+  extern __shared__ __align__ (16) unsigned char gen_smem[];
+  ThreadMb* tm = reinterpret_cast<ThreadMb*> (gen_smem);
+  ThreadMb& t = tm[threadIdx.x];
+  int p = 0, ri = 0;
+  const bool active = block_locate (pics, n_pics, total_recs, &p, &ri);
+  warp_stage_recs (tm, active ? &pics[p].recs[ri] : nullptr, active);
+  if (!active) return;
   const MPicDev& pic = pics[p];
-  const int ri = g - pic.rec_base;
-  WarpMb& s = sm[warp];
-  load_rec (s, &pic.recs[ri], pic.coefs, lane);
-  int sidx;
-  const lh264_model_slice* sl = find_slice (pic, ri, lane, &sidx);
-  if (!sl) { pic.lane_cnt[(size_t)ri * 32 + lane] = 0; return; }
+  t_count_chunks (t, pic.coefs);
+  const int sidx = find_slice (pic, ri);
+  if (sidx < 0) { pic.rec_cnt[ri] = 0; return; }
+  const lh264_model_slice& sl = pic.slices[sidx];
   MState* st = pic.st;
-  const lh264_model_mb& r = s.rec;
+  const lh264_model_mb& r = t.m.rec;
   const bool write = r.flags & LH264_MM_WRITE_BLOCK;
+  const bool in_range = (int)r.mb_addr < pic.mb_w * pic.mb_h;
+  if (!in_range) { pic.rec_cnt[ri] = 0; return; }
   // context record of this MB: a coded MB stores its own data, a skipped one copies the co-located record of the other frame
   // (decode_slice.cpp:3098-3109)
-  const int mycnt = lane < 24 ? chunk_count (&s.lev[lane * 16]) : 0;
-  const bool in_range = (int)r.mb_addr < pic.mb_w * pic.mb_h;
-  if (in_range) {
-    CtxRec* dst = &st->newrec[r.mb_addr];
+  const CtxRec* past = &st->frame[1 - st->cur][r.mb_addr];
+  {
+    uint4* dst = reinterpret_cast<uint4*> (&st->newrec[r.mb_addr]);
     if (write) {
-      if (lane < 24) dst->cnt[lane] = (uint8_t)mycnt;
-      if (lane == 24) {
-        dst->flags = 1; dst->type_code = r.type_code; dst->cbp = r.cbp; dst->num_ref = sl->num_ref_idx_l0;
-        dst->chroma_mode = r.chroma_mode; dst->i16_mode = r.i16_mode; dst->cachedSkips = 0;
-      }
-    } else if (lane < 8) {
-      reinterpret_cast<uint32_t*> (dst)[lane] = reinterpret_cast<const uint32_t*> (&st->frame[1 - st->cur][r.mb_addr])[lane];
+      CtxRec n;
+      n.flags = 1; n.type_code = r.type_code; n.cbp = r.cbp; n.num_ref = sl.num_ref_idx_l0;
+      n.chroma_mode = r.chroma_mode; n.i16_mode = r.i16_mode; n.cachedSkips = 0;
+#pragma unroll
+      for (int i = 0; i < 24; i++) n.cnt[i] = t.own[i];
+      dst[0] = reinterpret_cast<const uint4*> (&n)[0]; dst[1] = reinterpret_cast<const uint4*> (&n)[1];
+    } else {
+      dst[0] = reinterpret_cast<const uint4*> (past)[0]; dst[1] = reinterpret_cast<const uint4*> (past)[1];
     }
-    if (lane == 0) st->order[r.mb_addr] = ri;
+    st->order[r.mb_addr] = ri;
   }
-  // decision counts per lane role.  The binarisation is context free except for the two intra mode symbols, whose
-  // "preferred" value comes from the co-located record of the other frame (PAST), so only that neighbour is loaded here.
-  __shared__ uint8_t own[MB_WARPS][24];
-  if (lane < 24) own[warp][lane] = (uint8_t)mycnt;
-  if (lane < 24) {
-    uint32_t v = 0;
-    if (lane >= 16 && in_range && !(st->no_past_slice0 && sidx == 0)) v = reinterpret_cast<const uint32_t*> (&st->frame[1 - st->cur][r.mb_addr])[lane & 7];
-    reinterpret_cast<uint32_t*> (&s.L)[lane] = v;
-  }
-  __syncwarp();
-  if (lane == 0) s.flagsLAP = (s.P.flags & 1u) << 2;
-  __syncwarp();
+  // The binarisation is context free except for the two intra mode symbols, whose "preferred" value comes from the
+  // co-located record of the other frame (PAST), so only that neighbour is loaded for counting.
+  t_load_ctx (t.m.L, nullptr); t_load_ctx (t.m.A, nullptr);
+  t_load_ctx (t.m.P, (st->no_past_slice0 && sidx == 0) ? nullptr : past);
+  t.m.flagsLAP = (t.m.P.flags & 1u) << 2;
   Em<false> e; e.out = nullptr; e.n = 0;
   int err = 0;
   uint32_t touch = 0;
-  const bool last = ri == sl->first_rec + sl->n_recs - 1;
-  if (in_range) gen_lane<false> (e, s, *sl, lane, last, own[warp], &touch, &err);
-  pic.lane_cnt[(size_t)ri * 32 + lane] = (uint16_t)min (e.n, 65535u);
-  if (e.n > 65535u) err = 15;
-  touch = __reduce_or_sync (0xffffffffu, touch);
-  if (lane == 0 && touch) atomicOr (&st->used, touch);
+  const bool last = ri == sl.first_rec + sl.n_recs - 1;
+  for (int role = 0; role <= ROLE_TAIL; role++) gen_lane<false> (e, t.m, pic.coefs, sl, role, last, t.own, &touch, &err);
+  pic.rec_cnt[ri] = e.n;
+  if (touch) atomicOr (&st->used, touch);
   if (err) st->error = err;
 }
 
@@ -555,15 +601,7 @@ __global__ void __launch_bounds__ (1024) k_model_scan (const MPicDev* pics, int 
   __syncthreads();
   for (int base = 0; base < pic.n_recs; base += 1024) {
     const int i = base + tid;
-    uint32_t v = 0;
-    if (i < pic.n_recs) {
-      const uint4* q = reinterpret_cast<const uint4*> (pic.lane_cnt + (size_t)i * 32);
-#pragma unroll
-      for (int k = 0; k < 4; k++) {
-        const uint4 a = q[k];
-        v += (a.x & 0xffff) + (a.x >> 16) + (a.y & 0xffff) + (a.y >> 16) + (a.z & 0xffff) + (a.z >> 16) + (a.w & 0xffff) + (a.w >> 16);
-      }
-    }
+    const uint32_t v = i < pic.n_recs ? pic.rec_cnt[i] : 0u;
     uint32_t x = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync (0xffffffffu, x, o); if (lane >= o) x += y; }
@@ -585,58 +623,40 @@ __global__ void __launch_bounds__ (1024) k_model_scan (const MPicDev* pics, int 
   if (tid == 0) pic_total[p] = carry_s;
 }
 
-// ---- k_model_emit ------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__ (MB_WARPS * 32) k_model_emit (const MPicDev* pics, int n_pics, int total_recs, uint32_t* dec, const unsigned long long* dec_base) {
-  __shared__ WarpMb sm[MB_WARPS];
-  __shared__ uint8_t own[MB_WARPS][24];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = blockIdx.x * MB_WARPS + warp;
-  if (g >= total_recs) return;
-  const int p = find_pic (pics, n_pics, g);
+__global__ void __launch_bounds__ (GEN_THREADS) k_model_emit (const MPicDev* pics, int n_pics, int total_recs, uint32_t* dec, const unsigned long long* dec_base) {
+  extern __shared__ __align__ (16) unsigned char gen_smem[];
+  ThreadMb* tm = reinterpret_cast<ThreadMb*> (gen_smem);
+  ThreadMb& t = tm[threadIdx.x];
+  int p = 0, ri = 0;
+  bool active = block_locate (pics, n_pics, total_recs, &p, &ri);
+  const uint32_t cnt = active ? pics[p].rec_cnt[ri] : 0u;
+  active = active && cnt != 0;
+  warp_stage_recs (tm, active ? &pics[p].recs[ri] : nullptr, active);
+  if (!active) return;
   const MPicDev& pic = pics[p];
-  const int ri = g - pic.rec_base;
-  WarpMb& s = sm[warp];
-  load_rec (s, &pic.recs[ri], pic.coefs, lane);
-  int sidx;
-  const lh264_model_slice* sl = find_slice (pic, ri, lane, &sidx);
-  if (!sl) return;
+  t_count_chunks (t, pic.coefs);
+  const int sidx = find_slice (pic, ri);
+  if (sidx < 0) return;
+  const lh264_model_slice& sl = pic.slices[sidx];
   MState* st = pic.st;
-  const lh264_model_mb& r = s.rec;
-  if ((int)r.mb_addr >= pic.mb_w * pic.mb_h) return;
+  const lh264_model_mb& r = t.m.rec;
   const int mbx = (int) (r.mb_addr % (unsigned)pic.mb_w), mby = (int) (r.mb_addr / (unsigned)pic.mb_w);
   // Neighbors::init macroblock_model.cpp:9-44.  LEFT/ABOVE come from the frame being written: the record of this picture if
   // that MB precedes this one in slice-data order, else whatever the buffer still holds from two frames ago.
-  if (lane < 24) {
-    const int which = lane >> 3, w = lane & 7;         // 0 L, 1 A, 2 P
-    uint32_t v = 0;
-    if (which == 0 && mbx > 0) {
-      const int nb = (int)r.mb_addr - 1;
-      const CtxRec* src = st->order[nb] < ri ? &st->newrec[nb] : &st->frame[st->cur][nb];
-      v = reinterpret_cast<const uint32_t*> (src)[w];
-    } else if (which == 1 && mby > 0) {
-      const int nb = (int)r.mb_addr - pic.mb_w;
-      const CtxRec* src = st->order[nb] < ri ? &st->newrec[nb] : &st->frame[st->cur][nb];
-      v = reinterpret_cast<const uint32_t*> (src)[w];
-    } else if (which == 2 && !(st->no_past_slice0 && sidx == 0)) {
-      v = reinterpret_cast<const uint32_t*> (&st->frame[1 - st->cur][r.mb_addr])[w];
-    }
-    reinterpret_cast<uint32_t*> (&s.L)[lane] = v;      // L, A, P are contiguous
+  {
+    const CtxRec* l = nullptr; const CtxRec* a = nullptr;
+    if (mbx > 0) { const int nb = (int)r.mb_addr - 1; l = st->order[nb] < ri ? &st->newrec[nb] : &st->frame[st->cur][nb]; }
+    if (mby > 0) { const int nb = (int)r.mb_addr - pic.mb_w; a = st->order[nb] < ri ? &st->newrec[nb] : &st->frame[st->cur][nb]; }
+    t_load_ctx (t.m.L, l); t_load_ctx (t.m.A, a);
+    t_load_ctx (t.m.P, (st->no_past_slice0 && sidx == 0) ? nullptr : &st->frame[1 - st->cur][r.mb_addr]);
+    t.m.flagsLAP = (t.m.L.flags & 1u) | ((t.m.A.flags & 1u) << 1) | ((t.m.P.flags & 1u) << 2);
   }
-  if (lane < 24) own[warp][lane] = (uint8_t)chunk_count (&s.lev[lane * 16]);
-  __syncwarp();
-  if (lane == 0) s.flagsLAP = (s.L.flags & 1u) | ((s.A.flags & 1u) << 1) | ((s.P.flags & 1u) << 2);
-  __syncwarp();
-  // position of this lane's decisions
-  const uint32_t cnt = pic.lane_cnt[(size_t)ri * 32 + lane];
-  uint32_t x = cnt;
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync (0xffffffffu, x, o); if (lane >= o) x += y; }
   Em<true> e;
-  e.out = dec + dec_base[p] + pic.rec_off[ri] + (x - cnt);
+  e.out = dec + dec_base[p] + pic.rec_off[ri];
   e.n = 0;
   int err = 0;
-  const bool last = ri == sl->first_rec + sl->n_recs - 1;
-  if (cnt) gen_lane<true> (e, s, *sl, lane, last, own[warp], nullptr, &err);
+  const bool last = ri == sl.first_rec + sl.n_recs - 1;
+  for (int role = 0; role <= ROLE_TAIL; role++) gen_lane<true> (e, t.m, pic.coefs, sl, role, last, t.own, nullptr, &err);
   if (err) st->error = err; else if (e.n != cnt) st->error = 16;
 }
 
