@@ -25,7 +25,12 @@ typedef enum {
   DECODER_OPTION_DATAFORMAT = 0, DECODER_OPTION_END_OF_STREAM, DECODER_OPTION_VCL_NAL, DECODER_OPTION_TEMPORAL_ID,
   DECODER_OPTION_FRAME_NUM, DECODER_OPTION_IDR_PIC_ID, DECODER_OPTION_LTR_MARKING_FLAG, DECODER_OPTION_LTR_MARKED_FRAME_NUM,
   DECODER_OPTION_ERROR_CON_IDC, DECODER_OPTION_TRACE_LEVEL, DECODER_OPTION_TRACE_CALLBACK, DECODER_OPTION_TRACE_CALLBACK_CONTEXT,
-  DECODER_OPTION_GET_STATISTICS
+  DECODER_OPTION_GET_STATISTICS,
+  /* Extension of this library (not in OpenH264): SetOption (.., const char* path) switches the recompressor on, as the
+   * reference's h264dec does when its OUTPUT name contains ".pip" (h264dec.cpp:167-169).  Units fed through
+   * DecodeFrameNoDelay are then also modelled on the GPU; Uninitialize() (or a SetOption with NULL) writes `path` (the
+   * default stream) and `path.<tag>` (one file per arithmetic-coded side stream), compression_stream.cpp:269-287.     */
+  DECODER_OPTION_LH264_PIP_OUTPUT = 1000
 } DECODER_OPTION;
 
 /* codec_app_def.h:171-180 */

@@ -63,6 +63,7 @@ struct Decoder::Impl {
   std::vector<int8_t> ipm;               // [mb][16] Intra4x4/8x8PredMode per raster block; 2 for other MB types
   std::vector<int16_t> mb_slice;         // slice number of each MB, -1 = not decoded in this picture
   std::vector<ModelMbSide> side;
+  std::vector<uint8_t> slice_rbsp;
   // recompression-model hand-off (include/lh264_b200.h, lh264_model_*): records in slice-data order
   bool want_model = false;
   std::vector<lh264_model_mb> mrecs;
@@ -752,6 +753,7 @@ int Decoder::decode (const uint8_t* data, size_t len, unsigned long long timesta
   std::vector<NalSpan> nals;
   split_annexb (data, len, nals);
   int last_err = 0;
+  last_slice_ = LastSlice();
   for (const NalSpan& n : nals) {
     stats_.nals++;
     if (n.len < 1) continue;
@@ -763,6 +765,7 @@ int Decoder::decode (const uint8_t* data, size_t len, unsigned long long timesta
       if (parse_sps (br, s)) {
         if (D.open && D.active_sps == s.id) D.finish_picture (this);
         D.sps[s.id] = s;
+        sps_seen_ = true;
       } else { last_err = -10; stats_.errors++; }
     } else if (type == NAL_PPS) {
       Pps p;
@@ -810,6 +813,8 @@ int Decoder::decode (const uint8_t* data, size_t len, unsigned long long timesta
       D.slices.push_back (sr);
       stats_.slices++;
       br.seek (sh.header_bits);
+      D.slice_rbsp.assign (D.rbsp.begin(), D.rbsp.begin() + std::min (D.rbsp.size(), (sh.header_bits + 7) / 8));   // for last_slice()
+      last_slice_.decoded = true; last_slice_.cabac = pps.cabac; last_slice_.rbsp = D.slice_rbsp.data(); last_slice_.header_bits = sh.header_bits;
       if (D.parse_slice_data (br, this) < 0) last_err = -40;
       if (D.decoded >= D.n_mbs) D.finish_picture (this);
     } else if (type == NAL_END_SEQ || type == NAL_END_STREAM) {

@@ -71,6 +71,11 @@ class Decoder {
   const std::vector<DecodedPictureInfo>& output() const { return out_; }
   void clear_output() { out_.clear(); }
   void enable_model (bool on);           // produce lh264_model_picture hand-offs (PictureSink::submit_model)
+  // the last slice NAL handled by the last decode() call (for the `.pip` default stream, pip_container.h); rbsp is valid
+  // until the next decode() call
+  struct LastSlice { bool decoded = false, cabac = false; const uint8_t* rbsp = nullptr; size_t header_bits = 0; };
+  const LastSlice& last_slice() const { return last_slice_; }
+  bool sps_seen() const { return sps_seen_; }
   bool keep_model_side = false;          // fill ModelMbSide records
   const std::vector<ModelMbSide>& model_side() const;
 
@@ -79,6 +84,8 @@ class Decoder {
   std::unique_ptr<Impl> d_;
   DecoderStats stats_;
   std::vector<DecodedPictureInfo> out_;
+  LastSlice last_slice_;
+  bool sps_seen_ = false;
 };
 
 } // namespace lh264host

@@ -1,6 +1,7 @@
 // main_h264dec.cpp — h264dec-compatible console decoder over libopenh264_lh264.so.
 // Mirrors the reference CLI contract (codec/console/dec/src/h264dec.cpp:123-402, :407-564):
 //   h264dec <in.264> <out.yuv>           decode, write cropped I420 frames
+//   h264dec <in.264> <out.pip> [yuv]     compress: decode + recompression model; writes out.pip and out.pip.<tag>
 // one NAL unit per DecodeFrameNoDelay call (3- or 4-byte start codes), the same getters queried
 // after every call, the same "iWidth/height/Frames/decode time/FPS" block on stderr.
 // The .pip compress/decompress modes are selected by file-name suffix exactly like the reference
@@ -11,6 +12,7 @@
 #include <chrono>
 #include <vector>
 #include "../../include/lh264_codec_api.h"
+#include "pip_container.h"
 
 static void write_frame (FILE* f, unsigned char** d, const SBufferInfo& bi) {
   const int w = bi.UsrData.sSystemBuffer.iWidth, h = bi.UsrData.sSystemBuffer.iHeight;
@@ -20,8 +22,10 @@ static void write_frame (FILE* f, unsigned char** d, const SBufferInfo& bi) {
 }
 
 int main (int argc, char** argv) {
-  if (argc < 3) { fprintf (stderr, "usage: %s <in.264> <out.yuv>\n", argv[0]); return 1; }
-  if (strstr (argv[2], ".pip") || strstr (argv[1], ".pip")) { fprintf (stderr, "the .pip recompression modes are not built into this binary yet\n"); return 2; }
+  if (argc < 3) { fprintf (stderr, "usage: %s <in.264> <out.yuv> | <in.264> <out.pip> [out.yuv]\n", argv[0]); return 1; }
+  const bool compress = strstr (argv[2], ".pip") != nullptr;             // h264dec.cpp:167-169
+  if (!compress && strstr (argv[1], ".pip")) { fprintf (stderr, "decompression (.pip -> .264) is not built into this binary yet (SURVEY 8f N1)\n"); return 2; }
+  const char* yuv_path = compress ? (argc > 3 ? argv[3] : "/dev/null") : argv[2];
   FILE* fi = fopen (argv[1], "rb");
   if (!fi) { perror (argv[1]); return 1; }
   std::vector<unsigned char> buf;
@@ -32,8 +36,8 @@ int main (int argc, char** argv) {
   const size_t size = buf.size();
   static const unsigned char kStart[4] = {0, 0, 0, 1};
   buf.insert (buf.end(), kStart, kStart + 4);          // sentinel, h264dec.cpp:227-238
-  FILE* fo = fopen (argv[2], "wb");
-  if (!fo) { perror (argv[2]); return 1; }
+  FILE* fo = fopen (yuv_path, "wb");
+  if (!fo) { perror (yuv_path); return 1; }
 
   ISVCDecoder* dec = nullptr;
   if (WelsCreateDecoder (&dec) || !dec) { fprintf (stderr, "WelsCreateDecoder failed\n"); return 1; }
@@ -42,15 +46,14 @@ int main (int argc, char** argv) {
   param.eOutputColorFormat = videoFormatI420; param.uiTargetDqLayer = 255; param.eEcActiveIdc = ERROR_CON_SLICE_COPY;
   param.sVideoProperty.eVideoBsType = VIDEO_BITSTREAM_DEFAULT;
   if (dec->Initialize (&param)) { fprintf (stderr, "Initialize failed (no CUDA device? this build has no CPU fallback)\n"); return 1; }
+  if (compress && dec->SetOption (DECODER_OPTION_LH264_PIP_OUTPUT, argv[2])) { fprintf (stderr, "cannot switch the recompressor on\n"); return 1; }
 
   int frames = 0, width = 0, height = 0;
   double secs = 0;
-  // start-code positions (a 4-byte start code's leading zero is kept with the NAL it introduces)
-  std::vector<size_t> starts;
-  for (size_t i = 0; i + 3 <= size + 4; i++)
-    if (buf[i] == 0 && buf[i + 1] == 0 && buf[i + 2] == 1) { starts.push_back (i > 0 && buf[i - 1] == 0 && (starts.empty() || starts.back() + 3 < i) ? i - 1 : i); i += 2; }
-  for (size_t k = 0; k + 1 < starts.size(); k++) {
-    const size_t pos = starts[k], len = starts[k + 1] - starts[k];
+  // the Annex-B unit loop of the reference CLI (h264dec.cpp:246-364): a unit runs up to the next 3- or 4-byte start code
+  for (size_t pos = 0; pos < size;) {
+    const size_t len = lh264host::PipBoilerplate::next_unit (buf.data(), pos, size);
+    struct Advance { size_t& p; size_t n; ~Advance() { p += n; } } advance{pos, len};
     unsigned char* dst[3] = {nullptr, nullptr, nullptr};
     SBufferInfo bi;
     memset (&bi, 0, sizeof (bi));

@@ -10,6 +10,9 @@
 #include "../../include/lh264_codec_api.h"
 #include "decoder.h"
 #include "sinks.h"
+#include "pip_container.h"
+#include <string>
+#include <stdio.h>
 
 using namespace lh264host;
 
@@ -33,6 +36,7 @@ class CLh264Decoder : public ISVCDecoder {
     return cmResultSuccess;
   }
   long Uninitialize() override {
+    write_pip();
     delete dec_; dec_ = nullptr;
     delete sink_; sink_ = nullptr;
     if (out_) { lh264_host_free (out_); out_ = nullptr; out_cap_ = 0; }
@@ -62,6 +66,14 @@ class CLh264Decoder : public ISVCDecoder {
   DECODING_STATE DecodeFrameEx (const unsigned char*, const int, unsigned char*, int, int& iDstLen, int&, int&, int&) override { iDstLen = 0; return dsErrorFree; }
 
   long SetOption (DECODER_OPTION id, void* opt) override {
+    if (id == DECODER_OPTION_LH264_PIP_OUTPUT) {       // extension: see include/lh264_codec_api.h
+      if (!opt) return write_pip() ? cmResultSuccess : cmUnkonwReason;
+      if (!dec_) return cmInitExpected;
+      pip_path_ = (const char*)opt;
+      pip_ = new (std::nothrow) PipBoilerplate();
+      dec_->enable_model (true);
+      return pip_ ? cmResultSuccess : cmMallocMemeError;
+    }
     if (!opt) return cmInitParaError;
     switch (id) {
     case DECODER_OPTION_DATAFORMAT: return * (int*)opt == videoFormatI420 ? cmResultSuccess : cmInitParaError;
@@ -100,7 +112,17 @@ class CLh264Decoder : public ISVCDecoder {
     int state = dsErrorFree;
     dec_->clear_output();
     if (src && len > 0) {
+      if (pip_ && no_delay) {
+        if (len < 4) { pip_->raw (src, (size_t)len); return (DECODING_STATE)state; }     // h264dec.cpp:268-271
+        pip_->unit_begin (src, (size_t)len, dec_->sps_seen());
+      }
       const int rc = dec_->decode (src, (size_t)len, ts);
+      if (pip_ && no_delay) {
+        UnitSliceInfo u;
+        u.slice_decoded = dec_->last_slice().decoded; u.cabac = dec_->last_slice().cabac;
+        u.rbsp = dec_->last_slice().rbsp; u.header_bits = dec_->last_slice().header_bits;
+        pip_->unit_end (u);
+      }
       if (rc == -2) state |= dsNoParamSets;
       else if (rc < 0) state |= dsBitstreamError;
       last_vcl_ = 1;
@@ -135,8 +157,30 @@ class CLh264Decoder : public ISVCDecoder {
     return (DECODING_STATE)state;
   }
 
+  // writes the `.pip` file set: default stream + one file per tag that has a stream (MultiFileWriter, h264dec.cpp:79-104)
+  bool write_pip() {
+    if (!pip_ || !sink_ || !dec_) return true;
+    dec_->flush();
+    bool ok = sink_->model_finish() == LH264_OK;
+    const std::vector<uint8_t>& d = pip_->finish();
+    FILE* f = fopen (pip_path_.c_str(), "wb");
+    if (f) { fwrite (d.data(), 1, d.size(), f); fclose (f); } else ok = false;
+    std::vector<uint8_t> b;
+    for (int tag = 1; tag < LH264_NUM_TAGS && ok; tag++) {
+      if (sink_->model_tag_bytes (tag, b) != LH264_OK) { ok = false; break; }
+      if (b.empty()) continue;
+      const std::string name = pip_path_ + "." + std::to_string (tag);
+      FILE* ft = fopen (name.c_str(), "wb");
+      if (ft) { fwrite (b.data(), 1, b.size(), ft); fclose (ft); } else ok = false;
+    }
+    delete pip_; pip_ = nullptr;
+    return ok;
+  }
+
   Decoder* dec_ = nullptr;
   GpuSink* sink_ = nullptr;
+  PipBoilerplate* pip_ = nullptr;
+  std::string pip_path_;
   std::deque<DecodedPictureInfo> queue_;
   unsigned char* out_ = nullptr;
   size_t out_cap_ = 0;

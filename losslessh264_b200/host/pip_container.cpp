@@ -1,0 +1,74 @@
+// pip_container.cpp — see pip_container.h.
+#include "pip_container.h"
+#include "h264_syntax.h"
+
+namespace lh264host {
+
+void DefaultStream::append_byte (uint8_t x) {          // BitStream::appendByte, compression_stream.cpp:51-69
+  if (!escaping_) { buf_.push_back (x); return; }
+  if (x <= 3 && esc_n_ == 2 && esc_[0] == 0 && esc_[1] == 0) {
+    buf_.push_back (0); buf_.push_back (0); buf_.push_back (3); buf_.push_back (x);
+    esc_n_ = 0;
+  } else if (esc_n_ == 2) {
+    buf_.push_back (esc_[0]);
+    esc_[0] = esc_[1]; esc_[1] = x;
+  } else esc_[esc_n_++] = x;
+}
+void DefaultStream::append_bytes (const uint8_t* p, size_t n) { for (size_t i = 0; i < n; i++) append_byte (p[i]); }
+void DefaultStream::emit_bits (uint32_t bits, uint32_t n) {      // BitStream::emitBits :89-112
+  n += n_bits_;
+  bits <<= 32 - n;
+  bits |= bits_;
+  while (n >= 8) { append_byte ((uint8_t) (bits >> 24)); bits <<= 8; n -= 8; }
+  bits_ = bits; n_bits_ = (uint8_t)n;
+}
+void DefaultStream::pad_to_byte (int val) { for (int i = n_bits_; (i & 7) != 0; ++i) emit_bit ((uint32_t)val); }
+void DefaultStream::stop_escape() {                    // compression_stream.h:71-84 (flushBits pads with zero bits)
+  while (n_bits_ > 0) emit_bits (0, 1);
+  escaping_ = false;
+  const uint8_t tmp[2] = {esc_[0], esc_[1]};
+  const uint32_t n = esc_n_;
+  esc_n_ = 0;
+  append_bytes (tmp, n);
+}
+
+size_t PipBoilerplate::next_unit (const uint8_t* b, size_t pos, size_t file_size) {
+  size_t i;
+  for (i = 0; i < file_size; i++) {
+    const uint8_t* q = b + pos + i;
+    if (i > 0 && q[0] == 0 && q[1] == 0 && ((q[2] == 0 && q[3] == 1) || q[2] == 1)) break;   // at the latest: the sentinel
+  }
+  return i;
+}
+
+void PipBoilerplate::unit_begin (const uint8_t* u, size_t len, bool sps_seen) {
+  // DetectStartCodePrefix: everything up to and including the first 00 00 01
+  size_t off = 0;
+  for (size_t k = 0; k + 3 <= len; k++) if (u[k] == 0 && u[k + 1] == 0 && u[k + 2] == 1) { off = k + 3; break; }
+  if (off == 0) return;                                // no start code: the reference rejects the buffer
+  def_.append_bytes (u, off);
+  std::vector<uint8_t> nal;
+  const size_t n = unescape_nal (u + off, len - off, nal);
+  def_.escape_on();
+  if (n == 0) return;
+  size_t zeros = 0;
+  while (zeros < n && nal[n - 1 - zeros] == 0) zeros++;
+  if (zeros < n && !(nal[0] & 0x80)) {                 // forbidden_zero_bit set: ParseNalHeader returns before the append
+    def_.append_byte (nal[0]);
+    const int type = nal[0] & 31;
+    const bool param = type == NAL_SPS || type == NAL_PPS || type == 15 /* subset SPS */;
+    if ((type == NAL_SEI || param) && (type == NAL_SEI || type == NAL_SPS || sps_seen) && n - zeros > 1)
+      def_.append_bytes (nal.data() + 1, n - zeros - 1);
+  }
+  for (size_t i = 0; i < zeros; i++) def_.append_byte (0);
+}
+
+void PipBoilerplate::unit_end (const UnitSliceInfo& s) {
+  if (s.slice_decoded) {
+    for (size_t i = 0; i < s.header_bits; i++) def_.emit_bit ((uint32_t) (s.rbsp[i >> 3] >> (7 - (i & 7))) & 1u);
+    if (!s.cabac) def_.emit_bit (1);
+  }
+  def_.stop_escape();
+}
+
+} // namespace lh264host

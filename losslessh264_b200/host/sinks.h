@@ -36,6 +36,11 @@ class GpuSink : public PictureSink {
   ~GpuSink() override;
   int configure (int mb_w, int mb_h, int n_slots) override;
   int submit (const lh264_picture_desc& pic, const DecodedPictureInfo& info) override;
+  // recompression model of the picture on the GPU (lh264_model_submit); the model stream is opened on first use
+  int submit_model (const lh264_model_picture& pic, const DecodedPictureInfo& info) override;
+  // ends the model's tag streams; bytes of one `.pip.<tag>` side stream (empty = the tag has no file)
+  int model_finish();
+  int model_tag_bytes (int tag, std::vector<uint8_t>& out);
   // cropped I420 of a decoded picture into host memory (synchronous)
   int read (const DecodedPictureInfo& info, uint8_t* y, int stride_y, uint8_t* u, uint8_t* v, int stride_c);
   lh264_ctx* ctx() const { return ctx_; }
@@ -45,6 +50,7 @@ class GpuSink : public PictureSink {
   lh264_ctx* ctx_;
   bool own_ctx_;
   int stream_ = -1;
+  int model_ = -1, model_mbs_ = 0;
 };
 
 } // namespace lh264host

@@ -8,6 +8,7 @@ GpuSink::GpuSink (lh264_ctx* shared, int device) : ctx_ (shared), own_ctx_ (fals
   if (!ctx_) { if (lh264_ctx_create (&ctx_, device, nullptr) == LH264_OK) own_ctx_ = true; else ctx_ = nullptr; }
 }
 GpuSink::~GpuSink() {
+  if (ctx_ && model_ >= 0) lh264_model_close (ctx_, model_);
   if (ctx_ && stream_ >= 0) lh264_stream_close (ctx_, stream_);
   if (ctx_ && own_ctx_) lh264_ctx_destroy (ctx_);
 }
@@ -25,6 +26,29 @@ int GpuSink::submit (const lh264_picture_desc& pic, const DecodedPictureInfo&) {
   int rc = lh264_recon_submit (ctx_, &d, 1);
   if (rc) return rc;
   return lh264_sync (ctx_);          // the decoder reuses its record buffers for the next picture
+}
+int GpuSink::submit_model (const lh264_model_picture& pic, const DecodedPictureInfo&) {
+  if (!ctx_) return LH264_E_NO_DEVICE;
+  const int mbs = pic.mb_w * pic.mb_h;
+  if (model_ >= 0 && mbs > model_mbs_) return LH264_E_UNSUPPORTED;   // a larger picture mid-stream: reopen is not modelled
+  if (model_ < 0) {
+    model_ = lh264_model_open (ctx_, mbs, /*with_8x8*/1);
+    if (model_ < 0) return model_;
+    model_mbs_ = mbs;
+  }
+  lh264_model_picture p = pic;
+  p.model_stream = model_;
+  return lh264_model_submit (ctx_, &p, 1);
+}
+int GpuSink::model_finish() { return ctx_ && model_ >= 0 ? lh264_model_finish (ctx_, model_) : LH264_OK; }
+int GpuSink::model_tag_bytes (int tag, std::vector<uint8_t>& out) {
+  out.clear();
+  if (!ctx_ || model_ < 0) return LH264_OK;
+  const long long n = lh264_model_read (ctx_, model_, tag, nullptr, 0, 0);
+  if (n < 0) return (int)n;
+  out.resize ((size_t)n);
+  if (n > 0) { const long long m = lh264_model_read (ctx_, model_, tag, out.data(), 0, (size_t)n); if (m < 0) return (int)m; }
+  return LH264_OK;
 }
 int GpuSink::read (const DecodedPictureInfo& info, uint8_t* y, int sy, uint8_t* u, uint8_t* v, int sc) {
   if (!ctx_ || stream_ < 0) return LH264_E_NO_DEVICE;

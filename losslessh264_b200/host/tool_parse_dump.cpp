@@ -9,11 +9,12 @@
 #include "decoder.h"
 #include "sinks.h"
 #include "cavlc.h"
+#include "pip_container.h"
 
 using namespace lh264host;
 
 int main (int argc, char** argv) {
-  if (argc < 3) { fprintf (stderr, "usage: %s in.264 out.lhfb [repeat] [out.lhmd]\n", argv[0]); return 2; }
+  if (argc < 3) { fprintf (stderr, "usage: %s in.264 out.lhfb [repeat] [out.lhmd] [out.pip (default stream only)]\n", argv[0]); return 2; }
   if (!cavlc_selfcheck()) { fprintf (stderr, "CAVLC tables failed the Kraft/prefix self-check\n"); return 3; }
   FILE* f = fopen (argv[1], "rb");
   if (!f) { perror (argv[1]); return 1; }
@@ -30,7 +31,26 @@ int main (int argc, char** argv) {
     Decoder dec (&sink);
     if (argc > 4 && it == 0) { sink.set_model_path (argv[4]); dec.enable_model (true); }
     const auto t0 = std::chrono::steady_clock::now();
-    dec.decode (buf.data(), buf.size());
+    if (argc > 5 && it == 0) {                          // the unit loop of h264dec, writing the `.pip` default stream
+      PipBoilerplate pip;
+      const size_t size = buf.size();
+      static const uint8_t kStart[4] = {0, 0, 0, 1};
+      buf.insert (buf.end(), kStart, kStart + 4);       // sentinel, h264dec.cpp:238
+      for (size_t pos = 0; pos < size;) {
+        const size_t len = PipBoilerplate::next_unit (buf.data(), pos, size);
+        if (len < 4) { pip.raw (buf.data() + pos, len); pos += len; continue; }
+        pip.unit_begin (buf.data() + pos, len, dec.sps_seen());
+        dec.decode (buf.data() + pos, len);
+        UnitSliceInfo u;
+        u.slice_decoded = dec.last_slice().decoded; u.cabac = dec.last_slice().cabac; u.rbsp = dec.last_slice().rbsp; u.header_bits = dec.last_slice().header_bits;
+        pip.unit_end (u);
+        pos += len;
+      }
+      buf.resize (size);
+      const std::vector<uint8_t>& d = pip.finish();
+      FILE* fo = fopen (argv[5], "wb");
+      if (fo) { fwrite (d.data(), 1, d.size(), fo); fclose (fo); }
+    } else dec.decode (buf.data(), buf.size());
     dec.flush();
     const double dt = std::chrono::duration<double> (std::chrono::steady_clock::now() - t0).count();
     if (dt < best) best = dt;

@@ -20,3 +20,29 @@ def test_decoded_yuv_sha1_matches_reference(name, tmp_path):
     assert r.returncode == 0, r.stderr
     sha = hashlib.sha1(open(out, "rb").read()).hexdigest()
     assert sha == SHA1[name]["sha1"], f"{name}: SHA1 {sha} != reference {SHA1[name]['sha1']}\n{r.stderr[-400:]}"
+
+
+# ---- compress mode of the CLI: `h264dec in.264 out.pip out.yuv` writes the same file set as the reference ------------------
+import hashlib
+import json
+
+PIP_GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "pip_tag_sha1.json")))
+PIP_SET = ["tibby.264", "tibby8x8cavlc.264", "BA1_FT_C.264", "black.264", "BAMQ2_JVC_C.264", "MR2_TANDBERG_E.264", "SVA_FM1_E.264", "CVPCMNL1_SVA_C.264",
+           "syn_qcif_4slices_8f.264", "syn720p_8f.264"]
+
+
+@pytest.mark.parametrize("name", PIP_SET)
+def test_cli_compress_writes_the_reference_pip_file_set(name, tmp_path):
+    pip = os.path.join(str(tmp_path), "o.pip")
+    yuv = os.path.join(str(tmp_path), "o.yuv")
+    r = subprocess.run([os.path.join(LIB_DIR, "h264dec_lh264"), os.path.join(STREAM_DIR, name), pip, yuv], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-500:]
+    g = PIP_GOLD[name]
+    b = open(pip, "rb").read()
+    assert hashlib.sha1(b).hexdigest() == g["default"]["sha1"], f"{name}: default stream differs"
+    files = sorted(f[6:] for f in os.listdir(str(tmp_path)) if f.startswith("o.pip."))
+    assert files == sorted(g["tags"]), f"{name}: tag file set {files} != {sorted(g['tags'])}"
+    for t in files:
+        tb = open(pip + "." + t, "rb").read()
+        assert hashlib.sha1(tb).hexdigest() == g["tags"][t]["sha1"], f"{name}: .pip.{t} differs from the reference"
+    assert hashlib.sha1(open(yuv, "rb").read()).hexdigest() == SHA1[name]["sha1"], f"{name}: YUV differs"
