@@ -174,7 +174,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--streams", type=int, default=1024, help="independent 1080p streams per GPU (BASELINE config 4: 1024 streams)")
-    ap.add_argument("--e2e-threads", type=int, default=4, help="host threads (one context each) on the host-buffer path")
+    ap.add_argument("--e2e-threads", type=int, default=8, help="host threads (one context each) on the host-buffer path")
+    ap.add_argument("--e2e-streams", type=int, default=512, help="streams on the host-buffer path (all threads together)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
@@ -297,7 +298,7 @@ def main():
     # T host threads, each with its own context (CUDA streams) and Se streams, as a host application with one worker per
     # group of streams would drive the library; copies of one group overlap the kernels of another.
     T = args.e2e_threads
-    Se = max(1, min(S, 256) // T)                      # pictures per submit per thread
+    Se = max(1, min(S, args.e2e_streams) // T)         # pictures per submit per thread
     keep = []
     hp, hm = [], []
     for p, q in zip(pics, mpics):

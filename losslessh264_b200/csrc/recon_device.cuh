@@ -130,6 +130,65 @@ __device__ __forceinline__ int mc_luma_sample (const uint8_t* w, int ws, int fra
 #undef AVG2
 }
 
+// Four horizontally adjacent luma samples at once.  p points at the sample co-located with the first output pixel in a
+// window whose rows start 4-byte aligned (row stride ws, a multiple of 4).  Each of the 6 window rows is fetched as three
+// 32-bit words and funnel-shifted into place (18 word loads instead of up to 144 byte loads for a centre position); the
+// vertical 6-tap sums of the 9 columns are shared by the four outputs.  Same arithmetic as mc_luma_sample.
+__device__ __forceinline__ void mc_luma_quad (const uint8_t* p, int ws, int frac, int out[4]) {
+  const int fx = frac >> 2, fy = frac & 3;
+  const unsigned addr = (unsigned)__cvta_generic_to_shared (p - 2);
+  const unsigned sh = (addr & 3u) * 8u;
+  const uint32_t* q = reinterpret_cast<const uint32_t*> (p - 2 - (addr & 3u));
+  const int wsw = ws >> 2;
+  const bool needC = (fy == 2 && fx != 0) || (fx == 2 && fy != 0);
+  const bool needV = fy != 0 && fx != 2;
+  const bool needH = fx != 0 && fy != 2;
+  int vr[9];
+#pragma unroll
+  for (int j = 0; j < 9; j++) vr[j] = 0;
+  uint32_t r0a = 0, r0b = 0, r0c = 0, r1a = 0, r1b = 0, r1c = 0;      // rows y and y+1, bytes -2..1 | 2..5 | 6
+#pragma unroll
+  for (int r = 0; r < 6; r++) {
+    if (r != 2 && r != 3 && !needC && !needV) continue;
+    const uint32_t* rq = q + (r - 2) * wsw;
+    const uint32_t w0 = rq[0], w1 = rq[1], w2 = rq[2];
+    const uint32_t a = __funnelshift_r (w0, w1, sh), b = __funnelshift_r (w1, w2, sh), c = (w2 >> sh) & 0xffu;
+    if (r == 2) { r0a = a; r0b = b; r0c = c; }
+    if (r == 3) { r1a = a; r1b = b; r1c = c; }
+    if (needC || needV) {
+      const int kc = (r == 0 || r == 5) ? 1 : ((r == 1 || r == 4) ? -5 : 20);
+#pragma unroll
+      for (int j = 0; j < 4; j++) { vr[j] += kc * (int) ((a >> (8 * j)) & 0xffu); vr[4 + j] += kc * (int) ((b >> (8 * j)) & 0xffu); }
+      vr[8] += kc * (int)c;
+    }
+  }
+  // bytes of the row the horizontal filter runs on (row y, or y+1 when fy == 3)
+  const uint32_t ha = fy == 3 ? r1a : r0a, hb = fy == 3 ? r1b : r0b, hc = fy == 3 ? r1c : r0c;
+  int hrow[9];
+#pragma unroll
+  for (int j = 0; j < 4; j++) { hrow[j] = (int) ((ha >> (8 * j)) & 0xffu); hrow[4 + j] = (int) ((hb >> (8 * j)) & 0xffu); }
+  hrow[8] = (int)hc;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int G = (int) (((i < 2 ? r0a >> (8 * (i + 2)) : r0b >> (8 * (i - 2)))) & 0xffu);
+    int H = 0, V = 0, C = 0;
+    if (needH) H = clip255 ((tap6 (hrow[i], hrow[i + 1], hrow[i + 2], hrow[i + 3], hrow[i + 4], hrow[i + 5]) + 16) >> 5);
+    if (needV) V = clip255 (((fx == 3 ? vr[i + 3] : vr[i + 2]) + 16) >> 5);
+    if (needC) C = clip255 ((tap6 (vr[i], vr[i + 1], vr[i + 2], vr[i + 3], vr[i + 4], vr[i + 5]) + 512) >> 10);
+    int o;
+    if (fx == 0) {
+      const int Gb = (int) (((i < 2 ? r1a >> (8 * (i + 2)) : r1b >> (8 * (i - 2)))) & 0xffu);
+      o = fy == 0 ? G : (fy == 2 ? V : (((fy == 1 ? G : Gb) + V + 1) >> 1));
+    } else if (fx == 2) {
+      o = fy == 0 ? H : (fy == 2 ? C : ((H + C + 1) >> 1));
+    } else {
+      const int Gn = fx == 1 ? G : (int) (((i + 1 < 2 ? r0a >> (8 * (i + 3)) : r0b >> (8 * (i - 1)))) & 0xffu);   // fx == 3: the pixel to the right
+      o = fy == 0 ? ((Gn + H + 1) >> 1) : (fy == 2 ? ((V + C + 1) >> 1) : ((H + V + 1) >> 1));
+    }
+    out[i] = o;
+  }
+}
+
 // partition geometry of the 4x4 block (bx,by) (block units) inside an inter MB — GetInterPred's
 // partition walk, codec/decoder/core/src/rec_mb.cpp:344-545
 __device__ __forceinline__ void part_geom (int mb_type, int sub, int bx, int by, int& ox, int& oy, int& bw, int& bh) {

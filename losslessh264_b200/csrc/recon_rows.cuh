@@ -37,6 +37,11 @@ __device__ __forceinline__ void st_release (int* p, int v) {
   asm volatile ("st.release.gpu.global.s32 [%0], %1;" :: "l" (p), "r" (v) : "memory");
 }
 
+// k / d for k < 2048, d <= 32 without an integer division: (k * ceil(65536 / d)) >> 16
+__constant__ uint16_t c_rcp[33] = { 0, 65535, 32768, 21846, 16384, 13108, 10923, 9363, 8192, 7282, 6554, 5958, 5462, 5042, 4682, 4370, 4096,
+  3856, 3641, 3450, 3277, 3121, 2979, 2850, 2731, 2622, 2521, 2428, 2341, 2260, 2185, 2115, 2048 };
+__device__ __forceinline__ int fdiv (int k, int d) { return d == 1 ? k : (int) (((unsigned)k * c_rcp[d]) >> 16); }
+
 #define LW_STRIDE 28
 #define CW_STRIDE 16
 struct __align__ (16) WarpCtx {
@@ -46,8 +51,8 @@ struct __align__ (16) WarpCtx {
   uint8_t pred[384];            // prediction (same layout)
   uint8_t tile[17 * TS];        // intra luma tile with its top row / left column
   uint8_t cedge[2][2][12];      // chroma neighbours
-  uint8_t lwin[21 * LW_STRIDE + 4]; // luma reference window of one partition (word-aligned rows)
-  uint8_t cwin[2][9 * CW_STRIDE];   // chroma reference windows of one partition
+  __align__ (4) uint8_t lwin[21 * LW_STRIDE + 4]; // luma reference window of one partition (word-aligned rows)
+  __align__ (4) uint8_t cwin[2][9 * CW_STRIDE];   // chroma reference windows of one partition (word-aligned rows)
 };
 
 // residual_block() works on an MbShared; WarpCtx starts with the same four members.
@@ -121,23 +126,36 @@ __device__ void w_inter_partition (WarpCtx& s, const PicDev& pic, const lh264_sl
     const int ax = ix & ~3, nw = ((ix + ww + 3) >> 2) - (ax >> 2);
     woff = ix - ax;
     for (int k = lane; k < nw * wh; k += 32) {
-      const int wy = k / nw, wx = k - wy * nw;
+      const int wy = fdiv (k, nw), wx = k - wy * nw;
       const uint32_t v = __ldg (reinterpret_cast<const uint32_t*> (ref + (size_t)clip3i (iy + wy, 0, H - 1) * W + ax) + wx);
       *reinterpret_cast<uint32_t*> (s.lwin + wy * LW_STRIDE + 4 * wx) = v;
     }
   } else {                                         // picture border: clamp every sample (= ExpandPicture, expand_pic.cpp:37-115)
     woff = 0;
     for (int k = lane; k < ww * wh; k += 32) {
-      const int wy = k / ww, wx = k - wy * ww;
+      const int wy = fdiv (k, ww), wx = k - wy * ww;
       s.lwin[wy * LW_STRIDE + wx] = __ldg (ref + (size_t)clip3i (iy + wy, 0, H - 1) * W + clip3i (ix + wx, 0, W - 1));
     }
   }
   // ---- chroma windows: (bw/2 + 1) x (bh/2 + 1) per plane ----
   const int cx = fx >> 3, cy = fy >> 3, cw = (bw >> 1) + 1, chh = (bh >> 1) + 1;
-  for (int k = lane; k < 2 * cw * chh; k += 32) {
-    const int p = k >= cw * chh, kk = p ? k - cw * chh : k;
-    const int wy = kk / cw, wx = kk - wy * cw;
-    s.cwin[p][wy * CW_STRIDE + wx] = __ldg (plane_ptr (pic, slot, 1 + p) + (size_t)clip3i (cy + wy, 0, CH - 1) * CW + clip3i (cx + wx, 0, CW - 1));
+  int coff;                                        // byte offset of chroma sample (cx, cy) inside a cwin row
+  if (cx >= 0 && cx + cw <= CW) {                  // fast path: aligned 32-bit words (at most 3 per row), no horizontal clamp
+    const int ax = cx & ~3, nwc = ((cx + cw + 3) >> 2) - (ax >> 2), per = nwc * chh;
+    coff = cx - ax;
+    for (int k = lane; k < 2 * per; k += 32) {
+      const int p = k >= per, kk = p ? k - per : k;
+      const int wy = fdiv (kk, nwc), wx = kk - wy * nwc;
+      const uint32_t v = __ldg (reinterpret_cast<const uint32_t*> (plane_ptr (pic, slot, 1 + p) + (size_t)clip3i (cy + wy, 0, CH - 1) * CW + ax) + wx);
+      *reinterpret_cast<uint32_t*> (s.cwin[p] + wy * CW_STRIDE + 4 * wx) = v;
+    }
+  } else {
+    coff = 0;
+    for (int k = lane; k < 2 * cw * chh; k += 32) {
+      const int p = k >= cw * chh, kk = p ? k - cw * chh : k;
+      const int wy = fdiv (kk, cw), wx = kk - wy * cw;
+      s.cwin[p][wy * CW_STRIDE + wx] = __ldg (plane_ptr (pic, slot, 1 + p) + (size_t)clip3i (cy + wy, 0, CH - 1) * CW + clip3i (cx + wx, 0, CW - 1));
+    }
   }
   __syncwarp();
   // ---- luma samples: quads of 4 ----
@@ -146,15 +164,15 @@ __device__ void w_inter_partition (WarpCtx& s, const PicDev& pic, const lh264_sl
   if (wp) { lw = __ldg (&sl->luma_weight[refidx]); lo = __ldg (&sl->luma_offset[refidx]); ld = __ldg (&sl->luma_log2_denom); }
   const int qpr = bw >> 2;                          // quads per row
   for (int k = lane; k < qpr * bh; k += 32) {
-    const int y = k / qpr, x4 = (k - y * qpr) << 2;
+    const int y = fdiv (k, qpr), x4 = (k - y * qpr) << 2;
     const uint8_t* w0 = s.lwin + (2 + y) * LW_STRIDE + woff + 2 + x4;
-    uint8_t* out = s.pred + (oy + y) * 16 + ox + x4;
+    int v[4];
+    mc_luma_quad (w0, LW_STRIDE, frac, v);
+    if (wp) {
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-      int v = mc_luma_sample (w0 + i, LW_STRIDE, frac);
-      if (wp) v = wp_sample (v, lw, lo, ld);
-      out[i] = (uint8_t)v;
+      for (int i = 0; i < 4; i++) v[i] = wp_sample (v[i], lw, lo, ld);
     }
+    *reinterpret_cast<uint32_t*> (s.pred + (oy + y) * 16 + ox + x4) = (uint32_t)v[0] | ((uint32_t)v[1] << 8) | ((uint32_t)v[2] << 16) | ((uint32_t)v[3] << 24);
   }
   // ---- chroma samples: pairs of 2, both planes ----
   const int dx = fx & 7, dy = fy & 7;
@@ -162,10 +180,10 @@ __device__ void w_inter_partition (WarpCtx& s, const PicDev& pic, const lh264_sl
   const int ppr = bw >> 2, cbh = bh >> 1;           // pairs per chroma row, chroma rows
   for (int k = lane; k < 2 * ppr * cbh; k += 32) {
     const int p = k >= ppr * cbh, kk = p ? k - ppr * cbh : k;
-    const int y = kk / ppr, x2 = (kk - y * ppr) << 1;
+    const int y = fdiv (kk, ppr), x2 = (kk - y * ppr) << 1;
     int cwt = 0, co = 0, cd = 0;
     if (wp) { cwt = __ldg (&sl->chroma_weight[refidx][p]); co = __ldg (&sl->chroma_offset[refidx][p]); cd = __ldg (&sl->chroma_log2_denom); }
-    const uint8_t* c0 = s.cwin[p] + y * CW_STRIDE + x2;
+    const uint8_t* c0 = s.cwin[p] + y * CW_STRIDE + coff + x2;
 #pragma unroll
     for (int i = 0; i < 2; i++) {
       int o = (A * c0[i] + B * c0[i + 1] + C * c0[CW_STRIDE + i] + D * c0[CW_STRIDE + i + 1] + 32) >> 6;
@@ -351,10 +369,14 @@ __global__ void __launch_bounds__ (ROWS_WARPS * 32, 2) k_recon_rows (const PicDe
     int* my = progress + (size_t)pi * max_rows + mby;
     const int* above = my - 1;
     int seen = 0;                                   // progress of the row above known so far
+    const lh264_mb_rec* row = pic.mbs + mby * pic.mb_w;
+    uint32_t recw = __ldg (reinterpret_cast<const uint32_t*> (row) + lane);      // the record of the next MB is always in flight
 #pragma unroll 1
     for (int mbx = 0; mbx < pic.mb_w; mbx++) {
-      const lh264_mb_rec* m = pic.mbs + mby * pic.mb_w + mbx;
-      w_load_mb (s, m, lane);
+      __syncwarp();
+      reinterpret_cast<uint32_t*> (&s.mb)[lane] = recw;
+      __syncwarp();
+      if (mbx + 1 < pic.mb_w) recw = __ldg (reinterpret_cast<const uint32_t*> (row + mbx + 1) + lane);
       const int mb_type = s.mb.mb_type;
       if (LH264_MB_IS_INTER (mb_type)) w_inter_mb (s, pic, mbx, mby, lane);
       else if (LH264_MB_IS_INTRA (mb_type)) {
@@ -369,7 +391,7 @@ __global__ void __launch_bounds__ (ROWS_WARPS * 32, 2) k_recon_rows (const PicDe
       }
       __syncwarp();
       // publish: every MB for the last rows' consumers would be wasteful; intra consumers below need x+2
-      if (lane == 0 && ((mbx & 1) || mbx == pic.mb_w - 1)) { __threadfence(); st_release (my, mbx + 1); }
+      if (lane == 0 && ((mbx & 3) == 3 || mbx == pic.mb_w - 1)) { __threadfence(); st_release (my, mbx + 1); }
     }
   }
 }
@@ -486,7 +508,7 @@ __global__ void __launch_bounds__ (ROWS_WARPS * 32, 4) k_deblock_rows (const Pic
       }
       w_deblock_mb (pic, mbx, mby, lane);
       __syncwarp();
-      if (lane == 0 && ((mbx & 1) || mbx == pic.mb_w - 1)) { __threadfence(); st_release (my, mbx + 1); }
+      if (lane == 0 && ((mbx & 3) == 3 || mbx == pic.mb_w - 1)) { __threadfence(); st_release (my, mbx + 1); }
     }
   }
 }
