@@ -62,6 +62,22 @@ __device__ __forceinline__ void w_load_mb (WarpCtx& s, const lh264_mb_rec* m, in
   reinterpret_cast<uint32_t*> (&s.mb)[lane] = __ldg (reinterpret_cast<const uint32_t*> (m) + lane);
   __syncwarp();
 }
+// the same in two halves, so that the global loads are in flight while the warp does something else
+__device__ __forceinline__ void w_issue_levels (const WarpCtx& s, const int16_t* coefs, int lane, uint32_t v[6]) {
+  const uint32_t mask = s.mb.coded_mask;
+  const uint32_t* src = reinterpret_cast<const uint32_t*> (coefs) + (size_t)s.mb.coef_off * 8;
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    const int w = lane + 32 * i, blk = w >> 3;
+    v[i] = 0;
+    if ((mask >> blk) & 1) v[i] = __ldg (src + __popc (mask & ((1u << blk) - 1)) * 8 + (w & 7));
+  }
+}
+__device__ __forceinline__ void w_store_levels (WarpCtx& s, int lane, const uint32_t v[6]) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) reinterpret_cast<uint32_t*> (s.lev)[lane + 32 * i] = v[i];
+  __syncwarp();
+}
 __device__ __forceinline__ void w_load_levels (WarpCtx& s, const int16_t* coefs, int lane) {
   const uint32_t mask = s.mb.coded_mask;
   const uint32_t* src = reinterpret_cast<const uint32_t*> (coefs) + (size_t)s.mb.coef_off * 8;
@@ -121,36 +137,48 @@ __device__ void w_inter_partition (WarpCtx& s, const PicDev& pic, const lh264_sl
   // ---- luma window: (bw + 5) x (bh + 5) samples starting at (ix, iy), rows clamped ----
   const int ix = (fx >> 2) - 2, iy = (fy >> 2) - 2, ww = bw + 5, wh = bh + 5;
   const uint8_t* ref = plane_ptr (pic, slot, 0);
-  int woff;                                        // byte offset of sample (ix, iy) inside lwin
-  if (ix >= 0 && ix + ww <= W) {                   // fast path: aligned 32-bit words, no horizontal clamp
-    const int ax = ix & ~3, nw = ((ix + ww + 3) >> 2) - (ax >> 2);
-    woff = ix - ax;
-    for (int k = lane; k < nw * wh; k += 32) {
-      const int wy = fdiv (k, nw), wx = k - wy * nw;
-      const uint32_t v = __ldg (reinterpret_cast<const uint32_t*> (ref + (size_t)clip3i (iy + wy, 0, H - 1) * W + ax) + wx);
-      *reinterpret_cast<uint32_t*> (s.lwin + wy * LW_STRIDE + 4 * wx) = v;
+  const int cx = fx >> 3, cy = fy >> 3, cw = (bw >> 1) + 1, chh = (bh >> 1) + 1;
+  int woff, coff;                                  // byte offsets of sample (ix, iy) / (cx, cy) inside a window row
+  const bool lfast = ix >= 0 && ix + ww <= W, cfast = cx >= 0 && cx + cw <= CW;
+  if (lfast && cfast) {
+    // fast path: both windows as aligned 32-bit words, every global load issued before the first shared store so that
+    // the warp pays one memory latency per partition instead of one per window
+    const int ax = ix & ~3, nw = ((ix + ww + 3) >> 2) - (ax >> 2), nl = nw * wh;          // <= 6 x 21 words
+    const int acx = cx & ~3, nwc = ((cx + cw + 3) >> 2) - (acx >> 2), per = nwc * chh;    // <= 3 x 9 words per plane
+    woff = ix - ax; coff = cx - acx;
+    uint32_t lv[4], cv[2];
+    int lo_[4], co_[2];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int k = lane + 32 * i;
+      lo_[i] = -1; lv[i] = 0;
+      if (k < nl) {
+        const int wy = fdiv (k, nw), wx = k - wy * nw;
+        lv[i] = __ldg (reinterpret_cast<const uint32_t*> (ref + (size_t)clip3i (iy + wy, 0, H - 1) * W + ax) + wx);
+        lo_[i] = wy * LW_STRIDE + 4 * wx;
+      }
     }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const int k = lane + 32 * i;
+      co_[i] = -1; cv[i] = 0;
+      if (k < 2 * per) {
+        const int p = k >= per, kk = p ? k - per : k;
+        const int wy = fdiv (kk, nwc), wx = kk - wy * nwc;
+        cv[i] = __ldg (reinterpret_cast<const uint32_t*> (plane_ptr (pic, slot, 1 + p) + (size_t)clip3i (cy + wy, 0, CH - 1) * CW + acx) + wx);
+        co_[i] = p * (9 * CW_STRIDE) + wy * CW_STRIDE + 4 * wx;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 4; i++) if (lo_[i] >= 0) *reinterpret_cast<uint32_t*> (s.lwin + lo_[i]) = lv[i];
+#pragma unroll
+    for (int i = 0; i < 2; i++) if (co_[i] >= 0) *reinterpret_cast<uint32_t*> (&s.cwin[0][0] + co_[i]) = cv[i];
   } else {                                         // picture border: clamp every sample (= ExpandPicture, expand_pic.cpp:37-115)
-    woff = 0;
+    woff = 0; coff = 0;
     for (int k = lane; k < ww * wh; k += 32) {
       const int wy = fdiv (k, ww), wx = k - wy * ww;
       s.lwin[wy * LW_STRIDE + wx] = __ldg (ref + (size_t)clip3i (iy + wy, 0, H - 1) * W + clip3i (ix + wx, 0, W - 1));
     }
-  }
-  // ---- chroma windows: (bw/2 + 1) x (bh/2 + 1) per plane ----
-  const int cx = fx >> 3, cy = fy >> 3, cw = (bw >> 1) + 1, chh = (bh >> 1) + 1;
-  int coff;                                        // byte offset of chroma sample (cx, cy) inside a cwin row
-  if (cx >= 0 && cx + cw <= CW) {                  // fast path: aligned 32-bit words (at most 3 per row), no horizontal clamp
-    const int ax = cx & ~3, nwc = ((cx + cw + 3) >> 2) - (ax >> 2), per = nwc * chh;
-    coff = cx - ax;
-    for (int k = lane; k < 2 * per; k += 32) {
-      const int p = k >= per, kk = p ? k - per : k;
-      const int wy = fdiv (kk, nwc), wx = kk - wy * nwc;
-      const uint32_t v = __ldg (reinterpret_cast<const uint32_t*> (plane_ptr (pic, slot, 1 + p) + (size_t)clip3i (cy + wy, 0, CH - 1) * CW + ax) + wx);
-      *reinterpret_cast<uint32_t*> (s.cwin[p] + wy * CW_STRIDE + 4 * wx) = v;
-    }
-  } else {
-    coff = 0;
     for (int k = lane; k < 2 * cw * chh; k += 32) {
       const int p = k >= cw * chh, kk = p ? k - cw * chh : k;
       const int wy = fdiv (kk, cw), wx = kk - wy * cw;
@@ -199,13 +227,18 @@ __device__ void w_inter_mb (WarpCtx& s, const PicDev& pic, int mbx, int mby, int
   const lh264_slice_rec* sl = pic.slices + s.mb.slice_idx;
   const int t = s.mb.mb_type;
   const bool has_res = s.mb.cbp != 0;
-  if (has_res) {
-    w_load_levels (s, pic.coefs, lane);
+  uint32_t lv[6];
+  if (has_res) w_issue_levels (s, pic.coefs, lane, lv);          // in flight during the first partition
+  bool res_done = !has_res;
+  auto residual = [&] () {
+    if (res_done) return;
+    res_done = true;
+    w_store_levels (s, lane, lv);
     if (lane < 24) residual_block (reinterpret_cast<MbShared&> (s), lane);
-  }
-  if (t == LH264_MB_P16x16 || t == LH264_MB_PSKIP) w_inter_partition (s, pic, sl, mbx, mby, lane, 0, 0, 16, 16, 0, 0);
-  else if (t == LH264_MB_P16x8) { w_inter_partition (s, pic, sl, mbx, mby, lane, 0, 0, 16, 8, 0, 0); w_inter_partition (s, pic, sl, mbx, mby, lane, 0, 8, 16, 8, 8, 2); }
-  else if (t == LH264_MB_P8x16) { w_inter_partition (s, pic, sl, mbx, mby, lane, 0, 0, 8, 16, 0, 0); w_inter_partition (s, pic, sl, mbx, mby, lane, 8, 0, 8, 16, 2, 1); }
+  };
+  if (t == LH264_MB_P16x16 || t == LH264_MB_PSKIP) { w_inter_partition (s, pic, sl, mbx, mby, lane, 0, 0, 16, 16, 0, 0); residual(); }
+  else if (t == LH264_MB_P16x8) { w_inter_partition (s, pic, sl, mbx, mby, lane, 0, 0, 16, 8, 0, 0); residual(); w_inter_partition (s, pic, sl, mbx, mby, lane, 0, 8, 16, 8, 8, 2); }
+  else if (t == LH264_MB_P8x16) { w_inter_partition (s, pic, sl, mbx, mby, lane, 0, 0, 8, 16, 0, 0); residual(); w_inter_partition (s, pic, sl, mbx, mby, lane, 8, 0, 8, 16, 2, 1); }
   else {
 #pragma unroll 1
     for (int q = 0; q < 4; q++) {
@@ -217,6 +250,7 @@ __device__ void w_inter_mb (WarpCtx& s, const PicDev& pic, int mbx, int mby, int
         w_inter_partition (s, pic, sl, mbx, mby, lane, qx, qy, 4, 4, r0, q); w_inter_partition (s, pic, sl, mbx, mby, lane, qx + 4, qy, 4, 4, r0 + 1, q);
         w_inter_partition (s, pic, sl, mbx, mby, lane, qx, qy + 4, 4, 4, r0 + 4, q); w_inter_partition (s, pic, sl, mbx, mby, lane, qx + 4, qy + 4, 4, 4, r0 + 5, q);
       }
+      residual();
     }
   }
   __syncwarp();
