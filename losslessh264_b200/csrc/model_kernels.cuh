@@ -808,9 +808,16 @@ __global__ void __launch_bounds__ (64) k_model_code (const MPicDev* pics, int n_
     // The loop body is the bare vpx_write dependency chain, predicated instead of branched: with one warp per scheduler
     // every taken branch costs more than the arithmetic it skips.  Only the byte-output path (once per 8 shifted bits)
     // branches.
-    while (true) {
+    // one coder step; the ring entry for the NEXT step is fetched before this step's arithmetic so that the shared-memory
+    // latency is off the dependency chain (vnext is only trusted when that entry had been published at fetch time)
+    uint32_t vnext = 0;
+    bool vnext_ok = false;
+    auto step = [&] () -> bool {
       const bool has = consumed != avail;
-      const uint32_t v = myring[consumed & (CODE_RING - 1)];
+      uint32_t v = vnext;
+      if (has && !vnext_ok) v = myring[consumed & (CODE_RING - 1)];
+      vnext_ok = has && (consumed + 1u != avail);
+      vnext = myring[(consumed + 1u) & (CODE_RING - 1)];
       const uint32_t prob = v >> 1, bit = v & 1u;
       const uint32_t split = 1u + (((c.range - 1u) * prob) >> 8);
       uint32_t range = bit ? c.range - split : split;
@@ -841,11 +848,17 @@ __global__ void __launch_bounds__ (64) k_model_code (const MPicDev* pics, int n_
       }
       low <<= shift;
       if (has) { c.range = range; c.lowvalue = low; c.count = count; consumed++; }
+      return has;
+    };
+    while (true) {
+      const bool h0 = step();
+      const bool h1 = step();
       sh.cons[lane] = consumed;
-      if (!has) avail = sh.prod[lane];
-      if (!__any_sync (0xffffffffu, has)) {
+      if (!h1) { avail = sh.prod[lane]; vnext_ok = false; }
+      if (!__any_sync (0xffffffffu, h0 || h1)) {
         const int dn = sh.done;
         avail = sh.prod[lane];
+        vnext_ok = false;
         if (dn && __all_sync (0xffffffffu, avail == consumed)) break;
       }
     }
