@@ -288,8 +288,13 @@ def main():
              S * n_rec_seq * 3584, S * (dec_seq * 24 + pip_bytes_seq)]
     ach = [share[i] / (fam[i] / 1000.0) / 1e9 if fam[i] > 0 else 0.0 for i in range(4)]
     ach_all = sum(share) / (sum(fam) / 1000.0) / 1e9
+    # DRAM traffic of one launch (dram__bytes_read.sum + dram__bytes_write.sum, `ncu --set full`, captures summarised in profiles/):
+    # measured per P picture at S = 256 and scaled to this run's pictures per launch
+    traffic_per_picture = {"k_recon_rows": 8.35e6, "k_deblock_rows": None, "k_model_frame+count+scan+emit": None, "k_model_code": 3.05e6}
+    tpp = traffic_per_picture[fam_names[dom]]
     roofline = {"bound": "hbm", "kernel": fam_names[dom], "achieved": round(ach[dom], 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                "frac": round(ach[dom] / peak, 4), "traffic": None,
+                "frac": round(ach[dom] / peak, 4), "traffic": int(tpp * S) if tpp else None,
+                "traffic_note": "bytes per launch = ncu dram read+write per P picture (profiles/r1_summary.md) x pictures per launch" if tpp else None,
                 "whole_step": {"achieved": round(ach_all, 1), "frac": round(ach_all / peak, 4)},
                 "families": {n: {"ms_per_16_steps": round(t, 3), "achieved": round(a, 1), "frac": round(a / peak, 4)} for n, t, a in zip(fam_names, fam, ach)},
                 "model_decisions_per_s": round(S * dec_seq / (fam[3] / 1000.0)) if fam[3] > 0 else None}
