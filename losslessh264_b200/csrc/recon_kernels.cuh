@@ -36,6 +36,29 @@ struct MbShared {
 // DC transforms WelsLumaDcDequantIdct / WelsChromaDcIdct (decode_slice.cpp:271-311,:375-396).
 __device__ void residual_block (MbShared& s, int k) {
   const bool i16 = s.mb.mb_type == LH264_MB_I16x16;
+  // A block none of whose levels is present has a zero residual (the reference skips IdctResAddPred for it, gated by
+  // pNzc || coef[0], decode_slice.cpp:237-243 / rec_mb.cpp:206,567): write the zeros and skip dequant + transform.  Most inter
+  // MBs carry one or two coded blocks out of 24.
+  {
+    const uint32_t mask = s.mb.mb_type == LH264_MB_IPCM ? 0xffffffu : s.mb.coded_mask;
+    bool zero;
+    if (k < 16) zero = i16 ? (mask & 0xffffu) == 0 : ((s.mb.flags & LH264_MBF_TRANSFORM8x8) ? ((mask >> (k & ~3)) & 15u) == 0 : ((mask >> k) & 1u) == 0);
+    else zero = ((mask >> (16 + 4 * ((k - 16) >> 2))) & 15u) == 0;
+    if (zero) {
+      if (k < 16) {
+        if ((s.mb.flags & LH264_MBF_TRANSFORM8x8) && (k & 3)) return;       // the quadrant's first lane clears all of it
+        const int n = (s.mb.flags & LH264_MBF_TRANSFORM8x8) ? 8 : 4;
+        int16_t* res = s.res + blk_y (k) * 16 + blk_x (k);
+        for (int y = 0; y < n; y++) for (int x = 0; x < n; x += 4) *reinterpret_cast<uint2*> (res + 16 * y + x) = make_uint2 (0u, 0u);
+      } else {
+        const int p = (k - 16) >> 2, b = (k - 16) & 3;
+        int16_t* res = s.res + 256 + 64 * p + (b >> 1) * 32 + (b & 1) * 4;
+#pragma unroll
+        for (int y = 0; y < 4; y++) *reinterpret_cast<uint2*> (res + 8 * y) = make_uint2 (0u, 0u);
+      }
+      return;
+    }
+  }
   if (k < 16) {
     const int qp = s.mb.qp_y;
     if (s.mb.flags & LH264_MBF_TRANSFORM8x8) {
