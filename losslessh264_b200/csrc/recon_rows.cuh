@@ -431,9 +431,10 @@ __global__ void __launch_bounds__ (ROWS_WARPS * 32, 2) k_recon_rows (const PicDe
 }
 
 // ---- deblocking, one warp per MB row ---------------------------------------------------------------------------
-__device__ void w_deblock_mb (const PicDev& pic, int mbx, int mby, int lane) {
-  const int mb_w = pic.mb_w, mbi = mby * mb_w + mbx;
-  const lh264_mb_rec* m = pic.mbs + mbi;
+// m / ml / mt: the records of this MB, its left and its top neighbour, staged in shared memory by the caller (the record
+// of the next MB and of its top neighbour are loaded while this MB is filtered)
+__device__ void w_deblock_mb (const PicDev& pic, int mbx, int mby, int lane, const lh264_mb_rec* m, const lh264_mb_rec* ml, const lh264_mb_rec* mt) {
+  const int mb_w = pic.mb_w;
   const int mb_type = m->mb_type;
   if (mb_type == LH264_MB_NONE) return;
   const lh264_slice_rec* sl = pic.slices + m->slice_idx;
@@ -441,7 +442,7 @@ __device__ void w_deblock_mb (const PicDev& pic, int mbx, int mby, int lane) {
   if (idc == 1) return;
   const int aoff = sl->alpha_c0_offset, boff = sl->beta_offset;
   bool left = mbx > 0, top = mby > 0;               // DeblockingAvailableNoInterlayer, deblocking.cpp:354-369
-  if (idc == 2) { left = left && m[-1].slice_idx == m->slice_idx; top = top && m[-mb_w].slice_idx == m->slice_idx; }
+  if (idc == 2) { left = left && ml->slice_idx == m->slice_idx; top = top && mt->slice_idx == m->slice_idx; }
   const bool t8 = m->flags & LH264_MBF_TRANSFORM8x8;
   const bool intra = LH264_MB_IS_INTRA (mb_type);
   // boundary strength: lane = dir*16 + edge*4 + segment
@@ -451,7 +452,7 @@ __device__ void w_deblock_mb (const PicDev& pic, int mbx, int mby, int lane) {
   else if (e == 0) {
     const bool avail = dir ? top : left;
     if (avail) {
-      const lh264_mb_rec* nb = dir ? m - mb_w : m - 1;
+      const lh264_mb_rec* nb = dir ? mt : ml;
       if (LH264_MB_IS_INTRA (nb->mb_type)) bs = 4;
       else {                                  // DeblockingBsMarginalMBAvcbase
         const uint32_t nzc = m->nz_mask, nzn = nb->nz_mask;
@@ -485,7 +486,7 @@ __device__ void w_deblock_mb (const PicDev& pic, int mbx, int mby, int lane) {
   if (lane >= 16) { C = plane_ptr (pic, pic.cur_slot, 1 + cplane) + (size_t)mby * 8 * CW + mbx * 8; qpc_cur = m->qp_c[cplane]; }
 #pragma unroll 1
   for (int d = 0; d < 2; d++) {
-    const lh264_mb_rec* nb = d ? m - mb_w : m - 1;
+    const lh264_mb_rec* nb = d ? mt : ml;
 #pragma unroll 1
     for (int ed = 0; ed < 4; ed++) {
       const int seg = lane < 16 ? (lane >> 2) : ((lane & 7) >> 1);
@@ -517,7 +518,9 @@ __device__ void w_deblock_mb (const PicDev& pic, int mbx, int mby, int lane) {
 }
 
 __global__ void __launch_bounds__ (ROWS_WARPS * 32, 4) k_deblock_rows (const PicDev* __restrict__ pics, int n_pics, int max_rows, RowSync* sync) {
+  __shared__ __align__ (16) lh264_mb_rec recs[ROWS_WARPS][4];       // [0],[1]: this MB / its left neighbour (alternating), [2]: top
   const int lane = threadIdx.x & 31;
+  lh264_mb_rec* my_recs = recs[threadIdx.x >> 5];
   int* progress = reinterpret_cast<int*> (sync + 1) + (size_t)n_pics * max_rows;
   const unsigned total = (unsigned)n_pics * max_rows;
   for (;;) {
@@ -531,8 +534,18 @@ __global__ void __launch_bounds__ (ROWS_WARPS * 32, 4) k_deblock_rows (const Pic
     int* my = progress + (size_t)pi * max_rows + mby;
     const int* above = my - 1;
     int seen = 0;
+    const uint32_t* row = reinterpret_cast<const uint32_t*> (pic.mbs + (size_t)mby * pic.mb_w);
+    const uint32_t* row_top = mby > 0 ? reinterpret_cast<const uint32_t*> (pic.mbs + (size_t) (mby - 1) * pic.mb_w) : row;
+    uint32_t w_cur = __ldg (row + lane), w_top = __ldg (row_top + lane);
 #pragma unroll 1
     for (int mbx = 0; mbx < pic.mb_w; mbx++) {
+      lh264_mb_rec* mc = &my_recs[mbx & 1];
+      const lh264_mb_rec* ml = &my_recs[(mbx & 1) ^ 1];
+      __syncwarp();
+      reinterpret_cast<uint32_t*> (mc)[lane] = w_cur;
+      reinterpret_cast<uint32_t*> (&my_recs[2])[lane] = w_top;
+      __syncwarp();
+      if (mbx + 1 < pic.mb_w) { w_cur = __ldg (row + (mbx + 1) * 32 + lane); w_top = __ldg (row_top + (mbx + 1) * 32 + lane); }
       if (mby > 0) {
         const int need = min (mbx + 2, pic.mb_w);
         if (seen < need) {
@@ -540,7 +553,7 @@ __global__ void __launch_bounds__ (ROWS_WARPS * 32, 4) k_deblock_rows (const Pic
           seen = __shfl_sync (0xffffffffu, seen, 0);
         }
       }
-      w_deblock_mb (pic, mbx, mby, lane);
+      w_deblock_mb (pic, mbx, mby, lane, mc, ml, &my_recs[2]);
       __syncwarp();
       if (lane == 0 && ((mbx & 3) == 3 || mbx == pic.mb_w - 1)) { __threadfence(); st_release (my, mbx + 1); }
     }
