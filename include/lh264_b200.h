@@ -218,10 +218,13 @@ int  lh264_sync(lh264_ctx* ctx);
 int  lh264_join(lh264_ctx* ctx);
 /* Gathers the cropped I420 pictures of n (stream, slot) pairs on the device and brings them to
  * the host with ONE copy: for each picture Y (width x height) then U, V ((w+1)/2 x (h+1)/2),
- * tightly packed, pictures back to back.  dst should be pinned (lh264_host_alloc).           */
+ * tightly packed, pictures back to back.  dst should be pinned (lh264_host_alloc).  With sync == 0 the call returns once
+ * the gather kernel has run; the copy to the host proceeds on a copy stream of its own, concurrently with later submits,
+ * and is complete after lh264_output_wait() (or lh264_sync()).                                */
 int  lh264_pictures_read_packed(lh264_ctx* ctx, const int* streams, const int* slots, int n,
                                 int crop_x, int crop_y, int width, int height,
                                 uint8_t* dst, size_t dst_bytes, int sync);
+int  lh264_output_wait(lh264_ctx* ctx);
 /* Pinned host memory for hand-off records and output pictures (async copies need it).       */
 void* lh264_host_alloc(size_t bytes);
 void  lh264_host_free(void* p);

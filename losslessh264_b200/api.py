@@ -23,7 +23,7 @@ EXPORTS = [
     "lh264_stream_open", "lh264_stream_close", "lh264_recon_submit", "lh264_batch_upload",
     "lh264_batch_recon", "lh264_batch_free", "lh264_kernel_launches", "lh264_kernel_ms",
     "lh264_picture_read", "lh264_picture_write", "lh264_picture_device_ptrs", "lh264_sync", "lh264_join",
-    "lh264_pictures_read_packed", "lh264_host_alloc", "lh264_host_free",
+    "lh264_pictures_read_packed", "lh264_output_wait", "lh264_host_alloc", "lh264_host_free",
     "lh264_k_idct4x4_add", "lh264_k_idct8x8_add", "lh264_k_mc_luma", "lh264_k_mc_chroma",
     "lh264_k_expand_plane",
     "lh264_model_open", "lh264_model_close", "lh264_model_submit", "lh264_model_finish", "lh264_model_read",
@@ -88,6 +88,7 @@ def load_library():
     lib.lh264_kernel_ms.argtypes = [C.c_void_p, C.c_int]
     lib.lh264_sync.argtypes = [C.c_void_p]
     lib.lh264_join.argtypes = [C.c_void_p]
+    lib.lh264_output_wait.argtypes = [C.c_void_p]
     lib.lh264_picture_read.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     lib.lh264_picture_write.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
     lib.lh264_pictures_read_packed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_int]
@@ -219,11 +220,15 @@ class Context:
         base = yuv.ctypes.data
         _check(self.lib, self.lib.lh264_picture_write(self.h, stream, slot, base, w, base + w * h, base + w * h + w * h // 4, w // 2))
 
-    def read_packed(self, streams, slots, crop, dst: "PinnedArray"):
+    def read_packed(self, streams, slots, crop, dst: "PinnedArray", sync=True):
         s = np.ascontiguousarray(streams, np.int32)
         sl = np.ascontiguousarray(slots, np.int32)
         x, y, w, h = crop
-        _check(self.lib, self.lib.lh264_pictures_read_packed(self.h, s.ctypes.data, sl.ctypes.data, len(s), x, y, w, h, dst.ptr, dst.nbytes, 1))
+        _check(self.lib, self.lib.lh264_pictures_read_packed(self.h, s.ctypes.data, sl.ctypes.data, len(s), x, y, w, h, dst.ptr, dst.nbytes, 1 if sync else 0))
+
+    def output_wait(self):
+        """Waits for the device-to-host copies started by read_packed(sync=False)."""
+        _check(self.lib, self.lib.lh264_output_wait(self.h))
 
     def kernel_launches(self):
         return int(self.lib.lh264_kernel_launches(self.h))

@@ -104,6 +104,11 @@ struct lh264_ctx {
   // the same pool (it is the same data) reads the device copy instead of crossing PCIe twice
   std::vector<std::pair<const int16_t*, const int16_t*> > staged_coefs;
   cudaEvent_t recon_staged = nullptr;        // the H2D copies of that batch are done
+  // decoded pictures leave on a copy stream of their own, so that this batch's D2H overlaps the next batch's H2D (PCIe is
+  // full duplex) and kernels
+  cudaStream_t d2h_stream = nullptr;
+  cudaEvent_t packed = nullptr, d2h_done = nullptr;
+  bool d2h_pending = false;
 };
 static void model_destroy (lh264_ctx* c);
 static float model_ms (lh264_ctx* c, int which, bool reset);
@@ -135,6 +140,9 @@ int lh264_ctx_create (lh264_ctx** out, int device, void* cuda_stream) {
   else { CK (cudaStreamCreateWithFlags (&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
   CK (cudaEventCreateWithFlags (&c->staged, cudaEventDisableTiming));
   CK (cudaEventCreateWithFlags (&c->recon_staged, cudaEventDisableTiming));
+  CK (cudaStreamCreateWithFlags (&c->d2h_stream, cudaStreamNonBlocking));
+  CK (cudaEventCreateWithFlags (&c->packed, cudaEventDisableTiming));
+  CK (cudaEventCreateWithFlags (&c->d2h_done, cudaEventDisableTiming));
   for (int i = 0; i < 2; i++) CK (cudaEventCreateWithFlags (&c->batch_free[i], cudaEventDisableTiming));
   for (int i = 0; i < 4; i++) CK (cudaEventCreate (&c->ev[i]));
   *out = c;
@@ -153,6 +161,9 @@ void lh264_ctx_destroy (lh264_ctx* c) {
   c->scratch_a.release(); c->scratch_b.release(); c->scratch_c.release();
   if (c->staged) cudaEventDestroy (c->staged);
   if (c->recon_staged) cudaEventDestroy (c->recon_staged);
+  if (c->d2h_stream) { cudaStreamSynchronize (c->d2h_stream); cudaStreamDestroy (c->d2h_stream); }
+  if (c->packed) cudaEventDestroy (c->packed);
+  if (c->d2h_done) cudaEventDestroy (c->d2h_done);
   for (int i = 0; i < 4; i++) if (c->ev[i]) cudaEventDestroy (c->ev[i]);
   if (c->own_stream) cudaStreamDestroy (c->stream);
   delete c;
@@ -187,6 +198,23 @@ static int check_pic (lh264_ctx* c, const lh264_picture_desc& p) {
   return LH264_OK;
 }
 
+// Host -> device copies of a batch are laid out back to back on the device; when the caller's buffers are back to back on the
+// host too (a staging arena), consecutive copies are merged into one cudaMemcpyAsync.
+struct CopyMerger {
+  cudaStream_t st; char* d = nullptr; const char* h = nullptr; size_t n = 0; cudaError_t err = cudaSuccess; int issued = 0;
+  explicit CopyMerger (cudaStream_t s) : st (s) {}
+  void add (void* dev, const void* host, size_t bytes) {
+    if (!bytes) return;
+    if (n && d + n == (char*)dev && h + n == (const char*)host) { n += bytes; return; }
+    flush();
+    d = (char*)dev; h = (const char*)host; n = bytes;
+  }
+  void flush() {
+    if (n && err == cudaSuccess) { err = cudaMemcpyAsync (d, h, n, cudaMemcpyHostToDevice, st); issued++; }
+    n = 0;
+  }
+};
+
 // Copies the records of a batch into HBM (async) and fills the device picture table.
 static int stage_batch (lh264_ctx* c, BatchDev& b, PinBuf<PicDev>& h_pics, const lh264_picture_desc* pics, int n) {
   size_t tot_mbs = 0, tot_blk = 0, tot_sl = 0;
@@ -202,19 +230,22 @@ static int stage_batch (lh264_ctx* c, BatchDev& b, PinBuf<PicDev>& h_pics, const
   CK (h_pics.reserve (n));
   size_t o_mb = 0, o_blk = 0, o_sl = 0;
   b.n_pics = n; b.max_rows = 0;
+  CopyMerger cm_mb (c->stream), cm_co (c->stream), cm_sl (c->stream);
   for (int i = 0; i < n; i++) {
     const lh264_picture_desc& p = pics[i];
     const StreamRec& s = c->streams[p.stream];
     const size_t nmb = (size_t)s.mb_w * s.mb_h;
-    CK (cudaMemcpyAsync (b.mbs.p + o_mb, p.mbs, nmb * sizeof (lh264_mb_rec), cudaMemcpyHostToDevice, c->stream));
-    if (p.n_coef_blocks) CK (cudaMemcpyAsync (b.coefs.p + o_blk * 16, p.coefs, (size_t)p.n_coef_blocks * 32, cudaMemcpyHostToDevice, c->stream));
-    CK (cudaMemcpyAsync (b.slices.p + o_sl, p.slices, (size_t)p.n_slices * sizeof (lh264_slice_rec), cudaMemcpyHostToDevice, c->stream));
+    cm_mb.add (b.mbs.p + o_mb, p.mbs, nmb * sizeof (lh264_mb_rec));
+    cm_co.add (b.coefs.p + o_blk * 16, p.coefs, (size_t)p.n_coef_blocks * 32);
+    cm_sl.add (b.slices.p + o_sl, p.slices, (size_t)p.n_slices * sizeof (lh264_slice_rec));
     PicDev& d = h_pics.p[i];
     d.mbs = b.mbs.p + o_mb; d.coefs = b.coefs.p + o_blk * 16; d.slices = b.slices.p + o_sl;
     d.base = s.base; d.slot_stride = s.slot_stride; d.cur_slot = p.cur_slot; d.n_slots = s.n_slots; d.mb_w = s.mb_w; d.mb_h = s.mb_h;
     b.max_rows = std::max (b.max_rows, s.mb_h);
     o_mb += nmb; o_blk += p.n_coef_blocks; o_sl += p.n_slices;
   }
+  cm_mb.flush(); cm_co.flush(); cm_sl.flush();
+  CK (cm_mb.err); CK (cm_co.err); CK (cm_sl.err);
   CK (cudaMemcpyAsync (b.pics.p, h_pics.p, n * sizeof (PicDev), cudaMemcpyHostToDevice, c->stream));
   CK (cudaEventRecord (c->staged, c->stream));
   c->staged_pending = true;
@@ -377,12 +408,25 @@ int lh264_pictures_read_packed (lh264_ctx* c, const int* streams, const int* slo
     j[1] = PackDev{ u + (size_t) (crop_y >> 1) * (W >> 1) + (crop_x >> 1), W >> 1, cw, ch, per * i + (size_t)width * height };
     j[2] = PackDev{ v + (size_t) (crop_y >> 1) * (W >> 1) + (crop_x >> 1), W >> 1, cw, ch, per * i + (size_t)width * height + (size_t)cw * ch };
   }
+  if (c->d2h_pending) { CK (cudaStreamWaitEvent (c->stream, c->d2h_done, 0)); c->d2h_pending = false; }   // pack_out is free again
   CK (cudaMemcpyAsync (c->pack_jobs.p, c->h_pack_jobs.p, 3 * n * sizeof (PackDev), cudaMemcpyHostToDevice, c->stream));
   k_pack<<<dim3 (std::min (height, 64), 3 * n), 128, 0, c->stream>>> (c->pack_jobs.p, c->pack_out.p);
   c->launches++;
-  CK (cudaMemcpyAsync (dst, c->pack_out.p, per * n, cudaMemcpyDeviceToHost, c->stream));
-  CK (cudaStreamSynchronize (c->stream));     // h_pack_jobs is reused by the next call
-  (void)sync;
+  CK (cudaEventRecord (c->packed, c->stream));
+  CK (cudaStreamWaitEvent (c->d2h_stream, c->packed, 0));
+  CK (cudaMemcpyAsync (dst, c->pack_out.p, per * n, cudaMemcpyDeviceToHost, c->d2h_stream));
+  CK (cudaEventRecord (c->d2h_done, c->d2h_stream));
+  c->d2h_pending = true;
+  // h_pack_jobs is reused by the next call: its H2D is on the context stream, wait for that part only
+  CK (cudaEventSynchronize (c->packed));
+  if (sync) CK (cudaStreamSynchronize (c->d2h_stream));
+  return LH264_OK;
+}
+
+int lh264_output_wait (lh264_ctx* c) {
+  if (!c) return fail (LH264_E_INVALID, "null ctx");
+  CK (cudaSetDevice (c->device));
+  CK (cudaStreamSynchronize (c->d2h_stream));
   return LH264_OK;
 }
 
@@ -398,6 +442,7 @@ int lh264_sync (lh264_ctx* c) {
   CK (cudaSetDevice (c->device));
   CK (model_sync (c));
   CK (cudaStreamSynchronize (c->stream));
+  CK (cudaStreamSynchronize (c->d2h_stream));
   c->staged_pending = false;
   return LH264_OK;
 }

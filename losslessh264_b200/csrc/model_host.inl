@@ -193,15 +193,17 @@ static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_
   b.stream_of.assign (n, 0);
   bool any_shared = false;
   size_t o_rec = 0, o_sl = 0, o_blk = 0;
+  CopyMerger cm_rec (m->stream), cm_sl (m->stream), cm_co (m->stream);
   for (int i = 0; i < n; i++) {
     const lh264_model_picture& p = pics[i];
     const MStreamHost& s = m->streams[p.model_stream];
-    CK (cudaMemcpyAsync (b.recs.p + o_rec, p.recs, (size_t)p.n_recs * sizeof (lh264_model_mb), cudaMemcpyHostToDevice, m->stream));
-    CK (cudaMemcpyAsync (b.slices.p + o_sl, p.slices, (size_t)p.n_slices * sizeof (lh264_model_slice), cudaMemcpyHostToDevice, m->stream));
+    cm_rec.add (b.recs.p + o_rec, p.recs, (size_t)p.n_recs * sizeof (lh264_model_mb));
+    cm_sl.add (b.slices.p + o_sl, p.slices, (size_t)p.n_slices * sizeof (lh264_model_slice));
     const int16_t* dev_coefs = nullptr;
-    if (share_coefs && p.n_coef_blocks)
+    if (share_coefs && p.n_coef_blocks && (size_t)i < c->staged_coefs.size() && c->staged_coefs[i].first == p.coefs) { dev_coefs = c->staged_coefs[i].second; any_shared = true; }
+    else if (share_coefs && p.n_coef_blocks)
       for (const auto& sc : c->staged_coefs) if (sc.first == p.coefs) { dev_coefs = sc.second; any_shared = true; break; }
-    if (p.n_coef_blocks && !dev_coefs) CK (cudaMemcpyAsync (b.coefs.p + o_blk * 16, p.coefs, (size_t)p.n_coef_blocks * 32, cudaMemcpyHostToDevice, m->stream));
+    if (p.n_coef_blocks && !dev_coefs) cm_co.add (b.coefs.p + o_blk * 16, p.coefs, (size_t)p.n_coef_blocks * 32);
     MPicDev& d = b.h_pics.p[i];
     d.recs = b.recs.p + o_rec; d.slices = b.slices.p + o_sl; d.coefs = dev_coefs ? dev_coefs : b.coefs.p + o_blk * 16;
     d.st = s.d_state; d.rec_cnt = b.rec_cnt.p + o_rec; d.rec_off = b.rec_off.p + o_rec;
@@ -209,6 +211,8 @@ static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_
     b.stream_of[i] = p.model_stream;
     o_rec += p.n_recs; o_sl += p.n_slices; o_blk += p.n_coef_blocks;
   }
+  cm_rec.flush(); cm_sl.flush(); cm_co.flush();
+  CK (cm_rec.err); CK (cm_sl.err); CK (cm_co.err);
   CK (cudaMemcpyAsync (b.pics.p, b.h_pics.p, n * sizeof (MPicDev), cudaMemcpyHostToDevice, m->stream));
   b.shares_recon_batch = any_shared ? c->batch_cur : -1;
   if (any_shared) CK (cudaStreamWaitEvent (m->stream, c->recon_staged, 0));      // the shared pools are in HBM
