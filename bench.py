@@ -323,14 +323,15 @@ def main():
             c = Context(local)
             st = [c.open_stream(mb_w, mb_h, n_slots_needed(pics)) for _ in range(Se)]
             ms_ = [c.model_open(mb_w * mb_h) for _ in range(Se)]
-            out_pin = PinnedArray(Se * 1920 * 1080 * 3 // 2)
+            outs = [PinnedArray(Se * 1920 * 1080 * 3 // 2) for _ in range(2)]
 
             def steps(n):
                 for t in range(n):
                     i = t % n_frames
                     c.recon([hp[i]] * Se, st, sync=False)
                     c.model_submit([hm[i]] * Se, ms_, sync=False)
-                    c.read_packed(st, [hp[i].cur_slot] * Se, (0, 0, 1920, 1080), out_pin)
+                    # the D2H of this step's pictures runs on the library's copy stream while the next step's records go up
+                    c.read_packed(st, [hp[i].cur_slot] * Se, (0, 0, 1920, 1080), outs[t & 1], sync=False)
                 c.sync()
 
             steps(n_frames)                            # warm-up: one pass over the sequence
