@@ -22,11 +22,13 @@ struct MBatch {                    // one batch of model pictures in HBM
   DevBuf<MPicDev> pics; PinBuf<MPicDev> h_pics;
   DevBuf<uint32_t> rec_cnt; DevBuf<uint32_t> rec_off; DevBuf<uint32_t> pic_total; DevBuf<unsigned long long> dec_base;
   PinBuf<uint32_t> h_total; PinBuf<unsigned long long> h_base;
+  DevBuf<BatchCtl> ctl; PinBuf<BatchCtl> h_ctl;
+  bool pending = false;            // launched, totals not yet read back (model_settle)
   std::vector<int> stream_of;
   int n = 0, total_recs = 0;
   int shares_recon_batch = -1;     // index of the recon staging batch whose coefficient pools this batch reads
   void release() { recs.release(); slices.release(); coefs.release(); pics.release(); h_pics.release(); rec_cnt.release(); rec_off.release();
-                   pic_total.release(); dec_base.release(); h_total.release(); h_base.release(); }
+                   pic_total.release(); dec_base.release(); h_total.release(); h_base.release(); ctl.release(); h_ctl.release(); }
 };
 
 struct ModelCtx {
@@ -38,6 +40,7 @@ struct ModelCtx {
   unsigned int* d_next = nullptr;
   unsigned int n_pages = 0, reserved_pages = 0;
   MBatch batch;                    // staging of lh264_model_submit
+  MBatch* pending = nullptr;       // the batch whose kernels were launched last and whose totals the host has not read yet
   DevBuf<uint32_t> dec;            // decision list of the batch being coded
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float ms_gen = 0, ms_code = 0;
@@ -119,6 +122,8 @@ int model_grow_arena (lh264_ctx* c, ModelCtx* m, unsigned int need_pages) {
 
 extern "C" {
 
+static int model_settle (lh264_ctx* c, ModelCtx* m);
+
 int lh264_model_open (lh264_ctx* c, int max_mbs, int with_8x8) {
   if (!c || max_mbs <= 0 || max_mbs > (1 << 20)) return fail (LH264_E_INVALID, "bad model stream geometry");
   CK (cudaSetDevice (c->device));
@@ -160,7 +165,7 @@ int lh264_model_close (lh264_ctx* c, int ms) {
   int rc = model_stream_ok (c, ms, &m);
   if (rc) return rc;
   CK (cudaSetDevice (c->device));
-  CK (cudaStreamSynchronize (m->stream));
+  { int rs = model_settle (c, m); if (rs) return rs; }
   // the stream's output pages stay in the arena until the context is destroyed (bump allocator)
   model_free_stream (m->streams[ms]);
   return LH264_OK;
@@ -187,9 +192,9 @@ static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_
   }
   CK (b.recs.reserve (tot_rec)); CK (b.slices.reserve (tot_sl)); CK (b.coefs.reserve (tot_blk * 16 + 16));
   CK (b.pics.reserve (n)); CK (b.rec_cnt.reserve (tot_rec)); CK (b.rec_off.reserve (tot_rec));
-  CK (b.pic_total.reserve (n)); CK (b.dec_base.reserve (n));
-  CK (cudaStreamSynchronize (m->stream));          // pinned staging of the previous batch is free again
-  CK (b.h_pics.reserve (n)); CK (b.h_total.reserve (n + 1)); CK (b.h_base.reserve (n));
+  CK (b.pic_total.reserve (n)); CK (b.dec_base.reserve (n)); CK (b.ctl.reserve (1));
+  { int rs = model_settle (c, m); if (rs) return rs; }   // the previous batch is done, its totals are read, pinned staging is free again
+  CK (b.h_pics.reserve (n)); CK (b.h_total.reserve (n + 1)); CK (b.h_base.reserve (n)); CK (b.h_ctl.reserve (1));
   b.stream_of.assign (n, 0);
   bool any_shared = false;
   size_t o_rec = 0, o_sl = 0, o_blk = 0;
@@ -220,12 +225,55 @@ static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_
   return LH264_OK;
 }
 
-// The five launches of one batch.  The host waits once in the middle for the decision totals (they size the decision
-// list and bound the output pages the coder may take).
+// Launches of the second half of a batch (plan, emit, code); used again by model_settle when something was too small.
+static int model_launch_tail (lh264_ctx* c, ModelCtx* m, MBatch& b, bool timed) {
+  const int n = b.n, total_recs = b.total_recs;
+  const int mb_blocks = (total_recs + GEN_THREADS - 1) / GEN_THREADS;
+  const size_t gen_smem = (size_t)GEN_THREADS * sizeof (ThreadMb);
+  ArenaDev ar{ m->d_page_ptrs, m->d_next, m->n_pages };
+  k_model_plan<<<1, 1024, 0, m->stream>>> (n, b.pic_total.p, b.dec_base.p, b.ctl.p, (unsigned long long)m->dec.cap, ar);
+  k_model_emit<<<mb_blocks, GEN_THREADS, gen_smem, m->stream>>> (b.pics.p, n, total_recs, m->dec.p, b.dec_base.p, b.ctl.p);
+  if (timed) { CK (cudaEventRecord (m->ev[1], m->stream)); CK (cudaEventRecord (m->ev[2], m->stream)); }
+  k_model_code<<<n, 64, 0, m->stream>>> (b.pics.p, n, m->dec.p, b.dec_base.p, b.pic_total.p, ar, b.ctl.p);
+  c->launches += 3;
+  return LH264_OK;
+}
+
+// Reads back what the last launched batch reported (decision totals, capacity verdict).  If the decision list or the output
+// arena was too small the coding kernels skipped themselves: grow and run them again.  Called before anything that depends
+// on the batch being complete; in steady state the batch finished long ago and this costs one small D2H copy.
+static int model_settle (lh264_ctx* c, ModelCtx* m) {
+  MBatch* pb = m->pending;
+  if (!pb) { if (m->stream) CK (cudaStreamSynchronize (m->stream)); return LH264_OK; }
+  MBatch& b = *pb;
+  m->pending = nullptr;
+  b.pending = false;
+  for (int attempt = 0; attempt < 3; attempt++) {
+    CK (cudaMemcpyAsync (b.h_ctl.p, b.ctl.p, sizeof (BatchCtl), cudaMemcpyDeviceToHost, m->stream));
+    CK (cudaMemcpyAsync (b.h_total.p, b.pic_total.p, b.n * sizeof (uint32_t), cudaMemcpyDeviceToHost, m->stream));
+    CK (cudaStreamSynchronize (m->stream));
+    const BatchCtl ctl = *b.h_ctl.p;
+    if (!ctl.skip) {
+      for (int i = 0; i < b.n; i++) if (m->streams[b.stream_of[i]].open) m->streams[b.stream_of[i]].decisions += b.h_total.p[i];
+      return LH264_OK;
+    }
+    if (ctl.total + 32 > m->dec.cap) CK (m->dec.reserve ((size_t)ctl.total + ctl.total / 4 + 64));
+    int rc = model_grow_arena (c, m, ctl.pages_in_use + 2 * ctl.pages_needed);
+    if (rc) return rc;
+    if ((rc = model_launch_tail (c, m, b, false))) return rc;
+  }
+  return fail (LH264_E_NOMEM, "model batch does not fit after growing its buffers");
+}
+
+// The launches of one batch; nothing here waits for the device.
 static int model_run (lh264_ctx* c, ModelCtx* m, MBatch& b) {
   const int n = b.n, total_recs = b.total_recs;
   if (n == 0) return LH264_OK;
+  int rc = model_settle (c, m);                    // the previous batch (normally long finished)
+  if (rc) return rc;
   for (int i = 0; i < n; i++) if (!m->streams[b.stream_of[i]].open) return fail (LH264_E_INVALID, "batch names a closed model stream");
+  if (!m->d_page_ptrs && (rc = model_grow_arena (c, m, (unsigned int)n * CT_COUNT + 64))) return rc;
+  if (!m->dec.p) CK (m->dec.reserve ((size_t)total_recs * 96 + 1024));      // first guess; model_settle grows it when needed
   const int mb_blocks = (total_recs + GEN_THREADS - 1) / GEN_THREADS;
   const size_t gen_smem = (size_t)GEN_THREADS * sizeof (ThreadMb);
   if (c->timing) CK (cudaEventRecord (m->ev[0], m->stream));
@@ -233,30 +281,15 @@ static int model_run (lh264_ctx* c, ModelCtx* m, MBatch& b) {
   k_model_count<<<mb_blocks, GEN_THREADS, gen_smem, m->stream>>> (b.pics.p, n, total_recs);
   k_model_scan<<<n, 1024, 0, m->stream>>> (b.pics.p, n, b.pic_total.p);
   c->launches += 3;
-  CK (cudaMemcpyAsync (b.h_total.p, b.pic_total.p, n * sizeof (uint32_t), cudaMemcpyDeviceToHost, m->stream));
-  if (m->d_next) CK (cudaMemcpyAsync (b.h_total.p + n, m->d_next, sizeof (unsigned int), cudaMemcpyDeviceToHost, m->stream));
-  else b.h_total.p[n] = 0;
-  CK (cudaStreamSynchronize (m->stream));
-  unsigned long long total = 0;
-  for (int i = 0; i < n; i++) { b.h_base.p[i] = total; total += b.h_total.p[i]; m->streams[b.stream_of[i]].decisions += b.h_total.p[i]; }
-  CK (m->dec.reserve ((size_t)total + 32));
-  // pages in use + what this batch can add at most: every decision shifts out at most 7 bits, and a tag needs at most one
-  // partly filled page more than its bytes
-  m->reserved_pages = b.h_total.p[n] + (unsigned int) (total * 7 / 8 / PAGE_SIZE) + (unsigned int)n * CT_COUNT + 1;
-  int rc = model_grow_arena (c, m, m->reserved_pages);
-  if (rc) return rc;
-  CK (cudaMemcpyAsync (b.dec_base.p, b.h_base.p, n * sizeof (unsigned long long), cudaMemcpyHostToDevice, m->stream));
-  ArenaDev ar{ m->d_page_ptrs, m->d_next, m->n_pages };
-  k_model_emit<<<mb_blocks, GEN_THREADS, gen_smem, m->stream>>> (b.pics.p, n, total_recs, m->dec.p, b.dec_base.p);
-  if (c->timing) { CK (cudaEventRecord (m->ev[1], m->stream)); CK (cudaEventRecord (m->ev[2], m->stream)); }
-  k_model_code<<<n, 64, 0, m->stream>>> (b.pics.p, n, m->dec.p, b.dec_base.p, b.pic_total.p, ar);
-  c->launches += 2;
+  if ((rc = model_launch_tail (c, m, b, c->timing))) return rc;
+  b.pending = true; m->pending = &b;
   if (c->timing) {
     CK (cudaEventRecord (m->ev[3], m->stream));
     CK (cudaEventSynchronize (m->ev[3]));
     float t = 0;
     cudaEventElapsedTime (&t, m->ev[0], m->ev[1]); m->ms_gen += t;
     cudaEventElapsedTime (&t, m->ev[2], m->ev[3]); m->ms_code += t;
+    if ((rc = model_settle (c, m))) return rc;     // (a retry after growth is not part of the timed figures)
   }
   CK (cudaEventRecord (m->done, m->stream));
   if (b.shares_recon_batch >= 0) {                 // that staging batch may be overwritten once this run is over
@@ -299,12 +332,14 @@ int lh264_model_batch_run (lh264_ctx* c, lh264_model_batch* b) {
 void lh264_model_batch_free (lh264_ctx* c, lh264_model_batch* b) {
   if (!b) return;
   if (c) { cudaSetDevice (c->device); model_sync (c); }
+  if (c && c->model && static_cast<ModelCtx*> (c->model)->pending == &b->b) static_cast<ModelCtx*> (c->model)->pending = nullptr;
   b->b.release();
   delete b;
 }
 
 static int model_check_error (lh264_ctx* c, MStreamHost& s) {
   ModelCtx* m = static_cast<ModelCtx*> (c->model);
+  { int rs = model_settle (c, m); if (rs) return rs; }
   int err = 0;
   CK (cudaMemcpyAsync (&err, &s.d_state->error, sizeof (int), cudaMemcpyDeviceToHost, m->stream));
   CK (cudaStreamSynchronize (m->stream));
@@ -319,6 +354,7 @@ int lh264_model_finish (lh264_ctx* c, int ms) {
   int rc = model_stream_ok (c, ms, &m);
   if (rc) return rc;
   CK (cudaSetDevice (c->device));
+  if ((rc = model_settle (c, m))) return rc;
   unsigned int used = 0;
   if (m->d_next) { CK (cudaMemcpyAsync (&used, m->d_next, sizeof (used), cudaMemcpyDeviceToHost, m->stream)); CK (cudaStreamSynchronize (m->stream)); }
   if ((rc = model_grow_arena (c, m, used + CT_COUNT))) return rc;
@@ -364,6 +400,7 @@ long long lh264_model_read (lh264_ctx* c, int ms, int tag, uint8_t* dst, size_t 
 unsigned long long lh264_model_decisions (lh264_ctx* c, int ms) {
   ModelCtx* m;
   if (model_stream_ok (c, ms, &m)) return 0;
+  if (model_settle (c, m)) return 0;
   return m->streams[ms].decisions;
 }
 
@@ -371,6 +408,7 @@ unsigned long long lh264_model_decisions (lh264_ctx* c, int ms) {
 
 static cudaError_t model_sync (lh264_ctx* c) {
   ModelCtx* m = static_cast<ModelCtx*> (c->model);
+  if (m && m->pending) return model_settle (c, m) == LH264_OK ? cudaSuccess : cudaErrorUnknown;
   return m && m->stream ? cudaStreamSynchronize (m->stream) : cudaSuccess;
 }
 

@@ -123,6 +123,10 @@ struct MPicDev {                      // one picture of the batch
 
 struct ArenaDev { uint8_t** page_ptrs; unsigned int* next; unsigned int n_pages; };
 
+// Written by k_model_plan, read by the host when it next touches the batch.  `skip` makes k_model_emit / k_model_code return
+// without touching any state, so that the host can grow what was too small and run the two kernels again.
+struct BatchCtl { unsigned long long total; unsigned int skip; unsigned int pages_needed; unsigned int pages_in_use; unsigned int pad; };
+
 // ---- binarisation: identical decision sequences to the reference, prior = index into the table ---------
 template <bool W> struct Em {
   uint32_t* out; uint32_t n;
@@ -623,8 +627,49 @@ __global__ void __launch_bounds__ (1024) k_model_scan (const MPicDev* pics, int 
   if (tid == 0) pic_total[p] = carry_s;
 }
 
-__global__ void __launch_bounds__ (GEN_THREADS) k_model_emit (const MPicDev* pics, int n_pics, int total_recs, uint32_t* dec, const unsigned long long* dec_base) {
+// ---- k_model_plan: one block; positions of the pictures in the decision list, and the capacity checks the host used to
+// make between two launches (it no longer waits in the middle of a submit) ------------------------------------------
+__global__ void __launch_bounds__ (1024) k_model_plan (int n_pics, const uint32_t* pic_total, unsigned long long* dec_base, BatchCtl* ctl,
+                                                       unsigned long long dec_capacity, ArenaDev ar) {
+  __shared__ unsigned long long wsum[32];
+  __shared__ unsigned long long carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < n_pics; base += 1024) {
+    const int i = base + tid;
+    const unsigned long long v = i < n_pics ? pic_total[i] : 0ull;
+    unsigned long long x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync (0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      unsigned long long w = wsum[lane], z = w;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const unsigned long long y = __shfl_up_sync (0xffffffffu, z, o); if (lane >= o) z += y; }
+      wsum[lane] = z - w;
+    }
+    __syncthreads();
+    const unsigned long long excl = carry_s + wsum[warp] + x - v;
+    if (i < n_pics) dec_base[i] = excl;
+    __syncthreads();
+    if (tid == 1023) carry_s = excl + v;
+    __syncthreads();
+  }
+  if (tid == 0) {
+    const unsigned long long total = carry_s;
+    // every decision shifts out at most 7 bits, and a tag needs at most one partly filled page more than its bytes
+    const unsigned long long pages = total * 7 / 8 / PAGE_SIZE + (unsigned long long)n_pics * CT_COUNT + 1;
+    const unsigned int in_use = *ar.next;
+    ctl->total = total; ctl->pages_needed = (unsigned int)min (pages, 0xffffffffull); ctl->pages_in_use = in_use;
+    ctl->skip = (total + 32 > dec_capacity || in_use + pages > ar.n_pages) ? 1u : 0u;
+  }
+}
+
+__global__ void __launch_bounds__ (GEN_THREADS) k_model_emit (const MPicDev* pics, int n_pics, int total_recs, uint32_t* dec, const unsigned long long* dec_base, const BatchCtl* ctl) {
   extern __shared__ __align__ (16) unsigned char gen_smem[];
+  if (ctl->skip) return;
   ThreadMb* tm = reinterpret_cast<ThreadMb*> (gen_smem);
   ThreadMb& t = tm[threadIdx.x];
   int p = 0, ri = 0;
@@ -738,10 +783,10 @@ struct CodeShared {
 };
 
 __global__ void __launch_bounds__ (64) k_model_code (const MPicDev* pics, int n_pics, const uint32_t* dec, const unsigned long long* dec_base,
-                                                     const uint32_t* pic_total, ArenaDev ar) {
+                                                     const uint32_t* pic_total, ArenaDev ar, const BatchCtl* ctl) {
   __shared__ CodeShared sh;
   const int p = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  if (p >= n_pics) return;
+  if (p >= n_pics || ctl->skip) return;
   const MPicDev& pic = pics[p];
   MState* st = pic.st;
   if (st->error) return;
