@@ -216,6 +216,9 @@ int  lh264_sync(lh264_ctx* ctx);
 /* Orders the context stream after all model work submitted so far (the model runs on its own CUDA stream); for callers
  * that time or chain work with events on the stream they passed to lh264_ctx_create.                         */
 int  lh264_join(lh264_ctx* ctx);
+/* Waits until the host buffers handed to every lh264_recon_submit / lh264_model_submit so far have been copied to the device
+ * (they may then be overwritten), without waiting for the kernels.                                              */
+int  lh264_inputs_consumed(lh264_ctx* ctx);
 /* Gathers the cropped I420 pictures of n (stream, slot) pairs on the device and brings them to
  * the host with ONE copy: for each picture Y (width x height) then U, V ((w+1)/2 x (h+1)/2),
  * tightly packed, pictures back to back.  dst should be pinned (lh264_host_alloc).  With sync == 0 the call returns once

@@ -22,7 +22,7 @@ EXPORTS = [
     "lh264_abi_version", "lh264_last_error", "lh264_ctx_create", "lh264_ctx_destroy",
     "lh264_stream_open", "lh264_stream_close", "lh264_recon_submit", "lh264_batch_upload",
     "lh264_batch_recon", "lh264_batch_free", "lh264_kernel_launches", "lh264_kernel_ms",
-    "lh264_picture_read", "lh264_picture_write", "lh264_picture_device_ptrs", "lh264_sync", "lh264_join",
+    "lh264_picture_read", "lh264_picture_write", "lh264_picture_device_ptrs", "lh264_sync", "lh264_join", "lh264_inputs_consumed",
     "lh264_pictures_read_packed", "lh264_output_wait", "lh264_host_alloc", "lh264_host_free",
     "lh264_k_idct4x4_add", "lh264_k_idct8x8_add", "lh264_k_mc_luma", "lh264_k_mc_chroma",
     "lh264_k_expand_plane",
@@ -88,6 +88,7 @@ def load_library():
     lib.lh264_kernel_ms.argtypes = [C.c_void_p, C.c_int]
     lib.lh264_sync.argtypes = [C.c_void_p]
     lib.lh264_join.argtypes = [C.c_void_p]
+    lib.lh264_inputs_consumed.argtypes = [C.c_void_p]
     lib.lh264_output_wait.argtypes = [C.c_void_p]
     lib.lh264_picture_read.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int]
     lib.lh264_picture_write.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]

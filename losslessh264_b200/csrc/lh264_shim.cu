@@ -89,6 +89,7 @@ struct lh264_ctx {
   int batch_cur = 0;
   cudaEvent_t batch_free[2] = {nullptr, nullptr};   // recorded on the model stream after the model run that shared batch[k]
   bool batch_shared[2] = {false, false};
+  void* batch_sharer[2] = {nullptr, nullptr};   // the MBatch (model_host.inl) that shares batch[k]'s pools
   PinBuf<PicDev> h_pics;
   cudaEvent_t staged = nullptr;              // h_pics consumed by the H2D copy
   bool staged_pending = false;
@@ -114,6 +115,8 @@ static void model_destroy (lh264_ctx* c);
 static float model_ms (lh264_ctx* c, int which, bool reset);
 static cudaError_t model_sync (lh264_ctx* c);
 static cudaError_t model_join (lh264_ctx* c);
+static int model_settle_sharer (lh264_ctx* c, int k);
+static cudaError_t model_inputs_consumed (lh264_ctx* c);
 
 extern "C" {
 
@@ -284,7 +287,14 @@ int lh264_recon_submit (lh264_ctx* c, const lh264_picture_desc* pics, int n_pics
   c->staged_coefs.clear();
   c->batch_cur ^= 1;
   const int k = c->batch_cur;
-  if (c->batch_shared[k]) { CK (cudaStreamWaitEvent (c->stream, c->batch_free[k], 0)); c->batch_shared[k] = false; }
+  if (c->batch_shared[k]) {
+    // the model batch that reads this staging buffer's coefficient pools must have run for good (not skipped for lack of
+    // space and waiting to be run again) before the pools are overwritten
+    int rs = model_settle_sharer (c, k);
+    if (rs) return rs;
+    CK (cudaStreamWaitEvent (c->stream, c->batch_free[k], 0));
+    c->batch_shared[k] = false;
+  }
   int rc = stage_batch (c, c->batch[k], c->h_pics, pics, n_pics);
   if (rc) return rc;
   for (int i = 0; i < n_pics; i++) if (pics[i].n_coef_blocks) c->staged_coefs.push_back (std::make_pair (pics[i].coefs, c->h_pics.p[i].coefs));
@@ -427,6 +437,14 @@ int lh264_output_wait (lh264_ctx* c) {
   if (!c) return fail (LH264_E_INVALID, "null ctx");
   CK (cudaSetDevice (c->device));
   CK (cudaStreamSynchronize (c->d2h_stream));
+  return LH264_OK;
+}
+
+int lh264_inputs_consumed (lh264_ctx* c) {
+  if (!c) return fail (LH264_E_INVALID, "null ctx");
+  CK (cudaSetDevice (c->device));
+  if (c->staged_pending) { CK (cudaEventSynchronize (c->staged)); c->staged_pending = false; }
+  CK (model_inputs_consumed (c));
   return LH264_OK;
 }
 

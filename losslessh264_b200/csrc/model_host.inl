@@ -24,11 +24,15 @@ struct MBatch {                    // one batch of model pictures in HBM
   PinBuf<uint32_t> h_total; PinBuf<unsigned long long> h_base;
   DevBuf<BatchCtl> ctl; PinBuf<BatchCtl> h_ctl;
   bool pending = false;            // launched, totals not yet read back (model_settle)
+  cudaEvent_t done = nullptr;      // recorded after the batch's last kernel
+  cudaEvent_t staged = nullptr;    // recorded after the batch's host-to-device copies
   std::vector<int> stream_of;
   int n = 0, total_recs = 0;
   int shares_recon_batch = -1;     // index of the recon staging batch whose coefficient pools this batch reads
   void release() { recs.release(); slices.release(); coefs.release(); pics.release(); h_pics.release(); rec_cnt.release(); rec_off.release();
-                   pic_total.release(); dec_base.release(); h_total.release(); h_base.release(); ctl.release(); h_ctl.release(); }
+                   pic_total.release(); dec_base.release(); h_total.release(); h_base.release(); ctl.release(); h_ctl.release();
+                   if (done) { cudaEventDestroy (done); done = nullptr; }
+                   if (staged) { cudaEventDestroy (staged); staged = nullptr; } }
 };
 
 struct ModelCtx {
@@ -39,8 +43,11 @@ struct ModelCtx {
   uint8_t** d_page_ptrs = nullptr; size_t page_ptr_cap = 0;
   unsigned int* d_next = nullptr;
   unsigned int n_pages = 0, reserved_pages = 0;
-  MBatch batch;                    // staging of lh264_model_submit
-  MBatch* pending = nullptr;       // the batch whose kernels were launched last and whose totals the host has not read yet
+  MBatch batch[2];                 // staging of lh264_model_submit, alternating: batch t is staged while t-1 still runs
+  int batch_cur = 0;
+  std::vector<MBatch*> inflight;   // launched batches whose totals the host has not read yet, oldest first (at most 2)
+  unsigned int* d_poison = nullptr;  // set by a batch that skipped its coding: later batches skip entirely (model_settle)
+  cudaStream_t aux = nullptr;      // small D2H reads that must not queue behind running model kernels
   DevBuf<uint32_t> dec;            // decision list of the batch being coded
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float ms_gen = 0, ms_code = 0;
@@ -65,6 +72,9 @@ static ModelCtx* model_ctx (lh264_ctx* c) {
     if (!m) return nullptr;
     for (int i = 0; i < 4; i++) cudaEventCreate (&m->ev[i]);
     cudaStreamCreateWithFlags (&m->stream, cudaStreamNonBlocking);
+    cudaStreamCreateWithFlags (&m->aux, cudaStreamNonBlocking);
+    cudaMalloc (&m->d_poison, sizeof (unsigned int));
+    cudaMemset (m->d_poison, 0, sizeof (unsigned int));
     cudaFuncSetAttribute (k_model_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (GEN_THREADS * sizeof (ThreadMb)));
     cudaFuncSetAttribute (k_model_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (GEN_THREADS * sizeof (ThreadMb)));
     cudaEventCreateWithFlags (&m->done, cudaEventDisableTiming);
@@ -89,8 +99,10 @@ static void model_destroy (lh264_ctx* c) {
   for (uint8_t* p : m->segments) cudaFree (p);
   if (m->d_page_ptrs) cudaFree (m->d_page_ptrs);
   if (m->d_next) cudaFree (m->d_next);
-  m->batch.release();
+  m->batch[0].release(); m->batch[1].release();
   m->dec.release();
+  if (m->d_poison) cudaFree (m->d_poison);
+  if (m->aux) cudaStreamDestroy (m->aux);
   for (int i = 0; i < 4; i++) if (m->ev[i]) cudaEventDestroy (m->ev[i]);
   if (m->stream) { cudaStreamSynchronize (m->stream); cudaStreamDestroy (m->stream); }
   if (m->done) cudaEventDestroy (m->done);
@@ -123,6 +135,7 @@ int model_grow_arena (lh264_ctx* c, ModelCtx* m, unsigned int need_pages) {
 extern "C" {
 
 static int model_settle (lh264_ctx* c, ModelCtx* m);
+static int model_settle_batch (lh264_ctx* c, ModelCtx* m, MBatch* only);
 
 int lh264_model_open (lh264_ctx* c, int max_mbs, int with_8x8) {
   if (!c || max_mbs <= 0 || max_mbs > (1 << 20)) return fail (LH264_E_INVALID, "bad model stream geometry");
@@ -193,7 +206,7 @@ static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_
   CK (b.recs.reserve (tot_rec)); CK (b.slices.reserve (tot_sl)); CK (b.coefs.reserve (tot_blk * 16 + 16));
   CK (b.pics.reserve (n)); CK (b.rec_cnt.reserve (tot_rec)); CK (b.rec_off.reserve (tot_rec));
   CK (b.pic_total.reserve (n)); CK (b.dec_base.reserve (n)); CK (b.ctl.reserve (1));
-  { int rs = model_settle (c, m); if (rs) return rs; }   // the previous batch is done, its totals are read, pinned staging is free again
+  { int rs = model_settle_batch (c, m, &b); if (rs) return rs; }   // the batch that used this staging before is done and read
   CK (b.h_pics.reserve (n)); CK (b.h_total.reserve (n + 1)); CK (b.h_base.reserve (n)); CK (b.h_ctl.reserve (1));
   b.stream_of.assign (n, 0);
   bool any_shared = false;
@@ -219,70 +232,112 @@ static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_
   cm_rec.flush(); cm_sl.flush(); cm_co.flush();
   CK (cm_rec.err); CK (cm_sl.err); CK (cm_co.err);
   CK (cudaMemcpyAsync (b.pics.p, b.h_pics.p, n * sizeof (MPicDev), cudaMemcpyHostToDevice, m->stream));
+  if (!b.staged) CK (cudaEventCreateWithFlags (&b.staged, cudaEventDisableTiming));
+  CK (cudaEventRecord (b.staged, m->stream));
   b.shares_recon_batch = any_shared ? c->batch_cur : -1;
   if (any_shared) CK (cudaStreamWaitEvent (m->stream, c->recon_staged, 0));      // the shared pools are in HBM
   b.n = n; b.total_recs = (int)tot_rec;
   return LH264_OK;
 }
 
-// Launches of the second half of a batch (plan, emit, code); used again by model_settle when something was too small.
-static int model_launch_tail (lh264_ctx* c, ModelCtx* m, MBatch& b, bool timed) {
+static int model_launch (lh264_ctx* c, ModelCtx* m, MBatch& b, bool head, bool timed) {
   const int n = b.n, total_recs = b.total_recs;
   const int mb_blocks = (total_recs + GEN_THREADS - 1) / GEN_THREADS;
   const size_t gen_smem = (size_t)GEN_THREADS * sizeof (ThreadMb);
   ArenaDev ar{ m->d_page_ptrs, m->d_next, m->n_pages };
-  k_model_plan<<<1, 1024, 0, m->stream>>> (n, b.pic_total.p, b.dec_base.p, b.ctl.p, (unsigned long long)m->dec.cap, ar);
+  if (head) {
+    if (timed) CK (cudaEventRecord (m->ev[0], m->stream));
+    k_model_frame<<<n, 32, 0, m->stream>>> (b.pics.p, n, m->d_poison);
+    k_model_count<<<mb_blocks, GEN_THREADS, gen_smem, m->stream>>> (b.pics.p, n, total_recs, m->d_poison);
+    k_model_scan<<<n, 1024, 0, m->stream>>> (b.pics.p, n, b.pic_total.p, m->d_poison);
+    c->launches += 3;
+  }
+  k_model_plan<<<1, 1024, 0, m->stream>>> (n, b.pic_total.p, b.dec_base.p, b.ctl.p, (unsigned long long)m->dec.cap, ar, m->d_poison);
   k_model_emit<<<mb_blocks, GEN_THREADS, gen_smem, m->stream>>> (b.pics.p, n, total_recs, m->dec.p, b.dec_base.p, b.ctl.p);
   if (timed) { CK (cudaEventRecord (m->ev[1], m->stream)); CK (cudaEventRecord (m->ev[2], m->stream)); }
   k_model_code<<<n, 64, 0, m->stream>>> (b.pics.p, n, m->dec.p, b.dec_base.p, b.pic_total.p, ar, b.ctl.p);
   c->launches += 3;
+  if (!b.done) CK (cudaEventCreateWithFlags (&b.done, cudaEventDisableTiming));
+  CK (cudaEventRecord (b.done, m->stream));
   return LH264_OK;
 }
 
-// Reads back what the last launched batch reported (decision totals, capacity verdict).  If the decision list or the output
-// arena was too small the coding kernels skipped themselves: grow and run them again.  Called before anything that depends
-// on the batch being complete; in steady state the batch finished long ago and this costs one small D2H copy.
-static int model_settle (lh264_ctx* c, ModelCtx* m) {
-  MBatch* pb = m->pending;
-  if (!pb) { if (m->stream) CK (cudaStreamSynchronize (m->stream)); return LH264_OK; }
-  MBatch& b = *pb;
-  m->pending = nullptr;
-  b.pending = false;
-  for (int attempt = 0; attempt < 3; attempt++) {
+// blocking: runs a batch to completion, growing the decision list / output arena until it fits
+static int model_complete (lh264_ctx* c, ModelCtx* m, MBatch& b, bool head) {
+  for (int attempt = 0; attempt < 4; attempt++) {
+    int rc = model_launch (c, m, b, head, false);
+    if (rc) return rc;
     CK (cudaMemcpyAsync (b.h_ctl.p, b.ctl.p, sizeof (BatchCtl), cudaMemcpyDeviceToHost, m->stream));
     CK (cudaMemcpyAsync (b.h_total.p, b.pic_total.p, b.n * sizeof (uint32_t), cudaMemcpyDeviceToHost, m->stream));
     CK (cudaStreamSynchronize (m->stream));
     const BatchCtl ctl = *b.h_ctl.p;
-    if (!ctl.skip) {
-      for (int i = 0; i < b.n; i++) if (m->streams[b.stream_of[i]].open) m->streams[b.stream_of[i]].decisions += b.h_total.p[i];
-      return LH264_OK;
-    }
+    if (!ctl.skip) return LH264_OK;
+    head = false;                                   // frame / count / scan did run: the batch itself was the one that did not fit
+    CK (cudaMemsetAsync (m->d_poison, 0, sizeof (unsigned int), m->stream));
     if (ctl.total + 32 > m->dec.cap) CK (m->dec.reserve ((size_t)ctl.total + ctl.total / 4 + 64));
-    int rc = model_grow_arena (c, m, ctl.pages_in_use + 2 * ctl.pages_needed);
-    if (rc) return rc;
-    if ((rc = model_launch_tail (c, m, b, false))) return rc;
+    if ((rc = model_grow_arena (c, m, ctl.pages_in_use + 2 * ctl.pages_needed))) return rc;
   }
   return fail (LH264_E_NOMEM, "model batch does not fit after growing its buffers");
 }
 
-// The launches of one batch; nothing here waits for the device.
+static void model_account (ModelCtx* m, MBatch& b) {
+  for (int i = 0; i < b.n; i++) if (m->streams[b.stream_of[i]].open) m->streams[b.stream_of[i]].decisions += b.h_total.p[i];
+}
+
+// Reads back what a launched batch reported (decision totals, capacity verdict); `only` = settle up to and including that
+// batch (nullptr: all).  In steady state the batch finished long ago and this costs two small D2H copies on a side stream.
+// If a batch skipped its coding because the decision list or the output arena was too small, every later batch skipped
+// entirely (poison flag): grow, then run them again in launch order.
+static int model_settle_batch (lh264_ctx* c, ModelCtx* m, MBatch* only) {
+  if (only && !only->pending) return LH264_OK;
+  while (!m->inflight.empty()) {
+    MBatch& b = *m->inflight.front();
+    CK (cudaEventSynchronize (b.done));
+    CK (cudaMemcpyAsync (b.h_ctl.p, b.ctl.p, sizeof (BatchCtl), cudaMemcpyDeviceToHost, m->aux));
+    CK (cudaMemcpyAsync (b.h_total.p, b.pic_total.p, b.n * sizeof (uint32_t), cudaMemcpyDeviceToHost, m->aux));
+    CK (cudaStreamSynchronize (m->aux));
+    if (b.h_ctl.p->skip) {
+      CK (cudaStreamSynchronize (m->stream));       // the later batches have skipped themselves too by now
+      std::vector<MBatch*> redo = m->inflight;
+      m->inflight.clear();
+      bool head = b.h_ctl.p->skip == 2;             // 2 cannot be first in the list, but be safe
+      CK (cudaMemsetAsync (m->d_poison, 0, sizeof (unsigned int), m->stream));
+      {                                              // what the first one needs is known; later ones report when they run
+        const BatchCtl ctl = *b.h_ctl.p;
+        if (ctl.total + 32 > m->dec.cap) CK (m->dec.reserve ((size_t)ctl.total + ctl.total / 4 + 64));
+        int rc = model_grow_arena (c, m, ctl.pages_in_use + 2 * ctl.pages_needed);
+        if (rc) return rc;
+      }
+      for (MBatch* r : redo) {
+        int rc = model_complete (c, m, *r, head);
+        if (rc) return rc;
+        r->pending = false;
+        model_account (m, *r);
+        head = true;
+      }
+      return LH264_OK;
+    }
+    b.pending = false;
+    model_account (m, b);
+    m->inflight.erase (m->inflight.begin());
+    if (only == &b) return LH264_OK;
+  }
+  return LH264_OK;
+}
+static int model_settle (lh264_ctx* c, ModelCtx* m) { return model_settle_batch (c, m, nullptr); }
+
+// The launches of one batch; nothing here waits for the device unless two batches are already in flight.
 static int model_run (lh264_ctx* c, ModelCtx* m, MBatch& b) {
-  const int n = b.n, total_recs = b.total_recs;
+  const int n = b.n;
   if (n == 0) return LH264_OK;
-  int rc = model_settle (c, m);                    // the previous batch (normally long finished)
+  int rc = model_settle_batch (c, m, &b);          // a resident batch that is run again while still pending
   if (rc) return rc;
+  while (m->inflight.size() >= 2) if ((rc = model_settle_batch (c, m, m->inflight.front()))) return rc;
   for (int i = 0; i < n; i++) if (!m->streams[b.stream_of[i]].open) return fail (LH264_E_INVALID, "batch names a closed model stream");
   if (!m->d_page_ptrs && (rc = model_grow_arena (c, m, (unsigned int)n * CT_COUNT + 64))) return rc;
-  if (!m->dec.p) CK (m->dec.reserve ((size_t)total_recs * 96 + 1024));      // first guess; model_settle grows it when needed
-  const int mb_blocks = (total_recs + GEN_THREADS - 1) / GEN_THREADS;
-  const size_t gen_smem = (size_t)GEN_THREADS * sizeof (ThreadMb);
-  if (c->timing) CK (cudaEventRecord (m->ev[0], m->stream));
-  k_model_frame<<<n, 32, 0, m->stream>>> (b.pics.p, n);
-  k_model_count<<<mb_blocks, GEN_THREADS, gen_smem, m->stream>>> (b.pics.p, n, total_recs);
-  k_model_scan<<<n, 1024, 0, m->stream>>> (b.pics.p, n, b.pic_total.p);
-  c->launches += 3;
-  if ((rc = model_launch_tail (c, m, b, c->timing))) return rc;
-  b.pending = true; m->pending = &b;
+  if (!m->dec.p) CK (m->dec.reserve ((size_t)b.total_recs * 96 + 1024));    // first guess; model_settle grows it when needed
+  if ((rc = model_launch (c, m, b, true, c->timing))) return rc;
+  b.pending = true; m->inflight.push_back (&b);
   if (c->timing) {
     CK (cudaEventRecord (m->ev[3], m->stream));
     CK (cudaEventSynchronize (m->ev[3]));
@@ -295,6 +350,7 @@ static int model_run (lh264_ctx* c, ModelCtx* m, MBatch& b) {
   if (b.shares_recon_batch >= 0) {                 // that staging batch may be overwritten once this run is over
     CK (cudaEventRecord (c->batch_free[b.shares_recon_batch], m->stream));
     c->batch_shared[b.shares_recon_batch] = true;
+    c->batch_sharer[b.shares_recon_batch] = &b;
   }
   CK (cudaGetLastError());
   return LH264_OK;
@@ -306,9 +362,11 @@ int lh264_model_submit (lh264_ctx* c, const lh264_model_picture* pics, int n) {
   CK (cudaSetDevice (c->device));
   ModelCtx* m = model_ctx (c);
   if (!m) return fail (LH264_E_NOMEM, "out of host memory");
-  int rc = model_stage (c, m, m->batch, pics, n, true);
+  m->batch_cur ^= 1;
+  MBatch& b = m->batch[m->batch_cur];
+  int rc = model_stage (c, m, b, pics, n, true);
   if (rc) return rc;
-  return model_run (c, m, m->batch);
+  return model_run (c, m, b);
 }
 
 int lh264_model_batch_upload (lh264_ctx* c, const lh264_model_picture* pics, int n, lh264_model_batch** out) {
@@ -332,7 +390,6 @@ int lh264_model_batch_run (lh264_ctx* c, lh264_model_batch* b) {
 void lh264_model_batch_free (lh264_ctx* c, lh264_model_batch* b) {
   if (!b) return;
   if (c) { cudaSetDevice (c->device); model_sync (c); }
-  if (c && c->model && static_cast<ModelCtx*> (c->model)->pending == &b->b) static_cast<ModelCtx*> (c->model)->pending = nullptr;
   b->b.release();
   delete b;
 }
@@ -408,7 +465,7 @@ unsigned long long lh264_model_decisions (lh264_ctx* c, int ms) {
 
 static cudaError_t model_sync (lh264_ctx* c) {
   ModelCtx* m = static_cast<ModelCtx*> (c->model);
-  if (m && m->pending) return model_settle (c, m) == LH264_OK ? cudaSuccess : cudaErrorUnknown;
+  if (m && !m->inflight.empty()) return model_settle (c, m) == LH264_OK ? cudaSuccess : cudaErrorUnknown;
   return m && m->stream ? cudaStreamSynchronize (m->stream) : cudaSuccess;
 }
 
@@ -418,4 +475,27 @@ static cudaError_t model_join (lh264_ctx* c) {
   if (!m || !m->stream) return cudaSuccess;
   cudaError_t e = cudaEventRecord (m->done, m->stream);
   return e != cudaSuccess ? e : cudaStreamWaitEvent (c->stream, m->done, 0);
+}
+
+static int model_settle_sharer (lh264_ctx* c, int k) {
+  ModelCtx* m = static_cast<ModelCtx*> (c->model);
+  MBatch* b = static_cast<MBatch*> (c->batch_sharer[k]);
+  c->batch_sharer[k] = nullptr;
+  if (!m || !b) return LH264_OK;
+  for (MBatch* f : m->inflight) if (f == b) {
+      const int rc = model_settle_batch (c, m, b);
+      if (rc) return rc;
+      // a re-run recorded nothing on batch_free: order the context stream after the model stream as it is now
+      CK (cudaEventRecord (c->batch_free[k], m->stream));
+      return LH264_OK;
+    }
+  return LH264_OK;
+}
+
+// the caller's host buffers of every model submit so far have been copied to the device
+static cudaError_t model_inputs_consumed (lh264_ctx* c) {
+  ModelCtx* m = static_cast<ModelCtx*> (c->model);
+  if (!m) return cudaSuccess;
+  for (int k = 0; k < 2; k++) if (m->batch[k].staged) { cudaError_t e = cudaEventSynchronize (m->batch[k].staged); if (e != cudaSuccess) return e; }
+  return cudaSuccess;
 }

@@ -125,7 +125,7 @@ struct ArenaDev { uint8_t** page_ptrs; unsigned int* next; unsigned int n_pages;
 
 // Written by k_model_plan, read by the host when it next touches the batch.  `skip` makes k_model_emit / k_model_code return
 // without touching any state, so that the host can grow what was too small and run the two kernels again.
-struct BatchCtl { unsigned long long total; unsigned int skip; unsigned int pages_needed; unsigned int pages_in_use; unsigned int pad; };
+struct BatchCtl { unsigned long long total; unsigned int skip /* 1 too small, 2 behind a skipped batch */; unsigned int pages_needed; unsigned int pages_in_use; unsigned int pad; };
 
 // ---- binarisation: identical decision sequences to the reference, prior = index into the table ---------
 template <bool W> struct Em {
@@ -423,9 +423,9 @@ template <bool W> __device__ void gen_lane (Em<W>& e, const WarpMb& s, const int
 // ---- k_model_frame: per-stream frame bookkeeping -------------------------------------------------------------
 // WelsDecodeSlice decode_slice.cpp:3032-3046 for the first slice of the picture (later slices of the same picture repeat
 // the same updateFrame on unchanged data) and FreqImage::updateFrame decoded_macroblock.h:120-165.
-__global__ void __launch_bounds__ (32) k_model_frame (const MPicDev* pics, int n_pics) {
+__global__ void __launch_bounds__ (32) k_model_frame (const MPicDev* pics, int n_pics, const unsigned int* poison) {
   const int p = blockIdx.x, lane = threadIdx.x;
-  if (p >= n_pics) return;
+  if (p >= n_pics || *poison) return;
   const MPicDev& pic = pics[p];
   MState* st = pic.st;
   int cur = st->cur, len = st->frame_len;
@@ -544,8 +544,9 @@ __device__ __forceinline__ void t_load_ctx (CtxRecS& dst, const CtxRec* src) {
   }
 }
 
-__global__ void __launch_bounds__ (GEN_THREADS) k_model_count (const MPicDev* pics, int n_pics, int total_recs) {
+__global__ void __launch_bounds__ (GEN_THREADS) k_model_count (const MPicDev* pics, int n_pics, int total_recs, const unsigned int* poison) {
   extern __shared__ __align__ (16) unsigned char gen_smem[];
+  if (*poison) return;
   ThreadMb* tm = reinterpret_cast<ThreadMb*> (gen_smem);
   ThreadMb& t = tm[threadIdx.x];
   int p = 0, ri = 0;
@@ -595,11 +596,11 @@ __global__ void __launch_bounds__ (GEN_THREADS) k_model_count (const MPicDev* pi
 }
 
 // ---- k_model_scan: one block per picture ---------------------------------------------------------------------------------
-__global__ void __launch_bounds__ (1024) k_model_scan (const MPicDev* pics, int n_pics, uint32_t* pic_total) {
+__global__ void __launch_bounds__ (1024) k_model_scan (const MPicDev* pics, int n_pics, uint32_t* pic_total, const unsigned int* poison) {
   __shared__ uint32_t wsum[32];
   __shared__ uint32_t carry_s;
   const int p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  if (p >= n_pics) return;
+  if (p >= n_pics || *poison) return;
   const MPicDev& pic = pics[p];
   if (tid == 0) carry_s = 0;
   __syncthreads();
@@ -630,10 +631,12 @@ __global__ void __launch_bounds__ (1024) k_model_scan (const MPicDev* pics, int 
 // ---- k_model_plan: one block; positions of the pictures in the decision list, and the capacity checks the host used to
 // make between two launches (it no longer waits in the middle of a submit) ------------------------------------------
 __global__ void __launch_bounds__ (1024) k_model_plan (int n_pics, const uint32_t* pic_total, unsigned long long* dec_base, BatchCtl* ctl,
-                                                       unsigned long long dec_capacity, ArenaDev ar) {
+                                                       unsigned long long dec_capacity, ArenaDev ar, unsigned int* poison) {
   __shared__ unsigned long long wsum[32];
   __shared__ unsigned long long carry_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // an earlier batch skipped its coding: nothing of this one has run (every kernel checks), the host runs both again in order
+  if (*poison) { if (tid == 0) { ctl->skip = 2; ctl->total = 0; ctl->pages_needed = 0; ctl->pages_in_use = *ar.next; } return; }
   if (tid == 0) carry_s = 0;
   __syncthreads();
   for (int base = 0; base < n_pics; base += 1024) {
@@ -664,6 +667,7 @@ __global__ void __launch_bounds__ (1024) k_model_plan (int n_pics, const uint32_
     const unsigned int in_use = *ar.next;
     ctl->total = total; ctl->pages_needed = (unsigned int)min (pages, 0xffffffffull); ctl->pages_in_use = in_use;
     ctl->skip = (total + 32 > dec_capacity || in_use + pages > ar.n_pages) ? 1u : 0u;
+    if (ctl->skip) *poison = 1u;
   }
 }
 

@@ -33,21 +33,33 @@ using namespace lh264host;
 
 namespace {
 
-struct Staged {                         // one picture of one stream inside a staging arena (offsets in bytes from `base`)
+struct Staged {                         // one finished picture of one stream, waiting to be placed in the staging arena
   bool have = false;
-  const uint8_t* base = nullptr;        // the arena, or a heap block for the rare second picture completed by one NAL
-  std::shared_ptr<std::vector<uint8_t> > heap, mheap;
-  const uint8_t* mbase = nullptr;       // base of the model record offsets
-  size_t o_slices = 0, o_mbs = 0, o_coefs = 0, o_mslices = 0, o_mrecs = 0;
+  DecodedPictureInfo info;
+  // The records live either in the decoder itself (a complete picture ends the parse of its stream for this step, so they
+  // stay valid until the stream is advanced again) or in `own` (pictures finished by the arrival of the next one).
+  const lh264_slice_rec* slices = nullptr; const lh264_mb_rec* mbs = nullptr; const int16_t* coefs = nullptr;
+  const lh264_model_slice* mslices = nullptr; const lh264_model_mb* mrecs = nullptr;
   int n_slices = 0, n_mbs = 0, n_blocks = 0, n_mslices = 0, n_mrecs = 0;
+  std::shared_ptr<std::vector<uint8_t> > own, mown;
+};
+
+struct Placed {                         // a live picture of a step: where its arrays sit in the arena, and what the submit needs
+  int stream; size_t o_sl, o_mb, o_co, o_msl, o_mr;
+  int n_slices, n_blocks, n_mslices, n_mrecs;
   DecodedPictureInfo info;
 };
 
-struct Arena {                          // pinned, grow-only, bump allocated by the parse threads of one step
-  uint8_t* p = nullptr; size_t cap = 0; std::atomic<size_t> used{0};
-  uint8_t* take (size_t n) {
-    const size_t a = used.fetch_add ((n + 127) & ~(size_t)127);
-    return a + n <= cap ? p + a : nullptr;
+struct Arena {                          // pinned; five tightly packed regions per step (slices, mbs, coefs, model slices, model recs)
+  uint8_t* p = nullptr; size_t cap = 0;
+  std::vector<Placed> placed;
+  bool ensure (size_t need) {
+    if (need <= cap) return true;
+    if (p) lh264_host_free (p);
+    cap = need + need / 4;
+    p = (uint8_t*)lh264_host_alloc (cap);
+    if (!p) cap = 0;
+    return p != nullptr;
   }
 };
 
@@ -55,57 +67,38 @@ class CollectSink : public PictureSink {
  public:
   int mb_w = 0, mb_h = 0, n_slots = 0;
   bool reconfigured = false;
-  Arena* arena = nullptr;               // where submit() copies to (set by the runtime before every step)
   Staged* out = nullptr;
   std::vector<Staged> spill;            // pictures completed beyond the first one of a step (damaged streams), FIFO
-  bool overflow = false;
   int configure (int w, int h, int slots) override { mb_w = w; mb_h = h; n_slots = slots; reconfigured = true; return 0; }
   int submit (const lh264_picture_desc& pic, const DecodedPictureInfo& info) override {
-    const size_t b_sl = (size_t)pic.n_slices * sizeof (lh264_slice_rec), b_mb = (size_t)mb_w * mb_h * sizeof (lh264_mb_rec), b_co = (size_t)pic.n_coef_blocks * 32;
-    const size_t need = b_sl + b_mb + b_co + 256;
-    uint8_t* q;
-    if (!out->have) {
-      cur_ = out;
-      q = arena->take (need);
-      if (!q) { overflow = true; cur_ = nullptr; return 0; }
-      cur_->base = arena->p;
-    } else {
-      spill.emplace_back ();
-      cur_ = &spill.back();
-      cur_->heap = std::make_shared<std::vector<uint8_t> > (need);
-      q = cur_->heap->data();
-      cur_->base = q;
-    }
+    if (!out->have) cur_ = out; else { spill.emplace_back (); cur_ = &spill.back(); }
     Staged& s = *cur_;
-    s.o_mbs = (size_t) (q - s.base); memcpy (q, pic.mbs, b_mb); q += b_mb;
-    s.o_coefs = (size_t) (q - s.base); if (b_co) memcpy (q, pic.coefs, b_co); q += (b_co + 15) & ~(size_t)15;
-    s.o_slices = (size_t) (q - s.base); memcpy (q, pic.slices, b_sl);
-    s.n_slices = pic.n_slices; s.n_mbs = mb_w * mb_h; s.n_blocks = pic.n_coef_blocks; s.info = info; s.have = true;
+    s.info = info; s.have = true;
+    s.n_slices = pic.n_slices; s.n_mbs = mb_w * mb_h; s.n_blocks = pic.n_coef_blocks;
+    if (info.complete && cur_ == out) { s.slices = pic.slices; s.mbs = pic.mbs; s.coefs = pic.coefs; return 0; }
+    const size_t b_sl = (size_t)pic.n_slices * sizeof (lh264_slice_rec), b_mb = (size_t)s.n_mbs * sizeof (lh264_mb_rec), b_co = (size_t)pic.n_coef_blocks * 32;
+    s.own = std::make_shared<std::vector<uint8_t> > (b_mb + b_co + b_sl + 64);
+    uint8_t* q = s.own->data();
+    memcpy (q, pic.mbs, b_mb); s.mbs = reinterpret_cast<const lh264_mb_rec*> (q); q += b_mb;
+    if (b_co) memcpy (q, pic.coefs, b_co);
+    s.coefs = reinterpret_cast<const int16_t*> (q); q += (b_co + 15) & ~(size_t)15;
+    memcpy (q, pic.slices, b_sl); s.slices = reinterpret_cast<const lh264_slice_rec*> (q);
     return 0;
   }
   int submit_model (const lh264_model_picture& pic, const DecodedPictureInfo&) override {
     if (!cur_) return 0;
     Staged& s = *cur_;
-    const size_t b_sl = (size_t)pic.n_slices * sizeof (lh264_model_slice), b_rc = (size_t)pic.n_recs * sizeof (lh264_model_mb);
-    if (s.heap) {                       // model records of a spilled picture get their own block; offsets are relative to it
-      mheap_.push_back (std::make_shared<std::vector<uint8_t> > (b_sl + b_rc + 16));
-      uint8_t* q = mheap_.back()->data();
-      memcpy (q, pic.recs, b_rc); memcpy (q + b_rc, pic.slices, b_sl);
-      s.mbase = q; s.mheap = mheap_.back(); s.o_mrecs = 0; s.o_mslices = b_rc;
-      mheap_.clear();
-    } else {
-      uint8_t* q = arena->take (b_sl + b_rc + 128);
-      if (!q) { overflow = true; return 0; }
-      s.mbase = arena->p;
-      s.o_mrecs = (size_t) (q - arena->p); memcpy (q, pic.recs, b_rc); q += b_rc;
-      s.o_mslices = (size_t) (q - arena->p); memcpy (q, pic.slices, b_sl);
-    }
     s.n_mslices = pic.n_slices; s.n_mrecs = pic.n_recs;
+    if (!s.own) { s.mslices = pic.slices; s.mrecs = pic.recs; return 0; }
+    const size_t b_sl = (size_t)pic.n_slices * sizeof (lh264_model_slice), b_rc = (size_t)pic.n_recs * sizeof (lh264_model_mb);
+    s.mown = std::make_shared<std::vector<uint8_t> > (b_rc + b_sl + 16);
+    uint8_t* q = s.mown->data();
+    memcpy (q, pic.recs, b_rc); s.mrecs = reinterpret_cast<const lh264_model_mb*> (q);
+    memcpy (q + b_rc, pic.slices, b_sl); s.mslices = reinterpret_cast<const lh264_model_slice*> (q + b_rc);
     return 0;
   }
  private:
   Staged* cur_ = nullptr;
-  std::vector<std::shared_ptr<std::vector<uint8_t> > > mheap_;
 };
 
 struct Stream {
@@ -122,11 +115,11 @@ struct Stream {
   long pictures = 0, parsed = 0;
   int loops_left = 0;                             // replay the input this many more times (one long concatenated stream)
   // parses until one picture is complete (or the stream ends); h264dec's unit loop
-  void advance (Arena* arena, int buf, bool want_pip) {
+  void advance (int buf, bool want_pip) {
     Staged& st = staged[buf];
     st = Staged();
     if (!sink.spill.empty()) { st = sink.spill.front(); sink.spill.erase (sink.spill.begin()); parsed++; return; }
-    sink.arena = arena; sink.out = &st;
+    sink.out = &st;
     while (!st.have && !flushed) {
       if (pos >= size) {
         if (loops_left > 0) { loops_left--; pos = 0; continue; }
@@ -225,10 +218,6 @@ static void run_group (const Options& o, const std::vector<std::vector<uint8_t> 
     s.dec->enable_model (want_model);
   }
   Arena arena[2];
-  const size_t arena_cap = (size_t)S * (4u << 20) + (8u << 20);   // 4 MB per stream (a 1080p P picture needs ~2.7 MB)
-  for (int k = 0; k < 2; k++) { arena[k].p = (uint8_t*)lh264_host_alloc (arena_cap); arena[k].cap = arena[k].p ? arena_cap : 0; }
-  if (!arena[0].p || !arena[1].p) { fprintf (stderr, "cannot allocate pinned staging\n"); res->rc = 1; return; }
-
   Pool pool (threads);
   std::vector<uint8_t> out_host;
   uint8_t* out_pin[2] = {nullptr, nullptr}; size_t out_cap[2] = {0, 0};
@@ -237,29 +226,65 @@ static void run_group (const Options& o, const std::vector<std::vector<uint8_t> 
   std::vector<lh264_model_picture> mdescs;
   std::vector<int> live, rd_streams, rd_slots;
   long total_pictures = 0;
-  double t_parse_wait = 0, t_gpu = 0, t_hash = 0, t_open = 0, t_call[4] = {0, 0, 0, 0};
+  double t_parse_wait = 0, t_gpu = 0, t_hash = 0, t_open = 0, t_place = 0, t_call[4] = {0, 0, 0, 0};
   const int max_pictures = o.max_pictures;
+  const bool serial_model = getenv ("LH264_BATCH_FREE") == nullptr;
 #define FAIL(...) do { fprintf (stderr, __VA_ARGS__); res->rc = 1; pool.wait(); return; } while (0)
 
+  // Lays the pictures parsed into staged[k] out in arena[k]: five tightly packed regions in stream order, so that every array
+  // type of the whole batch goes up with ONE copy (the library merges contiguous host ranges); the copies into the arena run
+  // on the pool.
+  auto place = [&] (int k) -> bool {
+    Arena& a = arena[k];
+    a.placed.clear();
+    size_t n_sl = 0, n_mb = 0, n_co = 0, n_msl = 0, n_mr = 0;
+    for (int i = 0; i < S; i++) {
+      const Staged& st = streams[i].staged[k];
+      if (!st.have) continue;
+      a.placed.push_back (Placed{ i, n_sl, n_mb, n_co, n_msl, n_mr, st.n_slices, st.n_blocks, st.n_mslices, st.n_mrecs, st.info });
+      n_sl += (size_t)st.n_slices * sizeof (lh264_slice_rec); n_mb += (size_t)st.n_mbs * sizeof (lh264_mb_rec); n_co += (size_t)st.n_blocks * 32;
+      n_msl += (size_t)st.n_mslices * sizeof (lh264_model_slice); n_mr += (size_t)st.n_mrecs * sizeof (lh264_model_mb);
+    }
+    const size_t b_mb = 0, b_co = (n_mb + 255) & ~(size_t)255, b_mr = b_co + ((n_co + 255) & ~(size_t)255), b_sl = b_mr + ((n_mr + 255) & ~(size_t)255),
+                 b_msl = b_sl + ((n_sl + 255) & ~(size_t)255), total = b_msl + n_msl + 256;
+    if (!a.ensure (total)) return false;
+    for (Placed& pl : a.placed) { pl.o_mb += b_mb; pl.o_co += b_co; pl.o_mr += b_mr; pl.o_sl += b_sl; pl.o_msl += b_msl; }
+    pool.start ((int)a.placed.size(), [&, k] (int j) {
+      const Placed& pl = arena[k].placed[j];
+      const Staged& st = streams[pl.stream].staged[k];
+      uint8_t* base = arena[k].p;
+      memcpy (base + pl.o_mb, st.mbs, (size_t)st.n_mbs * sizeof (lh264_mb_rec));
+      if (st.n_blocks) memcpy (base + pl.o_co, st.coefs, (size_t)st.n_blocks * 32);
+      memcpy (base + pl.o_sl, st.slices, (size_t)st.n_slices * sizeof (lh264_slice_rec));
+      if (st.n_mrecs) { memcpy (base + pl.o_mr, st.mrecs, (size_t)st.n_mrecs * sizeof (lh264_model_mb)); memcpy (base + pl.o_msl, st.mslices, (size_t)st.n_mslices * sizeof (lh264_model_slice)); }
+    });
+    pool.wait();
+    return true;
+  };
+  const bool ktimes = getenv ("LH264_BATCH_KTIMES") != nullptr;   // diagnostic: per-family kernel times (serialises the launches)
+  if (ktimes) lh264_kernel_ms (ctx, -1);
   const double t0 = now();
   int buf = 0;
-  pool.start (S, [&] (int i) { streams[i].advance (&arena[0], 0, want_pip); });
+  pool.start (S, [&] (int i) { streams[i].advance (0, want_pip); });
   pool.wait();
+  if (!place (0)) FAIL ("cannot allocate pinned staging\n");
+  auto start_parse = [&] (int k) {                      // parse every stream's next picture into staged[k] (pool, asynchronous)
+    pool.start (S, [&, k] (int i) { if (streams[i].parsed < max_pictures) streams[i].advance (k, want_pip); else streams[i].staged[k] = Staged(); });
+  };
+  start_parse (1);
   for (int step = 0;; step++) {
-    for (int i = 0; i < S; i++) if (streams[i].sink.overflow) FAIL ("pinned staging arena too small\n");
     live.clear();
-    for (int i = 0; i < S; i++) if (streams[i].staged[buf].have && streams[i].pictures < max_pictures) live.push_back (i);
-    if (live.empty()) break;
-    const int nb = buf ^ 1;                             // parse the next step while this one is on the GPU
-    arena[nb].used = 0;
-    pool.start (S, [&, nb] (int i) { if (streams[i].parsed < max_pictures) streams[i].advance (&arena[nb], nb, want_pip); else streams[i].staged[nb] = Staged(); });
+    for (const Placed& pl : arena[buf].placed) live.push_back (pl.stream);
+    if (live.empty()) { pool.wait(); break; }
+    const int nb = buf ^ 1;
     const double tg0 = now();
     descs.clear(); mdescs.clear(); rd_streams.clear(); rd_slots.clear();
     int out_w = 0, out_h = 0, crop_x = 0, crop_y = 0;
     bool same_geometry = true;
-    for (int i : live) {
+    for (const Placed& pl : arena[buf].placed) {
+      const int i = pl.stream;
       Stream& s = streams[i];
-      const Staged& st = s.staged[buf];
+      const Placed& st = pl;                            // (staged[] of this step may already be reused by the parse of step t+2)
       const double to = now();
       if (s.sink.reconfigured) {
         if (s.gpu_stream >= 0) lh264_stream_close (ctx, s.gpu_stream);
@@ -272,18 +297,18 @@ static void run_group (const Options& o, const std::vector<std::vector<uint8_t> 
         if (s.model_stream < 0) FAIL ("lh264_model_open: %s\n", lh264_last_error());
       }
       t_open += now() - to;
-      const uint8_t* base = st.base;
+      const uint8_t* base = arena[buf].p;
       lh264_picture_desc d;
       d.stream = s.gpu_stream; d.cur_slot = st.info.slot; d.n_slices = st.n_slices; d.n_coef_blocks = st.n_blocks;
-      d.slices = reinterpret_cast<const lh264_slice_rec*> (base + st.o_slices);
-      d.mbs = reinterpret_cast<const lh264_mb_rec*> (base + st.o_mbs);
-      d.coefs = reinterpret_cast<const int16_t*> (base + st.o_coefs);
+      d.slices = reinterpret_cast<const lh264_slice_rec*> (base + pl.o_sl);
+      d.mbs = reinterpret_cast<const lh264_mb_rec*> (base + pl.o_mb);
+      d.coefs = reinterpret_cast<const int16_t*> (base + pl.o_co);
       descs.push_back (d);
       if (want_model && st.n_mrecs > 0) {
         lh264_model_picture m;
         m.model_stream = s.model_stream; m.mb_w = s.sink.mb_w; m.mb_h = s.sink.mb_h; m.n_slices = st.n_mslices; m.n_recs = st.n_mrecs; m.n_coef_blocks = st.n_blocks;
-        m.slices = reinterpret_cast<const lh264_model_slice*> (st.mbase + st.o_mslices);
-        m.recs = reinterpret_cast<const lh264_model_mb*> (st.mbase + st.o_mrecs);
+        m.slices = reinterpret_cast<const lh264_model_slice*> (base + pl.o_msl);
+        m.recs = reinterpret_cast<const lh264_model_mb*> (base + pl.o_mr);
         m.coefs = d.coefs;
         mdescs.push_back (m);
       }
@@ -295,7 +320,14 @@ static void run_group (const Options& o, const std::vector<std::vector<uint8_t> 
     if (lh264_recon_submit (ctx, descs.data(), (int)descs.size()) != LH264_OK) FAIL ("lh264_recon_submit: %s\n", lh264_last_error());
     t_call[0] += now() - tq; tq = now();
     if (!mdescs.empty() && lh264_model_submit (ctx, mdescs.data(), (int)mdescs.size()) != LH264_OK) FAIL ("lh264_model_submit: %s\n", lh264_last_error());
-    t_call[1] += now() - tq; tq = now();
+    if (serial_model) lh264_join (ctx);               // next reconstruction after this model (they slow each other down)
+    t_call[1] += now() - tq;
+    // host work of the NEXT step while this one is on the GPU: wait for its parse, copy its records into the other arena
+    { const double tw = now(); pool.wait(); t_parse_wait += now() - tw; }
+    if (lh264_inputs_consumed (ctx) != LH264_OK) FAIL ("lh264_inputs_consumed: %s\n", lh264_last_error());   // arena[nb] fed step t-1
+    { const double tp = now(); if (!place (nb)) FAIL ("cannot allocate pinned staging\n"); t_place += now() - tp; }
+    start_parse (buf);                                  // step t+2: its records are copied out of staged[] only after the next place()
+    tq = now();
     // The decoded pictures of step t-1 are still on their way to the host (copy stream) while step t's records went up and its
     // kernels ran: wait for them now, start this step's copy, then hash the previous pictures while it runs.
     struct Out { bool valid = false; std::vector<int> lv; size_t per = 0; int idx = 0; };
@@ -304,6 +336,7 @@ static void run_group (const Options& o, const std::vector<std::vector<uint8_t> 
       if (!prev.valid) return;
       prev.valid = false;
       if (!want_hash) return;
+      pool.wait();                                      // (the pool runs one job at a time: the parse of step t+2 first)
       const double th = now();
       const Out p = prev;
       pool.start ((int)p.lv.size(), [&, p] (int k) { streams[p.lv[k]].yuv.update (out_pin[p.idx] + p.per * k, p.per); });
@@ -320,16 +353,12 @@ static void run_group (const Options& o, const std::vector<std::vector<uint8_t> 
         if (!out_pin[oi] || lh264_pictures_read_packed (ctx, rd_streams.data(), rd_slots.data(), (int)live.size(), crop_x, crop_y, out_w, out_h, out_pin[oi], out_cap[oi], 0) != LH264_OK)
           FAIL ("lh264_pictures_read_packed: %s\n", lh264_last_error());
         t_call[3] += now() - tq;
-        const double tw = now();
-        pool.wait();                                      // the parse of the next step
-        t_parse_wait += now() - tw;
         consume_prev();
         prev.valid = true; prev.lv = live; prev.per = per; prev.idx = oi;
       } else {                                           // mixed geometry: picture by picture
-        pool.wait();
         consume_prev();
-        for (int i : live) {
-          const Staged& st = streams[i].staged[buf];
+        for (const Placed& st : arena[buf].placed) {
+          const int i = st.stream;
           const int w = st.info.width, h = st.info.height, cw = (w + 1) / 2, ch = (h + 1) / 2;
           out_host.resize ((size_t)w * h + 2 * (size_t)cw * ch);
           uint8_t* y = out_host.data();
@@ -340,13 +369,10 @@ static void run_group (const Options& o, const std::vector<std::vector<uint8_t> 
       }
     } else {
       if (lh264_sync (ctx) != LH264_OK) FAIL ("lh264_sync: %s\n", lh264_last_error());
-      const double tw = now();
-      pool.wait();
-      t_parse_wait += now() - tw;
     }
     last_consume = consume_prev;
-    t_gpu += now() - tg0;
     for (int i : live) { streams[i].pictures++; total_pictures++; }
+    t_gpu += now() - tg0;
     buf = nb;
   }
   lh264_sync (ctx);
@@ -386,10 +412,11 @@ static void run_group (const Options& o, const std::vector<std::vector<uint8_t> 
   res->t_all = now() - t0;
   res->pictures = total_pictures; res->t_main = t_gpu; res->t_open = t_open; res->t_hash = t_hash; res->t_parse_wait = t_parse_wait;
   res->launches = lh264_kernel_launches (ctx);
-  if (getenv ("LH264_BATCH_TIMES")) fprintf (stderr, "group %d: recon_submit %.3f s, model_submit %.3f s, output_wait %.3f s, read_packed %.3f s, open %.3f s, parse wait %.3f s\n", first, t_call[0], t_call[1], t_call[2], t_call[3], t_open, t_parse_wait);
+  if (ktimes) fprintf (stderr, "group %d kernels: recon %.1f ms, deblock %.1f ms, model generation %.1f ms, model coder %.1f ms\n", first, lh264_kernel_ms (ctx, 0), lh264_kernel_ms (ctx, 2), lh264_kernel_ms (ctx, 4), lh264_kernel_ms (ctx, 5));
+  if (getenv ("LH264_BATCH_TIMES")) fprintf (stderr, "group %d: recon_submit %.3f s, model_submit %.3f s, output_wait %.3f s, read_packed %.3f s, open %.3f s, parse wait %.3f s, staging copy %.3f s\n", first, t_call[0], t_call[1], t_call[2], t_call[3], t_open, t_parse_wait, t_place);
   for (auto& s : streams) delete s.dec;
   for (int k = 0; k < 2; k++) if (out_pin[k]) lh264_host_free (out_pin[k]);
-  lh264_host_free (arena[0].p); lh264_host_free (arena[1].p);
+  for (int k = 0; k < 2; k++) if (arena[k].p) lh264_host_free (arena[k].p);
   lh264_ctx_destroy (ctx);
 #undef FAIL
 }

@@ -51,3 +51,21 @@ def test_cuda_model_batches_independent_streams(ctx, tmp_path):
     finally:
         for h in handles:
             ctx.model_close(h)
+
+
+def test_pipelined_submits_survive_a_batch_that_does_not_fit(tmp_path):
+    """Two batches in flight, no host wait between submits: the first picture overflows the initial decision list, so it skips
+    its coding on the device and the batch behind it skips entirely; the library grows and runs both again in order."""
+    from losslessh264_b200.api import Context
+
+    name = "syn720p_8f.264"
+    pics = model_pictures(name, str(tmp_path))
+    c = Context(0)                                          # a fresh context: its decision list starts at the first guess
+    try:
+        ms = c.model_open(max(p.mb_w * p.mb_h for p in pics))
+        for p in pics:
+            c.model_submit([p], [ms], sync=False)
+        check_tags(name, c.model_finish(ms))
+        c.model_close(ms)
+    finally:
+        c.close()
