@@ -46,3 +46,23 @@ def test_cli_compress_writes_the_reference_pip_file_set(name, tmp_path):
         tb = open(pip + "." + t, "rb").read()
         assert hashlib.sha1(tb).hexdigest() == g["tags"][t]["sha1"], f"{name}: .pip.{t} differs from the reference"
     assert hashlib.sha1(open(yuv, "rb").read()).hexdigest() == SHA1[name]["sha1"], f"{name}: YUV differs"
+
+
+# ---- lossless round trip (BASELINE config 1, roundtriptest/run.sh:27-39): the `.pip` file set written by the B200 path is fed to the
+# UNMODIFIED reference decompressor (oracle/_ref/h264dec x.pip x.264, test infrastructure) and must give back the original
+# file byte for byte.  Streams on which the reference itself does not round-trip are not in the list.
+REF_DEC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "h264dec")
+ROUNDTRIP_SET = ["tibby.264", "black.264", "BAMQ2_JVC_C.264", "BA1_FT_C.264", "tibby8x8cavlc.264", "BA_MW_D.264", "MR2_TANDBERG_E.264", "syn720p_8f.264"]
+
+
+@pytest.mark.skipif(not os.path.exists(REF_DEC), reason="compiled reference (oracle/_ref) not present")
+@pytest.mark.parametrize("name", ROUNDTRIP_SET)
+def test_pip_written_on_the_gpu_round_trips_through_the_reference_decompressor(name, tmp_path):
+    src = os.path.join(STREAM_DIR, name)
+    pip = os.path.join(str(tmp_path), "o.pip")
+    r = subprocess.run([os.path.join(LIB_DIR, "h264dec_lh264"), src, pip], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-400:]
+    back = os.path.join(str(tmp_path), "back.264")
+    r = subprocess.run([REF_DEC, pip, back], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-400:]
+    assert open(back, "rb").read() == open(src, "rb").read(), f"{name}: the reference decompressor does not reproduce the original from our .pip"
