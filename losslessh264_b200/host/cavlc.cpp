@@ -92,6 +92,14 @@ static const uint8_t kRunCode[7][15] = {
   {7, 6, 5, 4, 3, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1},
 };
 
+// the (length, code) tables, for the writing direction (cavlc_writer.cpp)
+void cavlc_tables (const uint8_t (**tok_len)[4][17], const uint8_t (**tok_code)[4][17], const uint8_t (**tokc_len)[5], const uint8_t (**tokc_code)[5],
+                   const uint8_t (**tz_len)[16], const uint8_t (**tz_code)[16], const uint8_t (**tzc_len)[4], const uint8_t (**tzc_code)[4],
+                   const uint8_t (**run_len)[15], const uint8_t (**run_code)[15]) {
+  *tok_len = kTokLen; *tok_code = kTokCode; *tokc_len = kTokLenC; *tokc_code = kTokCodeC; *tz_len = kTzLen; *tz_code = kTzCode;
+  *tzc_len = kTzLenC; *tzc_code = kTzCodeC; *run_len = kRunLen; *run_code = kRunCode;
+}
+
 // ---- generic prefix-code LUT ------------------------------------------------------------------------------------
 struct Lut {
   int bits = 0;                         // index width

@@ -19,5 +19,7 @@ int cavlc_residual_block (BitReader& br, int nC, int max_coeff, const uint8_t* s
 
 extern const uint8_t kZigzag4x4[16];
 extern const uint8_t kZigzag8x8[64];
+extern const uint8_t kCbpIntra[48], kCbpInter[48];   // Table 9-4 (decoder.cpp)
+extern const uint8_t kZtoR[16], kRtoZ[16];           // decode order <-> raster index of the 4x4 luma blocks
 
 } // namespace lh264host

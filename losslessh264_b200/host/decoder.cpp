@@ -1,14 +1,14 @@
 // decoder.cpp — see decoder.h.  Clause numbers refer to ITU-T H.264.
 #include "decoder.h"
 #include "cavlc.h"
+#include "cavlc_writer.h"
+#include <memory>
 #include <string.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <algorithm>
 
 namespace lh264host {
-
-namespace {
 
 // Table 9-4: coded_block_pattern me(v) mapping for ChromaArrayType 1/2
 const uint8_t kCbpIntra[48] = {47, 31, 15, 0, 23, 27, 29, 30, 7, 11, 13, 14, 39, 43, 45, 46, 16, 3, 5, 10, 12, 19, 21, 26, 28, 35, 37, 42, 44, 1, 2, 4,
@@ -17,13 +17,16 @@ const uint8_t kCbpIntra[48] = {47, 31, 15, 0, 23, 27, 29, 30, 7, 11, 13, 14, 39,
 const uint8_t kCbpInter[48] = {0, 16, 1, 2, 4, 8, 32, 3, 5, 10, 12, 15, 47, 7, 11, 13, 14, 6, 9, 31, 35, 37, 42, 44, 33, 34, 36, 40, 39, 43, 45, 46,
                                17, 18, 20, 24, 19, 21, 26, 28, 23, 27, 29, 30, 22, 25, 38, 41
                               };
+// z (decode order) <-> raster index of the 4x4 luma blocks
+const uint8_t kZtoR[16] = {0, 1, 4, 5, 2, 3, 6, 7, 8, 9, 12, 13, 10, 11, 14, 15};
+const uint8_t kRtoZ[16] = {0, 1, 4, 5, 2, 3, 6, 7, 8, 9, 12, 13, 10, 11, 14, 15};
+
+namespace {
+
 // Table 8-15: QPc as a function of qPI
 const uint8_t kChromaQp[52] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29,
                                29, 30, 31, 32, 32, 33, 34, 34, 35, 35, 36, 36, 37, 37, 37, 38, 38, 38, 39, 39, 39, 39
                               };
-// z (decode order) <-> raster index of the 4x4 luma blocks
-const uint8_t kZtoR[16] = {0, 1, 4, 5, 2, 3, 6, 7, 8, 9, 12, 13, 10, 11, 14, 15};
-const uint8_t kRtoZ[16] = {0, 1, 4, 5, 2, 3, 6, 7, 8, 9, 12, 13, 10, 11, 14, 15};
 const uint8_t kChromaDcScan[4] = {0, 16, 32, 48};   // DC k -> slot 0 of block k
 
 struct RefPic {
@@ -66,6 +69,8 @@ struct Decoder::Impl {
   std::vector<uint8_t> slice_rbsp;
   // recompression-model hand-off (include/lh264_b200.h, lh264_model_*): records in slice-data order
   bool want_model = false;
+  bool check_rewrite = false;
+  std::unique_ptr<PictureSyntaxWriter> rewriter;
   std::vector<lh264_model_mb> mrecs;
   std::vector<lh264_model_slice> mslices;
   // per-position decoder state the reference keeps across pictures and reads back when it fills its
@@ -669,6 +674,7 @@ int Decoder::Impl::parse_slice_data (BitReader& br, Decoder* self) {
   int mb_addr = sh.first_mb;
   qp = sh.slice_qp;
   const int first = mb_addr;
+  const size_t data_begin = br.pos();
   bool more = true;
   int rc = 0;
   // model records: one per MB in slice-data order, with the reference's skip-run / stop-bit bookkeeping
@@ -736,6 +742,26 @@ int Decoder::Impl::parse_slice_data (BitReader& br, Decoder* self) {
     ms.pad_bits = (uint8_t) (br.size_bits() ? (br.data()[br.payload_end() >> 3] & ((1u << ms.n_pad_bits) - 1)) : 0);
     ms.chroma_format_idc = 1;
     mslices.push_back (ms);
+    if (check_rewrite && rc == 0) {
+      if (mslices.size() == 1 || !rewriter) rewriter.reset (new PictureSyntaxWriter (mb_w, mb_h));
+      SliceWriteParams wp;
+      wp.slice_type = ms.slice_type; wp.num_ref_idx_l0 = ms.num_ref_idx_l0; wp.slice_qp = sh.slice_qp; wp.transform_8x8_mode = P->transform_8x8_mode;
+      rewriter->begin_slice (wp);
+      BitWriter bw;
+      bool ok = true;
+      for (size_t i = rec0; i < mrecs.size() && ok; i++) ok = rewriter->write_mb (bw, mrecs[i], coefs.data());
+      const size_t n = br.pos() - data_begin;
+      ok = ok && bw.bits() == n;
+      for (size_t i = 0; ok && i < n; i++) {
+        const size_t a = data_begin + i;
+        ok = (((br.data()[a >> 3] >> (7 - (a & 7))) ^ (bw.bytes()[i >> 3] >> (7 - (i & 7)))) & 1) == 0;
+      }
+      self->stats_.rewritten_slices++;
+      if (!ok) {
+        self->stats_.rewrite_mismatches++;
+        if (getenv ("LH264_DEBUG")) fprintf (stderr, "rewrite mismatch: slice first_mb %d type %d: %zu bits parsed, %zu written\n", first, ms.slice_type, n, bw.bits());
+      }
+    }
   }
   return rc;
 }
@@ -745,6 +771,7 @@ Decoder::Decoder (PictureSink* sink) : d_ (new Impl()) { d_->sink = sink; cavlc_
 Decoder::~Decoder() {}
 const std::vector<ModelMbSide>& Decoder::model_side() const { return d_->side; }
 void Decoder::enable_model (bool on) { d_->want_model = on; }
+void Decoder::enable_rewrite_check (bool on) { d_->check_rewrite = on; if (on) d_->want_model = true; }
 
 int Decoder::flush() { return d_->finish_picture (this); }
 

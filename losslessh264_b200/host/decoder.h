@@ -55,7 +55,8 @@ class PictureSink {
   virtual int submit_model (const lh264_model_picture& pic, const DecodedPictureInfo& info) { (void)pic; (void)info; return 0; }
 };
 
-struct DecoderStats { uint64_t nals = 0, slices = 0, pictures = 0, mbs = 0, coef_blocks = 0, errors = 0; };
+struct DecoderStats { uint64_t nals = 0, slices = 0, pictures = 0, mbs = 0, coef_blocks = 0, errors = 0;
+                      uint64_t rewritten_slices = 0, rewrite_mismatches = 0; };   // enable_rewrite_check()
 
 class Decoder {
  public:
@@ -67,6 +68,9 @@ class Decoder {
   // Flushes a picture still pending (end of stream).
   int flush();
   const DecoderStats& stats() const { return stats_; }
+  // self-check of the decompress direction: re-serialise every parsed slice_data() from its model records (cavlc_writer.h)
+  // and compare with the bits that were parsed.  Implies enable_model().
+  void enable_rewrite_check (bool on);
   // pictures completed by the last decode()/flush() call, in output order
   const std::vector<DecodedPictureInfo>& output() const { return out_; }
   void clear_output() { out_.clear(); }

@@ -29,6 +29,7 @@ int main (int argc, char** argv) {
   for (int it = 0; it < repeat; it++) {
     LhfbSink sink (it == 0 ? argv[2] : "/dev/null");
     Decoder dec (&sink);
+    if (getenv ("LH264_CHECK_REWRITE")) dec.enable_rewrite_check (true);   // decompress-direction self-check (cavlc_writer.h)
     if (argc > 4 && it == 0) { sink.set_model_path (argv[4]); dec.enable_model (true); }
     const auto t0 = std::chrono::steady_clock::now();
     if (argc > 5 && it == 0) {                          // the unit loop of h264dec, writing the `.pip` default stream
@@ -63,5 +64,9 @@ int main (int argc, char** argv) {
   fprintf (stderr, "nals %llu slices %llu pictures %llu mbs %llu coef_blocks %llu errors %llu  parse %.4f s (%.1f pictures/s)\n",
            (unsigned long long)st.nals, (unsigned long long)st.slices, (unsigned long long)st.pictures, (unsigned long long)st.mbs,
            (unsigned long long)st.coef_blocks, (unsigned long long)st.errors, best, st.pictures / best);
+  if (getenv ("LH264_CHECK_REWRITE")) {
+    fprintf (stderr, "rewrite check: %llu slices re-serialised, %llu mismatches\n", (unsigned long long)st.rewritten_slices, (unsigned long long)st.rewrite_mismatches);
+    if (st.rewrite_mismatches) return 5;
+  }
   return st.errors ? 4 : 0;
 }
