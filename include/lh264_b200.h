@@ -194,7 +194,7 @@ void lh264_batch_free(lh264_ctx* ctx, lh264_resident_batch* batch);
 uint64_t lh264_kernel_launches(const lh264_ctx* ctx);
 /* accumulated device time (ms, CUDA events on the context stream) of one kernel family
  * since the last reset: 0 k_recon_rows (inter + intra), 1 unused, 2 k_deblock_rows, 3 all reconstruction, 4 model generation
- * kernels (k_model_frame/count/scan/emit), 5 k_model_code; family = -1 resets and switches the
+ * kernels (k_model_frame/count/scan/emit), 5 k_model_code, 6 k_model_decode; family = -1 resets and switches the
  * (synchronising) per-family timing on, family = -2 switches it off                          */
 float lh264_kernel_ms(lh264_ctx* ctx, int family);
 
@@ -356,6 +356,51 @@ int  lh264_model_finish(lh264_ctx* ctx, int model_stream);
 long long lh264_model_read(lh264_ctx* ctx, int model_stream, int tag, uint8_t* dst, size_t offset, size_t cap);
 /* decisions coded so far by a model stream (for throughput reporting)                                                         */
 unsigned long long lh264_model_decisions(lh264_ctx* ctx, int model_stream);
+
+/* ---- decompress direction -----------------------------------------------------------------------------
+ * The reference's round trip (h264dec x.pip out.264): every arithmetic-coded side stream is read back through the same
+ * adaptive priors (decode4x4 / readMv / scanInt / scanUEGkInt, codec/decoder/core/inc/compression_stream.h:601-689,
+ * src/decode_slice.cpp:2476-2956; bool decoder inc/bitreader.h:77-136) and each macroblock is re-serialised as CAVLC
+ * (EncoderState, decode_slice.cpp:1442-1835 -> encoder/core/src/svc_set_mb_syn_cavlc.cpp).  Here one job = one stream: its
+ * side streams and the parameters of its slices (from the slice headers kept in the default stream) go in, the slice_data()
+ * bits of every slice come out.  Decoding is strictly serial inside a stream; a call runs all of its jobs concurrently.   */
+typedef struct lh264_decode_slice {
+  uint32_t first_mb;         /* first_mb_in_slice                                                                           */
+  int32_t  frame_num;        /* FreqImage::updateFrame key (decode_slice.cpp:3034)                                          */
+  uint16_t mb_w, mb_h;       /* picture size in macroblocks (active SPS)                                                    */
+  uint8_t  slice_type;       /* 0 P, 2 I                                                                                    */
+  uint8_t  num_ref_idx_l0;   /* active L0 reference count of the slice (PPS default for I slices)                           */
+  uint8_t  slice_qp;         /* SliceQPY                                                                                    */
+  uint8_t  flags;            /* bit0 PPS transform_8x8_mode_flag, bit1 PPS constrained_intra_pred_flag                      */
+  uint32_t header_bits;      /* bit position of slice_data() in the slice RBSP (trailing alignment bits, :3133-3147)        */
+} lh264_decode_slice;
+
+typedef struct lh264_decode_slice_out {
+  uint64_t byte_offset;      /* where this slice's bits start in the job's `out` buffer (byte aligned)                     */
+  uint32_t n_bits;           /* slice_data() length                                                                         */
+  uint32_t n_mbs;            /* macroblocks in the slice, skipped ones included                                            */
+  uint8_t  n_pad_bits;       /* alignment bits that follow the stop bit ...                                                */
+  uint8_t  pad_bits;         /* ... and their value (PADBYTE stream)                                                       */
+  uint16_t reserved;
+  uint32_t reserved2;
+} lh264_decode_slice_out;
+
+typedef struct lh264_decode_job {
+  int32_t  max_mbs;          /* largest picture of the stream, in macroblocks                                              */
+  int32_t  with_8x8;         /* != 0: the stream may use the 8x8 transform                                                 */
+  const uint8_t* tag_data[LH264_NUM_TAGS];   /* the `.pip.<tag>` side streams (NULL = no such file)                        */
+  uint32_t tag_len[LH264_NUM_TAGS];
+  const lh264_decode_slice* slices;
+  int32_t  n_slices;
+  int32_t  error;            /* out: 0, or 21 I_PCM (not representable, as in the reference), 22 `out` too small,
+                                23 corrupt side streams, 24 picture larger than max_mbs, 25 context outside the prior tables */
+  uint8_t* out;              /* host buffer receiving the slice_data() bits of all slices                                   */
+  uint64_t out_capacity;
+  lh264_decode_slice_out* slice_out;         /* [n_slices]                                                                 */
+} lh264_decode_job;
+
+/* Synchronous: uploads the jobs, runs one warp per job, downloads the bits.  Returns LH264_OK when every job decoded.    */
+int  lh264_model_decode(lh264_ctx* ctx, lh264_decode_job* jobs, int n_jobs);
 
 #ifdef __cplusplus
 }

@@ -101,6 +101,7 @@ struct lh264_ctx {
   float ms[3] = {0, 0, 0};
   bool timing = false;
   void* model = nullptr;                     // ModelCtx (model_host.inl), created by the first lh264_model_open
+  void* decode = nullptr;                    // DecodeCtx (model_decode.cuh), created by the first lh264_model_decode
   // host pointer -> device copy of the coefficient pools staged by the last lh264_recon_submit: a model picture that names
   // the same pool (it is the same data) reads the device copy instead of crossing PCIe twice
   std::vector<std::pair<const int16_t*, const int16_t*> > staged_coefs;
@@ -112,6 +113,8 @@ struct lh264_ctx {
   bool d2h_pending = false;
 };
 static void model_destroy (lh264_ctx* c);
+static void decode_destroy (lh264_ctx* c);
+static float decode_ms (lh264_ctx* c, bool reset);
 static float model_ms (lh264_ctx* c, int which, bool reset);
 static cudaError_t model_sync (lh264_ctx* c);
 static cudaError_t model_join (lh264_ctx* c);
@@ -157,6 +160,7 @@ void lh264_ctx_destroy (lh264_ctx* c) {
   cudaSetDevice (c->device);
   cudaStreamSynchronize (c->stream);
   model_destroy (c);
+  decode_destroy (c);
   for (auto& s : c->streams) if (s.base) cudaFree (s.base);
   c->batch[0].release(); c->batch[1].release(); c->h_pics.release();
   for (int i = 0; i < 2; i++) if (c->batch_free[i]) cudaEventDestroy (c->batch_free[i]);
@@ -330,7 +334,8 @@ uint64_t lh264_kernel_launches (const lh264_ctx* c) { return c ? c->launches : 0
 float lh264_kernel_ms (lh264_ctx* c, int family) {
   if (!c) return 0.f;
   if (family == -2) { c->timing = false; return 0.f; }
-  if (family < 0) { c->ms[0] = c->ms[1] = c->ms[2] = 0.f; model_ms (c, 0, true); c->timing = true; return 0.f; }
+  if (family < 0) { c->ms[0] = c->ms[1] = c->ms[2] = 0.f; model_ms (c, 0, true); decode_ms (c, true); c->timing = true; return 0.f; }
+  if (family == 6) return decode_ms (c, false);
   if (family < 3) return c->ms[family];
   if (family == 4 || family == 5) return model_ms (c, family - 4, false);
   return c->ms[0] + c->ms[1] + c->ms[2];
@@ -532,6 +537,7 @@ int lh264_k_expand_plane (lh264_ctx* c, const uint8_t* in, int w, int h, int pad
 } // extern "C"
 
 #include "model_host.inl"
+#include "model_decode.cuh"
 
 static float model_ms (lh264_ctx* c, int which, bool reset) {
   ModelCtx* m = static_cast<ModelCtx*> (c->model);

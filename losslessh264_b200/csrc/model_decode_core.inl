@@ -1,0 +1,639 @@
+// model_decode_core.inl — the DECOMPRESS direction of the recompression model, one stream = one strictly serial decoder.
+//
+// Replaces, per stream, the reference's round-trip path: reading the arithmetic-coded side streams back through the same
+// adaptive priors (decode4x4 / readMv / scanInt / scanUEGkInt / scanBits*, codec/decoder/core/inc/compression_stream.h
+// :601-689, src/decode_slice.cpp:2476-2956; bool decoder inc/bitreader.h:77-136), rebuilding every macroblock's syntax
+// elements, and re-serialising them as the original CAVLC slice_data() (EncoderState::writeMbSynCavlc, decode_slice.cpp
+// :1442-1835 -> encoder/core/src/svc_set_mb_syn_cavlc.cpp).  Every binary decision depends on all earlier ones of the stream
+// (adaptive probabilities AND the symbol-dependent choice of the next prior), so the only parallel axis is the stream: the
+// CUDA kernel (model_decode.cuh) runs one warp per stream, lane 0 walking this code.
+//
+// This file is plain C++ behind three macros so that the tests can compile the very same code for the CPU as a checker:
+//   MD_FN     function qualifier   (`__device__` in the CUDA build, `static inline` on the CPU)
+//   MD_CLZ    count-leading-zeros of a non-zero 32-bit value
+//   tables    host/cavlc_tables.h is included by the includer with LH264_CAVLC_TABLE set accordingly
+// The includer is in namespace scope; model_layout.h (tags, prior layout, CtxRec) must already be included.
+
+namespace lh264md {
+using namespace lh264m;
+using namespace lh264host;              // CAVLC tables
+
+// ---- DynProb word (compression_stream.h:87-115); identical packing to the compress kernels ---------------------------
+MD_FN uint32_t md_prob (uint32_t w) { return (w >> 24) ^ 0x80u; }
+MD_FN uint32_t md_adapt (uint32_t w, uint32_t bit) {
+  uint32_t c0 = w & 0x3ffu, c1 = (w >> 10) & 0x3ffu;
+  if (bit) c1++; else c0++;
+  const uint32_t prob = (256u * (c0 + 1u)) / (c0 + c1 + 2u);
+  if (c0 + c1 > 512u) { c0 = (c0 + 1u) >> 1; c1 = (c1 + 1u) >> 1; }
+  return c0 | (c1 << 10) | ((prob ^ 0x80u) << 24);
+}
+
+// ---- VP8 bool decoder (bitreader.h:77-136, bitreader.cpp:45-110), 32-bit window; bytes past the end read as zero ------
+struct MdReader { const uint8_t* buf; uint32_t len, pos, value, range; int32_t count; };
+MD_FN void md_reader_init (MdReader& r, const uint8_t* buf, uint32_t len) { r.buf = buf; r.len = len; r.pos = 0; r.value = 0; r.range = 255; r.count = -8; }
+MD_FN uint32_t md_read (MdReader& r, uint32_t prob) {
+  const uint32_t split = 1u + (((r.range - 1u) * prob) >> 8);
+  if (r.count < 0) {
+    int shift = 32 - 8 - (r.count + 8);
+    while (shift >= 0) {
+      const uint32_t b = r.pos < r.len ? r.buf[r.pos] : 0u;
+      r.pos++;
+      r.value |= b << shift;
+      shift -= 8; r.count += 8;
+    }
+  }
+  const uint32_t bigsplit = split << 24;
+  uint32_t range = split, bit = 0;
+  if (r.value >= bigsplit) { range = r.range - split; r.value -= bigsplit; bit = 1; }
+  const int shift = MD_CLZ (range) - 24;
+  r.range = range << shift; r.value <<= shift; r.count -= shift;
+  return bit;
+}
+
+// ---- per-stream state ------------------------------------------------------------------------------------------
+struct MdStream {
+  uint32_t* priors;               // pruned prior table (model_layout.h), zero = fresh
+  CtxRec* frame[2];               // FreqImage ring (decoded_macroblock.h:106-191)
+  uint8_t* ipm;                   // [mb][16] Intra4x4/8x8PredMode per raster 4x4 block (2 for every other MB type)
+  int32_t* mb_slice;              // [mb] number of the slice that last coded the MB (availability, 6.4.8)
+  uint8_t* mb_intra;              // [mb] 1 = intra MB (constrained_intra_pred)
+  uint8_t* tcoef;                 // [mb][24] total_coeff per 4x4 block: 16 luma (raster), 4 Cb, 4 Cr (nC context, 9.2.1)
+  int32_t width, height, frame_len, cur, lastFrameId, max_mbs, slice_counter, error;
+  MdReader rd[CT_COUNT];
+  uint32_t present;               // compact tags that have a side stream
+  uint32_t pad_;
+};
+// error codes
+enum { MD_ERR_PCM = 21, MD_ERR_OUT_FULL = 22, MD_ERR_SYNTAX = 23, MD_ERR_DIMS = 24, MD_ERR_CONTEXT = 25 };
+
+struct MdCtx { uint32_t* priors; MdReader* rd; };
+
+MD_FN uint32_t md_bit (MdCtx& c, int tag, uint32_t prior) {     // ArithmeticCodedInput::scanBit + DynProb update
+  const uint32_t w = c.priors[prior];
+  const uint32_t bit = md_read (c.rd[tag], md_prob (w));
+  c.priors[prior] = md_adapt (w, bit);
+  return bit;
+}
+// scanBits(nBits, Branch<n>): compression_stream.h pre-order tree, mirror of emitBits :477-487
+MD_FN uint32_t md_branch (MdCtx& c, int tag, int nbits, uint32_t tree) {
+  uint32_t data = 0;
+  for (int n = nbits; n >= 1; n--) {
+    const uint32_t bit = md_bit (c, tag, tree);
+    data = (data << 1) | bit;
+    tree += bit ? (1u << (n - 1)) : 1u;
+  }
+  return data;
+}
+MD_FN uint32_t md_raw (MdCtx& c, int tag, int nbits) {          // scanBits(nBits) through TEST_PROB
+  uint32_t data = 0;
+  for (int i = 0; i < nbits; i++) data = (data << 1) | md_bit (c, tag, P_TEST);
+  return data;
+}
+MD_FN uint32_t md_zero_to_pow2 (MdCtx& c, int tag, int nbits, uint32_t priors, uint32_t preferred) {   // scanBitsZeroToPow2Inclusive
+  if (!md_bit (c, tag, priors)) return preferred;
+  const uint32_t d = md_branch (c, tag, nbits, priors + 1);
+  return d >= preferred ? d + 1 : d;
+}
+MD_FN int md_unary (MdCtx& c, int tag, uint32_t base, int n, int early) {                              // scanUnary
+  int i = 0;
+  for (;;) {
+    if (!md_bit (c, tag, base + (uint32_t) (i < n - 1 ? i : n - 1))) return i;
+    i++;
+    if (i == early || i > 64) return i;
+  }
+}
+// scanInt: mirror of CompressionStream::emitInt :523-572 (mantissa size 4)
+MD_FN int md_int (MdCtx& c, uint32_t expo, int n_exp, uint32_t mant, int order, uint32_t zero, uint32_t sign, int tagExp, int tagMant, int tagZero, int tagSign) {
+  if (zero != NO_PRIOR && md_bit (c, tagZero, zero)) return 0;
+  uint32_t positive = 1;
+  if (sign != NO_PRIOR) positive = md_bit (c, tagSign, sign);
+  const int log2 = md_unary (c, tagExp, expo, n_exp, -1);
+  if (log2 > 30) return 0;
+  int lo = 0, hi = 4;
+  uint32_t data_high = 1, low = 0;
+  for (int k = 0; k < log2 + order; k++) {
+    uint32_t bit;
+    if (hi > lo) {
+      const int mid = (hi + lo) >> 1;
+      bit = md_bit (c, tagMant, mant + (uint32_t)mid);
+      if (bit) lo = mid + 1; else hi = mid;
+    } else bit = md_bit (c, tagMant, P_TEST);
+    if (k < log2) data_high = (data_high << 1) | bit; else low = (low << 1) | bit;
+  }
+  const int data = (int) ((((data_high - 1u) << order) | low) + 1u);
+  return positive ? data : -data;
+}
+// scanUEGkInt: mirror of emitUEGkInt :575-591
+MD_FN int md_uegk (MdCtx& c, int threshold, uint32_t p, int n_exp, int order, int tagExp, int tagMant, int tagZero, int tagSign) {
+  if (md_bit (c, tagZero, p + U_ZERO)) return 0;
+  const uint32_t neg = md_bit (c, tagSign, p + U_SIGN);
+  const int u = md_unary (c, tagMant, p + U_FIRST, 4, threshold);
+  int mag = u + 1;
+  if (u >= threshold)
+    mag = 1 + threshold + md_int (c, p + U_EXP, n_exp, p + U_EXP + n_exp, order, p + U_EXP + n_exp + 4, NO_PRIOR, tagExp, tagMant, tagZero, tagSign);
+  return neg ? -mag : mag;
+}
+
+MD_TABLE uint8_t md_zz16[16] = { 0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15 };     // decode_slice.cpp:2035-2040
+MD_TABLE uint8_t md_zz64[64] = {                                                              // decode_slice.cpp:2041-2050
+  0, 1, 5, 6, 14, 15, 27, 28, 2, 4, 7, 13, 16, 26, 29, 42, 3, 8, 12, 17, 25, 30, 41, 43, 9, 11, 18, 24, 31, 40, 44, 53,
+  10, 19, 23, 32, 39, 45, 52, 54, 20, 22, 33, 38, 46, 51, 55, 60, 21, 34, 37, 47, 50, 56, 59, 61, 35, 36, 48, 49, 57, 58, 62, 63 };
+MD_TABLE uint8_t md_scan4[16] = { 0, 1, 4, 5, 2, 3, 6, 7, 8, 9, 12, 13, 10, 11, 14, 15 };    // g_kuiScan4 (z order <-> raster)
+// H.264 scans (Figure 8-8 frame scan; 8x8 zig-zag as read by CAVLC: 4 interleaved 4x4 blocks)
+MD_TABLE uint8_t md_zigzag4[16] = { 0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15 };
+MD_TABLE uint8_t md_zigzag8[64] = {
+  0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
+  35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63 };
+MD_TABLE uint8_t md_cbp_intra[48] = { 47, 31, 15, 0, 23, 27, 29, 30, 7, 11, 13, 14, 39, 43, 45, 46, 16, 3, 5, 10, 12, 19, 21, 26, 28, 35, 37, 42, 44, 1, 2, 4,
+                                      8, 17, 18, 20, 24, 6, 9, 22, 25, 32, 33, 34, 36, 40, 38, 41 };   // Table 9-4
+MD_TABLE uint8_t md_cbp_inter[48] = { 0, 16, 1, 2, 4, 8, 32, 3, 5, 10, 12, 15, 47, 7, 11, 13, 14, 6, 9, 31, 35, 37, 42, 44, 33, 34, 36, 40, 39, 43, 45, 46,
+                                      17, 18, 20, 24, 19, 21, 26, 28, 23, 27, 29, 30, 22, 25, 38, 41 };
+
+// decode4x4<n>: mirror of encode4x4 decode_slice.cpp:2060-2094 (see gen_block in model_kernels.cuh for the prior indexing)
+MD_FN void md_block (MdCtx& c, int16_t* ac, int n, bool emit_dc, int color, uint32_t nzp, uint32_t acbase) {
+  const uint8_t* zz = n == 16 ? md_zz16 : md_zz64;
+  const int tEob = color ? CT_C_EOB : CT_L0_EOB;
+  const int nonzeros = md_int (c, nzp + I_EXP, 3, nzp + I_MANT, 0, nzp + I_ZERO, NO_PRIOR, tEob, tEob, tEob, tEob);
+  int left = nonzeros, emitted = 0, prev = 0, prev2 = 0;
+  for (int i = emit_dc ? 0 : 1; i < n && left > 0; i++) {
+    const int tb = color ? CT_C_BITMASK : (i == 0 ? CT_L0_BITMASK : CT_LN_BITMASK);
+    const int l4 = left < 4 ? left : 4;
+    const int a = prev + 2 < 0 ? 0 : (prev + 2 > 4 ? 4 : prev + 2), b = prev2 + 2 < 0 ? 0 : (prev2 + 2 > 4 ? 4 : prev2 + 2);
+    const uint32_t p = acbase + ((uint32_t) (emitted * 5 + l4) * 25u + (uint32_t)a * 5u + (uint32_t)b) * 16u;
+    const int v = md_uegk (c, 14, p, 2, 0, tb + 1, tb + 2, tb, tb + 3);
+    ac[zz[i]] = (int16_t)v;
+    prev2 = prev; prev = v; emitted++;
+    if (v) left--;
+  }
+}
+
+// ---- bit sink of the re-serialiser ------------------------------------------------------------------------------------
+struct MdBits {
+  uint8_t* out; uint64_t cap_bits, n_bits; uint32_t acc; int n_acc; int overflow;
+};
+MD_FN void mb_init (MdBits& b, uint8_t* out, uint64_t cap_bytes) { b.out = out; b.cap_bits = cap_bytes * 8; b.n_bits = 0; b.acc = 0; b.n_acc = 0; b.overflow = 0; }
+MD_FN void mb_put (MdBits& b, uint32_t v, int n) {              // n <= 24
+  if (n <= 0) return;
+  b.acc = (b.acc << n) | (v & ((1u << n) - 1u));
+  b.n_acc += n;
+  while (b.n_acc >= 8) {
+    if (b.n_bits + 8 > b.cap_bits) { b.overflow = 1; b.n_acc -= 8; continue; }
+    b.out[b.n_bits >> 3] = (uint8_t) (b.acc >> (b.n_acc - 8));
+    b.n_bits += 8; b.n_acc -= 8;
+  }
+}
+MD_FN void mb_put_long (MdBits& b, uint32_t v, int n) { if (n > 16) { mb_put (b, v >> 16, n - 16); mb_put (b, v & 0xffffu, 16); } else mb_put (b, v, n); }
+MD_FN uint64_t mb_bits (const MdBits& b) { return b.n_bits + (uint64_t)b.n_acc; }
+MD_FN void mb_flush (MdBits& b) {                               // left-aligns what is pending into one more byte (not counted in n_bits)
+  if (b.n_acc > 0 && b.n_bits + 8 <= b.cap_bits) b.out[b.n_bits >> 3] = (uint8_t) (b.acc << (8 - b.n_acc));
+}
+MD_FN void mb_ue (MdBits& b, uint32_t v) {
+  const uint32_t x = v + 1u;
+  const int len = 31 - MD_CLZ (x);
+  mb_put (b, 0, len > 24 ? 24 : len);
+  if (len > 24) mb_put (b, 0, len - 24);
+  mb_put_long (b, x, len + 1);
+}
+MD_FN void mb_se (MdBits& b, int v) { mb_ue (b, v > 0 ? (uint32_t) (2 * v - 1) : (uint32_t) (-2 * v)); }
+MD_FN void mb_te (MdBits& b, int range, uint32_t v) { if (range > 1) mb_ue (b, v); else mb_put (b, v ^ 1u, 1); }
+
+// residual_block_cavlc() (7.3.5.3.2 / 9.2) in the writing direction, canonical choices; levels in scan order
+MD_FN void cw_residual_block (MdBits& bw, int nC, int max_coeff, const int16_t* c) {
+  int level[16], run[16], total = 0, last = -1, zeros = 0;
+  for (int i = max_coeff - 1; i >= 0; i--) if (c[i]) { last = i; break; }
+  for (int i = last; i >= 0; i--) {
+    if (c[i]) { level[total] = c[i]; run[total] = 0; total++; }
+    else { run[total - 1]++; zeros++; }
+  }
+  int t1 = 0;
+  while (t1 < total && t1 < 3 && (level[t1] == 1 || level[t1] == -1)) t1++;
+  if (nC < 0) mb_put (bw, kTokCodeC[t1][total], kTokLenC[t1][total]);
+  else if (nC >= 8) mb_put (bw, total == 0 ? 3u : (uint32_t) (((total - 1) << 2) | t1), 6);
+  else { const int t = nC < 2 ? 0 : (nC < 4 ? 1 : 2); mb_put (bw, kTokCode[t][t1][total], kTokLen[t][t1][total]); }
+  if (total == 0) return;
+  for (int i = 0; i < t1; i++) mb_put (bw, level[i] < 0, 1);
+  int suffix_len = (total > 10 && t1 < 3) ? 1 : 0;
+  for (int i = t1; i < total; i++) {
+    const int lv = level[i];
+    int code = lv > 0 ? 2 * lv - 2 : -2 * lv - 1;
+    if (i == t1 && t1 < 3) code -= 2;
+    int rest = -1;                                     // >= 0: escape with level_prefix >= 15
+    if (suffix_len == 0) {
+      if (code < 14) mb_put (bw, 1, code + 1);
+      else if (code < 30) { mb_put (bw, 1, 15); mb_put (bw, (uint32_t) (code - 14), 4); }
+      else rest = code - 30;
+    } else {
+      if (code < (15 << suffix_len)) { mb_put (bw, 1, (code >> suffix_len) + 1); mb_put (bw, (uint32_t)code & ((1u << suffix_len) - 1u), suffix_len); }
+      else rest = code - (15 << suffix_len);
+    }
+    if (rest >= 0) {
+      if (rest < 4096) { mb_put (bw, 1, 16); mb_put (bw, (uint32_t)rest, 12); }
+      else {
+        int prefix = 16;
+        while (rest - ((1 << (prefix - 3)) - 4096) >= (1 << (prefix - 3))) prefix++;
+        mb_put (bw, 1, prefix + 1); mb_put_long (bw, (uint32_t) (rest - ((1 << (prefix - 3)) - 4096)), prefix - 3);
+      }
+    }
+    if (suffix_len == 0) suffix_len = 1;
+    if ((lv < 0 ? -lv : lv) > (3 << (suffix_len - 1)) && suffix_len < 6) suffix_len++;
+  }
+  if (total < max_coeff) {
+    if (nC < 0) mb_put (bw, kTzCodeC[total - 1][zeros], kTzLenC[total - 1][zeros]);
+    else mb_put (bw, kTzCode[total - 1][zeros], kTzLen[total - 1][zeros]);
+  }
+  int zeros_left = zeros;
+  for (int i = 0; i + 1 < total && zeros_left > 0; i++) {
+    const int k = (zeros_left > 7 ? 7 : zeros_left) - 1;
+    mb_put (bw, kRunCode[k][run[i]], kRunLen[k][run[i]]);
+    zeros_left -= run[i];
+  }
+}
+
+// per-slice state of the syntax writer
+struct CwSlice { int slice_type /*0 P, 2 I*/, num_ref_idx_l0, qp, transform_8x8_mode; };
+
+MD_FN int cw_nC (int nA, int nB) { if (nA >= 0 && nB >= 0) return (nA + nB + 1) >> 1; return nA >= 0 ? nA : (nB >= 0 ? nB : 0); }
+
+// macroblock_layer() (7.3.5) for one record; lev = the MB's 384 levels in the layout of the coefficient pool (24 chunks of 16).
+// tc = this MB's total_coeff[24] (written), tcL / tcT = the left / top neighbour's (nullptr when not available, 6.4.8).
+// Returns false for what cannot be expressed (I_PCM).
+MD_FN bool cw_mb (MdBits& bw, const lh264_model_mb& r, const int16_t* lev, CwSlice& s, uint8_t* tc, const uint8_t* tcL, const uint8_t* tcT) {
+  const bool p_slice = s.slice_type == 0;
+  if (p_slice && (r.flags & LH264_MM_EMIT_SKIP_RUN)) mb_ue (bw, r.skip_run);
+  if (!(r.flags & LH264_MM_WRITE_BLOCK)) { for (int i = 0; i < 24; i++) tc[i] = 0; return true; }
+  const int tcode = r.type_code;
+  if (tcode >= 8) return false;
+  const int cbp = r.cbp, cbpL = cbp & 15, cbpC = cbp >> 4;
+  const bool t8 = (r.flags & LH264_MM_T8) != 0;
+  const bool intra = tcode <= 2, i16 = tcode == 1;
+  if (intra) {
+    uint32_t t = 0;
+    if (i16) { const int raw = r.i16_mode > 3 ? 2 : r.i16_mode; t = 1u + (uint32_t)raw + 4u * (uint32_t)cbpC + (cbpL == 15 ? 12u : 0u); }
+    mb_ue (bw, p_slice ? t + 5u : t);
+    if (!i16) {
+      if (s.transform_8x8_mode) mb_put (bw, tcode == 2, 1);
+      const int n = tcode == 2 ? 4 : 16;
+      for (int i = 0; i < n; i++) {
+        const int mode = r.pred_mode[i] & 15, pred = r.pred_mode[i] >> 4;
+        if (mode == pred) mb_put (bw, 1, 1);
+        else { mb_put (bw, 0, 1); mb_put (bw, (uint32_t) (mode < pred ? mode : mode - 1), 3); }
+      }
+    }
+    mb_ue (bw, r.chroma_mode > 3 ? 0u : r.chroma_mode);      // 4..6 are the availability-resolved DC predictors
+  } else {
+    mb_ue (bw, (uint32_t) (tcode - 3));
+    const int nref = s.num_ref_idx_l0;
+    if (tcode == 6 || tcode == 7) {
+      for (int q = 0; q < 4; q++) { const int sb = r.sub_mb_type[q]; mb_ue (bw, sb == 1 ? 0u : (sb == 2 ? 1u : (sb == 4 ? 2u : 3u))); }
+      if (tcode == 6 && nref > 1) for (int q = 0; q < 4; q++) mb_te (bw, nref - 1, (uint32_t)r.ref_idx[q]);
+      for (int q = 0; q < 4; q++) {
+        const int sb = r.sub_mb_type[q], qx = (q & 1) * 2, qy = (q >> 1) * 2;
+        const int cnt = sb == 1 ? 1 : (sb == 8 ? 4 : 2);
+        for (int j = 0; j < cnt; j++) {
+          int bx = qx, by = qy;
+          if (sb == 2) by += j; else if (sb == 4) bx += j; else if (sb == 8) { bx += j & 1; by += j >> 1; }
+          mb_se (bw, r.mvd[by * 4 + bx][0]); mb_se (bw, r.mvd[by * 4 + bx][1]);
+        }
+      }
+    } else if (tcode == 4 || tcode == 5) {
+      if (nref > 1) for (int i = 0; i < 2; i++) mb_te (bw, nref - 1, (uint32_t)r.ref_idx[i]);
+      for (int i = 0; i < 2; i++) { const int b = tcode == 4 ? i * 8 : i * 2; mb_se (bw, r.mvd[b][0]); mb_se (bw, r.mvd[b][1]); }
+    } else {
+      if (nref > 1) mb_te (bw, nref - 1, (uint32_t)r.ref_idx[0]);
+      mb_se (bw, r.mvd[0][0]); mb_se (bw, r.mvd[0][1]);
+    }
+  }
+  if (!i16) {
+    const uint8_t* table = intra ? md_cbp_intra : md_cbp_inter;
+    int code = 0;
+    while (code < 48 && table[code] != cbp) code++;
+    if (code >= 48) return false;
+    mb_ue (bw, (uint32_t)code);
+    if (!intra && (r.flags & LH264_MM_T8_CODED)) mb_put (bw, t8, 1);
+  }
+  if (cbp == 0 && !i16) { for (int i = 0; i < 24; i++) tc[i] = 0; return true; }
+  {
+    int d = (int)r.luma_qp - s.qp;
+    if (d > 25) d -= 52; else if (d < -26) d += 52;
+    mb_se (bw, d);
+    s.qp = r.luma_qp;
+  }
+  int16_t blk[16];
+  if (i16) {
+    for (int i = 0; i < 16; i++) blk[i] = lev[16 * md_scan4[md_zigzag4[i]]];
+    cw_residual_block (bw, cw_nC (tcL ? tcL[3] : -1, tcT ? tcT[12] : -1), 16, blk);
+  }
+  for (int q = 0; q < 4; q++) {
+    if (!(cbpL & (1 << q))) { for (int k = 0; k < 4; k++) tc[md_scan4[4 * q + k]] = 0; continue; }
+    for (int k = 0; k < 4; k++) {
+      const int z = 4 * q + k, rr = md_scan4[z], bx = rr & 3, by = rr >> 2;
+      int n = 0, maxc = 16;
+      if (t8) { for (int i = 0; i < 16; i++) blk[i] = lev[64 * q + md_zigzag8[4 * i + k]]; }
+      else if (i16) { maxc = 15; for (int i = 0; i < 15; i++) blk[i] = lev[16 * z + md_zigzag4[i + 1]]; }
+      else { for (int i = 0; i < 16; i++) blk[i] = lev[16 * z + md_zigzag4[i]]; }
+      for (int i = 0; i < maxc; i++) n += blk[i] != 0;
+      const int nA = bx > 0 ? tc[rr - 1] : (tcL ? tcL[rr + 3] : -1), nB = by > 0 ? tc[rr - 4] : (tcT ? tcT[rr + 12] : -1);
+      cw_residual_block (bw, cw_nC (nA, nB), maxc, blk);
+      tc[rr] = (uint8_t)n;
+    }
+  }
+  if (cbpC) {
+    for (int p = 0; p < 2; p++) {
+      for (int b = 0; b < 4; b++) blk[b] = lev[16 * (16 + 4 * p + b)];
+      cw_residual_block (bw, -1, 4, blk);
+    }
+  }
+  for (int p = 0; p < 2; p++)
+    for (int b = 0; b < 4; b++) {
+      const int base = 16 + 4 * p;
+      if (cbpC & 2) {
+        int n = 0;
+        for (int i = 0; i < 15; i++) { blk[i] = lev[16 * (base + b) + md_zigzag4[i + 1]]; n += blk[i] != 0; }
+        const int nA = (b & 1) ? tc[base + b - 1] : (tcL ? tcL[base + b + 1] : -1), nB = (b & 2) ? tc[base + b - 2] : (tcT ? tcT[base + b + 2] : -1);
+        cw_residual_block (bw, cw_nC (nA, nB), 15, blk);
+        tc[base + b] = (uint8_t)n;
+      } else tc[base + b] = 0;
+    }
+  return true;
+}
+
+// ---- one slice ------------------------------------------------------------------------------------------------------
+// FreqImage::updateFrame (decoded_macroblock.h:120-165), serial form; the CUDA build replaces it by a warp-wide one.
+MD_FN void md_update_frame_serial (CtxRec* f, int len) {
+  int run_start = 0;
+  for (int i = 0; i < len; i++) {
+    bool zeroed = true;
+    for (int k = 0; k < 24; k++) if (f[i].cnt[k]) { zeroed = false; break; }
+    f[i].flags = (uint8_t) (zeroed ? (f[i].flags | 2) : (f[i].flags & ~2));
+    if (!zeroed) {
+      const int run = i - run_start;
+      for (int j = i - run + 1; j <= i && run > 0; j++) f[j].cachedSkips = (uint16_t)run;
+      run_start = i + 1;
+    }
+  }
+}
+// frame flip + resize of WelsDecodeSlice decode_slice.cpp:3032-3046; returns priorValid.  (updateFrame itself runs between
+// md_slice_begin_flip and the rest so that the CUDA build can do it with all lanes.)
+MD_FN CtxRec* md_slice_flip (MdStream& st, int frame_num) {
+  if (frame_num != st.lastFrameId) { st.cur ^= 1; st.lastFrameId = frame_num; }
+  return st.frame[1 - st.cur];
+}
+MD_FN bool md_slice_resize (MdStream& st, int mb_w, int mb_h) {
+  if (st.width == mb_w && st.height == mb_h) return true;
+  const int n = mb_w * mb_h;
+  if (n > st.max_mbs) { st.error = MD_ERR_DIMS; return false; }
+  for (int k = 0; k < 2; k++)
+    for (int j = st.frame_len; j < n; j++) { uint32_t* q = reinterpret_cast<uint32_t*> (&st.frame[k][j]); for (int w = 0; w < 8; w++) q[w] = 0; }
+  for (int j = 0; j < n; j++) st.mb_slice[j] = -1;
+  st.width = mb_w; st.height = mb_h; st.frame_len = n;
+  return false;
+}
+
+struct MdSliceIn {                 // = lh264_decode_slice (include/lh264_b200.h)
+  uint32_t first_mb; int32_t frame_num; uint16_t mb_w, mb_h; uint8_t slice_type, num_ref_idx_l0, slice_qp, flags; uint32_t header_bits;
+};
+
+// Decodes the slice's macroblocks from the side streams and appends their CAVLC syntax to bw.  lev = 384-entry scratch.
+// Returns the number of macroblocks (skipped ones included); st.error is set on failure.
+MD_FN int md_slice (MdStream& st, const MdSliceIn& sl, bool prior_valid, MdBits& bw, int16_t* lev, uint8_t* pad_bits_out, uint8_t* n_pad_out) {
+  MdCtx c = { st.priors, st.rd };
+  const int W = st.width, n_mbs = st.frame_len;
+  CtxRec* cur = st.frame[st.cur];
+  CtxRec* last = st.frame[1 - st.cur];
+  const uint32_t stype = sl.slice_type == 0 ? 0u : 1u;
+  const bool p_slice = sl.slice_type == 0;
+  const bool t8mode = sl.flags & 1, cip = sl.flags & 2;
+  const int slice_no = ++st.slice_counter;
+  CwSlice cs = { sl.slice_type, sl.num_ref_idx_l0, sl.slice_qp, t8mode ? 1 : 0 };
+  int mb_addr = (int)sl.first_mb, mb_in_slice = 0, cached_qp = 0, last_dqp = 0, pending_skips = 0;
+  bool run_known = false, stop = false;
+  lh264_model_mb r;
+  auto avail = [&] (int mb) -> bool { return mb >= 0 && st.mb_slice[mb] == slice_no; };
+  auto avail_intra = [&] (int mb) -> bool { return avail (mb) && (!cip || st.mb_intra[mb]); };
+  while (!stop && mb_addr < n_mbs && !st.error) {
+    const int mbx = mb_addr % W, mby = mb_addr / W;
+    const CtxRec* P = prior_valid && (last[mb_addr].flags & 1) ? &last[mb_addr] : nullptr;
+    { uint32_t* q = reinterpret_cast<uint32_t*> (&r); for (unsigned w = 0; w < sizeof (r) / 4; w++) q[w] = 0; }
+    r.mb_addr = (uint32_t)mb_addr; r.mb_in_slice = (uint16_t) (mb_in_slice < 65535 ? mb_in_slice : 65535);
+    const uint32_t stop_idx = P_STOP + (uint32_t) (mb_in_slice < 2047 ? mb_in_slice : 2047);
+    bool skipped = false;
+    if (pending_skips > 0) skipped = true;
+    else if (!run_known) {                             // mb_skip_run: decode_slice.cpp:2210-2217, getSkipRunPrior macroblock_model.cpp:375-390
+      const int csk = P ? P->cachedSkips : 0;
+      const int prior = csk / 8 + (csk % 8 ? 1 : 0);
+      if (prior >= 512) { st.error = MD_ERR_CONTEXT; break; }
+      const uint32_t run = md_branch (c, CT_SKIP, 9, P_SKIP + (uint32_t)prior * 512u);
+      r.flags |= LH264_MM_EMIT_SKIP_RUN; r.skip_run = (uint16_t)run;
+      if (p_slice && run > 0) {
+        if ((int)run > n_mbs - mb_addr) { st.error = MD_ERR_SYNTAX; break; }
+        pending_skips = (int)run; skipped = true;
+      }
+    }
+    run_known = false;
+    uint8_t* tc = &st.tcoef[(size_t)mb_addr * 24];
+    const bool hasLs = mbx > 0 && avail (mb_addr - 1), hasTs = mby > 0 && avail (mb_addr - W);   // before this MB joins the slice
+    if (skipped) {
+      pending_skips--;
+      if (pending_skips == 0) {                        // last MB of the run: stop bit (:2223-2226); a coded MB follows without a new run
+        r.flags |= LH264_MM_STOP_IN_SKIP;
+        stop = md_bit (c, CT_SKIP_END, stop_idx) != 0;
+        if (stop) r.flags |= LH264_MM_STOP_BIT;
+        run_known = true;
+      }
+      cur[mb_addr] = last[mb_addr];                    // :3105
+      cw_mb (bw, r, lev, cs, tc, nullptr, nullptr);
+      uint8_t* pm = &st.ipm[(size_t)mb_addr * 16];
+      for (int i = 0; i < 16; i++) pm[i] = 2;
+      st.mb_intra[mb_addr] = 0; st.mb_slice[mb_addr] = slice_no;
+      mb_addr++; mb_in_slice++;
+      continue;
+    }
+    // ---- a coded macroblock: decode_slice.cpp:2244-2434 in the reading direction ----
+    r.flags |= LH264_MM_WRITE_BLOCK;
+    const CtxRec* L = mbx > 0 && (cur[mb_addr - 1].flags & 1) ? &cur[mb_addr - 1] : nullptr;          // Neighbors::init macroblock_model.cpp:9-44
+    const CtxRec* A = mby > 0 && (cur[mb_addr - W].flags & 1) ? &cur[mb_addr - W] : nullptr;
+    stop = md_bit (c, CT_SKIP_END, stop_idx) != 0;                                                   // :2252
+    if (stop) r.flags |= LH264_MM_STOP_BIT;
+    int tcd;
+    {
+      int prior = 15, prevType = 15;
+      if (A) prior = A->type_code;
+      if (L) prior = L->type_code;
+      if (P) prevType = P->type_code;
+      tcd = (int)md_branch (c, CT_MB_TYPE, 4, P_MBTYPE + ((uint32_t) (prior + prevType) * 2u + (stype == 0)) * 16u);
+    }
+    if (tcd >= (int)NT) { st.error = MD_ERR_SYNTAX; break; }
+    r.type_code = (uint8_t)tcd;
+    const int cbpC = (int)md_branch (c, CT_CBPL, 2, P_CBPC + ((uint32_t) (P ? P->cbp >> 4 : 0) * NT + tcd) * 4u);
+    const int cbpL = (int)md_branch (c, CT_CBPL, 4, P_CBPL + ((uint32_t) (P ? P->cbp & 15 : 0) * NT + tcd) * 16u);
+    r.cbp = (uint8_t) (cbpL | (cbpC << 4));
+    {
+      const uint32_t cls = last_dqp < 0 ? 0u : (last_dqp == 0 ? 1u : 2u);
+      const uint32_t sw = md_zero_to_pow2 (c, CT_QPL, 7, P_QPL + ((mb_in_slice == 0 ? 3u : 0u) + cls) * 128u, 0);
+      const int d = (sw & 1u) ? - (int) (sw >> 1) - 1 : (int) (sw >> 1);
+      r.qp_delta = (int8_t)d;
+      r.flags |= (uint16_t) (cls << LH264_MM_LASTDQP_SHIFT);
+      r.luma_qp = (uint8_t) (cached_qp + d);
+      cached_qp = r.luma_qp;
+      if (d) last_dqp = d;
+    }
+    int num_ref;
+    {
+      const int pr = P ? P->num_ref : 0;
+      if (pr >= 16) { st.error = MD_ERR_CONTEXT; break; }
+      num_ref = (int)md_branch (c, CT_REF, 4, P_NUMREF + ((uint32_t)pr * NT + tcd) * 16u);
+    }
+    int refBits = 0;
+    while ((1 << refBits) < num_ref) refBits++;
+    {
+      const uint32_t pc = P ? (uint32_t) (P->chroma_mode < 6 ? P->chroma_mode : 6) : 7u;
+      r.chroma_mode = (uint8_t)md_zero_to_pow2 (c, CT_8x8, 3, P_CMODE + pc * 8u, pc);
+      const uint32_t pl = P ? (uint32_t) (P->i16_mode < 6 ? P->i16_mode : 6) : 7u;
+      r.i16_mode = (uint8_t)md_zero_to_pow2 (c, CT_16x16, 3, P_CMODE + pl * 8u, pl);
+    }
+    uint8_t* pm = &st.ipm[(size_t)mb_addr * 16];
+    for (int i = 0; i < 16; i++) pm[i] = 2;
+    if (tcd == 0 || tcd == 2) {                        // Intra4x4 / Intra8x8 prediction modes: 8.3.1.1 / 8.3.2.1
+      const int nL = mbx > 0 ? mb_addr - 1 : -1, nT = mby > 0 ? mb_addr - W : -1, nTL = (mbx > 0 && mby > 0) ? mb_addr - W - 1 : -1;
+      const bool aL = avail_intra (nL), aT = avail_intra (nT), aTL = avail_intra (nTL);
+      const bool i8 = tcd == 2;
+      const int n = i8 ? 4 : 16;
+      for (int i = 0; i < n; i++) {
+        const int rr = i8 ? md_scan4[4 * i] : md_scan4[i], bx = rr & 3, by = rr >> 2;
+        int a, b;
+        bool okA = true, okB = true;
+        if (bx > 0) a = pm[rr - 1]; else if (aL) a = st.ipm[(size_t)nL * 16 + rr + 3]; else { a = 2; okA = false; }
+        if (by > 0) b = pm[rr - 4]; else if (aT) b = st.ipm[(size_t)nT * 16 + rr + 12]; else { b = 2; okB = false; }
+        const int pred = (!okA || !okB) ? 2 : (a < b ? a : b);
+        int mode;
+        if (!i8) {
+          const bool l = bx > 0 ? true : aL, tp = by > 0 ? true : aT;
+          const bool tl = (bx > 0 && by > 0) ? true : (bx > 0 ? aT : (by > 0 ? aL : aTL));
+          const uint32_t av = (l ? 4u : 0u) | (tp ? 2u : 0u) | (tl ? 1u : 0u);
+          r.pred_avail[i] = (uint8_t)av;
+          mode = (int)md_branch (c, CT_PRED_MODE, 4, P_PREDMODE + (((uint32_t)tcd * 8u + av) * 9u + (uint32_t) (pred < 8 ? pred : 8)) * 16u);
+          pm[rr] = (uint8_t)mode;
+        } else {
+          mode = (int)md_branch (c, CT_PRED_MODE, 4, P_PREDMODE + (((uint32_t)tcd * 8u + 6u) * 9u + 1u) * 16u);
+          pm[rr] = pm[rr + 1] = pm[rr + 4] = pm[rr + 5] = (uint8_t)mode;
+        }
+        if (mode > 8) { st.error = MD_ERR_SYNTAX; break; }
+        r.pred_mode[i] = (uint8_t) (mode | (pred << 4));
+      }
+      if (st.error) break;
+    }
+    auto read_mv = [&] (int b) {
+      const uint32_t p = P_MVD + ((uint32_t) (tcd - 3) * 16u + (uint32_t)b) * 16u;
+      r.mvd[b][0] = (int16_t)md_uegk (c, 9, p, 3, 3, CT_MVX, CT_MVX, CT_MVX, CT_MVX);
+      r.mvd[b][1] = (int16_t)md_uegk (c, 9, p, 3, 3, CT_MVY, CT_MVY, CT_MVY, CT_MVY);
+    };
+    bool sub_lt8 = false;
+    if (tcd == 2) {
+      for (int i = 0; i < 4; i++) r.sub_mb_type[i] = (uint8_t)md_branch (c, CT_SUB_MB, 8, P_SUBMB + (uint32_t)tcd * 256u);
+      for (int i = 0; i < 4; i++) r.ref_idx[i] = (int8_t)md_raw (c, CT_REF, refBits);
+    } else if (tcd == 6 || tcd == 7) {
+      for (int i = 0; i < 4; i++) { r.sub_mb_type[i] = (uint8_t)md_branch (c, CT_SUB_MB, 8, P_SUBMB + (uint32_t)tcd * 256u); if (r.sub_mb_type[i] != 1) sub_lt8 = true; }
+      if (tcd == 6) for (int i = 0; i < 4; i++) r.ref_idx[i] = (int8_t)md_raw (c, CT_REF, refBits);
+      for (int i = 0; i < 4 && !st.error; i++) {
+        const int sub = r.sub_mb_type[i];
+        if (sub != 1 && sub != 2 && sub != 4 && sub != 8) { st.error = MD_ERR_SYNTAX; break; }
+        const int cnt = sub == 1 ? 1 : (sub == 8 ? 4 : 2), step = sub == 2 ? 2 : 1;
+        for (int j = 0; j < cnt; j++) read_mv (md_scan4[(i << 2) + j * step]);
+      }
+      if (st.error) break;
+    } else if (tcd == 4 || tcd == 5) {
+      for (int i = 0; i < 2; i++) r.ref_idx[i] = (int8_t)md_raw (c, CT_REF, refBits);
+      for (int i = 0; i < 2; i++) read_mv (tcd == 4 ? i * 8 : i * 2);
+    } else if (tcd == 3) {
+      r.ref_idx[0] = (int8_t)md_raw (c, CT_REF, refBits);
+      read_mv (0);
+    }
+    bool t8 = tcd == 2;
+    if (tcd >= 3 && tcd <= 7 && cbpL && t8mode && !((tcd == 6 || tcd == 7) && sub_lt8)) {               // needParseTransformSize8x8
+      r.flags |= LH264_MM_T8_CODED;
+      t8 = md_bit (c, CT_T8, P_T8 + (uint32_t)tcd * 64u + (uint32_t) (r.luma_qp < 63 ? r.luma_qp : 63)) != 0;
+    }
+    if (t8) r.flags |= LH264_MM_T8;
+    // ---- coefficients ----
+    for (int i = 0; i < 384; i++) lev[i] = 0;
+    uint8_t cnt[24];
+    for (int i = 0; i < 24; i++) cnt[i] = 0;
+    if (tcd == 1)
+      for (int i = 0; i < 16; i++) {
+        const uint32_t p = P_LDC + (((uint32_t)i * 2u + stype) * NT + (uint32_t)tcd) * 16u;
+        lev[16 * i] = (int16_t)md_int (c, p + I_EXP, 3, p + I_MANT, 0, p + I_ZERO, p + I_SIGN, CT_LDC, CT_LDC, CT_LDC, CT_LDC);
+        cnt[i] = lev[16 * i] != 0;
+      }
+    if (cbpC == 1 || cbpC == 2)
+      for (int i = 0; i < 8; i++) {
+        const uint32_t p = P_CDC + (((uint32_t)i * 2u + stype) * NT + (uint32_t)tcd) * 16u;
+        lev[16 * (16 + i)] = (int16_t)md_int (c, p + I_EXP, 3, p + I_MANT, 0, p + I_ZERO, p + I_SIGN, CT_CRDC, CT_CRDC, CT_CRDC, CT_CRDC);
+        cnt[16 + i] = lev[16 * (16 + i)] != 0;
+      }
+    auto count16 = [&] (int chunk) { int n = 0; for (int i = 0; i < 16; i++) n += lev[16 * chunk + i] != 0; cnt[chunk] = (uint8_t)n; };
+    auto m2 = [] (int v) { return (uint32_t) (v < 2 ? v : 2); };
+    const bool emit_ldc = tcd != 1;
+    for (int q = 0; q < 4; q++) {
+      if (!(cbpL & (1 << q))) continue;
+      if (t8) {                                         // getNonzerosPrior8x8 macroblock_model.cpp:529-560
+        const int idx = q * 4;
+        int past = 0, left = 0, above = 0;
+        if (P) past = P->cnt[idx] + P->cnt[idx + 1] + P->cnt[idx + 2] + P->cnt[idx + 3];
+        if ((q & 1) == 0) { if (L) { const int k = (q + 1) * 4; left = L->cnt[k] + L->cnt[k + 1] + L->cnt[k + 2] + L->cnt[k + 3]; } }
+        else { const int k = (q - 1) * 4; left = cnt[k] + cnt[k + 1] + cnt[k + 2] + cnt[k + 3]; }
+        if ((q & 2) == 0) { if (A) { const int k = (q + 2) * 4; above = A->cnt[k] + A->cnt[k + 1] + A->cnt[k + 2] + A->cnt[k + 3]; } }
+        else { const int k = (q - 2) * 4; above = cnt[k] + cnt[k + 1] + cnt[k + 2] + cnt[k + 3]; }
+        if (tcd > 7) { st.error = MD_ERR_CONTEXT; break; }
+        const uint32_t nzp = P_NZ8 + (((stype * NT + (uint32_t)tcd) * 3u + m2 (past)) * 3u + m2 (left)) * 3u * 8u + m2 (above) * 8u;
+        const uint32_t acb = P_AC8 + ((stype * 8u + (uint32_t)tcd) * 64u) * 125u * 16u;
+        md_block (c, lev + 64 * q, 64, emit_ldc, 0, nzp, acb);
+        for (int k = 0; k < 4; k++) count16 (idx + k);
+      } else {
+        for (int k = 0; k < 4; k++) {                   // getNonzerosPrior4x4 macroblock_model.cpp:478-527
+          const int idx = q * 4 + k;
+          int past = 0, left = 0, above = 0;
+          if (P) past = P->cnt[idx];
+          if ((idx & 3) == 0) { if (L) left = L->cnt[idx + 3]; } else left = cnt[idx - 1];
+          if (idx < 4) { if (A) above = A->cnt[idx + 12]; } else above = cnt[idx - 4];
+          const uint32_t nzp = P_NZ + ((((stype * NT + (uint32_t)tcd) * 3u + 0u) * 3u + m2 (past)) * 3u + m2 (left)) * 3u * 8u + m2 (above) * 8u;
+          const uint32_t acb = P_AC + (((stype * 8u + (uint32_t) (tcd < 7 ? tcd : 7)) * 3u + 0u) * 16u) * 125u * 16u;
+          md_block (c, lev + 16 * idx, 16, emit_ldc, 0, nzp, acb);
+          count16 (idx);
+        }
+      }
+    }
+    if (st.error) break;
+    if (cbpC == 2)
+      for (int i = 0; i < 8; i++) {
+        const uint32_t color = i < 4 ? 1u : 2u;
+        int past = 0, left = 0, above = 0;
+        if (P) past = P->cnt[16 + i];
+        if ((i & 1) == 0) { if (L) left = L->cnt[16 + i + 1]; } else left = cnt[16 + i - 1];
+        if ((i & 2) == 0) { if (A) above = A->cnt[16 + i + 2]; } else above = cnt[16 + i - 2];
+        const uint32_t nzp = P_NZ + ((((stype * NT + (uint32_t)tcd) * 3u + color) * 3u + m2 (past)) * 3u + m2 (left)) * 3u * 8u + m2 (above) * 8u;
+        const uint32_t acb = P_AC + (((stype * 8u + (uint32_t) (tcd < 7 ? tcd : 7)) * 3u + color) * 16u) * 125u * 16u;
+        md_block (c, lev + 16 * (16 + i), 16, false, (int)color, nzp, acb);
+        count16 (16 + i);
+      }
+    // ---- FreqImage store (:3107) ----
+    {
+      CtxRec& o = cur[mb_addr];
+      o.flags = 1; o.type_code = (uint8_t)tcd; o.cbp = r.cbp; o.num_ref = (uint8_t)num_ref; o.chroma_mode = r.chroma_mode; o.i16_mode = r.i16_mode;
+      o.cachedSkips = 0;
+      for (int i = 0; i < 24; i++) o.cnt[i] = cnt[i];
+    }
+    // ---- CAVLC ----
+    if (tcd >= 8) { st.error = MD_ERR_PCM; break; }
+    if (!cw_mb (bw, r, lev, cs, tc, hasLs ? &st.tcoef[(size_t) (mb_addr - 1) * 24] : nullptr, hasTs ? &st.tcoef[(size_t) (mb_addr - W) * 24] : nullptr)) { st.error = MD_ERR_SYNTAX; break; }
+    if (bw.overflow) { st.error = MD_ERR_OUT_FULL; break; }
+    st.mb_intra[mb_addr] = tcd <= 2; st.mb_slice[mb_addr] = slice_no;
+    mb_addr++; mb_in_slice++;
+  }
+  // slice trailing alignment bits (decode_slice.cpp:3133-3147): coded through TEST_PROB into the PADBYTE stream
+  const int n_pad = 7 - (int) ((sl.header_bits + mb_bits (bw)) & 7u);
+  *n_pad_out = (uint8_t)n_pad;
+  *pad_bits_out = (uint8_t) (n_pad && !st.error ? md_raw (c, CT_PAD, n_pad) : 0u);
+  return mb_addr - (int)sl.first_mb;
+}
+
+} // namespace lh264md

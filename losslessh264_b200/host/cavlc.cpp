@@ -1,5 +1,6 @@
 // cavlc.cpp — see cavlc.h.
 #include "cavlc.h"
+#include "cavlc_tables.h"
 #include <string.h>
 #include <vector>
 #include <mutex>
@@ -10,86 +11,6 @@ const uint8_t kZigzag4x4[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14
 const uint8_t kZigzag8x8[64] = {
   0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
   35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63
-};
-
-// ---- Table 9-5: coeff_token, [table][trailing_ones][total_coeff] -----------------------------------
-static const uint8_t kTokLen[3][4][17] = {
-  { { 1, 6, 8, 9, 10, 11, 13, 13, 13, 14, 14, 15, 15, 16, 16, 16, 16},
-    { 0, 2, 6, 8, 9, 10, 11, 13, 13, 14, 14, 15, 15, 15, 16, 16, 16},
-    { 0, 0, 3, 7, 8, 9, 10, 11, 13, 13, 14, 14, 15, 15, 16, 16, 16},
-    { 0, 0, 0, 5, 6, 7, 8, 9, 10, 11, 13, 14, 14, 15, 15, 16, 16} },
-  { { 2, 6, 6, 7, 8, 8, 9, 11, 11, 12, 12, 12, 13, 13, 13, 14, 14},
-    { 0, 2, 5, 6, 6, 7, 8, 9, 11, 11, 12, 12, 13, 13, 14, 14, 14},
-    { 0, 0, 3, 6, 6, 7, 8, 9, 11, 11, 12, 12, 13, 13, 13, 14, 14},
-    { 0, 0, 0, 4, 4, 5, 6, 6, 7, 9, 11, 11, 12, 13, 13, 13, 14} },
-  { { 4, 6, 6, 6, 7, 7, 7, 7, 8, 8, 9, 9, 9, 10, 10, 10, 10},
-    { 0, 4, 5, 5, 5, 5, 6, 6, 7, 8, 8, 9, 9, 9, 10, 10, 10},
-    { 0, 0, 4, 5, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 10},
-    { 0, 0, 0, 4, 4, 4, 4, 4, 5, 6, 7, 8, 8, 9, 10, 10, 10} },
-};
-static const uint8_t kTokCode[3][4][17] = {
-  { { 1, 5, 7, 7, 7, 7, 15, 11, 8, 15, 11, 15, 11, 15, 11, 7, 4},
-    { 0, 1, 4, 6, 6, 6, 6, 14, 10, 14, 10, 14, 10, 1, 14, 10, 6},
-    { 0, 0, 1, 5, 5, 5, 5, 5, 13, 9, 13, 9, 13, 9, 13, 9, 5},
-    { 0, 0, 0, 3, 3, 4, 4, 4, 4, 4, 12, 12, 8, 12, 8, 12, 8} },
-  { { 3, 11, 7, 7, 7, 4, 7, 15, 11, 15, 11, 8, 15, 11, 7, 9, 7},
-    { 0, 2, 7, 10, 6, 6, 6, 6, 14, 10, 14, 10, 14, 10, 11, 8, 6},
-    { 0, 0, 3, 9, 5, 5, 5, 5, 13, 9, 13, 9, 13, 9, 6, 10, 5},
-    { 0, 0, 0, 5, 4, 6, 8, 4, 4, 4, 12, 8, 12, 12, 8, 1, 4} },
-  { { 15, 15, 11, 8, 15, 11, 9, 8, 15, 11, 15, 11, 8, 13, 9, 5, 1},
-    { 0, 14, 15, 12, 10, 8, 14, 10, 14, 14, 10, 14, 10, 7, 12, 8, 4},
-    { 0, 0, 13, 14, 11, 9, 13, 9, 13, 10, 13, 9, 13, 9, 11, 7, 3},
-    { 0, 0, 0, 12, 11, 10, 9, 8, 13, 12, 12, 12, 8, 12, 10, 6, 2} },
-};
-// chroma DC (4:2:0) coeff_token, [trailing_ones][total_coeff]
-static const uint8_t kTokLenC[4][5] = { {2, 6, 6, 6, 6}, {0, 1, 6, 7, 8}, {0, 0, 3, 7, 8}, {0, 0, 0, 6, 7} };
-static const uint8_t kTokCodeC[4][5] = { {1, 7, 4, 3, 2}, {0, 1, 6, 3, 3}, {0, 0, 1, 2, 2}, {0, 0, 0, 5, 0} };
-
-// ---- Tables 9-7 / 9-8: total_zeros, [total_coeff-1][total_zeros] ------------------------------------------
-static const uint8_t kTzLen[15][16] = {
-  {1, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 9},
-  {3, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 6, 6, 6, 6},
-  {4, 3, 3, 3, 4, 4, 3, 3, 4, 5, 5, 6, 5, 6},
-  {5, 3, 4, 4, 3, 3, 3, 4, 3, 4, 5, 5, 5},
-  {4, 4, 4, 3, 3, 3, 3, 3, 4, 5, 4, 5},
-  {6, 5, 3, 3, 3, 3, 3, 3, 4, 3, 6},
-  {6, 5, 3, 3, 3, 2, 3, 4, 3, 6},
-  {6, 4, 5, 3, 2, 2, 3, 3, 6},
-  {6, 6, 4, 2, 2, 3, 2, 5},
-  {5, 5, 3, 2, 2, 2, 4},
-  {4, 4, 3, 3, 1, 3},
-  {4, 4, 2, 1, 3},
-  {3, 3, 1, 2},
-  {2, 2, 1},
-  {1, 1},
-};
-static const uint8_t kTzCode[15][16] = {
-  {1, 3, 2, 3, 2, 3, 2, 3, 2, 3, 2, 3, 2, 3, 2, 1},
-  {7, 6, 5, 4, 3, 5, 4, 3, 2, 3, 2, 3, 2, 1, 0},
-  {5, 7, 6, 5, 4, 3, 4, 3, 2, 3, 2, 1, 1, 0},
-  {3, 7, 5, 4, 6, 5, 4, 3, 3, 2, 2, 1, 0},
-  {5, 4, 3, 7, 6, 5, 4, 3, 2, 1, 1, 0},
-  {1, 1, 7, 6, 5, 4, 3, 2, 1, 1, 0},
-  {1, 1, 5, 4, 3, 3, 2, 1, 1, 0},
-  {1, 1, 1, 3, 3, 2, 2, 1, 0},
-  {1, 0, 1, 3, 2, 1, 1, 1},
-  {1, 0, 1, 3, 2, 1, 1},
-  {0, 1, 1, 2, 1, 3},
-  {0, 1, 1, 1, 1},
-  {0, 1, 1, 1},
-  {0, 1, 1},
-  {0, 1},
-};
-static const uint8_t kTzLenC[3][4] = { {1, 2, 3, 3}, {1, 2, 2, 0}, {1, 1, 0, 0} };
-static const uint8_t kTzCodeC[3][4] = { {1, 1, 1, 0}, {1, 1, 0, 0}, {1, 0, 0, 0} };
-// ---- Table 9-10: run_before, [min(zeros_left,7)-1][run_before] ------------------------------------------------
-static const uint8_t kRunLen[7][15] = {
-  {1, 1}, {1, 2, 2}, {2, 2, 2, 2}, {2, 2, 2, 3, 3}, {2, 2, 3, 3, 3, 3}, {2, 3, 3, 3, 3, 3, 3},
-  {3, 3, 3, 3, 3, 3, 3, 4, 5, 6, 7, 8, 9, 10, 11},
-};
-static const uint8_t kRunCode[7][15] = {
-  {1, 0}, {1, 1, 0}, {3, 2, 1, 0}, {3, 2, 1, 1, 0}, {3, 2, 3, 2, 1, 0}, {3, 0, 1, 3, 2, 5, 4},
-  {7, 6, 5, 4, 3, 2, 1, 1, 1, 1, 1, 1, 1, 1, 1},
 };
 
 // the (length, code) tables, for the writing direction (cavlc_writer.cpp)

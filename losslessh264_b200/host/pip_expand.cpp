@@ -1,0 +1,120 @@
+// pip_expand.cpp — see pip_expand.h.
+#include "pip_expand.h"
+#include "pip_container.h"
+#include "h264_syntax.h"
+#include <string.h>
+
+namespace lh264host {
+
+namespace {
+struct Bits {                                          // RBSP under construction
+  std::vector<uint8_t> buf; size_t n = 0;
+  void bit (uint32_t b) { if ((n & 7) == 0) buf.push_back (0); if (b) buf.back() |= (uint8_t) (0x80u >> (n & 7)); n++; }
+  void copy (const uint8_t* src, size_t first_bit, size_t count) {
+    size_t i = 0;
+    if ((n & 7) == 0 && (first_bit & 7) == 0) {        // byte-aligned fast path
+      const size_t bytes = count >> 3;
+      buf.insert (buf.end(), src + (first_bit >> 3), src + (first_bit >> 3) + bytes);
+      n += bytes * 8; i = bytes * 8;
+    }
+    for (; i < count; i++) { const size_t a = first_bit + i; bit ((src[a >> 3] >> (7 - (a & 7))) & 1u); }
+  }
+};
+size_t start_code_end (const uint8_t* u, size_t len) {
+  for (size_t k = 0; k + 3 <= len; k++) if (u[k] == 0 && u[k + 1] == 0 && u[k + 2] == 1) return k + 3;
+  return 0;
+}
+} // namespace
+
+bool expand_plan (const uint8_t* def_in, size_t n, ExpandPlan& plan) {
+  plan = ExpandPlan();
+  std::vector<uint8_t> def (def_in, def_in + n);
+  static const uint8_t kStart[4] = {0, 0, 0, 1};
+  def.insert (def.end(), kStart, kStart + 4);           // sentinel for next_unit (h264dec.cpp:238)
+  std::vector<Sps> sps (32);
+  std::vector<Pps> pps (256);
+  std::vector<uint8_t> nal;
+  auto literal = [&] (size_t off, size_t len) {
+    if (!len) return;
+    if (!plan.pieces.empty() && plan.pieces.back().slice < 0 && plan.pieces.back().def_off + plan.pieces.back().def_len == off) plan.pieces.back().def_len += len;
+    else { ExpandPiece p; p.def_off = off; p.def_len = len; plan.pieces.push_back (p); }
+  };
+  for (size_t pos = 0; pos < n;) {
+    const size_t len = PipBoilerplate::next_unit (def.data(), pos, n);
+    const uint8_t* u = def.data() + pos;
+    const size_t off = len >= 4 ? start_code_end (u, len) : 0;
+    if (off == 0 || off >= len) { literal (pos, len); pos += len; continue; }
+    const size_t plen = unescape_nal (u + off, len - off, nal);
+    const int type = nal[0] & 31, ref_idc = (nal[0] >> 5) & 3;
+    const bool forbidden = nal[0] & 0x80;
+    if (forbidden || plen < 1) { literal (pos, len); pos += len; continue; }
+    if (type == NAL_SPS) {
+      BitReader br (nal.data() + 1, plen - 1);
+      Sps s;
+      if (parse_sps (br, s)) { sps[s.id] = s; if (s.mb_w * s.mb_h > plan.max_mbs) plan.max_mbs = s.mb_w * s.mb_h; }
+      literal (pos, len);
+    } else if (type == NAL_PPS) {
+      BitReader br (nal.data() + 1, plen - 1);
+      Pps p;
+      if (parse_pps (br, p, sps.data())) { pps[p.id] = p; if (p.transform_8x8_mode) plan.with_8x8 = true; }
+      literal (pos, len);
+    } else if (type == NAL_SLICE || type == NAL_IDR) {
+      if (plen < 2) { plan.error = "a slice was dropped at compression time (only its NAL header is in the default stream)"; return false; }
+      BitReader br (nal.data() + 1, plen - 1);
+      SliceHeader sh;
+      if (parse_slice_header (br, ref_idc, type, sps.data(), pps.data(), sh) < 0) { plan.error = "slice header does not parse"; return false; }
+      const Pps& pp = pps[sh.pps_id];
+      const Sps& sp = sps[pp.sps_id];
+      if (pp.cabac) { plan.error = "CABAC slice: not built (SURVEY 8f N3)"; return false; }
+      // the header is followed by exactly one stop bit and zero padding (pip_container.cpp: unit_end)
+      const uint8_t* rb = nal.data() + 1;
+      const size_t hb = sh.header_bits, rl = plen - 1;
+      bool ok = (hb >> 3) < rl && ((rb[hb >> 3] >> (7 - (hb & 7))) & 1u) && (hb + 8) / 8 == rl;
+      if (ok) ok = (rb[hb >> 3] & ((1u << (7 - (hb & 7))) - 1u)) == 0;
+      if (!ok) { plan.error = "slice unit of the default stream is not <header bits><stop bit> (trailing zero bytes in the original NAL?)"; return false; }
+      if (sh.slice_type != SLICE_P && sh.slice_type != SLICE_I) { plan.error = "B/SP/SI slice"; return false; }
+      lh264_decode_slice ds;
+      memset (&ds, 0, sizeof (ds));
+      ds.first_mb = (uint32_t)sh.first_mb; ds.frame_num = sh.frame_num;
+      ds.mb_w = (uint16_t)sp.mb_w; ds.mb_h = (uint16_t)sp.mb_h;
+      ds.slice_type = (uint8_t) (sh.slice_type == SLICE_I ? 2 : 0);
+      ds.num_ref_idx_l0 = (uint8_t) (sh.slice_type == SLICE_P ? sh.num_ref_idx_l0 : pp.num_ref_idx_l0_default);
+      ds.slice_qp = (uint8_t)sh.slice_qp;
+      ds.flags = (uint8_t) ((pp.transform_8x8_mode ? 1 : 0) | (pp.constrained_intra_pred ? 2 : 0));
+      ds.header_bits = (uint32_t)hb;
+      literal (pos, off);
+      ExpandPiece p; p.def_off = pos + off; p.def_len = len - off; p.slice = (int)plan.slices.size();
+      plan.pieces.push_back (p);
+      plan.slices.push_back (ds);
+    } else literal (pos, len);
+    pos += len;
+  }
+  return true;
+}
+
+bool expand_assemble (const ExpandPlan& plan, const uint8_t* def, const uint8_t* slice_bits, const lh264_decode_slice_out* outs, std::vector<uint8_t>& out) {
+  std::vector<uint8_t> nal;
+  for (const ExpandPiece& p : plan.pieces) {
+    if (p.slice < 0) { out.insert (out.end(), def + p.def_off, def + p.def_off + p.def_len); continue; }
+    const lh264_decode_slice& ds = plan.slices[p.slice];
+    const lh264_decode_slice_out& so = outs[p.slice];
+    unescape_nal (def + p.def_off, p.def_len, nal);
+    Bits b;
+    b.buf.reserve (ds.header_bits / 8 + so.n_bits / 8 + 8);
+    b.copy (nal.data() + 1, 0, ds.header_bits);
+    b.copy (slice_bits + so.byte_offset, 0, so.n_bits);
+    b.bit (1);
+    for (int i = so.n_pad_bits - 1; i >= 0; i--) b.bit ((so.pad_bits >> i) & 1u);
+    if (b.n & 7) return false;
+    out.push_back (nal[0]);
+    int zeros = 0;                                     // emulation prevention (7.4.1)
+    for (uint8_t x : b.buf) {
+      if (zeros >= 2 && x <= 3) { out.push_back (3); zeros = 0; }
+      out.push_back (x);
+      zeros = x == 0 ? zeros + 1 : 0;
+    }
+  }
+  return true;
+}
+
+} // namespace lh264host
