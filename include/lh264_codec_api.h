@@ -114,6 +114,24 @@ int WelsGetDecoderCapability (SDecoderCapability* pDecCapability);
 OpenH264Version WelsGetCodecVersion (void);
 void WelsGetCodecVersionEx (OpenH264Version* pVersion);
 
+/* ---- Extension of this library (not in OpenH264): the `.pip` container in the decompress direction -------------------
+ * What the reference's h264dec does around the model when its INPUT name contains ".pip" (h264dec.cpp:170-173), split at
+ * the hot-path boundary so that many files can share one lh264_model_decode() call (include/lh264_b200.h):
+ *   plan     = lh264_pip_plan (default stream)            parameter sets + slice headers -> lh264_decode_slice list
+ *   lh264_model_decode (ctx, jobs ...)                    side streams -> slice_data() bits, on the GPU
+ *   lh264_pip_assemble (plan, default stream, bits ...)   -> the original Annex-B file                                  */
+struct lh264_decode_slice;
+struct lh264_decode_slice_out;
+typedef struct lh264_pip_plan_s lh264_pip_plan_t;
+/* NULL on failure, with the reason in err (CABAC slices, slices dropped at compression time ...) */
+lh264_pip_plan_t* lh264_pip_plan (const unsigned char* default_stream, size_t len, char* err, size_t err_cap);
+void lh264_pip_plan_free (lh264_pip_plan_t* plan);
+/* slices of the plan (n_slices of them), and what lh264_decode_job needs: max_mbs, with_8x8 */
+const struct lh264_decode_slice* lh264_pip_plan_slices (const lh264_pip_plan_t* plan, int* n_slices, int* max_mbs, int* with_8x8);
+/* returns the length of the expanded file (copied into dst when it fits in cap), or -1 */
+long long lh264_pip_assemble (const lh264_pip_plan_t* plan, const unsigned char* default_stream, const unsigned char* slice_bits,
+                              const struct lh264_decode_slice_out* outs, unsigned char* dst, size_t cap);
+
 #ifdef __cplusplus
 }
 #endif

@@ -28,7 +28,24 @@ EXPORTS = [
     "lh264_k_expand_plane",
     "lh264_model_open", "lh264_model_close", "lh264_model_submit", "lh264_model_finish", "lh264_model_read",
     "lh264_model_decisions", "lh264_model_batch_upload", "lh264_model_batch_run", "lh264_model_batch_free",
+    "lh264_model_decode",
 ]
+
+
+class DecodeSlice(C.Structure):       # lh264_decode_slice
+    _fields_ = [("first_mb", C.c_uint32), ("frame_num", C.c_int32), ("mb_w", C.c_uint16), ("mb_h", C.c_uint16), ("slice_type", C.c_uint8),
+                ("num_ref_idx_l0", C.c_uint8), ("slice_qp", C.c_uint8), ("flags", C.c_uint8), ("header_bits", C.c_uint32)]
+
+
+class DecodeSliceOut(C.Structure):    # lh264_decode_slice_out
+    _fields_ = [("byte_offset", C.c_uint64), ("n_bits", C.c_uint32), ("n_mbs", C.c_uint32), ("n_pad_bits", C.c_uint8), ("pad_bits", C.c_uint8),
+                ("reserved", C.c_uint16), ("reserved2", C.c_uint32)]
+
+
+class DecodeJob(C.Structure):         # lh264_decode_job
+    _fields_ = [("max_mbs", C.c_int32), ("with_8x8", C.c_int32), ("tag_data", C.c_void_p * NUM_TAGS), ("tag_len", C.c_uint32 * NUM_TAGS),
+                ("slices", C.c_void_p), ("n_slices", C.c_int32), ("error", C.c_int32), ("out", C.c_void_p), ("out_capacity", C.c_uint64),
+                ("slice_out", C.c_void_p)]
 
 
 class PictureDesc(C.Structure):
@@ -87,6 +104,7 @@ def load_library():
     lib.lh264_kernel_launches.argtypes = [C.c_void_p]
     lib.lh264_kernel_ms.argtypes = [C.c_void_p, C.c_int]
     lib.lh264_sync.argtypes = [C.c_void_p]
+    lib.lh264_model_decode.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
     lib.lh264_join.argtypes = [C.c_void_p]
     lib.lh264_inputs_consumed.argtypes = [C.c_void_p]
     lib.lh264_output_wait.argtypes = [C.c_void_p]
@@ -290,6 +308,40 @@ class Context:
 
     def model_decisions(self, ms):
         return int(self.lib.lh264_model_decisions(self.h, ms))
+
+    def model_decode(self, streams, out_capacity=None):
+        """Decompress direction: one job per stream, all jobs concurrently on the GPU (lh264_model_decode).
+        streams: list of dicts {tags: {tag id: bytes}, slices: ctypes array of DecodeSlice (or pointer + n_slices), max_mbs, with_8x8}.
+        Returns a list of (bits: np.uint8 array, outs: ctypes array of DecodeSliceOut) — or raises; a job that needs a larger
+        output buffer is retried with twice the capacity."""
+        n = len(streams)
+        caps = [int(out_capacity or (4 * sum(len(b) for b in s["tags"].values()) + (1 << 20))) for s in streams]
+        while True:
+            jobs = (DecodeJob * n)()
+            keep = []
+            bits, outs = [], []
+            for j, s in enumerate(streams):
+                job = jobs[j]
+                job.max_mbs = int(s["max_mbs"]); job.with_8x8 = int(bool(s.get("with_8x8", True)))
+                for t, b in s["tags"].items():
+                    buf = np.frombuffer(bytes(b) + b"\0", np.uint8)
+                    keep.append(buf)
+                    job.tag_data[int(t)] = buf.ctypes.data; job.tag_len[int(t)] = len(b)
+                ns = int(s["n_slices"])
+                job.slices = C.cast(s["slices"], C.c_void_p).value if ns else None
+                job.n_slices = ns
+                o = np.zeros(caps[j], np.uint8)
+                so = (DecodeSliceOut * max(ns, 1))()
+                bits.append(o); outs.append(so)
+                job.out = o.ctypes.data; job.out_capacity = caps[j]; job.slice_out = C.cast(so, C.c_void_p).value
+            rc = self.lib.lh264_model_decode(self.h, jobs, n)
+            small = [j for j in range(n) if jobs[j].error == 22]
+            if rc != 0 and small and all(jobs[j].error in (0, 22) for j in range(n)):
+                for j in small:
+                    caps[j] *= 2
+                continue
+            _check(self.lib, rc)
+            return list(zip(bits, outs))
 
     # ---- kernel-level entry points ---------------------------------------------------------------
     def k_idct4x4_add(self, pix, coef):

@@ -2,6 +2,7 @@
 // Mirrors the reference CLI contract (codec/console/dec/src/h264dec.cpp:123-402, :407-564):
 //   h264dec <in.264> <out.yuv>           decode, write cropped I420 frames
 //   h264dec <in.264> <out.pip> [yuv]     compress: decode + recompression model; writes out.pip and out.pip.<tag>
+//   h264dec <in.pip> <out.264>           decompress: in.pip + in.pip.<tag> -> the original Annex-B file, byte for byte
 // one NAL unit per DecodeFrameNoDelay call (3- or 4-byte start codes), the same getters queried
 // after every call, the same "iWidth/height/Frames/decode time/FPS" block on stderr.
 // The .pip compress/decompress modes are selected by file-name suffix exactly like the reference
@@ -13,6 +14,8 @@
 #include <vector>
 #include "../../include/lh264_codec_api.h"
 #include "pip_container.h"
+#include "pip_expand.h"
+#include <string>
 
 static void write_frame (FILE* f, unsigned char** d, const SBufferInfo& bi) {
   const int w = bi.UsrData.sSystemBuffer.iWidth, h = bi.UsrData.sSystemBuffer.iHeight;
@@ -21,10 +24,68 @@ static void write_frame (FILE* f, unsigned char** d, const SBufferInfo& bi) {
   for (int p = 1; p < 3; p++) for (int y = 0; y < h / 2; y++) fwrite (d[p] + (size_t)y * sc, 1, w / 2, f);
 }
 
+static bool slurp (const std::string& path, std::vector<uint8_t>& out) {
+  FILE* f = fopen (path.c_str(), "rb");
+  if (!f) return false;
+  uint8_t tmp[65536];
+  size_t n;
+  out.clear();
+  while ((n = fread (tmp, 1, sizeof (tmp), f)) > 0) out.insert (out.end(), tmp, tmp + n);
+  fclose (f);
+  return true;
+}
+
+// Round-trip mode of the reference CLI (isRecoding, h264dec.cpp:170-173): the default stream gives the NAL skeleton and the
+// slice headers, the side streams go through the model on the GPU (lh264_model_decode), the host frames the result.
+static int decompress (const char* pip_path, const char* out_path) {
+  std::vector<uint8_t> def;
+  if (!slurp (pip_path, def)) { perror (pip_path); return 1; }
+  std::vector<std::vector<uint8_t> > tags (LH264_NUM_TAGS);
+  lh264_decode_job job;
+  memset (&job, 0, sizeof (job));
+  size_t total = def.size();
+  for (int t = 0; t < LH264_NUM_TAGS; t++)
+    if (slurp (std::string (pip_path) + "." + std::to_string (t), tags[t])) {
+      tags[t].push_back (0);
+      job.tag_data[t] = tags[t].data(); job.tag_len[t] = (uint32_t)tags[t].size() - 1; total += tags[t].size();
+    }
+  lh264host::ExpandPlan plan;
+  if (!lh264host::expand_plan (def.data(), def.size(), plan)) { fprintf (stderr, "cannot expand %s: %s\n", pip_path, plan.error.c_str()); return 3; }
+  lh264_ctx* ctx = nullptr;
+  if (lh264_ctx_create (&ctx, 0, nullptr) != LH264_OK) { fprintf (stderr, "%s (this build has no CPU fallback)\n", lh264_last_error()); return 1; }
+  std::vector<lh264_decode_slice_out> outs (plan.slices.size() + 1);
+  std::vector<uint8_t> bits;
+  const auto t0 = std::chrono::steady_clock::now();
+  int rc = LH264_OK;
+  for (size_t cap = total * 4 + (1u << 20);; cap *= 2) {
+    bits.assign (cap, 0);
+    job.max_mbs = plan.max_mbs > 0 ? plan.max_mbs : 1; job.with_8x8 = plan.with_8x8;
+    job.slices = plan.slices.data(); job.n_slices = (int)plan.slices.size();
+    job.out = bits.data(); job.out_capacity = bits.size(); job.slice_out = outs.data();
+    rc = lh264_model_decode (ctx, &job, 1);
+    if (job.error != 22) break;                        // 22: output buffer too small
+  }
+  const double secs = std::chrono::duration<double> (std::chrono::steady_clock::now() - t0).count();
+  if (rc != LH264_OK) { fprintf (stderr, "model decode failed: %s\n", lh264_last_error()); lh264_ctx_destroy (ctx); return 4; }
+  std::vector<uint8_t> out;
+  const float kms = lh264_kernel_ms (ctx, 6);
+  const bool ok = lh264host::expand_assemble (plan, def.data(), bits.data(), outs.data(), out);
+  lh264_ctx_destroy (ctx);
+  if (!ok) { fprintf (stderr, "assembly failed\n"); return 5; }
+  FILE* fo = fopen (out_path, "wb");
+  if (!fo) { perror (out_path); return 1; }
+  fwrite (out.data(), 1, out.size(), fo);
+  fclose (fo);
+  fprintf (stderr, "-------------------------------------------------------\n");
+  fprintf (stderr, "slices:\t\t%zu\noutput bytes:\t%zu\nmodel decode time:\t%f sec (k_model_decode %.3f ms)\n", plan.slices.size(), out.size(), secs, (double)kms);
+  fprintf (stderr, "-------------------------------------------------------\n");
+  return 0;
+}
+
 int main (int argc, char** argv) {
-  if (argc < 3) { fprintf (stderr, "usage: %s <in.264> <out.yuv> | <in.264> <out.pip> [out.yuv]\n", argv[0]); return 1; }
+  if (argc < 3) { fprintf (stderr, "usage: %s <in.264> <out.yuv> | <in.264> <out.pip> [out.yuv] | <in.pip> <out.264>\n", argv[0]); return 1; }
   const bool compress = strstr (argv[2], ".pip") != nullptr;             // h264dec.cpp:167-169
-  if (!compress && strstr (argv[1], ".pip")) { fprintf (stderr, "decompression (.pip -> .264) is not built into this binary yet (SURVEY 8f N1)\n"); return 2; }
+  if (!compress && strstr (argv[1], ".pip")) return decompress (argv[1], argv[2]);                        // h264dec.cpp:170-173
   const char* yuv_path = compress ? (argc > 3 ? argv[3] : "/dev/null") : argv[2];
   FILE* fi = fopen (argv[1], "rb");
   if (!fi) { perror (argv[1]); return 1; }

@@ -118,3 +118,33 @@ bool expand_assemble (const ExpandPlan& plan, const uint8_t* def, const uint8_t*
 }
 
 } // namespace lh264host
+
+// ---- C entry points (include/lh264_codec_api.h) ---------------------------------------------------------------------
+struct lh264_pip_plan_s { lh264host::ExpandPlan plan; };
+extern "C" {
+lh264_pip_plan_s* lh264_pip_plan (const unsigned char* def, size_t len, char* err, size_t err_cap) {
+  lh264_pip_plan_s* p = new lh264_pip_plan_s();
+  if (!lh264host::expand_plan (def, len, p->plan)) {
+    if (err && err_cap) { strncpy (err, p->plan.error.c_str(), err_cap - 1); err[err_cap - 1] = 0; }
+    delete p;
+    return nullptr;
+  }
+  return p;
+}
+void lh264_pip_plan_free (lh264_pip_plan_s* p) { delete p; }
+const lh264_decode_slice* lh264_pip_plan_slices (const lh264_pip_plan_s* p, int* n_slices, int* max_mbs, int* with_8x8) {
+  if (!p) return nullptr;
+  if (n_slices) *n_slices = (int)p->plan.slices.size();
+  if (max_mbs) *max_mbs = p->plan.max_mbs;
+  if (with_8x8) *with_8x8 = p->plan.with_8x8 ? 1 : 0;
+  return p->plan.slices.data();
+}
+long long lh264_pip_assemble (const lh264_pip_plan_s* p, const unsigned char* def, const unsigned char* bits, const lh264_decode_slice_out* outs,
+                              unsigned char* dst, size_t cap) {
+  if (!p) return -1;
+  std::vector<uint8_t> out;
+  if (!lh264host::expand_assemble (p->plan, def, bits, outs, out)) return -1;
+  if (dst && out.size() <= cap) memcpy (dst, out.data(), out.size());
+  return (long long)out.size();
+}
+}

@@ -24,6 +24,20 @@ def build(force=False):
     return so
 
 
+def build_expand_checker(force=False):
+    """oracle/expand_cpu: CPU build of the decompress core the CUDA kernel runs (oracle/model_decode_cpu.cpp)."""
+    root = os.path.dirname(_HERE)
+    host = os.path.join(root, "losslessh264_b200", "host")
+    exe = os.path.join(_HERE, "expand_cpu")
+    srcs = [os.path.join(_HERE, "model_decode_cpu.cpp")] + [os.path.join(host, f) for f in ("pip_expand.cpp", "pip_container.cpp", "h264_syntax.cpp")]
+    deps = srcs + [os.path.join(root, "include", "lh264_b200.h"), os.path.join(host, "cavlc_tables.h"), os.path.join(host, "pip_expand.h"),
+                   os.path.join(root, "losslessh264_b200", "csrc", "model_decode_core.inl"), os.path.join(root, "losslessh264_b200", "csrc", "model_layout.h")]
+    dep = max(os.path.getmtime(p) for p in deps)
+    if force or not os.path.exists(exe) or os.path.getmtime(exe) < dep:
+        subprocess.check_call(["g++", "-O2", "-std=c++17", "-o", exe] + srcs)
+    return exe
+
+
 class _Pic(C.Structure):
     _fields_ = [("plane", C.c_void_p * 3), ("w", C.c_int), ("h", C.c_int)]
 
