@@ -152,6 +152,50 @@ def parse_stream():
         return read_lhfb(out), read_lhmd(md), float(m.group(1)) if m else None
 
 
+def bench_expand(ctx, mpics, n_streams, world):
+    """Decompress direction: `.pip` file sets of n_streams copies of the workload stream -> the original .264,
+    through lh264_pip_plan (host) + lh264_model_decode (k_model_decode, one warp per stream) + lh264_pip_assemble (host).
+    The `.pip` is made by the product's own compress path (container code of lh264_parse_dump + the model kernels)."""
+    from losslessh264_b200 import pip as pipmod
+
+    with tempfile.TemporaryDirectory() as tmp:
+        dflt = os.path.join(tmp, "s.pip")
+        r = subprocess.run([PARSE_TOOL, STREAM, os.path.join(tmp, "s.lhfb"), "1", os.path.join(tmp, "s.lhmd"), dflt], capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("host parser failed: " + r.stderr[-300:])
+        default = open(dflt, "rb").read()
+    ms_ = ctx.model_open(mpics[0].mb_w * mpics[0].mb_h)
+    for q in mpics:
+        ctx.model_submit([q], [ms_])
+    tags = ctx.model_finish(ms_)
+    decisions = ctx.model_decisions(ms_)
+    ctx.model_close(ms_)
+    plan = pipmod.Plan(default)
+    original = open(STREAM, "rb").read()
+    try:
+        jobs = [plan.job(tags)] * n_streams
+        res = ctx.model_decode(jobs)                          # warm-up (allocations, page-in)
+        identical = all(plan.assemble(b, o) == original for b, o in res[:4])
+        ctx.kernel_ms(-1)
+        t0 = time.perf_counter()
+        res = ctx.model_decode(jobs)
+        wall = time.perf_counter() - t0
+        kms = ctx.kernel_ms(6)
+        ctx.kernel_ms(-2)
+        t1 = time.perf_counter()
+        out = plan.assemble(*res[0])
+        asm = time.perf_counter() - t1
+        identical = identical and out == original
+    finally:
+        plan.close()
+    n = len(mpics)
+    return {"streams_per_gpu": n_streams, "pictures": n * n_streams, "kernel": "k_model_decode", "kernel_ms": round(kms, 2),
+            "frames_per_s_kernel": round(world * n * n_streams / (kms / 1000.0), 1), "frames_per_s_call": round(world * n * n_streams / wall, 1),
+            "decisions_per_s": round(world * decisions * n_streams / (kms / 1000.0)), "decisions_per_stream": int(decisions),
+            "host_assemble_ms_per_stream": round(asm * 1000.0, 3), "byte_identical_to_original": bool(identical),
+            "path": "lh264_pip_plan + lh264_model_decode (host side streams in, slice_data bits out) + lh264_pip_assemble"}
+
+
 def pinned_copy(arr, keep):
     """Copy of a numpy array in pinned host memory (lh264_host_alloc), so that H2D copies are real async DMA."""
     import numpy as np
@@ -177,6 +221,8 @@ def main():
     ap.add_argument("--e2e-threads", type=int, default=8, help="host threads (one context each) on the host-buffer path")
     ap.add_argument("--e2e-streams", type=int, default=512, help="streams on the host-buffer path (all threads together)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-expand", action="store_true", help="skip the decompress-direction leg")
+    ap.add_argument("--expand-streams", type=int, default=1024, help="streams of the decompress-direction leg (one warp each)")
     args = ap.parse_args()
     if args.impl == "reference":
         return bench_reference(args)
@@ -375,6 +421,15 @@ def main():
                 "path": "lh264_recon_submit + lh264_model_submit (pinned host records) + lh264_pictures_read_packed (I420 to pinned host)"},
         "gpu_launches": int(launches), "clocks": sampler.summary(),
     }
+    if not args.no_expand:
+        for b in batches:                                 # make room: the decompress leg keeps one prior table per stream
+            ctx.free_batch(b)
+        for b in mbatches:
+            ctx.model_free_batch(b)
+        batches, mbatches = [], []
+        for h_ in mstreams:
+            ctx.model_close(h_)
+        line["expand"] = bench_expand(ctx, mpics, min(S, args.expand_streams), world)
     if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(REF_DEC):
         k, cores = reference_concurrency()
         with tempfile.TemporaryDirectory() as tmp:

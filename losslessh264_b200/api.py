@@ -318,14 +318,15 @@ class Context:
         caps = [int(out_capacity or (4 * sum(len(b) for b in s["tags"].values()) + (1 << 20))) for s in streams]
         while True:
             jobs = (DecodeJob * n)()
-            keep = []
+            keep = {}
             bits, outs = [], []
             for j, s in enumerate(streams):
                 job = jobs[j]
                 job.max_mbs = int(s["max_mbs"]); job.with_8x8 = int(bool(s.get("with_8x8", True)))
                 for t, b in s["tags"].items():
-                    buf = np.frombuffer(bytes(b) + b"\0", np.uint8)
-                    keep.append(buf)
+                    buf = keep.get(id(b))                 # jobs that share a bytes object share the host copy
+                    if buf is None:
+                        buf = keep[id(b)] = np.frombuffer(bytes(b) + b"\0", np.uint8)
                     job.tag_data[int(t)] = buf.ctypes.data; job.tag_len[int(t)] = len(b)
                 ns = int(s["n_slices"])
                 job.slices = C.cast(s["slices"], C.c_void_p).value if ns else None

@@ -538,6 +538,7 @@ int lh264_k_expand_plane (lh264_ctx* c, const uint8_t* in, int w, int h, int pad
 
 #include "model_host.inl"
 #include "model_decode.cuh"
+#include "model_decode_host.inl"
 
 static float model_ms (lh264_ctx* c, int which, bool reset) {
   ModelCtx* m = static_cast<ModelCtx*> (c->model);

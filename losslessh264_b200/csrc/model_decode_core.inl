@@ -10,7 +10,9 @@
 //
 // This file is plain C++ behind three macros so that the tests can compile the very same code for the CPU as a checker:
 //   MD_FN     function qualifier   (`__device__` in the CUDA build, `static inline` on the CPU)
-//   MD_CLZ    count-leading-zeros of a non-zero 32-bit value
+//   MD_FN_NOINLINE  the same, never inlined (keeps the kernel small enough for the instruction cache)
+//   MD_CLZ    count-leading-zeros of a non-zero 32-bit value;  MD_DIV(n, d) exact unsigned n / d for n < 2^18, d < 2^11
+//   MD_READER(c, tag) / MD_TEST(c)  lvalues of a tag's bool-decoder state and of TEST_PROB (shared memory in the CUDA build)
 //   tables    host/cavlc_tables.h is included by the includer with LH264_CAVLC_TABLE set accordingly
 // The includer is in namespace scope; model_layout.h (tags, prior layout, CtxRec) must already be included.
 
@@ -23,30 +25,43 @@ MD_FN uint32_t md_prob (uint32_t w) { return (w >> 24) ^ 0x80u; }
 MD_FN uint32_t md_adapt (uint32_t w, uint32_t bit) {
   uint32_t c0 = w & 0x3ffu, c1 = (w >> 10) & 0x3ffu;
   if (bit) c1++; else c0++;
-  const uint32_t prob = (256u * (c0 + 1u)) / (c0 + c1 + 2u);
+  const uint32_t prob = MD_DIV (256u * (c0 + 1u), c0 + c1 + 2u);
   if (c0 + c1 > 512u) { c0 = (c0 + 1u) >> 1; c1 = (c1 + 1u) >> 1; }
   return c0 | (c1 << 10) | ((prob ^ 0x80u) << 24);
 }
 
 // ---- VP8 bool decoder (bitreader.h:77-136, bitreader.cpp:45-110), 32-bit window; bytes past the end read as zero ------
 struct MdReader { const uint8_t* buf; uint32_t len, pos, value, range; int32_t count; };
+#ifdef MD_SHARED_STATE
+__shared__ MdReader s_rd[CT_COUNT];
+__shared__ uint32_t s_test;
+#endif
 MD_FN void md_reader_init (MdReader& r, const uint8_t* buf, uint32_t len) { r.buf = buf; r.len = len; r.pos = 0; r.value = 0; r.range = 255; r.count = -8; }
 MD_FN uint32_t md_read (MdReader& r, uint32_t prob) {
-  const uint32_t split = 1u + (((r.range - 1u) * prob) >> 8);
-  if (r.count < 0) {
-    int shift = 32 - 8 - (r.count + 8);
-    while (shift >= 0) {
-      const uint32_t b = r.pos < r.len ? r.buf[r.pos] : 0u;
-      r.pos++;
-      r.value |= b << shift;
-      shift -= 8; r.count += 8;
+  // the state is worked on in registers and stored once: `buf` is a byte pointer, so every store through `r` inside the
+  // refill loop would otherwise have to be assumed to alias it
+  uint32_t value = r.value, range = r.range;
+  int32_t count = r.count;
+  const uint32_t split = 1u + (((range - 1u) * prob) >> 8);
+  if (count < 0) {
+    uint32_t pos = r.pos;
+    const uint32_t len = r.len;
+    const uint8_t* buf = r.buf;
+    int shift = 32 - 8 - (count + 8);                 // 17..24: three bytes, four when the window is empty
+    for (int k = 0; k < 4; k++) {
+      if (shift < 0) break;
+      const uint32_t b = pos < len ? buf[pos] : 0u;
+      pos++;
+      value |= b << shift;
+      shift -= 8; count += 8;
     }
+    r.pos = pos;
   }
   const uint32_t bigsplit = split << 24;
-  uint32_t range = split, bit = 0;
-  if (r.value >= bigsplit) { range = r.range - split; r.value -= bigsplit; bit = 1; }
+  uint32_t bit = 0;
+  if (value >= bigsplit) { range -= split; value -= bigsplit; bit = 1; } else range = split;
   const int shift = MD_CLZ (range) - 24;
-  r.range = range << shift; r.value <<= shift; r.count -= shift;
+  r.range = range << shift; r.value = value << shift; r.count = count - shift;
   return bit;
 }
 
@@ -66,16 +81,30 @@ struct MdStream {
 // error codes
 enum { MD_ERR_PCM = 21, MD_ERR_OUT_FULL = 22, MD_ERR_SYNTAX = 23, MD_ERR_DIMS = 24, MD_ERR_CONTEXT = 25 };
 
-struct MdCtx { uint32_t* priors; MdReader* rd; };
+// Decoder context.  Priors are read-modified-written in place in the table: their loads hit L1 (99.6 % in the ncu capture,
+// profiles/r1_decode_ncu.md) and account for ~8 % of the stall samples.  Two software caches of the table in shared memory were
+// measured and rejected (a one-record write-back buffer, and a 256-record direct-mapped cache with a 95 % hit rate): the
+// decoder is bound by the length of its dependent instruction chain (~170 instructions per decision), not by these loads.
+// TEST_PROB (shared by all tags, interleaved with everything) lives next to the bool-decoder states.
+struct MdCtx { uint32_t* priors; MdReader* rd; uint32_t test; };
+MD_FN void md_ctx_init (MdCtx& c, uint32_t* priors, MdReader* rd) { c.priors = priors; c.rd = rd; }
+MD_FN uint32_t* md_prior (MdCtx& c, uint32_t prior) { return &c.priors[prior]; }
 
-MD_FN uint32_t md_bit (MdCtx& c, int tag, uint32_t prior) {     // ArithmeticCodedInput::scanBit + DynProb update
-  const uint32_t w = c.priors[prior];
-  const uint32_t bit = md_read (c.rd[tag], md_prob (w));
-  c.priors[prior] = md_adapt (w, bit);
+MD_FN_NOINLINE uint32_t md_bit (MdCtx& c, int tag, uint32_t prior) {     // ArithmeticCodedInput::scanBit + DynProb update
+  if (prior == P_TEST) {
+    const uint32_t t = MD_TEST (c);
+    const uint32_t bit = md_read (MD_READER (c, tag), md_prob (t));
+    MD_TEST (c) = md_adapt (t, bit);
+    return bit;
+  }
+  uint32_t* w = md_prior (c, prior);
+  const uint32_t v = *w;
+  const uint32_t bit = md_read (MD_READER (c, tag), md_prob (v));
+  *w = md_adapt (v, bit);
   return bit;
 }
 // scanBits(nBits, Branch<n>): compression_stream.h pre-order tree, mirror of emitBits :477-487
-MD_FN uint32_t md_branch (MdCtx& c, int tag, int nbits, uint32_t tree) {
+MD_FN_NOINLINE uint32_t md_branch (MdCtx& c, int tag, int nbits, uint32_t tree) {
   uint32_t data = 0;
   for (int n = nbits; n >= 1; n--) {
     const uint32_t bit = md_bit (c, tag, tree);
@@ -94,7 +123,7 @@ MD_FN uint32_t md_zero_to_pow2 (MdCtx& c, int tag, int nbits, uint32_t priors, u
   const uint32_t d = md_branch (c, tag, nbits, priors + 1);
   return d >= preferred ? d + 1 : d;
 }
-MD_FN int md_unary (MdCtx& c, int tag, uint32_t base, int n, int early) {                              // scanUnary
+MD_FN_NOINLINE int md_unary (MdCtx& c, int tag, uint32_t base, int n, int early) {                              // scanUnary
   int i = 0;
   for (;;) {
     if (!md_bit (c, tag, base + (uint32_t) (i < n - 1 ? i : n - 1))) return i;
@@ -103,7 +132,7 @@ MD_FN int md_unary (MdCtx& c, int tag, uint32_t base, int n, int early) {       
   }
 }
 // scanInt: mirror of CompressionStream::emitInt :523-572 (mantissa size 4)
-MD_FN int md_int (MdCtx& c, uint32_t expo, int n_exp, uint32_t mant, int order, uint32_t zero, uint32_t sign, int tagExp, int tagMant, int tagZero, int tagSign) {
+MD_FN_NOINLINE int md_int (MdCtx& c, uint32_t expo, int n_exp, uint32_t mant, int order, uint32_t zero, uint32_t sign, int tagExp, int tagMant, int tagZero, int tagSign) {
   if (zero != NO_PRIOR && md_bit (c, tagZero, zero)) return 0;
   uint32_t positive = 1;
   if (sign != NO_PRIOR) positive = md_bit (c, tagSign, sign);
@@ -124,7 +153,7 @@ MD_FN int md_int (MdCtx& c, uint32_t expo, int n_exp, uint32_t mant, int order, 
   return positive ? data : -data;
 }
 // scanUEGkInt: mirror of emitUEGkInt :575-591
-MD_FN int md_uegk (MdCtx& c, int threshold, uint32_t p, int n_exp, int order, int tagExp, int tagMant, int tagZero, int tagSign) {
+MD_FN_NOINLINE int md_uegk (MdCtx& c, int threshold, uint32_t p, int n_exp, int order, int tagExp, int tagMant, int tagZero, int tagSign) {
   if (md_bit (c, tagZero, p + U_ZERO)) return 0;
   const uint32_t neg = md_bit (c, tagSign, p + U_SIGN);
   const int u = md_unary (c, tagMant, p + U_FIRST, 4, threshold);
@@ -144,13 +173,16 @@ MD_TABLE uint8_t md_zigzag4[16] = { 0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11
 MD_TABLE uint8_t md_zigzag8[64] = {
   0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4, 5, 12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13, 6, 7, 14, 21, 28,
   35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31, 39, 46, 53, 60, 61, 54, 47, 55, 62, 63 };
+MD_TABLE uint8_t md_i16dc_scan[16] = { 0, 16, 32, 128, 48, 64, 80, 96, 144, 160, 176, 192, 112, 208, 224, 240 };   // 16 * z(raster zigzag4[i]): Intra16x16 DC levels sit in slot 0 of block z
+MD_TABLE uint8_t md_cdc_scan[4] = { 0, 16, 32, 48 };                                                                  // chroma DC k -> slot 0 of block k
 MD_TABLE uint8_t md_cbp_intra[48] = { 47, 31, 15, 0, 23, 27, 29, 30, 7, 11, 13, 14, 39, 43, 45, 46, 16, 3, 5, 10, 12, 19, 21, 26, 28, 35, 37, 42, 44, 1, 2, 4,
                                       8, 17, 18, 20, 24, 6, 9, 22, 25, 32, 33, 34, 36, 40, 38, 41 };   // Table 9-4
 MD_TABLE uint8_t md_cbp_inter[48] = { 0, 16, 1, 2, 4, 8, 32, 3, 5, 10, 12, 15, 47, 7, 11, 13, 14, 6, 9, 31, 35, 37, 42, 44, 33, 34, 36, 40, 39, 43, 45, 46,
                                       17, 18, 20, 24, 19, 21, 26, 28, 23, 27, 29, 30, 22, 25, 38, 41 };
 
 // decode4x4<n>: mirror of encode4x4 decode_slice.cpp:2060-2094 (see gen_block in model_kernels.cuh for the prior indexing)
-MD_FN void md_block (MdCtx& c, int16_t* ac, int n, bool emit_dc, int color, uint32_t nzp, uint32_t acbase) {
+// cnt = non-zero counts of the block's 16-coefficient chunks (DC slot included), kept current as levels are written
+MD_FN_NOINLINE void md_block (MdCtx& c, int16_t* ac, uint8_t* cnt, int n, bool emit_dc, int color, uint32_t nzp, uint32_t acbase) {
   const uint8_t* zz = n == 16 ? md_zz16 : md_zz64;
   const int tEob = color ? CT_C_EOB : CT_L0_EOB;
   const int nonzeros = md_int (c, nzp + I_EXP, 3, nzp + I_MANT, 0, nzp + I_ZERO, NO_PRIOR, tEob, tEob, tEob, tEob);
@@ -162,10 +194,19 @@ MD_FN void md_block (MdCtx& c, int16_t* ac, int n, bool emit_dc, int color, uint
     const uint32_t p = acbase + ((uint32_t) (emitted * 5 + l4) * 25u + (uint32_t)a * 5u + (uint32_t)b) * 16u;
     const int v = md_uegk (c, 14, p, 2, 0, tb + 1, tb + 2, tb, tb + 3);
     ac[zz[i]] = (int16_t)v;
+    if (v) cnt[zz[i] >> 4]++;
     prev2 = prev; prev = v; emitted++;
     if (v) left--;
   }
 }
+
+// Per-stream scratch (shared memory in the CUDA build: a lone lane's stack costs a 128-byte cache line per word)
+struct MdScratch {
+  lh264_model_mb r;               // the macroblock being decoded
+  int16_t lev[384];               // its levels, layout of the coefficient pool (24 chunks of 16)
+  int32_t level[16], run[16];     // cw_residual_block
+  uint8_t cnt[24];
+};
 
 // ---- bit sink of the re-serialiser ------------------------------------------------------------------------------------
 struct MdBits {
@@ -187,7 +228,7 @@ MD_FN uint64_t mb_bits (const MdBits& b) { return b.n_bits + (uint64_t)b.n_acc; 
 MD_FN void mb_flush (MdBits& b) {                               // left-aligns what is pending into one more byte (not counted in n_bits)
   if (b.n_acc > 0 && b.n_bits + 8 <= b.cap_bits) b.out[b.n_bits >> 3] = (uint8_t) (b.acc << (8 - b.n_acc));
 }
-MD_FN void mb_ue (MdBits& b, uint32_t v) {
+MD_FN_NOINLINE void mb_ue (MdBits& b, uint32_t v) {
   const uint32_t x = v + 1u;
   const int len = 31 - MD_CLZ (x);
   mb_put (b, 0, len > 24 ? 24 : len);
@@ -197,20 +238,24 @@ MD_FN void mb_ue (MdBits& b, uint32_t v) {
 MD_FN void mb_se (MdBits& b, int v) { mb_ue (b, v > 0 ? (uint32_t) (2 * v - 1) : (uint32_t) (-2 * v)); }
 MD_FN void mb_te (MdBits& b, int range, uint32_t v) { if (range > 1) mb_ue (b, v); else mb_put (b, v ^ 1u, 1); }
 
-// residual_block_cavlc() (7.3.5.3.2 / 9.2) in the writing direction, canonical choices; levels in scan order
-MD_FN void cw_residual_block (MdBits& bw, int nC, int max_coeff, const int16_t* c) {
-  int level[16], run[16], total = 0, last = -1, zeros = 0;
-  for (int i = max_coeff - 1; i >= 0; i--) if (c[i]) { last = i; break; }
-  for (int i = last; i >= 0; i--) {
-    if (c[i]) { level[total] = c[i]; run[total] = 0; total++; }
-    else { run[total - 1]++; zeros++; }
+// residual_block_cavlc() (7.3.5.3.2 / 9.2) in the writing direction, canonical choices.  The block's levels are read in place:
+// coefficient i of the scan is base[scan[i * step]] (one pass from the highest frequency down collects levels, runs and
+// total_zeros).  Returns total_coeff.
+MD_FN_NOINLINE int cw_residual_block (MdBits& bw, MdScratch& sc, int nC, int max_coeff, const int16_t* base, const uint8_t* scan, int step) {
+  int32_t* level = sc.level;
+  int32_t* run = sc.run;
+  int total = 0, zeros = 0;
+  for (int i = max_coeff - 1; i >= 0; i--) {
+    const int v = base[scan[i * step]];
+    if (v) { level[total] = v; run[total] = 0; total++; }
+    else if (total) { run[total - 1]++; zeros++; }
   }
   int t1 = 0;
   while (t1 < total && t1 < 3 && (level[t1] == 1 || level[t1] == -1)) t1++;
   if (nC < 0) mb_put (bw, kTokCodeC[t1][total], kTokLenC[t1][total]);
   else if (nC >= 8) mb_put (bw, total == 0 ? 3u : (uint32_t) (((total - 1) << 2) | t1), 6);
   else { const int t = nC < 2 ? 0 : (nC < 4 ? 1 : 2); mb_put (bw, kTokCode[t][t1][total], kTokLen[t][t1][total]); }
-  if (total == 0) return;
+  if (total == 0) return 0;
   for (int i = 0; i < t1; i++) mb_put (bw, level[i] < 0, 1);
   int suffix_len = (total > 10 && t1 < 3) ? 1 : 0;
   for (int i = t1; i < total; i++) {
@@ -247,6 +292,7 @@ MD_FN void cw_residual_block (MdBits& bw, int nC, int max_coeff, const int16_t* 
     mb_put (bw, kRunCode[k][run[i]], kRunLen[k][run[i]]);
     zeros_left -= run[i];
   }
+  return total;
 }
 
 // per-slice state of the syntax writer
@@ -257,7 +303,9 @@ MD_FN int cw_nC (int nA, int nB) { if (nA >= 0 && nB >= 0) return (nA + nB + 1) 
 // macroblock_layer() (7.3.5) for one record; lev = the MB's 384 levels in the layout of the coefficient pool (24 chunks of 16).
 // tc = this MB's total_coeff[24] (written), tcL / tcT = the left / top neighbour's (nullptr when not available, 6.4.8).
 // Returns false for what cannot be expressed (I_PCM).
-MD_FN bool cw_mb (MdBits& bw, const lh264_model_mb& r, const int16_t* lev, CwSlice& s, uint8_t* tc, const uint8_t* tcL, const uint8_t* tcT) {
+MD_FN_NOINLINE bool cw_mb (MdBits& bw, MdScratch& sc, CwSlice& s, uint8_t* tc, const uint8_t* tcL, const uint8_t* tcT) {
+  const lh264_model_mb& r = sc.r;
+  const int16_t* lev = sc.lev;
   const bool p_slice = s.slice_type == 0;
   if (p_slice && (r.flags & LH264_MM_EMIT_SKIP_RUN)) mb_ue (bw, r.skip_run);
   if (!(r.flags & LH264_MM_WRITE_BLOCK)) { for (int i = 0; i < 24; i++) tc[i] = 0; return true; }
@@ -318,40 +366,27 @@ MD_FN bool cw_mb (MdBits& bw, const lh264_model_mb& r, const int16_t* lev, CwSli
     mb_se (bw, d);
     s.qp = r.luma_qp;
   }
-  int16_t blk[16];
-  if (i16) {
-    for (int i = 0; i < 16; i++) blk[i] = lev[16 * md_scan4[md_zigzag4[i]]];
-    cw_residual_block (bw, cw_nC (tcL ? tcL[3] : -1, tcT ? tcT[12] : -1), 16, blk);
-  }
+  if (i16) cw_residual_block (bw, sc, cw_nC (tcL ? tcL[3] : -1, tcT ? tcT[12] : -1), 16, lev, md_i16dc_scan, 1);
   for (int q = 0; q < 4; q++) {
     if (!(cbpL & (1 << q))) { for (int k = 0; k < 4; k++) tc[md_scan4[4 * q + k]] = 0; continue; }
     for (int k = 0; k < 4; k++) {
       const int z = 4 * q + k, rr = md_scan4[z], bx = rr & 3, by = rr >> 2;
-      int n = 0, maxc = 16;
-      if (t8) { for (int i = 0; i < 16; i++) blk[i] = lev[64 * q + md_zigzag8[4 * i + k]]; }
-      else if (i16) { maxc = 15; for (int i = 0; i < 15; i++) blk[i] = lev[16 * z + md_zigzag4[i + 1]]; }
-      else { for (int i = 0; i < 16; i++) blk[i] = lev[16 * z + md_zigzag4[i]]; }
-      for (int i = 0; i < maxc; i++) n += blk[i] != 0;
       const int nA = bx > 0 ? tc[rr - 1] : (tcL ? tcL[rr + 3] : -1), nB = by > 0 ? tc[rr - 4] : (tcT ? tcT[rr + 12] : -1);
-      cw_residual_block (bw, cw_nC (nA, nB), maxc, blk);
+      int n;
+      if (t8) n = cw_residual_block (bw, sc, cw_nC (nA, nB), 16, lev + 64 * q, md_zigzag8 + k, 4);       // 4 interleaved sub-blocks
+      else if (i16) n = cw_residual_block (bw, sc, cw_nC (nA, nB), 15, lev + 16 * z, md_zigzag4 + 1, 1);
+      else n = cw_residual_block (bw, sc, cw_nC (nA, nB), 16, lev + 16 * z, md_zigzag4, 1);
       tc[rr] = (uint8_t)n;
     }
   }
-  if (cbpC) {
-    for (int p = 0; p < 2; p++) {
-      for (int b = 0; b < 4; b++) blk[b] = lev[16 * (16 + 4 * p + b)];
-      cw_residual_block (bw, -1, 4, blk);
-    }
-  }
+  if (cbpC)
+    for (int p = 0; p < 2; p++) cw_residual_block (bw, sc, -1, 4, lev + 16 * (16 + 4 * p), md_cdc_scan, 1);
   for (int p = 0; p < 2; p++)
     for (int b = 0; b < 4; b++) {
       const int base = 16 + 4 * p;
       if (cbpC & 2) {
-        int n = 0;
-        for (int i = 0; i < 15; i++) { blk[i] = lev[16 * (base + b) + md_zigzag4[i + 1]]; n += blk[i] != 0; }
         const int nA = (b & 1) ? tc[base + b - 1] : (tcL ? tcL[base + b + 1] : -1), nB = (b & 2) ? tc[base + b - 2] : (tcT ? tcT[base + b + 2] : -1);
-        cw_residual_block (bw, cw_nC (nA, nB), 15, blk);
-        tc[base + b] = (uint8_t)n;
+        tc[base + b] = (uint8_t)cw_residual_block (bw, sc, cw_nC (nA, nB), 15, lev + 16 * (base + b), md_zigzag4 + 1, 1);
       } else tc[base + b] = 0;
     }
   return true;
@@ -393,10 +428,15 @@ struct MdSliceIn {                 // = lh264_decode_slice (include/lh264_b200.h
   uint32_t first_mb; int32_t frame_num; uint16_t mb_w, mb_h; uint8_t slice_type, num_ref_idx_l0, slice_qp, flags; uint32_t header_bits;
 };
 
-// Decodes the slice's macroblocks from the side streams and appends their CAVLC syntax to bw.  lev = 384-entry scratch.
+// Decodes the slice's macroblocks from the side streams and appends their CAVLC syntax to bw.  sc = per-stream scratch,
+// c = the stream's decoder context.
 // Returns the number of macroblocks (skipped ones included); st.error is set on failure.
-MD_FN int md_slice (MdStream& st, const MdSliceIn& sl, bool prior_valid, MdBits& bw, int16_t* lev, uint8_t* pad_bits_out, uint8_t* n_pad_out) {
-  MdCtx c = { st.priors, st.rd };
+MD_FN int md_slice (MdStream& st, MdCtx& c, const MdSliceIn& sl, bool prior_valid, MdBits& bw, MdScratch& sc, uint8_t* pad_bits_out, uint8_t* n_pad_out) {
+  lh264_model_mb& r = sc.r;
+  int16_t* lev = sc.lev;
+  uint8_t* cnt = sc.cnt;
+  for (int i = 0; i < 384; i++) lev[i] = 0;
+  for (int i = 0; i < 24; i++) cnt[i] = 0;
   const int W = st.width, n_mbs = st.frame_len;
   CtxRec* cur = st.frame[st.cur];
   CtxRec* last = st.frame[1 - st.cur];
@@ -407,7 +447,6 @@ MD_FN int md_slice (MdStream& st, const MdSliceIn& sl, bool prior_valid, MdBits&
   CwSlice cs = { sl.slice_type, sl.num_ref_idx_l0, sl.slice_qp, t8mode ? 1 : 0 };
   int mb_addr = (int)sl.first_mb, mb_in_slice = 0, cached_qp = 0, last_dqp = 0, pending_skips = 0;
   bool run_known = false, stop = false;
-  lh264_model_mb r;
   auto avail = [&] (int mb) -> bool { return mb >= 0 && st.mb_slice[mb] == slice_no; };
   auto avail_intra = [&] (int mb) -> bool { return avail (mb) && (!cip || st.mb_intra[mb]); };
   while (!stop && mb_addr < n_mbs && !st.error) {
@@ -441,7 +480,7 @@ MD_FN int md_slice (MdStream& st, const MdSliceIn& sl, bool prior_valid, MdBits&
         run_known = true;
       }
       cur[mb_addr] = last[mb_addr];                    // :3105
-      cw_mb (bw, r, lev, cs, tc, nullptr, nullptr);
+      cw_mb (bw, sc, cs, tc, nullptr, nullptr);
       uint8_t* pm = &st.ipm[(size_t)mb_addr * 16];
       for (int i = 0; i < 16; i++) pm[i] = 2;
       st.mb_intra[mb_addr] = 0; st.mb_slice[mb_addr] = slice_no;
@@ -555,9 +594,8 @@ MD_FN int md_slice (MdStream& st, const MdSliceIn& sl, bool prior_valid, MdBits&
     }
     if (t8) r.flags |= LH264_MM_T8;
     // ---- coefficients ----
-    for (int i = 0; i < 384; i++) lev[i] = 0;
-    uint8_t cnt[24];
-    for (int i = 0; i < 24; i++) cnt[i] = 0;
+    for (int b = 0; b < 24; b++)                       // only the chunks the previous coded macroblock left non-zero
+      if (cnt[b]) { for (int i = 0; i < 16; i++) lev[16 * b + i] = 0; cnt[b] = 0; }
     if (tcd == 1)
       for (int i = 0; i < 16; i++) {
         const uint32_t p = P_LDC + (((uint32_t)i * 2u + stype) * NT + (uint32_t)tcd) * 16u;
@@ -570,7 +608,6 @@ MD_FN int md_slice (MdStream& st, const MdSliceIn& sl, bool prior_valid, MdBits&
         lev[16 * (16 + i)] = (int16_t)md_int (c, p + I_EXP, 3, p + I_MANT, 0, p + I_ZERO, p + I_SIGN, CT_CRDC, CT_CRDC, CT_CRDC, CT_CRDC);
         cnt[16 + i] = lev[16 * (16 + i)] != 0;
       }
-    auto count16 = [&] (int chunk) { int n = 0; for (int i = 0; i < 16; i++) n += lev[16 * chunk + i] != 0; cnt[chunk] = (uint8_t)n; };
     auto m2 = [] (int v) { return (uint32_t) (v < 2 ? v : 2); };
     const bool emit_ldc = tcd != 1;
     for (int q = 0; q < 4; q++) {
@@ -586,8 +623,7 @@ MD_FN int md_slice (MdStream& st, const MdSliceIn& sl, bool prior_valid, MdBits&
         if (tcd > 7) { st.error = MD_ERR_CONTEXT; break; }
         const uint32_t nzp = P_NZ8 + (((stype * NT + (uint32_t)tcd) * 3u + m2 (past)) * 3u + m2 (left)) * 3u * 8u + m2 (above) * 8u;
         const uint32_t acb = P_AC8 + ((stype * 8u + (uint32_t)tcd) * 64u) * 125u * 16u;
-        md_block (c, lev + 64 * q, 64, emit_ldc, 0, nzp, acb);
-        for (int k = 0; k < 4; k++) count16 (idx + k);
+        md_block (c, lev + 64 * q, cnt + idx, 64, emit_ldc, 0, nzp, acb);
       } else {
         for (int k = 0; k < 4; k++) {                   // getNonzerosPrior4x4 macroblock_model.cpp:478-527
           const int idx = q * 4 + k;
@@ -597,8 +633,7 @@ MD_FN int md_slice (MdStream& st, const MdSliceIn& sl, bool prior_valid, MdBits&
           if (idx < 4) { if (A) above = A->cnt[idx + 12]; } else above = cnt[idx - 4];
           const uint32_t nzp = P_NZ + ((((stype * NT + (uint32_t)tcd) * 3u + 0u) * 3u + m2 (past)) * 3u + m2 (left)) * 3u * 8u + m2 (above) * 8u;
           const uint32_t acb = P_AC + (((stype * 8u + (uint32_t) (tcd < 7 ? tcd : 7)) * 3u + 0u) * 16u) * 125u * 16u;
-          md_block (c, lev + 16 * idx, 16, emit_ldc, 0, nzp, acb);
-          count16 (idx);
+          md_block (c, lev + 16 * idx, cnt + idx, 16, emit_ldc, 0, nzp, acb);
         }
       }
     }
@@ -612,8 +647,7 @@ MD_FN int md_slice (MdStream& st, const MdSliceIn& sl, bool prior_valid, MdBits&
         if ((i & 2) == 0) { if (A) above = A->cnt[16 + i + 2]; } else above = cnt[16 + i - 2];
         const uint32_t nzp = P_NZ + ((((stype * NT + (uint32_t)tcd) * 3u + color) * 3u + m2 (past)) * 3u + m2 (left)) * 3u * 8u + m2 (above) * 8u;
         const uint32_t acb = P_AC + (((stype * 8u + (uint32_t) (tcd < 7 ? tcd : 7)) * 3u + color) * 16u) * 125u * 16u;
-        md_block (c, lev + 16 * (16 + i), 16, false, (int)color, nzp, acb);
-        count16 (16 + i);
+        md_block (c, lev + 16 * (16 + i), cnt + 16 + i, 16, false, (int)color, nzp, acb);
       }
     // ---- FreqImage store (:3107) ----
     {
@@ -624,7 +658,7 @@ MD_FN int md_slice (MdStream& st, const MdSliceIn& sl, bool prior_valid, MdBits&
     }
     // ---- CAVLC ----
     if (tcd >= 8) { st.error = MD_ERR_PCM; break; }
-    if (!cw_mb (bw, r, lev, cs, tc, hasLs ? &st.tcoef[(size_t) (mb_addr - 1) * 24] : nullptr, hasTs ? &st.tcoef[(size_t) (mb_addr - W) * 24] : nullptr)) { st.error = MD_ERR_SYNTAX; break; }
+    if (!cw_mb (bw, sc, cs, tc, hasLs ? &st.tcoef[(size_t) (mb_addr - 1) * 24] : nullptr, hasTs ? &st.tcoef[(size_t) (mb_addr - W) * 24] : nullptr)) { st.error = MD_ERR_SYNTAX; break; }
     if (bw.overflow) { st.error = MD_ERR_OUT_FULL; break; }
     st.mb_intra[mb_addr] = tcd <= 2; st.mb_slice[mb_addr] = slice_no;
     mb_addr++; mb_in_slice++;

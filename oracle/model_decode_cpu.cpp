@@ -21,8 +21,12 @@
 #include "../losslessh264_b200/csrc/model_layout.h"
 #include "../losslessh264_b200/host/cavlc_tables.h"
 #define MD_FN static inline
+#define MD_FN_NOINLINE static
 #define MD_TABLE static const
 #define MD_CLZ(x) __builtin_clz (x)
+#define MD_DIV(n, d) ((n) / (d))
+#define MD_READER(c, tag) ((c).rd[tag])
+#define MD_TEST(c) ((c).test)
 #include "../losslessh264_b200/csrc/model_decode_core.inl"
 #include "../losslessh264_b200/host/pip_expand.h"
 
@@ -50,7 +54,10 @@ extern "C" int mdc_model_decode (lh264_decode_job* jobs, int n_jobs) {
       md_reader_init (st.rd[t], job.tag_data[tag], job.tag_data[tag] ? job.tag_len[tag] : 0);
       if (job.tag_data[tag]) st.present |= 1u << t;
     }
-    int16_t lev[384];
+    MdScratch sc;
+    MdCtx c;
+    md_ctx_init (c, st.priors, st.rd);
+    c.test = priors[P_TEST];
     uint64_t off = 0;
     for (int s = 0; s < job.n_slices && !st.error; s++) {
       MdSliceIn sl;
@@ -63,7 +70,7 @@ extern "C" int mdc_model_decode (lh264_decode_job* jobs, int n_jobs) {
       mb_init (bw, job.out + off, job.out_capacity - off);
       lh264_decode_slice_out& so = job.slice_out[s];
       memset (&so, 0, sizeof (so));
-      so.n_mbs = (uint32_t)md_slice (st, sl, prior_valid, bw, lev, &so.pad_bits, &so.n_pad_bits);
+      so.n_mbs = (uint32_t)md_slice (st, c, sl, prior_valid, bw, sc, &so.pad_bits, &so.n_pad_bits);
       mb_flush (bw);
       so.byte_offset = off; so.n_bits = (uint32_t)mb_bits (bw);
       off += (mb_bits (bw) + 7) / 8;

@@ -10,7 +10,7 @@ import csv, os, re, subprocess, sys, tempfile, collections
 rep, kern = sys.argv[1], sys.argv[2]
 top = int(sys.argv[3]) if len(sys.argv) > 3 else 40
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-so = os.path.join(ROOT, "losslessh264_b200", "_lib", "liblh264_b200.so")
+so = os.environ.get("NCU_LINES_BIN") or os.path.join(ROOT, "losslessh264_b200", "_lib", "liblh264_b200.so")
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(out.splitlines()))
 hi = [i for i, r in enumerate(rows) if "# Samples" in r][0]
