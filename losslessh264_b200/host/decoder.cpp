@@ -1,6 +1,7 @@
 // decoder.cpp — see decoder.h.  Clause numbers refer to ITU-T H.264.
 #include "decoder.h"
 #include "cavlc.h"
+#include "cabac.h"
 #include "cavlc_writer.h"
 #include <memory>
 #include <string.h>
@@ -77,6 +78,16 @@ struct Decoder::Impl {
   // DecodedMacroblock (initRTDFromDecoderState, decode_slice.cpp:81-108): pCbp, pChromaPredMode,
   // pIntraPredMode[][7], pSubMbType are only written by the MB types that carry them
   std::vector<uint8_t> st_cbp, st_chroma, st_i16, st_sub;
+
+  // CABAC (9.3): the engine, and what context selection reads from neighbouring macroblocks of the picture
+  struct CabMb {
+    uint32_t cbf;                        // coded_block_flag: bits 0..15 luma 4x4 (raster), 16..19 Cb AC, 20..23 Cr AC, 24 luma DC, 25 Cb DC, 26 Cr DC
+    uint8_t cbp, chroma;                 // coded_block_pattern as 9.3.3.1.1.4 sees it (I_PCM: 0x2f), intra_chroma_pred_mode as coded
+  };
+  CabacDecoder cab;
+  bool cabac_on = false, last_dqp_nz = false;
+  std::vector<CabMb> cabmb;
+  std::vector<uint8_t> mvd_abs;          // [mb][16][2] |mvd| per raster 4x4 block, saturated at 128
 
   // slice being parsed
   const Sps* S = nullptr;
@@ -271,6 +282,7 @@ struct Decoder::Impl {
     side.assign (n_mbs, ModelMbSide());
     st_cbp.assign (n_mbs, 0); st_chroma.assign (n_mbs, 0); st_i16.assign (n_mbs, 0); st_sub.assign ((size_t)n_mbs * 4, 0);
     coefs.reserve ((size_t)n_mbs * 64);
+    cabmb.assign (n_mbs, CabMb()); mvd_abs.assign ((size_t)n_mbs * 32, 0);
     return sink->configure (mb_w, mb_h, n_slots);
   }
   bool is_new_picture (const SliceHeader& a, const SliceHeader& b) const {   // 7.4.1.2.4
@@ -338,6 +350,20 @@ struct Decoder::Impl {
   void resolve_intra (lh264_mb_rec& m, int mb_addr, const int8_t* modes, bool i8x8);
   int nC_luma (int mb_addr, int r) const;
   int nC_chroma (int mb_addr, int plane, int b) const;
+  // CABAC twins of the syntax element readers (9.3.2 binarisations, 9.3.3.1 ctxIdx derivation)
+  int parse_slice_data_cabac (BitReader& br, Decoder* self);
+  int parse_residual_cabac (lh264_mb_rec& m, int mb_addr, int16_t* lev, uint32_t& coded, bool i16, int cbp);
+  int cabac_block (int cat, int cbf_inc, int16_t* out, const uint8_t* scan, int scan_off);
+  int cabac_intra_mb_type (int base, bool i_slice, int mb_addr);
+  int cabac_mb_type (int mb_addr);
+  int cabac_sub_mb_type();
+  int cabac_ref_idx (int mb_addr, int q, const int8_t* cur_refs);
+  int cabac_mvd (int mb_addr, int bx, int by, int comp);
+  int cabac_cbp (int mb_addr);
+  int cabac_chroma_mode (int mb_addr);
+  int cabac_dqp();
+  int cabac_t8_flag (int mb_addr);
+  int cbf_inc (int mb_addr, int bit_cur_a, int bit_left, int bit_cur_b, int bit_top) const;
 };
 
 // ---- nC derivation (9.2.1) -----------------------------------------------------------------------------
@@ -463,6 +489,12 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_mod
   };
   memset (cur_done, 0, sizeof (cur_done));
   memset (m.ref_idx, -1, 4);
+  uint8_t* const mvda = cabac_on ? &mvd_abs[(size_t)mb_addr * 32] : nullptr;
+  if (cabac_on) { cabmb[mb_addr] = CabMb(); memset (mvda, 0, 32); }
+  auto put_mvd = [&] (int bx, int by, int bw, int bh, int dx, int dy) {
+    const uint8_t ax = (uint8_t)std::min (128, std::abs (dx)), ay = (uint8_t)std::min (128, std::abs (dy));
+    for (int y = by; y < by + bh; y++) for (int x = bx; x < bx + bw; x++) { mvda[2 * (y * 4 + x)] = ax; mvda[2 * (y * 4 + x) + 1] = ay; }
+  };
 
   if (skipped) {                                    // P_Skip: 8.4.1.1
     m.mb_type = LH264_MB_PSKIP;
@@ -477,10 +509,11 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_mod
     mb_slice[mb_addr] = (int16_t)slice_no;
     st_cbp[mb_addr] = 0;                             // pCbp[iMbXy] = 0, decode_slice.cpp:3945
     if (mr) { mr->type_code = 11; mr->luma_qp = (uint8_t)qp; }
+    last_dqp_nz = false;
     return 0;
   }
 
-  uint32_t t = br.ue();
+  uint32_t t = cabac_on ? (uint32_t)cabac_mb_type (mb_addr) : br.ue();
   const bool p_slice = sh.slice_type == SLICE_P;
   bool intra = true;
   if (p_slice) {
@@ -503,7 +536,7 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_mod
     };
     if (m.mb_type == LH264_MB_P8x8) {
       for (int q = 0; q < 4; q++) {
-        const uint32_t s = br.ue();
+        const uint32_t s = cabac_on ? (uint32_t)cabac_sub_mb_type() : br.ue();
         if (s > 3) return -1;
         m.sub_mb_type[q] = (uint8_t)s;
         if (s) sub_lt8 = true;
@@ -511,7 +544,7 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_mod
       }
       for (int q = 0; q < 4; q++) {
         int ref = 0;
-        if (t != 4 && nref > 1) { ref = (int)br.te (nref - 1); if (ref >= nref) return -1; }
+        if (t != 4 && nref > 1) { ref = cabac_on ? cabac_ref_idx (mb_addr, q, m.ref_idx) : (int)br.te (nref - 1); if (ref < 0 || ref >= nref) return -1; }
         m.ref_idx[q] = (int8_t)ref;
         if (mr) mr->ref_idx[q] = (int8_t)ref;
       }
@@ -530,7 +563,9 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_mod
           }
           int px, py;
           pred_mv (bx, by, bw, bh, ref, 0, px, py);
-          const int dx = br.se(), dy = br.se();
+          int dx, dy;
+          if (cabac_on) { dx = cabac_mvd (mb_addr, bx, by, 0); dy = cabac_mvd (mb_addr, bx, by, 1); put_mvd (bx, by, bw, bh, dx, dy); }
+          else { dx = br.se(); dy = br.se(); }
           if (mr) { mr->mvd[by * 4 + bx][0] = (int16_t)dx; mr->mvd[by * 4 + bx][1] = (int16_t)dy; }
           put_mv (bx, by, bw, bh, px + dx, py + dy);
         }
@@ -538,7 +573,13 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_mod
     } else {
       const int nparts = m.mb_type == LH264_MB_P16x16 ? 1 : 2;
       int refs_[2] = {0, 0};
-      for (int p = 0; p < nparts; p++) if (nref > 1) { refs_[p] = (int)br.te (nref - 1); if (refs_[p] >= nref) return -1; }
+      int8_t vis[4] = {-1, -1, -1, -1};              // ref_idx of the partitions parsed so far, per 8x8 (CABAC context selection)
+      for (int p = 0; p < nparts; p++) {
+        const int q0 = m.mb_type == LH264_MB_P16x8 ? 2 * p : p;
+        if (nref > 1) { refs_[p] = cabac_on ? cabac_ref_idx (mb_addr, q0, vis) : (int)br.te (nref - 1); if (refs_[p] < 0 || refs_[p] >= nref) return -1; }
+        if (m.mb_type == LH264_MB_P16x8) vis[2 * p] = vis[2 * p + 1] = (int8_t)refs_[p];
+        else if (m.mb_type == LH264_MB_P8x16) vis[p] = vis[p + 2] = (int8_t)refs_[p];
+      }
       for (int p = 0; p < nparts; p++) {
         int bx = 0, by = 0, bw = 4, bh = 4, shape = 0;
         if (m.mb_type == LH264_MB_P16x8) { bh = 2; by = 2 * p; shape = 1; }
@@ -547,17 +588,22 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_mod
         for (int y = by; y < by + bh; y += 2) for (int x = bx; x < bx + bw; x += 2) m.ref_idx[(y >> 1) * 2 + (x >> 1)] = (int8_t)refs_[p];
         int px, py;
         pred_mv (bx, by, bw, bh, refs_[p], shape, px, py);
-        const int dx = br.se(), dy = br.se();
+        int dx, dy;
+        if (cabac_on) { dx = cabac_mvd (mb_addr, bx, by, 0); dy = cabac_mvd (mb_addr, bx, by, 1); put_mvd (bx, by, bw, bh, dx, dy); }
+        else { dx = br.se(); dy = br.se(); }
         if (mr) { mr->ref_idx[p] = (int8_t)refs_[p]; mr->mvd[by * 4 + bx][0] = (int16_t)dx; mr->mvd[by * 4 + bx][1] = (int16_t)dy; }
         put_mv (bx, by, bw, bh, px + dx, py + dy);
       }
     }
     if (mr) mr->type_code = (uint8_t) (3 + t);          // 16x16 3, 16x8 4, 8x16 5, 8x8 6, 8x8ref0 7
-    const uint32_t c = br.ue();
-    if (c > 47) return -1;
-    cbp = kCbpInter[c];
+    if (cabac_on) cbp = cabac_cbp (mb_addr);
+    else {
+      const uint32_t c = br.ue();
+      if (c > 47) return -1;
+      cbp = kCbpInter[c];
+    }
     if ((cbp & 15) && P->transform_8x8_mode && ! (m.mb_type == LH264_MB_P8x8 && sub_lt8)) {
-      if (br.u1()) m.flags |= LH264_MBF_TRANSFORM8x8;
+      if (cabac_on ? cabac_t8_flag (mb_addr) : (int)br.u1()) m.flags |= LH264_MBF_TRANSFORM8x8;
       if (mr) mr->flags |= LH264_MM_T8_CODED;
     }
   } else if (t == 25) {                               // I_PCM
@@ -578,10 +624,15 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_mod
       mr->type_code = 8; mr->luma_qp = 0; mr->cbp = st_cbp[mb_addr]; mr->chroma_mode = st_chroma[mb_addr]; mr->i16_mode = st_i16[mb_addr];
       mr->coded_mask = 0; mr->coef_off = 0;
     }
+    if (cabac_on) {                                   // 9.3.1.2: the engine starts again behind the samples
+      cab.start (&br);
+      cabmb[mb_addr].cbf = 0x7FFFFFFu; cabmb[mb_addr].cbp = 0x2f;
+      last_dqp_nz = false;
+    }
     return br.overrun() ? -1 : 0;
   } else if (t == 0) {                                // I_NxN
     bool i8 = false;
-    if (P->transform_8x8_mode) i8 = br.u1();
+    if (P->transform_8x8_mode) i8 = cabac_on ? cabac_t8_flag (mb_addr) : (int)br.u1();
     m.mb_type = i8 ? LH264_MB_I8x8 : LH264_MB_I4x4;
     if (i8) m.flags |= LH264_MBF_TRANSFORM8x8;
     int8_t modes[16];
@@ -599,7 +650,9 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_mod
       if (i8 && by == 0 && aT && mbs[nT].mb_type == LH264_MB_I4x4) b = ipm[(size_t)nT * 16 + 12 + bx];        // 4x4 block 8x8idxB*4+2 = (x=bx, y=3)
       int pred = (!okA || !okB) ? 2 : std::min (a, b);
       int mode = pred;
-      if (!br.u1()) { const int rem = (int)br.u (3); mode = rem < pred ? rem : rem + 1; }
+      if (cabac_on) {                                 // prev_intra4x4_pred_mode_flag ctxIdx 68, rem_intra4x4_pred_mode 3 bins of ctxIdx 69, LSB first
+        if (!cab.decision (68)) { int rem = cab.decision (69); rem |= cab.decision (69) << 1; rem |= cab.decision (69) << 2; mode = rem < pred ? rem : rem + 1; }
+      } else if (!br.u1()) { const int rem = (int)br.u (3); mode = rem < pred ? rem : rem + 1; }
       modes[i] = (int8_t)mode;
       if (mr) {
         mr->pred_mode[i] = (uint8_t) (mode | (pred << 4));
@@ -613,36 +666,43 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_mod
       if (i8) { pm[r] = pm[r + 1] = pm[r + 4] = pm[r + 5] = (int8_t)mode; }
       else pm[r] = (int8_t)mode;
     }
-    const uint32_t cm = br.ue();
+    const uint32_t cm = cabac_on ? (uint32_t)cabac_chroma_mode (mb_addr) : br.ue();
     if (cm > 3) return -1;
     m.chroma_mode = (uint8_t)cm;
+    if (cabac_on) cabmb[mb_addr].chroma = (uint8_t)cm;
     resolve_intra (m, mb_addr, modes, i8);
     st_chroma[mb_addr] = m.chroma_mode;
     if (mr) mr->type_code = i8 ? 2 : 0;
-    const uint32_t c = br.ue();
-    if (c > 47) return -1;
-    cbp = kCbpIntra[c];
+    if (cabac_on) cbp = cabac_cbp (mb_addr);
+    else {
+      const uint32_t c = br.ue();
+      if (c > 47) return -1;
+      cbp = kCbpIntra[c];
+    }
   } else {                                            // Intra16x16
     m.mb_type = LH264_MB_I16x16;
     i16 = true;
     m.i16_mode = (uint8_t) ((t - 1) & 3);
     cbp = (((t - 1) >> 2) % 3) << 4 | ((t - 1) >= 12 ? 15 : 0);
-    const uint32_t cm = br.ue();
+    const uint32_t cm = cabac_on ? (uint32_t)cabac_chroma_mode (mb_addr) : br.ue();
     if (cm > 3) return -1;
     m.chroma_mode = (uint8_t)cm;
+    if (cabac_on) cabmb[mb_addr].chroma = (uint8_t)cm;
     resolve_intra (m, mb_addr, nullptr, false);
     st_chroma[mb_addr] = m.chroma_mode; st_i16[mb_addr] = m.i16_mode;
     if (mr) mr->type_code = 1;
   }
   m.cbp = (uint8_t)cbp;
   st_cbp[mb_addr] = (uint8_t)cbp;
+  if (cabac_on) cabmb[mb_addr].cbp = (uint8_t)cbp;
   if (cbp > 0 || i16) {
-    const int dqp = br.se();
+    const int dqp = cabac_on ? cabac_dqp() : br.se();
+    last_dqp_nz = dqp != 0;
     if (dqp < -26 || dqp > 25) return -1;
     qp = (qp + dqp + 52) % 52;
     set_qp (m);
     memset (lev, 0, sizeof (lev));
-    if (parse_residual (br, m, mb_addr, lev, coded, i16, cbp) < 0) return -1;
+    if ((cabac_on ? parse_residual_cabac (m, mb_addr, lev, coded, i16, cbp) : parse_residual (br, m, mb_addr, lev, coded, i16, cbp)) < 0) return -1;
     if (coded) {
       m.coded_mask = coded;
       m.coef_off = (uint32_t) (coefs.size() / 16);
@@ -654,6 +714,7 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_mod
   } else {
     set_qp (m);
     memset (nz, 0, 24);
+    last_dqp_nz = false;
   }
   uint32_t nzm = 0;
   for (int r = 0; r < 24; r++) if (nz[r]) nzm |= 1u << r;
@@ -667,6 +728,263 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_mod
     mr->coded_mask = m.coded_mask; mr->coef_off = m.coef_off;
   }
   return br.overrun() ? -1 : 0;
+}
+
+
+// ---- CABAC syntax elements (9.3.2 binarisation + 9.3.3.1 ctxIdx) -----------------------------------------------------
+// Replaces parse_mb_syn_cabac.cpp (ParseMBTypeISliceCabac :189, ParseMBTypePSliceCabac :227, ParseSubMBTypeCabac :301,
+// ParseIntraPredModeLumaCabac :322, ParseIntraPredModeChromaCabac :346, ParseInterMotionInfoCabac :393, ParseRefIdxCabac :600,
+// ParseMvdInfoCabac :651, ParseCbpInfoCabac :687, ParseDeltaQpCabac :760, ParseCbfInfoCabac :792, ParseSignificantMapCabac
+// :844, ParseSignificantCoeffCabac :889, ParseResidualBlockCabac :929-1040, ParseIPCMInfoCabac :1044) on the records of
+// this decoder.  Only what frame macroblocks of I and P slices need (no MBAFF, no B slices: as the reference).
+namespace {
+const uint8_t kSig8x8[63] = {0, 1, 2, 3, 4, 5, 5, 4, 4, 3, 3, 4, 4, 4, 5, 5, 4, 4, 4, 4, 3, 3, 6, 7, 7, 7, 8, 9, 10, 9, 8, 7,
+                             7, 6, 11, 12, 13, 11, 6, 7, 8, 9, 14, 10, 9, 8, 6, 11, 12, 13, 11, 6, 9, 14, 10, 9, 11, 12, 13, 11, 14, 10, 12
+                            };                        // Table 9-43, frame coded: significant_coeff_flag ctxIdxInc for ctxBlockCat 5
+const uint8_t kLast8x8[63] = {0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2,
+                              3, 3, 3, 3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 4, 4, 4, 5, 5, 5, 5, 6, 6, 6, 6, 7, 7, 7, 7, 8, 8, 8
+                             };                       // Table 9-43: last_significant_coeff_flag
+}
+
+int Decoder::Impl::cabac_intra_mb_type (int base, bool i_slice, int mb_addr) {
+  if (i_slice) {                                      // ctxIdxInc of bin 0: neighbours that are not I_NxN
+    const int mbx = mb_addr % mb_w, mby = mb_addr / mb_w;
+    const int nA = nb_mb (mbx, mby, -1, 0), nB = nb_mb (mbx, mby, 0, -1);
+    auto cond = [&] (int n) { return mb_avail (n) && mbs[n].mb_type != LH264_MB_I4x4 && mbs[n].mb_type != LH264_MB_I8x8; };
+    if (!cab.decision (base + (cond (nA) ? 1 : 0) + (cond (nB) ? 1 : 0))) return 0;
+    base += 2;
+  } else if (!cab.decision (base)) return 0;
+  if (cab.terminate()) return 25;
+  int t = 1 + 12 * cab.decision (base + 1);
+  if (cab.decision (base + 2)) t += 4 + 4 * cab.decision (base + 2 + (i_slice ? 1 : 0));
+  t += 2 * cab.decision (base + 3 + (i_slice ? 1 : 0));
+  t += cab.decision (base + 3 + (i_slice ? 2 : 0));
+  return t;
+}
+
+int Decoder::Impl::cabac_mb_type (int mb_addr) {       // value of mb_type as Tables 7-11 / 7-13 number it (P: intra types follow 5)
+  if (sh.slice_type == SLICE_I) return cabac_intra_mb_type (3, true, mb_addr);
+  if (!cab.decision (14)) {
+    if (!cab.decision (15)) return 3 * cab.decision (16);
+    return 2 - cab.decision (17);
+  }
+  return 5 + cabac_intra_mb_type (17, false, mb_addr);
+}
+
+int Decoder::Impl::cabac_sub_mb_type() {
+  if (cab.decision (21)) return 0;
+  if (!cab.decision (22)) return 1;
+  return cab.decision (23) ? 2 : 3;
+}
+
+int Decoder::Impl::cabac_ref_idx (int mb_addr, int q, const int8_t* cur_refs) {
+  const int mbx = mb_addr % mb_w, mby = mb_addr / mb_w;
+  auto gt0 = [&] (int n, int nq) { return mb_avail (n) && !LH264_MB_IS_INTRA (mbs[n].mb_type) && mbs[n].ref_idx[nq] > 0; };
+  const bool a = (q & 1) ? cur_refs[q - 1] > 0 : gt0 (nb_mb (mbx, mby, -1, 0), q + 1);
+  const bool b = (q & 2) ? cur_refs[q - 2] > 0 : gt0 (nb_mb (mbx, mby, 0, -1), q + 2);
+  int ctx = (a ? 1 : 0) + (b ? 2 : 0), ref = 0;
+  while (cab.decision (54 + ctx)) {
+    ref++;
+    ctx = (ctx >> 2) + 4;
+    if (ref >= 32) return -1;
+  }
+  return ref;
+}
+
+int Decoder::Impl::cabac_mvd (int mb_addr, int bx, int by, int comp) {
+  const int mbx = mb_addr % mb_w, mby = mb_addr / mb_w;
+  int sum = 0;
+  if (bx > 0) sum += mvd_abs[(size_t)mb_addr * 32 + 2 * (by * 4 + bx - 1) + comp];
+  else { const int n = nb_mb (mbx, mby, -1, 0); if (mb_avail (n)) sum += mvd_abs[(size_t)n * 32 + 2 * (by * 4 + 3) + comp]; }
+  if (by > 0) sum += mvd_abs[(size_t)mb_addr * 32 + 2 * ((by - 1) * 4 + bx) + comp];
+  else { const int n = nb_mb (mbx, mby, 0, -1); if (mb_avail (n)) sum += mvd_abs[(size_t)n * 32 + 2 * (12 + bx) + comp]; }
+  int ctx = (comp ? 47 : 40);
+  if (!cab.decision (ctx + (sum < 3 ? 0 : (sum > 32 ? 2 : 1)))) return 0;
+  int v = 1;
+  ctx += 3;
+  while (v < 9 && cab.decision (ctx)) { if (v < 4) ctx++; v++; }
+  if (v >= 9) {                                       // UEG3 suffix
+    int k = 3;
+    while (cab.bypass()) { v += 1 << k; if (++k > 24) return 0; }
+    while (k--) v += cab.bypass() << k;
+  }
+  return cab.bypass() ? -v : v;
+}
+
+int Decoder::Impl::cabac_cbp (int mb_addr) {
+  const int mbx = mb_addr % mb_w, mby = mb_addr / mb_w;
+  const int nA = nb_mb (mbx, mby, -1, 0), nB = nb_mb (mbx, mby, 0, -1);
+  // unavailable neighbours count as "all luma blocks coded, no chroma"
+  const int ca = mb_avail (nA) ? cabmb[nA].cbp : 0x0f, cb = mb_avail (nB) ? cabmb[nB].cbp : 0x0f;
+  int cbp = 0;
+  cbp |= cab.decision (73 + ! (ca & 2) + 2 * ! (cb & 4));
+  cbp |= cab.decision (73 + ! (cbp & 1) + 2 * ! (cb & 8)) << 1;
+  cbp |= cab.decision (73 + ! (ca & 8) + 2 * ! (cbp & 1)) << 2;
+  cbp |= cab.decision (73 + ! (cbp & 4) + 2 * ! (cbp & 2)) << 3;
+  const int xa = ca >> 4, xb = cb >> 4;
+  if (cab.decision (77 + (xa > 0 ? 1 : 0) + (xb > 0 ? 2 : 0)))
+    cbp |= (1 + cab.decision (77 + 4 + (xa == 2 ? 1 : 0) + (xb == 2 ? 2 : 0))) << 4;
+  return cbp;
+}
+
+int Decoder::Impl::cabac_chroma_mode (int mb_addr) {
+  const int mbx = mb_addr % mb_w, mby = mb_addr / mb_w;
+  auto cond = [&] (int n) { return mb_avail (n) && LH264_MB_IS_INTRA (mbs[n].mb_type) && mbs[n].mb_type != LH264_MB_IPCM && cabmb[n].chroma != 0; };
+  if (!cab.decision (64 + (cond (nb_mb (mbx, mby, -1, 0)) ? 1 : 0) + (cond (nb_mb (mbx, mby, 0, -1)) ? 1 : 0))) return 0;
+  if (!cab.decision (64 + 3)) return 1;
+  return 2 + cab.decision (64 + 3);
+}
+
+int Decoder::Impl::cabac_dqp() {
+  int ctx = last_dqp_nz ? 1 : 0, v = 0;
+  while (cab.decision (60 + ctx)) {
+    ctx = 2 + (ctx >> 1);
+    if (++v > 104) return 99;                         // out of range: rejected by the caller
+  }
+  return (v & 1) ? (v + 1) >> 1 : - (v >> 1);
+}
+
+int Decoder::Impl::cabac_t8_flag (int mb_addr) {
+  const int mbx = mb_addr % mb_w, mby = mb_addr / mb_w;
+  auto cond = [&] (int n) { return mb_avail (n) && (mbs[n].flags & LH264_MBF_TRANSFORM8x8); };
+  return cab.decision (399 + (cond (nb_mb (mbx, mby, -1, 0)) ? 1 : 0) + (cond (nb_mb (mbx, mby, 0, -1)) ? 1 : 0));
+}
+
+// 9.3.3.1.1.9: ctxIdxInc of coded_block_flag.  bit_cur_* >= 0: the neighbouring block lies in the current macroblock (that bit
+// of its cbf word); otherwise the bit of the left / top macroblock's word.  Unavailable macroblock: 1 for intra, 0 for inter.
+int Decoder::Impl::cbf_inc (int mb_addr, int bit_cur_a, int bit_left, int bit_cur_b, int bit_top) const {
+  const int mbx = mb_addr % mb_w, mby = mb_addr / mb_w;
+  const int dflt = LH264_MB_IS_INTRA (mbs[mb_addr].mb_type) ? 1 : 0;
+  int a, b;
+  if (bit_cur_a >= 0) a = (cabmb[mb_addr].cbf >> bit_cur_a) & 1;
+  else { const int n = nb_mb (mbx, mby, -1, 0); a = mb_avail (n) ? (int) ((cabmb[n].cbf >> bit_left) & 1) : dflt; }
+  if (bit_cur_b >= 0) b = (cabmb[mb_addr].cbf >> bit_cur_b) & 1;
+  else { const int n = nb_mb (mbx, mby, 0, -1); b = mb_avail (n) ? (int) ((cabmb[n].cbf >> bit_top) & 1) : dflt; }
+  return a + 2 * b;
+}
+
+// residual_block_cabac( ) (7.3.5.3.3).  cat = ctxBlockCat 0..5; cbf_inc < 0: no coded_block_flag is read (8x8 blocks).  Level of
+// coefficient i goes to out[scan[scan_off + i]]; returns the number of non-zero coefficients.
+int Decoder::Impl::cabac_block (int cat, int cbf_ctx_inc, int16_t* out, const uint8_t* scan, int scan_off) {
+  static const int kCbfBase[5] = {85, 85 + 4, 85 + 8, 85 + 12, 85 + 16};
+  static const int kSigBase[6] = {105, 105 + 15, 105 + 29, 105 + 44, 105 + 47, 402};
+  static const int kLastBase[6] = {166, 166 + 15, 166 + 29, 166 + 44, 166 + 47, 417};
+  static const int kAbsBase[6] = {227, 227 + 10, 227 + 20, 227 + 30, 227 + 39, 426};
+  static const int kMax[6] = {16, 15, 16, 4, 15, 64};
+  if (cbf_ctx_inc >= 0 && !cab.decision (kCbfBase[cat] + cbf_ctx_inc)) return 0;
+  const int n_max = kMax[cat];
+  uint8_t pos[64];
+  int n = 0, i;
+  for (i = 0; i < n_max - 1; i++) {
+    const int inc_s = cat == 5 ? kSig8x8[i] : (cat == 3 ? std::min (i, 2) : i);
+    if (!cab.decision (kSigBase[cat] + inc_s)) continue;
+    pos[n++] = (uint8_t)i;
+    const int inc_l = cat == 5 ? kLast8x8[i] : (cat == 3 ? std::min (i, 2) : i);
+    if (cab.decision (kLastBase[cat] + inc_l)) break;
+  }
+  if (i == n_max - 1) pos[n++] = (uint8_t) (n_max - 1);   // the last position is significant by inference
+  int eq1 = 0, gt1 = 0;
+  const int gt1_cap = cat == 3 ? 3 : 4;
+  for (int k = n - 1; k >= 0; k--) {
+    int a = 1;
+    if (cab.decision (kAbsBase[cat] + (gt1 ? 0 : std::min (4, 1 + eq1)))) {
+      const int ctx = kAbsBase[cat] + 5 + std::min (gt1_cap, gt1);
+      a = 2;
+      while (a < 15 && cab.decision (ctx)) a++;
+      if (a >= 15) {                                  // Exp-Golomb (k = 0) suffix, bypass coded
+        int e = 0;
+        while (cab.bypass()) { a += 1 << e; if (++e > 20) return -1; }
+        while (e--) a += cab.bypass() << e;
+      }
+      gt1++;
+    } else eq1++;
+    out[scan[scan_off + pos[k]]] = (int16_t) (cab.bypass() ? -a : a);
+  }
+  return n;
+}
+
+int Decoder::Impl::parse_residual_cabac (lh264_mb_rec& m, int mb_addr, int16_t* lev, uint32_t& coded, bool i16, int cbp) {
+  uint8_t* nz = &nzc[(size_t)mb_addr * 24];
+  uint32_t& cbf = cabmb[mb_addr].cbf;
+  const bool t8 = m.flags & LH264_MBF_TRANSFORM8x8;
+  if (i16) {                                          // Intra16x16DCLevel
+    int16_t dc[16];
+    memset (dc, 0, sizeof (dc));
+    const int tc = cabac_block (0, cbf_inc (mb_addr, -1, 24, -1, 24), dc, kZigzag4x4, 0);
+    if (tc < 0) return -1;
+    if (tc) cbf |= 1u << 24;
+    for (int r = 0; r < 16; r++) if (dc[r]) { const int z = kRtoZ[r]; lev[16 * z] = dc[r]; coded |= 1u << z; }
+  }
+  for (int q = 0; q < 4; q++) {
+    if (! (cbp & (1 << q))) { for (int k = 0; k < 4; k++) nz[kZtoR[4 * q + k]] = 0; continue; }
+    if (t8) {
+      const int tc = cabac_block (5, -1, lev + 64 * q, kZigzag8x8, 0);
+      if (tc < 0) return -1;
+      for (int k = 0; k < 4; k++) { const int r = kZtoR[4 * q + k]; nz[r] = (uint8_t)tc; cbf |= 1u << r; }   // coded_block_flag inferred 1
+      if (tc) coded |= 0xFu << (4 * q);
+      continue;
+    }
+    for (int k = 0; k < 4; k++) {
+      const int z = 4 * q + k, r = kZtoR[z], bx = r & 3, by = r >> 2;
+      const int inc = cbf_inc (mb_addr, bx > 0 ? r - 1 : -1, r + 3, by > 0 ? r - 4 : -1, r + 12);
+      const int tc = i16 ? cabac_block (1, inc, lev + 16 * z, kZigzag4x4, 1) : cabac_block (2, inc, lev + 16 * z, kZigzag4x4, 0);
+      if (tc < 0) return -1;
+      nz[r] = (uint8_t)tc;
+      if (tc) { coded |= 1u << z; cbf |= 1u << r; }
+    }
+  }
+  const int cc = cbp >> 4;
+  if (cc) {
+    for (int p = 0; p < 2; p++) {                     // ChromaDCLevel
+      int16_t dc[64];
+      memset (dc, 0, sizeof (dc));
+      const int tc = cabac_block (3, cbf_inc (mb_addr, -1, 25 + p, -1, 25 + p), dc, kChromaDcScan, 0);
+      if (tc < 0) return -1;
+      if (tc) cbf |= 1u << (25 + p);
+      for (int b = 0; b < 4; b++) if (dc[16 * b]) { lev[16 * (16 + 4 * p + b)] = dc[16 * b]; coded |= 1u << (16 + 4 * p + b); }
+    }
+  }
+  for (int p = 0; p < 2; p++) for (int b = 0; b < 4; b++) {
+      const int bit = 16 + 4 * p + b;
+      if (cc & 2) {                                   // ChromaACLevel
+        const int inc = cbf_inc (mb_addr, (b & 1) ? bit - 1 : -1, bit + 1, (b & 2) ? bit - 2 : -1, bit + 2);
+        const int tc = cabac_block (4, inc, lev + 16 * bit, kZigzag4x4, 1);
+        if (tc < 0) return -1;
+        nz[bit] = (uint8_t)tc;
+        if (tc) { coded |= 1u << bit; cbf |= 1u << bit; }
+      } else nz[bit] = 0;
+    }
+  return 0;
+}
+
+// ---- slice_data( ) (7.3.4), CABAC ----------------------------------------------------------------------------
+int Decoder::Impl::parse_slice_data_cabac (BitReader& br, Decoder* self) {
+  int mb_addr = sh.first_mb;
+  const int first = mb_addr;
+  qp = sh.slice_qp;
+  br.align();                                         // cabac_alignment_one_bit
+  cab.init_contexts (sh.slice_type == SLICE_I ? 0 : 1 + sh.cabac_init_idc, sh.slice_qp);
+  cab.start (&br);
+  cabac_on = true;
+  last_dqp_nz = false;
+  int rc = 0;
+  while (mb_addr < n_mbs) {
+    bool skip = false;
+    if (sh.slice_type != SLICE_I) {
+      const int mbx = mb_addr % mb_w, mby = mb_addr / mb_w;
+      auto cond = [&] (int n) { return mb_avail (n) && mbs[n].mb_type != LH264_MB_PSKIP; };
+      skip = cab.decision (11 + (cond (nb_mb (mbx, mby, -1, 0)) ? 1 : 0) + (cond (nb_mb (mbx, mby, 0, -1)) ? 1 : 0));
+    }
+    if (parse_mb (br, mb_addr, skip, nullptr) < 0 || br.overrun()) { rc = -1; self->stats_.errors++; break; }
+    mb_addr++;
+    if (cab.terminate()) break;                       // end_of_slice_flag
+  }
+  cabac_on = false;
+  lh264_slice_rec& sr = slices.back();
+  sr.num_mbs = mb_addr - first;
+  decoded += mb_addr - first;
+  self->stats_.mbs += mb_addr - first;
+  return rc;
 }
 
 // ---- slice_data( ) (7.3.4), CAVLC --------------------------------------------------------------------------
@@ -803,7 +1121,7 @@ int Decoder::decode (const uint8_t* data, size_t len, unsigned long long timesta
       if (rc < 0) { last_err = rc; stats_.errors++; continue; }
       const Pps& pps = D.pps[sh.pps_id];
       const Sps& sps = D.sps[pps.sps_id];
-      if (pps.cabac) { last_err = -20; stats_.errors++; continue; }      // CABAC parse: not built yet
+      if (pps.cabac && D.want_model) { last_err = -20; stats_.errors++; continue; }   // the recompression model of CABAC streams: SURVEY 8f N4
       if (sps.scaling_matrix_present || pps.scaling_matrix_present) { last_err = -21; stats_.errors++; continue; }
       if (D.open && D.is_new_picture (D.sh0, sh)) D.finish_picture (this);
       if (!D.open) {
@@ -842,7 +1160,7 @@ int Decoder::decode (const uint8_t* data, size_t len, unsigned long long timesta
       br.seek (sh.header_bits);
       D.slice_rbsp.assign (D.rbsp.begin(), D.rbsp.begin() + std::min (D.rbsp.size(), (sh.header_bits + 7) / 8));   // for last_slice()
       last_slice_.decoded = true; last_slice_.cabac = pps.cabac; last_slice_.rbsp = D.slice_rbsp.data(); last_slice_.header_bits = sh.header_bits;
-      if (D.parse_slice_data (br, this) < 0) last_err = -40;
+      if ((pps.cabac ? D.parse_slice_data_cabac (br, this) : D.parse_slice_data (br, this)) < 0) last_err = -40;
       if (D.decoded >= D.n_mbs) D.finish_picture (this);
     } else if (type == NAL_END_SEQ || type == NAL_END_STREAM) {
       D.finish_picture (this);

@@ -9,15 +9,19 @@ SHA1 = json.load(open(os.path.join(HERE, "golden", "stream_sha1.json")))
 LIB_DIR = os.path.join(ROOT, "losslessh264_b200", "_lib")
 
 # Streams of the parity corpus that the host decoder does not cover yet, with the reason.  They are
-# "next" rows of SURVEY.md §8f (N3: error concealment / PCM in CABAC; CABAC parse), not silently skipped.
+# "next" rows of SURVEY.md §8f (N3: error concealment), not silently skipped.
 NOT_YET = {
     "BA_MW_D_IDR_LOST.264": "lost IDR: needs the reference's error concealment (SURVEY §8f N3)",
     "Error_I_P.264": "damaged stream: needs error concealment (SURVEY §8f N3)",
-    "QCIF_2P_I_allIPCM.264": "CABAC entropy coding: host CABAC parse not built yet",
-    "test_qcif_cabac.264": "CABAC entropy coding: host CABAC parse not built yet",
-    "tibbycabac.264": "CABAC entropy coding: host CABAC parse not built yet",
 }
+# CABAC streams decode (host CABAC parse, BASELINE config 2); their recompression model is SURVEY §8f N4 (outside the parity
+# contract: `esCabac` / CABAC_HACK), so the model / `.pip` tests run on the CAVLC streams only.
+CABAC = {"QCIF_2P_I_allIPCM.264", "test_qcif_cabac.264", "tibbycabac.264"}
+
+
+def decodable_streams():
+    return sorted(f for f in os.listdir(STREAM_DIR) if f in SHA1 and f not in NOT_YET)
 
 
 def cavlc_streams():
-    return sorted(f for f in os.listdir(STREAM_DIR) if f in SHA1 and f not in NOT_YET)
+    return [f for f in decodable_streams() if f not in CABAC]
