@@ -330,7 +330,7 @@ static void run_group (const Options& o, const std::vector<std::vector<uint8_t> 
     tq = now();
     // The decoded pictures of step t-1 are still on their way to the host (copy stream) while step t's records went up and its
     // kernels ran: wait for them now, start this step's copy, then hash the previous pictures while it runs.
-    struct Out { bool valid = false; std::vector<int> lv; size_t per = 0; int idx = 0; };
+    struct Out { bool valid = false; std::vector<int> lv; std::vector<char> shown; size_t per = 0; int idx = 0; };
     static thread_local Out prev;
     auto consume_prev = [&] () {
       if (!prev.valid) return;
@@ -339,7 +339,7 @@ static void run_group (const Options& o, const std::vector<std::vector<uint8_t> 
       pool.wait();                                      // (the pool runs one job at a time: the parse of step t+2 first)
       const double th = now();
       const Out p = prev;
-      pool.start ((int)p.lv.size(), [&, p] (int k) { streams[p.lv[k]].yuv.update (out_pin[p.idx] + p.per * k, p.per); });
+      pool.start ((int)p.lv.size(), [&, p] (int k) { if (p.shown[k]) streams[p.lv[k]].yuv.update (out_pin[p.idx] + p.per * k, p.per); });
       pool.wait();
       t_hash += now() - th;
     };
@@ -355,6 +355,8 @@ static void run_group (const Options& o, const std::vector<std::vector<uint8_t> 
         t_call[3] += now() - tq;
         consume_prev();
         prev.valid = true; prev.lv = live; prev.per = per; prev.idx = oi;
+        prev.shown.clear();
+        for (const Placed& st : arena[buf].placed) prev.shown.push_back (st.info.output ? 1 : 0);   // pictures before a stream's first IDR are held back
       } else {                                           // mixed geometry: picture by picture
         consume_prev();
         for (const Placed& st : arena[buf].placed) {
@@ -364,7 +366,7 @@ static void run_group (const Options& o, const std::vector<std::vector<uint8_t> 
           uint8_t* y = out_host.data();
           if (lh264_picture_read (ctx, streams[i].gpu_stream, st.info.slot, st.info.crop_x, st.info.crop_y, w, h, y, w, y + (size_t)w * h, y + (size_t)w * h + (size_t)cw * ch, cw, 1) != LH264_OK)
             FAIL ("lh264_picture_read: %s\n", lh264_last_error());
-          if (want_hash) streams[i].yuv.update (y, out_host.size());
+          if (want_hash && st.info.output) streams[i].yuv.update (y, out_host.size());
         }
       }
     } else {

@@ -59,6 +59,10 @@ struct Decoder::Impl {
   bool open = false;
   SliceHeader sh0;                       // first slice header of the picture
   int cur_slot = 0, decoded = 0;
+  // the reference holds its output back until the first IDR picture has been decoded (bFreezeOutput under the freeze error
+  // concealment modes h264dec selects, decoder_core.cpp:56-217): pictures of a stream whose leading IDR was lost are parsed,
+  // modelled and reconstructed, but marked `output = false` for the sink and not handed out
+  bool frozen = true;
   unsigned long long ts = 0;
   std::vector<lh264_mb_rec> mbs;
   std::vector<int16_t> coefs;
@@ -328,6 +332,8 @@ struct Decoder::Impl {
     info.frame_num = sh0.frame_num; info.poc_lsb = sh0.poc_lsb; info.idr_pic_id = sh0.idr_pic_id; info.nal_ref_idc = sh0.nal_ref_idc;
     info.slot = cur_slot; info.serial = serial++; info.complete = decoded >= n_mbs; info.timestamp = ts;
     int rc = 0;
+    if (sh0.idr) frozen = false;
+    info.output = !frozen;
     if (!slices.empty()) rc = sink->submit (d, info);
     if (want_model && !mslices.empty()) {
       lh264_model_picture mp;
@@ -339,7 +345,7 @@ struct Decoder::Impl {
     mark_current();
     self->stats_.pictures++;
     self->stats_.coef_blocks += coefs.size() / 16;
-    self->out_.push_back (info);
+    if (info.output) self->out_.push_back (info);
     return rc;
   }
 

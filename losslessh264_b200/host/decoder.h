@@ -27,6 +27,7 @@ struct DecodedPictureInfo {
   int slot;
   int serial;
   bool complete;                         // every macroblock was decoded
+  bool output = true;                    // false: decoded before the first IDR picture of the stream, held back (see decoder.cpp `frozen`)
   unsigned long long timestamp;
 };
 

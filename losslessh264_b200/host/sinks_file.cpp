@@ -19,6 +19,7 @@ int LhfbSink::submit_model (const lh264_model_picture& pic, const DecodedPicture
 int LhfbSink::configure (int mb_w, int mb_h, int) { mb_w_ = mb_w; mb_h_ = mb_h; return 0; }
 int LhfbSink::submit (const lh264_picture_desc& pic, const DecodedPictureInfo& info) {
   if (!f_) return -1;
+  if (!info.output) return 0;                        // held back by the decoder: not part of the decoded sequence
   auto w32 = [&] (int32_t v) { fwrite (&v, 4, 1, f_); };
   for (int s = 0; s < pic.n_slices; s++) {
     const lh264_slice_rec& sl = pic.slices[s];

@@ -11,8 +11,7 @@ LIB_DIR = os.path.join(ROOT, "losslessh264_b200", "_lib")
 # Streams of the parity corpus that the host decoder does not cover yet, with the reason.  They are
 # "next" rows of SURVEY.md §8f (N3: error concealment), not silently skipped.
 NOT_YET = {
-    "BA_MW_D_IDR_LOST.264": "lost IDR: needs the reference's error concealment (SURVEY §8f N3)",
-    "Error_I_P.264": "damaged stream: needs error concealment (SURVEY §8f N3)",
+    "Error_I_P.264": "damaged stream with resolution changes: needs the reference's error concealment (SURVEY §8f N3)",
 }
 # CABAC streams decode (host CABAC parse, BASELINE config 2); their recompression model is SURVEY §8f N4 (outside the parity
 # contract: `esCabac` / CABAC_HACK), so the model / `.pip` tests run on the CAVLC streams only.
