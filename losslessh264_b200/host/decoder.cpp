@@ -974,22 +974,60 @@ int Decoder::Impl::parse_slice_data_cabac (BitReader& br, Decoder* self) {
   cabac_on = true;
   last_dqp_nz = false;
   int rc = 0;
+  // model records: the reference codes a one-macroblock "skip run" (0 or 1) in front of every macroblock of a CABAC slice and
+  // takes the stop bit from end_of_slice_flag (WelsDecodeSliceForNonRecoding decode_slice.cpp:2197-2226, WelsDecodeMbCabacPSlice
+  // :1164-1228)
+  const size_t rec0 = mrecs.size();
+  int m_cached_qp = 0, m_last_dqp = 0;
   while (mb_addr < n_mbs) {
     bool skip = false;
     if (sh.slice_type != SLICE_I) {
       const int mbx = mb_addr % mb_w, mby = mb_addr / mb_w;
       auto cond = [&] (int n) { return mb_avail (n) && mbs[n].mb_type != LH264_MB_PSKIP; };
+      st_cbp[mb_addr] = 0; st_chroma[mb_addr] = 0;    // pCbp / pChromaPredMode are reset before the skip flag is read (:1172-1174)
       skip = cab.decision (11 + (cond (nb_mb (mbx, mby, -1, 0)) ? 1 : 0) + (cond (nb_mb (mbx, mby, 0, -1)) ? 1 : 0));
     }
-    if (parse_mb (br, mb_addr, skip, nullptr) < 0 || br.overrun()) { rc = -1; self->stats_.errors++; break; }
+    lh264_model_mb* mr = nullptr;
+    if (want_model) {
+      mrecs.emplace_back ();
+      mr = &mrecs.back();
+      memset (mr, 0, sizeof (*mr));
+      mr->mb_addr = (uint32_t)mb_addr; mr->mb_in_slice = (uint16_t)std::min<size_t> (mrecs.size() - 1 - rec0, 65535);
+      mr->flags |= LH264_MM_EMIT_SKIP_RUN | (skip ? LH264_MM_STOP_IN_SKIP : LH264_MM_WRITE_BLOCK);
+      mr->skip_run = skip ? 1 : 0;
+    }
+    if (parse_mb (br, mb_addr, skip, mr) < 0 || br.overrun()) { rc = -1; self->stats_.errors++; if (mr) mrecs.pop_back(); break; }
+    if (mr && !skip) {
+      const int d = (int)mr->luma_qp - m_cached_qp;
+      mr->qp_delta = (int8_t)d;
+      mr->flags |= (uint16_t) ((m_last_dqp < 0 ? 0 : (m_last_dqp == 0 ? 1 : 2)) << LH264_MM_LASTDQP_SHIFT);
+      m_cached_qp = mr->luma_qp;
+      if (d) m_last_dqp = d;
+    }
     mb_addr++;
-    if (cab.terminate()) break;                       // end_of_slice_flag
+    const bool eos = cab.terminate();                 // end_of_slice_flag
+    if (mr && eos) mr->flags |= LH264_MM_STOP_BIT;
+    if (eos) break;
   }
   cabac_on = false;
   lh264_slice_rec& sr = slices.back();
   sr.num_mbs = mb_addr - first;
   decoded += mb_addr - first;
   self->stats_.mbs += mb_addr - first;
+  if (want_model) {
+    lh264_model_slice ms;
+    memset (&ms, 0, sizeof (ms));
+    ms.first_rec = (int32_t)rec0; ms.n_recs = (int32_t) (mrecs.size() - rec0);
+    ms.frame_num = sh.frame_num;
+    ms.slice_type = (uint8_t) (sh.slice_type == SLICE_I ? 2 : 0);
+    ms.num_ref_idx_l0 = (uint8_t) (sh.slice_type == SLICE_P ? sh.num_ref_idx_l0 : P->num_ref_idx_l0_default);
+    // the reference hands its bit reader back byte aligned (RestoreCabacDecEngineToBS), so `7 - (iLeftBits & 7)` is always 7:
+    // the low seven bits of the slice's last byte go to the PADBYTE stream, whatever the arithmetic decoder consumed of them
+    ms.n_pad_bits = 7;
+    ms.pad_bits = (uint8_t) (br.size_bits() ? (br.data()[br.payload_end() >> 3] & 0x7fu) : 0);
+    ms.chroma_format_idc = 1;
+    mslices.push_back (ms);
+  }
   return rc;
 }
 
@@ -1127,7 +1165,6 @@ int Decoder::decode (const uint8_t* data, size_t len, unsigned long long timesta
       if (rc < 0) { last_err = rc; stats_.errors++; continue; }
       const Pps& pps = D.pps[sh.pps_id];
       const Sps& sps = D.sps[pps.sps_id];
-      if (pps.cabac && D.want_model) { last_err = -20; stats_.errors++; continue; }   // the recompression model of CABAC streams: SURVEY 8f N4
       if (sps.scaling_matrix_present || pps.scaling_matrix_present) { last_err = -21; stats_.errors++; continue; }
       if (D.open && D.is_new_picture (D.sh0, sh)) D.finish_picture (this);
       if (!D.open) {

@@ -28,6 +28,7 @@
  * zero bits: prob is kept XOR 0x80) — observationally identical.
  */
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include "../include/lh264_b200.h"
@@ -134,7 +135,10 @@ static writer* tagw (mo_stream* s, int tag) {         /* CompressionStream::tag(
   if (!w->used) w_start (w);
   return w;
 }
+static int mo_trace = -1;                                               /* MO_TRACE=1: every decision as "tag prob bit" on stderr */
 static void emit_bit (mo_stream* s, int tag, int bit, dynprob* p) {   /* ArithmeticCodedOutput::emitBit :407-435 */
+  if (mo_trace < 0) mo_trace = getenv ("MO_TRACE") != NULL;
+  if (mo_trace) fprintf (stderr, "%d %d %d\n", tag, (int)dp_prob (p), bit);
   w_write (tagw (s, tag), bit, dp_prob (p));
   dp_update (p, bit);
 }

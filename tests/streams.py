@@ -13,9 +13,10 @@ LIB_DIR = os.path.join(ROOT, "losslessh264_b200", "_lib")
 NOT_YET = {
     "Error_I_P.264": "damaged stream with resolution changes: needs the reference's error concealment (SURVEY §8f N3)",
 }
-# CABAC streams decode (host CABAC parse, BASELINE config 2); their recompression model is SURVEY §8f N4 (outside the parity
-# contract: `esCabac` / CABAC_HACK), so the model / `.pip` tests run on the CAVLC streams only.
-CABAC = {"QCIF_2P_I_allIPCM.264", "test_qcif_cabac.264", "tibbycabac.264"}
+# CABAC streams decode and compress (host CABAC parse; the model hand-off follows the reference's one-macroblock skip runs and
+# end_of_slice stop bits); their DECOMPRESS direction needs a CABAC slice-data writer (`esCabac`), so the
+# `.pip` -> `.264` tests run on the CAVLC streams only.
+CABAC = {"QCIF_2P_I_allIPCM.264", "test_qcif_cabac.264", "tibbycabac.264", "syn_cif_cabac_4slices_ltr_6f.264", "syn_qcif_cabac_qp38_8f.264"}
 
 
 def decodable_streams():

@@ -11,7 +11,7 @@ import pytest
 
 from oracle import oracle
 from streams import LIB_DIR, STREAM_DIR
-from test_model_oracle import CPU_SET
+from test_pip_expand import CPU_SET
 from test_pip_expand import write_pip_cpu
 
 pytestmark = pytest.mark.gpu

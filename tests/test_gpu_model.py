@@ -5,11 +5,11 @@ import os
 import pytest
 
 from test_model_oracle import GOLD, check_tags, model_pictures
-from streams import cavlc_streams
+from streams import decodable_streams
 
 pytestmark = pytest.mark.gpu
 
-ALL = [s for s in cavlc_streams() if s in GOLD and "tags" in GOLD[s]]
+ALL = [s for s in decodable_streams() if s in GOLD and "tags" in GOLD[s]]
 
 
 def run_cuda(ctx, pics, with_8x8):

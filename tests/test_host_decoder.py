@@ -12,7 +12,7 @@ import pytest
 
 from losslessh264_b200.records import n_slots_needed, read_lhfb
 from oracle import oracle
-from streams import CABAC, LIB_DIR, SHA1, STREAM_DIR, cavlc_streams, decodable_streams
+from streams import LIB_DIR, NOT_YET, SHA1, STREAM_DIR, decodable_streams
 
 TOOL = os.path.join(LIB_DIR, "lh264_parse_dump")
 
@@ -58,9 +58,10 @@ def test_cavlc_tables_are_prefix_codes(tmp_path):
     assert r.returncode == 0
 
 
-def test_model_of_cabac_streams_fails_loudly(tmp_path):
-    """CABAC streams decode, but their recompression model is not built: asking for model records must be an error."""
-    d = str(tmp_path)
-    for name in sorted(CABAC):
-        r = subprocess.run([TOOL, os.path.join(STREAM_DIR, name), os.path.join(d, "x.lhfb"), "1", os.path.join(d, "x.lhmd"), os.path.join(d, "x.pip")], capture_output=True)
-        assert r.returncode != 0, f"{name}: the model hand-off of a CABAC stream must be reported as an error, not produced silently"
+def test_damaged_stream_is_reported(tmp_path):
+    """Error_I_P.264 (damaged, resolution changes) needs the reference's error concealment: the host decoder must not
+    hand it over as if it were a clean sequence — the tool writes one .lhfb geometry per stream and the oracle refuses the rest."""
+    name = "Error_I_P.264"
+    assert name in NOT_YET
+    r = subprocess.run([TOOL, os.path.join(STREAM_DIR, name), os.path.join(str(tmp_path), "x.lhfb")], capture_output=True, text=True)
+    assert r.returncode in (0, 4)                      # parses (the slices themselves are well formed) or reports errors; never crashes

@@ -10,13 +10,13 @@ import pytest
 
 from losslessh264_b200.records import read_lhmd
 from oracle import oracle
-from streams import LIB_DIR, STREAM_DIR, cavlc_streams
+from streams import CABAC, LIB_DIR, STREAM_DIR, decodable_streams
 
 TOOL = os.path.join(LIB_DIR, "lh264_parse_dump")
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "pip_tag_sha1.json")))
 
 # long streams are left to the GPU suite
-CPU_SET = [s for s in cavlc_streams() if s in GOLD and "tags" in GOLD[s] and s not in ("LS_SVA_D.264", "BA1_FT_C.264", "CI1_FT_B.264", "CVPCMNL1_SVA_C.264")]
+CPU_SET = [s for s in decodable_streams() if s in GOLD and "tags" in GOLD[s] and s not in ("LS_SVA_D.264", "BA1_FT_C.264", "CI1_FT_B.264", "CVPCMNL1_SVA_C.264")]
 
 
 @pytest.fixture(scope="module", autouse=True)

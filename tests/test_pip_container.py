@@ -13,8 +13,7 @@ from streams import LIB_DIR, SHA1, STREAM_DIR
 
 TOOL = os.path.join(LIB_DIR, "lh264_parse_dump")
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "pip_tag_sha1.json")))
-CABAC = {"QCIF_2P_I_allIPCM.264", "test_qcif_cabac.264", "tibbycabac.264"}      # host CABAC parse: SURVEY 8f N3
-NAMES = sorted(n for n in GOLD if "default" in GOLD[n] and n not in CABAC)
+NAMES = sorted(n for n in GOLD if "default" in GOLD[n])
 
 
 @pytest.fixture(scope="module", autouse=True)

@@ -35,7 +35,7 @@ def synth_yuv(w, h, frames, seed):
     return bytes(out)
 
 
-def encode(w, h, frames, seed, out_path, qp=26, slices=1, ltr=0):
+def encode(w, h, frames, seed, out_path, qp=26, slices=1, ltr=0, cabac=0):
     enc = os.path.join(ROOT, "oracle", "_ref", "h264enc")
     with tempfile.TemporaryDirectory() as td:
         for f in ("welsenc.cfg", "layer2.cfg"):
@@ -47,6 +47,8 @@ def encode(w, h, frames, seed, out_path, qp=26, slices=1, ltr=0):
         cmd += ["-slcmd", "0", "1", "-slcnum", "0", str(slices)] if slices > 1 else ["-slcmd", "0", "0"]
         if ltr:
             cmd += ["-ltrnum", "2"]
+        if cabac:
+            cmd += ["-cabac", "1"]
         subprocess.run(cmd, cwd=td, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
         shutil.copy(os.path.join(td, "out.264"), out_path)
     return os.path.getsize(out_path)
@@ -60,3 +62,6 @@ if __name__ == "__main__":
     print("syn1080p", encode(1920, 1080, 16, 1234, os.path.join(a.out, "syn1080p_cbp_ippp_16f.264")))
     print("syn720p", encode(1280, 720, 8, 720, os.path.join(a.out, "syn720p_8f.264")))
     print("syn_qcif_multislice", encode(176, 144, 8, 5, os.path.join(a.out, "syn_qcif_4slices_8f.264"), slices=4))
+    # CABAC twins (host CABAC parse): multi-slice + two long-term references, and a coarse-QP single-slice stream
+    print("syn_cif_cabac", encode(352, 288, 6, 7, os.path.join(a.out, "syn_cif_cabac_4slices_ltr_6f.264"), qp=28, slices=4, ltr=1, cabac=1))
+    print("syn_qcif_cabac", encode(176, 144, 8, 9, os.path.join(a.out, "syn_qcif_cabac_qp38_8f.264"), qp=38, cabac=1))
