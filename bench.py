@@ -222,7 +222,7 @@ def main():
     ap.add_argument("--e2e-streams", type=int, default=512, help="streams on the host-buffer path (all threads together)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-expand", action="store_true", help="skip the decompress-direction leg")
-    ap.add_argument("--expand-streams", type=int, default=1024, help="streams of the decompress-direction leg (one warp each)")
+    ap.add_argument("--expand-streams", type=int, default=2048, help="streams of the decompress-direction leg (one warp each; throughput peaks near 2048, profiles/r1_summary.md)")
     args = ap.parse_args()
     if args.impl == "reference":
         return bench_reference(args)
@@ -429,7 +429,7 @@ def main():
         batches, mbatches = [], []
         for h_ in mstreams:
             ctx.model_close(h_)
-        line["expand"] = bench_expand(ctx, mpics, min(S, args.expand_streams), world)
+        line["expand"] = bench_expand(ctx, mpics, args.expand_streams, world)
     if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(REF_DEC):
         k, cores = reference_concurrency()
         with tempfile.TemporaryDirectory() as tmp:

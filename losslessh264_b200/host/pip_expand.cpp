@@ -65,7 +65,7 @@ bool expand_plan (const uint8_t* def_in, size_t n, ExpandPlan& plan) {
       if (parse_slice_header (br, ref_idc, type, sps.data(), pps.data(), sh) < 0) { plan.error = "slice header does not parse"; return false; }
       const Pps& pp = pps[sh.pps_id];
       const Sps& sp = sps[pp.sps_id];
-      if (pp.cabac) { plan.error = "CABAC slice: not built (SURVEY 8f N3)"; return false; }
+      if (pp.cabac) { plan.error = "CABAC slice: the decompress direction needs a CABAC slice-data writer, not built (SURVEY 8f N4)"; return false; }
       // the header is followed by exactly one stop bit and zero padding (pip_container.cpp: unit_end)
       const uint8_t* rb = nal.data() + 1;
       const size_t hb = sh.header_bits, rl = plen - 1;
