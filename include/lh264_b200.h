@@ -371,7 +371,8 @@ typedef struct lh264_decode_slice {
   uint8_t  slice_type;       /* 0 P, 2 I                                                                                    */
   uint8_t  num_ref_idx_l0;   /* active L0 reference count of the slice (PPS default for I slices)                           */
   uint8_t  slice_qp;         /* SliceQPY                                                                                    */
-  uint8_t  flags;            /* bit0 PPS transform_8x8_mode_flag, bit1 PPS constrained_intra_pred_flag                      */
+  uint8_t  flags;            /* bit0 PPS transform_8x8_mode_flag, bit1 PPS constrained_intra_pred_flag, bit2 PPS
+                                entropy_coding_mode_flag (CABAC slice data), bits 3-4 cabac_init_idc                           */
   uint32_t header_bits;      /* bit position of slice_data() in the slice RBSP (trailing alignment bits, :3133-3147)        */
 } lh264_decode_slice;
 

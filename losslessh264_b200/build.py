@@ -26,6 +26,7 @@ def _newest(paths):
 def build_library(force: bool = False, verbose: bool = False) -> str:
     so = library_path()
     srcs = [os.path.join(_SRC, f) for f in os.listdir(_SRC)] + [os.path.join(os.path.dirname(_HERE), "include", "lh264_b200.h")]
+    srcs += [os.path.join(_HERE, "host", f) for f in ("cavlc_tables.h", "cabac_tables.h")]      # tables the decompress kernel includes
     if not force and os.path.exists(so) and os.path.getmtime(so) >= _newest(srcs):
         return so
     os.makedirs(_OUT, exist_ok=True)

@@ -9,6 +9,8 @@
 #pragma once
 #define LH264_CAVLC_TABLE __device__ const
 #include "../host/cavlc_tables.h"
+#define LH264_CABAC_TABLE __device__ const
+#include "../host/cabac_tables.h"
 #define MD_FN __device__
 #define MD_FN_NOINLINE __device__ __noinline__
 #define MD_TABLE __device__ const
@@ -166,7 +168,7 @@ __global__ void __launch_bounds__ (32, 28) k_model_decode (MdJobDev* jobs, int n
         so.reserved = 0; so.reserved2 = 0;
         so.n_mbs = (uint32_t)md_slice (st, c, sl, prior_valid, bw, sc, &so.pad_bits, &so.n_pad_bits);
         mb_flush (bw);
-        so.byte_offset = off; so.n_bits = (uint32_t)mb_bits (bw);
+        so.byte_offset = off; so.n_bits = (uint32_t) (mb_bits (bw) - (uint64_t)bw.trim);
         job.sout[s] = so;
         off += (mb_bits (bw) + 7) / 8;
       }

@@ -66,13 +66,15 @@ MD_FN uint32_t md_read (MdReader& r, uint32_t prob) {
 }
 
 // ---- per-stream state ------------------------------------------------------------------------------------------
+#define MD_NB_STRIDE 48
 struct MdStream {
   uint32_t* priors;               // pruned prior table (model_layout.h), zero = fresh
   CtxRec* frame[2];               // FreqImage ring (decoded_macroblock.h:106-191)
   uint8_t* ipm;                   // [mb][16] Intra4x4/8x8PredMode per raster 4x4 block (2 for every other MB type)
   int32_t* mb_slice;              // [mb] number of the slice that last coded the MB (availability, 6.4.8)
   uint8_t* mb_intra;              // [mb] 1 = intra MB (constrained_intra_pred)
-  uint8_t* tcoef;                 // [mb][24] total_coeff per 4x4 block: 16 luma (raster), 4 Cb, 4 Cr (nC context, 9.2.1)
+  uint8_t* tcoef;                 // [mb][MD_NB_STRIDE] what the entropy coder's context selection reads from a neighbouring macroblock.
+                                  // CAVLC slices: total_coeff per 4x4 block, 16 luma (raster), 4 Cb, 4 Cr (nC, 9.2.1); CABAC: see cb_mb
   int32_t width, height, frame_len, cur, lastFrameId, max_mbs, slice_counter, error;
   MdReader rd[CT_COUNT];
   uint32_t present;               // compact tags that have a side stream
@@ -206,13 +208,17 @@ struct MdScratch {
   int16_t lev[384];               // its levels, layout of the coefficient pool (24 chunks of 16)
   int32_t level[16], run[16];     // cw_residual_block
   uint8_t cnt[24];
+  // CABAC slices: arithmetic encoder (9.3.4.2) and the context variables of the slice, (pStateIdx << 1) | valMPS
+  uint32_t cb_low, cb_range, cb_outstanding, cb_first;
+  uint8_t cb_state[460];
 };
 
 // ---- bit sink of the re-serialiser ------------------------------------------------------------------------------------
 struct MdBits {
   uint8_t* out; uint64_t cap_bits, n_bits; uint32_t acc; int n_acc; int overflow;
+  int trim;                       // bits at the end that belong to the caller's trailer (CABAC: the flush ends with the rbsp_stop_one_bit)
 };
-MD_FN void mb_init (MdBits& b, uint8_t* out, uint64_t cap_bytes) { b.out = out; b.cap_bits = cap_bytes * 8; b.n_bits = 0; b.acc = 0; b.n_acc = 0; b.overflow = 0; }
+MD_FN void mb_init (MdBits& b, uint8_t* out, uint64_t cap_bytes) { b.out = out; b.cap_bits = cap_bytes * 8; b.n_bits = 0; b.acc = 0; b.n_acc = 0; b.overflow = 0; b.trim = 0; }
 MD_FN void mb_put (MdBits& b, uint32_t v, int n) {              // n <= 24
   if (n <= 0) return;
   b.acc = (b.acc << n) | (v & ((1u << n) - 1u));
@@ -296,7 +302,7 @@ MD_FN_NOINLINE int cw_residual_block (MdBits& bw, MdScratch& sc, int nC, int max
 }
 
 // per-slice state of the syntax writer
-struct CwSlice { int slice_type /*0 P, 2 I*/, num_ref_idx_l0, qp, transform_8x8_mode; };
+struct CwSlice { int slice_type /*0 P, 2 I*/, num_ref_idx_l0, qp, transform_8x8_mode, cabac, last_dqp_nz; };
 
 MD_FN int cw_nC (int nA, int nB) { if (nA >= 0 && nB >= 0) return (nA + nB + 1) >> 1; return nA >= 0 ? nA : (nB >= 0 ? nB : 0); }
 
@@ -392,6 +398,309 @@ MD_FN_NOINLINE bool cw_mb (MdBits& bw, MdScratch& sc, CwSlice& s, uint8_t* tc, c
   return true;
 }
 
+
+// ---- CABAC slice_data() writer (decompress direction of CABAC streams) ---------------------------------------------------
+// Replaces EncoderState::writeMbSynCabac (decode_slice.cpp:1536-1539 -> encoder/core/src/svc_set_mb_syn_cabac.cpp, set_mb_syn_cabac.cpp):
+// the arithmetic encoder of 9.3.4.2, and for every syntax element the binarisation and ctxIdx rule the host parser reads with
+// (host/decoder.cpp cabac_*).  Per macroblock, MD_NB_STRIDE bytes of st.tcoef hold what context selection needs from a neighbour:
+//   [0..3] coded_block_flag word (bits 0..15 luma raster, 16..19 Cb AC, 20..23 Cr AC, 24 luma DC, 25 Cb DC, 26 Cr DC)
+//   [4] coded_block_pattern  [5] intra_chroma_pred_mode  [6] kind (1 skip, 2 inter, 3 I_NxN, 4 I16x16)  [7] transform 8x8
+//   [8..11] ref_idx per 8x8  [12..43] |mvd| per raster 4x4 block and component, saturated at 128
+enum { CB_SKIP = 1, CB_INTER = 2, CB_INXN = 3, CB_I16 = 4 };
+MD_TABLE uint8_t cb_sig8[63] = { 0, 1, 2, 3, 4, 5, 5, 4, 4, 3, 3, 4, 4, 4, 5, 5, 4, 4, 4, 4, 3, 3, 6, 7, 7, 7, 8, 9, 10, 9, 8, 7,
+                                 7, 6, 11, 12, 13, 11, 6, 7, 8, 9, 14, 10, 9, 8, 6, 11, 12, 13, 11, 6, 9, 14, 10, 9, 11, 12, 13, 11, 14, 10, 12 };
+MD_TABLE uint8_t cb_last8[63] = { 0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2, 2,
+                                  3, 3, 3, 3, 3, 3, 3, 3, 4, 4, 4, 4, 4, 4, 4, 4, 5, 5, 5, 5, 6, 6, 6, 6, 7, 7, 7, 7, 8, 8, 8 };
+MD_FN uint32_t cb_word (const uint8_t* nb) { return (uint32_t)nb[0] | ((uint32_t)nb[1] << 8) | ((uint32_t)nb[2] << 16) | ((uint32_t)nb[3] << 24); }
+MD_FN void cb_set_word (uint8_t* nb, uint32_t w) { nb[0] = (uint8_t)w; nb[1] = (uint8_t) (w >> 8); nb[2] = (uint8_t) (w >> 16); nb[3] = (uint8_t) (w >> 24); }
+
+MD_FN void cb_slice_begin (MdBits& bw, MdScratch& sc, int cls, int slice_qp, uint32_t header_bits) {
+  for (uint32_t i = header_bits & 7u; i & 7u; i++) mb_put (bw, 1, 1);       // cabac_alignment_one_bit
+  const int qp = slice_qp < 0 ? 0 : (slice_qp > 51 ? 51 : slice_qp);
+  for (int i = 0; i < 460; i++) {                                            // 9.3.1.1
+    const int v = kCabacInitMN[cls][i], m = v >> 8, n = (int8_t) (v & 0xff);
+    int pre = ((m * qp) >> 4) + n;
+    pre = pre < 1 ? 1 : (pre > 126 ? 126 : pre);
+    sc.cb_state[i] = pre <= 63 ? (uint8_t) ((63 - pre) << 1) : (uint8_t) (((pre - 64) << 1) | 1);
+  }
+  sc.cb_low = 0; sc.cb_range = 510; sc.cb_outstanding = 0; sc.cb_first = 1;
+}
+MD_FN void cb_put (MdBits& bw, MdScratch& sc, uint32_t bit) {                // PutBit
+  if (sc.cb_first) sc.cb_first = 0; else mb_put (bw, bit, 1);
+  while (sc.cb_outstanding) { const uint32_t n = sc.cb_outstanding > 16u ? 16u : sc.cb_outstanding; mb_put (bw, bit ? 0u : 0xffffu, (int)n); sc.cb_outstanding -= n; }
+}
+MD_FN void cb_renorm (MdBits& bw, MdScratch& sc) {                           // RenormE
+  while (sc.cb_range < 256u) {
+    if (sc.cb_low < 256u) cb_put (bw, sc, 0);
+    else if (sc.cb_low >= 512u) { sc.cb_low -= 512u; cb_put (bw, sc, 1); }
+    else { sc.cb_low -= 256u; sc.cb_outstanding++; }
+    sc.cb_range <<= 1; sc.cb_low <<= 1;
+  }
+}
+MD_FN_NOINLINE void cb_bin (MdBits& bw, MdScratch& sc, int ctx, uint32_t bin) {   // EncodeDecision
+  uint8_t& s = sc.cb_state[ctx];
+  const uint32_t idx = s >> 1;
+  uint32_t mps = s & 1u;
+  const uint32_t lps = kCabacRangeLps[(sc.cb_range >> 6) & 3u][idx];
+  sc.cb_range -= lps;
+  if (bin != mps) {
+    sc.cb_low += sc.cb_range; sc.cb_range = lps;
+    if (idx == 0) mps ^= 1u;
+    s = (uint8_t) ((kCabacNextLps[idx] << 1) | mps);
+  } else s = (uint8_t) (((idx < 62u ? idx + 1u : idx) << 1) | mps);
+  cb_renorm (bw, sc);
+}
+MD_FN_NOINLINE void cb_bypass (MdBits& bw, MdScratch& sc, uint32_t bin) {         // EncodeBypass
+  sc.cb_low <<= 1;
+  if (bin) sc.cb_low += sc.cb_range;
+  if (sc.cb_low >= 1024u) { cb_put (bw, sc, 1); sc.cb_low -= 1024u; }
+  else if (sc.cb_low < 512u) cb_put (bw, sc, 0);
+  else { sc.cb_low -= 512u; sc.cb_outstanding++; }
+}
+MD_FN void cb_terminate (MdBits& bw, MdScratch& sc, uint32_t bin) {               // EncodeTerminate + EncodeFlush: the last bit written is the
+  sc.cb_range -= 2u;                                                               // rbsp_stop_one_bit
+  if (bin) {
+    sc.cb_low += sc.cb_range; sc.cb_range = 2u;
+    cb_renorm (bw, sc);
+    cb_put (bw, sc, (sc.cb_low >> 9) & 1u);
+    mb_put (bw, ((sc.cb_low >> 7) & 3u) | 1u, 2);
+  } else cb_renorm (bw, sc);
+}
+
+// residual_block_cabac(): coefficient i of the block is base[scan[i * 1 + off]]; returns the number of non-zero coefficients
+MD_FN_NOINLINE int cb_block (MdBits& bw, MdScratch& sc, int cat, int cbf_inc, const int16_t* base, const uint8_t* scan, int off) {
+  const int n_max = cat == 5 ? 64 : (cat == 3 ? 4 : ((cat == 1 || cat == 4) ? 15 : 16));
+  const int sig0 = cat == 5 ? 402 : 105 + (cat == 0 ? 0 : (cat == 1 ? 15 : (cat == 2 ? 29 : (cat == 3 ? 44 : 47))));
+  const int last0 = cat == 5 ? 417 : sig0 + 61;
+  const int abs0 = cat == 5 ? 426 : 227 + (cat == 0 ? 0 : (cat == 1 ? 10 : (cat == 2 ? 20 : (cat == 3 ? 30 : 39))));
+  int n = 0, last = -1;
+  for (int i = 0; i < n_max; i++) if (base[scan[off + i]]) { n++; last = i; }
+  if (cbf_inc >= 0) cb_bin (bw, sc, 85 + 4 * cat + cbf_inc, n != 0);
+  if (!n) return 0;
+  for (int i = 0; i < n_max - 1; i++) {
+    const int inc_s = cat == 5 ? cb_sig8[i] : (cat == 3 ? (i < 2 ? i : 2) : i);
+    const uint32_t sig = base[scan[off + i]] != 0;
+    cb_bin (bw, sc, sig0 + inc_s, sig);
+    if (!sig) continue;
+    const int inc_l = cat == 5 ? cb_last8[i] : (cat == 3 ? (i < 2 ? i : 2) : i);
+    cb_bin (bw, sc, last0 + inc_l, i == last);
+    if (i == last) break;
+  }
+  int eq1 = 0, gt1 = 0;
+  const int cap = cat == 3 ? 3 : 4;
+  for (int i = last; i >= 0; i--) {
+    const int v = base[scan[off + i]];
+    if (!v) continue;
+    const int a = v < 0 ? -v : v;
+    const int c0 = abs0 + (gt1 ? 0 : (1 + eq1 < 4 ? 1 + eq1 : 4));
+    if (a == 1) { cb_bin (bw, sc, c0, 0); eq1++; }
+    else {
+      cb_bin (bw, sc, c0, 1);
+      const int c1 = abs0 + 5 + (gt1 < cap ? gt1 : cap);
+      for (int k = 2; k < a && k < 15; k++) cb_bin (bw, sc, c1, 1);
+      if (a < 15) cb_bin (bw, sc, c1, 0);
+      else {                                           // Exp-Golomb (k = 0) suffix of a - 15
+        int rest = a - 15, e = 0;
+        while (rest >= (1 << e)) { cb_bypass (bw, sc, 1); rest -= 1 << e; e++; }
+        cb_bypass (bw, sc, 0);
+        while (e--) cb_bypass (bw, sc, (uint32_t) (rest >> e) & 1u);
+      }
+      gt1++;
+    }
+    cb_bypass (bw, sc, v < 0);
+  }
+  return n;
+}
+MD_FN int cb_cbf_inc (const uint8_t* cur, const uint8_t* L, const uint8_t* T, bool intra, int bit_cur_a, int bit_left, int bit_cur_b, int bit_top) {
+  const int dflt = intra ? 1 : 0;
+  const int a = bit_cur_a >= 0 ? (int) ((cb_word (cur) >> bit_cur_a) & 1u) : (L ? (int) ((cb_word (L) >> bit_left) & 1u) : dflt);
+  const int b = bit_cur_b >= 0 ? (int) ((cb_word (cur) >> bit_cur_b) & 1u) : (T ? (int) ((cb_word (T) >> bit_top) & 1u) : dflt);
+  return a + 2 * b;
+}
+MD_FN_NOINLINE void cb_mvd (MdBits& bw, MdScratch& sc, uint8_t* cur, const uint8_t* L, const uint8_t* T, int bx, int by, int bw4, int bh4, int comp, int v) {
+  int sum = 0;
+  if (bx > 0) sum += cur[12 + 2 * (by * 4 + bx - 1) + comp]; else if (L) sum += L[12 + 2 * (by * 4 + 3) + comp];
+  if (by > 0) sum += cur[12 + 2 * ((by - 1) * 4 + bx) + comp]; else if (T) sum += T[12 + 2 * (12 + bx) + comp];
+  int ctx = comp ? 47 : 40;
+  const int a = v < 0 ? -v : v;
+  cb_bin (bw, sc, ctx + (sum < 3 ? 0 : (sum > 32 ? 2 : 1)), a != 0);
+  if (a) {
+    ctx += 3;
+    int k = 1;
+    for (; k < a && k < 9; k++) { cb_bin (bw, sc, ctx, 1); if (k < 4) ctx++; }
+    if (a < 9) cb_bin (bw, sc, ctx, 0);
+    else {                                             // UEG3 suffix of a - 9
+      int rest = a - 9, e = 3;
+      while (rest >= (1 << e)) { cb_bypass (bw, sc, 1); rest -= 1 << e; e++; }
+      cb_bypass (bw, sc, 0);
+      while (e--) cb_bypass (bw, sc, (uint32_t) (rest >> e) & 1u);
+    }
+    cb_bypass (bw, sc, v < 0);
+  }
+  const uint8_t s8 = (uint8_t) (a > 128 ? 128 : a);
+  for (int y = by; y < by + bh4; y++) for (int x = bx; x < bx + bw4; x++) cur[12 + 2 * (y * 4 + x) + comp] = s8;
+}
+MD_FN void cb_ref (MdBits& bw, MdScratch& sc, const uint8_t* L, const uint8_t* T, int q, const int8_t* vis, int ref) {
+  const bool a = (q & 1) ? vis[q - 1] > 0 : (L && (int8_t)L[8 + q + 1] > 0);
+  const bool b = (q & 2) ? vis[q - 2] > 0 : (T && (int8_t)T[8 + q + 2] > 0);
+  int ctx = (a ? 1 : 0) + (b ? 2 : 0);
+  for (int i = 0; i < ref; i++) { cb_bin (bw, sc, 54 + ctx, 1); ctx = (ctx >> 2) + 4; }
+  cb_bin (bw, sc, 54 + ctx, 0);
+}
+MD_FN void cb_intra_type (MdBits& bw, MdScratch& sc, int base, bool i_slice, int inc0, int t) {   // t: 0 I_NxN, 1..24 Intra16x16
+  cb_bin (bw, sc, i_slice ? base + inc0 : base, t != 0);
+  if (!t) return;
+  if (i_slice) base += 2;
+  cb_terminate (bw, sc, 0);
+  const int v = t - 1, pred = v & 3, chroma = (v >> 2) % 3, luma = v >= 12;
+  cb_bin (bw, sc, base + 1, (uint32_t)luma);
+  cb_bin (bw, sc, base + 2, chroma != 0);
+  if (chroma) cb_bin (bw, sc, base + 2 + (i_slice ? 1 : 0), chroma == 2);
+  cb_bin (bw, sc, base + 3 + (i_slice ? 1 : 0), (uint32_t) (pred >> 1));
+  cb_bin (bw, sc, base + 3 + (i_slice ? 2 : 0), (uint32_t) (pred & 1));
+}
+
+// macroblock_layer() with mb_skip_flag in front and end_of_slice_flag behind, for one record.  cur = this macroblock's neighbour
+// record (written), L / T = the left / top macroblock's (nullptr when not available).  Returns false for I_PCM.
+MD_FN_NOINLINE bool cb_mb (MdBits& bw, MdScratch& sc, CwSlice& s, uint8_t* cur, const uint8_t* L, const uint8_t* T) {
+  const lh264_model_mb& r = sc.r;
+  const int16_t* lev = sc.lev;
+  const bool p_slice = s.slice_type == 0;
+  const bool coded = (r.flags & LH264_MM_WRITE_BLOCK) != 0;
+  for (int i = 0; i < MD_NB_STRIDE; i++) cur[i] = 0;
+  if (p_slice) cb_bin (bw, sc, 11 + (L && L[6] != CB_SKIP ? 1 : 0) + (T && T[6] != CB_SKIP ? 1 : 0), !coded);
+  if (!coded) {
+    cur[6] = CB_SKIP;
+    s.last_dqp_nz = 0;
+    cb_terminate (bw, sc, (r.flags & LH264_MM_STOP_BIT) != 0);
+    return true;
+  }
+  const int tcode = r.type_code;
+  if (tcode >= 8) return false;
+  const int cbp = r.cbp, cbpL = cbp & 15, cbpC = cbp >> 4;
+  const bool intra = tcode <= 2, i16 = tcode == 1;
+  bool t8 = (r.flags & LH264_MM_T8) != 0;
+  for (int q = 0; q < 4; q++) cur[8 + q] = (uint8_t) (intra ? 0xff : 0);
+  auto t8_flag = [&] (bool v) { cb_bin (bw, sc, 399 + (L && L[7] ? 1 : 0) + (T && T[7] ? 1 : 0), v); };
+  if (intra) {
+    int t = 0;
+    if (i16) { const int raw = r.i16_mode > 3 ? 2 : r.i16_mode; t = 1 + raw + 4 * cbpC + (cbpL == 15 ? 12 : 0); }
+    if (p_slice) { cb_bin (bw, sc, 14, 1); cb_intra_type (bw, sc, 17, false, 0, t); }
+    else cb_intra_type (bw, sc, 3, true, (L && L[6] != CB_INXN ? 1 : 0) + (T && T[6] != CB_INXN ? 1 : 0), t);
+    cur[6] = (uint8_t) (i16 ? CB_I16 : CB_INXN);
+    if (!i16) {
+      if (s.transform_8x8_mode) t8_flag (tcode == 2);
+      t8 = tcode == 2;
+      const int n = tcode == 2 ? 4 : 16;
+      for (int i = 0; i < n; i++) {
+        const int mode = r.pred_mode[i] & 15, pred = r.pred_mode[i] >> 4;
+        cb_bin (bw, sc, 68, mode == pred);
+        if (mode != pred) { const int rem = mode < pred ? mode : mode - 1; cb_bin (bw, sc, 69, rem & 1); cb_bin (bw, sc, 69, (rem >> 1) & 1); cb_bin (bw, sc, 69, (rem >> 2) & 1); }
+      }
+    }
+    const int cm = r.chroma_mode > 3 ? 0 : r.chroma_mode;
+    auto cnd = [] (const uint8_t* n) { return n && (n[6] == CB_INXN || n[6] == CB_I16) && n[5] != 0; };
+    cb_bin (bw, sc, 64 + (cnd (L) ? 1 : 0) + (cnd (T) ? 1 : 0), cm != 0);
+    if (cm) { cb_bin (bw, sc, 67, cm != 1); if (cm != 1) cb_bin (bw, sc, 67, cm == 3); }
+    cur[5] = (uint8_t)cm;
+  } else {
+    cur[6] = CB_INTER;
+    cb_bin (bw, sc, 14, 0);
+    if (tcode == 3) { cb_bin (bw, sc, 15, 0); cb_bin (bw, sc, 16, 0); }
+    else if (tcode == 6 || tcode == 7) { cb_bin (bw, sc, 15, 0); cb_bin (bw, sc, 16, 1); }
+    else { cb_bin (bw, sc, 15, 1); cb_bin (bw, sc, 17, tcode == 4); }       // 16x8 -> 1, 8x16 -> 0
+    const int nref = s.num_ref_idx_l0;
+    int8_t vis[4] = { -1, -1, -1, -1 };
+    if (tcode == 6 || tcode == 7) {
+      for (int q = 0; q < 4; q++) {
+        const int sb = r.sub_mb_type[q];
+        if (sb == 1) cb_bin (bw, sc, 21, 1);
+        else { cb_bin (bw, sc, 21, 0); if (sb == 2) cb_bin (bw, sc, 22, 0); else { cb_bin (bw, sc, 22, 1); cb_bin (bw, sc, 23, sb == 4); } }
+      }
+      for (int q = 0; q < 4; q++) { if (nref > 1) cb_ref (bw, sc, L, T, q, vis, r.ref_idx[q]); vis[q] = r.ref_idx[q]; }
+      for (int q = 0; q < 4; q++) cur[8 + q] = (uint8_t)vis[q];
+      for (int q = 0; q < 4; q++) {
+        const int sb = r.sub_mb_type[q], qx = (q & 1) * 2, qy = (q >> 1) * 2;
+        const int cnt = sb == 1 ? 1 : (sb == 8 ? 4 : 2);
+        for (int j = 0; j < cnt; j++) {
+          int bx = qx, by = qy, w4 = 2, h4 = 2;
+          if (sb == 2) { by += j; h4 = 1; } else if (sb == 4) { bx += j; w4 = 1; } else if (sb == 8) { bx += j & 1; by += j >> 1; w4 = h4 = 1; }
+          cb_mvd (bw, sc, cur, L, T, bx, by, w4, h4, 0, r.mvd[by * 4 + bx][0]);
+          cb_mvd (bw, sc, cur, L, T, bx, by, w4, h4, 1, r.mvd[by * 4 + bx][1]);
+        }
+      }
+    } else {
+      const int nparts = tcode == 3 ? 1 : 2;
+      for (int i = 0; i < nparts; i++) {
+        const int q0 = tcode == 4 ? 2 * i : i;
+        if (nref > 1) cb_ref (bw, sc, L, T, q0, vis, r.ref_idx[i]);
+        if (tcode == 3) vis[0] = vis[1] = vis[2] = vis[3] = r.ref_idx[0];
+        else if (tcode == 4) vis[2 * i] = vis[2 * i + 1] = r.ref_idx[i];
+        else vis[i] = vis[i + 2] = r.ref_idx[i];
+      }
+      for (int q = 0; q < 4; q++) cur[8 + q] = (uint8_t)vis[q];
+      for (int i = 0; i < nparts; i++) {
+        int bx = 0, by = 0, w4 = 4, h4 = 4;
+        if (tcode == 4) { by = 2 * i; h4 = 2; } else if (tcode == 5) { bx = 2 * i; w4 = 2; }
+        cb_mvd (bw, sc, cur, L, T, bx, by, w4, h4, 0, r.mvd[by * 4 + bx][0]);
+        cb_mvd (bw, sc, cur, L, T, bx, by, w4, h4, 1, r.mvd[by * 4 + bx][1]);
+      }
+    }
+  }
+  if (!i16) {                                          // coded_block_pattern (9.3.2.6, 9.3.3.1.1.4)
+    const int ca = L ? L[4] : 0x0f, cb = T ? T[4] : 0x0f;
+    cb_bin (bw, sc, 73 + !(ca & 2) + 2 * !(cb & 4), cbpL & 1);
+    cb_bin (bw, sc, 73 + !(cbpL & 1) + 2 * !(cb & 8), (cbpL >> 1) & 1);
+    cb_bin (bw, sc, 73 + !(ca & 8) + 2 * !(cbpL & 1), (cbpL >> 2) & 1);
+    cb_bin (bw, sc, 73 + !(cbpL & 4) + 2 * !(cbpL & 2), (cbpL >> 3) & 1);
+    const int xa = ca >> 4, xb = cb >> 4;
+    cb_bin (bw, sc, 77 + (xa > 0 ? 1 : 0) + (xb > 0 ? 2 : 0), cbpC != 0);
+    if (cbpC) cb_bin (bw, sc, 77 + 4 + (xa == 2 ? 1 : 0) + (xb == 2 ? 2 : 0), cbpC == 2);
+    if (!intra && (r.flags & LH264_MM_T8_CODED)) t8_flag (t8);
+  }
+  cur[4] = (uint8_t)cbp; cur[7] = t8 ? 1 : 0;
+  if (cbp == 0 && !i16) { s.last_dqp_nz = 0; cb_terminate (bw, sc, (r.flags & LH264_MM_STOP_BIT) != 0); return true; }
+  {
+    int d = (int)r.luma_qp - s.qp;
+    if (d > 25) d -= 52; else if (d < -26) d += 52;
+    const int v = d > 0 ? 2 * d - 1 : -2 * d;          // mapped value, unary
+    int ctx = s.last_dqp_nz ? 1 : 0;
+    for (int i = 0; i < v; i++) { cb_bin (bw, sc, 60 + ctx, 1); ctx = 2 + (ctx >> 1); }
+    cb_bin (bw, sc, 60 + ctx, 0);
+    s.last_dqp_nz = d != 0;
+    s.qp = r.luma_qp;
+  }
+  uint32_t cbf = 0;
+  if (i16) { if (cb_block (bw, sc, 0, cb_cbf_inc (cur, L, T, intra, -1, 24, -1, 24), lev, md_i16dc_scan, 0)) { cbf |= 1u << 24; cb_set_word (cur, cbf); } }
+  for (int q = 0; q < 4; q++) {
+    if (!(cbpL & (1 << q))) continue;
+    if (t8) {
+      cb_block (bw, sc, 5, -1, lev + 64 * q, md_zigzag8, 0);
+      for (int k = 0; k < 4; k++) cbf |= 1u << md_scan4[4 * q + k];
+      cb_set_word (cur, cbf);
+      continue;
+    }
+    for (int k = 0; k < 4; k++) {
+      const int z = 4 * q + k, rr = md_scan4[z], bx = rr & 3, by = rr >> 2;
+      const int inc = cb_cbf_inc (cur, L, T, intra, bx > 0 ? rr - 1 : -1, rr + 3, by > 0 ? rr - 4 : -1, rr + 12);
+      const int n = i16 ? cb_block (bw, sc, 1, inc, lev + 16 * z, md_zigzag4, 1) : cb_block (bw, sc, 2, inc, lev + 16 * z, md_zigzag4, 0);
+      if (n) { cbf |= 1u << rr; cb_set_word (cur, cbf); }
+    }
+  }
+  if (cbpC)
+    for (int p = 0; p < 2; p++)
+      if (cb_block (bw, sc, 3, cb_cbf_inc (cur, L, T, intra, -1, 25 + p, -1, 25 + p), lev + 16 * (16 + 4 * p), md_cdc_scan, 0)) { cbf |= 1u << (25 + p); cb_set_word (cur, cbf); }
+  if (cbpC & 2)
+    for (int p = 0; p < 2; p++)
+      for (int b = 0; b < 4; b++) {
+        const int bit = 16 + 4 * p + b;
+        const int inc = cb_cbf_inc (cur, L, T, intra, (b & 1) ? bit - 1 : -1, bit + 1, (b & 2) ? bit - 2 : -1, bit + 2);
+        if (cb_block (bw, sc, 4, inc, lev + 16 * bit, md_zigzag4, 1)) { cbf |= 1u << bit; cb_set_word (cur, cbf); }
+      }
+  cb_terminate (bw, sc, (r.flags & LH264_MM_STOP_BIT) != 0);
+  return true;
+}
+
 // ---- one slice ------------------------------------------------------------------------------------------------------
 // FreqImage::updateFrame (decoded_macroblock.h:120-165), serial form; the CUDA build replaces it by a warp-wide one.
 MD_FN void md_update_frame_serial (CtxRec* f, int len) {
@@ -442,9 +751,10 @@ MD_FN int md_slice (MdStream& st, MdCtx& c, const MdSliceIn& sl, bool prior_vali
   CtxRec* last = st.frame[1 - st.cur];
   const uint32_t stype = sl.slice_type == 0 ? 0u : 1u;
   const bool p_slice = sl.slice_type == 0;
-  const bool t8mode = sl.flags & 1, cip = sl.flags & 2;
+  const bool t8mode = sl.flags & 1, cip = sl.flags & 2, cabac = sl.flags & 4;
   const int slice_no = ++st.slice_counter;
-  CwSlice cs = { sl.slice_type, sl.num_ref_idx_l0, sl.slice_qp, t8mode ? 1 : 0 };
+  CwSlice cs = { sl.slice_type, sl.num_ref_idx_l0, sl.slice_qp, t8mode ? 1 : 0, cabac ? 1 : 0, 0 };
+  if (cabac) cb_slice_begin (bw, sc, p_slice ? 1 + ((sl.flags >> 3) & 3) : 0, sl.slice_qp, sl.header_bits);
   int mb_addr = (int)sl.first_mb, mb_in_slice = 0, cached_qp = 0, last_dqp = 0, pending_skips = 0;
   bool run_known = false, stop = false;
   auto avail = [&] (int mb) -> bool { return mb >= 0 && st.mb_slice[mb] == slice_no; };
@@ -469,7 +779,7 @@ MD_FN int md_slice (MdStream& st, MdCtx& c, const MdSliceIn& sl, bool prior_vali
       }
     }
     run_known = false;
-    uint8_t* tc = &st.tcoef[(size_t)mb_addr * 24];
+    uint8_t* tc = &st.tcoef[(size_t)mb_addr * MD_NB_STRIDE];
     const bool hasLs = mbx > 0 && avail (mb_addr - 1), hasTs = mby > 0 && avail (mb_addr - W);   // before this MB joins the slice
     if (skipped) {
       pending_skips--;
@@ -477,10 +787,11 @@ MD_FN int md_slice (MdStream& st, MdCtx& c, const MdSliceIn& sl, bool prior_vali
         r.flags |= LH264_MM_STOP_IN_SKIP;
         stop = md_bit (c, CT_SKIP_END, stop_idx) != 0;
         if (stop) r.flags |= LH264_MM_STOP_BIT;
-        run_known = true;
+        run_known = !cabac;                            // CABAC: a one-macroblock run (0 or 1) is coded in front of EVERY macroblock (:2207-2209)
       }
       cur[mb_addr] = last[mb_addr];                    // :3105
-      cw_mb (bw, sc, cs, tc, nullptr, nullptr);
+      if (cabac) cb_mb (bw, sc, cs, tc, hasLs ? &st.tcoef[(size_t) (mb_addr - 1) * MD_NB_STRIDE] : nullptr, hasTs ? &st.tcoef[(size_t) (mb_addr - W) * MD_NB_STRIDE] : nullptr);
+      else cw_mb (bw, sc, cs, tc, nullptr, nullptr);
       uint8_t* pm = &st.ipm[(size_t)mb_addr * 16];
       for (int i = 0; i < 16; i++) pm[i] = 2;
       st.mb_intra[mb_addr] = 0; st.mb_slice[mb_addr] = slice_no;
@@ -658,12 +969,27 @@ MD_FN int md_slice (MdStream& st, MdCtx& c, const MdSliceIn& sl, bool prior_vali
     }
     // ---- CAVLC ----
     if (tcd >= 8) { st.error = MD_ERR_PCM; break; }
-    if (!cw_mb (bw, sc, cs, tc, hasLs ? &st.tcoef[(size_t) (mb_addr - 1) * 24] : nullptr, hasTs ? &st.tcoef[(size_t) (mb_addr - W) * 24] : nullptr)) { st.error = MD_ERR_SYNTAX; break; }
+    {
+      const uint8_t* nbL = hasLs ? &st.tcoef[(size_t) (mb_addr - 1) * MD_NB_STRIDE] : nullptr;
+      const uint8_t* nbT = hasTs ? &st.tcoef[(size_t) (mb_addr - W) * MD_NB_STRIDE] : nullptr;
+      if (!(cabac ? cb_mb (bw, sc, cs, tc, nbL, nbT) : cw_mb (bw, sc, cs, tc, nbL, nbT))) { st.error = MD_ERR_SYNTAX; break; }
+    }
     if (bw.overflow) { st.error = MD_ERR_OUT_FULL; break; }
     st.mb_intra[mb_addr] = tcd <= 2; st.mb_slice[mb_addr] = slice_no;
     mb_addr++; mb_in_slice++;
   }
   // slice trailing alignment bits (decode_slice.cpp:3133-3147): coded through TEST_PROB into the PADBYTE stream
+  if (cabac) {
+    // the reference stores the low seven bits of the slice's last byte (decoder.cpp parse_slice_data_cabac); the arithmetic
+    // encoder's flush ended with the stop bit, which the caller's trailer writes again: hand it back
+    const uint32_t pad7 = st.error ? 0u : md_raw (c, CT_PAD, 7);
+    if (!stop && !st.error) st.error = MD_ERR_SYNTAX;  // a CABAC slice ends with end_of_slice_flag = 1
+    bw.trim = stop ? 1 : 0;
+    const int n_pad = 7 - (int) ((sl.header_bits + mb_bits (bw) - (uint64_t)bw.trim) & 7u);
+    *n_pad_out = (uint8_t)n_pad;
+    *pad_bits_out = (uint8_t) (pad7 & ((1u << n_pad) - 1u));
+    return mb_addr - (int)sl.first_mb;
+  }
   const int n_pad = 7 - (int) ((sl.header_bits + mb_bits (bw)) & 7u);
   *n_pad_out = (uint8_t)n_pad;
   *pad_bits_out = (uint8_t) (n_pad && !st.error ? md_raw (c, CT_PAD, n_pad) : 0u);

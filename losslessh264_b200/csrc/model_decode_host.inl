@@ -56,7 +56,7 @@ extern "C" int lh264_model_decode (lh264_ctx* c, lh264_decode_job* jobs, int n_j
     lay[j].ipm = off; off = up (off + n * 16);
     lay[j].mb_slice = off; off = up (off + n * 4);
     lay[j].intra = off; off = up (off + n);
-    lay[j].tcoef = off; off = up (off + n * 24);
+    lay[j].tcoef = off; off = up (off + n * MD_NB_STRIDE);
     lay[j].sout = off; off = up (off + sizeof (lh264_decode_slice_out) * (size_t)job.n_slices);
     lay[j].out = off; off = up (off + job.out_capacity);
   }

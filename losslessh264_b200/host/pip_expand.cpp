@@ -65,12 +65,17 @@ bool expand_plan (const uint8_t* def_in, size_t n, ExpandPlan& plan) {
       if (parse_slice_header (br, ref_idc, type, sps.data(), pps.data(), sh) < 0) { plan.error = "slice header does not parse"; return false; }
       const Pps& pp = pps[sh.pps_id];
       const Sps& sp = sps[pp.sps_id];
-      if (pp.cabac) { plan.error = "CABAC slice: the decompress direction needs a CABAC slice-data writer, not built (SURVEY 8f N4)"; return false; }
-      // the header is followed by exactly one stop bit and zero padding (pip_container.cpp: unit_end)
+      // the header is followed by exactly one stop bit (CAVLC; none for CABAC) and zero padding (pip_container.cpp: unit_end)
       const uint8_t* rb = nal.data() + 1;
       const size_t hb = sh.header_bits, rl = plen - 1;
-      bool ok = (hb >> 3) < rl && ((rb[hb >> 3] >> (7 - (hb & 7))) & 1u) && (hb + 8) / 8 == rl;
-      if (ok) ok = (rb[hb >> 3] & ((1u << (7 - (hb & 7))) - 1u)) == 0;
+      bool ok;
+      if (pp.cabac) {
+        ok = (hb + 7) / 8 == rl || ((hb & 7) == 0 && hb / 8 == rl);
+        if (ok && (hb & 7)) ok = (rb[hb >> 3] & ((1u << (8 - (hb & 7))) - 1u)) == 0;
+      } else {
+        ok = (hb >> 3) < rl && ((rb[hb >> 3] >> (7 - (hb & 7))) & 1u) && (hb + 8) / 8 == rl;
+        if (ok) ok = (rb[hb >> 3] & ((1u << (7 - (hb & 7))) - 1u)) == 0;
+      }
       if (!ok) { plan.error = "slice unit of the default stream is not <header bits><stop bit> (trailing zero bytes in the original NAL?)"; return false; }
       if (sh.slice_type != SLICE_P && sh.slice_type != SLICE_I) { plan.error = "B/SP/SI slice"; return false; }
       lh264_decode_slice ds;
@@ -80,7 +85,7 @@ bool expand_plan (const uint8_t* def_in, size_t n, ExpandPlan& plan) {
       ds.slice_type = (uint8_t) (sh.slice_type == SLICE_I ? 2 : 0);
       ds.num_ref_idx_l0 = (uint8_t) (sh.slice_type == SLICE_P ? sh.num_ref_idx_l0 : pp.num_ref_idx_l0_default);
       ds.slice_qp = (uint8_t)sh.slice_qp;
-      ds.flags = (uint8_t) ((pp.transform_8x8_mode ? 1 : 0) | (pp.constrained_intra_pred ? 2 : 0));
+      ds.flags = (uint8_t) ((pp.transform_8x8_mode ? 1 : 0) | (pp.constrained_intra_pred ? 2 : 0) | (pp.cabac ? 4 | ((sh.cabac_init_idc & 3) << 3) : 0));
       ds.header_bits = (uint32_t)hb;
       literal (pos, off);
       ExpandPiece p; p.def_off = pos + off; p.def_len = len - off; p.slice = (int)plan.slices.size();

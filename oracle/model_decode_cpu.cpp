@@ -20,6 +20,7 @@
 #include "../include/lh264_b200.h"
 #include "../losslessh264_b200/csrc/model_layout.h"
 #include "../losslessh264_b200/host/cavlc_tables.h"
+#include "../losslessh264_b200/host/cabac_tables.h"
 #define MD_FN static inline
 #define MD_FN_NOINLINE static
 #define MD_TABLE static const
@@ -42,7 +43,7 @@ extern "C" int mdc_model_decode (lh264_decode_job* jobs, int n_jobs) {
     std::vector<uint32_t> priors (job.with_8x8 ? P_END : P_END_NO8, 0);
     std::vector<CtxRec> f0 (n), f1 (n);
     memset (f0.data(), 0, n * sizeof (CtxRec)); memset (f1.data(), 0, n * sizeof (CtxRec));
-    std::vector<uint8_t> ipm (n * 16, 2), intra (n, 0), tcoef (n * 24, 0);
+    std::vector<uint8_t> ipm (n * 16, 2), intra (n, 0), tcoef (n * 48, 0);
     std::vector<int32_t> mb_slice (n, -1);
     MdStream st;
     memset (&st, 0, sizeof (st));
@@ -72,7 +73,7 @@ extern "C" int mdc_model_decode (lh264_decode_job* jobs, int n_jobs) {
       memset (&so, 0, sizeof (so));
       so.n_mbs = (uint32_t)md_slice (st, c, sl, prior_valid, bw, sc, &so.pad_bits, &so.n_pad_bits);
       mb_flush (bw);
-      so.byte_offset = off; so.n_bits = (uint32_t)mb_bits (bw);
+      so.byte_offset = off; so.n_bits = (uint32_t) (mb_bits (bw) - (uint64_t)bw.trim);
       off += (mb_bits (bw) + 7) / 8;
     }
     job.error = st.error;

@@ -13,9 +13,9 @@ LIB_DIR = os.path.join(ROOT, "losslessh264_b200", "_lib")
 NOT_YET = {
     "Error_I_P.264": "damaged stream with resolution changes: needs the reference's error concealment (SURVEY §8f N3)",
 }
-# CABAC streams decode and compress (host CABAC parse; the model hand-off follows the reference's one-macroblock skip runs and
-# end_of_slice stop bits); their DECOMPRESS direction needs a CABAC slice-data writer (`esCabac`), so the
-# `.pip` -> `.264` tests run on the CAVLC streams only.
+# CABAC streams decode, compress and decompress like the CAVLC ones (host CABAC parse; the model hand-off follows the reference's
+# one-macroblock skip runs and end_of_slice stop bits; the decompress core has a CABAC slice-data writer).  The set is only
+# needed where a test is about CAVLC itself (the host CAVLC writer check).
 CABAC = {"QCIF_2P_I_allIPCM.264", "test_qcif_cabac.264", "tibbycabac.264", "syn_cif_cabac_4slices_ltr_6f.264", "syn_qcif_cabac_qp38_8f.264"}
 
 

@@ -20,7 +20,7 @@ ALL = sorted(CPU_SET + ["LS_SVA_D.264", "BA1_FT_C.264", "CI1_FT_B.264"])
 # the two-process CLI round trip costs seconds of context set-up per file: a representative subset; every stream of the corpus goes
 # through the same kernel in test_every_stream_in_one_call below
 CLI_SET = ["tibby.264", "tibby8x8cavlc.264", "BA1_FT_C.264", "LS_SVA_D.264", "black.264", "BAMQ2_JVC_C.264", "MR2_TANDBERG_E.264", "SVA_FM1_E.264",
-           "syn_qcif_4slices_8f.264", "syn4k_8slices_ltr_4f.264", "CVFC1_Sony_C.jsv", "MR1_BT_A.h264"]
+           "syn_qcif_4slices_8f.264", "syn4k_8slices_ltr_4f.264", "CVFC1_Sony_C.jsv", "MR1_BT_A.h264", "tibbycabac.264", "syn_cif_cabac_4slices_ltr_6f.264"]
 
 
 @pytest.mark.parametrize("name", CLI_SET)
@@ -80,10 +80,10 @@ def test_pcm_stream_is_refused_like_the_reference(tmp_path):
     assert r.returncode != 0 and "21" in r.stderr          # I_PCM samples are not in the model (reference: same limitation)
 
 
-def test_corrupt_side_stream_does_not_hang_or_pass(ctx, tmp_path):
+@pytest.mark.parametrize("name", ["SVA_BA1_B.264", "test_qcif_cabac.264"])
+def test_corrupt_side_stream_does_not_hang_or_pass(name, ctx, tmp_path):
     from losslessh264_b200 import api, pip as pipmod
 
-    name = "SVA_BA1_B.264"
     d, tags = pipmod.read_pip(write_pip_cpu(name, str(tmp_path)))
     big = max(tags, key=lambda t: len(tags[t]))
     rng = np.random.default_rng(5)

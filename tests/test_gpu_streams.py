@@ -52,7 +52,7 @@ def test_cli_compress_writes_the_reference_pip_file_set(name, tmp_path):
 # UNMODIFIED reference decompressor (oracle/_ref/h264dec x.pip x.264, test infrastructure) and must give back the original
 # file byte for byte.  Streams on which the reference itself does not round-trip are not in the list.
 REF_DEC = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "h264dec")
-ROUNDTRIP_SET = ["tibby.264", "black.264", "BAMQ2_JVC_C.264", "BA1_FT_C.264", "tibby8x8cavlc.264", "BA_MW_D.264", "MR2_TANDBERG_E.264", "syn720p_8f.264"]
+ROUNDTRIP_SET = ["tibby.264", "black.264", "BAMQ2_JVC_C.264", "BA1_FT_C.264", "tibby8x8cavlc.264", "BA_MW_D.264", "MR2_TANDBERG_E.264", "syn720p_8f.264", "tibbycabac.264"]
 
 
 @pytest.mark.skipif(not os.path.exists(REF_DEC), reason="compiled reference (oracle/_ref) not present")

@@ -10,10 +10,10 @@ import pytest
 
 from oracle import oracle
 from streams import LIB_DIR, STREAM_DIR
-from streams import CABAC
 from test_model_oracle import CPU_SET as MODEL_SET, TOOL
 
-CPU_SET = [s for s in MODEL_SET if s not in CABAC]      # the decompress direction re-serialises CAVLC only
+# CAVLC and CABAC streams alike (the core re-serialises both); I_PCM macroblocks are not in the model, as in the reference
+CPU_SET = [s for s in MODEL_SET if s != "QCIF_2P_I_allIPCM.264"]
 from losslessh264_b200.records import read_lhmd
 
 
@@ -48,9 +48,9 @@ def test_expanded_pip_is_the_original_file(name, tmp_path, expand_cpu):
     assert open(out, "rb").read() == open(os.path.join(STREAM_DIR, name), "rb").read(), f"{name}: expanded file differs from the original"
 
 
-def test_truncated_side_stream_is_not_silently_accepted(tmp_path, expand_cpu):
+@pytest.mark.parametrize("name", ["SVA_BA1_B.264", "test_qcif_cabac.264"])
+def test_truncated_side_stream_is_not_silently_accepted(name, tmp_path, expand_cpu):
     d = str(tmp_path)
-    name = "SVA_BA1_B.264"
     pip = write_pip_cpu(name, d)
     big = max((f for f in os.listdir(d) if f.startswith("x.pip.")), key=lambda f: os.path.getsize(os.path.join(d, f)))
     b = open(os.path.join(d, big), "rb").read()
@@ -61,9 +61,9 @@ def test_truncated_side_stream_is_not_silently_accepted(tmp_path, expand_cpu):
     assert not same
 
 
-def test_cabac_is_refused(tmp_path, expand_cpu):
+def test_cabac_pcm_stream_is_refused_like_the_reference(tmp_path, expand_cpu):
+    """I_PCM in a CABAC stream: the reference aborts in computeNeighborPriorsCabac (decode_slice.cpp:1754); here error 21."""
     d = str(tmp_path)
-    pip = os.path.join(d, "x.pip")
-    subprocess.run([TOOL, os.path.join(STREAM_DIR, "test_qcif_cabac.264"), os.path.join(d, "d.lhfb"), "1", os.path.join(d, "d.lhmd"), pip], capture_output=True)
+    pip = write_pip_cpu("QCIF_2P_I_allIPCM.264", d)
     r = subprocess.run([expand_cpu, pip, os.path.join(d, "o.264")], capture_output=True, text=True)
     assert r.returncode != 0
