@@ -82,6 +82,7 @@ struct Decoder::Impl {
   // DecodedMacroblock (initRTDFromDecoderState, decode_slice.cpp:81-108): pCbp, pChromaPredMode,
   // pIntraPredMode[][7], pSubMbType are only written by the MB types that carry them
   std::vector<uint8_t> st_cbp, st_chroma, st_i16, st_sub;
+  int st_alloc_w = 0, st_alloc_h = 0;
 
   // CABAC (9.3): the engine, and what context selection reads from neighbouring macroblocks of the picture
   struct CabMb {
@@ -284,7 +285,13 @@ struct Decoder::Impl {
     ipm.assign ((size_t)n_mbs * 16, 2);
     mb_slice.assign (n_mbs, -1);
     side.assign (n_mbs, ModelMbSide());
-    st_cbp.assign (n_mbs, 0); st_chroma.assign (n_mbs, 0); st_i16.assign (n_mbs, 0); st_sub.assign ((size_t)n_mbs * 4, 0);
+    // the reference reallocates (zeroed) its per-macroblock arrays only when the picture GROWS beyond what it has
+    // (InitialDqLayersContext, decoder_core.cpp:1233-1235, :1344-1345); a smaller picture keeps the old bytes, indexed by the
+    // new macroblock addresses
+    if (mb_w * 16 > st_alloc_w || mb_h * 16 > st_alloc_h) {
+      st_alloc_w = mb_w * 16; st_alloc_h = mb_h * 16;
+      st_cbp.assign (n_mbs, 0); st_chroma.assign (n_mbs, 0); st_i16.assign (n_mbs, 0); st_sub.assign ((size_t)n_mbs * 4, 0);
+    }
     coefs.reserve ((size_t)n_mbs * 64);
     cabmb.assign (n_mbs, CabMb()); mvd_abs.assign ((size_t)n_mbs * 32, 0);
     return sink->configure (mb_w, mb_h, n_slots);
@@ -332,8 +339,12 @@ struct Decoder::Impl {
     info.frame_num = sh0.frame_num; info.poc_lsb = sh0.poc_lsb; info.idr_pic_id = sh0.idr_pic_id; info.nal_ref_idc = sh0.nal_ref_idc;
     info.slot = cur_slot; info.serial = serial++; info.complete = decoded >= n_mbs; info.timestamp = ts;
     int rc = 0;
-    if (sh0.idr) frozen = false;
+    // ... and freezes it again at a picture with missing macroblocks (no concealment here: the reference's freeze modes do not
+    // hand concealed pictures out either) until the next complete IDR picture
+    if (!info.complete) frozen = true;
+    else if (sh0.idr) frozen = false;
     info.output = !frozen;
+    if (getenv ("LH264_DEBUG")) fprintf (stderr, "picture: %dx%d idr %d frame_num %d decoded %d of %d slices %zu\n", mb_w, mb_h, (int)sh0.idr, sh0.frame_num, decoded, n_mbs, slices.size());
     if (!slices.empty()) rc = sink->submit (d, info);
     if (want_model && !mslices.empty()) {
       lh264_model_picture mp;

@@ -8,11 +8,10 @@ STREAM_DIR = os.path.join(HERE, "golden", "streams")
 SHA1 = json.load(open(os.path.join(HERE, "golden", "stream_sha1.json")))
 LIB_DIR = os.path.join(ROOT, "losslessh264_b200", "_lib")
 
-# Streams of the parity corpus that the host decoder does not cover yet, with the reason.  They are
-# "next" rows of SURVEY.md §8f (N3: error concealment), not silently skipped.
-NOT_YET = {
-    "Error_I_P.264": "damaged stream with resolution changes: needs the reference's error concealment (SURVEY §8f N3)",
-}
+# Streams of the parity corpus that the host decoder does not cover: none any more (the damaged ones - BA_MW_D_IDR_LOST,
+# Error_I_P - follow the reference's freeze-output behaviour, host/decoder.cpp `frozen`).  Kept as the place to list, with
+# the reason, anything a later change has to exclude: never skip silently.
+NOT_YET = {}
 # CABAC streams decode, compress and decompress like the CAVLC ones (host CABAC parse; the model hand-off follows the reference's
 # one-macroblock skip runs and end_of_slice stop bits; the decompress core has a CABAC slice-data writer).  The set is only
 # needed where a test is about CAVLC itself (the host CAVLC writer check).

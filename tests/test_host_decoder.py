@@ -12,7 +12,7 @@ import pytest
 
 from losslessh264_b200.records import n_slots_needed, read_lhfb
 from oracle import oracle
-from streams import LIB_DIR, NOT_YET, SHA1, STREAM_DIR, decodable_streams
+from streams import LIB_DIR, SHA1, STREAM_DIR, decodable_streams
 
 TOOL = os.path.join(LIB_DIR, "lh264_parse_dump")
 
@@ -58,10 +58,8 @@ def test_cavlc_tables_are_prefix_codes(tmp_path):
     assert r.returncode == 0
 
 
-def test_damaged_stream_is_reported(tmp_path):
-    """Error_I_P.264 (damaged, resolution changes) needs the reference's error concealment: the host decoder must not
-    hand it over as if it were a clean sequence — the tool writes one .lhfb geometry per stream and the oracle refuses the rest."""
-    name = "Error_I_P.264"
-    assert name in NOT_YET
-    r = subprocess.run([TOOL, os.path.join(STREAM_DIR, name), os.path.join(str(tmp_path), "x.lhfb")], capture_output=True, text=True)
-    assert r.returncode in (0, 4)                      # parses (the slices themselves are well formed) or reports errors; never crashes
+def test_damaged_stream_freezes_output_like_the_reference(tmp_path):
+    """Error_I_P.264: three sequences of two resolutions, five of its six pictures have lost slices.  The reference (freeze error
+    concealment modes) hands out exactly one picture, the complete 640x480 IDR; so does the host decoder."""
+    sha, n = decode_with_oracle(os.path.join(STREAM_DIR, "Error_I_P.264"), str(tmp_path))
+    assert n == 1 and sha == SHA1["Error_I_P.264"]["sha1"]
