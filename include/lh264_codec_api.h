@@ -132,6 +132,13 @@ const struct lh264_decode_slice* lh264_pip_plan_slices (const lh264_pip_plan_t* 
 long long lh264_pip_assemble (const lh264_pip_plan_t* plan, const unsigned char* default_stream, const unsigned char* slice_bits,
                               const struct lh264_decode_slice_out* outs, unsigned char* dst, size_t cap);
 
+/* Single-file container (an addition, the reference only knows the file set): `x.pipx` holds the default stream
+ * and every tag stream of a `.pip` file set behind a table of (tag, length) entries (format: host/pip_container.h).  Lossless in
+ * both directions; 0 on success, -1 cannot read the input, -2 cannot write the output.  h264dec_lh264 accepts `.pipx` wherever
+ * the reference CLI takes `.pip`.                                                                                              */
+int lh264_pip_pack (const char* pip_path, const char* archive_path);
+int lh264_pip_unpack (const char* archive_path, const char* pip_path);
+
 #ifdef __cplusplus
 }
 #endif

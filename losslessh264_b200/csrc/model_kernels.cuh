@@ -738,7 +738,7 @@ struct CodeShared {
 };
 
 __global__ void __launch_bounds__ (64) k_model_code (const MPicDev* pics, int n_pics, const uint32_t* dec, const unsigned long long* dec_base,
-                                                     const uint32_t* pic_total, ArenaDev ar, const BatchCtl* ctl) {
+                                                     const uint32_t* pic_total, ArenaDev ar, const BatchCtl* ctl, unsigned idle_ns) {
   __shared__ CodeShared sh;
   const int p = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (p >= n_pics || ctl->skip) return;
@@ -779,7 +779,7 @@ __global__ void __launch_bounds__ (64) k_model_code (const MPicDev* pics, int n_
       const unsigned tpeers = __match_any_sync (0xffffffffu, tag);
       if (valid) {
         const uint32_t pos = sh.prod[tag] + (uint32_t)__popc (tpeers & lt);
-        while (pos - sh.cons[tag] >= (uint32_t)CODE_RING) { }
+        while (pos - sh.cons[tag] >= (uint32_t)CODE_RING) { if (idle_ns) __nanosleep (idle_ns); }   // ring full: leave the issue slots to the other warps of the SM
         sh.ring[tag][pos & (CODE_RING - 1)] = (uint16_t) ((prob << 1) | bit);
       }
       __threadfence_block();
@@ -812,6 +812,8 @@ __global__ void __launch_bounds__ (64) k_model_code (const MPicDev* pics, int n_
     // latency is off the dependency chain (vnext is only trusted when that entry had been published at fetch time)
     uint32_t vnext = 0;
     bool vnext_ok = false;
+    uint32_t lastb = 0;                                 // last byte this lane wrote in this launch (carry fast path)
+    bool have_last = false;
     auto step = [&] () -> bool {
       const bool has = consumed != avail;
       uint32_t v = vnext;
@@ -828,18 +830,25 @@ __global__ void __launch_bounds__ (64) k_model_code (const MPicDev* pics, int n_
       if (has && count >= 0) {
         const int offset = shift - count;
         if ((low << (offset - 1)) & 0x80000000u) {      // carry into the bytes already written
-          int x = (int)c.pos - 1;
-          while (x >= 0) {
-            uint8_t* q = out_ptr (st, ar, lane, (uint32_t)x, false);
-            if (!q) break;
-            if (*q == 0xff) { *q = 0; x--; } else { *q += 1; break; }
+          if (have_last && lastb != 0xffu) {            // the common case touches only the byte this lane wrote last: it is still in a
+            lastb++;                                    // register and `page` is the page it went to - no loads on the coder chain
+            page[(c.pos - 1u) & (PAGE_SIZE - 1)] = (uint8_t)lastb;
+          } else {
+            int x = (int)c.pos - 1;
+            while (x >= 0) {
+              uint8_t* q = out_ptr (st, ar, lane, (uint32_t)x, false);
+              if (!q) break;
+              if (*q == 0xff) { *q = 0; x--; } else { *q += 1; break; }
+            }
           }
         }
         if (((c.pos & (PAGE_SIZE - 1)) == 0 || !page) && !err) {
           uint8_t* q = out_ptr (st, ar, lane, c.pos, true);
           if (!q) err = 2; else page = q - (c.pos & (PAGE_SIZE - 1));
         }
-        if (!err) page[c.pos & (PAGE_SIZE - 1)] = (uint8_t) (low >> (24 - offset));
+        lastb = (low >> (24 - offset)) & 0xffu;
+        have_last = !err;
+        if (!err) page[c.pos & (PAGE_SIZE - 1)] = (uint8_t)lastb;
         c.pos++;
         low <<= offset;
         shift = count;
@@ -856,6 +865,7 @@ __global__ void __launch_bounds__ (64) k_model_code (const MPicDev* pics, int n_
       sh.cons[lane] = consumed;
       if (!h1) { avail = sh.prod[lane]; vnext_ok = false; }
       if (!__any_sync (0xffffffffu, h0 || h1)) {
+        if (idle_ns) __nanosleep (idle_ns);             // nothing to code in any ring: do not spin on the issue slots the producers need
         const int dn = sh.done;
         avail = sh.prod[lane];
         vnext_ok = false;

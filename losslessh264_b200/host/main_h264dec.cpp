@@ -3,6 +3,7 @@
 //   h264dec <in.264> <out.yuv>           decode, write cropped I420 frames
 //   h264dec <in.264> <out.pip> [yuv]     compress: decode + recompression model; writes out.pip and out.pip.<tag>
 //   h264dec <in.pip> <out.264>           decompress: in.pip + in.pip.<tag> -> the original Annex-B file, byte for byte
+//   ... and `.pipx` in place of `.pip`: the single-file container (pip_container.h), an addition of this build
 // one NAL unit per DecodeFrameNoDelay call (3- or 4-byte start codes), the same getters queried
 // after every call, the same "iWidth/height/Frames/decode time/FPS" block on stderr.
 // The .pip compress/decompress modes are selected by file-name suffix exactly like the reference
@@ -38,14 +39,15 @@ static bool slurp (const std::string& path, std::vector<uint8_t>& out) {
 // Round-trip mode of the reference CLI (isRecoding, h264dec.cpp:170-173): the default stream gives the NAL skeleton and the
 // slice headers, the side streams go through the model on the GPU (lh264_model_decode), the host frames the result.
 static int decompress (const char* pip_path, const char* out_path) {
-  std::vector<uint8_t> def;
-  if (!slurp (pip_path, def)) { perror (pip_path); return 1; }
-  std::vector<std::vector<uint8_t> > tags (LH264_NUM_TAGS);
+  lh264host::PipFileSet fs;
+  if (!(lh264host::is_pip_archive_name (pip_path) ? lh264host::pip_archive_read (pip_path, fs) : lh264host::pip_set_read (pip_path, fs))) { fprintf (stderr, "cannot read %s\n", pip_path); return 1; }
+  std::vector<uint8_t>& def = fs.def;
+  std::vector<std::vector<uint8_t> >& tags = fs.tags;
   lh264_decode_job job;
   memset (&job, 0, sizeof (job));
   size_t total = def.size();
   for (int t = 0; t < LH264_NUM_TAGS; t++)
-    if (slurp (std::string (pip_path) + "." + std::to_string (t), tags[t])) {
+    if (fs.present[t]) {
       tags[t].push_back (0);
       job.tag_data[t] = tags[t].data(); job.tag_len[t] = (uint32_t)tags[t].size() - 1; total += tags[t].size();
     }
@@ -87,6 +89,9 @@ int main (int argc, char** argv) {
   const bool compress = strstr (argv[2], ".pip") != nullptr;             // h264dec.cpp:167-169
   if (!compress && strstr (argv[1], ".pip")) return decompress (argv[1], argv[2]);                        // h264dec.cpp:170-173
   const char* yuv_path = compress ? (argc > 3 ? argv[3] : "/dev/null") : argv[2];
+  // `.pipx`: the file set is written next to the archive first, packed, and removed
+  const bool archive = compress && lh264host::is_pip_archive_name (argv[2]);
+  const std::string set_path = archive ? std::string (argv[2]) + ".tmp.pip" : std::string (argv[2]);
   FILE* fi = fopen (argv[1], "rb");
   if (!fi) { perror (argv[1]); return 1; }
   std::vector<unsigned char> buf;
@@ -107,7 +112,7 @@ int main (int argc, char** argv) {
   param.eOutputColorFormat = videoFormatI420; param.uiTargetDqLayer = 255; param.eEcActiveIdc = ERROR_CON_SLICE_COPY;
   param.sVideoProperty.eVideoBsType = VIDEO_BITSTREAM_DEFAULT;
   if (dec->Initialize (&param)) { fprintf (stderr, "Initialize failed (no CUDA device? this build has no CPU fallback)\n"); return 1; }
-  if (compress && dec->SetOption (DECODER_OPTION_LH264_PIP_OUTPUT, argv[2])) { fprintf (stderr, "cannot switch the recompressor on\n"); return 1; }
+  if (compress && dec->SetOption (DECODER_OPTION_LH264_PIP_OUTPUT, (void*)set_path.c_str())) { fprintf (stderr, "cannot switch the recompressor on\n"); return 1; }
 
   int frames = 0, width = 0, height = 0;
   double secs = 0;
@@ -142,5 +147,12 @@ int main (int argc, char** argv) {
   fprintf (stderr, "-------------------------------------------------------\n");
   dec->Uninitialize();
   WelsDestroyDecoder (dec);
+  if (archive) {
+    lh264host::PipFileSet fs;
+    const bool ok = lh264host::pip_set_read (set_path.c_str(), fs) && lh264host::pip_archive_write (argv[2], fs);
+    remove (set_path.c_str());
+    for (int t = 0; t < LH264_NUM_TAGS; t++) remove ((set_path + "." + std::to_string (t)).c_str());
+    if (!ok) { fprintf (stderr, "cannot write %s\n", argv[2]); return 1; }
+  }
   return 0;
 }

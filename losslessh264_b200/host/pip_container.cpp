@@ -1,5 +1,8 @@
 // pip_container.cpp — see pip_container.h.
 #include "pip_container.h"
+#include <stdio.h>
+#include <string.h>
+#include <string>
 #include "h264_syntax.h"
 
 namespace lh264host {
@@ -69,6 +72,78 @@ void PipBoilerplate::unit_end (const UnitSliceInfo& s) {
     if (!s.cabac) def_.emit_bit (1);
   }
   def_.stop_escape();
+}
+
+
+// ---- file sets and the single-file container --------------------------------------------------------------------
+namespace {
+bool slurp_file (const std::string& path, std::vector<uint8_t>& out) {
+  FILE* f = fopen (path.c_str(), "rb");
+  if (!f) return false;
+  uint8_t tmp[65536];
+  size_t n;
+  out.clear();
+  while ((n = fread (tmp, 1, sizeof (tmp), f)) > 0) out.insert (out.end(), tmp, tmp + n);
+  fclose (f);
+  return true;
+}
+bool spill_file (const std::string& path, const std::vector<uint8_t>& b) {
+  FILE* f = fopen (path.c_str(), "wb");
+  if (!f) return false;
+  const bool ok = b.empty() || fwrite (b.data(), 1, b.size(), f) == b.size();
+  return fclose (f) == 0 && ok;
+}
+void put32 (std::vector<uint8_t>& o, uint32_t v) { for (int i = 0; i < 4; i++) o.push_back ((uint8_t) (v >> (8 * i))); }
+void put64 (std::vector<uint8_t>& o, uint64_t v) { for (int i = 0; i < 8; i++) o.push_back ((uint8_t) (v >> (8 * i))); }
+uint64_t get_le (const uint8_t* p, int n) { uint64_t v = 0; for (int i = 0; i < n; i++) v |= (uint64_t)p[i] << (8 * i); return v; }
+const int kNumTags = 70;               // LH264_NUM_TAGS (include/lh264_b200.h)
+}
+
+bool pip_set_read (const char* pip_path, PipFileSet& out) {
+  out.tags.assign (kNumTags, std::vector<uint8_t>());
+  out.present.assign (kNumTags, false);
+  if (!slurp_file (pip_path, out.def)) return false;
+  for (int t = 0; t < kNumTags; t++) out.present[t] = slurp_file (std::string (pip_path) + "." + std::to_string (t), out.tags[t]);
+  return true;
+}
+bool pip_set_write (const char* pip_path, const PipFileSet& in) {
+  if (!spill_file (pip_path, in.def)) return false;
+  for (int t = 0; t < kNumTags && t < (int)in.tags.size(); t++)
+    if (in.present[t] && !spill_file (std::string (pip_path) + "." + std::to_string (t), in.tags[t])) return false;
+  return true;
+}
+bool pip_archive_write (const char* archive_path, const PipFileSet& in) {
+  std::vector<uint8_t> o;
+  uint32_t n = 1;
+  for (int t = 0; t < (int)in.tags.size(); t++) if (in.present[t]) n++;
+  o.insert (o.end(), {'L', 'H', 'P', 'X'});
+  put32 (o, 1); put32 (o, n);
+  put32 (o, 0xffffffffu); put64 (o, in.def.size());
+  for (int t = 0; t < (int)in.tags.size(); t++) if (in.present[t]) { put32 (o, (uint32_t)t); put64 (o, in.tags[t].size()); }
+  o.insert (o.end(), in.def.begin(), in.def.end());
+  for (int t = 0; t < (int)in.tags.size(); t++) if (in.present[t]) o.insert (o.end(), in.tags[t].begin(), in.tags[t].end());
+  return spill_file (archive_path, o);
+}
+bool pip_archive_read (const char* archive_path, PipFileSet& out) {
+  std::vector<uint8_t> b;
+  if (!slurp_file (archive_path, b) || b.size() < 12 || memcmp (b.data(), "LHPX", 4) || get_le (b.data() + 4, 4) != 1) return false;
+  const uint64_t n = get_le (b.data() + 8, 4);
+  if (n < 1 || n > (uint64_t)kNumTags + 1 || b.size() < 12 + 12 * n) return false;
+  out.tags.assign (kNumTags, std::vector<uint8_t>());
+  out.present.assign (kNumTags, false);
+  out.def.clear();
+  uint64_t at = 12 + 12 * n;
+  bool have_def = false;
+  for (uint64_t i = 0; i < n; i++) {
+    const uint32_t tag = (uint32_t)get_le (b.data() + 12 + 12 * i, 4);
+    const uint64_t len = get_le (b.data() + 16 + 12 * i, 8);
+    if (len > b.size() - at) return false;             // truncated or corrupt table
+    if (tag == 0xffffffffu) { if (have_def) return false; out.def.assign (b.begin() + at, b.begin() + at + len); have_def = true; }
+    else if (tag < (uint32_t)kNumTags && !out.present[tag]) { out.tags[tag].assign (b.begin() + at, b.begin() + at + len); out.present[tag] = true; }
+    else return false;
+    at += len;
+  }
+  return have_def && at == b.size();
 }
 
 } // namespace lh264host

@@ -17,6 +17,7 @@
 #pragma once
 #include <stdint.h>
 #include <stddef.h>
+#include <string.h>
 #include <vector>
 
 namespace lh264host {
@@ -60,5 +61,21 @@ class PipBoilerplate {
  private:
   DefaultStream def_;
 };
+
+// ---- single-file container (not in the reference, which writes <= ~35 side files per stream) -----------------
+// `x.pipx` = one file holding the default stream and every tag stream of a `.pip` file set:
+//   "LHPX", u32 version (1), u32 n_entries, n_entries x { u32 tag (0xffffffff = default stream), u64 length }, then the payloads
+//   in table order.  Little endian.  The payload bytes are exactly the files of the set, so packing and unpacking are lossless
+//   and a set unpacked from an archive still expands with the unmodified reference.
+struct PipFileSet {
+  std::vector<uint8_t> def;
+  std::vector<std::vector<uint8_t> > tags;   // [LH264_NUM_TAGS]
+  std::vector<bool> present;                 // a tag that was never used has no side file
+};
+bool pip_set_read (const char* pip_path, PipFileSet& out);            // x.pip + x.pip.<tag>
+bool pip_set_write (const char* pip_path, const PipFileSet& in);
+bool pip_archive_read (const char* archive_path, PipFileSet& out);
+bool pip_archive_write (const char* archive_path, const PipFileSet& in);
+inline bool is_pip_archive_name (const char* path) { const char* d = strrchr (path, '.'); return d && !strcmp (d, ".pipx"); }
 
 } // namespace lh264host

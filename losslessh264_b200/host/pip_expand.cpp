@@ -144,6 +144,17 @@ const lh264_decode_slice* lh264_pip_plan_slices (const lh264_pip_plan_s* p, int*
   if (with_8x8) *with_8x8 = p->plan.with_8x8 ? 1 : 0;
   return p->plan.slices.data();
 }
+// single-file container (pip_container.h): x.pip + x.pip.<tag>  <->  x.pipx.  0 on success.
+int lh264_pip_pack (const char* pip_path, const char* archive_path) {
+  lh264host::PipFileSet fs;
+  if (!pip_path || !archive_path || !lh264host::pip_set_read (pip_path, fs)) return -1;
+  return lh264host::pip_archive_write (archive_path, fs) ? 0 : -2;
+}
+int lh264_pip_unpack (const char* archive_path, const char* pip_path) {
+  lh264host::PipFileSet fs;
+  if (!pip_path || !archive_path || !lh264host::pip_archive_read (archive_path, fs)) return -1;
+  return lh264host::pip_set_write (pip_path, fs) ? 0 : -2;
+}
 long long lh264_pip_assemble (const lh264_pip_plan_s* p, const unsigned char* def, const unsigned char* bits, const lh264_decode_slice_out* outs,
                               unsigned char* dst, size_t cap) {
   if (!p) return -1;

@@ -82,3 +82,47 @@ def expand(ctx, file_sets):
     finally:
         for p in plans:
             p.close()
+
+
+# ---- single-file container `.pipx` (host/pip_container.h) -------------------------------------------------------
+def pack(pip_path, archive_path):
+    """x.pip + x.pip.<tag> -> one `.pipx` file (lh264_pip_pack)."""
+    lib = _lib()
+    lib.lh264_pip_pack.argtypes = [C.c_char_p, C.c_char_p]
+    rc = lib.lh264_pip_pack(os.fsencode(pip_path), os.fsencode(archive_path))
+    if rc:
+        raise OSError(f"lh264_pip_pack({pip_path}) failed: {rc}")
+
+
+def unpack(archive_path, pip_path):
+    """`.pipx` -> x.pip + x.pip.<tag> (lh264_pip_unpack); a missing, truncated or corrupt archive raises."""
+    lib = _lib()
+    lib.lh264_pip_unpack.argtypes = [C.c_char_p, C.c_char_p]
+    rc = lib.lh264_pip_unpack(os.fsencode(archive_path), os.fsencode(pip_path))
+    if rc:
+        raise OSError(f"lh264_pip_unpack({archive_path}) failed: {rc}")
+
+
+def read_archive(archive_path):
+    """(default stream bytes, {tag: bytes}) of a `.pipx` file, parsed here (the format is documented in host/pip_container.h)."""
+    import struct
+
+    b = open(archive_path, "rb").read()
+    if b[:4] != b"LHPX" or struct.unpack_from("<I", b, 4)[0] != 1:
+        raise ValueError("not a .pipx archive")
+    n = struct.unpack_from("<I", b, 8)[0]
+    at = 12 + 12 * n
+    default, tags = None, {}
+    for i in range(n):
+        tag, length = struct.unpack_from("<IQ", b, 12 + 12 * i)
+        payload = b[at : at + length]
+        if len(payload) != length:
+            raise ValueError("truncated .pipx archive")
+        if tag == 0xFFFFFFFF:
+            default = payload
+        else:
+            tags[tag] = payload
+        at += length
+    if default is None or at != len(b):
+        raise ValueError("corrupt .pipx archive")
+    return default, tags

@@ -96,3 +96,16 @@ def test_corrupt_side_stream_does_not_hang_or_pass(name, ctx, tmp_path):
         out = None
     assert out != open(os.path.join(STREAM_DIR, name), "rb").read()
     plan.close()
+
+
+def test_cli_single_file_container_round_trip(tmp_path):
+    """`.pipx` in place of `.pip`: compress writes ONE file, decompress reads it back to the original."""
+    src = os.path.join(STREAM_DIR, "tibby.264")
+    arc = os.path.join(str(tmp_path), "o.pipx")
+    back = os.path.join(str(tmp_path), "b.264")
+    r = subprocess.run([CLI, src, arc], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-400:]
+    assert os.listdir(str(tmp_path)) == ["o.pipx"]
+    r = subprocess.run([CLI, arc, back], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-400:]
+    assert open(back, "rb").read() == open(src, "rb").read()
