@@ -395,10 +395,15 @@ def main():
     workers = [threading.Thread(target=e2e_worker, args=(i,)) for i in range(T)]
     for w_ in workers:
         w_.start()
-    gate.wait()
-    barrier()
-    t0 = time.perf_counter()
-    gate.wait()
+    try:
+        gate.wait()
+        barrier()
+        t0 = time.perf_counter()
+        gate.wait()
+    except threading.BrokenBarrierError:               # a worker failed and aborted the gate: report ITS error
+        for w_ in workers:
+            w_.join()
+        raise RuntimeError("e2e worker failed: " + (errors[0] if errors else "unknown"))
     e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1000.0)
     for w_ in workers:
         w_.join()

@@ -255,8 +255,7 @@ static int model_launch (lh264_ctx* c, ModelCtx* m, MBatch& b, bool head, bool t
   k_model_plan<<<1, 1024, 0, m->stream>>> (n, b.pic_total.p, b.dec_base.p, b.ctl.p, (unsigned long long)m->dec.cap, ar, m->d_poison);
   k_model_emit<<<mb_blocks, GEN_THREADS, gen_smem, m->stream>>> (b.pics.p, n, total_recs, m->dec.p, b.dec_base.p, b.ctl.p);
   if (timed) { CK (cudaEventRecord (m->ev[1], m->stream)); CK (cudaEventRecord (m->ev[2], m->stream)); }
-  static const unsigned idle_ns = [] { const char* e = getenv ("LH264_CODE_IDLE_NS"); return e ? (unsigned)atoi (e) : 0u; } ();   // tuning knob, see profiles/
-  k_model_code<<<n, 64, 0, m->stream>>> (b.pics.p, n, m->dec.p, b.dec_base.p, b.pic_total.p, ar, b.ctl.p, idle_ns);
+  k_model_code<<<n, 64, 0, m->stream>>> (b.pics.p, n, m->dec.p, b.dec_base.p, b.pic_total.p, ar, b.ctl.p);
   c->launches += 3;
   if (!b.done) CK (cudaEventCreateWithFlags (&b.done, cudaEventDisableTiming));
   CK (cudaEventRecord (b.done, m->stream));

@@ -738,7 +738,7 @@ struct CodeShared {
 };
 
 __global__ void __launch_bounds__ (64) k_model_code (const MPicDev* pics, int n_pics, const uint32_t* dec, const unsigned long long* dec_base,
-                                                     const uint32_t* pic_total, ArenaDev ar, const BatchCtl* ctl, unsigned idle_ns) {
+                                                     const uint32_t* pic_total, ArenaDev ar, const BatchCtl* ctl) {
   __shared__ CodeShared sh;
   const int p = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   if (p >= n_pics || ctl->skip) return;
@@ -779,7 +779,7 @@ __global__ void __launch_bounds__ (64) k_model_code (const MPicDev* pics, int n_
       const unsigned tpeers = __match_any_sync (0xffffffffu, tag);
       if (valid) {
         const uint32_t pos = sh.prod[tag] + (uint32_t)__popc (tpeers & lt);
-        while (pos - sh.cons[tag] >= (uint32_t)CODE_RING) { if (idle_ns) __nanosleep (idle_ns); }   // ring full: leave the issue slots to the other warps of the SM
+        while (pos - sh.cons[tag] >= (uint32_t)CODE_RING) { }
         sh.ring[tag][pos & (CODE_RING - 1)] = (uint16_t) ((prob << 1) | bit);
       }
       __threadfence_block();
@@ -865,7 +865,6 @@ __global__ void __launch_bounds__ (64) k_model_code (const MPicDev* pics, int n_
       sh.cons[lane] = consumed;
       if (!h1) { avail = sh.prod[lane]; vnext_ok = false; }
       if (!__any_sync (0xffffffffu, h0 || h1)) {
-        if (idle_ns) __nanosleep (idle_ns);             // nothing to code in any ring: do not spin on the issue slots the producers need
         const int dn = sh.done;
         avail = sh.prod[lane];
         vnext_ok = false;
