@@ -4,7 +4,7 @@
  *
  * CPU build of losslessh264_b200/csrc/model_decode_core.inl (the code the CUDA kernel k_model_decode runs, compiled here
  * with MD_FN = static inline) behind the signature of lh264_model_decode(), plus a small CLI:
- *     expand_cpu x.pip out.264
+ *     expand_cpu x.pip out.264 [--intra-as-cabac]
  * which reads x.pip (default stream) and x.pip.<tag>, expands them with host/pip_expand.cpp and writes the .264.
  * Parity is PINNED by the data itself: the expanded file must equal the original .264 byte for byte, and the side streams
  * fed in are those of the compiled, unmodified reference (oracle/_ref/h264dec) or of this repository's compress direction,
@@ -93,7 +93,7 @@ static bool slurp (const std::string& path, std::vector<uint8_t>& out) {
 }
 
 int main (int argc, char** argv) {
-  if (argc < 3) { fprintf (stderr, "usage: %s x.pip out.264\n", argv[0]); return 2; }
+  if (argc < 3) { fprintf (stderr, "usage: %s x.pip out.264 [--intra-as-cabac]\n", argv[0]); return 2; }
   std::vector<uint8_t> def;
   if (!slurp (argv[1], def)) { perror (argv[1]); return 1; }
   std::vector<std::vector<uint8_t>> tags (LH264_NUM_TAGS);
@@ -107,6 +107,11 @@ int main (int argc, char** argv) {
     }
   lh264host::ExpandPlan plan;
   if (!lh264host::expand_plan (def.data(), def.size(), plan)) { fprintf (stderr, "cannot expand: %s\n", plan.error.c_str()); return 3; }
+  // test hook (tests/test_cabac_transcode.py): write the slice data of I slices with the CABAC writer instead of the CAVLC one.
+  // The header of an I slice is the same for both entropy coders, so flipping entropy_coding_mode_flag in the PPS of the result
+  // gives a valid CABAC stream - a way to exercise CABAC paths (8x8 residual blocks) no stream of the corpus has.
+  if (argc > 3 && !strcmp (argv[3], "--intra-as-cabac"))
+    for (lh264_decode_slice& sl : plan.slices) if (sl.slice_type == 2) sl.flags |= 4;
   std::vector<lh264_decode_slice_out> outs (plan.slices.size() + 1);
   std::vector<uint8_t> bits;
   for (size_t cap = total * 4 + (1u << 20);; cap *= 2) {
