@@ -204,6 +204,18 @@ class Context:
         if sync:
             self.sync()
 
+    def recon_descs(self, pics, streams):
+        """The lh264_picture_desc array of a submit, built once (plain structs of pointers into the caller's host buffers - what a
+        C host has at hand anyway); pass it to recon_prepared() as often as needed.  The buffers must stay alive and unchanged."""
+        arr, keep = self._descs(pics, streams)
+        return (arr, len(pics), keep)
+
+    def recon_prepared(self, prepared, sync=True):
+        arr, n, _ = prepared
+        _check(self.lib, self.lib.lh264_recon_submit(self.h, arr, n))
+        if sync:
+            self.sync()
+
     def upload_batch(self, pics, streams):
         arr, keep = self._descs(pics, streams)
         h = C.c_void_p()
@@ -279,6 +291,17 @@ class Context:
         arr, keep = self._model_descs(mpics, model_streams)
         self._keep_model = keep
         _check(self.lib, self.lib.lh264_model_submit(self.h, arr, len(mpics)))
+        if sync:
+            self.sync()
+
+    def model_descs(self, mpics, model_streams):
+        """The lh264_model_picture array of a submit, built once; see recon_descs()."""
+        arr, keep = self._model_descs(mpics, model_streams)
+        return (arr, len(mpics), keep)
+
+    def model_submit_prepared(self, prepared, sync=True):
+        arr, n, _ = prepared
+        _check(self.lib, self.lib.lh264_model_submit(self.h, arr, n))
         if sync:
             self.sync()
 
