@@ -30,7 +30,8 @@ class BitReader {
   bool overrun() const { return pos_ > n_; }
   const uint8_t* data() const { return p_; }
 
-  inline uint32_t peek (int n) const {   // 1..32 bits, MSB first
+  inline uint32_t peek (int n) const {   // 1..32 bits, MSB first; past the end of the buffer (damaged streams) reads are zeros
+    if (pos_ > n_) return 0;             // (pos_ <= n_ keeps the 8-byte load inside the zero padding the caller guarantees)
     uint64_t v;
     memcpy (&v, p_ + (pos_ >> 3), 8);
     v = __builtin_bswap64 (v) << (pos_ & 7);
@@ -38,7 +39,7 @@ class BitReader {
   }
   inline void skip (int n) { pos_ += n; }
   inline uint32_t u (int n) { if (n == 0) return 0; uint32_t v = peek (n); pos_ += n; return v; }
-  inline uint32_t u1() { uint32_t v = (p_[pos_ >> 3] >> (7 - (pos_ & 7))) & 1; pos_++; return v; }
+  inline uint32_t u1() { if (pos_ > n_) { pos_++; return 0; } uint32_t v = (p_[pos_ >> 3] >> (7 - (pos_ & 7))) & 1; pos_++; return v; }
   inline uint32_t ue() {
     const uint32_t w = peek (32);
     if (w == 0) {                       // >= 32 leading zeros: malformed for every syntax element we read

@@ -629,6 +629,7 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_mod
     const size_t at = coefs.size();
     coefs.resize (at + 384);
     int16_t* o = coefs.data() + at;
+    if (br.pos() + 384 * 8 > br.size_bits()) { coefs.resize (at); return -1; }   // samples cut off (damaged stream)
     const uint8_t* src = br.data() + (br.pos() >> 3);
     for (int i = 0; i < 384; i++) o[i] = src[i];
     br.skip (384 * 8);

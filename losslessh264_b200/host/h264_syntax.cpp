@@ -186,6 +186,7 @@ int parse_slice_header (BitReader& br, int nal_ref_idc, int nal_type, const Sps*
       sh.has_wp = true;
       sh.luma_log2_denom = br.ue();
       sh.chroma_log2_denom = br.ue();
+      if ((unsigned)sh.luma_log2_denom > 7 || (unsigned)sh.chroma_log2_denom > 7) return -1;   // 7.4.3.2: 0..7
       for (int i = 0; i < sh.num_ref_idx_l0; i++) {
         sh.luma_weight[i] = 1 << sh.luma_log2_denom; sh.luma_offset[i] = 0;
         for (int c = 0; c < 2; c++) { sh.chroma_weight[i][c] = 1 << sh.chroma_log2_denom; sh.chroma_offset[i][c] = 0; }
@@ -210,7 +211,7 @@ int parse_slice_header (BitReader& br, int nal_ref_idc, int nal_type, const Sps*
       }
     }
   }
-  if (pps.cabac && sh.slice_type != SLICE_I) sh.cabac_init_idc = br.ue();
+  if (pps.cabac && sh.slice_type != SLICE_I) { const uint32_t idc = br.ue(); if (idc > 2) return -1; sh.cabac_init_idc = (int)idc; }   // 7.4.3: 0..2
   sh.slice_qp = pps.pic_init_qp + br.se();
   if (sh.slice_qp < 0 || sh.slice_qp > 51) return -1;
   if (pps.deblocking_filter_control_present) {

@@ -39,6 +39,7 @@ extern "C" int mdc_model_decode (lh264_decode_job* jobs, int n_jobs) {
   int bad = 0;
   for (int j = 0; j < n_jobs; j++) {
     lh264_decode_job& job = jobs[j];
+    if (job.max_mbs <= 0 || !job.out) { job.error = MD_ERR_DIMS; bad++; continue; }   // as lh264_model_decode (model_decode_host.inl)
     const size_t n = (size_t)job.max_mbs;
     std::vector<uint32_t> priors (job.with_8x8 ? P_END : P_END_NO8, 0);
     std::vector<CtxRec> f0 (n), f1 (n);
