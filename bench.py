@@ -134,7 +134,9 @@ def bench_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(v, 2), "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
         "ms_per_step": round(1000 * dt / steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD},
+        "config": {"workload": WORKLOAD, "streams_per_gpu": args.streams, "resolution": "1920x1080 (coded 1920x1088)",
+                   "step": "reconstruction (decode) + recompression model, i.e. the whole `h264dec in.264 out.pip` hot path; a reference step = "
+                           f"{k} one-stream processes (its model state is process-global) x the 16 pictures of the workload stream"},
         "cpu_baseline": {"value": round(v, 2), "unit": UNIT, "cores": k, "host_cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": round(v, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
