@@ -144,6 +144,7 @@ __global__ void __launch_bounds__ (32, 28) k_model_decode (MdJobDev* jobs, int n
   const int lane = threadIdx.x;
   for (unsigned i = lane; i < sizeof (MdStream) / 4; i += 32) reinterpret_cast<uint32_t*> (&st)[i] = reinterpret_cast<const uint32_t*> (&job.st)[i];
   __syncwarp();
+  md_scratch_init (sc, lane, 32);
   if (lane == 0) s_test = job.st.priors[P_TEST];
   if (lane < CT_COUNT) {
     md_reader_init (s_rd[lane], job.tag_buf[lane], job.tag_buf[lane] ? job.tag_len[lane] : 0u);

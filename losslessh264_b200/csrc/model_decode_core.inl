@@ -208,10 +208,20 @@ struct MdScratch {
   int16_t lev[384];               // its levels, layout of the coefficient pool (24 chunks of 16)
   int32_t level[16], run[16];     // cw_residual_block
   uint8_t cnt[24];
+  // the scan tables of the slice-data writers, staged here (CUDA build: shared memory) so that the per-coefficient look-ups of
+  // cw_residual_block / cb_block stay off the global-load path (md_scratch_init)
+  uint8_t t_zigzag4[16], t_zigzag8[64], t_i16dc[16], t_cdc[4], t_scan4[16];
   // CABAC slices: arithmetic encoder (9.3.4.2) and the context variables of the slice, (pStateIdx << 1) | valMPS
   uint32_t cb_low, cb_range, cb_outstanding, cb_first;
   uint8_t cb_state[460];
 };
+MD_FN void md_scratch_init (MdScratch& sc, int lane, int n_lanes) {
+  for (int i = lane; i < 64; i += n_lanes) {
+    sc.t_zigzag8[i] = md_zigzag8[i];
+    if (i < 16) { sc.t_zigzag4[i] = md_zigzag4[i]; sc.t_i16dc[i] = md_i16dc_scan[i]; sc.t_scan4[i] = md_scan4[i]; }
+    if (i < 4) sc.t_cdc[i] = md_cdc_scan[i];
+  }
+}
 
 // ---- bit sink of the re-serialiser ------------------------------------------------------------------------------------
 struct MdBits {
@@ -372,27 +382,27 @@ MD_FN_NOINLINE bool cw_mb (MdBits& bw, MdScratch& sc, CwSlice& s, uint8_t* tc, c
     mb_se (bw, d);
     s.qp = r.luma_qp;
   }
-  if (i16) cw_residual_block (bw, sc, cw_nC (tcL ? tcL[3] : -1, tcT ? tcT[12] : -1), 16, lev, md_i16dc_scan, 1);
+  if (i16) cw_residual_block (bw, sc, cw_nC (tcL ? tcL[3] : -1, tcT ? tcT[12] : -1), 16, lev, sc.t_i16dc, 1);
   for (int q = 0; q < 4; q++) {
-    if (!(cbpL & (1 << q))) { for (int k = 0; k < 4; k++) tc[md_scan4[4 * q + k]] = 0; continue; }
+    if (!(cbpL & (1 << q))) { for (int k = 0; k < 4; k++) tc[sc.t_scan4[4 * q + k]] = 0; continue; }
     for (int k = 0; k < 4; k++) {
-      const int z = 4 * q + k, rr = md_scan4[z], bx = rr & 3, by = rr >> 2;
+      const int z = 4 * q + k, rr = sc.t_scan4[z], bx = rr & 3, by = rr >> 2;
       const int nA = bx > 0 ? tc[rr - 1] : (tcL ? tcL[rr + 3] : -1), nB = by > 0 ? tc[rr - 4] : (tcT ? tcT[rr + 12] : -1);
       int n;
-      if (t8) n = cw_residual_block (bw, sc, cw_nC (nA, nB), 16, lev + 64 * q, md_zigzag8 + k, 4);       // 4 interleaved sub-blocks
-      else if (i16) n = cw_residual_block (bw, sc, cw_nC (nA, nB), 15, lev + 16 * z, md_zigzag4 + 1, 1);
-      else n = cw_residual_block (bw, sc, cw_nC (nA, nB), 16, lev + 16 * z, md_zigzag4, 1);
+      if (t8) n = cw_residual_block (bw, sc, cw_nC (nA, nB), 16, lev + 64 * q, sc.t_zigzag8 + k, 4);       // 4 interleaved sub-blocks
+      else if (i16) n = cw_residual_block (bw, sc, cw_nC (nA, nB), 15, lev + 16 * z, sc.t_zigzag4 + 1, 1);
+      else n = cw_residual_block (bw, sc, cw_nC (nA, nB), 16, lev + 16 * z, sc.t_zigzag4, 1);
       tc[rr] = (uint8_t)n;
     }
   }
   if (cbpC)
-    for (int p = 0; p < 2; p++) cw_residual_block (bw, sc, -1, 4, lev + 16 * (16 + 4 * p), md_cdc_scan, 1);
+    for (int p = 0; p < 2; p++) cw_residual_block (bw, sc, -1, 4, lev + 16 * (16 + 4 * p), sc.t_cdc, 1);
   for (int p = 0; p < 2; p++)
     for (int b = 0; b < 4; b++) {
       const int base = 16 + 4 * p;
       if (cbpC & 2) {
         const int nA = (b & 1) ? tc[base + b - 1] : (tcL ? tcL[base + b + 1] : -1), nB = (b & 2) ? tc[base + b - 2] : (tcT ? tcT[base + b + 2] : -1);
-        tc[base + b] = (uint8_t)cw_residual_block (bw, sc, cw_nC (nA, nB), 15, lev + 16 * (base + b), md_zigzag4 + 1, 1);
+        tc[base + b] = (uint8_t)cw_residual_block (bw, sc, cw_nC (nA, nB), 15, lev + 16 * (base + b), sc.t_zigzag4 + 1, 1);
       } else tc[base + b] = 0;
     }
   return true;
@@ -671,31 +681,31 @@ MD_FN_NOINLINE bool cb_mb (MdBits& bw, MdScratch& sc, CwSlice& s, uint8_t* cur, 
     s.qp = r.luma_qp;
   }
   uint32_t cbf = 0;
-  if (i16) { if (cb_block (bw, sc, 0, cb_cbf_inc (cur, L, T, intra, -1, 24, -1, 24), lev, md_i16dc_scan, 0)) { cbf |= 1u << 24; cb_set_word (cur, cbf); } }
+  if (i16) { if (cb_block (bw, sc, 0, cb_cbf_inc (cur, L, T, intra, -1, 24, -1, 24), lev, sc.t_i16dc, 0)) { cbf |= 1u << 24; cb_set_word (cur, cbf); } }
   for (int q = 0; q < 4; q++) {
     if (!(cbpL & (1 << q))) continue;
     if (t8) {
-      cb_block (bw, sc, 5, -1, lev + 64 * q, md_zigzag8, 0);
-      for (int k = 0; k < 4; k++) cbf |= 1u << md_scan4[4 * q + k];
+      cb_block (bw, sc, 5, -1, lev + 64 * q, sc.t_zigzag8, 0);
+      for (int k = 0; k < 4; k++) cbf |= 1u << sc.t_scan4[4 * q + k];
       cb_set_word (cur, cbf);
       continue;
     }
     for (int k = 0; k < 4; k++) {
-      const int z = 4 * q + k, rr = md_scan4[z], bx = rr & 3, by = rr >> 2;
+      const int z = 4 * q + k, rr = sc.t_scan4[z], bx = rr & 3, by = rr >> 2;
       const int inc = cb_cbf_inc (cur, L, T, intra, bx > 0 ? rr - 1 : -1, rr + 3, by > 0 ? rr - 4 : -1, rr + 12);
-      const int n = i16 ? cb_block (bw, sc, 1, inc, lev + 16 * z, md_zigzag4, 1) : cb_block (bw, sc, 2, inc, lev + 16 * z, md_zigzag4, 0);
+      const int n = i16 ? cb_block (bw, sc, 1, inc, lev + 16 * z, sc.t_zigzag4, 1) : cb_block (bw, sc, 2, inc, lev + 16 * z, sc.t_zigzag4, 0);
       if (n) { cbf |= 1u << rr; cb_set_word (cur, cbf); }
     }
   }
   if (cbpC)
     for (int p = 0; p < 2; p++)
-      if (cb_block (bw, sc, 3, cb_cbf_inc (cur, L, T, intra, -1, 25 + p, -1, 25 + p), lev + 16 * (16 + 4 * p), md_cdc_scan, 0)) { cbf |= 1u << (25 + p); cb_set_word (cur, cbf); }
+      if (cb_block (bw, sc, 3, cb_cbf_inc (cur, L, T, intra, -1, 25 + p, -1, 25 + p), lev + 16 * (16 + 4 * p), sc.t_cdc, 0)) { cbf |= 1u << (25 + p); cb_set_word (cur, cbf); }
   if (cbpC & 2)
     for (int p = 0; p < 2; p++)
       for (int b = 0; b < 4; b++) {
         const int bit = 16 + 4 * p + b;
         const int inc = cb_cbf_inc (cur, L, T, intra, (b & 1) ? bit - 1 : -1, bit + 1, (b & 2) ? bit - 2 : -1, bit + 2);
-        if (cb_block (bw, sc, 4, inc, lev + 16 * bit, md_zigzag4, 1)) { cbf |= 1u << bit; cb_set_word (cur, cbf); }
+        if (cb_block (bw, sc, 4, inc, lev + 16 * bit, sc.t_zigzag4, 1)) { cbf |= 1u << bit; cb_set_word (cur, cbf); }
       }
   cb_terminate (bw, sc, (r.flags & LH264_MM_STOP_BIT) != 0);
   return true;

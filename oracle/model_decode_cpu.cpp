@@ -57,6 +57,7 @@ extern "C" int mdc_model_decode (lh264_decode_job* jobs, int n_jobs) {
       if (job.tag_data[tag]) st.present |= 1u << t;
     }
     MdScratch sc;
+    md_scratch_init (sc, 0, 1);
     MdCtx c;
     md_ctx_init (c, st.priors, st.rd);
     c.test = priors[P_TEST];

@@ -61,7 +61,7 @@ int main (int argc, char** argv) {
     uint8_t* p = base + o_state + per * (size_t)j;
     jd.st.priors = (uint32_t*)p; p += per_priors;
     jd.st.frame[0] = (CtxRec*)p; p += up (n * 32); jd.st.frame[1] = (CtxRec*)p; p += up (n * 32);
-    jd.st.ipm = p; p += up (n * 16); jd.st.mb_slice = (int32_t*)p; p += up (n * 4); jd.st.mb_intra = p; p += up (n); jd.st.tcoef = p; p += up (n * 24);
+    jd.st.ipm = p; p += up (n * 16); jd.st.mb_slice = (int32_t*)p; p += up (n * 4); jd.st.mb_intra = p; p += up (n); jd.st.tcoef = p; p += up (n * MD_NB_STRIDE);
     jd.sout = (lh264_decode_slice_out*)p; p += up (ns * sizeof (lh264_decode_slice_out));
     jd.out = p; jd.cap = cap;
     jd.st.max_mbs = plan.max_mbs; jd.slices = (const MdSliceIn*) (base + o_slices); jd.n_slices = (int)ns;
