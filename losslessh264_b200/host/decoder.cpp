@@ -90,6 +90,7 @@ struct Decoder::Impl {
     uint8_t cbp, chroma;                 // coded_block_pattern as 9.3.3.1.1.4 sees it (I_PCM: 0x2f), intra_chroma_pred_mode as coded
   };
   CabacDecoder cab;
+  int16_t lev_[384] = {0};               // residual scratch of parse_mb
   bool cabac_on = false, last_dqp_nz = false;
   std::vector<CabMb> cabmb;
   std::vector<uint8_t> mvd_abs;          // [mb][16][2] |mvd| per raster 4x4 block, saturated at 128
@@ -538,7 +539,7 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_mod
     else t -= 5;
   }
   if (intra && t > 25) return -1;
-  int16_t lev[384];
+  int16_t* const lev = lev_;                         // all zero between macroblocks (see below)
   uint32_t coded = 0;
   int cbp = 0;
   bool i16 = false;
@@ -719,15 +720,16 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_mod
     if (dqp < -26 || dqp > 25) return -1;
     qp = (qp + dqp + 52) % 52;
     set_qp (m);
-    memset (lev, 0, sizeof (lev));
-    if ((cabac_on ? parse_residual_cabac (m, mb_addr, lev, coded, i16, cbp) : parse_residual (br, m, mb_addr, lev, coded, i16, cbp)) < 0) return -1;
+    // the residual parsers write levels only into blocks they flag in `coded`, and the copy below zeroes those again: the
+    // 768-byte scratch never needs a full clear (only after a parse error, which may stop in the middle of a block)
+    if ((cabac_on ? parse_residual_cabac (m, mb_addr, lev, coded, i16, cbp) : parse_residual (br, m, mb_addr, lev, coded, i16, cbp)) < 0) { memset (lev_, 0, sizeof (lev_)); return -1; }
     if (coded) {
       m.coded_mask = coded;
       m.coef_off = (uint32_t) (coefs.size() / 16);
       size_t at = coefs.size();
       coefs.resize (at + 16 * (size_t)__builtin_popcount (coded));
       int16_t* o = coefs.data() + at;
-      for (uint32_t mk = coded; mk; mk &= mk - 1) { const int k = __builtin_ctz (mk); memcpy (o, lev + 16 * k, 32); o += 16; }
+      for (uint32_t mk = coded; mk; mk &= mk - 1) { const int k = __builtin_ctz (mk); memcpy (o, lev + 16 * k, 32); memset (lev + 16 * k, 0, 32); o += 16; }
     }
   } else {
     set_qp (m);
