@@ -83,3 +83,21 @@ def test_kernel_idct_mc_expand_match_oracle(ctx):
         assert np.array_equal(g[: b[5], : b[4]], want)
     assert np.array_equal(ctx.k_expand_plane(ref, 32), oracle.expand_plane(ref, 32))
     assert np.array_equal(ctx.k_expand_plane(ref[:24, :32], 16), oracle.expand_plane(ref[:24, :32], 16))
+
+
+def test_prepared_descriptor_arrays_submit_the_same_work(ctx):
+    """Context.recon_descs / recon_prepared (descriptor arrays built once, submitted many times — what bench.py's host-buffer loop
+    does) must give the pictures of the plain recon() call."""
+    mb_w, mb_h = 20, 15
+    seq = synth.synthetic_sequence(mb_w, mb_h, n_pictures=3, seed=77)
+    a, b = ctx.open_stream(mb_w, mb_h, 3), ctx.open_stream(mb_w, mb_h, 3)
+    try:
+        prepared = [ctx.recon_descs([p], [b]) for p in seq]
+        for rep in range(2):                              # the same arrays again: a second pass over the sequence
+            for p, d in zip(seq, prepared):
+                ctx.recon([p], [a])
+                ctx.recon_prepared(d)
+                assert np.array_equal(ctx.read_picture(a, p.cur_slot, mb_w, mb_h), ctx.read_picture(b, p.cur_slot, mb_w, mb_h))
+    finally:
+        ctx.close_stream(a)
+        ctx.close_stream(b)
