@@ -35,6 +35,13 @@ def test_openh264_api_library_exports_decoder_symbols():
     lib = C.CDLL(os.path.join(ROOT, "losslessh264_b200", "_lib", "libopenh264_lh264.so"))
     for n in ("WelsCreateDecoder", "WelsDestroyDecoder", "WelsGetDecoderCapability", "WelsGetCodecVersion", "WelsGetCodecVersionEx"):
         assert hasattr(lib, n)
+    # ... and every lh264_pip_* entry point include/lh264_codec_api.h declares (container code of both directions)
+    src = open(os.path.join(ROOT, "include", "lh264_codec_api.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = sorted(set(re.findall(r"\b(lh264_pip_[a-z0-9_]+)\s*\(", src)))
+    assert names == ["lh264_pip_assemble", "lh264_pip_pack", "lh264_pip_plan", "lh264_pip_plan_free", "lh264_pip_plan_slices", "lh264_pip_unpack"]
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in include/lh264_codec_api.h but not exported"
 
 
 def test_record_layouts():
