@@ -24,6 +24,9 @@ const uint8_t kRtoZ[16] = {0, 1, 4, 5, 2, 3, 6, 7, 8, 9, 12, 13, 10, 11, 14, 15}
 
 namespace {
 
+// LH264_DEBUG=1: per-slice / per-picture trace of the host decoder on stderr (reference lists, completeness); read once
+bool debug_trace() { static const bool on = getenv ("LH264_DEBUG") != nullptr; return on; }
+
 // Table 8-15: QPc as a function of qPI
 const uint8_t kChromaQp[52] = {0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26, 27, 28, 29,
                                29, 30, 31, 32, 32, 33, 34, 34, 35, 35, 36, 36, 37, 37, 37, 38, 38, 38, 39, 39, 39, 39
@@ -345,7 +348,7 @@ struct Decoder::Impl {
     if (!info.complete) frozen = true;
     else if (sh0.idr) frozen = false;
     info.output = !frozen;
-    if (getenv ("LH264_DEBUG")) fprintf (stderr, "picture: %dx%d idr %d frame_num %d decoded %d of %d slices %zu\n", mb_w, mb_h, (int)sh0.idr, sh0.frame_num, decoded, n_mbs, slices.size());
+    if (debug_trace()) fprintf (stderr, "picture: %dx%d idr %d frame_num %d decoded %d of %d slices %zu\n", mb_w, mb_h, (int)sh0.idr, sh0.frame_num, decoded, n_mbs, slices.size());
     if (!slices.empty()) rc = sink->submit (d, info);
     if (want_model && !mslices.empty()) {
       lh264_model_picture mp;
@@ -1135,7 +1138,7 @@ int Decoder::Impl::parse_slice_data (BitReader& br, Decoder* self) {
       self->stats_.rewritten_slices++;
       if (!ok) {
         self->stats_.rewrite_mismatches++;
-        if (getenv ("LH264_DEBUG")) fprintf (stderr, "rewrite mismatch: slice first_mb %d type %d: %zu bits parsed, %zu written\n", first, ms.slice_type, n, bw.bits());
+        if (debug_trace()) fprintf (stderr, "rewrite mismatch: slice first_mb %d type %d: %zu bits parsed, %zu written\n", first, ms.slice_type, n, bw.bits());
       }
     }
   }
@@ -1198,7 +1201,7 @@ int Decoder::decode (const uint8_t* data, size_t len, unsigned long long timesta
       sr.num_ref_idx_l0 = (uint8_t)sh.num_ref_idx_l0;
       if (sh.slice_type == SLICE_P) {
         D.build_list0();
-        if (getenv("LH264_DEBUG")) { fprintf(stderr, "slice fn=%d nref=%d refs=%zu mods:", sh.frame_num, sh.num_ref_idx_l0, D.refs.size()); for (auto& mm : sh.mods) fprintf(stderr, " (%d,%u)", mm.op, mm.val); fprintf(stderr, " | refs:"); for (auto& r : D.refs) fprintf(stderr, " [slot %d fn %d long %d idx %d]", r.slot, r.frame_num, r.is_long, r.long_idx); fprintf(stderr, " | mmco:"); for (auto& mm : sh.mmcos) fprintf(stderr, " (%d,%u,%u)", mm.op, mm.a, mm.b); fprintf(stderr, "\n"); }
+        if (debug_trace()) { fprintf(stderr, "slice fn=%d nref=%d refs=%zu mods:", sh.frame_num, sh.num_ref_idx_l0, D.refs.size()); for (auto& mm : sh.mods) fprintf(stderr, " (%d,%u)", mm.op, mm.val); fprintf(stderr, " | refs:"); for (auto& r : D.refs) fprintf(stderr, " [slot %d fn %d long %d idx %d]", r.slot, r.frame_num, r.is_long, r.long_idx); fprintf(stderr, " | mmco:"); for (auto& mm : sh.mmcos) fprintf(stderr, " (%d,%u,%u)", mm.op, mm.a, mm.b); fprintf(stderr, "\n"); }
         const int fallback = D.list0[0] ? D.list0[0]->slot : (D.refs.empty() ? 0 : D.refs.back().slot);
         for (int i = 0; i < LH264_MAX_REFS; i++) sr.ref_slot[i] = (int16_t) (D.list0[i] ? D.list0[i]->slot : fallback);
         // explicit WP is "on" in the reference only when some weight differs from the default
