@@ -1013,7 +1013,7 @@ int Decoder::Impl::parse_slice_data_cabac (BitReader& br, Decoder* self) {
       mr->flags |= LH264_MM_EMIT_SKIP_RUN | (skip ? LH264_MM_STOP_IN_SKIP : LH264_MM_WRITE_BLOCK);
       mr->skip_run = skip ? 1 : 0;
     }
-    if (parse_mb (br, mb_addr, skip, mr) < 0 || br.overrun()) { rc = -1; self->stats_.errors++; if (mr) mrecs.pop_back(); break; }
+    if (parse_mb (br, mb_addr, skip, mr) < 0 || cab.overrun()) { rc = -1; self->stats_.errors++; if (mr) mrecs.pop_back(); break; }
     if (mr && !skip) {
       const int d = (int)mr->luma_qp - m_cached_qp;
       mr->qp_delta = (int8_t)d;
