@@ -30,11 +30,14 @@ int GpuSink::submit (const lh264_picture_desc& pic, const DecodedPictureInfo&) {
 int GpuSink::submit_model (const lh264_model_picture& pic, const DecodedPictureInfo&) {
   if (!ctx_) return LH264_E_NO_DEVICE;
   const int mbs = pic.mb_w * pic.mb_h;
-  if (model_ >= 0 && mbs > model_mbs_) return LH264_E_UNSUPPORTED;   // a larger picture mid-stream: reopen is not modelled
+  if (model_ >= 0 && mbs > model_mbs_) return LH264_E_UNSUPPORTED;   // beyond level 5.2: not a stream the reference decodes either
   if (model_ < 0) {
-    model_ = lh264_model_open (ctx_, mbs, /*with_8x8*/1);
+    // The model's priors live across a change of resolution (the reference only drops its FreqImage then), so the stream is
+    // opened once, for the largest picture an H.264 level allows (level 5.2: 36 864 macroblocks; this sizes two frames of 32-byte
+    // context records, 2.4 MB) - a sequence that switches to a bigger picture (Error_I_P.264) keeps coding into the same state.
+    model_mbs_ = mbs > 36864 ? mbs : 36864;
+    model_ = lh264_model_open (ctx_, model_mbs_, /*with_8x8*/1);
     if (model_ < 0) return model_;
-    model_mbs_ = mbs;
   }
   lh264_model_picture p = pic;
   p.model_stream = model_;
