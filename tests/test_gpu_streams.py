@@ -28,7 +28,7 @@ import json
 
 PIP_GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "pip_tag_sha1.json")))
 PIP_SET = ["tibby.264", "tibby8x8cavlc.264", "BA1_FT_C.264", "black.264", "BAMQ2_JVC_C.264", "MR2_TANDBERG_E.264", "SVA_FM1_E.264", "CVPCMNL1_SVA_C.264",
-           "syn_qcif_4slices_8f.264", "syn720p_8f.264"]
+           "syn_qcif_4slices_8f.264", "syn720p_8f.264", "Error_I_P.264"]      # the last one: damaged, switches to a BIGGER picture mid-stream
 
 
 @pytest.mark.parametrize("name", PIP_SET)
