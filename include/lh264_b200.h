@@ -361,7 +361,8 @@ unsigned long long lh264_model_decisions(lh264_ctx* ctx, int model_stream);
  * The reference's round trip (h264dec x.pip out.264): every arithmetic-coded side stream is read back through the same
  * adaptive priors (decode4x4 / readMv / scanInt / scanUEGkInt, codec/decoder/core/inc/compression_stream.h:601-689,
  * src/decode_slice.cpp:2476-2956; bool decoder inc/bitreader.h:77-136) and each macroblock is re-serialised as CAVLC
- * (EncoderState, decode_slice.cpp:1442-1835 -> encoder/core/src/svc_set_mb_syn_cavlc.cpp).  Here one job = one stream: its
+ * (EncoderState, decode_slice.cpp:1442-1835 -> encoder/core/src/svc_set_mb_syn_cavlc.cpp) or, for slices of a CABAC picture
+ * parameter set, as CABAC (decode_slice.cpp:1512-1539 -> svc_set_mb_syn_cabac.cpp; flags bit 2 of lh264_decode_slice).  Here one job = one stream: its
  * side streams and the parameters of its slices (from the slice headers kept in the default stream) go in, the slice_data()
  * bits of every slice come out.  Decoding is strictly serial inside a stream; a call runs all of its jobs concurrently.   */
 typedef struct lh264_decode_slice {
