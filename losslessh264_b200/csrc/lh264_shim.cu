@@ -31,6 +31,7 @@ namespace {
 
 struct StreamRec {
   bool open = false;
+  uint64_t batch_stamp = 0;                  // serial number of the last batch that named this stream (duplicate check, O(n))
   int mb_w = 0, mb_h = 0, n_slots = 0;
   uint8_t* base = nullptr;
   size_t slot_stride = 0;
@@ -96,6 +97,7 @@ struct lh264_ctx {
   DevBuf<PackDev> pack_jobs; PinBuf<PackDev> h_pack_jobs; DevBuf<uint8_t> pack_out;
   DevBuf<uint8_t> scratch_a, scratch_b, scratch_c;
   uint64_t launches = 0;
+  uint64_t batch_serial = 0;
   // per-family device timing
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float ms[3] = {0, 0, 0};
@@ -104,7 +106,8 @@ struct lh264_ctx {
   void* decode = nullptr;                    // DecodeCtx (model_decode.cuh), created by the first lh264_model_decode
   // host pointer -> device copy of the coefficient pools staged by the last lh264_recon_submit: a model picture that names
   // the same pool (it is the same data) reads the device copy instead of crossing PCIe twice
-  std::vector<std::pair<const int16_t*, const int16_t*> > staged_coefs;
+  struct StagedPool { const int16_t* host; const int16_t* dev; int n_blocks; };
+  std::vector<StagedPool> staged_coefs;        // valid for ONE lh264_model_submit: consumed (cleared) by it
   cudaEvent_t recon_staged = nullptr;        // the H2D copies of that batch are done
   // decoded pictures leave on a copy stream of their own, so that this batch's D2H overlaps the next batch's H2D (PCIe is
   // full duplex) and kernels
@@ -286,8 +289,14 @@ static int launch_recon (lh264_ctx* c, BatchDev& b) {
 int lh264_recon_submit (lh264_ctx* c, const lh264_picture_desc* pics, int n_pics) {
   if (!c || (n_pics > 0 && !pics) || n_pics < 0) return fail (LH264_E_INVALID, "bad arguments");
   CK (cudaSetDevice (c->device));
-  for (int i = 0; i < n_pics; i++) for (int j = i + 1; j < n_pics; j++)
-      if (n_pics <= 64 && pics[i].stream == pics[j].stream) return fail (LH264_E_INVALID, "two pictures of one stream in a batch");
+  // two pictures of one stream in a batch would race on cur_slot (and on the stream's references): refuse, at every batch size
+  c->batch_serial++;
+  for (int i = 0; i < n_pics; i++) {
+    const int s = pics[i].stream;
+    if (s < 0 || s >= (int)c->streams.size() || !c->streams[s].open) return fail (LH264_E_INVALID, "picture names a closed stream");
+    if (c->streams[s].batch_stamp == c->batch_serial) return fail (LH264_E_INVALID, "two pictures of one stream in a batch");
+    c->streams[s].batch_stamp = c->batch_serial;
+  }
   c->staged_coefs.clear();
   c->batch_cur ^= 1;
   const int k = c->batch_cur;
@@ -301,7 +310,7 @@ int lh264_recon_submit (lh264_ctx* c, const lh264_picture_desc* pics, int n_pics
   }
   int rc = stage_batch (c, c->batch[k], c->h_pics, pics, n_pics);
   if (rc) return rc;
-  for (int i = 0; i < n_pics; i++) if (pics[i].n_coef_blocks) c->staged_coefs.push_back (std::make_pair (pics[i].coefs, c->h_pics.p[i].coefs));
+  for (int i = 0; i < n_pics; i++) if (pics[i].n_coef_blocks) c->staged_coefs.push_back (lh264_ctx::StagedPool{pics[i].coefs, c->h_pics.p[i].coefs, pics[i].n_coef_blocks});
   CK (cudaEventRecord (c->recon_staged, c->stream));
   return launch_recon (c, c->batch[k]);
 }

@@ -734,6 +734,7 @@ MD_FN CtxRec* md_slice_flip (MdStream& st, int frame_num) {
 }
 MD_FN bool md_slice_resize (MdStream& st, int mb_w, int mb_h) {
   if (st.width == mb_w && st.height == mb_h) return true;
+  if (mb_w <= 0 || mb_h <= 0) { st.error = MD_ERR_SYNTAX; return false; }   // a crafted default stream must not reach the index arithmetic below
   const int n = mb_w * mb_h;
   if (n > st.max_mbs) { st.error = MD_ERR_DIMS; return false; }
   for (int k = 0; k < 2; k++)
@@ -765,6 +766,8 @@ MD_FN int md_slice (MdStream& st, MdCtx& c, const MdSliceIn& sl, bool prior_vali
   const int slice_no = ++st.slice_counter;
   CwSlice cs = { sl.slice_type, sl.num_ref_idx_l0, sl.slice_qp, t8mode ? 1 : 0, cabac ? 1 : 0, 0 };
   if (cabac) cb_slice_begin (bw, sc, p_slice ? 1 + ((sl.flags >> 3) & 3) : 0, sl.slice_qp, sl.header_bits);
+  // first_mb_in_slice comes from an untrusted default stream: outside the picture it would index last[], tcoef[] and mb_slice[] out of bounds
+  if (W <= 0 || n_mbs <= 0 || sl.first_mb >= (uint32_t)n_mbs) { st.error = MD_ERR_SYNTAX; return 0; }
   int mb_addr = (int)sl.first_mb, mb_in_slice = 0, cached_qp = 0, last_dqp = 0, pending_skips = 0;
   bool run_known = false, stop = false;
   auto avail = [&] (int mb) -> bool { return mb >= 0 && st.mb_slice[mb] == slice_no; };

@@ -15,6 +15,7 @@ struct MStreamHost {
   int* d_order = nullptr;
   uint32_t* d_pagelist = nullptr;
   unsigned long long decisions = 0;
+  uint64_t batch_stamp = 0;        // serial number of the last batch that named this stream (duplicate check, O(n))
 };
 
 struct MBatch {                    // one batch of model pictures in HBM
@@ -43,6 +44,7 @@ struct ModelCtx {
   uint8_t** d_page_ptrs = nullptr; size_t page_ptr_cap = 0;
   unsigned int* d_next = nullptr;
   unsigned int n_pages = 0, reserved_pages = 0;
+  uint64_t batch_serial = 0;
   MBatch batch[2];                 // staging of lh264_model_submit, alternating: batch t is staged while t-1 still runs
   int batch_cur = 0;
   std::vector<MBatch*> inflight;   // launched batches whose totals the host has not read yet, oldest first (at most 2)
@@ -187,6 +189,7 @@ int lh264_model_close (lh264_ctx* c, int ms) {
 // Validates a batch and copies its records into HBM (async); fills the device picture table.
 static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_picture* pics, int n, bool share_coefs) {
   size_t tot_rec = 0, tot_sl = 0, tot_blk = 0;
+  m->batch_serial++;
   for (int i = 0; i < n; i++) {
     const lh264_model_picture& p = pics[i];
     ModelCtx* mm;
@@ -200,7 +203,8 @@ static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_
       if (sl.first_rec < 0 || sl.n_recs < 0 || sl.first_rec + sl.n_recs > p.n_recs) return fail (LH264_E_INVALID, "slice record range out of bounds");
       if (sl.slice_type != 0 && sl.slice_type != 2) return fail (LH264_E_UNSUPPORTED, "only P and I slices are modelled");
     }
-    for (int j = 0; j < i; j++) if (n <= 64 && pics[j].model_stream == p.model_stream) return fail (LH264_E_INVALID, "two pictures of one model stream in a batch");
+    if (m->streams[p.model_stream].batch_stamp == m->batch_serial) return fail (LH264_E_INVALID, "two pictures of one model stream in a batch");
+    m->streams[p.model_stream].batch_stamp = m->batch_serial;
     tot_rec += p.n_recs; tot_sl += p.n_slices; tot_blk += p.n_coef_blocks;
   }
   CK (b.recs.reserve (tot_rec)); CK (b.slices.reserve (tot_sl)); CK (b.coefs.reserve (tot_blk * 16 + 16));
@@ -218,9 +222,10 @@ static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_
     cm_rec.add (b.recs.p + o_rec, p.recs, (size_t)p.n_recs * sizeof (lh264_model_mb));
     cm_sl.add (b.slices.p + o_sl, p.slices, (size_t)p.n_slices * sizeof (lh264_model_slice));
     const int16_t* dev_coefs = nullptr;
-    if (share_coefs && p.n_coef_blocks && (size_t)i < c->staged_coefs.size() && c->staged_coefs[i].first == p.coefs) { dev_coefs = c->staged_coefs[i].second; any_shared = true; }
+    // same host pool AND same length as a picture of the preceding recon submit: it is that picture's pool, read its device copy
+    if (share_coefs && p.n_coef_blocks && (size_t)i < c->staged_coefs.size() && c->staged_coefs[i].host == p.coefs && c->staged_coefs[i].n_blocks == p.n_coef_blocks) { dev_coefs = c->staged_coefs[i].dev; any_shared = true; }
     else if (share_coefs && p.n_coef_blocks)
-      for (const auto& sc : c->staged_coefs) if (sc.first == p.coefs) { dev_coefs = sc.second; any_shared = true; break; }
+      for (const auto& sc : c->staged_coefs) if (sc.host == p.coefs && sc.n_blocks == p.n_coef_blocks) { dev_coefs = sc.dev; any_shared = true; break; }
     if (p.n_coef_blocks && !dev_coefs) cm_co.add (b.coefs.p + o_blk * 16, p.coefs, (size_t)p.n_coef_blocks * 32);
     MPicDev& d = b.h_pics.p[i];
     d.recs = b.recs.p + o_rec; d.slices = b.slices.p + o_sl; d.coefs = dev_coefs ? dev_coefs : b.coefs.p + o_blk * 16;
@@ -235,6 +240,9 @@ static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_
   if (!b.staged) CK (cudaEventCreateWithFlags (&b.staged, cudaEventDisableTiming));
   CK (cudaEventRecord (b.staged, m->stream));
   b.shares_recon_batch = any_shared ? c->batch_cur : -1;
+  // the device copies are named once: a later model submit with the same host pointers (a reused or overwritten buffer, a
+  // model-only caller) must upload its own data instead of silently coding the previous picture's
+  if (share_coefs) c->staged_coefs.clear();
   if (any_shared) CK (cudaStreamWaitEvent (m->stream, c->recon_staged, 0));      // the shared pools are in HBM
   b.n = n; b.total_recs = (int)tot_rec;
   return LH264_OK;

@@ -103,29 +103,36 @@ bool parse_sps (BitReader& br, Sps& s) {
 
 bool parse_pps (BitReader& br, Pps& p, const Sps* sps_table) {
   p = Pps();
-  p.id = br.ue();
-  p.sps_id = br.ue();
-  if (p.id < 0 || p.id > 255 || p.sps_id < 0 || p.sps_id > 31) return false;
+  const uint32_t pid = br.ue(), sid = br.ue();
+  if (pid > 255 || sid > 31) return false;
+  p.id = (int)pid; p.sps_id = (int)sid;
   p.cabac = br.u1();
   p.bottom_field_pic_order = br.u1();
-  p.num_slice_groups = br.ue() + 1;
-  if (p.num_slice_groups > 1) {
-    // slice groups (FMO) are parsed so the rest of the PPS stays aligned; decoding them is a "next" row
-    const int type = br.ue();
-    if (type == 0) for (int i = 0; i < p.num_slice_groups; i++) br.ue();
-    else if (type == 2) for (int i = 0; i < p.num_slice_groups - 1; i++) { br.ue(); br.ue(); }
-    else if (type >= 3 && type <= 5) { br.u1(); br.ue(); }
-    else if (type == 6) {
-      const int n = br.ue() + 1;
-      int bits = 0;
-      while ((1 << bits) < p.num_slice_groups) bits++;
-      for (int i = 0; i < n; i++) br.u (bits);
-    }
+  {
+    const uint32_t nsg = br.ue();                      // num_slice_groups_minus1: 0..7 (7.4.2.2; ParsePps: MAX_SLICEGROUP_IDS, au_parser.cpp:1315)
+    if (nsg > 7) return false;
+    p.num_slice_groups = (int)nsg + 1;
   }
-  p.num_ref_idx_l0_default = br.ue() + 1;
-  p.num_ref_idx_l1_default = br.ue() + 1;
+  if (p.num_slice_groups > 1) {
+    // The reference decodes slice_group_map_type 0 (interleaved) and 1 (dispersed) only and drops a parameter set with any other
+    // type (au_parser.cpp:1322-1326); the same here, which also keeps crafted type-6 maps (2^32 map units) out of the parser.
+    const uint32_t type = br.ue();
+    if (type > 1) return false;
+    p.slice_group_map_type = (int)type;
+    if (type == 0) for (int i = 0; i < p.num_slice_groups; i++) {
+        const uint32_t rl = br.ue();
+        if (rl >= (1u << 20)) return false;
+        p.run_length[i] = (int)rl + 1;
+      }
+  }
+  {
+    const uint32_t l0 = br.ue(), l1 = br.ue();         // ParsePps drops the set when either exceeds MAX_REF_PIC_COUNT = 16 (au_parser.cpp:1345-1348)
+    if (l0 > 15 || l1 > 15) return false;
+    p.num_ref_idx_l0_default = (int)l0 + 1; p.num_ref_idx_l1_default = (int)l1 + 1;
+  }
   p.weighted_pred = br.u1();
   p.weighted_bipred_idc = br.u (2);
+  if (p.weighted_bipred_idc != 0) return false;      // B-slice tool: ParsePps drops the set (au_parser.cpp:1352-1358)
   p.pic_init_qp = 26 + br.se();
   p.pic_init_qs = 26 + br.se();
   p.chroma_qp_index_offset = br.se();
@@ -150,18 +157,21 @@ bool parse_pps (BitReader& br, Pps& p, const Sps* sps_table) {
 int parse_slice_header (BitReader& br, int nal_ref_idc, int nal_type, const Sps* sps_table, const Pps* pps_table, SliceHeader& sh) {
   sh = SliceHeader();
   sh.nal_ref_idc = nal_ref_idc; sh.nal_type = nal_type; sh.idr = nal_type == NAL_IDR;
-  sh.first_mb = br.ue();
-  int st = br.ue();
+  const uint32_t first_mb = br.ue();                   // unsigned: 32 leading zero bits give 0xffffffff, which must not become -1
+  const uint32_t st = br.ue();
   if (st > 9) return -1;
   sh.slice_type = st % 5;
-  sh.pps_id = br.ue();
-  if (sh.pps_id < 0 || sh.pps_id > 255 || !pps_table[sh.pps_id].valid) return -2;
+  const uint32_t pps_id = br.ue();
+  if (pps_id > 255 || !pps_table[pps_id].valid) return -2;
+  sh.pps_id = (int)pps_id;
   const Pps& pps = pps_table[sh.pps_id];
   if (!sps_table[pps.sps_id].valid) return -2;
   const Sps& sps = sps_table[pps.sps_id];
+  if (first_mb >= (uint32_t) (sps.mb_w * sps.mb_h)) return -1;   // 7.4.3: first_mb_in_slice < PicSizeInMbs
+  sh.first_mb = (int)first_mb;
   if (sh.slice_type != SLICE_P && sh.slice_type != SLICE_I) return -3;     // B/SP/SI: not in the reference decoder either
   sh.frame_num = br.u (sps.log2_max_frame_num);
-  if (sh.idr) sh.idr_pic_id = br.ue();
+  if (sh.idr) { const uint32_t v = br.ue(); if (v > 65535) return -1; sh.idr_pic_id = (int)v; }   // 7.4.3: 0..65535
   if (sps.poc_type == 0) {
     sh.poc_lsb = br.u (sps.log2_max_poc_lsb);
     if (pps.bottom_field_pic_order) sh.delta_poc_bottom = br.se();
@@ -169,24 +179,25 @@ int parse_slice_header (BitReader& br, int nal_ref_idc, int nal_type, const Sps*
     sh.delta_poc[0] = br.se();
     if (pps.bottom_field_pic_order) sh.delta_poc[1] = br.se();
   }
-  if (pps.redundant_pic_cnt_present) sh.redundant_pic_cnt = br.ue();
+  if (pps.redundant_pic_cnt_present) { const uint32_t v = br.ue(); if (v > 127) return -1; sh.redundant_pic_cnt = (int)v; }   // 0..127
   sh.num_ref_idx_l0 = pps.num_ref_idx_l0_default;
   if (sh.slice_type == SLICE_P) {
-    if (br.u1()) sh.num_ref_idx_l0 = br.ue() + 1;     // num_ref_idx_active_override_flag
-    if (sh.num_ref_idx_l0 < 1 || sh.num_ref_idx_l0 > 32) return -1;
+    if (br.u1()) { const uint32_t v = br.ue(); if (v > 31) return -1; sh.num_ref_idx_l0 = (int)v + 1; }   // num_ref_idx_active_override_flag
+    // frame-only decoding: 7.4.3 limits num_ref_idx_l0_active_minus1 to 0..15; lh264_slice_rec carries LH264_MAX_REFS = 16 entries
+    if (sh.num_ref_idx_l0 < 1 || sh.num_ref_idx_l0 > 16) return -1;
     if (br.u1()) {                                    // ref_pic_list_modification_flag_l0
       for (;;) {
-        const int op = br.ue();
+        const uint32_t op = br.ue();
         if (op == 3) break;
         if (op > 3 || sh.mods.size() > 64) return -1;
-        sh.mods.push_back (RefPicListMod{op, br.ue()});
+        sh.mods.push_back (RefPicListMod{(int)op, br.ue()});
       }
     }
     if (pps.weighted_pred) {
       sh.has_wp = true;
-      sh.luma_log2_denom = br.ue();
-      sh.chroma_log2_denom = br.ue();
-      if ((unsigned)sh.luma_log2_denom > 7 || (unsigned)sh.chroma_log2_denom > 7) return -1;   // 7.4.3.2: 0..7
+      const uint32_t ld = br.ue(), cd = br.ue();
+      if (ld > 7 || cd > 7) return -1;                // 7.4.3.2: 0..7
+      sh.luma_log2_denom = (int)ld; sh.chroma_log2_denom = (int)cd;
       for (int i = 0; i < sh.num_ref_idx_l0; i++) {
         sh.luma_weight[i] = 1 << sh.luma_log2_denom; sh.luma_offset[i] = 0;
         for (int c = 0; c < 2; c++) { sh.chroma_weight[i][c] = 1 << sh.chroma_log2_denom; sh.chroma_offset[i][c] = 0; }
@@ -199,10 +210,10 @@ int parse_slice_header (BitReader& br, int nal_ref_idc, int nal_type, const Sps*
     if (sh.idr) { sh.no_output_of_prior_pics = br.u1(); sh.long_term_reference_flag = br.u1(); }
     else if ((sh.adaptive_marking = br.u1())) {
       for (;;) {
-        const int op = br.ue();
+        const uint32_t op = br.ue();
         if (op == 0) break;
         if (op > 6 || sh.mmcos.size() > 64) return -1;
-        Mmco m{op, 0, 0};
+        Mmco m{(int)op, 0, 0};
         if (op == 1 || op == 3) m.a = br.ue();        // difference_of_pic_nums_minus1
         if (op == 2) m.a = br.ue();                   // long_term_pic_num
         if (op == 3 || op == 6) m.b = br.ue();        // long_term_frame_idx
@@ -215,8 +226,9 @@ int parse_slice_header (BitReader& br, int nal_ref_idc, int nal_type, const Sps*
   sh.slice_qp = pps.pic_init_qp + br.se();
   if (sh.slice_qp < 0 || sh.slice_qp > 51) return -1;
   if (pps.deblocking_filter_control_present) {
-    sh.disable_deblocking_idc = br.ue();
-    if (sh.disable_deblocking_idc > 2) return -1;
+    const uint32_t idc = br.ue();
+    if (idc > 2) return -1;
+    sh.disable_deblocking_idc = (int)idc;
     if (sh.disable_deblocking_idc != 1) { sh.alpha_c0_offset = 2 * br.se(); sh.beta_offset = 2 * br.se(); }
   }
   if (pps.num_slice_groups > 1) return -4;            // FMO: "next" row N3

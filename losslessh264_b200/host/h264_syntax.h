@@ -36,7 +36,8 @@ struct Pps {
   bool valid = false;
   int id = 0, sps_id = 0;
   bool cabac = false, bottom_field_pic_order = false;
-  int num_slice_groups = 1;
+  int num_slice_groups = 1, slice_group_map_type = 0;
+  int run_length[8] = {0, 0, 0, 0, 0, 0, 0, 0};        // slice_group_map_type 0: run_length_minus1 + 1 per group
   int num_ref_idx_l0_default = 1, num_ref_idx_l1_default = 1;
   bool weighted_pred = false;
   int weighted_bipred_idc = 0;

@@ -60,14 +60,29 @@ bool expand_plan (const uint8_t* def_in, size_t n, ExpandPlan& plan) {
       literal (pos, len);
     } else if (type == NAL_SLICE || type == NAL_IDR) {
       if (plen < 2) { plan.error = "a slice was dropped at compression time (only its NAL header is in the default stream)"; return false; }
-      BitReader br (nal.data() + 1, plen - 1);
+      // The unit holds <slice header bits><stop bit (CAVLC only)><zero padding to the byte> (pip_container.cpp: unit_end) and its last
+      // two bytes are written unescaped (stop_escape).  When a CABAC header's last byte is 0x00 that byte runs into the zeros of the
+      // next start code prefix and next_unit() - the reference's own unit split, h264dec.cpp:238 - hands it to the NEXT unit
+      // (test_cif_I_CABAC_slice.264: `.. 21 00 02 00 | 00 00 01 65` is read as `.. 21 00 02 | 00 00 00 01 65`).  The header's length is
+      // known from its own syntax, so parse it over zero-extended bytes and take the missing zero bytes back from the next unit.
+      std::vector<uint8_t> ext (nal.begin(), nal.begin() + plen);
+      ext.resize (plen + 24, 0);
+      BitReader br (ext.data() + 1, plen - 1 + 8);
       SliceHeader sh;
       if (parse_slice_header (br, ref_idc, type, sps.data(), pps.data(), sh) < 0) { plan.error = "slice header does not parse"; return false; }
       const Pps& pp = pps[sh.pps_id];
       const Sps& sp = sps[pp.sps_id];
-      // the header is followed by exactly one stop bit (CAVLC; none for CABAC) and zero padding (pip_container.cpp: unit_end)
-      const uint8_t* rb = nal.data() + 1;
-      const size_t hb = sh.header_bits, rl = plen - 1;
+      const uint8_t* rb = ext.data() + 1;
+      const size_t hb = sh.header_bits;
+      size_t rl = plen - 1, missing = 0;
+      if (pp.cabac && (hb + 7) / 8 > rl) {
+        missing = (hb + 7) / 8 - rl;
+        // the bytes taken back must be zeros in front of the next start code, and a start code (00 00 01) must remain
+        size_t z = 0;
+        while (pos + len + z < n + 4 && def[pos + len + z] == 0) z++;
+        if (missing + 2 > z || def[pos + len + z] != 1) { plan.error = "slice header runs past its unit"; return false; }
+        rl += missing;
+      }
       bool ok;
       if (pp.cabac) {
         ok = (hb + 7) / 8 == rl || ((hb & 7) == 0 && hb / 8 == rl);
@@ -91,6 +106,7 @@ bool expand_plan (const uint8_t* def_in, size_t n, ExpandPlan& plan) {
       ExpandPiece p; p.def_off = pos + off; p.def_len = len - off; p.slice = (int)plan.slices.size();
       plan.pieces.push_back (p);
       plan.slices.push_back (ds);
+      pos += missing;                                   // those zero bytes are part of this slice's header, not of the next start code
     } else literal (pos, len);
     pos += len;
   }

@@ -15,11 +15,27 @@ NOT_YET = {}
 # CABAC streams decode, compress and decompress like the CAVLC ones (host CABAC parse; the model hand-off follows the reference's
 # one-macroblock skip runs and end_of_slice stop bits; the decompress core has a CABAC slice-data writer).  The set is only
 # needed where a test is about CAVLC itself (the host CAVLC writer check).
-CABAC = {"QCIF_2P_I_allIPCM.264", "test_qcif_cabac.264", "tibbycabac.264", "syn_cif_cabac_4slices_ltr_6f.264", "syn_qcif_cabac_qp38_8f.264"}
+CABAC = {"QCIF_2P_I_allIPCM.264", "test_qcif_cabac.264", "tibbycabac.264", "syn_cif_cabac_4slices_ltr_6f.264", "syn_qcif_cabac_qp38_8f.264",
+         "test_cif_I_CABAC_slice.264", "test_cif_P_CABAC_slice.264"}
+
+
+# Streams the reference itself refuses: it hands out 0 frames and a `.pip` that holds only the default stream.
+# test_scalinglist_jm: every PPS carries weighted_bipred_idc != 0 (B slices), which ParsePps rejects (au_parser.cpp), so no slice
+# finds its parameter set.  The parity requirement is "refused, 0 frames, default stream identical" - tested explicitly.
+REFUSED = {"test_scalinglist_jm.264"}
+
+# Every stream with a golden SHA1 MUST be present: a missing file is an error, not a smaller test set (round-1 verdict: three
+# corpus streams were absent and dropped out of the parametrised lists without a trace).
+_missing = sorted(f for f in SHA1 if not os.path.exists(os.path.join(STREAM_DIR, f)))
+if _missing:
+    raise RuntimeError(f"tests/golden/streams lacks {_missing}: stream_sha1.json names them, the parity corpus is incomplete")
+_unpinned = sorted(f for f in os.listdir(STREAM_DIR) if f not in SHA1)
+if _unpinned:
+    raise RuntimeError(f"tests/golden/streams holds {_unpinned} without a golden SHA1 in stream_sha1.json")
 
 
 def decodable_streams():
-    return sorted(f for f in os.listdir(STREAM_DIR) if f in SHA1 and f not in NOT_YET)
+    return sorted(f for f in SHA1 if f not in NOT_YET and f not in REFUSED)
 
 
 def cavlc_streams():

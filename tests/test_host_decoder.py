@@ -63,3 +63,22 @@ def test_damaged_stream_freezes_output_like_the_reference(tmp_path):
     concealment modes) hands out exactly one picture, the complete 640x480 IDR; so does the host decoder."""
     sha, n = decode_with_oracle(os.path.join(STREAM_DIR, "Error_I_P.264"), str(tmp_path))
     assert n == 1 and sha == SHA1["Error_I_P.264"]["sha1"]
+
+
+def test_stream_the_reference_refuses_is_refused_with_the_same_default_stream(tmp_path):
+    """test_scalinglist_jm.264: every PPS carries weighted_bipred_idc != 0, which the reference's ParsePps rejects, so no slice finds
+    its parameter set: the reference hands out 0 frames and writes a `.pip` holding only the default stream.
+    The host decoder must refuse the same way: 0 pictures, no side streams, byte-identical default stream."""
+    import json
+
+    from streams import REFUSED
+
+    gold = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "pip_tag_sha1.json")))
+    for name in sorted(REFUSED):
+        d = str(tmp_path)
+        pip = os.path.join(d, "o.pip")
+        r = subprocess.run([TOOL, os.path.join(STREAM_DIR, name), os.path.join(d, "o.lhfb"), "1", os.path.join(d, "o.lhmd"), pip], capture_output=True, text=True)
+        assert re.search(r"pictures 0 ", r.stderr), r.stderr[-300:]
+        assert os.path.getsize(os.path.join(d, "o.lhfb")) == 0 and os.path.getsize(os.path.join(d, "o.lhmd")) == 0
+        assert SHA1[name]["frames"] == 0 and gold[name]["tags"] == {}
+        assert hashlib.sha1(open(pip, "rb").read()).hexdigest() == gold[name]["default"]["sha1"], f"{name}: default stream differs from the reference's"
