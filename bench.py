@@ -338,10 +338,10 @@ def main():
     d0 = ctx.model_decisions(mstreams[0])
     ctx.kernel_ms(-1)                                   # reset + enable per-family event timing
     resident_steps(n_frames)
-    fam = [ctx.kernel_ms(i) for i in (0, 2, 4, 5)]
+    fam = [ctx.kernel_ms(i) for i in (0, 4, 5)]
     ctx.kernel_ms(-2)
     dec_seq = ctx.model_decisions(mstreams[0]) - d0     # decisions of one pass over the sequence, per stream
-    fam_names = ["k_recon_rows", "k_deblock_rows", "k_model_frame+count+scan+emit", "k_model_code"]
+    fam_names = ["k_decode_rows", "k_model_frame+count+scan+emit", "k_model_code"]
     dom = int(np.argmax(fam))
     n_p = sum(1 for p in pics if int(p.slices["slice_type"][0]) == 0)
     peak, peak_kind = measured_peak()
@@ -352,20 +352,22 @@ def main():
     #   k_deblock_rows picture read + write + MB metadata (128 B / MB)
     #   model gen      MB record + coefficients (896 B) + three neighbour context records (SURVEY 8d charges 3 x 896)
     #   k_model_code   24 B per decision (one DynProb read + write at the reference's 12 B) + output bytes
-    share = [S * (n_p * PIC_BYTES + n_frames * (PIC_BYTES + MB_PER_PIC * 896)), S * n_frames * (2 * PIC_BYTES + MB_PER_PIC * 128),
+    #   k_decode_rows  = the two above (SURVEY 8d counts reconstruction and deblocking as separate passes; the fused kernel does
+    #                  the work of both and is charged their algorithmic bytes: 4P per P picture + 1024 B per macroblock)
+    share = [S * (n_p * PIC_BYTES + n_frames * (PIC_BYTES + MB_PER_PIC * 896)) + S * n_frames * (2 * PIC_BYTES + MB_PER_PIC * 128),
              S * n_rec_seq * 3584, S * (dec_seq * 24 + pip_bytes_seq)]
-    ach = [share[i] / (fam[i] / 1000.0) / 1e9 if fam[i] > 0 else 0.0 for i in range(4)]
+    ach = [share[i] / (fam[i] / 1000.0) / 1e9 if fam[i] > 0 else 0.0 for i in range(3)]
     ach_all = sum(share) / (sum(fam) / 1000.0) / 1e9
     # DRAM traffic of one launch (dram__bytes_read.sum + dram__bytes_write.sum, `ncu --set full`, captures summarised in profiles/):
     # measured per P picture at S = 256 and scaled to this run's pictures per launch
-    traffic_per_picture = {"k_recon_rows": 8.35e6, "k_deblock_rows": None, "k_model_frame+count+scan+emit": None, "k_model_code": 3.05e6}
+    traffic_per_picture = {"k_decode_rows": None, "k_model_frame+count+scan+emit": None, "k_model_code": 3.05e6}
     tpp = traffic_per_picture[fam_names[dom]]
     roofline = {"bound": "hbm", "kernel": fam_names[dom], "achieved": round(ach[dom], 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                 "frac": round(ach[dom] / peak, 4), "traffic": int(tpp * S) if tpp else None,
                 "traffic_note": "bytes per launch = ncu dram read+write per P picture (profiles/r1_summary.md) x pictures per launch" if tpp else None,
                 "whole_step": {"achieved": round(ach_all, 1), "frac": round(ach_all / peak, 4)},
                 "families": {n: {"ms_per_16_steps": round(t, 3), "achieved": round(a, 1), "frac": round(a / peak, 4)} for n, t, a in zip(fam_names, fam, ach)},
-                "model_decisions_per_s": round(S * dec_seq / (fam[3] / 1000.0)) if fam[3] > 0 else None}
+                "model_decisions_per_s": round(S * dec_seq / (fam[2] / 1000.0)) if fam[2] > 0 else None}
 
     # ---- e2e: pinned host records in, decoded pictures back to pinned host memory -------------------------------------
     # T host threads, each with its own context (CUDA streams) and Se streams, as a host application with one worker per

@@ -193,7 +193,7 @@ void lh264_batch_free(lh264_ctx* ctx, lh264_resident_batch* batch);
 /* number of kernel launches issued by this context so far                                   */
 uint64_t lh264_kernel_launches(const lh264_ctx* ctx);
 /* accumulated device time (ms, CUDA events on the context stream) of one kernel family
- * since the last reset: 0 k_recon_rows (inter + intra), 1 unused, 2 k_deblock_rows, 3 all reconstruction, 4 model generation
+ * since the last reset: 0 k_decode_rows (reconstruction + deblocking, one fused kernel), 1-2 unused (0), 3 = 0, 4 model generation
  * kernels (k_model_frame/count/scan/emit), 5 k_model_code, 6 k_model_decode; family = -1 resets and switches the
  * (synchronising) per-family timing on, family = -2 switches it off                          */
 float lh264_kernel_ms(lh264_ctx* ctx, int family);

@@ -16,6 +16,7 @@
 
 #include "recon_kernels.cuh"
 #include "recon_rows.cuh"
+#include "decode_rows.cuh"
 #include "model_kernels.cuh"
 
 using namespace lh264;
@@ -35,6 +36,7 @@ struct StreamRec {
   int mb_w = 0, mb_h = 0, n_slots = 0;
   uint8_t* base = nullptr;
   size_t slot_stride = 0;
+  uint8_t* lines = nullptr;                  // unfiltered bottom rows, one line set per MB row (decode_rows.cuh)
 };
 
 template <typename T> struct DevBuf {       // grow-only device buffer
@@ -71,7 +73,7 @@ struct BatchDev {                            // device-resident batch
   DevBuf<int16_t> coefs;
   DevBuf<lh264_slice_rec> slices;
   DevBuf<PicDev> pics;
-  DevBuf<int> row_sync;                      // RowSync header + progress[2][n_pics][max_rows]
+  DevBuf<int> row_sync;                      // DecodeSync header + progress[n_pics][max_rows]
   int n_pics = 0, max_rows = 0;
   void release() { mbs.release(); coefs.release(); slices.release(); pics.release(); row_sync.release(); }
 };
@@ -81,7 +83,8 @@ struct BatchDev {                            // device-resident batch
 struct lh264_resident_batch { BatchDev dev; };
 
 struct lh264_ctx {
-  int device = 0, n_sm = 148, occ_recon = 2, occ_deblock = 4;
+  int device = 0, n_sm = 148, occ_recon = 2;
+  unsigned int* d_error = nullptr;           // records that failed validation on the device (sticky until lh264_sync reports it)
   cudaStream_t stream = nullptr;
   bool own_stream = false;
   std::vector<StreamRec> streams;
@@ -141,10 +144,10 @@ int lh264_ctx_create (lh264_ctx** out, int device, void* cuda_stream) {
   if (!c) return fail (LH264_E_NOMEM, "out of host memory");
   c->device = device;
   cudaDeviceGetAttribute (&c->n_sm, cudaDevAttrMultiProcessorCount, device);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor (&c->occ_recon, k_recon_rows, ROWS_WARPS * 32, 0);
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor (&c->occ_deblock, k_deblock_rows, ROWS_WARPS * 32, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor (&c->occ_recon, k_decode_rows, ROWS_WARPS * 32, 0);
   if (c->occ_recon < 1) c->occ_recon = 1;
-  if (c->occ_deblock < 1) c->occ_deblock = 1;
+  CK (cudaMalloc (&c->d_error, sizeof (unsigned int)));
+  CK (cudaMemset (c->d_error, 0, sizeof (unsigned int)));
   if (cuda_stream) c->stream = (cudaStream_t)cuda_stream;
   else { CK (cudaStreamCreateWithFlags (&c->stream, cudaStreamNonBlocking)); c->own_stream = true; }
   CK (cudaEventCreateWithFlags (&c->staged, cudaEventDisableTiming));
@@ -164,7 +167,8 @@ void lh264_ctx_destroy (lh264_ctx* c) {
   cudaStreamSynchronize (c->stream);
   model_destroy (c);
   decode_destroy (c);
-  for (auto& s : c->streams) if (s.base) cudaFree (s.base);
+  for (auto& s : c->streams) { if (s.base) cudaFree (s.base); if (s.lines) cudaFree (s.lines); }
+  if (c->d_error) cudaFree (c->d_error);
   c->batch[0].release(); c->batch[1].release(); c->h_pics.release();
   for (int i = 0; i < 2; i++) if (c->batch_free[i]) cudaEventDestroy (c->batch_free[i]);
   c->pack_jobs.release(); c->h_pack_jobs.release(); c->pack_out.release();
@@ -185,8 +189,10 @@ int lh264_stream_open (lh264_ctx* c, int mb_w, int mb_h, int n_slots) {
   StreamRec s;
   s.open = true; s.mb_w = mb_w; s.mb_h = mb_h; s.n_slots = n_slots;
   s.slot_stride = (size_t)mb_w * mb_h * 384;
-  CK (cudaMalloc (&s.base, s.slot_stride * n_slots));
-  CK (cudaMemsetAsync (s.base, 128, s.slot_stride * n_slots, c->stream));   // pic_queue.cpp:96
+  // + 64: the aligned word loads of the reconstruction kernel may touch up to 3 bytes past the last row of the last plane
+  CK (cudaMalloc (&s.base, s.slot_stride * n_slots + 64));
+  CK (cudaMemsetAsync (s.base, 128, s.slot_stride * n_slots + 64, c->stream));   // pic_queue.cpp:96
+  if (cudaMalloc (&s.lines, (size_t)mb_h * 2 * mb_w * 16) != cudaSuccess) { cudaFree (s.base); return fail (LH264_E_NOMEM, "out of device memory (line buffer)"); }
   for (size_t i = 0; i < c->streams.size(); i++) if (!c->streams[i].open) { c->streams[i] = s; return (int)i; }
   c->streams.push_back (s);
   return (int)c->streams.size() - 1;
@@ -196,6 +202,7 @@ int lh264_stream_close (lh264_ctx* c, int stream) {
   if (!c || stream < 0 || stream >= (int)c->streams.size() || !c->streams[stream].open) return fail (LH264_E_INVALID, "bad stream");
   CK (cudaStreamSynchronize (c->stream));
   cudaFree (c->streams[stream].base);
+  if (c->streams[stream].lines) cudaFree (c->streams[stream].lines);
   c->streams[stream] = StreamRec();
   return LH264_OK;
 }
@@ -251,6 +258,7 @@ static int stage_batch (lh264_ctx* c, BatchDev& b, PinBuf<PicDev>& h_pics, const
     PicDev& d = h_pics.p[i];
     d.mbs = b.mbs.p + o_mb; d.coefs = b.coefs.p + o_blk * 16; d.slices = b.slices.p + o_sl;
     d.base = s.base; d.slot_stride = s.slot_stride; d.cur_slot = p.cur_slot; d.n_slots = s.n_slots; d.mb_w = s.mb_w; d.mb_h = s.mb_h;
+    d.lines = s.lines; d.n_slices = p.n_slices; d.n_coef_blocks = p.n_coef_blocks;
     b.max_rows = std::max (b.max_rows, s.mb_h);
     o_mb += nmb; o_blk += p.n_coef_blocks; o_sl += p.n_slices;
   }
@@ -259,28 +267,24 @@ static int stage_batch (lh264_ctx* c, BatchDev& b, PinBuf<PicDev>& h_pics, const
   CK (cudaMemcpyAsync (b.pics.p, h_pics.p, n * sizeof (PicDev), cudaMemcpyHostToDevice, c->stream));
   CK (cudaEventRecord (c->staged, c->stream));
   c->staged_pending = true;
-  CK (b.row_sync.reserve (4 + 2 * (size_t)n * b.max_rows));
+  CK (b.row_sync.reserve (4 + (size_t)n * b.max_rows));
   return LH264_OK;
 }
 
 static int launch_recon (lh264_ctx* c, BatchDev& b) {
   if (b.n_pics == 0) return LH264_OK;
-  // persistent row kernels: enough warps to fill the machine, never more than there are rows
-  const size_t sync_bytes = (4 + 2 * (size_t)b.n_pics * b.max_rows) * sizeof (int);
+  // one persistent launch: enough warps to fill the machine, never more than there are rows
+  const size_t sync_bytes = (4 + (size_t)b.n_pics * b.max_rows) * sizeof (int);
   const long long rows = (long long)b.n_pics * b.max_rows;
   const int blocks = (int)std::max (1LL, std::min ((long long)c->n_sm * c->occ_recon, (rows + ROWS_WARPS - 1) / ROWS_WARPS));
-  const int dblocks = (int)std::max (1LL, std::min ((long long)c->n_sm * c->occ_deblock, (rows + ROWS_WARPS - 1) / ROWS_WARPS));
   if (c->timing) CK (cudaEventRecord (c->ev[0], c->stream));
   CK (cudaMemsetAsync (b.row_sync.p, 0, sync_bytes, c->stream));
-  k_recon_rows<<<blocks, ROWS_WARPS * 32, 0, c->stream>>> (b.pics.p, b.n_pics, b.max_rows, reinterpret_cast<RowSync*> (b.row_sync.p));
-  c->launches++;
-  if (c->timing) { CK (cudaEventRecord (c->ev[1], c->stream)); CK (cudaEventRecord (c->ev[2], c->stream)); }
-  k_deblock_rows<<<dblocks, ROWS_WARPS * 32, 0, c->stream>>> (b.pics.p, b.n_pics, b.max_rows, reinterpret_cast<RowSync*> (b.row_sync.p));
+  k_decode_rows<<<blocks, ROWS_WARPS * 32, 0, c->stream>>> (b.pics.p, b.n_pics, b.max_rows, reinterpret_cast<DecodeSync*> (b.row_sync.p), c->d_error);
   c->launches++;
   if (c->timing) {
-    CK (cudaEventRecord (c->ev[3], c->stream));
-    CK (cudaEventSynchronize (c->ev[3]));
-    for (int i = 0; i < 3; i++) { float t = 0; cudaEventElapsedTime (&t, c->ev[i], c->ev[i + 1]); c->ms[i] += t; }
+    CK (cudaEventRecord (c->ev[1], c->stream));
+    CK (cudaEventSynchronize (c->ev[1]));
+    float t = 0; cudaEventElapsedTime (&t, c->ev[0], c->ev[1]); c->ms[0] += t;
   }
   CK (cudaGetLastError());
   return LH264_OK;
@@ -473,9 +477,15 @@ int lh264_sync (lh264_ctx* c) {
   if (!c) return fail (LH264_E_INVALID, "null ctx");
   CK (cudaSetDevice (c->device));
   CK (model_sync (c));
+  unsigned int bad = 0;
+  CK (cudaMemcpyAsync (&bad, c->d_error, sizeof (bad), cudaMemcpyDeviceToHost, c->stream));
   CK (cudaStreamSynchronize (c->stream));
   CK (cudaStreamSynchronize (c->d2h_stream));
   c->staged_pending = false;
+  if (bad) {
+    CK (cudaMemsetAsync (c->d_error, 0, sizeof (bad), c->stream));
+    return fail (LH264_E_INVALID, "malformed macroblock record(s) in a submitted picture (slice_idx, coded_mask / coef_off or mb_type out of range): those macroblocks were left untouched");
+  }
   return LH264_OK;
 }
 

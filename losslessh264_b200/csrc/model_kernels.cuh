@@ -29,7 +29,13 @@
 // dense table, inc/macroblock_model.h:36-136, restricted to the index ranges that can occur; a fresh
 // DynProb is all zero bits), two frames of 32-byte context records, 32 coder states and paged output.
 #pragma once
+#ifndef LH264_CPU_EMU          // tests/emu compiles these sources with g++ behind a CUDA-model shim (test infrastructure)
 #include <cuda_runtime.h>
+#define LH264_SPIN_HINT()
+#define LH264_DYN_SHARED(name) extern __shared__ __align__ (16) unsigned char name[]
+#else
+#define LH264_DYN_SHARED(name) unsigned char* name = emu::dyn_shared()
+#endif
 #include <stdint.h>
 #include "../../include/lh264_b200.h"
 #include "model_layout.h"
@@ -496,7 +502,7 @@ __device__ __forceinline__ void t_load_ctx (CtxRecS& dst, const CtxRec* src) {
 }
 
 __global__ void __launch_bounds__ (GEN_THREADS) k_model_count (const MPicDev* pics, int n_pics, int total_recs, const unsigned int* poison) {
-  extern __shared__ __align__ (16) unsigned char gen_smem[];
+  LH264_DYN_SHARED (gen_smem);
   if (*poison) return;
   ThreadMb* tm = reinterpret_cast<ThreadMb*> (gen_smem);
   ThreadMb& t = tm[threadIdx.x];
@@ -623,7 +629,7 @@ __global__ void __launch_bounds__ (1024) k_model_plan (int n_pics, const uint32_
 }
 
 __global__ void __launch_bounds__ (GEN_THREADS) k_model_emit (const MPicDev* pics, int n_pics, int total_recs, uint32_t* dec, const unsigned long long* dec_base, const BatchCtl* ctl) {
-  extern __shared__ __align__ (16) unsigned char gen_smem[];
+  LH264_DYN_SHARED (gen_smem);
   if (ctl->skip) return;
   ThreadMb* tm = reinterpret_cast<ThreadMb*> (gen_smem);
   ThreadMb& t = tm[threadIdx.x];
@@ -768,8 +774,19 @@ __global__ void __launch_bounds__ (64) k_model_code (const MPicDev* pics, int n_
       const uint32_t idx = w >> 6, tag = valid ? (w >> 1) & 31u : 31u, bit = w & 1u;
       const unsigned peers = __match_any_sync (0xffffffffu, idx);
       const unsigned bits = __ballot_sync (0xffffffffu, bit);
+      // Earlier decisions of this chunk on the same prior, in decision order.  Until the counts are halved (their sum passes 512)
+      // an update only increments one of them and recomputes the probability from the new counts, so a run of updates equals
+      // ONE update applied to counts advanced by the run's zeros and ones (minus its last decision): hot priors, which can
+      // occupy most lanes of a chunk, cost two updates per lane instead of one per predecessor.
       unsigned m = peers & lt;
-      while (m) { const int j = __ffs (m) - 1; m &= m - 1; sv = dp_update (sv, (bits >> j) & 1u); }
+      if (m) {
+        const int jl = 31 - __clz (m);
+        const unsigned head = m & ~(1u << jl);
+        const uint32_t ones = (uint32_t)__popc (head & bits), zeros = (uint32_t)__popc (head) - ones;
+        const uint32_t c0 = sv & 0x3ffu, c1 = (sv >> 10) & 0x3ffu;
+        if (c0 + c1 + zeros + ones <= 512u) sv = dp_update ((sv & 0xff000000u) | (c0 + zeros) | ((c1 + ones) << 10), (bits >> jl) & 1u);
+        else while (m) { const int j = __ffs (m) - 1; m &= m - 1; sv = dp_update (sv, (bits >> j) & 1u); }
+      }
       const uint32_t prob = dp_prob (sv);
       sv = dp_update (sv, bit);
       if (valid && (peers >> lane) <= 1u) priors[idx] = sv;      // the last decision of the chain stores
@@ -779,7 +796,7 @@ __global__ void __launch_bounds__ (64) k_model_code (const MPicDev* pics, int n_
       const unsigned tpeers = __match_any_sync (0xffffffffu, tag);
       if (valid) {
         const uint32_t pos = sh.prod[tag] + (uint32_t)__popc (tpeers & lt);
-        while (pos - sh.cons[tag] >= (uint32_t)CODE_RING) { }
+        while (pos - sh.cons[tag] >= (uint32_t)CODE_RING) { LH264_SPIN_HINT(); }
         sh.ring[tag][pos & (CODE_RING - 1)] = (uint16_t) ((prob << 1) | bit);
       }
       __threadfence_block();

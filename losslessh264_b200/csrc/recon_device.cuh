@@ -6,7 +6,9 @@
 // thread per coefficient block for dequant+IDCT, warp-lane-per-line deblocking.
 #pragma once
 #include <stdint.h>
+#ifndef LH264_CPU_EMU          // tests/emu compiles these sources with g++ behind a CUDA-model shim (test infrastructure)
 #include <cuda_runtime.h>
+#endif
 #include "../../include/lh264_b200.h"
 
 namespace lh264 {

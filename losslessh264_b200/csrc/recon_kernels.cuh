@@ -16,6 +16,8 @@ struct PicDev {
   uint8_t* base;                  // picture pool of the stream
   unsigned long long slot_stride; // bytes per picture slot
   int cur_slot, n_slots, mb_w, mb_h;
+  uint8_t* lines;                 // per-stream line buffer: unfiltered bottom row of every MB row (mb_h x 2 x mb_w*16 bytes), decode_rows.cuh
+  int n_slices, n_coef_blocks;    // bounds of `slices` / `coefs`, for record validation on the device
 };
 
 __device__ __forceinline__ uint8_t* plane_ptr (const PicDev& p, int slot, int plane) {

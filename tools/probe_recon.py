@@ -16,4 +16,4 @@ for b in bs: ctx.recon_resident(b)
 ctx.sync()
 ctx.kernel_ms(-1)
 for b in bs[1:]: ctx.recon_resident(b)
-print(f"S={S} 5 P pictures: recon {ctx.kernel_ms(0):.2f} ms deblock {ctx.kernel_ms(2):.2f} ms")
+print(f"S={S} 5 P pictures: k_decode_rows (reconstruction + deblocking) {ctx.kernel_ms(0):.2f} ms")
