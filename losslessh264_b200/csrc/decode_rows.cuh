@@ -29,6 +29,12 @@
 #pragma once
 #include "recon_rows.cuh"
 
+#ifdef LH264_CPU_EMU
+#define LH264_NOINLINE __attribute__ ((noinline))
+#else
+#define LH264_NOINLINE __noinline__
+#endif
+
 namespace lh264 {
 
 #define RY 36                 // row stride of the luma tile array: prev MB at columns 0..15, cur MB at 16..31, 4 bytes of padding
@@ -41,6 +47,9 @@ struct __align__ (16) RowCtx : WarpCtx {
   __align__ (4) uint8_t ry[(RY_TOP + 16) * RY];
   __align__ (4) uint8_t rc[2][(RC_TOP + 8) * RC];
   __align__ (4) uint8_t ucol[32];               // unfiltered right column of the previous MB: luma 16, Cb 8, Cr 8
+  // what the hot path reads of the current slice's record, refreshed when slice_idx changes (most pictures: once per row)
+  int16_t sl_slot[LH264_MAX_REFS];              // picture slot of RefPicList0[i], clamped to the stream's pool
+  uint8_t sl_wp, sl_idc; int8_t sl_aoff, sl_boff;
 };
 
 struct DecodeSync {          // device-resident, zeroed before every batch
@@ -92,25 +101,40 @@ __device__ __forceinline__ void w_residual_direct (RowCtx& s, const int16_t* coe
   const int dc2 = __shfl_sync (0xffffffffu, dc_own, cb + 2), dc3 = __shfl_sync (0xffffffffu, dc_own, cb + 3);
   if (lane >= 24) return;
   const uint32_t w[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+  // A block whose only non-zero coefficient is the DC one transforms to a constant: with c[1..15] = 0 both passes of
+  // IdctResAddPred_c reduce to (32 + c[0]) >> 6 for all sixteen residuals (most blocks of a typical inter picture).
+  const bool ac_zero = ((w[0] & 0xffff0000u) | w[1] | w[2] | w[3] | w[4] | w[5] | w[6] | w[7]) == 0;
   int c[16];
+  int16_t* dst; int stride;
   if (lane < 16) {
     if (!present) return;
     const int qp = s.mb.qp_y;
+    dst = s.res + blk_y (lane) * 16 + blk_x (lane); stride = 16;
+    c[0] = S16 (dc_own * dq4 (qp, 0));
+    if (!ac_zero) {
 #pragma unroll
-    for (int j = 0; j < 16; j++) c[j] = S16 ((int) (int16_t) (w[j >> 1] >> ((j & 1) * 16)) * dq4 (qp, j));
-    idct4x4_res (c, s.res + blk_y (lane) * 16 + blk_x (lane), 16);
+      for (int j = 1; j < 16; j++) c[j] = S16 ((int) (int16_t) (w[j >> 1] >> ((j & 1) * 16)) * dq4 (qp, j));
+    }
   } else {
     const int p = (lane - 16) >> 2, b = (lane - 16) & 3;
     if (((mask >> (16 + 4 * p)) & 15u) == 0) return;
     const int qp = s.mb.qp_c[p];
-#pragma unroll
-    for (int j = 1; j < 16; j++) c[j] = S16 ((int) (int16_t) (w[j >> 1] >> ((j & 1) * 16)) * dq4 (qp, j));
+    dst = s.res + 256 + 64 * p + (b >> 1) * 32 + (b & 1) * 4; stride = 8;
     const int q0 = dq4 (qp, 0);
     int a = S16 (dc0 * q0), bb = S16 (dc1 * q0), cc = S16 (dc2 * q0), d = S16 (dc3 * q0);
     const int e = a - bb; a += bb; bb = cc - d; cc += d;
     c[0] = S16 (b == 0 ? (a + cc) >> 1 : (b == 1 ? (e + bb) >> 1 : (b == 2 ? (a - cc) >> 1 : (e - bb) >> 1)));
-    idct4x4_res (c, s.res + 256 + 64 * p + (b >> 1) * 32 + (b & 1) * 4, 8);
+    if (!ac_zero) {
+#pragma unroll
+      for (int j = 1; j < 16; j++) c[j] = S16 ((int) (int16_t) (w[j >> 1] >> ((j & 1) * 16)) * dq4 (qp, j));
+    }
   }
+  if (ac_zero) {
+    const uint32_t v = (uint32_t) (uint16_t) (int16_t) ((32 + c[0]) >> 6);
+    const uint2 vv = make_uint2 (v | (v << 16), v | (v << 16));
+#pragma unroll
+    for (int y = 0; y < 4; y++) *reinterpret_cast<uint2*> (dst + y * stride) = vv;
+  } else idct4x4_res (c, dst, stride);
 }
 
 // ---- commit of the unfiltered macroblock into the "cur" tile ----------------------------------------------------------------
@@ -145,8 +169,8 @@ __device__ __forceinline__ void commit_from_pred (RowCtx& s, int lane, bool add_
 
 // ---- P_L0_16x16 / P_Skip fast path ---------------------------------------------------------------------------------------------
 // Returns false (nothing done) when the macroblock needs the general routine.
-__device__ __forceinline__ bool w_inter16_fast (RowCtx& s, const PicDev& pic, const lh264_slice_rec* sl, int mbx, int mby, int lane) {
-  if (__ldg (&sl->weighted_pred)) return false;
+__device__ __forceinline__ bool w_inter16_fast (RowCtx& s, const PicDev& pic, int mbx, int mby, int lane) {
+  if (s.sl_wp) return false;
   const int W = pic.mb_w * 16, H = pic.mb_h * 16, CW = W >> 1, CH = H >> 1;
   // BaseMC: the motion vector is clamped into the 32-pixel border (rec_mb.cpp:251-252); rows are clamped at read below
   const int fx = clip3i (((mbx * 16) << 2) + s.mb.mv[0][0], (-32 + 2) * 4, (W + 32 - 19) << 2);
@@ -155,8 +179,7 @@ __device__ __forceinline__ bool w_inter16_fast (RowCtx& s, const PicDev& pic, co
   const bool frac = ((fx | fy) & 3) != 0;
   if (cx < 0 || cx + 8 + (dx != 0) > CW) return false;
   if (frac ? (x0 - 2 < 0 || x0 + 19 > W) : (x0 < 0 || x0 + 16 > W)) return false;
-  const int refidx = s.mb.ref_idx[0] & 15;
-  const int slot = clip3i (__ldg (&sl->ref_slot[refidx]), 0, pic.n_slots - 1);
+  const int slot = s.sl_slot[s.mb.ref_idx[0] & 15];
   const uint8_t* ref = plane_ptr (pic, slot, 0);
   const int r = lane >> 1, h = lane & 1;
   // ---- issue every global load first ----
@@ -234,7 +257,7 @@ __device__ __forceinline__ bool w_inter16_fast (RowCtx& s, const PicDev& pic, co
 }
 
 // ---- inter macroblock, general routine: partitions / weighting / border windows (recon_rows.cuh) -----------------------------
-__device__ void w_inter_general (RowCtx& s, const PicDev& pic, const lh264_slice_rec* sl, int mbx, int mby, int lane) {
+__device__ LH264_NOINLINE void w_inter_general (RowCtx& s, const PicDev& pic, const lh264_slice_rec* sl, int mbx, int mby, int lane) {
   const int t = s.mb.mb_type;
   const bool has_res = s.mb.cbp != 0;
   uint32_t lv[6];
@@ -273,7 +296,7 @@ __device__ void w_inter_general (RowCtx& s, const PicDev& pic, const lh264_slice
 // column from s.ucol, the row above (and the corner) from the line buffer of row y - 1.
 #define F3(a, b, c) (((a) + 2 * (b) + (c) + 2) >> 2)
 #define F2(a, b) (((a) + (b) + 1) >> 1)
-__device__ void w_intra_row (RowCtx& s, const PicDev& pic, int mbx, int mby, int lane) {
+__device__ LH264_NOINLINE void w_intra_row (RowCtx& s, const PicDev& pic, int mbx, int mby, int lane) {
   uint8_t* tile = s.tile;
   const int mb_type = s.mb.mb_type;
   const int W = pic.mb_w * 16, CW = W >> 1;
@@ -399,14 +422,51 @@ __device__ void w_intra_row (RowCtx& s, const PicDev& pic, int mbx, int mby, int
 // WelsDeblockingMb (deblocking.cpp:815-870), bS derivation (:160-353), FilteringEdge* and DeblockLuma/Chroma{Lt4,Eq4}_c
 // (deblocking_common.cpp:5-246).  Samples: s.ry / s.rc (prev | cur, rows of the macroblock above on top of cur).
 // Returns true when the top edge was filtered (the rows above must be written back).
-__device__ bool w_deblock_tile (RowCtx& s, const PicDev& pic, int mbx, int mby, int lane) {
+// One line across an edge, luma and chroma in ONE instruction stream (the chroma lanes of the warp run the same code with
+// `chroma` set instead of a divergent second routine): DeblockLumaLt4_c / DeblockLumaEq4_c / DeblockChromaLt4_c /
+// DeblockChromaEq4_c, deblocking_common.cpp:5-246.
+__device__ __forceinline__ void edge_line (uint8_t* p, int sx, int bS, int ia, int alpha, int beta, bool chroma) {
+  const int p0 = p[-sx], p1 = p[-2 * sx], q0 = p[0], q1 = p[sx];
+  const int d = abs (p0 - q0);
+  if (! (d < alpha && abs (p1 - p0) < beta && abs (q1 - q0) < beta)) return;
+  if (bS == 4) {
+    if (chroma || d >= ((alpha >> 2) + 2)) {
+      p[-sx] = (uint8_t) ((2 * p1 + p0 + q1 + 2) >> 2); p[0] = (uint8_t) ((2 * q1 + q0 + p1 + 2) >> 2);
+      return;
+    }
+    const int p2 = p[-3 * sx], q2 = p[2 * sx];
+    if (abs (p2 - p0) < beta) {
+      const int p3 = p[-4 * sx];
+      p[-sx] = (uint8_t) ((p2 + 2 * p1 + 2 * p0 + 2 * q0 + q1 + 4) >> 3);
+      p[-2 * sx] = (uint8_t) ((p2 + p1 + p0 + q0 + 2) >> 2);
+      p[-3 * sx] = (uint8_t) ((2 * p3 + 3 * p2 + p1 + p0 + q0 + 4) >> 3);
+    } else p[-sx] = (uint8_t) ((2 * p1 + p0 + q1 + 2) >> 2);
+    if (abs (q2 - q0) < beta) {
+      const int q3 = p[3 * sx];
+      p[0] = (uint8_t) ((p1 + 2 * p0 + 2 * q0 + 2 * q1 + q2 + 4) >> 3);
+      p[sx] = (uint8_t) ((p0 + q0 + q1 + q2 + 2) >> 2);
+      p[2 * sx] = (uint8_t) ((2 * q3 + 3 * q2 + q1 + q0 + p0 + 4) >> 3);
+    } else p[0] = (uint8_t) ((2 * q1 + q0 + p1 + 2) >> 2);
+    return;
+  }
+  const int tc0 = c_tc0[ia][bS];
+  int tc = tc0 + (chroma ? 1 : 0);
+  if (!chroma) {
+    const int p2 = p[-3 * sx], q2 = p[2 * sx];
+    if (abs (p2 - p0) < beta) { p[-2 * sx] = (uint8_t) (p1 + clip3i ((p2 + ((p0 + q0 + 1) >> 1) - (p1 << 1)) >> 1, -tc0, tc0)); tc++; }
+    if (abs (q2 - q0) < beta) { p[sx] = (uint8_t) (q1 + clip3i ((q2 + ((p0 + q0 + 1) >> 1) - (q1 << 1)) >> 1, -tc0, tc0)); tc++; }
+  }
+  const int dl = clip3i ((((q0 - p0) << 2) + (p1 - q1) + 4) >> 3, -tc, tc);
+  p[-sx] = (uint8_t)clip255 (p0 + dl); p[0] = (uint8_t)clip255 (q0 - dl);
+}
+
+__device__ __forceinline__ bool w_deblock_tile (RowCtx& s, int mbx, int mby, int lane) {
   const lh264_mb_rec* m = &s.mb; const lh264_mb_rec* ml = &s.left; const lh264_mb_rec* mt = &s.top;
   const int mb_type = m->mb_type;
   if (mb_type == LH264_MB_NONE) return false;
-  const lh264_slice_rec* sl = pic.slices + m->slice_idx;
-  const int idc = __ldg (&sl->disable_deblocking_idc);
+  const int idc = s.sl_idc;
   if (idc == 1) return false;
-  const int aoff = __ldg (&sl->alpha_c0_offset), boff = __ldg (&sl->beta_offset);
+  const int aoff = s.sl_aoff, boff = s.sl_boff;
   bool left = mbx > 0, top = mby > 0;               // DeblockingAvailableNoInterlayer, deblocking.cpp:354-369
   if (idc == 2) { left = left && ml->slice_idx == m->slice_idx; top = top && mt->slice_idx == m->slice_idx; }
   const bool t8 = m->flags & LH264_MBF_TRANSFORM8x8;
@@ -441,44 +501,37 @@ __device__ bool w_deblock_tile (RowCtx& s, const PicDev& pic, int mbx, int mby, 
   }
   if (!left && dir == 0 && e == 0) bs = 0;
   if (!top && dir == 1 && e == 0) bs = 0;
-  if (__ballot_sync (0xffffffffu, bs != 0) == 0) return false;     // nothing to filter in this MB
-
-  const int qp_cur = m->qp_y;
-  const int cplane = (lane - 16) >> 3;         // chroma lanes: 16..23 Cb, 24..31 Cr
-  int qpc_cur = 0;
-  if (lane >= 16) qpc_cur = m->qp_c[cplane];
-  bool top_done = false;
+  // edges with anything to filter, in the standard's order: bit 4 * k of `live` for edge k = dir * 4 + edge
+  unsigned live = __ballot_sync (0xffffffffu, bs != 0);
+  if (live == 0) return false;
+  live = (live | (live >> 1) | (live >> 2) | (live >> 3)) & 0x11111111u;
+  if (t8) live &= 0x01010101u;                         // 8x8 transform: edges 1 and 3 do not exist
+  const bool top_done = (live >> 16) & 1u;
+  const bool chroma = lane >= 16;
+  const int cplane = (lane >> 3) & 1;                  // chroma lanes: 16..23 Cb, 24..31 Cr
+  const int qp_own = chroma ? m->qp_c[cplane] : m->qp_y;
+  const int seg = chroma ? ((lane & 7) >> 1) : (lane >> 2);
+  const int l = chroma ? (lane & 7) : lane;            // line index along the edge
+  uint8_t* const plane = chroma ? s.rc[cplane] + RC_TOP * RC + 8 : s.ry + RY_TOP * RY + 16;   // sample (0, 0) of the cur tile
+  const int stride = chroma ? RC : RY;
 #pragma unroll 1
-  for (int d = 0; d < 2; d++) {
-    const lh264_mb_rec* nb = d ? mt : ml;
-#pragma unroll 1
-    for (int ed = 0; ed < 4; ed++) {
-      const int seg = lane < 16 ? (lane >> 2) : ((lane & 7) >> 1);
-      const int my_bs = __shfl_sync (0xffffffffu, bs, d * 16 + ed * 4 + seg);
-      const unsigned any = __ballot_sync (0xffffffffu, my_bs != 0);
-      if ((ed & 1) && t8) continue;
-      if (!any) continue;
-      if (d == 1 && ed == 0) top_done = true;
-      if (lane < 16) {
-        int qp = qp_cur;
-        if (ed == 0) qp = (qp + nb->qp_y + 1) >> 1;
-        const int ia = clip3i (qp + aoff, 0, 51), alpha = c_alpha[ia], beta = c_beta[clip3i (qp + boff, 0, 51)];
-        if ((alpha | beta) && my_bs) {
-          uint8_t* p = d ? s.ry + (RY_TOP + 4 * ed) * RY + 16 + lane : s.ry + (RY_TOP + lane) * RY + 16 + 4 * ed;
-          luma_line (p, d ? RY : 1, my_bs, ia, alpha, beta);
-        }
-      } else if (! (ed & 1)) {
-        int qp = qpc_cur;
-        if (ed == 0) qp = (qp + nb->qp_c[cplane] + 1) >> 1;
-        const int ia = clip3i (qp + aoff, 0, 51), alpha = c_alpha[ia], beta = c_beta[clip3i (qp + boff, 0, 51)];
-        if ((alpha | beta) && my_bs) {
-          const int l = lane & 7;
-          uint8_t* p = d ? s.rc[cplane] + (RC_TOP + 2 * ed) * RC + 8 + l : s.rc[cplane] + (RC_TOP + l) * RC + 8 + 2 * ed;
-          chroma_line (p, d ? RC : 1, my_bs, ia, alpha, beta);
-        }
+  while (live) {
+    const int k = (__ffs (live) - 1) >> 2;             // dir * 4 + edge
+    live &= live - 1;
+    const int d = k >> 2, ed = k & 3;
+    const int my_bs = __shfl_sync (0xffffffffu, bs, 4 * k + seg);
+    if (my_bs && ! (chroma && (ed & 1))) {
+      const lh264_mb_rec* nb = d ? mt : ml;
+      int qp = qp_own;
+      if (ed == 0) qp = (qp + (chroma ? nb->qp_c[cplane] : nb->qp_y) + 1) >> 1;
+      const int ia = clip3i (qp + aoff, 0, 51), alpha = c_alpha[ia], beta = c_beta[clip3i (qp + boff, 0, 51)];
+      if (alpha | beta) {
+        const int pos = chroma ? 2 * ed : 4 * ed;      // edge position inside the tile
+        uint8_t* p = d ? plane + pos * stride + l : plane + l * stride + pos;
+        edge_line (p, d ? stride : 1, my_bs, ia, alpha, beta, chroma);
       }
-      __syncwarp();
     }
+    __syncwarp();
   }
   return top_done;
 }
@@ -503,6 +556,7 @@ __global__ void __launch_bounds__ (ROWS_WARPS * 32, 2) k_decode_rows (const PicD
     int* my = progress + (size_t)pi * max_rows + mby;
     const int* above = my - 1;
     int seen = 0;                                   // progress of the row above known so far
+    int cached_slice = -1;                          // slice whose fields are in s.sl_*
     const uint32_t* row = reinterpret_cast<const uint32_t*> (pic.mbs + (size_t)mby * mb_w);
     const uint32_t* row_top = mby > 0 ? reinterpret_cast<const uint32_t*> (pic.mbs + (size_t) (mby - 1) * mb_w) : row;
     uint32_t recw = __ldg (row + lane), topw = __ldg (row_top + lane);   // the records of the next MB are always in flight
@@ -530,6 +584,14 @@ __global__ void __launch_bounds__ (ROWS_WARPS * 32, 2) k_decode_rows (const PicD
         }
       }
       const int mb_type = s.mb.mb_type;
+      if (mb_type != LH264_MB_NONE && (int)s.mb.slice_idx != cached_slice) {      // uniform: every lane reads the same record
+        cached_slice = s.mb.slice_idx;
+        const lh264_slice_rec* sl = pic.slices + cached_slice;
+        __syncwarp();
+        if (lane < LH264_MAX_REFS) s.sl_slot[lane] = (int16_t)clip3i (__ldg (&sl->ref_slot[lane]), 0, pic.n_slots - 1);
+        else if (lane == 16) { s.sl_wp = __ldg (&sl->weighted_pred); s.sl_idc = __ldg (&sl->disable_deblocking_idc); s.sl_aoff = __ldg (&sl->alpha_c0_offset); s.sl_boff = __ldg (&sl->beta_offset); }
+        __syncwarp();
+      }
       // the row above must have stored macroblock x (its final state but for the edge filtered here) and written the
       // unfiltered bottom row of macroblock x + 1: both are true once it has finished macroblock x + 1, i.e. published x + 1
       if (mby > 0) {
@@ -552,7 +614,7 @@ __global__ void __launch_bounds__ (ROWS_WARPS * 32, 2) k_decode_rows (const PicD
       if (LH264_MB_IS_INTER (mb_type)) {
         const lh264_slice_rec* sl = pic.slices + s.mb.slice_idx;
         bool done = false;
-        if ((mb_type == LH264_MB_P16x16 || mb_type == LH264_MB_PSKIP) && ! (s.mb.flags & LH264_MBF_TRANSFORM8x8)) done = w_inter16_fast (s, pic, sl, mbx, mby, lane);
+        if ((mb_type == LH264_MB_P16x16 || mb_type == LH264_MB_PSKIP) && ! (s.mb.flags & LH264_MBF_TRANSFORM8x8)) done = w_inter16_fast (s, pic, mbx, mby, lane);
         if (!done) w_inter_general (s, pic, sl, mbx, mby, lane);
       } else if (LH264_MB_IS_INTRA (mb_type)) w_intra_row (s, pic, mbx, mby, lane);
       else {                                        // not decoded in this picture: the samples stay as they are
@@ -576,7 +638,7 @@ __global__ void __launch_bounds__ (ROWS_WARPS * 32, 2) k_decode_rows (const PicD
       }
       __syncwarp();
       // ---- deblocking of macroblock x: left edge across prev | cur, top edge across the rows above | cur ----
-      const bool top_done = w_deblock_tile (s, pic, mbx, mby, lane);
+      const bool top_done = w_deblock_tile (s, mbx, mby, lane);
       __syncwarp();
       // ---- macroblock x - 1 is final (but for its bottom edge): store it; rows of the macroblock above go back; cur -> prev ----
       {
