@@ -1,21 +1,24 @@
 #!/usr/bin/env python
 """bench.py — 1080p decode frames/s of the B200 hot path (BASELINE.json config 4).
 
-Workload: S independent 1920x1080 Constrained-Baseline IPPP streams per GPU.  Every stream decodes
-the same 16-picture synthetic sequence (tests/golden/streams/syn1080p_cbp_ippp_16f.264, made by the
-reference encoder from the seeded generator of tools/make_synth_stream.py); stream state (DPB
-slots, records) is per stream, so the device does S times the work.  The hand-off records are
-produced by the host CAVLC parser (losslessh264_b200/host) before the timed region.
+Workload: S independent 1920x1080 Constrained-Baseline IPPP streams per GPU, drawn from EIGHT distinct 16-picture synthetic
+sequences (tests/golden/bench_streams/, made by the reference encoder from the seeded generator of tools/make_synth_stream.py with
+eight seeds and pinned by the unmodified reference decoder, tools/make_bench_streams.py).  Streams are STAGGERED: stream i plays
+sequence i mod 8 and is (i mod 16) pictures ahead of stream 0, so every step mixes I and P pictures of different streams (no step
+is all-I or all-P) and the per-stream coders never run in lock-step.
 
-One "step" = one coded picture for every stream = S pictures reconstructed (inter pass, intra
-row wavefront, deblocking row wavefront: 2 kernel launches).
-  value : records resident in HBM when the timed region starts (lh264_batch_recon).
-  e2e   : records in pinned HOST memory -> lh264_recon_submit (H2D inside) -> decoded I420 of every
-          picture back to pinned host memory (lh264_pictures_read_packed), all inside the timed region.
-  roofline : dominant kernel family, algorithmic bytes / CUDA-event time, vs the
-          measured HBM copy bandwidth in MEASURED_PEAKS.json.
-  cpu_baseline / --impl reference : the compiled reference (oracle/_ref/h264dec: parse + model +
-          reconstruction, C kernels) on the box's host cores, same stream.
+One "step" = one coded picture for every stream = S pictures through reconstruction + deblocking (k_decode_rows) and the
+recompression model (k_model_*).
+  value : records resident in HBM when the timed region starts (lh264_batch_recon + lh264_model_batch_run).
+  e2e   : BITSTREAM IN.  Annex-B bytes in host memory -> lh264_rt_run (include/lh264_runtime.h: parse threads -> pinned staging
+          -> one recon + one model submit per step -> packed D2H) -> decoded I420 of every picture in pinned host memory +
+          `.pip` side streams; host<->device copies and the host CAVLC parse are inside the timed region, as they are inside
+          the reference arm's number.  `e2e_records` keeps round 1's figure (pre-parsed records in pinned host memory).
+  recompress : the `x.264 -> x.pip` leg without a YUV sink: model only, no reconstruction, no picture comes back.
+  roofline : dominant kernel family, algorithmic bytes / CUDA-event time, vs the measured HBM copy bandwidth in
+          MEASURED_PEAKS.json; `traffic` from the committed ncu summary of that kernel (profiles/).
+  cpu_baseline / --impl reference : the compiled reference (oracle/_ref/h264dec: parse + model + reconstruction, C kernels) on
+          the box's host cores, same streams.
 """
 from __future__ import annotations
 
@@ -32,13 +35,26 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-STREAM = os.path.join(ROOT, "tests", "golden", "streams", "syn1080p_cbp_ippp_16f.264")
+BENCH_DIR = os.path.join(ROOT, "tests", "golden", "bench_streams")
+BENCH_META = json.load(open(os.path.join(BENCH_DIR, "bench_streams.json")))
+BENCH_NAMES = sorted(BENCH_META)
+STREAMS = [os.path.join(BENCH_DIR, n) for n in BENCH_NAMES]
+STREAM = STREAMS[0]
+N_SEQ_FRAMES = 16
 PARSE_TOOL = os.path.join(ROOT, "losslessh264_b200", "_lib", "lh264_parse_dump")
 REF_DEC = os.path.join(ROOT, "oracle", "_ref", "h264dec")
 METRIC, UNIT = "1080p decode frames/s + recompress MB/s", "frames/s"
-WORKLOAD = "syn1080p_cbp_ippp_16f x S independent streams (BASELINE config 4), 1 picture per stream per step"
+WORKLOAD = "syn1080p IPPP 16-picture sequences (8 seeds) x S independent staggered streams (BASELINE config 4), 1 picture per stream per step"
 MB_PER_PIC = 120 * 68
 PIC_BYTES = 1920 * 1088 * 3 // 2
+
+
+def config_dict(streams):
+    """`config` of both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "streams_per_gpu": streams, "pictures_per_step_per_gpu": streams, "resolution": "1920x1080 (coded 1920x1088)",
+            "step": "reconstruction (decode) + recompression model of one picture per stream, i.e. the whole `h264dec in.264 out.pip` hot path",
+            "sequences": len(STREAMS), "stagger": "stream i is (i mod 16) pictures ahead: S/16 I pictures in every step",
+            "l2": "inputs larger than L2 (each step touches > 1 GB of records, pictures and decisions)"}
 
 
 def measured_peak():
@@ -86,7 +102,7 @@ def run_reference_once(k, tmp):
     for i in range(k):
         d = os.path.join(tmp, f"p{i}")
         os.makedirs(d, exist_ok=True)
-        procs.append(subprocess.Popen([REF_DEC, STREAM, os.path.join(d, "o.pip"), os.path.join(d, "o.yuv")], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True))
+        procs.append(subprocess.Popen([REF_DEC, STREAMS[i % len(STREAMS)], os.path.join(d, "o.pip"), os.path.join(d, "o.yuv")], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True))
     fps_core, frames = 0.0, 0
     for p in procs:
         err = p.communicate()[1]
@@ -107,8 +123,8 @@ def run_reference_expand(k, tmp):
         d = os.path.join(tmp, f"p{i}")
         procs.append(subprocess.Popen([REF_DEC, os.path.join(d, "o.pip"), os.path.join(d, "back.264")], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True))
     fps = 0.0
-    original = open(STREAM, "rb").read()
     for i, p in enumerate(procs):
+        original = open(STREAMS[i % len(STREAMS)], "rb").read()
         err = p.communicate()[1]
         m = re.search(r"Frames:\s+(\d+)\s+decode time:\s+([\d.]+) sec", err)
         if p.returncode != 0 or not m:
@@ -154,24 +170,83 @@ def bench_reference(args):
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": round(v, 2), "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": min(args.warmup, 1),
         "ms_per_step": round(1000 * dt / steps, 1), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "streams_per_gpu": args.streams, "resolution": "1920x1080 (coded 1920x1088)",
-                   "step": "reconstruction (decode) + recompression model, i.e. the whole `h264dec in.264 out.pip` hot path; a reference step = "
-                           f"{k} one-stream processes (its model state is process-global) x the 16 pictures of the workload stream"},
+        "config": config_dict(args.streams),
+        "reference_step": f"{k} one-stream processes (the reference's model state is process-global) x the 16 pictures of bench stream i mod 8; "
+                          f"--steps is clamped to 3 and --warmup to 1 (a step is a 5-7 s run of {k} processes)",
         "cpu_baseline": {"value": round(v, 2), "unit": UNIT, "cores": k, "host_cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": round(v, 2), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
-def parse_stream():
+def parse_stream(path=None):
     from losslessh264_b200.records import read_lhfb, read_lhmd
 
     with tempfile.TemporaryDirectory() as tmp:
         out, md = os.path.join(tmp, "s.lhfb"), os.path.join(tmp, "s.lhmd")
-        r = subprocess.run([PARSE_TOOL, STREAM, out, "3", md], capture_output=True, text=True)
+        r = subprocess.run([PARSE_TOOL, path or STREAM, out, "3", md], capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("host parser failed: " + r.stderr[-300:])
         m = re.search(r"\(([\d.]+) pictures/s\)", r.stderr)
         return read_lhfb(out), read_lhmd(md), float(m.group(1)) if m else None
+
+
+def split_units(data):
+    """Byte offsets of the NAL units of an Annex-B buffer (4-byte start codes, as the reference encoder writes them)."""
+    offs, i = [], data.find(b"\x00\x00\x00\x01")
+    while i >= 0:
+        offs.append(i)
+        i = data.find(b"\x00\x00\x00\x01", i + 4)
+    return offs
+
+
+def staggered_input(data, k):
+    """The first k pictures of the sequence (SPS, PPS, IDR, k - 1 P pictures), then the whole sequence: a valid stream of 16 + k
+    pictures whose IDR pictures fall k steps later than those of the plain sequence."""
+    if k == 0:
+        return data
+    offs = split_units(data)
+    return data[:offs[2 + k]] + data
+
+
+def ncu_traffic(kernel):
+    """dram bytes per picture of the dominant kernel from the newest committed `ncu --set full` summary (tools/ncu_summary.py)."""
+    best = None
+    prof = os.path.join(ROOT, "profiles")
+    for f in sorted(os.listdir(prof)):
+        if f.endswith("_ncu_summary.json"):
+            try:
+                d = json.load(open(os.path.join(prof, f)))
+            except Exception:
+                continue
+            if d.get("kernel") == kernel and d.get("dram_bytes_per_unit"):
+                best = (f, d)
+    return best
+
+
+def bench_runtime(streams_bytes, S, threads, loops, device, want_yuv, pipelines=1, verify=None):
+    """Bitstream-in leg through lh264_rt_* (include/lh264_runtime.h).  Returns the stats dict + pictures."""
+    from losslessh264_b200.runtime import Runtime
+
+    rt = Runtime(device=device, threads=threads, pipelines=pipelines, want_yuv=want_yuv, want_hash=verify is not None, want_pip=True, loops=loops)
+    bufs = {}
+    for i in range(S):
+        key = (i % len(streams_bytes), (i % N_SEQ_FRAMES) if verify is None else 0)
+        if key not in bufs:
+            rt.add(staggered_input(streams_bytes[key[0]], key[1]))
+            bufs[key] = (rt._keep[-1], len(rt._keep[-1]) - 4)
+        else:
+            rt.add_shared(*bufs[key])
+    rt.run()
+    st = rt.stats()
+    ok = None
+    if verify is not None:
+        ok = True
+        for i in range(S):
+            r, g = rt.result(i), verify[i % len(verify)]
+            if (want_yuv and r["yuv_sha1"] != g["yuv_sha1"]) or r["pip_sha1"] != g["pip_sha1"] or r["pictures"] != g["frames"] * loops:
+                ok = False
+    rt.close()
+    return st, ok
 
 
 def bench_expand(ctx, mpics, n_streams, world):
@@ -240,8 +315,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=16)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--streams", type=int, default=1024, help="independent 1080p streams per GPU (BASELINE config 4: 1024 streams)")
-    ap.add_argument("--e2e-threads", type=int, default=8, help="host threads (one context each) on the host-buffer path")
-    ap.add_argument("--e2e-streams", type=int, default=512, help="streams on the host-buffer path (all threads together)")
+    ap.add_argument("--e2e-threads", type=int, default=0, help="parse threads of the bitstream-in leg per GPU (0 = host cores / GPUs)")
+    ap.add_argument("--e2e-streams", type=int, default=1024, help="streams of the bitstream-in leg per GPU")
+    ap.add_argument("--e2e-loops", type=int, default=2, help="times every stream replays its input on the bitstream-in leg")
+    ap.add_argument("--e2e-pipelines", type=int, default=1)
+    ap.add_argument("--no-records-leg", action="store_true", help="skip e2e_records (round 1's host-records figure)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-expand", action="store_true", help="skip the decompress-direction leg")
     ap.add_argument("--expand-streams", type=int, default=2048, help="streams of the decompress-direction leg (one warp each; throughput peaks near 2048, profiles/r1_summary.md)")
@@ -268,17 +346,22 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     S, K, W = args.streams, args.steps, max(args.warmup, 3)
 
-    pics, mpics, parse_pps = parse_stream()
-    n_frames = len(pics)
-    assert len(mpics) == n_frames
-    mb_w, mb_h = pics[0].mb_w, pics[0].mb_h
-    stream_bytes = os.path.getsize(STREAM)
+    parsed = [parse_stream(p) for p in STREAMS]           # 8 sequences x (reconstruction records, model records, parse rate)
+    n_seq = len(parsed)
+    n_frames = N_SEQ_FRAMES
+    assert all(len(p[0]) == n_frames and len(p[1]) == n_frames for p in parsed)
+    parse_pps = sum(p[2] for p in parsed if p[2]) / max(1, sum(1 for p in parsed if p[2]))
+    pics0 = parsed[0][0]
+    mb_w, mb_h = pics0[0].mb_w, pics0[0].mb_h
+    stream_bytes = sum(os.path.getsize(p) for p in STREAMS) / n_seq
+    n_slots = max(n_slots_needed(p[0]) for p in parsed)
     tstream = torch.cuda.Stream()
     ctx = Context(local, tstream.cuda_stream)
-    streams = [ctx.open_stream(mb_w, mb_h, n_slots_needed(pics)) for _ in range(S)]
+    streams = [ctx.open_stream(mb_w, mb_h, n_slots) for _ in range(S)]
     mstreams = [ctx.model_open(mb_w * mb_h) for _ in range(S)]
-    batches = [ctx.upload_batch([p] * S, streams) for p in pics]   # S independent copies of every picture's records
-    mbatches = [ctx.model_upload_batch([p] * S, mstreams) for p in mpics]
+    # step t: stream i decodes picture (t + i) mod 16 of sequence i mod 8 (staggered: every step holds S/16 I pictures)
+    batches = [ctx.upload_batch([parsed[i % n_seq][0][(t + i) % n_frames] for i in range(S)], streams) for t in range(n_frames)]
+    mbatches = [ctx.model_upload_batch([parsed[i % n_seq][1][(t + i) % n_frames] for i in range(S)], mstreams) for t in range(n_frames)]
     ctx.sync()
 
     def barrier():
@@ -297,24 +380,24 @@ def main():
     # ---- value: records resident in HBM; a step = reconstruction + recompression model of one picture per stream -----
     # every step touches S x (records + 2-4 picture planes + decision list) = S x ~16 MB >> 126 MB L2: inputs larger than L2
     step_no = 0
-    FREE = os.environ.get("LH264_BENCH_FREE") == "1"       # experiment: let reconstruction t+1 overlap the model of picture t
+    SERIAL = os.environ.get("LH264_BENCH_SERIAL") == "1"   # experiment: next reconstruction only after this step's model
 
-    def resident_steps(n, model=True):
+    def resident_steps(n, recon=True, model=True):
         nonlocal step_no
         for _ in range(n):
-            ctx.recon_resident(batches[step_no % n_frames])
+            if recon:
+                ctx.recon_resident(batches[step_no % n_frames])
             if model:
                 ctx.model_run_resident(mbatches[step_no % n_frames])
-                if not FREE:
-                    ctx.join()                         # measured: the persistent row kernels and the coder slow each other down
-                                                       # when co-resident, so the next reconstruction starts after this model
+                if SERIAL:
+                    ctx.join()
             step_no += 1
 
-    def timed(n, model):
+    def timed(n, recon, model):
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(tstream)
-        resident_steps(n, model)
+        resident_steps(n, recon, model)
         ctx.join()                                     # the model runs on its own CUDA stream: order tstream after it
         e1.record(tstream)
         barrier()
@@ -325,145 +408,181 @@ def main():
         sampler = ClockSampler(local)
         sampler.start()
         l0 = ctx.kernel_launches()
-        ms = timed(K, True)
+        ms = timed(K, True, True)
         launches = ctx.kernel_launches() - l0
         sampler.stop_flag = True
         step_no = 0
-        ms_dec = timed(K, False)                       # reconstruction alone (decode without the recompression model)
+        ms_dec = timed(K, True, False)                 # reconstruction alone (decode without the recompression model)
+        step_no = 0
+        ms_mod = timed(K, False, True)                 # the model alone (`x.264 -> x.pip` without a YUV sink)
     value = world * S * K / (ms / 1000.0)
     value_dec = world * S * K / (ms_dec / 1000.0)
+    value_mod = world * S * K / (ms_mod / 1000.0)
 
     # ---- roofline per kernel family (CUDA events on the launching stream) ---------------------------------------------
     step_no = 0
-    d0 = ctx.model_decisions(mstreams[0])
+    d0 = sum(ctx.model_decisions(mstreams[i]) for i in range(n_seq))
     ctx.kernel_ms(-1)                                   # reset + enable per-family event timing
     resident_steps(n_frames)
     fam = [ctx.kernel_ms(i) for i in (0, 4, 5)]
     ctx.kernel_ms(-2)
-    dec_seq = ctx.model_decisions(mstreams[0]) - d0     # decisions of one pass over the sequence, per stream
+    dec_seq = (sum(ctx.model_decisions(mstreams[i]) for i in range(n_seq)) - d0) / n_seq   # decisions of one pass over a sequence, per stream
     fam_names = ["k_decode_rows", "k_model_frame+count+scan+emit", "k_model_code"]
     dom = int(np.argmax(fam))
-    n_p = sum(1 for p in pics if int(p.slices["slice_type"][0]) == 0)
+    n_p = sum(sum(1 for q in p[0] if int(q.slices["slice_type"][0]) == 0) for p in parsed) / n_seq
     peak, peak_kind = measured_peak()
-    pip_bytes_seq = 175638                               # .pip side-stream bytes of one pass (reference output size)
-    n_rec_seq = sum(len(p.recs) for p in mpics)
+    pip_bytes_seq = sum(BENCH_META[n]["pip_bytes"] for n in BENCH_NAMES) / n_seq        # `.pip` bytes of one pass (reference output size)
+    n_rec_seq = sum(sum(len(q.recs) for q in p[1]) for p in parsed) / n_seq
     # algorithmic bytes of each family over one pass of the sequence, all S streams (DESIGN.md "Algorithmic bytes"):
-    #   k_recon_rows   reference read (P pictures) + reconstruction write + records and coefficients (896 B / MB)
-    #   k_deblock_rows picture read + write + MB metadata (128 B / MB)
+    #   k_decode_rows  SURVEY 8d counts reconstruction and deblocking as separate passes; the fused kernel does the work of both and
+    #                  is charged their algorithmic bytes: reference read (P pictures) + reconstruction write + deblock read + write
+    #                  + records and coefficients (896 B / MB) + MB metadata for deblocking (128 B / MB)
     #   model gen      MB record + coefficients (896 B) + three neighbour context records (SURVEY 8d charges 3 x 896)
     #   k_model_code   24 B per decision (one DynProb read + write at the reference's 12 B) + output bytes
-    #   k_decode_rows  = the two above (SURVEY 8d counts reconstruction and deblocking as separate passes; the fused kernel does
-    #                  the work of both and is charged their algorithmic bytes: 4P per P picture + 1024 B per macroblock)
     share = [S * (n_p * PIC_BYTES + n_frames * (PIC_BYTES + MB_PER_PIC * 896)) + S * n_frames * (2 * PIC_BYTES + MB_PER_PIC * 128),
              S * n_rec_seq * 3584, S * (dec_seq * 24 + pip_bytes_seq)]
     ach = [share[i] / (fam[i] / 1000.0) / 1e9 if fam[i] > 0 else 0.0 for i in range(3)]
     ach_all = sum(share) / (sum(fam) / 1000.0) / 1e9
-    # DRAM traffic of one launch (dram__bytes_read.sum + dram__bytes_write.sum, `ncu --set full`, captures summarised in profiles/):
-    # measured per P picture at S = 256 and scaled to this run's pictures per launch
-    traffic_per_picture = {"k_decode_rows": None, "k_model_frame+count+scan+emit": None, "k_model_code": 3.05e6}
-    tpp = traffic_per_picture[fam_names[dom]]
+    # DRAM traffic of one launch of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum per picture from the committed
+    # `ncu --set full` summary of that kernel (profiles/*_ncu_summary.json, tools/ncu_summary.py) x the pictures of one launch
+    tr = ncu_traffic(fam_names[dom].split("+")[0])
     roofline = {"bound": "hbm", "kernel": fam_names[dom], "achieved": round(ach[dom], 1), "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                "frac": round(ach[dom] / peak, 4), "traffic": int(tpp * S) if tpp else None,
-                "traffic_note": "bytes per launch = ncu dram read+write per P picture (profiles/r1_summary.md) x pictures per launch" if tpp else None,
+                "frac": round(ach[dom] / peak, 4), "traffic": int(tr[1]["dram_bytes_per_unit"] * S) if tr else None,
+                "traffic_note": (f"bytes per launch = ncu dram read+write per picture (profiles/{tr[0]}: {tr[1].get('note', '')}) x {S} pictures per launch" if tr else None),
                 "whole_step": {"achieved": round(ach_all, 1), "frac": round(ach_all / peak, 4)},
                 "families": {n: {"ms_per_16_steps": round(t, 3), "achieved": round(a, 1), "frac": round(a / peak, 4)} for n, t, a in zip(fam_names, fam, ach)},
                 "model_decisions_per_s": round(S * dec_seq / (fam[2] / 1000.0)) if fam[2] > 0 else None}
 
-    # ---- e2e: pinned host records in, decoded pictures back to pinned host memory -------------------------------------
-    # T host threads, each with its own context (CUDA streams) and Se streams, as a host application with one worker per
-    # group of streams would drive the library; copies of one group overlap the kernels of another.
-    T = args.e2e_threads
-    Se = max(1, min(S, args.e2e_streams) // T)         # pictures per submit per thread
-    keep = []
-    hp, hm = [], []
-    for p, q in zip(pics, mpics):
-        p2, q2 = copy.copy(p), copy.copy(q)
-        p2.mbs, p2.coefs, p2.slices = pinned_copy(p.mbs, keep), pinned_copy(p.coefs, keep), pinned_copy(p.slices, keep)
-        q2.recs, q2.slices, q2.coefs = pinned_copy(q.recs, keep), pinned_copy(q.slices, keep), p2.coefs   # the same coefficient pool
-        hp.append(p2)
-        hm.append(q2)
-    h2d = T * Se * int(pics[1].mbs.nbytes + pics[1].coefs.nbytes + pics[1].slices.nbytes + mpics[1].recs.nbytes + mpics[1].slices.nbytes)
-    d2h = T * Se * 1920 * 1080 * 3 // 2
-    Ke = max(n_frames, min(K, 32))
-    gate = threading.Barrier(T + 1)
-    errors = []
-
-    def e2e_worker(tid):
-        try:
-            c = Context(local)
-            st = [c.open_stream(mb_w, mb_h, n_slots_needed(pics)) for _ in range(Se)]
-            ms_ = [c.model_open(mb_w * mb_h) for _ in range(Se)]
-            outs = [PinnedArray(Se * 1920 * 1080 * 3 // 2) for _ in range(2)]
-
-            # descriptor arrays (structs of pointers into the pinned host buffers) are built once per frame index, as a C host
-            # application would have them; the timed loop is the three C-ABI calls and the copies they start
-            rd = [c.recon_descs([hp[i]] * Se, st) for i in range(n_frames)]
-            md = [c.model_descs([hm[i]] * Se, ms_) for i in range(n_frames)]
-
-            def steps(n):
-                for t in range(n):
-                    i = t % n_frames
-                    c.recon_prepared(rd[i], sync=False)
-                    c.model_submit_prepared(md[i], sync=False)
-                    # the D2H of this step's pictures runs on the library's copy stream while the next step's records go up
-                    c.read_packed(st, [hp[i].cur_slot] * Se, (0, 0, 1920, 1080), outs[t & 1], sync=False)
-                c.sync()
-
-            steps(n_frames)                            # warm-up: one pass over the sequence
-            gate.wait()
-            steps(Ke)
-            gate.wait()
-            c.close()
-        except Exception as e:                         # surface worker failures in the main thread
-            errors.append(repr(e))
-            try:
-                gate.abort()
-            except Exception:
-                pass
-
-    workers = [threading.Thread(target=e2e_worker, args=(i,)) for i in range(T)]
-    for w_ in workers:
-        w_.start()
-    try:
-        gate.wait()
-        barrier()
-        t0 = time.perf_counter()
-        gate.wait()
-    except threading.BrokenBarrierError:               # a worker failed and aborted the gate: report ITS error
-        for w_ in workers:
-            w_.join()
-        raise RuntimeError("e2e worker failed: " + (errors[0] if errors else "unknown"))
-    e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1000.0)
-    for w_ in workers:
-        w_.join()
-    if errors:
-        raise RuntimeError("e2e worker failed: " + errors[0])
-    e2e_value = world * T * Se * Ke / (e2e_ms / 1000.0)
-    mb_per_frame = stream_bytes / n_frames / 1e6
-
     line = {
         "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": round(ms / K, 4),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "streams_per_gpu": S, "pictures_per_step_per_gpu": S, "resolution": "1920x1080 (coded 1920x1088)",
-                   "step": "reconstruction (decode) + recompression model of one picture per stream, i.e. the whole `h264dec in.264 out.pip` hot path",
-                   "l2": "inputs larger than L2 (each step touches > 1 GB of records, pictures and decisions)", "host_parse_pictures_per_s_per_core": parse_pps},
-        "recompress": {"value": round(value * mb_per_frame, 2), "unit": "MB/s of input .264", "pip_out_mb_s": round(value * pip_bytes_seq / n_frames / 1e6, 2)},
+        "config": config_dict(S), "host_parse_pictures_per_s_per_core": round(parse_pps, 1),
         "decode_only": {"value": round(value_dec, 1), "unit": UNIT, "ms_per_step": round(ms_dec / K, 4)},
+        "model_only": {"value": round(value_mod, 1), "unit": UNIT, "ms_per_step": round(ms_mod / K, 4), "input_mb_s": round(value_mod * stream_bytes / n_frames / 1e6, 2)},
         "roofline": roofline,
-        "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "pictures_per_step": T * Se, "host_threads": T,
-                "recompress_mb_s": round(e2e_value * mb_per_frame, 2),
-                "path": "lh264_recon_submit + lh264_model_submit (pinned host records) + lh264_pictures_read_packed (I420 to pinned host)"},
         "gpu_launches": int(launches), "clocks": sampler.summary(),
     }
+    mb_per_frame = stream_bytes / n_frames / 1e6
+
+    # ---- e2e_records (round 1's figure): pre-parsed records in pinned host memory in, decoded pictures back -----------
+    if not args.no_records_leg:
+        T = 8
+        Se = max(1, min(S, 512) // T)                      # pictures per submit per thread
+        keep = []
+        hp, hm = [], []
+        for p, q in zip(parsed[0][0], parsed[0][1]):
+            p2, q2 = copy.copy(p), copy.copy(q)
+            p2.mbs, p2.coefs, p2.slices = pinned_copy(p.mbs, keep), pinned_copy(p.coefs, keep), pinned_copy(p.slices, keep)
+            q2.recs, q2.slices, q2.coefs = pinned_copy(q.recs, keep), pinned_copy(q.slices, keep), p2.coefs   # the same coefficient pool
+            hp.append(p2)
+            hm.append(q2)
+        Ke = n_frames
+        gate = threading.Barrier(T + 1)
+        errors = []
+
+        def rec_worker(tid):
+            try:
+                c = Context(local)
+                st = [c.open_stream(mb_w, mb_h, n_slots) for _ in range(Se)]
+                ms_ = [c.model_open(mb_w * mb_h) for _ in range(Se)]
+                outs = [PinnedArray(Se * 1920 * 1080 * 3 // 2) for _ in range(2)]
+                rd = [c.recon_descs([hp[i]] * Se, st) for i in range(n_frames)]
+                md = [c.model_descs([hm[i]] * Se, ms_) for i in range(n_frames)]
+
+                def steps(n):
+                    for t in range(n):
+                        i = t % n_frames
+                        c.recon_prepared(rd[i], sync=False)
+                        c.model_submit_prepared(md[i], sync=False)
+                        c.read_packed(st, [hp[i].cur_slot] * Se, (0, 0, 1920, 1080), outs[t & 1], sync=False)
+                    c.sync()
+
+                steps(n_frames)
+                gate.wait()
+                steps(Ke)
+                gate.wait()
+                c.close()
+            except Exception as e:                         # surface worker failures in the main thread
+                errors.append(repr(e))
+                try:
+                    gate.abort()
+                except Exception:
+                    pass
+
+        workers = [threading.Thread(target=rec_worker, args=(i,)) for i in range(T)]
+        for w_ in workers:
+            w_.start()
+        try:
+            gate.wait()
+            barrier()
+            t0 = time.perf_counter()
+            gate.wait()
+        except threading.BrokenBarrierError:
+            for w_ in workers:
+                w_.join()
+            raise RuntimeError("e2e_records worker failed: " + (errors[0] if errors else "unknown"))
+        rec_ms = max_over_ranks((time.perf_counter() - t0) * 1000.0)
+        for w_ in workers:
+            w_.join()
+        if errors:
+            raise RuntimeError("e2e_records worker failed: " + errors[0])
+        line["e2e_records"] = {"value": round(world * T * Se * Ke / (rec_ms / 1000.0), 1), "unit": UNIT, "pictures_per_step": T * Se, "host_threads": T,
+                               "path": "pre-parsed records in pinned host memory -> lh264_recon_submit + lh264_model_submit -> lh264_pictures_read_packed (parse NOT included)"}
+        keep = []
+
+    # ---- make room: the bitstream-in legs open their own device streams ------------------------------------------------
+    for b in batches:
+        ctx.free_batch(b)
+    for b in mbatches:
+        ctx.model_free_batch(b)
+    batches, mbatches = [], []
+    for h_ in streams:
+        ctx.close_stream(h_)
+    for h_ in mstreams:
+        ctx.model_close(h_)
+    mstreams = []
+
+    # ---- e2e: Annex-B bytes in host memory -> lh264_rt_run -> I420 in pinned host memory + `.pip` ---------------------
+    cores = os.cpu_count() or 1
+    threads = args.e2e_threads or max(1, cores // world)
+    data = [open(p, "rb").read() for p in STREAMS]
+    gold = [BENCH_META[n] for n in BENCH_NAMES]
+    _, verified = bench_runtime(data, n_seq, min(threads, n_seq), 1, local, True, verify=gold)     # untimed: 8 streams, SHA1s vs the reference's
+    if not verified:
+        raise RuntimeError("bitstream-in leg: YUV / .pip SHA1 of the bench streams differ from the reference's (tests/golden/bench_streams/bench_streams.json)")
+    Se = args.e2e_streams
+    barrier()
+    st, _ = bench_runtime(data, Se, threads, args.e2e_loops, local, True, pipelines=args.e2e_pipelines)
+    steady_s = max_over_ranks(max(1e-9, st["seconds"] - st["setup_s"]) * 1000.0) / 1000.0
+    total_s = max_over_ranks(st["seconds"] * 1000.0) / 1000.0
+    pics_steady, pics_all = st["pictures"] - st["setup_pictures"], st["pictures"]
+    steps_e2e = max(1, pics_all // Se)
+    e2e_value = world * pics_steady / steady_s
+    line["e2e"] = {"value": round(e2e_value, 1), "unit": UNIT,
+                   "h2d_bytes_per_step": int(st["h2d_bytes"] // steps_e2e), "d2h_bytes_per_step": int(st["d2h_bytes"] // steps_e2e),
+                   "pictures_per_step": Se, "streams": Se, "pictures": int(pics_all), "loops": args.e2e_loops,
+                   "host_threads": int(st["threads"]), "host_cores": cores, "pipelines": int(st["pipelines"]),
+                   "including_setup": round(world * pics_all / total_s, 1), "setup_s": round(st["setup_s"], 3),
+                   "recompress_mb_s": round(e2e_value * mb_per_frame, 2),
+                   "submit_wait_parse_s": round(st["submit_wait_parse_s"], 3), "submit_wait_gpu_s": round(st["submit_wait_gpu_s"], 3),
+                   "parse_busy_s": round(st["parse_busy_s"], 3), "parse_wait_s": round(st["parse_wait_s"], 3), "seconds": round(st["seconds"], 3),
+                   "verified": "YUV SHA1 + .pip SHA1 of all 8 bench streams equal the unmodified reference's (untimed run before the timed one)",
+                   "path": "Annex-B bytes in host memory -> lh264_rt_run (parse threads, pinned staging, lh264_recon_submit + lh264_model_submit per step, "
+                           "packed D2H) -> I420 of every picture in pinned host memory + .pip side streams; value = steady state (after step 0, which opens "
+                           "the device streams), including_setup = whole run"}
+    # ---- recompress: x.264 -> x.pip without a YUV sink (model only: no reconstruction, no picture comes back) ---------
+    barrier()
+    sm, _ = bench_runtime(data, Se, threads, args.e2e_loops, local, False, pipelines=args.e2e_pipelines)
+    mod_s = max_over_ranks(max(1e-9, sm["seconds"] - sm["setup_s"]) * 1000.0) / 1000.0
+    mod_fps = world * (sm["pictures"] - sm["setup_pictures"]) / mod_s
+    line["recompress"] = {"value": round(mod_fps * mb_per_frame, 2), "unit": "MB/s of input .264", "frames_per_s": round(mod_fps, 1),
+                          "pip_out_mb_s": round(mod_fps * pip_bytes_seq / n_frames / 1e6, 2),
+                          "h2d_bytes_per_step": int(sm["h2d_bytes"] // max(1, sm["pictures"] // Se)), "d2h_bytes_per_step": 0,
+                          "device_resident_mb_s": round(value_mod * mb_per_frame, 2),
+                          "path": "bitstream in -> lh264_rt_run(want_yuv = 0): host parse + lh264_model_submit only (`h264dec in.264 out.pip`)"}
+
     if not args.no_expand:
-        for b in batches:                                 # make room: the decompress leg keeps one prior table per stream
-            ctx.free_batch(b)
-        for b in mbatches:
-            ctx.model_free_batch(b)
-        batches, mbatches = [], []
-        for h_ in mstreams:
-            ctx.model_close(h_)
-        line["expand"] = bench_expand(ctx, mpics, args.expand_streams, world)
+        line["expand"] = bench_expand(ctx, parsed[0][1], args.expand_streams, world)
     if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(REF_DEC):
         k, cores = reference_concurrency()
         with tempfile.TemporaryDirectory() as tmp:
@@ -476,11 +595,7 @@ def main():
                     line["expand"]["reference_frames_per_s"] = None
                     line["expand"]["reference_note"] = "reference decompress failed: " + str(e)[:200]
         line["cpu_baseline"] = {"value": round(core, 2), "unit": UNIT, "cores": k, "host_cores": cores, "kind": "reference",
-                                "sample": f"{k} concurrent oracle/_ref/h264dec processes x 16 frames of the workload stream (parse + model + reconstruction, tool-reported decode time; {wall:.2f} frames/s including the ~8 s start-up per process)"}
-    for b in batches:
-        ctx.free_batch(b)
-    for b in mbatches:
-        ctx.model_free_batch(b)
+                                "sample": f"{k} concurrent oracle/_ref/h264dec processes x 16 frames, process i on bench stream i mod 8 (parse + model + reconstruction, tool-reported decode time; {wall:.2f} frames/s including the ~8 s start-up per process)"}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

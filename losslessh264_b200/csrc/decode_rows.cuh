@@ -32,7 +32,7 @@
 #ifdef LH264_CPU_EMU
 #define LH264_NOINLINE __attribute__ ((noinline))
 #else
-#define LH264_NOINLINE __noinline__
+#define LH264_NOINLINE                 // (measured: __noinline__ here puts the PicDev copy and 264 bytes of spills into local memory, +65 % kernel time)
 #endif
 
 namespace lh264 {

@@ -1,0 +1,639 @@
+// runtime.cpp — the multi-stream runtime of include/lh264_runtime.h (lh264_rt_*): many independent Annex-B streams through the
+// GPU path at once, bitstream in, pictures + `.pip` out.
+//
+// The reference is one stream per process and strictly single-threaded (its model state is process-global,
+// compression_stream.cpp:18-30); its driver is h264dec's unit loop (h264dec.cpp:246-364).  This is the host runtime the B200
+// path wants instead (SURVEY.md §7 "host thread per stream", §8f N2):
+//
+//   parse threads ── thread w owns streams w, w + T, w + 2T, ...: the unit loop of h264dec → host decoder (NAL / slice /
+//        │           CAVLC / CABAC parse).  Step k of a thread = the next picture of each of its streams; the hand-off records
+//        │           go into the thread's pinned staging buffer k mod D (five tightly packed regions: MB records, coefficient
+//        │           pools, model records, slice records, model slice records), so the records of a step leave for the device
+//        │           with a handful of H2D copies per thread.  A thread runs up to D - 1 steps ahead of the device.
+//   submit thread ── per pipeline: waits until every parse thread has finished step k, hands the step's pictures to the GPU
+//                    with ONE lh264_recon_submit + ONE lh264_model_submit, starts the packed D2H copy of the decoded pictures,
+//                    delivers the pictures of step k - 1 (callback / SHA-1) while step k runs, and releases staging buffer
+//                    k mod D once its H2D copies are done.
+//   at the end    ── lh264_model_finish per stream; the `.pip` default stream (host) + tag side streams (GPU) are kept for
+//                    lh264_rt_pip_read().
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+#include "../../include/lh264_runtime.h"
+#include "decoder.h"
+#include "pip_container.h"
+#include "sha1.h"
+
+using namespace lh264host;
+
+namespace {
+
+double now() { return std::chrono::duration<double> (std::chrono::steady_clock::now().time_since_epoch()).count(); }
+
+struct PinRegion {                      // growable pinned buffer, bump-allocated within a step
+  uint8_t* p = nullptr; size_t cap = 0, used = 0;
+  ~PinRegion() { if (p) lh264_host_free (p); }
+  // returns the offset of n fresh bytes (contents so far are kept when the buffer has to grow), or (size_t)-1
+  size_t take (size_t n) {
+    const size_t at = used, need = used + n;
+    if (need > cap) {
+      const size_t ncap = std::max (need + need / 2, (size_t)1 << 16);
+      uint8_t* q = (uint8_t*)lh264_host_alloc (ncap);
+      if (!q) return (size_t) -1;
+      if (used) memcpy (q, p, used);
+      if (p) lh264_host_free (p);
+      p = q; cap = ncap;
+    }
+    used = need;
+    return at;
+  }
+};
+
+struct Placed {                         // one picture of a step: where its arrays sit in the thread's staging buffer
+  int stream;
+  size_t o_sl, o_mb, o_co, o_msl, o_mr;
+  int n_slices, n_mbs, n_blocks, n_mslices, n_mrecs;
+  int mb_w, mb_h, n_slots, geo_serial;
+  DecodedPictureInfo info;
+};
+
+struct StepBuf {
+  PinRegion mbs, coefs, mrecs, slices, mslices;
+  std::vector<Placed> placed;
+  bool failed = false;                  // pinned allocation failed
+  void reset() { mbs.used = coefs.used = mrecs.used = slices.used = mslices.used = 0; placed.clear(); failed = false; }
+};
+
+// Receives the pictures a Decoder completes and copies their records into the current step buffer of the owning thread.
+class StageSink : public PictureSink {
+ public:
+  int stream = 0;
+  int mb_w = 0, mb_h = 0, n_slots = 0, geo_serial = 0;
+  StepBuf* buf = nullptr;               // where pictures completed now are placed
+  int placed_now = 0;                   // pictures placed since the owner last looked
+  int configure (int w, int h, int slots) override { mb_w = w; mb_h = h; n_slots = slots; geo_serial++; return 0; }
+  int submit (const lh264_picture_desc& pic, const DecodedPictureInfo& info) override {
+    Placed pl = Placed();
+    pl.stream = stream; pl.info = info;
+    pl.n_slices = pic.n_slices; pl.n_mbs = mb_w * mb_h; pl.n_blocks = pic.n_coef_blocks;
+    pl.mb_w = mb_w; pl.mb_h = mb_h; pl.n_slots = n_slots; pl.geo_serial = geo_serial;
+    const size_t b_sl = (size_t)pic.n_slices * sizeof (lh264_slice_rec), b_mb = (size_t)pl.n_mbs * sizeof (lh264_mb_rec), b_co = (size_t)pic.n_coef_blocks * 32;
+    pl.o_sl = buf->slices.take (b_sl); pl.o_mb = buf->mbs.take (b_mb); pl.o_co = buf->coefs.take (b_co);
+    if (pl.o_sl == (size_t) -1 || pl.o_mb == (size_t) -1 || pl.o_co == (size_t) -1) { buf->failed = true; return LH264_E_NOMEM; }
+    memcpy (buf->slices.p + pl.o_sl, pic.slices, b_sl);
+    memcpy (buf->mbs.p + pl.o_mb, pic.mbs, b_mb);
+    if (b_co) memcpy (buf->coefs.p + pl.o_co, pic.coefs, b_co);
+    buf->placed.push_back (pl);
+    placed_now++;
+    cur_ = (int)buf->placed.size() - 1;
+    return 0;
+  }
+  int submit_model (const lh264_model_picture& pic, const DecodedPictureInfo&) override {
+    if (cur_ < 0 || cur_ >= (int)buf->placed.size()) return 0;
+    Placed& pl = buf->placed[cur_];
+    const size_t b_sl = (size_t)pic.n_slices * sizeof (lh264_model_slice), b_rc = (size_t)pic.n_recs * sizeof (lh264_model_mb);
+    pl.o_msl = buf->mslices.take (b_sl); pl.o_mr = buf->mrecs.take (b_rc);
+    if (pl.o_msl == (size_t) -1 || pl.o_mr == (size_t) -1) { buf->failed = true; return LH264_E_NOMEM; }
+    memcpy (buf->mslices.p + pl.o_msl, pic.slices, b_sl);
+    memcpy (buf->mrecs.p + pl.o_mr, pic.recs, b_rc);
+    pl.n_mslices = pic.n_slices; pl.n_mrecs = pic.n_recs;
+    return 0;
+  }
+  void begin_step (StepBuf* b) { buf = b; cur_ = -1; placed_now = 0; }
+ private:
+  int cur_ = -1;
+};
+
+struct Stream {
+  const uint8_t* data = nullptr;        // Annex-B bytes, followed by the 00 00 00 01 sentinel
+  size_t size = 0, pos = 0;
+  std::vector<uint8_t> own;             // when the caller's bytes had no sentinel
+  StageSink sink;
+  std::unique_ptr<Decoder> dec;
+  PipBoilerplate pip;
+  bool flushed = false;
+  int loops_left = 0;
+  long parsed = 0;                      // pictures placed so far
+  int last_error = 0;
+  // a damaged stream can complete more than one picture in one unit; a step takes one picture per stream, the others wait in
+  // a private step buffer (heap, not pinned: the rare path) and are moved into the staging of the following steps
+  struct Spill { Placed pl; std::vector<uint8_t> sl, mb, co, msl, mr; };
+  std::vector<Spill> spill;
+  // submit-thread side
+  int gpu_stream = -1, model_stream = -1, model_mbs = 0, geo_seen = 0;
+  long pictures = 0, pictures_output = 0;
+  Sha1 yuv;
+  // results
+  std::vector<uint8_t> pip_default;
+  std::vector<std::vector<uint8_t> > pip_tags;
+  std::string yuv_hex = "-", pip_hex = "-";
+  size_t pip_bytes = 0;
+};
+
+} // namespace
+
+struct lh264_rt {
+  lh264_rt_config cfg;
+  std::vector<std::unique_ptr<Stream> > streams;
+  std::string error;
+  lh264_rt_stats stats;
+  bool ran = false;
+  std::mutex err_mu;
+  void fail (const std::string& e) { std::lock_guard<std::mutex> g (err_mu); if (error.empty()) error = e; }
+};
+
+namespace {
+
+struct Pipeline;
+
+struct Worker {
+  Pipeline* pl = nullptr;
+  std::vector<int> streams;             // indices into rt->streams
+  std::vector<StepBuf> bufs;
+  long steps_done = 0;                  // guarded by Pipeline::mu
+  bool finished = false;                // no picture after step steps_done - 1
+  double busy = 0, wait = 0;
+  std::thread th;
+};
+
+struct Pipeline {
+  lh264_rt* rt = nullptr;
+  int index = 0;
+  lh264_ctx* ctx = nullptr;
+  std::vector<std::unique_ptr<Worker> > workers;
+  std::mutex mu;
+  std::condition_variable cv_parsed, cv_released;
+  long released = 0;                    // steps whose staging buffers may be overwritten again
+  bool abort = false;
+  int rc = 0;
+  long pictures = 0;
+  double t_wait_parse = 0, t_wait_gpu = 0, t_end = 0, t_first = 0;
+  long first_pictures = 0;
+  size_t h2d = 0, d2h = 0;
+  unsigned long long launches = 0;
+  lh264_rt_picture_fn fn = nullptr; void* user = nullptr;
+  std::thread th;
+};
+
+// Parses until the stream has placed one picture into `buf` (or ended).  h264dec's unit loop, h264dec.cpp:246-364.
+void advance (Stream& s, StepBuf* buf, bool want_pip, long max_pictures) {
+  s.sink.begin_step (buf);
+  if (max_pictures > 0 && s.parsed >= max_pictures) return;
+  if (!s.spill.empty()) {                // a picture that was completed together with an earlier one
+    Stream::Spill& sp = s.spill.front();
+    Placed pl = sp.pl;
+    pl.o_sl = buf->slices.take (sp.sl.size()); pl.o_mb = buf->mbs.take (sp.mb.size()); pl.o_co = buf->coefs.take (sp.co.size());
+    pl.o_msl = buf->mslices.take (sp.msl.size()); pl.o_mr = buf->mrecs.take (sp.mr.size());
+    if (pl.o_sl == (size_t) -1 || pl.o_mb == (size_t) -1 || pl.o_co == (size_t) -1 || pl.o_msl == (size_t) -1 || pl.o_mr == (size_t) -1) { buf->failed = true; return; }
+    memcpy (buf->slices.p + pl.o_sl, sp.sl.data(), sp.sl.size()); memcpy (buf->mbs.p + pl.o_mb, sp.mb.data(), sp.mb.size());
+    if (!sp.co.empty()) memcpy (buf->coefs.p + pl.o_co, sp.co.data(), sp.co.size());
+    if (!sp.msl.empty()) memcpy (buf->mslices.p + pl.o_msl, sp.msl.data(), sp.msl.size());
+    if (!sp.mr.empty()) memcpy (buf->mrecs.p + pl.o_mr, sp.mr.data(), sp.mr.size());
+    buf->placed.push_back (pl);
+    s.spill.erase (s.spill.begin());
+    s.parsed++;
+    return;
+  }
+  const size_t first = buf->placed.size();
+  const size_t m0[5] = {buf->slices.used, buf->mbs.used, buf->coefs.used, buf->mslices.used, buf->mrecs.used};
+  while (s.sink.placed_now == 0 && !s.flushed) {
+    if (s.pos >= s.size) {
+      if (s.loops_left > 0) { s.loops_left--; s.pos = 0; continue; }
+      s.dec->flush(); s.flushed = true; break;
+    }
+    const size_t len = PipBoilerplate::next_unit (s.data, s.pos, s.size);
+    if (len < 4) { if (want_pip) s.pip.raw (s.data + s.pos, len); s.pos += len; continue; }
+    if (want_pip) s.pip.unit_begin (s.data + s.pos, len, s.dec->sps_seen());
+    const int rc = s.dec->decode (s.data + s.pos, len);
+    if (rc < 0) s.last_error = rc;
+    if (want_pip) {
+      UnitSliceInfo u;
+      u.slice_decoded = s.dec->last_slice().decoded; u.cabac = s.dec->last_slice().cabac; u.rbsp = s.dec->last_slice().rbsp; u.header_bits = s.dec->last_slice().header_bits;
+      s.pip.unit_end (u);
+    }
+    s.pos += len;
+  }
+  // more than one picture completed by the last unit: the first stays in this step, the others move to the spill list
+  if (buf->placed.size() > first + 1) {
+    for (size_t i = first + 1; i < buf->placed.size(); i++) {
+      const Placed& pl = buf->placed[i];
+      Stream::Spill sp;
+      sp.pl = pl;
+      sp.sl.assign (buf->slices.p + pl.o_sl, buf->slices.p + pl.o_sl + (size_t)pl.n_slices * sizeof (lh264_slice_rec));
+      sp.mb.assign (buf->mbs.p + pl.o_mb, buf->mbs.p + pl.o_mb + (size_t)pl.n_mbs * sizeof (lh264_mb_rec));
+      sp.co.assign (buf->coefs.p + pl.o_co, buf->coefs.p + pl.o_co + (size_t)pl.n_blocks * 32);
+      if (pl.n_mrecs) {
+        sp.msl.assign (buf->mslices.p + pl.o_msl, buf->mslices.p + pl.o_msl + (size_t)pl.n_mslices * sizeof (lh264_model_slice));
+        sp.mr.assign (buf->mrecs.p + pl.o_mr, buf->mrecs.p + pl.o_mr + (size_t)pl.n_mrecs * sizeof (lh264_model_mb));
+      }
+      s.spill.push_back (std::move (sp));
+    }
+    // give the bytes back: everything behind the first picture of this call
+    const Placed& f = buf->placed[first];
+    buf->slices.used = f.o_sl + (size_t)f.n_slices * sizeof (lh264_slice_rec); buf->mbs.used = f.o_mb + (size_t)f.n_mbs * sizeof (lh264_mb_rec);
+    buf->coefs.used = f.o_co + (size_t)f.n_blocks * 32;
+    buf->mslices.used = f.n_mrecs ? f.o_msl + (size_t)f.n_mslices * sizeof (lh264_model_slice) : m0[3];
+    buf->mrecs.used = f.n_mrecs ? f.o_mr + (size_t)f.n_mrecs * sizeof (lh264_model_mb) : m0[4];
+    buf->placed.resize (first + 1);
+  }
+  (void)m0;
+  if (buf->placed.size() > first) s.parsed++;
+}
+
+void worker_main (Worker* w) {
+  Pipeline* P = w->pl;
+  lh264_rt* rt = P->rt;
+  const int D = (int)w->bufs.size();
+  const bool want_pip = rt->cfg.want_pip != 0;
+  for (long k = 0;; k++) {
+    {
+      const double t0 = now();
+      std::unique_lock<std::mutex> g (P->mu);
+      P->cv_released.wait (g, [&] { return P->abort || k < P->released + D; });
+      w->wait += now() - t0;
+      if (P->abort) { w->finished = true; w->steps_done = k; P->cv_parsed.notify_all(); return; }
+    }
+    const double t0 = now();
+    StepBuf& b = w->bufs[k % D];
+    b.reset();
+    bool more = false;
+    for (int si : w->streams) {
+      Stream& s = *rt->streams[si];
+      advance (s, &b, want_pip, rt->cfg.max_pictures);
+      if (!s.spill.empty() || (!s.flushed && !(rt->cfg.max_pictures > 0 && s.parsed >= rt->cfg.max_pictures))) more = true;
+    }
+    w->busy += now() - t0;
+    {
+      std::lock_guard<std::mutex> g (P->mu);
+      w->steps_done = k + 1;
+      if (!more) w->finished = true;
+    }
+    P->cv_parsed.notify_all();
+    if (!more) return;
+  }
+}
+
+struct Out {                             // pictures on their way to the host
+  bool valid = false;
+  std::vector<Placed> pics;
+  size_t per = 0;
+  int idx = 0;
+};
+
+void pipeline_main (Pipeline* P) {
+  lh264_rt* rt = P->rt;
+  const lh264_rt_config& cfg = rt->cfg;
+  const bool want_yuv = cfg.want_yuv != 0, want_hash = want_yuv && cfg.want_hash != 0, want_pip = cfg.want_pip != 0;
+  lh264_ctx* ctx = P->ctx;
+  const int D = (int)P->workers[0]->bufs.size();
+  uint8_t* out_pin[2] = {nullptr, nullptr}; size_t out_cap[2] = {0, 0};
+  std::vector<uint8_t> out_host;
+  std::vector<lh264_picture_desc> descs;
+  std::vector<lh264_model_picture> mdescs;
+  std::vector<int> rd_streams, rd_slots;
+  std::vector<Placed> step;
+  std::vector<const StepBuf*> step_buf;
+  std::vector<long> done_snapshot;
+  Out prev;
+#define FAIL(msg) do { rt->fail (std::string (msg) + ": " + lh264_last_error()); P->rc = -1; goto done; } while (0)
+
+  auto deliver = [&] (const Out& o) {    // pictures of a finished step: SHA-1 + callback
+    const int n = (int)o.pics.size();
+    if (want_hash && n > 0) {
+      const int T = std::min (n, std::max (1, std::min (8, (int)std::thread::hardware_concurrency())));
+      std::atomic<int> next (0);
+      auto job = [&] { for (int i; (i = next.fetch_add (1)) < n;) if (o.pics[i].info.output) rt->streams[o.pics[i].stream]->yuv.update (out_pin[o.idx] + o.per * i, o.per); };
+      if (T <= 1) job();
+      else { std::vector<std::thread> th; for (int t = 0; t < T; t++) th.emplace_back (job); for (auto& t : th) t.join(); }
+    }
+    for (int i = 0; i < n; i++) {
+      Stream& s = *rt->streams[o.pics[i].stream];
+      if (!o.pics[i].info.output) continue;
+      if (P->fn) P->fn (P->user, o.pics[i].stream, s.pictures_output, o.pics[i].info.width, o.pics[i].info.height, out_pin[o.idx] + o.per * i);
+      s.pictures_output++;
+    }
+  };
+
+  for (long k = 0;; k++) {
+    // ---- wait for step k of every parse thread ----
+    bool all_finished = true;
+    {
+      const double t0 = now();
+      std::unique_lock<std::mutex> g (P->mu);
+      P->cv_parsed.wait (g, [&] { for (auto& w : P->workers) if (w->steps_done <= k && !w->finished) return false; return true; });
+      P->t_wait_parse += now() - t0;
+      done_snapshot.clear();
+      for (auto& w : P->workers) { if (!(w->finished && w->steps_done <= k + 1)) all_finished = false; done_snapshot.push_back (w->steps_done); }
+    }
+    step.clear(); step_buf.clear();
+    for (size_t wi = 0; wi < P->workers.size(); wi++) {
+      if (done_snapshot[wi] <= k) continue;
+      StepBuf& b = P->workers[wi]->bufs[k % D];
+      if (b.failed) { rt->fail ("cannot allocate pinned staging memory"); P->rc = LH264_E_NOMEM; goto done; }
+      for (const Placed& pl : b.placed) { step.push_back (pl); step_buf.push_back (&b); }
+    }
+    if (step.empty()) {
+      if (all_finished) break;
+      std::lock_guard<std::mutex> g (P->mu);
+      P->released = k + 1;
+      P->cv_released.notify_all();
+      continue;
+    }
+    // ---- device streams follow the geometry of their stream (SPS change = new picture storage) ----
+    {
+      bool reopen = false;
+      for (const Placed& pl : step) if (rt->streams[pl.stream]->geo_seen != pl.geo_serial) reopen = true;
+      if (reopen) {
+        if (want_yuv) { if (lh264_output_wait (ctx) != LH264_OK) FAIL ("lh264_output_wait"); if (prev.valid) { deliver (prev); prev.valid = false; } }
+        if (lh264_sync (ctx) != LH264_OK) FAIL ("lh264_sync");
+      }
+      for (const Placed& pl : step) {
+        Stream& s = *rt->streams[pl.stream];
+        if (s.geo_seen != pl.geo_serial) {
+          if (s.gpu_stream >= 0) lh264_stream_close (ctx, s.gpu_stream);
+          s.gpu_stream = -1;
+          if (want_yuv) { s.gpu_stream = lh264_stream_open (ctx, pl.mb_w, pl.mb_h, pl.n_slots); if (s.gpu_stream < 0) FAIL ("lh264_stream_open"); }
+          s.geo_seen = pl.geo_serial;
+        }
+        if (want_pip && pl.n_mrecs > 0 && s.model_stream < 0) {
+          // the model's priors live across a change of resolution: opened once, for the largest picture a level allows
+          s.model_mbs = std::max (pl.mb_w * pl.mb_h, 36864);
+          s.model_stream = lh264_model_open (ctx, s.model_mbs, 1);
+          if (s.model_stream < 0) FAIL ("lh264_model_open");
+        }
+      }
+    }
+    // ---- descriptors ----
+    descs.clear(); mdescs.clear(); rd_streams.clear(); rd_slots.clear();
+    {
+      int out_w = 0, out_h = 0, crop_x = 0, crop_y = 0;
+      bool same_geometry = true;
+      for (size_t pi = 0; pi < step.size(); pi++) {
+        const Placed& pl = step[pi];
+        const StepBuf* b = step_buf[pi];
+        Stream& s = *rt->streams[pl.stream];
+        lh264_picture_desc d;
+        d.stream = s.gpu_stream; d.cur_slot = pl.info.slot; d.n_slices = pl.n_slices; d.n_coef_blocks = pl.n_blocks;
+        d.slices = reinterpret_cast<const lh264_slice_rec*> (b->slices.p + pl.o_sl);
+        d.mbs = reinterpret_cast<const lh264_mb_rec*> (b->mbs.p + pl.o_mb);
+        d.coefs = reinterpret_cast<const int16_t*> (b->coefs.p + pl.o_co);
+        if (want_yuv) { descs.push_back (d); P->h2d += (size_t)pl.n_slices * sizeof (lh264_slice_rec) + (size_t)pl.n_mbs * sizeof (lh264_mb_rec); }
+        P->h2d += (size_t)pl.n_blocks * 32;
+        if (want_pip && pl.n_mrecs > 0) {
+          if (pl.mb_w * pl.mb_h > s.model_mbs) { rt->fail ("a stream's picture grew beyond level 5.2"); P->rc = LH264_E_UNSUPPORTED; goto done; }
+          lh264_model_picture m;
+          m.model_stream = s.model_stream; m.mb_w = pl.mb_w; m.mb_h = pl.mb_h; m.n_slices = pl.n_mslices; m.n_recs = pl.n_mrecs; m.n_coef_blocks = pl.n_blocks;
+          m.slices = reinterpret_cast<const lh264_model_slice*> (b->mslices.p + pl.o_msl);
+          m.recs = reinterpret_cast<const lh264_model_mb*> (b->mrecs.p + pl.o_mr);
+          m.coefs = d.coefs;
+          mdescs.push_back (m);
+          P->h2d += (size_t)pl.n_mslices * sizeof (lh264_model_slice) + (size_t)pl.n_mrecs * sizeof (lh264_model_mb);
+        }
+        rd_streams.push_back (s.gpu_stream); rd_slots.push_back (pl.info.slot);
+        if (out_w == 0) { out_w = pl.info.width; out_h = pl.info.height; crop_x = pl.info.crop_x; crop_y = pl.info.crop_y; }
+        else if (out_w != pl.info.width || out_h != pl.info.height || crop_x != pl.info.crop_x || crop_y != pl.info.crop_y) same_geometry = false;
+      }
+      // ---- the device ----
+      if (!descs.empty() && lh264_recon_submit (ctx, descs.data(), (int)descs.size()) != LH264_OK) FAIL ("lh264_recon_submit");
+      if (!mdescs.empty() && lh264_model_submit (ctx, mdescs.data(), (int)mdescs.size()) != LH264_OK) FAIL ("lh264_model_submit");
+      const double tg0 = now();
+      if (want_yuv) {
+        // the pictures of step k - 1 were on their way to the host while step k's records went up: take them now, start this
+        // step's copy, then hash / hand out the previous pictures while it runs
+        if (lh264_output_wait (ctx) != LH264_OK) FAIL ("lh264_output_wait");
+        P->t_wait_gpu += now() - tg0;
+        if (same_geometry) {
+          const size_t per = (size_t)out_w * out_h + 2 * (size_t) ((out_w + 1) / 2) * ((out_h + 1) / 2);
+          const int oi = prev.valid ? prev.idx ^ 1 : 0;
+          if (per * step.size() > out_cap[oi]) {
+            if (out_pin[oi]) lh264_host_free (out_pin[oi]);
+            out_cap[oi] = per * step.size(); out_pin[oi] = (uint8_t*)lh264_host_alloc (out_cap[oi]);
+            if (!out_pin[oi]) { out_cap[oi] = 0; rt->fail ("cannot allocate pinned output memory"); P->rc = LH264_E_NOMEM; goto done; }
+          }
+          if (lh264_pictures_read_packed (ctx, rd_streams.data(), rd_slots.data(), (int)step.size(), crop_x, crop_y, out_w, out_h, out_pin[oi], out_cap[oi], 0) != LH264_OK)
+            FAIL ("lh264_pictures_read_packed");
+          P->d2h += per * step.size();
+          if (prev.valid) deliver (prev);
+          prev.valid = true; prev.pics = step; prev.per = per; prev.idx = oi;
+        } else {                                           // mixed geometry in one step: picture by picture
+          if (prev.valid) { deliver (prev); prev.valid = false; }
+          for (const Placed& pl : step) {
+            Stream& s = *rt->streams[pl.stream];
+            const int w = pl.info.width, h = pl.info.height, cw = (w + 1) / 2, ch = (h + 1) / 2;
+            out_host.resize ((size_t)w * h + 2 * (size_t)cw * ch);
+            uint8_t* y = out_host.data();
+            if (lh264_picture_read (ctx, s.gpu_stream, pl.info.slot, pl.info.crop_x, pl.info.crop_y, w, h, y, w, y + (size_t)w * h, y + (size_t)w * h + (size_t)cw * ch, cw, 1) != LH264_OK)
+              FAIL ("lh264_picture_read");
+            P->d2h += out_host.size();
+            if (!pl.info.output) continue;
+            if (want_hash) s.yuv.update (y, out_host.size());
+            if (P->fn) P->fn (P->user, pl.stream, s.pictures_output, w, h, y);
+            s.pictures_output++;
+          }
+        }
+      }
+      for (const Placed& pl : step) { rt->streams[pl.stream]->pictures++; P->pictures++; }
+      // ---- staging buffer k mod D is free again once its H2D copies are done ----
+      const double tc0 = now();
+      if (lh264_inputs_consumed (ctx) != LH264_OK) FAIL ("lh264_inputs_consumed");
+      P->t_wait_gpu += now() - tc0;
+    }
+    if (P->t_first == 0) { P->t_first = now(); P->first_pictures = (long)step.size(); }
+    {
+      std::lock_guard<std::mutex> g (P->mu);
+      P->released = k + 1;
+    }
+    P->cv_released.notify_all();
+  }
+  if (lh264_sync (ctx) != LH264_OK) FAIL ("lh264_sync");
+  if (prev.valid) { deliver (prev); prev.valid = false; }
+done:
+#undef FAIL
+  P->t_end = now();
+  {
+    std::lock_guard<std::mutex> g (P->mu);
+    P->abort = true;                     // (also the normal end: no parse thread is waiting any more)
+  }
+  P->cv_released.notify_all();
+  for (int k = 0; k < 2; k++) if (out_pin[k]) lh264_host_free (out_pin[k]);
+}
+
+// the `.pip` file set of every stream of a pipeline: default stream (host) + tag side streams (GPU)
+void collect_pip (Pipeline* P) {
+  lh264_rt* rt = P->rt;
+  for (auto& w : P->workers) for (int si : w->streams) {
+    Stream& s = *rt->streams[si];
+    Sha1 h;
+    s.pip_default = s.pip.finish();
+    h.update (s.pip_default.data(), s.pip_default.size());
+    s.pip_bytes = s.pip_default.size();
+    s.pip_tags.assign (LH264_NUM_TAGS, std::vector<uint8_t>());
+    if (s.model_stream >= 0) {
+      if (lh264_model_finish (P->ctx, s.model_stream) != LH264_OK) { rt->fail (std::string ("lh264_model_finish: ") + lh264_last_error()); P->rc = -1; return; }
+      for (int tag = 1; tag < LH264_NUM_TAGS; tag++) {
+        const long long n = lh264_model_read (P->ctx, s.model_stream, tag, nullptr, 0, 0);
+        if (n <= 0) continue;
+        std::vector<uint8_t>& b = s.pip_tags[tag];
+        b.resize ((size_t)n);
+        lh264_model_read (P->ctx, s.model_stream, tag, b.data(), 0, b.size());
+        const uint8_t t8 = (uint8_t)tag;
+        h.update (&t8, 1); h.update (b.data(), b.size());
+        s.pip_bytes += b.size();
+      }
+    }
+    s.pip_hex = h.hex();
+  }
+}
+
+} // namespace
+
+extern "C" {
+
+int lh264_rt_create (lh264_rt** out, const lh264_rt_config* cfg) {
+  if (!out) return LH264_E_INVALID;
+  lh264_rt* rt = new (std::nothrow) lh264_rt();
+  if (!rt) return LH264_E_NOMEM;
+  memset (&rt->cfg, 0, sizeof (rt->cfg));
+  memset (&rt->stats, 0, sizeof (rt->stats));
+  if (cfg) rt->cfg = *cfg;
+  else { rt->cfg.want_yuv = rt->cfg.want_hash = rt->cfg.want_pip = 1; }
+  if (rt->cfg.threads <= 0) rt->cfg.threads = std::max (1, (int)std::thread::hardware_concurrency());
+  if (rt->cfg.pipelines <= 0) rt->cfg.pipelines = 1;
+  if (rt->cfg.loops <= 0) rt->cfg.loops = 1;
+  if (rt->cfg.depth <= 0) rt->cfg.depth = 3;
+  rt->cfg.depth = std::max (2, std::min (rt->cfg.depth, 8));
+  if (!rt->cfg.want_yuv) rt->cfg.want_hash = 0;
+  *out = rt;
+  return LH264_OK;
+}
+
+void lh264_rt_destroy (lh264_rt* rt) { delete rt; }
+
+int lh264_rt_add_stream (lh264_rt* rt, const uint8_t* annexb, size_t len, int trailing_start_code) {
+  if (!rt || (!annexb && len) || rt->ran) return LH264_E_INVALID;
+  std::unique_ptr<Stream> s (new (std::nothrow) Stream());
+  if (!s) return LH264_E_NOMEM;
+  if (trailing_start_code) s->data = annexb;
+  else {
+    static const uint8_t kStart[4] = {0, 0, 0, 1};
+    s->own.assign (annexb, annexb + len);
+    s->own.insert (s->own.end(), kStart, kStart + 4);
+    s->data = s->own.data();
+  }
+  s->size = len;
+  s->loops_left = rt->cfg.loops - 1;
+  s->sink.stream = (int)rt->streams.size();
+  s->dec.reset (new Decoder (&s->sink));
+  s->dec->enable_model (rt->cfg.want_pip != 0);
+  rt->streams.push_back (std::move (s));
+  return (int)rt->streams.size() - 1;
+}
+
+int lh264_rt_run (lh264_rt* rt, lh264_rt_picture_fn fn, void* user) {
+  if (!rt || rt->ran) return LH264_E_INVALID;
+  rt->ran = true;
+  const int S = (int)rt->streams.size();
+  if (S == 0) return LH264_OK;
+  const int G = std::max (1, std::min (rt->cfg.pipelines, S));
+  const int T = std::max (G, std::min (rt->cfg.threads, S));
+  std::vector<std::unique_ptr<Pipeline> > pipes;
+  const double t0 = now();
+  for (int g = 0; g < G; g++) {
+    std::unique_ptr<Pipeline> P (new Pipeline());
+    P->rt = rt; P->index = g; P->fn = fn; P->user = user;
+    if (lh264_ctx_create (&P->ctx, rt->cfg.device, nullptr) != LH264_OK) {
+      rt->fail (std::string ("no usable CUDA device (") + lh264_last_error() + "): this runtime has no CPU fallback");
+      for (auto& q : pipes) lh264_ctx_destroy (q->ctx);
+      return LH264_E_NO_DEVICE;
+    }
+    const int first = (int) ((long long)S * g / G), last = (int) ((long long)S * (g + 1) / G);
+    const int tw = std::max (1, std::min (last - first, T * (g + 1) / G - T * g / G));
+    for (int w = 0; w < tw; w++) {
+      std::unique_ptr<Worker> W (new Worker());
+      W->pl = P.get();
+      W->bufs.resize (rt->cfg.depth);
+      for (int i = first + w; i < last; i += tw) W->streams.push_back (i);
+      P->workers.push_back (std::move (W));
+    }
+    pipes.push_back (std::move (P));
+  }
+  for (auto& P : pipes) {
+    for (auto& w : P->workers) w->th = std::thread (worker_main, w.get());
+    P->th = std::thread (pipeline_main, P.get());
+  }
+  int rc = 0;
+  double t_end = t0;
+  for (auto& P : pipes) {
+    P->th.join();
+    for (auto& w : P->workers) w->th.join();
+    t_end = std::max (t_end, P->t_end);
+    if (P->rc && !rc) rc = P->rc;
+  }
+  lh264_rt_stats& st = rt->stats;
+  st.streams = S; st.threads = 0; st.pipelines = G;
+  st.seconds = t_end - t0;
+  for (auto& P : pipes) {
+    if (!rc && rt->cfg.want_pip) { collect_pip (P.get()); if (P->rc && !rc) rc = P->rc; }
+    st.pictures += P->pictures; st.submit_wait_parse_s += P->t_wait_parse; st.submit_wait_gpu_s += P->t_wait_gpu;
+    st.h2d_bytes += P->h2d; st.d2h_bytes += P->d2h;
+    if (P->t_first > 0) { st.setup_s = std::max (st.setup_s, P->t_first - t0); st.setup_pictures += P->first_pictures; }
+    for (auto& w : P->workers) { st.parse_busy_s += w->busy; st.parse_wait_s += w->wait; st.threads++; }
+    st.kernel_launches += lh264_kernel_launches (P->ctx);
+  }
+  for (auto& sp : rt->streams) {
+    Stream& s = *sp;
+    st.input_bytes += s.size * (size_t)rt->cfg.loops;
+    st.pip_bytes += s.pip_bytes;
+    if (rt->cfg.want_hash) s.yuv_hex = s.yuv.hex();
+  }
+  for (auto& P : pipes) {
+    for (auto& w : P->workers) for (int si : w->streams) {
+      Stream& s = *rt->streams[si];
+      if (s.model_stream >= 0) lh264_model_close (P->ctx, s.model_stream);
+      if (s.gpu_stream >= 0) lh264_stream_close (P->ctx, s.gpu_stream);
+      s.dec.reset();
+    }
+    lh264_ctx_destroy (P->ctx);
+  }
+  st.seconds_total = now() - t0;
+  return rc;
+}
+
+int lh264_rt_stream_result_get (const lh264_rt* rt, int stream, lh264_rt_stream_result* out) {
+  if (!rt || !out || stream < 0 || stream >= (int)rt->streams.size()) return LH264_E_INVALID;
+  const Stream& s = *rt->streams[stream];
+  memset (out, 0, sizeof (*out));
+  out->pictures = s.pictures; out->pictures_output = s.pictures_output;
+  snprintf (out->yuv_sha1, sizeof (out->yuv_sha1), "%s", s.yuv_hex.c_str());
+  snprintf (out->pip_sha1, sizeof (out->pip_sha1), "%s", s.pip_hex.c_str());
+  out->pip_bytes = s.pip_bytes; out->error = s.last_error;
+  return LH264_OK;
+}
+
+long long lh264_rt_pip_read (const lh264_rt* rt, int stream, int tag, uint8_t* dst, size_t cap) {
+  if (!rt || stream < 0 || stream >= (int)rt->streams.size() || tag < 0 || tag >= LH264_NUM_TAGS) return LH264_E_INVALID;
+  const Stream& s = *rt->streams[stream];
+  const std::vector<uint8_t>* b = tag == 0 ? &s.pip_default : (tag < (int)s.pip_tags.size() ? &s.pip_tags[tag] : nullptr);
+  if (!b) return 0;
+  if (dst && cap) memcpy (dst, b->data(), std::min (cap, b->size()));
+  return (long long)b->size();
+}
+
+int lh264_rt_stats_get (const lh264_rt* rt, lh264_rt_stats* out) {
+  if (!rt || !out) return LH264_E_INVALID;
+  *out = rt->stats;
+  return LH264_OK;
+}
+
+const char* lh264_rt_last_error (const lh264_rt* rt) { return rt ? rt->error.c_str() : "no runtime"; }
+
+} // extern "C"

@@ -8,6 +8,7 @@
 #include "../../losslessh264_b200/csrc/model_kernels.cuh"
 #include "../../losslessh264_b200/host/decoder.h"
 #include "../../losslessh264_b200/host/pip_container.h"
+#include "model_emu_core.h"
 #include <string>
 #include <vector>
 
@@ -18,87 +19,24 @@ class ModelEmuSink : public PictureSink {
  public:
   int configure (int, int, int) override { return 0; }
   int submit (const lh264_picture_desc&, const DecodedPictureInfo&) override { return 0; }
-  int submit_model (const lh264_model_picture& pic, const DecodedPictureInfo&) override {
-    if (!open_) {                                     // = lh264_model_open (model_host.inl), level-5.2 sized like the API sink
-      max_mbs_ = 36864;
-      priors_.assign (P_END, 0u);
-      frames_.assign ((size_t)3 * max_mbs_, CtxRec());
-      memset (frames_.data(), 0, frames_.size() * sizeof (CtxRec));
-      order_.assign (max_mbs_, 0);
-      pagelist_.assign ((size_t)CT_COUNT * MAX_PAGES_PER_TAG, 0u);
-      memset (&st_, 0, sizeof (st_));
-      st_.priors = priors_.data(); st_.frame[0] = frames_.data(); st_.frame[1] = frames_.data() + max_mbs_; st_.newrec = frames_.data() + 2 * (size_t)max_mbs_;
-      st_.order = order_.data(); st_.pagelist = pagelist_.data(); st_.max_mbs = max_mbs_;
-      MState* st = &st_;
-      emu::launch (1, 1, 32, [&] { k_model_init_state (st); });
-      open_ = true;
-    }
-    if (pic.mb_w * pic.mb_h > max_mbs_) return -1;
-    MPicDev d;
-    memset (&d, 0, sizeof (d));
-    std::vector<uint32_t> rec_cnt (pic.n_recs, 0u), rec_off (pic.n_recs, 0u);
-    d.recs = pic.recs; d.slices = pic.slices; d.coefs = pic.coefs; d.st = &st_;
-    d.rec_cnt = rec_cnt.data(); d.rec_off = rec_off.data();
-    d.n_recs = pic.n_recs; d.n_slices = pic.n_slices; d.mb_w = pic.mb_w; d.mb_h = pic.mb_h; d.rec_base = 0;
-    const MPicDev* pd = &d;
-    unsigned int poison = 0;
-    uint32_t pic_total = 0;
-    unsigned long long dec_base = 0;
-    BatchCtl ctl;
-    memset (&ctl, 0, sizeof (ctl));
-    const int total_recs = pic.n_recs, blocks = (total_recs + GEN_THREADS - 1) / GEN_THREADS;
-    const size_t gen_smem = (size_t)GEN_THREADS * sizeof (ThreadMb);
-    emu::launch (1, 1, 32, [&] { k_model_frame (pd, 1, &poison); });
-    emu::launch ((unsigned)blocks, 1, GEN_THREADS, [&] { k_model_count (pd, 1, total_recs, &poison); }, gen_smem);
-    emu::launch (1, 1, 1024, [&] { k_model_scan (pd, 1, &pic_total, &poison); });
-    for (int attempt = 0; attempt < 2; attempt++) {
-      ArenaDev ar{ page_ptrs_.data(), &next_, (unsigned int)page_ptrs_.size() };
-      emu::launch (1, 1, 1024, [&] { k_model_plan (1, &pic_total, &dec_base, &ctl, (unsigned long long)dec_.size(), ar, &poison); });
-      if (!ctl.skip) break;
-      poison = 0;                                     // grow and plan again (model_complete, model_host.inl)
-      if (ctl.total + 32 > dec_.size()) dec_.assign ((size_t)ctl.total + ctl.total / 4 + 64, 0u);
-      while (page_ptrs_.size() < (size_t)ctl.pages_in_use + 2 * ctl.pages_needed) { pages_.emplace_back (PAGE_SIZE, 0); page_ptrs_.push_back (pages_.back().data()); }
-    }
-    if (ctl.skip) return -2;
-    ArenaDev ar{ page_ptrs_.data(), &next_, (unsigned int)page_ptrs_.size() };
-    uint32_t* dec = dec_.data();
-    emu::launch ((unsigned)blocks, 1, GEN_THREADS, [&] { k_model_emit (pd, 1, total_recs, dec, &dec_base, &ctl); }, gen_smem);
-    emu::launch (1, 1, 64, [&] { k_model_code (pd, 1, dec, &dec_base, &pic_total, ar, &ctl); });
-    return st_.error ? -3 : 0;
-  }
+  int submit_model (const lh264_model_picture& pic, const DecodedPictureInfo&) override { return m_.submit (pic); }
   // = lh264_model_finish + lh264_model_read for every tag
   int finish (const std::string& pip) {
-    if (!open_) return 0;
-    while (page_ptrs_.size() < (size_t)next_ + CT_COUNT) { pages_.emplace_back (PAGE_SIZE, 0); page_ptrs_.push_back (pages_.back().data()); }
-    ArenaDev ar{ page_ptrs_.data(), &next_, (unsigned int)page_ptrs_.size() };
-    MState* st = &st_;
-    emu::launch (1, 1, 32, [&] { k_model_finish (st, ar); });
-    if (st_.error) return st_.error;
-    for (int ct = 0; ct < CT_COUNT; ct++) {
-      if (! ((st_.used >> ct) & 1u)) continue;
-      FILE* f = fopen ((pip + "." + std::to_string (kTagOfCompact[ct])).c_str(), "wb");
+    const int rc = m_.finish();
+    if (rc) return rc;
+    std::vector<uint8_t> b;
+    for (int tag = 1; tag < LH264_NUM_TAGS; tag++) {
+      if (!m_.tag_bytes (tag, b)) return -4;
+      if (b.empty()) continue;
+      FILE* f = fopen ((pip + "." + std::to_string (tag)).c_str(), "wb");
       if (!f) return -1;
-      for (uint32_t at = 0; at < st_.coder[ct].pos;) {
-        const uint32_t idx = pagelist_[(size_t)ct * MAX_PAGES_PER_TAG + (at >> PAGE_SHIFT)];
-        const uint32_t nb = std::min<uint32_t> (PAGE_SIZE - (at & (PAGE_SIZE - 1)), st_.coder[ct].pos - at);
-        if (idx == 0) { fclose (f); return -4; }
-        fwrite (page_ptrs_[idx - 1] + (at & (PAGE_SIZE - 1)), 1, nb, f);
-        at += nb;
-      }
+      fwrite (b.data(), 1, b.size(), f);
       fclose (f);
     }
     return 0;
   }
  private:
-  bool open_ = false;
-  int max_mbs_ = 0;
-  MState st_;
-  std::vector<uint32_t> priors_, pagelist_, dec_;
-  std::vector<CtxRec> frames_;
-  std::vector<int> order_;
-  std::vector<std::vector<uint8_t> > pages_;
-  std::vector<uint8_t*> page_ptrs_;
-  unsigned int next_ = 0;
+  ModelEmu m_;
 };
 
 int main (int argc, char** argv) {

@@ -44,6 +44,25 @@ def test_openh264_api_library_exports_decoder_symbols():
         assert hasattr(lib, n), f"{n} is declared in include/lh264_codec_api.h but not exported"
 
 
+def test_runtime_entry_points_are_exported():
+    """include/lh264_runtime.h: the multi-stream runtime lives behind the library boundary (libopenh264_lh264.so)."""
+    import subprocess
+
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "losslessh264_b200", "host")])
+    lib = C.CDLL(os.path.join(ROOT, "losslessh264_b200", "_lib", "libopenh264_lh264.so"))
+    src = open(os.path.join(ROOT, "include", "lh264_runtime.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    names = sorted(set(re.findall(r"\b(lh264_rt_[a-z0-9_]+)\s*\(", src)) - {"lh264_rt_picture_fn"})
+    assert names == ["lh264_rt_add_stream", "lh264_rt_create", "lh264_rt_destroy", "lh264_rt_last_error", "lh264_rt_pip_read", "lh264_rt_run",
+                     "lh264_rt_stats_get", "lh264_rt_stream_result_get"]
+    for n in names:
+        assert hasattr(lib, n), f"{n} is declared in include/lh264_runtime.h but not exported"
+    # the ctypes mirror of the structs has the C layout
+    from losslessh264_b200.runtime import RtConfig, RtStats, RtStreamResult
+
+    assert C.sizeof(RtConfig) == 64 and C.sizeof(RtStreamResult) == 2 * 8 + 82 + 6 + 8 + 8 and C.sizeof(RtStats) == 16 * 8
+
+
 def test_record_layouts():
     assert MB_REC.itemsize == 128 and MODEL_MB.itemsize == 128 and MODEL_SLICE.itemsize == 20
     assert SLICE_REC.itemsize == 16 + 2 * 16 * 7
