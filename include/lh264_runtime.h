@@ -70,6 +70,8 @@ typedef struct lh264_rt_stats {
   double setup_s;              /* start of the run until step 0 (one picture per stream) has been handed to the device:
                                   opening every device stream and model stream happens here                                */
   long   setup_pictures;       /* pictures of step 0                                                                       */
+  double pinned_alloc_s;       /* parse threads: time spent growing pinned staging memory (summed; part of parse_busy_s)   */
+  double open_streams_s;       /* submit threads: time spent opening device streams and model streams                      */
   int32_t threads, pipelines;
 } lh264_rt_stats;
 

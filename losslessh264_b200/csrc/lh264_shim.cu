@@ -562,6 +562,7 @@ int lh264_k_expand_plane (lh264_ctx* c, const uint8_t* in, int w, int h, int pad
 static float model_ms (lh264_ctx* c, int which, bool reset) {
   ModelCtx* m = static_cast<ModelCtx*> (c->model);
   if (!m) return 0.f;
+  model_flush_coder (c, m);                           // steps still waiting for the coder are coded now (timed if timing is on)
   if (reset) { m->ms_gen = m->ms_code = 0.f; return 0.f; }
   return which == 0 ? m->ms_gen : m->ms_code;
 }

@@ -50,7 +50,17 @@ struct ModelCtx {
   std::vector<MBatch*> inflight;   // launched batches whose totals the host has not read yet, oldest first (at most 2)
   unsigned int* d_poison = nullptr;  // set by a batch that skipped its coding: later batches skip entirely (model_settle)
   cudaStream_t aux = nullptr;      // small D2H reads that must not queue behind running model kernels
-  DevBuf<uint32_t> dec;            // decision list of the batch being coded
+  DevBuf<uint32_t> dec;            // decision pool: the lists of the steps generated and not yet coded, back to back
+  // deferred coding (model_kernels.cuh CodeJob): up to code_steps steps are generated before ONE k_model_code launch codes them
+  int code_steps = 16;             // LH264_CODE_STEPS
+  size_t dec_cap_limit = 0;        // decisions the pool may grow to for the sake of deferral (a single step may exceed it)
+  DevBuf<CodeJob> jobs; int job_stride = 0;        // [code_steps][job_stride]
+  int pend_steps = 0;
+  std::vector<std::vector<int> > pend_streams;     // model stream of every job of a pending step
+  std::vector<int> slot_of;                        // scratch: model stream -> block of the coder launch
+  unsigned long long* d_pool_used = nullptr; unsigned int* d_pages_pending = nullptr;
+  DevBuf<int> job_index; PinBuf<int> h_index[2]; cudaEvent_t index_copied[2] = {nullptr, nullptr}; int index_cur = 0;
+  unsigned long long est_pool_used = 0, last_step_total = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float ms_gen = 0, ms_code = 0;
   // The model runs on its own CUDA stream: it consumes syntax elements, not samples, so the model of picture t overlaps
@@ -80,6 +90,20 @@ static ModelCtx* model_ctx (lh264_ctx* c) {
     cudaFuncSetAttribute (k_model_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (GEN_THREADS * sizeof (ThreadMb)));
     cudaFuncSetAttribute (k_model_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (GEN_THREADS * sizeof (ThreadMb)));
     cudaEventCreateWithFlags (&m->done, cudaEventDisableTiming);
+    cudaMalloc (&m->d_pool_used, sizeof (unsigned long long));
+    cudaMalloc (&m->d_pages_pending, sizeof (unsigned int));
+    cudaMemset (m->d_pool_used, 0, sizeof (unsigned long long));
+    cudaMemset (m->d_pages_pending, 0, sizeof (unsigned int));
+    for (int k = 0; k < 2; k++) cudaEventCreateWithFlags (&m->index_copied[k], cudaEventDisableTiming);
+    if (const char* e = getenv ("LH264_CODE_STEPS")) m->code_steps = std::max (1, std::min (atoi (e), 64));
+    {
+      size_t free_b = 0, total_b = 0;
+      cudaMemGetInfo (&free_b, &total_b);
+      size_t limit_mb = 24576;                       // LH264_DEC_POOL_MB: memory the decision pool may take for deferral
+      if (const char* e = getenv ("LH264_DEC_POOL_MB")) limit_mb = (size_t)std::max (1, atoi (e));
+      m->dec_cap_limit = std::min (limit_mb << 20, free_b / 4) / sizeof (uint32_t);
+    }
+    m->pend_streams.resize (m->code_steps);
     c->model = m;
   }
   return static_cast<ModelCtx*> (c->model);
@@ -102,7 +126,10 @@ static void model_destroy (lh264_ctx* c) {
   if (m->d_page_ptrs) cudaFree (m->d_page_ptrs);
   if (m->d_next) cudaFree (m->d_next);
   m->batch[0].release(); m->batch[1].release();
-  m->dec.release();
+  m->dec.release(); m->jobs.release(); m->job_index.release(); m->h_index[0].release(); m->h_index[1].release();
+  if (m->d_pool_used) cudaFree (m->d_pool_used);
+  if (m->d_pages_pending) cudaFree (m->d_pages_pending);
+  for (int k = 0; k < 2; k++) if (m->index_copied[k]) cudaEventDestroy (m->index_copied[k]);
   if (m->d_poison) cudaFree (m->d_poison);
   if (m->aux) cudaStreamDestroy (m->aux);
   for (int i = 0; i < 4; i++) if (m->ev[i]) cudaEventDestroy (m->ev[i]);
@@ -138,6 +165,7 @@ extern "C" {
 
 static int model_settle (lh264_ctx* c, ModelCtx* m);
 static int model_settle_batch (lh264_ctx* c, ModelCtx* m, MBatch* only);
+static int model_flush_coder (lh264_ctx* c, ModelCtx* m);
 
 int lh264_model_open (lh264_ctx* c, int max_mbs, int with_8x8) {
   if (!c || max_mbs <= 0 || max_mbs > (1 << 20)) return fail (LH264_E_INVALID, "bad model stream geometry");
@@ -181,6 +209,9 @@ int lh264_model_close (lh264_ctx* c, int ms) {
   if (rc) return rc;
   CK (cudaSetDevice (c->device));
   { int rs = model_settle (c, m); if (rs) return rs; }
+  // pending jobs name the stream's state, and a coder launch may still be working on it
+  if ((rc = model_flush_coder (c, m))) return rc;
+  CK (cudaStreamSynchronize (m->stream));
   // the stream's output pages stay in the arena until the context is destroyed (bump allocator)
   model_free_stream (m->streams[ms]);
   return LH264_OK;
@@ -248,11 +279,55 @@ static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_
   return LH264_OK;
 }
 
+// Codes every pending step with ONE launch: block b = one model stream, walking its pictures in step order.
+static int model_flush_coder (lh264_ctx* c, ModelCtx* m) {
+  const int T = m->pend_steps;
+  if (T == 0) return LH264_OK;
+  m->slot_of.assign (m->streams.size(), -1);
+  int nb = 0;
+  for (int j = 0; j < T; j++) for (int s : m->pend_streams[j]) if (m->slot_of[s] < 0) m->slot_of[s] = nb++;
+  const size_t n_idx = (size_t)nb * T;
+  const int k = (m->index_cur ^= 1);
+  CK (cudaEventSynchronize (m->index_copied[k]));      // (the copy of two flushes ago: long done)
+  CK (m->h_index[k].reserve (n_idx)); CK (m->job_index.reserve (n_idx));
+  for (size_t i = 0; i < n_idx; i++) m->h_index[k].p[i] = -1;
+  for (int j = 0; j < T; j++) for (size_t i = 0; i < m->pend_streams[j].size(); i++) m->h_index[k].p[(size_t)m->slot_of[m->pend_streams[j][i]] * T + j] = (int)i;
+  CK (cudaMemcpyAsync (m->job_index.p, m->h_index[k].p, n_idx * sizeof (int), cudaMemcpyHostToDevice, m->stream));
+  CK (cudaEventRecord (m->index_copied[k], m->stream));
+  ArenaDev ar{ m->d_page_ptrs, m->d_next, m->n_pages };
+  if (c->timing) CK (cudaEventRecord (m->ev[2], m->stream));
+  k_model_code<<<nb, 64, 0, m->stream>>> (m->jobs.p, m->job_index.p, T, m->job_stride, m->dec.p, ar);
+  c->launches++;
+  CK (cudaMemsetAsync (m->d_pool_used, 0, sizeof (unsigned long long), m->stream));
+  CK (cudaMemsetAsync (m->d_pages_pending, 0, sizeof (unsigned int), m->stream));
+  m->pend_steps = 0; m->est_pool_used = 0;
+  if (c->timing) {
+    CK (cudaEventRecord (m->ev[3], m->stream));
+    CK (cudaEventSynchronize (m->ev[3]));
+    float t = 0;
+    cudaEventElapsedTime (&t, m->ev[2], m->ev[3]); m->ms_code += t;
+  }
+  CK (cudaGetLastError());
+  return LH264_OK;
+}
+
+// The generation launches of one step (one picture per stream): its decisions go into the pool, its jobs into row pend_steps.
 static int model_launch (lh264_ctx* c, ModelCtx* m, MBatch& b, bool head, bool timed) {
   const int n = b.n, total_recs = b.total_recs;
   const int mb_blocks = (total_recs + GEN_THREADS - 1) / GEN_THREADS;
   const size_t gen_smem = (size_t)GEN_THREADS * sizeof (ThreadMb);
+  if (m->pend_steps >= m->code_steps) { int rc = model_flush_coder (c, m); if (rc) return rc; }
+  if (n > m->job_stride) {                            // a wider step than any before: the job table is re-laid
+    int rc = model_flush_coder (c, m);
+    if (rc) return rc;
+    CK (cudaStreamSynchronize (m->stream));
+    m->job_stride = n + n / 4 + 16;
+    CK (m->jobs.reserve ((size_t)m->job_stride * m->code_steps));
+  }
   ArenaDev ar{ m->d_page_ptrs, m->d_next, m->n_pages };
+  PoolDev pool{ m->d_pool_used, m->d_pages_pending };
+  CodeJob* row = m->jobs.p + (size_t)m->pend_steps * m->job_stride;
+  CK (cudaMemsetAsync (row, 0, (size_t)n * sizeof (CodeJob), m->stream));       // st == nullptr: a step that skips leaves no jobs
   if (head) {
     if (timed) CK (cudaEventRecord (m->ev[0], m->stream));
     k_model_frame<<<n, 32, 0, m->stream>>> (b.pics.p, n, m->d_poison);
@@ -260,13 +335,26 @@ static int model_launch (lh264_ctx* c, ModelCtx* m, MBatch& b, bool head, bool t
     k_model_scan<<<n, 1024, 0, m->stream>>> (b.pics.p, n, b.pic_total.p, m->d_poison);
     c->launches += 3;
   }
-  k_model_plan<<<1, 1024, 0, m->stream>>> (n, b.pic_total.p, b.dec_base.p, b.ctl.p, (unsigned long long)m->dec.cap, ar, m->d_poison);
+  k_model_plan<<<1, 1024, 0, m->stream>>> (n, b.pic_total.p, b.dec_base.p, b.ctl.p, (unsigned long long)m->dec.cap, ar, pool, m->d_poison);
   k_model_emit<<<mb_blocks, GEN_THREADS, gen_smem, m->stream>>> (b.pics.p, n, total_recs, m->dec.p, b.dec_base.p, b.ctl.p);
-  if (timed) { CK (cudaEventRecord (m->ev[1], m->stream)); CK (cudaEventRecord (m->ev[2], m->stream)); }
-  k_model_code<<<n, 64, 0, m->stream>>> (b.pics.p, n, m->dec.p, b.dec_base.p, b.pic_total.p, ar, b.ctl.p);
+  k_model_commit<<<n, 128, 0, m->stream>>> (b.pics.p, n, b.dec_base.p, b.pic_total.p, b.ctl.p, row);
   c->launches += 3;
+  if (timed) CK (cudaEventRecord (m->ev[1], m->stream));
+  m->pend_streams[m->pend_steps] = b.stream_of;
+  m->pend_steps++;
+  m->est_pool_used += m->last_step_total;
   if (!b.done) CK (cudaEventCreateWithFlags (&b.done, cudaEventDisableTiming));
   CK (cudaEventRecord (b.done, m->stream));
+  return LH264_OK;
+}
+
+// The pool must hold one step of `step_total` decisions; for the sake of deferral it is given room for code_steps such steps
+// as long as that stays below dec_cap_limit.  Call with the pool empty (after model_flush_coder).
+static int model_grow_pool (lh264_ctx* c, ModelCtx* m, unsigned long long step_total) {
+  (void)c;
+  const size_t one = (size_t)step_total + (size_t)step_total / 4 + 64;
+  const size_t want = std::max (one, std::min (one * (size_t)m->code_steps, m->dec_cap_limit));
+  if (want > m->dec.cap) { CK (cudaStreamSynchronize (m->stream)); CK (m->dec.reserve (want)); }
   return LH264_OK;
 }
 
@@ -282,14 +370,17 @@ static int model_complete (lh264_ctx* c, ModelCtx* m, MBatch& b, bool head) {
     if (!ctl.skip) return LH264_OK;
     head = false;                                   // frame / count / scan did run: the batch itself was the one that did not fit
     CK (cudaMemsetAsync (m->d_poison, 0, sizeof (unsigned int), m->stream));
-    if (ctl.total + 32 > m->dec.cap) CK (m->dec.reserve ((size_t)ctl.total + ctl.total / 4 + 64));
+    if ((rc = model_flush_coder (c, m))) return rc;  // empties the pool (the step that skipped left no jobs)
+    if ((rc = model_grow_pool (c, m, ctl.total))) return rc;
     if ((rc = model_grow_arena (c, m, ctl.pages_in_use + 2 * ctl.pages_needed))) return rc;
   }
   return fail (LH264_E_NOMEM, "model batch does not fit after growing its buffers");
 }
 
 static void model_account (ModelCtx* m, MBatch& b) {
-  for (int i = 0; i < b.n; i++) if (m->streams[b.stream_of[i]].open) m->streams[b.stream_of[i]].decisions += b.h_total.p[i];
+  unsigned long long tot = 0;
+  for (int i = 0; i < b.n; i++) { tot += b.h_total.p[i]; if (m->streams[b.stream_of[i]].open) m->streams[b.stream_of[i]].decisions += b.h_total.p[i]; }
+  m->last_step_total = tot;
 }
 
 // Reads back what a launched batch reported (decision totals, capacity verdict); `only` = settle up to and including that
@@ -312,9 +403,10 @@ static int model_settle_batch (lh264_ctx* c, ModelCtx* m, MBatch* only) {
       CK (cudaMemsetAsync (m->d_poison, 0, sizeof (unsigned int), m->stream));
       {                                              // what the first one needs is known; later ones report when they run
         const BatchCtl ctl = *b.h_ctl.p;
-        if (ctl.total + 32 > m->dec.cap) CK (m->dec.reserve ((size_t)ctl.total + ctl.total / 4 + 64));
-        int rc = model_grow_arena (c, m, ctl.pages_in_use + 2 * ctl.pages_needed);
+        int rc = model_flush_coder (c, m);           // the steps generated before it are coded; the pool is empty again
         if (rc) return rc;
+        if ((rc = model_grow_pool (c, m, ctl.total))) return rc;
+        if ((rc = model_grow_arena (c, m, ctl.pages_in_use + 2 * ctl.pages_needed))) return rc;
       }
       for (MBatch* r : redo) {
         int rc = model_complete (c, m, *r, head);
@@ -343,15 +435,15 @@ static int model_run (lh264_ctx* c, ModelCtx* m, MBatch& b) {
   while (m->inflight.size() >= 2) if ((rc = model_settle_batch (c, m, m->inflight.front()))) return rc;
   for (int i = 0; i < n; i++) if (!m->streams[b.stream_of[i]].open) return fail (LH264_E_INVALID, "batch names a closed model stream");
   if (!m->d_page_ptrs && (rc = model_grow_arena (c, m, (unsigned int)n * CT_COUNT + 64))) return rc;
-  if (!m->dec.p) CK (m->dec.reserve ((size_t)b.total_recs * 96 + 1024));    // first guess; model_settle grows it when needed
+  if (!m->dec.p && (rc = model_grow_pool (c, m, (unsigned long long)b.total_recs * 96 + 1024))) return rc;   // first guess; model_settle grows it when needed
+  // a step about as large as the last one would not fit behind the pending ones: code those first (saves a skip + re-run)
+  if (m->pend_steps > 0 && m->est_pool_used + m->last_step_total + m->last_step_total / 2 + 64 > m->dec.cap && (rc = model_flush_coder (c, m))) return rc;
   if ((rc = model_launch (c, m, b, true, c->timing))) return rc;
   b.pending = true; m->inflight.push_back (&b);
   if (c->timing) {
-    CK (cudaEventRecord (m->ev[3], m->stream));
-    CK (cudaEventSynchronize (m->ev[3]));
+    CK (cudaEventSynchronize (m->ev[1]));
     float t = 0;
     cudaEventElapsedTime (&t, m->ev[0], m->ev[1]); m->ms_gen += t;
-    cudaEventElapsedTime (&t, m->ev[2], m->ev[3]); m->ms_code += t;
     if ((rc = model_settle (c, m))) return rc;     // (a retry after growth is not part of the timed figures)
   }
   CK (cudaEventRecord (m->done, m->stream));
@@ -405,6 +497,7 @@ void lh264_model_batch_free (lh264_ctx* c, lh264_model_batch* b) {
 static int model_check_error (lh264_ctx* c, MStreamHost& s) {
   ModelCtx* m = static_cast<ModelCtx*> (c->model);
   { int rs = model_settle (c, m); if (rs) return rs; }
+  { int rs = model_flush_coder (c, m); if (rs) return rs; }
   int err = 0;
   CK (cudaMemcpyAsync (&err, &s.d_state->error, sizeof (int), cudaMemcpyDeviceToHost, m->stream));
   CK (cudaStreamSynchronize (m->stream));
@@ -420,6 +513,7 @@ int lh264_model_finish (lh264_ctx* c, int ms) {
   if (rc) return rc;
   CK (cudaSetDevice (c->device));
   if ((rc = model_settle (c, m))) return rc;
+  if ((rc = model_flush_coder (c, m))) return rc;
   unsigned int used = 0;
   if (m->d_next) { CK (cudaMemcpyAsync (&used, m->d_next, sizeof (used), cudaMemcpyDeviceToHost, m->stream)); CK (cudaStreamSynchronize (m->stream)); }
   if ((rc = model_grow_arena (c, m, used + CT_COUNT))) return rc;
@@ -473,7 +567,8 @@ unsigned long long lh264_model_decisions (lh264_ctx* c, int ms) {
 
 static cudaError_t model_sync (lh264_ctx* c) {
   ModelCtx* m = static_cast<ModelCtx*> (c->model);
-  if (m && !m->inflight.empty()) return model_settle (c, m) == LH264_OK ? cudaSuccess : cudaErrorUnknown;
+  if (m && !m->inflight.empty() && model_settle (c, m) != LH264_OK) return cudaErrorUnknown;
+  if (m && model_flush_coder (c, m) != LH264_OK) return cudaErrorUnknown;
   return m && m->stream ? cudaStreamSynchronize (m->stream) : cudaSuccess;
 }
 
@@ -481,6 +576,7 @@ static cudaError_t model_sync (lh264_ctx* c) {
 static cudaError_t model_join (lh264_ctx* c) {
   ModelCtx* m = static_cast<ModelCtx*> (c->model);
   if (!m || !m->stream) return cudaSuccess;
+  if (model_flush_coder (c, m) != LH264_OK) return cudaErrorUnknown;
   cudaError_t e = cudaEventRecord (m->done, m->stream);
   return e != cudaSuccess ? e : cudaStreamWaitEvent (c->stream, m->done, 0);
 }

@@ -80,9 +80,17 @@ struct MPicDev {                      // one picture of the batch
 
 struct ArenaDev { uint8_t** page_ptrs; unsigned int* next; unsigned int n_pages; };
 
+// Coding is DEFERRED: the generation kernels of a step (one picture per stream) append the step's decisions to a pool and leave
+// one CodeJob per picture; k_model_code later codes the jobs of up to T steps in ONE launch, the block of a stream walking that
+// stream's pictures in step order.  (With one launch per step the slowest picture of the step - an I picture among P pictures -
+// set the step's time while every other stream's coder sat idle: streams whose I pictures fall in different steps now overlap.)
+struct CodeJob { MState* st; unsigned long long base; uint32_t n; uint32_t pad; };   // st == nullptr: nothing to code
+struct PoolDev { unsigned long long* used; unsigned int* pages_pending; };             // decisions in the pool; output pages promised to pending jobs
+
 // Written by k_model_plan, read by the host when it next touches the batch.  `skip` makes k_model_emit / k_model_code return
 // without touching any state, so that the host can grow what was too small and run the two kernels again.
-struct BatchCtl { unsigned long long total; unsigned int skip /* 1 too small, 2 behind a skipped batch */; unsigned int pages_needed; unsigned int pages_in_use; unsigned int pad; };
+struct BatchCtl { unsigned long long total; unsigned int skip /* 1 too small, 2 behind a skipped batch */; unsigned int pages_needed; unsigned int pages_in_use; unsigned int pad;
+                  unsigned long long pool_base /* position of the step's decisions in the pool */; };
 
 // ---- binarisation: identical decision sequences to the reference, prior = index into the table ---------
 template <bool W> struct Em {
@@ -588,12 +596,12 @@ __global__ void __launch_bounds__ (1024) k_model_scan (const MPicDev* pics, int 
 // ---- k_model_plan: one block; positions of the pictures in the decision list, and the capacity checks the host used to
 // make between two launches (it no longer waits in the middle of a submit) ------------------------------------------
 __global__ void __launch_bounds__ (1024) k_model_plan (int n_pics, const uint32_t* pic_total, unsigned long long* dec_base, BatchCtl* ctl,
-                                                       unsigned long long dec_capacity, ArenaDev ar, unsigned int* poison) {
+                                                       unsigned long long dec_capacity, ArenaDev ar, PoolDev pool, unsigned int* poison) {
   __shared__ unsigned long long wsum[32];
   __shared__ unsigned long long carry_s;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   // an earlier batch skipped its coding: nothing of this one has run (every kernel checks), the host runs both again in order
-  if (*poison) { if (tid == 0) { ctl->skip = 2; ctl->total = 0; ctl->pages_needed = 0; ctl->pages_in_use = *ar.next; } return; }
+  if (*poison) { if (tid == 0) { ctl->skip = 2; ctl->total = 0; ctl->pages_needed = 0; ctl->pages_in_use = *ar.next; ctl->pool_base = *pool.used; } return; }
   if (tid == 0) carry_s = 0;
   __syncthreads();
   for (int base = 0; base < n_pics; base += 1024) {
@@ -621,10 +629,13 @@ __global__ void __launch_bounds__ (1024) k_model_plan (int n_pics, const uint32_
     const unsigned long long total = carry_s;
     // every decision shifts out at most 7 bits, and a tag needs at most one partly filled page more than its bytes
     const unsigned long long pages = total * 7 / 8 / PAGE_SIZE + (unsigned long long)n_pics * CT_COUNT + 1;
-    const unsigned int in_use = *ar.next;
-    ctl->total = total; ctl->pages_needed = (unsigned int)min (pages, 0xffffffffull); ctl->pages_in_use = in_use;
-    ctl->skip = (total + 32 > dec_capacity || in_use + pages > ar.n_pages) ? 1u : 0u;
+    // pages already promised to steps that are generated but not coded yet count as in use
+    const unsigned int in_use = *ar.next + *pool.pages_pending;
+    const unsigned long long base = *pool.used;
+    ctl->total = total; ctl->pages_needed = (unsigned int)min (pages, 0xffffffffull); ctl->pages_in_use = in_use; ctl->pool_base = base;
+    ctl->skip = (base + total + 32 > dec_capacity || in_use + pages > ar.n_pages) ? 1u : 0u;
     if (ctl->skip) *poison = 1u;
+    else { *pool.used = base + total; *pool.pages_pending += (unsigned int)min (pages, 0xffffffffull); }
   }
 }
 
@@ -658,7 +669,7 @@ __global__ void __launch_bounds__ (GEN_THREADS) k_model_emit (const MPicDev* pic
     t.m.flagsLAP = (t.m.L.flags & 1u) | ((t.m.A.flags & 1u) << 1) | ((t.m.P.flags & 1u) << 2);
   }
   Em<true> e;
-  e.out = dec + dec_base[p] + pic.rec_off[ri];
+  e.out = dec + ctl->pool_base + dec_base[p] + pic.rec_off[ri];
   e.n = 0;
   int err = 0;
   const bool last = ri == sl.first_rec + sl.n_recs - 1;
@@ -741,24 +752,52 @@ struct CodeShared {
   volatile uint32_t prod[32];               // entries ever appended to ring t (producer writes)
   volatile uint32_t cons[32];               // entries consumed from ring t (consumer lane t writes)
   volatile int done;
+  volatile int skip;
 };
 
-__global__ void __launch_bounds__ (64) k_model_code (const MPicDev* pics, int n_pics, const uint32_t* dec, const unsigned long long* dec_base,
-                                                     const uint32_t* pic_total, ArenaDev ar, const BatchCtl* ctl) {
-  __shared__ CodeShared sh;
-  const int p = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// ---- k_model_commit: end of a picture's generation -------------------------------------------------------------------------------
+// Commits the picture's context records to the stream's current frame (decode_slice.cpp:3104-3108) - the generation kernels of the
+// stream's NEXT picture read them - and leaves the picture's CodeJob for the deferred coder.  One block per picture.
+__global__ void __launch_bounds__ (128) k_model_commit (const MPicDev* pics, int n_pics, const unsigned long long* dec_base, const uint32_t* pic_total,
+                                                        const BatchCtl* ctl, CodeJob* jobs) {
+  const int p = blockIdx.x;
   if (p >= n_pics || ctl->skip) return;
   const MPicDev& pic = pics[p];
   MState* st = pic.st;
   if (st->error) return;
+  CtxRec* dst = st->frame[st->cur];
+  for (int i = threadIdx.x; i < pic.n_recs; i += blockDim.x) {
+    const uint32_t a = pic.recs[i].mb_addr;
+    if ((int)a < pic.mb_w * pic.mb_h) {
+      const uint4* q = reinterpret_cast<const uint4*> (&st->newrec[a]);
+      uint4* o = reinterpret_cast<uint4*> (&dst[a]);
+      o[0] = q[0]; o[1] = q[1];
+    }
+  }
+  if (threadIdx.x == 0) { CodeJob j; j.st = st; j.base = ctl->pool_base + dec_base[p]; j.n = pic_total[p]; j.pad = 0; jobs[p] = j; }
+}
+
+// `index[b * n_steps + j]` = position of stream-block b's picture in step j's job row (jobs + j * stride), or -1.
+__global__ void __launch_bounds__ (64) k_model_code (const CodeJob* jobs, const int* index, int n_steps, int stride, const uint32_t* dec, ArenaDev ar) {
+  __shared__ CodeShared sh;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll 1
+  for (int step_j = 0; step_j < n_steps; step_j++) {
+  const int ji = index[(size_t)blockIdx.x * n_steps + step_j];
+  if (ji < 0) continue;
+  const CodeJob job = jobs[(size_t)step_j * stride + ji];
+  MState* st = job.st;
+  if (!st) continue;
+  __syncthreads();                                   // the previous picture's rings are drained, its coder states and error flag stored
   if (threadIdx.x < 32) { sh.prod[threadIdx.x] = 0; sh.cons[threadIdx.x] = 0; }
-  if (threadIdx.x == 0) sh.done = 0;
+  if (threadIdx.x == 0) { sh.done = 0; sh.skip = st->error; }
   __syncthreads();
-  const uint32_t n = pic_total[p];
+  if (sh.skip) continue;                             // (one read for the whole block: the two warps must agree)
+  const uint32_t n = job.n;
   if (warp == 0) {
     // ---- producer ---------------------------------------------------------------------------------------------------
     uint32_t* priors = st->priors;
-    const uint32_t* d = dec + dec_base[p];
+    const uint32_t* d = dec + job.base;
     const uint32_t lt = (1u << lane) - 1u;
     // software pipeline: decision words are loaded two chunks ahead and the priors of chunk k+1 are gathered right after
     // the scatter of chunk k
@@ -806,15 +845,6 @@ __global__ void __launch_bounds__ (64) k_model_code (const MPicDev* pics, int n_
     }
     __threadfence_block();
     if (lane == 0) { sh.done = 1; st->decisions += n; }
-    // commit the picture's context records (decode_slice.cpp:3104-3108)
-    for (int i = lane; i < pic.n_recs; i += 32) {
-      const uint32_t a = pic.recs[i].mb_addr;
-      if ((int)a < pic.mb_w * pic.mb_h) {
-        const uint4* q = reinterpret_cast<const uint4*> (&st->newrec[a]);
-        uint4* o = reinterpret_cast<uint4*> (&st->frame[st->cur][a]);
-        o[0] = q[0]; o[1] = q[1];
-      }
-    }
   } else {
     // ---- consumer: lane t = bool coder of compact tag t -----------------------------------------------------------------
     Coder c = st->coder[lane];
@@ -896,6 +926,7 @@ __global__ void __launch_bounds__ (64) k_model_code (const MPicDev* pics, int n_
       if (errm) st->error = 2;
     }
   }
+  }                                                  // next picture of this stream
 }
 
 // vpx_stop_encode (bitwriter.cpp:28-38) for every tag stream that exists; one warp per stream

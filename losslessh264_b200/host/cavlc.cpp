@@ -23,25 +23,33 @@ void cavlc_tables (const uint8_t (**tok_len)[4][17], const uint8_t (**tok_code)[
 
 // ---- generic prefix-code LUT ------------------------------------------------------------------------------------
 struct Lut {
-  int bits = 0;                         // index width
-  std::vector<uint8_t> sym, len;        // len == 0 -> invalid code
+  // two levels: the top 8 bits resolve every code of up to 8 bits (the bulk of what real streams hold) from a 512-byte table that
+  // stays in L1; longer codes go through the full-width table.  Entry = (symbol << 8) | length, 0 = not a code.
+  int bits = 0;                         // index width of the full table (<= 16)
+  uint16_t l1[256];
+  std::vector<uint16_t> full;
   void build (int nbits, const uint8_t* lens, const uint8_t* codes, int n) {
     bits = nbits;
-    sym.assign ((size_t)1 << nbits, 0);
-    len.assign ((size_t)1 << nbits, 0);
+    memset (l1, 0, sizeof (l1));
+    full.assign ((size_t)1 << nbits, 0);
     for (int s = 0; s < n; s++) {
       const int l = lens[s];
       if (!l) continue;
+      const uint16_t e = (uint16_t) ((s << 8) | l);
       const uint32_t first = (uint32_t)codes[s] << (nbits - l), cnt = 1u << (nbits - l);
-      for (uint32_t k = 0; k < cnt; k++) { sym[first + k] = (uint8_t)s; len[first + k] = (uint8_t)l; }
+      for (uint32_t k = 0; k < cnt; k++) full[first + k] = e;
+      if (l <= 8) { const uint32_t f1 = (uint32_t)codes[s] << (8 - l), c1 = 1u << (8 - l); for (uint32_t k = 0; k < c1; k++) l1[f1 + k] = e; }
     }
   }
   inline int get (BitReader& br) const {
-    const uint32_t idx = br.peek (bits);
-    const int l = len[idx];
-    if (!l) return -1;
-    br.skip (l);
-    return sym[idx];
+    const uint32_t w = br.peek (16);
+    uint32_t e = l1[w >> 8];
+    if (!e) {
+      e = full[w >> (16 - bits)];
+      if (!e) return -1;
+    }
+    br.skip ((int) (e & 0xffu));
+    return (int) (e >> 8);
   }
 };
 

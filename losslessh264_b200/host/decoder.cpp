@@ -40,6 +40,74 @@ struct RefPic {
 
 struct Nb { bool avail; int ref; int mvx, mvy; };
 
+// Growable array of hand-off records that lives either in heap memory of the decoder or in a RecordArena (decoder.h).  grow()
+// leaves the new elements uninitialised (the parser overwrites every one of them).
+template <class T, int KIND> class RecBuf {
+ public:
+  RecBuf() {}
+  RecBuf (const RecBuf&) = delete;
+  RecBuf& operator= (const RecBuf&) = delete;
+  ~RecBuf() { free (own_); }
+  T* data() const { return p_; }
+  size_t size() const { return n_; }
+  T& operator[] (size_t i) { return p_[i]; }
+  const T& operator[] (size_t i) const { return p_[i]; }
+  T& back() { return p_[n_ - 1]; }
+  void clear() { n_ = 0; if (arena_) { p_ = nullptr; cap_ = 0; } }       // (arena storage belongs to ONE picture)
+  void pop_back() { n_--; }
+  void truncate (size_t n) { n_ = n; }
+  T* grow (size_t k) {
+    if (n_ + k > cap_ && !reserve (n_ + k)) return nullptr;
+    T* r = p_ + n_;
+    n_ += k;
+    return r;
+  }
+  bool reserve (size_t need) {
+    if (need <= cap_) return true;
+    if (arena_) {
+      size_t capb = 0;
+      uint8_t* q = arena_->storage (KIND, need * sizeof (T), &capb, reinterpret_cast<const uint8_t*> (p_), n_ * sizeof (T));
+      if (!q) return false;
+      p_ = reinterpret_cast<T*> (q); cap_ = capb / sizeof (T);
+      return true;
+    }
+    const size_t ncap = std::max (need, std::max<size_t> (2 * own_cap_, 1024));
+    T* q = static_cast<T*> (realloc (own_, ncap * sizeof (T)));
+    if (!q) return false;
+    own_ = q; own_cap_ = ncap; p_ = q; cap_ = ncap;
+    return true;
+  }
+  bool set_arena (RecordArena* a) {
+    if (!a && !arena_) return true;
+    if (n_ == 0) {
+      arena_ = a;
+      if (a) { p_ = nullptr; cap_ = 0; } else { p_ = own_; cap_ = own_cap_; }
+      return true;
+    }
+    if (a) {                                          // the records so far move into the arena
+      size_t capb = 0;
+      uint8_t* q = a->storage (KIND, n_ * sizeof (T), &capb, reinterpret_cast<const uint8_t*> (p_), n_ * sizeof (T));
+      if (!q) return false;
+      arena_ = a; p_ = reinterpret_cast<T*> (q); cap_ = capb / sizeof (T);
+      return true;
+    }
+    if (n_ > own_cap_) {
+      T* q = static_cast<T*> (realloc (own_, n_ * sizeof (T)));
+      if (!q) return false;
+      own_ = q; own_cap_ = n_;
+    }
+    memcpy (own_, p_, n_ * sizeof (T));
+    arena_ = nullptr; p_ = own_; cap_ = own_cap_;
+    return true;
+  }
+ private:
+  T* p_ = nullptr;
+  size_t n_ = 0, cap_ = 0;
+  RecordArena* arena_ = nullptr;
+  T* own_ = nullptr;
+  size_t own_cap_ = 0;
+};
+
 inline int median3 (int a, int b, int c) { return a > b ? (b > c ? b : (a > c ? c : a)) : (a > c ? a : (b > c ? c : b)); }
 
 } // namespace
@@ -62,13 +130,14 @@ struct Decoder::Impl {
   bool open = false;
   SliceHeader sh0;                       // first slice header of the picture
   int cur_slot = 0, decoded = 0;
+  bool alloc_failed = false;             // record storage could not be had (RecordArena / heap): the picture is dropped
   // the reference holds its output back until the first IDR picture has been decoded (bFreezeOutput under the freeze error
   // concealment modes h264dec selects, decoder_core.cpp:56-217): pictures of a stream whose leading IDR was lost are parsed,
   // modelled and reconstructed, but marked `output = false` for the sink and not handed out
   bool frozen = true;
   unsigned long long ts = 0;
-  std::vector<lh264_mb_rec> mbs;
-  std::vector<int16_t> coefs;
+  RecBuf<lh264_mb_rec, RecordArena::MBS> mbs;      // n_mbs records while a picture is open
+  RecBuf<int16_t, RecordArena::COEFS> coefs;
   std::vector<lh264_slice_rec> slices;
   std::vector<uint8_t> nzc;              // [mb][24] total_coeff (luma raster 0..15, Cb 16..19, Cr 20..23)
   std::vector<int8_t> ipm;               // [mb][16] Intra4x4/8x8PredMode per raster block; 2 for other MB types
@@ -79,7 +148,7 @@ struct Decoder::Impl {
   bool want_model = false;
   bool check_rewrite = false;
   std::unique_ptr<PictureSyntaxWriter> rewriter;
-  std::vector<lh264_model_mb> mrecs;
+  RecBuf<lh264_model_mb, RecordArena::MRECS> mrecs;
   std::vector<lh264_model_slice> mslices;
   // per-position decoder state the reference keeps across pictures and reads back when it fills its
   // DecodedMacroblock (initRTDFromDecoderState, decode_slice.cpp:81-108): pCbp, pChromaPredMode,
@@ -105,7 +174,7 @@ struct Decoder::Impl {
   int slice_no = 0, qp = 26;
   RefPic* list0[33];
   bool cur_done[16];                     // per raster 4x4 block of the current MB: MV already derived
-  int cur_mb = 0;
+  int cur_mb = 0, cur_mbx = 0, cur_mby = 0;        // macroblock being parsed and its position (set by parse_mb: no division per neighbour look-up)
 
   // ---------------------------------------------------------------------------------------------
   bool mb_avail (int mb) const { return mb >= 0 && mb < n_mbs && mb_slice[mb] == slice_no; }
@@ -121,8 +190,7 @@ struct Decoder::Impl {
   // negative / >= 4.  Returns motion data as 6.4.11.7 + 8.4.1.3.2 want it.
   Nb nb_block (int bx, int by) const {
     Nb r{false, -2, 0, 0};
-    const int mbx = cur_mb % mb_w, mby = cur_mb / mb_w;
-    int tx = mbx, ty = mby;
+    int tx = cur_mbx, ty = cur_mby;
     if (bx < 0) { tx--; bx += 4; } else if (bx > 3) { tx++; bx -= 4; }
     if (by < 0) { ty--; by += 4; } else if (by > 3) return r;
     if (tx < 0 || tx >= mb_w || ty < 0) return r;
@@ -284,7 +352,7 @@ struct Decoder::Impl {
     mb_w = s.mb_w; mb_h = s.mb_h; n_mbs = mb_w * mb_h;
     n_slots = std::max (3, s.max_num_ref_frames + 2);
     refs.clear(); max_long_idx = -1;
-    mbs.assign (n_mbs, lh264_mb_rec());
+    mbs.clear();
     nzc.assign ((size_t)n_mbs * 24, 0);
     ipm.assign ((size_t)n_mbs * 16, 2);
     mb_slice.assign (n_mbs, -1);
@@ -296,7 +364,6 @@ struct Decoder::Impl {
       st_alloc_w = mb_w * 16; st_alloc_h = mb_h * 16;
       st_cbp.assign (n_mbs, 0); st_chroma.assign (n_mbs, 0); st_i16.assign (n_mbs, 0); st_sub.assign ((size_t)n_mbs * 4, 0);
     }
-    coefs.reserve ((size_t)n_mbs * 64);
     cabmb.assign (n_mbs, CabMb()); mvd_abs.assign ((size_t)n_mbs * 32, 0);
     return sink->configure (mb_w, mb_h, n_slots);
   }
@@ -308,6 +375,7 @@ struct Decoder::Impl {
   void start_picture (Decoder* self) {
     (void)self;
     open = true; sh0 = sh; decoded = 0; slice_no = 0;
+    cur_mb = -2;                           // (cur_mbx / cur_mby are recomputed for the first macroblock)
     if (sh.idr) { /* refs dropped at marking time; lists are empty for an I picture anyway */ }
     else if (S->gaps_in_frame_num_allowed) {
       // 8.2.5.2: fill frame_num gaps with non-existing short-term frames
@@ -327,12 +395,17 @@ struct Decoder::Impl {
       }
     }
     cur_slot = free_slot();
-    slices.clear(); coefs.clear(); mrecs.clear(); mslices.clear();
-    for (int i = 0; i < n_mbs; i++) { mbs[i].mb_type = LH264_MB_NONE; mb_slice[i] = -1; }
+    slices.clear(); coefs.clear(); mrecs.clear(); mslices.clear(); mbs.clear();
+    if (!mbs.grow (n_mbs)) { open = false; alloc_failed = true; return; }
+    coefs.reserve ((size_t)n_mbs * 32);               // two coefficient blocks per macroblock to start with
+    // (records of macroblocks that stay undecoded are marked LH264_MB_NONE when the picture is handed over: no pass over
+    // ~1 MB of records for the usual, complete picture)
+    std::fill (mb_slice.begin(), mb_slice.end(), (int16_t) -1);
   }
   int finish_picture (Decoder* self) {
     if (!open) return 0;
     open = false;
+    if (decoded < n_mbs) { for (int i = 0; i < n_mbs; i++) if (mb_slice[i] < 0) mbs[i].mb_type = LH264_MB_NONE; }
     lh264_picture_desc d;
     d.stream = 0; d.cur_slot = cur_slot; d.n_slices = (int)slices.size(); d.n_coef_blocks = (int) (coefs.size() / 16);
     d.slices = slices.data(); d.mbs = mbs.data(); d.coefs = coefs.data();
@@ -361,6 +434,7 @@ struct Decoder::Impl {
     self->stats_.pictures++;
     self->stats_.coef_blocks += coefs.size() / 16;
     if (info.output) self->out_.push_back (info);
+    mbs.clear(); coefs.clear(); mrecs.clear();       // handed over: arena storage is the sink's now
     return rc;
   }
 
@@ -389,7 +463,7 @@ struct Decoder::Impl {
 
 // ---- nC derivation (9.2.1) -----------------------------------------------------------------------------
 int Decoder::Impl::nC_luma (int mb_addr, int r) const {
-  const int mbx = mb_addr % mb_w, mby = mb_addr / mb_w, bx = r & 3, by = r >> 2;
+  const int mbx = cur_mbx, mby = cur_mby, bx = r & 3, by = r >> 2;        // (mb_addr == cur_mb)
   int nA = -1, nB = -1;
   if (bx > 0) nA = nzc[(size_t)mb_addr * 24 + r - 1];
   else { const int n = nb_mb (mbx, mby, -1, 0); if (mb_avail (n)) nA = nzc[(size_t)n * 24 + r + 3]; }
@@ -399,7 +473,7 @@ int Decoder::Impl::nC_luma (int mb_addr, int r) const {
   return nA >= 0 ? nA : (nB >= 0 ? nB : 0);
 }
 int Decoder::Impl::nC_chroma (int mb_addr, int plane, int b) const {
-  const int mbx = mb_addr % mb_w, mby = mb_addr / mb_w, bx = b & 1, by = b >> 1, base = 16 + 4 * plane;
+  const int mbx = cur_mbx, mby = cur_mby, bx = b & 1, by = b >> 1, base = 16 + 4 * plane;
   int nA = -1, nB = -1;
   if (bx > 0) nA = nzc[(size_t)mb_addr * 24 + base + b - 1];
   else { const int n = nb_mb (mbx, mby, -1, 0); if (mb_avail (n)) nA = nzc[(size_t)n * 24 + base + b + 1]; }
@@ -412,7 +486,7 @@ int Decoder::Impl::nC_chroma (int mb_addr, int plane, int b) const {
 // ---- intra mode resolution: what the reference does at parse time (CheckIntraNxNPredMode etc.,
 // parse_mb_syn_cavlc.cpp:519-612) expressed on neighbour availability -----------------------------------
 void Decoder::Impl::resolve_intra (lh264_mb_rec& m, int mb_addr, const int8_t* modes, bool i8x8) {
-  const int mbx = mb_addr % mb_w, mby = mb_addr / mb_w;
+  const int mbx = cur_mbx, mby = cur_mby;            // (mb_addr == cur_mb)
   const bool L = mb_avail_intra (nb_mb (mbx, mby, -1, 0)), T = mb_avail_intra (nb_mb (mbx, mby, 0, -1));
   const bool TL = mb_avail_intra (nb_mb (mbx, mby, -1, -1)), TR = mb_avail_intra (nb_mb (mbx, mby, 1, -1));
   m.nxn_avail = (uint8_t) ((T ? 1 : 0) | (TL ? 2 : 0) | (L ? 4 : 0) | (TR ? 8 : 0));
@@ -460,7 +534,7 @@ int Decoder::Impl::parse_residual (BitReader& br, lh264_mb_rec& m, int mb_addr, 
     for (int r = 0; r < 16; r++) if (dc[r]) { const int z = kRtoZ[r]; lev[16 * z] = dc[r]; coded |= 1u << z; }
   }
   for (int q = 0; q < 4; q++) {
-    if (! (cbp & (1 << q))) { for (int k = 0; k < 4; k++) nz[kZtoR[4 * q + k]] = 0; continue; }
+    if (! (cbp & (1 << q))) { uint8_t* z = nz + (q >> 1) * 8 + (q & 1) * 2; z[0] = z[1] = z[4] = z[5] = 0; continue; }
     for (int k = 0; k < 4; k++) {
       const int z = 4 * q + k, r = kZtoR[z];
       int tc;
@@ -475,11 +549,11 @@ int Decoder::Impl::parse_residual (BitReader& br, lh264_mb_rec& m, int mb_addr, 
   const int cc = cbp >> 4;
   if (cc) {
     for (int p = 0; p < 2; p++) {                   // ChromaDCLevel
-      int16_t dc[64];
-      memset (dc, 0, sizeof (dc));
-      const int tc = cavlc_residual_block (br, -1, 4, kChromaDcScan, 1, 0, dc);
+      int16_t dc[4] = {0, 0, 0, 0};
+      static const uint8_t kDcScan[4] = {0, 1, 2, 3};
+      const int tc = cavlc_residual_block (br, -1, 4, kDcScan, 1, 0, dc);
       if (tc < 0) return -1;
-      for (int b = 0; b < 4; b++) if (dc[16 * b]) { lev[16 * (16 + 4 * p + b)] = dc[16 * b]; coded |= 1u << (16 + 4 * p + b); }
+      if (tc) for (int b = 0; b < 4; b++) if (dc[b]) { lev[16 * (16 + 4 * p + b)] = dc[b]; coded |= 1u << (16 + 4 * p + b); }
     }
   }
   for (int p = 0; p < 2; p++) for (int b = 0; b < 4; b++) {
@@ -502,7 +576,9 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_mod
   uint8_t* nz = &nzc[(size_t)mb_addr * 24];
   int8_t* pm = &ipm[(size_t)mb_addr * 16];
   memset (pm, 2, 16);
-  const int mbx = mb_addr % mb_w, mby = mb_addr / mb_w;
+  if (mb_addr == cur_mb + 1 && cur_mbx + 1 < mb_w) cur_mbx++;                        // the usual step: next macroblock of the row
+  else { cur_mbx = mb_addr % mb_w; cur_mby = mb_addr / mb_w; }
+  const int mbx = cur_mbx, mby = cur_mby;
   auto set_qp = [&] (lh264_mb_rec & mm) {
     mm.qp_y = (uint8_t)qp;
     mm.qp_c[0] = kChromaQp[std::min (51, std::max (0, qp + P->chroma_qp_index_offset))];
@@ -526,7 +602,11 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_mod
     const Nb A = nb_block (-1, 0), B = nb_block (0, -1);
     if (A.avail && B.avail && ! (A.ref == 0 && A.mvx == 0 && A.mvy == 0) && ! (B.ref == 0 && B.mvx == 0 && B.mvy == 0))
       pred_mv (0, 0, 4, 4, 0, 0, px, py);
-    for (int r = 0; r < 16; r++) { m.mv[r][0] = (int16_t)px; m.mv[r][1] = (int16_t)py; }
+    {
+      const uint32_t v = (uint32_t) (uint16_t) (int16_t)px | ((uint32_t) (uint16_t) (int16_t)py << 16);
+      uint32_t* mvw = reinterpret_cast<uint32_t*> (&m.mv[0][0]);
+      for (int r = 0; r < 16; r++) mvw[r] = v;
+    }
     mb_slice[mb_addr] = (int16_t)slice_no;
     st_cbp[mb_addr] = 0;                             // pCbp[iMbXy] = 0, decode_slice.cpp:3945
     if (mr) { mr->type_code = 11; mr->luma_qp = (uint8_t)qp; }
@@ -553,7 +633,9 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_mod
     const int nref = sh.num_ref_idx_l0;
     bool sub_lt8 = false;
     auto put_mv = [&] (int bx, int by, int bw, int bh, int mvx, int mvy) {
-      for (int y = by; y < by + bh; y++) for (int x = bx; x < bx + bw; x++) { m.mv[y * 4 + x][0] = (int16_t)mvx; m.mv[y * 4 + x][1] = (int16_t)mvy; cur_done[y * 4 + x] = true; }
+      const uint32_t v = (uint32_t) (uint16_t) (int16_t)mvx | ((uint32_t) (uint16_t) (int16_t)mvy << 16);
+      uint32_t* mvw = reinterpret_cast<uint32_t*> (&m.mv[0][0]);                   // mv[r] = {x, y}: one 32-bit word per block
+      for (int y = by; y < by + bh; y++) for (int x = bx; x < bx + bw; x++) { mvw[y * 4 + x] = v; cur_done[y * 4 + x] = true; }
     };
     if (m.mb_type == LH264_MB_P8x8) {
       for (int q = 0; q < 4; q++) {
@@ -631,9 +713,9 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_mod
     m.mb_type = LH264_MB_IPCM;
     br.align();
     const size_t at = coefs.size();
-    coefs.resize (at + 384);
-    int16_t* o = coefs.data() + at;
-    if (br.pos() + 384 * 8 > br.size_bits()) { coefs.resize (at); return -1; }   // samples cut off (damaged stream)
+    int16_t* o = coefs.grow (384);
+    if (!o) return -1;
+    if (br.pos() + 384 * 8 > br.size_bits()) { coefs.truncate (at); return -1; }   // samples cut off (damaged stream)
     const uint8_t* src = br.data() + (br.pos() >> 3);
     for (int i = 0; i < 384; i++) o[i] = src[i];
     br.skip (384 * 8);
@@ -729,9 +811,8 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_mod
     if (coded) {
       m.coded_mask = coded;
       m.coef_off = (uint32_t) (coefs.size() / 16);
-      size_t at = coefs.size();
-      coefs.resize (at + 16 * (size_t)__builtin_popcount (coded));
-      int16_t* o = coefs.data() + at;
+      int16_t* o = coefs.grow (16 * (size_t)__builtin_popcount (coded));
+      if (!o) { memset (lev_, 0, sizeof (lev_)); return -1; }
       for (uint32_t mk = coded; mk; mk &= mk - 1) { const int k = __builtin_ctz (mk); memcpy (o, lev + 16 * k, 32); memset (lev + 16 * k, 0, 32); o += 16; }
     }
   } else {
@@ -740,7 +821,12 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_mod
     last_dqp_nz = false;
   }
   uint32_t nzm = 0;
-  for (int r = 0; r < 24; r++) if (nz[r]) nzm |= 1u << r;
+  for (int w = 0; w < 3; w++) {                       // 24 total_coeff bytes -> 24 flag bits, eight at a time
+    uint64_t v;
+    memcpy (&v, nz + 8 * w, 8);
+    v = ((v & 0x7f7f7f7f7f7f7f7full) + 0x7f7f7f7f7f7f7f7full) | v;      // bit 7 of every byte = byte != 0
+    nzm |= (uint32_t) (((v & 0x8080808080808080ull) >> 7) * 0x0102040810204080ull >> 56) << (8 * w);
+  }
   m.nz_mask = nzm;
   mb_slice[mb_addr] = (int16_t)slice_no;
   if (mr) {
@@ -771,7 +857,7 @@ const uint8_t kLast8x8[63] = {0, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 1, 2,
 
 int Decoder::Impl::cabac_intra_mb_type (int base, bool i_slice, int mb_addr) {
   if (i_slice) {                                      // ctxIdxInc of bin 0: neighbours that are not I_NxN
-    const int mbx = mb_addr % mb_w, mby = mb_addr / mb_w;
+    const int mbx = cur_mbx, mby = cur_mby;            // (mb_addr == cur_mb)
     const int nA = nb_mb (mbx, mby, -1, 0), nB = nb_mb (mbx, mby, 0, -1);
     auto cond = [&] (int n) { return mb_avail (n) && mbs[n].mb_type != LH264_MB_I4x4 && mbs[n].mb_type != LH264_MB_I8x8; };
     if (!cab.decision (base + (cond (nA) ? 1 : 0) + (cond (nB) ? 1 : 0))) return 0;
@@ -801,7 +887,7 @@ int Decoder::Impl::cabac_sub_mb_type() {
 }
 
 int Decoder::Impl::cabac_ref_idx (int mb_addr, int q, const int8_t* cur_refs) {
-  const int mbx = mb_addr % mb_w, mby = mb_addr / mb_w;
+  const int mbx = cur_mbx, mby = cur_mby;            // (mb_addr == cur_mb)
   auto gt0 = [&] (int n, int nq) { return mb_avail (n) && !LH264_MB_IS_INTRA (mbs[n].mb_type) && mbs[n].ref_idx[nq] > 0; };
   const bool a = (q & 1) ? cur_refs[q - 1] > 0 : gt0 (nb_mb (mbx, mby, -1, 0), q + 1);
   const bool b = (q & 2) ? cur_refs[q - 2] > 0 : gt0 (nb_mb (mbx, mby, 0, -1), q + 2);
@@ -815,7 +901,7 @@ int Decoder::Impl::cabac_ref_idx (int mb_addr, int q, const int8_t* cur_refs) {
 }
 
 int Decoder::Impl::cabac_mvd (int mb_addr, int bx, int by, int comp) {
-  const int mbx = mb_addr % mb_w, mby = mb_addr / mb_w;
+  const int mbx = cur_mbx, mby = cur_mby;            // (mb_addr == cur_mb)
   int sum = 0;
   if (bx > 0) sum += mvd_abs[(size_t)mb_addr * 32 + 2 * (by * 4 + bx - 1) + comp];
   else { const int n = nb_mb (mbx, mby, -1, 0); if (mb_avail (n)) sum += mvd_abs[(size_t)n * 32 + 2 * (by * 4 + 3) + comp]; }
@@ -835,7 +921,7 @@ int Decoder::Impl::cabac_mvd (int mb_addr, int bx, int by, int comp) {
 }
 
 int Decoder::Impl::cabac_cbp (int mb_addr) {
-  const int mbx = mb_addr % mb_w, mby = mb_addr / mb_w;
+  const int mbx = cur_mbx, mby = cur_mby;            // (mb_addr == cur_mb)
   const int nA = nb_mb (mbx, mby, -1, 0), nB = nb_mb (mbx, mby, 0, -1);
   // unavailable neighbours count as "all luma blocks coded, no chroma"
   const int ca = mb_avail (nA) ? cabmb[nA].cbp : 0x0f, cb = mb_avail (nB) ? cabmb[nB].cbp : 0x0f;
@@ -851,7 +937,7 @@ int Decoder::Impl::cabac_cbp (int mb_addr) {
 }
 
 int Decoder::Impl::cabac_chroma_mode (int mb_addr) {
-  const int mbx = mb_addr % mb_w, mby = mb_addr / mb_w;
+  const int mbx = cur_mbx, mby = cur_mby;            // (mb_addr == cur_mb)
   auto cond = [&] (int n) { return mb_avail (n) && LH264_MB_IS_INTRA (mbs[n].mb_type) && mbs[n].mb_type != LH264_MB_IPCM && cabmb[n].chroma != 0; };
   if (!cab.decision (64 + (cond (nb_mb (mbx, mby, -1, 0)) ? 1 : 0) + (cond (nb_mb (mbx, mby, 0, -1)) ? 1 : 0))) return 0;
   if (!cab.decision (64 + 3)) return 1;
@@ -868,7 +954,7 @@ int Decoder::Impl::cabac_dqp() {
 }
 
 int Decoder::Impl::cabac_t8_flag (int mb_addr) {
-  const int mbx = mb_addr % mb_w, mby = mb_addr / mb_w;
+  const int mbx = cur_mbx, mby = cur_mby;            // (mb_addr == cur_mb)
   auto cond = [&] (int n) { return mb_avail (n) && (mbs[n].flags & LH264_MBF_TRANSFORM8x8); };
   return cab.decision (399 + (cond (nb_mb (mbx, mby, -1, 0)) ? 1 : 0) + (cond (nb_mb (mbx, mby, 0, -1)) ? 1 : 0));
 }
@@ -876,7 +962,7 @@ int Decoder::Impl::cabac_t8_flag (int mb_addr) {
 // 9.3.3.1.1.9: ctxIdxInc of coded_block_flag.  bit_cur_* >= 0: the neighbouring block lies in the current macroblock (that bit
 // of its cbf word); otherwise the bit of the left / top macroblock's word.  Unavailable macroblock: 1 for intra, 0 for inter.
 int Decoder::Impl::cbf_inc (int mb_addr, int bit_cur_a, int bit_left, int bit_cur_b, int bit_top) const {
-  const int mbx = mb_addr % mb_w, mby = mb_addr / mb_w;
+  const int mbx = cur_mbx, mby = cur_mby;            // (mb_addr == cur_mb)
   const int dflt = LH264_MB_IS_INTRA (mbs[mb_addr].mb_type) ? 1 : 0;
   int a, b;
   if (bit_cur_a >= 0) a = (cabmb[mb_addr].cbf >> bit_cur_a) & 1;
@@ -939,7 +1025,7 @@ int Decoder::Impl::parse_residual_cabac (lh264_mb_rec& m, int mb_addr, int16_t* 
     for (int r = 0; r < 16; r++) if (dc[r]) { const int z = kRtoZ[r]; lev[16 * z] = dc[r]; coded |= 1u << z; }
   }
   for (int q = 0; q < 4; q++) {
-    if (! (cbp & (1 << q))) { for (int k = 0; k < 4; k++) nz[kZtoR[4 * q + k]] = 0; continue; }
+    if (! (cbp & (1 << q))) { uint8_t* z = nz + (q >> 1) * 8 + (q & 1) * 2; z[0] = z[1] = z[4] = z[5] = 0; continue; }
     if (t8) {
       const int tc = cabac_block (5, -1, lev + 64 * q, kZigzag8x8, 0);
       if (tc < 0) return -1;
@@ -1006,8 +1092,8 @@ int Decoder::Impl::parse_slice_data_cabac (BitReader& br, Decoder* self) {
     }
     lh264_model_mb* mr = nullptr;
     if (want_model) {
-      mrecs.emplace_back ();
-      mr = &mrecs.back();
+      mr = mrecs.grow (1);
+      if (!mr) { rc = -1; break; }
       memset (mr, 0, sizeof (*mr));
       mr->mb_addr = (uint32_t)mb_addr; mr->mb_in_slice = (uint16_t)std::min<size_t> (mrecs.size() - 1 - rec0, 65535);
       mr->flags |= LH264_MM_EMIT_SKIP_RUN | (skip ? LH264_MM_STOP_IN_SKIP : LH264_MM_WRITE_BLOCK);
@@ -1061,8 +1147,8 @@ int Decoder::Impl::parse_slice_data (BitReader& br, Decoder* self) {
   const size_t rec0 = mrecs.size();
   auto new_rec = [&] (int addr) -> lh264_model_mb* {
     if (!want_model) return nullptr;
-    mrecs.emplace_back ();
-    lh264_model_mb* r = &mrecs.back();
+    lh264_model_mb* r = mrecs.grow (1);
+    if (!r) return nullptr;
     memset (r, 0, sizeof (*r));
     r->mb_addr = (uint32_t)addr; r->mb_in_slice = (uint16_t)std::min<size_t> (mrecs.size() - 1 - rec0, 65535);
     return r;
@@ -1153,6 +1239,12 @@ void Decoder::enable_model (bool on) { d_->want_model = on; }
 void Decoder::enable_rewrite_check (bool on) { d_->check_rewrite = on; if (on) d_->want_model = true; }
 
 int Decoder::flush() { return d_->finish_picture (this); }
+bool Decoder::picture_open() const { return d_->open; }
+bool Decoder::set_arena (RecordArena* a) {
+  const bool ok = d_->mbs.set_arena (a) & d_->coefs.set_arena (a) & d_->mrecs.set_arena (a);
+  if (!ok) d_->alloc_failed = true;
+  return ok;
+}
 
 int Decoder::decode (const uint8_t* data, size_t len, unsigned long long timestamp) {
   Impl& D = *d_;
@@ -1188,6 +1280,7 @@ int Decoder::decode (const uint8_t* data, size_t len, unsigned long long timesta
         if (D.activate (sps) < 0) { last_err = -30; continue; }
         D.S = &D.sps[pps.sps_id]; D.P = &D.pps[sh.pps_id]; D.sh = sh; D.ts = timestamp;
         D.start_picture (this);
+        if (!D.open) { last_err = -31; stats_.errors++; continue; }        // no storage for the picture's records
       } else { D.S = &D.sps[pps.sps_id]; D.P = &D.pps[sh.pps_id]; D.sh = sh; }
       if (sh.first_mb >= D.n_mbs) { last_err = -1; stats_.errors++; continue; }
       D.slice_no = (int)D.slices.size();

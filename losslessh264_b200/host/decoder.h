@@ -43,6 +43,18 @@ struct ModelMbSide {
   uint8_t reserved;
 };
 
+// Where a Decoder writes the bulky hand-off records (MB records, coefficient pools, model records) of the picture it is parsing.
+// Default: heap buffers of its own.  A host that stages records for the GPU (runtime.cpp) installs an arena so that the parser
+// writes STRAIGHT into pinned staging memory: no second pass over ~2.6 MB per 1080p picture.
+class RecordArena {
+ public:
+  enum Kind { MBS = 0, COEFS = 1, MRECS = 2 };
+  virtual ~RecordArena() {}
+  // Storage of at least `need` bytes of `kind` for the picture in progress; the `keep` bytes at `old` (this picture's records so
+  // far; NULL when there are none) are preserved at the start of the returned block.  *cap = usable bytes.  NULL = no memory.
+  virtual uint8_t* storage (int kind, size_t need, size_t* cap, const uint8_t* old, size_t keep) = 0;
+};
+
 class PictureSink {
  public:
   virtual ~PictureSink() {}
@@ -76,6 +88,10 @@ class Decoder {
   const std::vector<DecodedPictureInfo>& output() const { return out_; }
   void clear_output() { out_.clear(); }
   void enable_model (bool on);           // produce lh264_model_picture hand-offs (PictureSink::submit_model)
+  // Switches record storage to `arena` (NULL = the decoder's own heap buffers) for the following pictures AND for a picture in
+  // progress, whose records so far move over.  The pointers PictureSink::submit() sees then point into the arena.
+  bool set_arena (RecordArena* arena);
+  bool picture_open() const;             // a picture has been started and not yet handed to the sink
   // the last slice NAL handled by the last decode() call (for the `.pip` default stream, pip_container.h); rbsp is valid
   // until the next decode() call
   struct LastSlice { bool decoded = false, cabac = false; const uint8_t* rbsp = nullptr; size_t header_bits = 0; };

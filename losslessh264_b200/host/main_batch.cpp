@@ -79,10 +79,10 @@ int main (int argc, char** argv) {
   lh264_rt_stats st;
   lh264_rt_stats_get (rt, &st);
   printf ("{\"streams\": %ld, \"threads\": %d, \"groups\": %d, \"loops\": %d, \"pictures\": %ld, \"seconds\": %.4f, \"frames_per_s\": %.1f, \"input_mb_per_s\": %.2f, \"pip_bytes\": %zu, "
-          "\"seconds_incl_finish\": %.4f, \"submit_wait_parse_s\": %.4f, \"submit_wait_gpu_s\": %.4f, \"parse_busy_s\": %.4f, \"parse_wait_s\": %.4f, \"h2d_bytes\": %zu, \"d2h_bytes\": %zu, \"setup_s\": %.4f, \"steady_frames_per_s\": %.1f, "
+          "\"seconds_incl_finish\": %.4f, \"submit_wait_parse_s\": %.4f, \"submit_wait_gpu_s\": %.4f, \"parse_busy_s\": %.4f, \"parse_wait_s\": %.4f, \"h2d_bytes\": %zu, \"d2h_bytes\": %zu, \"setup_s\": %.4f, \"pinned_alloc_s\": %.4f, \"open_streams_s\": %.4f, \"steady_frames_per_s\": %.1f, "
           "\"copy_mismatches\": %d, \"kernel_launches\": %llu}\n",
           st.streams, st.threads, st.pipelines, cfg.loops, st.pictures, st.seconds, st.pictures / st.seconds, st.input_bytes / st.seconds / 1e6, st.pip_bytes, st.seconds_total,
-          st.submit_wait_parse_s, st.submit_wait_gpu_s, st.parse_busy_s, st.parse_wait_s, st.h2d_bytes, st.d2h_bytes, st.setup_s,
+          st.submit_wait_parse_s, st.submit_wait_gpu_s, st.parse_busy_s, st.parse_wait_s, st.h2d_bytes, st.d2h_bytes, st.setup_s, st.pinned_alloc_s, st.open_streams_s,
           st.seconds > st.setup_s ? (st.pictures - st.setup_pictures) / (st.seconds - st.setup_s) : 0.0, mismatches, st.kernel_launches);
   lh264_rt_destroy (rt);
   return mismatches ? 3 : 0;

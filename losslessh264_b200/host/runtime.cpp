@@ -41,17 +41,21 @@ double now() { return std::chrono::duration<double> (std::chrono::steady_clock::
 
 struct PinRegion {                      // growable pinned buffer, bump-allocated within a step
   uint8_t* p = nullptr; size_t cap = 0, used = 0;
+  double* alloc_s = nullptr;            // where the time spent in pinned allocation is accounted
   ~PinRegion() { if (p) lh264_host_free (p); }
-  // returns the offset of n fresh bytes (contents so far are kept when the buffer has to grow), or (size_t)-1
-  size_t take (size_t n) {
+  // returns the offset of n fresh bytes (contents so far are kept when the buffer has to grow), or (size_t)-1;
+  // `room` = what the region is expected to hold in the end (pinning memory is slow: grow in few, large steps)
+  size_t take (size_t n, size_t room = 0) {
     const size_t at = used, need = used + n;
     if (need > cap) {
-      const size_t ncap = std::max (need + need / 2, (size_t)1 << 16);
+      const double t0 = now();
+      const size_t ncap = std::max (std::max (need + need / 2, room), (size_t)1 << 16);
       uint8_t* q = (uint8_t*)lh264_host_alloc (ncap);
       if (!q) return (size_t) -1;
       if (used) memcpy (q, p, used);
       if (p) lh264_host_free (p);
       p = q; cap = ncap;
+      if (alloc_s) *alloc_s += now() - t0;
     }
     used = need;
     return at;
@@ -68,12 +72,43 @@ struct Placed {                         // one picture of a step: where its arra
 
 struct StepBuf {
   PinRegion mbs, coefs, mrecs, slices, mslices;
+  size_t expect = 1;                    // pictures a step of the owning thread usually holds (its number of streams)
   std::vector<Placed> placed;
   bool failed = false;                  // pinned allocation failed
   void reset() { mbs.used = coefs.used = mrecs.used = slices.used = mslices.used = 0; placed.clear(); failed = false; }
 };
 
-// Receives the pictures a Decoder completes and copies their records into the current step buffer of the owning thread.
+// The parser writes MB records, coefficient pools and model records of the picture in progress straight into the step buffer
+// of the owning thread (decoder.h RecordArena): the open picture is the LAST allocation of each region and grows in place.
+class StepArena : public RecordArena {
+ public:
+  void bind (StepBuf* b) { buf_ = b; for (int k = 0; k < 3; k++) open_[k] = false; }
+  void picture_done() { for (int k = 0; k < 3; k++) open_[k] = false; }
+  PinRegion& region (int kind) { return kind == MBS ? buf_->mbs : (kind == COEFS ? buf_->coefs : buf_->mrecs); }
+  uint8_t* storage (int kind, size_t need, size_t* cap, const uint8_t* old, size_t keep) override {
+    PinRegion& r = region (kind);
+    const bool mine = open_[kind] && old == r.p + start_[kind];
+    // headroom: the parser asks again only when it runs out, so hand out generously (the sink trims to the final size)
+    const size_t want = need + (kind == MBS ? 0 : std::max<size_t> (need / 2, (size_t)64 << 10));
+    size_t kept = 0;
+    if (mine) { kept = keep; r.used = start_[kind] + keep; }     // grow in place (a region that has to move takes its bytes along)
+    else { start_[kind] = r.used; open_[kind] = true; }          // a new picture, or records arriving from the heap
+    // room for the thread's whole step at this picture's size (coefficient pools: at what the parser reserves first)
+    const size_t room = start_[kind] + want * buf_->expect + want * buf_->expect / 8;
+    if (want > kept && r.take (want - kept, room) == (size_t) -1) { buf_->failed = true; return nullptr; }
+    uint8_t* q = r.p + start_[kind];
+    if (!mine && old && keep) memcpy (q, old, keep);
+    *cap = want;
+    return q;
+  }
+ private:
+  StepBuf* buf_ = nullptr;
+  size_t start_[3] = {0, 0, 0};
+  bool open_[3] = {false, false, false};
+};
+
+// Receives the pictures a Decoder completes; their bulky records already sit in the step buffer (StepArena), the small slice
+// records are copied behind them.
 class StageSink : public PictureSink {
  public:
   int stream = 0;
@@ -87,11 +122,14 @@ class StageSink : public PictureSink {
     pl.n_slices = pic.n_slices; pl.n_mbs = mb_w * mb_h; pl.n_blocks = pic.n_coef_blocks;
     pl.mb_w = mb_w; pl.mb_h = mb_h; pl.n_slots = n_slots; pl.geo_serial = geo_serial;
     const size_t b_sl = (size_t)pic.n_slices * sizeof (lh264_slice_rec), b_mb = (size_t)pl.n_mbs * sizeof (lh264_mb_rec), b_co = (size_t)pic.n_coef_blocks * 32;
-    pl.o_sl = buf->slices.take (b_sl); pl.o_mb = buf->mbs.take (b_mb); pl.o_co = buf->coefs.take (b_co);
+    pl.o_sl = buf->slices.take (b_sl);
+    if (inside (buf->mbs, pic.mbs)) { pl.o_mb = (size_t) ((const uint8_t*)pic.mbs - buf->mbs.p); buf->mbs.used = pl.o_mb + b_mb; }       // parsed in place
+    else { pl.o_mb = buf->mbs.take (b_mb); if (pl.o_mb != (size_t) -1) memcpy (buf->mbs.p + pl.o_mb, pic.mbs, b_mb); }
+    if (b_co && inside (buf->coefs, pic.coefs)) { pl.o_co = (size_t) ((const uint8_t*)pic.coefs - buf->coefs.p); buf->coefs.used = pl.o_co + b_co; }
+    else { pl.o_co = buf->coefs.take (b_co); if (pl.o_co != (size_t) -1 && b_co) memcpy (buf->coefs.p + pl.o_co, pic.coefs, b_co); }
     if (pl.o_sl == (size_t) -1 || pl.o_mb == (size_t) -1 || pl.o_co == (size_t) -1) { buf->failed = true; return LH264_E_NOMEM; }
     memcpy (buf->slices.p + pl.o_sl, pic.slices, b_sl);
-    memcpy (buf->mbs.p + pl.o_mb, pic.mbs, b_mb);
-    if (b_co) memcpy (buf->coefs.p + pl.o_co, pic.coefs, b_co);
+    if (arena) arena->picture_done();
     buf->placed.push_back (pl);
     placed_now++;
     cur_ = (int)buf->placed.size() - 1;
@@ -101,15 +139,18 @@ class StageSink : public PictureSink {
     if (cur_ < 0 || cur_ >= (int)buf->placed.size()) return 0;
     Placed& pl = buf->placed[cur_];
     const size_t b_sl = (size_t)pic.n_slices * sizeof (lh264_model_slice), b_rc = (size_t)pic.n_recs * sizeof (lh264_model_mb);
-    pl.o_msl = buf->mslices.take (b_sl); pl.o_mr = buf->mrecs.take (b_rc);
+    pl.o_msl = buf->mslices.take (b_sl);
+    if (inside (buf->mrecs, pic.recs)) { pl.o_mr = (size_t) ((const uint8_t*)pic.recs - buf->mrecs.p); buf->mrecs.used = pl.o_mr + b_rc; }
+    else { pl.o_mr = buf->mrecs.take (b_rc); if (pl.o_mr != (size_t) -1) memcpy (buf->mrecs.p + pl.o_mr, pic.recs, b_rc); }
     if (pl.o_msl == (size_t) -1 || pl.o_mr == (size_t) -1) { buf->failed = true; return LH264_E_NOMEM; }
     memcpy (buf->mslices.p + pl.o_msl, pic.slices, b_sl);
-    memcpy (buf->mrecs.p + pl.o_mr, pic.recs, b_rc);
     pl.n_mslices = pic.n_slices; pl.n_mrecs = pic.n_recs;
     return 0;
   }
-  void begin_step (StepBuf* b) { buf = b; cur_ = -1; placed_now = 0; }
+  void begin_step (StepBuf* b, StepArena* a) { buf = b; arena = a; cur_ = -1; placed_now = 0; }
+  StepArena* arena = nullptr;
  private:
+  static bool inside (const PinRegion& r, const void* p) { return r.p && (const uint8_t*)p >= r.p && (const uint8_t*)p < r.p + r.cap; }
   int cur_ = -1;
 };
 
@@ -161,7 +202,7 @@ struct Worker {
   std::vector<StepBuf> bufs;
   long steps_done = 0;                  // guarded by Pipeline::mu
   bool finished = false;                // no picture after step steps_done - 1
-  double busy = 0, wait = 0;
+  double busy = 0, wait = 0, alloc = 0;
   std::thread th;
 };
 
@@ -176,7 +217,7 @@ struct Pipeline {
   bool abort = false;
   int rc = 0;
   long pictures = 0;
-  double t_wait_parse = 0, t_wait_gpu = 0, t_end = 0, t_first = 0;
+  double t_wait_parse = 0, t_wait_gpu = 0, t_end = 0, t_first = 0, t_open = 0;
   long first_pictures = 0;
   size_t h2d = 0, d2h = 0;
   unsigned long long launches = 0;
@@ -185,8 +226,8 @@ struct Pipeline {
 };
 
 // Parses until the stream has placed one picture into `buf` (or ended).  h264dec's unit loop, h264dec.cpp:246-364.
-void advance (Stream& s, StepBuf* buf, bool want_pip, long max_pictures) {
-  s.sink.begin_step (buf);
+void advance (Stream& s, StepBuf* buf, StepArena* arena, bool want_pip, long max_pictures) {
+  s.sink.begin_step (buf, arena);
   if (max_pictures > 0 && s.parsed >= max_pictures) return;
   if (!s.spill.empty()) {                // a picture that was completed together with an earlier one
     Stream::Spill& sp = s.spill.front();
@@ -203,6 +244,8 @@ void advance (Stream& s, StepBuf* buf, bool want_pip, long max_pictures) {
     s.parsed++;
     return;
   }
+  arena->bind (buf);
+  if (!s.dec->set_arena (arena)) { buf->failed = true; return; }   // (a picture left open by the previous step moves into this buffer)
   const size_t first = buf->placed.size();
   const size_t m0[5] = {buf->slices.used, buf->mbs.used, buf->coefs.used, buf->mslices.used, buf->mrecs.used};
   while (s.sink.placed_now == 0 && !s.flushed) {
@@ -245,6 +288,8 @@ void advance (Stream& s, StepBuf* buf, bool want_pip, long max_pictures) {
     buf->mrecs.used = f.n_mrecs ? f.o_mr + (size_t)f.n_mrecs * sizeof (lh264_model_mb) : m0[4];
     buf->placed.resize (first + 1);
   }
+  // a picture still in progress (damaged streams: completed only by the arrival of the next one) must not stay in this buffer
+  if (s.dec->picture_open() && !s.dec->set_arena (nullptr)) buf->failed = true;
   (void)m0;
   if (buf->placed.size() > first) s.parsed++;
 }
@@ -254,6 +299,7 @@ void worker_main (Worker* w) {
   lh264_rt* rt = P->rt;
   const int D = (int)w->bufs.size();
   const bool want_pip = rt->cfg.want_pip != 0;
+  StepArena arena;
   for (long k = 0;; k++) {
     {
       const double t0 = now();
@@ -268,7 +314,7 @@ void worker_main (Worker* w) {
     bool more = false;
     for (int si : w->streams) {
       Stream& s = *rt->streams[si];
-      advance (s, &b, want_pip, rt->cfg.max_pictures);
+      advance (s, &b, &arena, want_pip, rt->cfg.max_pictures);
       if (!s.spill.empty() || (!s.flushed && !(rt->cfg.max_pictures > 0 && s.parsed >= rt->cfg.max_pictures))) more = true;
     }
     w->busy += now() - t0;
@@ -356,6 +402,7 @@ void pipeline_main (Pipeline* P) {
         if (want_yuv) { if (lh264_output_wait (ctx) != LH264_OK) FAIL ("lh264_output_wait"); if (prev.valid) { deliver (prev); prev.valid = false; } }
         if (lh264_sync (ctx) != LH264_OK) FAIL ("lh264_sync");
       }
+      const double to0 = now();
       for (const Placed& pl : step) {
         Stream& s = *rt->streams[pl.stream];
         if (s.geo_seen != pl.geo_serial) {
@@ -371,6 +418,7 @@ void pipeline_main (Pipeline* P) {
           if (s.model_stream < 0) FAIL ("lh264_model_open");
         }
       }
+      P->t_open += now() - to0;
     }
     // ---- descriptors ----
     descs.clear(); mdescs.clear(); rd_streams.clear(); rd_slots.clear();
@@ -403,10 +451,12 @@ void pipeline_main (Pipeline* P) {
         else if (out_w != pl.info.width || out_h != pl.info.height || crop_x != pl.info.crop_x || crop_y != pl.info.crop_y) same_geometry = false;
       }
       // ---- the device ----
+      static const bool parse_only = getenv ("LH264_RT_PARSE_ONLY") != nullptr;   // diagnostic: how fast the parse threads alone are
+      if (parse_only) { descs.clear(); mdescs.clear(); }
       if (!descs.empty() && lh264_recon_submit (ctx, descs.data(), (int)descs.size()) != LH264_OK) FAIL ("lh264_recon_submit");
       if (!mdescs.empty() && lh264_model_submit (ctx, mdescs.data(), (int)mdescs.size()) != LH264_OK) FAIL ("lh264_model_submit");
       const double tg0 = now();
-      if (want_yuv) {
+      if (want_yuv && !parse_only) {
         // the pictures of step k - 1 were on their way to the host while step k's records went up: take them now, start this
         // step's copy, then hash / hand out the previous pictures while it runs
         if (lh264_output_wait (ctx) != LH264_OK) FAIL ("lh264_output_wait");
@@ -562,6 +612,10 @@ int lh264_rt_run (lh264_rt* rt, lh264_rt_picture_fn fn, void* user) {
       W->pl = P.get();
       W->bufs.resize (rt->cfg.depth);
       for (int i = first + w; i < last; i += tw) W->streams.push_back (i);
+      for (StepBuf& b : W->bufs) {
+        b.expect = W->streams.size();
+        b.mbs.alloc_s = b.coefs.alloc_s = b.mrecs.alloc_s = b.slices.alloc_s = b.mslices.alloc_s = &W->alloc;
+      }
       P->workers.push_back (std::move (W));
     }
     pipes.push_back (std::move (P));
@@ -586,7 +640,8 @@ int lh264_rt_run (lh264_rt* rt, lh264_rt_picture_fn fn, void* user) {
     st.pictures += P->pictures; st.submit_wait_parse_s += P->t_wait_parse; st.submit_wait_gpu_s += P->t_wait_gpu;
     st.h2d_bytes += P->h2d; st.d2h_bytes += P->d2h;
     if (P->t_first > 0) { st.setup_s = std::max (st.setup_s, P->t_first - t0); st.setup_pictures += P->first_pictures; }
-    for (auto& w : P->workers) { st.parse_busy_s += w->busy; st.parse_wait_s += w->wait; st.threads++; }
+    for (auto& w : P->workers) { st.parse_busy_s += w->busy; st.parse_wait_s += w->wait; st.pinned_alloc_s += w->alloc; st.threads++; }
+    st.open_streams_s += P->t_open;
     st.kernel_launches += lh264_kernel_launches (P->ctx);
   }
   for (auto& sp : rt->streams) {

@@ -26,7 +26,7 @@ class RtStats(C.Structure):
     _fields_ = [("streams", C.c_long), ("pictures", C.c_long), ("seconds", C.c_double), ("seconds_total", C.c_double),
                 ("input_bytes", C.c_size_t), ("pip_bytes", C.c_size_t), ("submit_wait_parse_s", C.c_double), ("submit_wait_gpu_s", C.c_double),
                 ("parse_busy_s", C.c_double), ("parse_wait_s", C.c_double), ("kernel_launches", C.c_ulonglong),
-                ("h2d_bytes", C.c_size_t), ("d2h_bytes", C.c_size_t), ("setup_s", C.c_double), ("setup_pictures", C.c_long),
+                ("h2d_bytes", C.c_size_t), ("d2h_bytes", C.c_size_t), ("setup_s", C.c_double), ("setup_pictures", C.c_long), ("pinned_alloc_s", C.c_double), ("open_streams_s", C.c_double),
                 ("threads", C.c_int32), ("pipelines", C.c_int32)]
 
 

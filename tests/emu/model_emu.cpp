@@ -8,12 +8,12 @@
 #include "../../losslessh264_b200/csrc/model_kernels.cuh"
 #include "../../losslessh264_b200/host/decoder.h"
 #include "../../losslessh264_b200/host/pip_container.h"
-#include "model_emu_core.h"
 #include <string>
 #include <vector>
 
 using namespace lh264m;
 using namespace lh264host;
+#include "model_emu_core.h"
 
 class ModelEmuSink : public PictureSink {
  public:

@@ -23,6 +23,8 @@ class ModelEmu {
       open_ = true;
     }
     if (pic.mb_w * pic.mb_h > max_mbs_) return -1;
+    // The generation launches of model_launch (model_host.inl).  The picture's records and coefficients must outlive this call only
+    // until it returns: the coder, which runs later (flush), reads the decision pool and the CodeJob, nothing of the picture.
     MPicDev d;
     memset (&d, 0, sizeof (d));
     std::vector<uint32_t> rec_cnt (pic.n_recs, 0u), rec_off (pic.n_recs, 0u);
@@ -37,27 +39,49 @@ class ModelEmu {
     memset (&ctl, 0, sizeof (ctl));
     const int total_recs = pic.n_recs, blocks = (total_recs + GEN_THREADS - 1) / GEN_THREADS;
     const size_t gen_smem = (size_t)GEN_THREADS * sizeof (ThreadMb);
+    if ((int)jobs_.size() >= code_steps_) { const int rc = flush(); if (rc) return rc; }
+    PoolDev pool{ &pool_used_, &pages_pending_ };
     emu::launch (1, 1, 32, [&] { k_model_frame (pd, 1, &poison); });
     emu::launch ((unsigned)blocks, 1, GEN_THREADS, [&] { k_model_count (pd, 1, total_recs, &poison); }, gen_smem);
     emu::launch (1, 1, 1024, [&] { k_model_scan (pd, 1, &pic_total, &poison); });
-    for (int attempt = 0; attempt < 2; attempt++) {
+    for (int attempt = 0; attempt < 3; attempt++) {
       ArenaDev ar{ page_ptrs_.data(), &next_, (unsigned int)page_ptrs_.size() };
-      emu::launch (1, 1, 1024, [&] { k_model_plan (1, &pic_total, &dec_base, &ctl, (unsigned long long)dec_.size(), ar, &poison); });
+      emu::launch (1, 1, 1024, [&] { k_model_plan (1, &pic_total, &dec_base, &ctl, (unsigned long long)dec_.size(), ar, pool, &poison); });
       if (!ctl.skip) break;
-      poison = 0;                                     // grow and plan again (model_complete, model_host.inl)
+      poison = 0;                                     // code what is pending (empties the pool), grow, plan again (model_settle_batch)
+      const int rc = flush();
+      if (rc) return rc;
       if (ctl.total + 32 > dec_.size()) dec_.assign ((size_t)ctl.total + ctl.total / 4 + 64, 0u);
       while (page_ptrs_.size() < (size_t)ctl.pages_in_use + 2 * ctl.pages_needed) { pages_.emplace_back (PAGE_SIZE, 0); page_ptrs_.push_back (pages_.back().data()); }
     }
     if (ctl.skip) return -2;
-    ArenaDev ar{ page_ptrs_.data(), &next_, (unsigned int)page_ptrs_.size() };
     uint32_t* dec = dec_.data();
     emu::launch ((unsigned)blocks, 1, GEN_THREADS, [&] { k_model_emit (pd, 1, total_recs, dec, &dec_base, &ctl); }, gen_smem);
-    emu::launch (1, 1, 64, [&] { k_model_code (pd, 1, dec, &dec_base, &pic_total, ar, &ctl); });
+    CodeJob job;
+    memset (&job, 0, sizeof (job));
+    emu::launch (1, 1, 128, [&] { k_model_commit (pd, 1, &dec_base, &pic_total, &ctl, &job); });
+    jobs_.push_back (job);
     return st_.error ? -3 : 0;
   }
+  // = model_flush_coder: ONE k_model_code launch codes the pending pictures of the stream in order
+  int flush() {
+    if (jobs_.empty()) return 0;
+    const int T = (int)jobs_.size();
+    std::vector<int> index (T, 0);                    // one stream = one block; step j's job row holds one job, at position 0
+    ArenaDev ar{ page_ptrs_.data(), &next_, (unsigned int)page_ptrs_.size() };
+    const CodeJob* jobs = jobs_.data();
+    const int* idx = index.data();
+    const uint32_t* dec = dec_.data();
+    emu::launch (1, 1, 64, [&] { k_model_code (jobs, idx, T, 1, dec, ar); });
+    jobs_.clear();
+    pool_used_ = 0; pages_pending_ = 0;
+    return st_.error ? -3 : 0;
+  }
+  void set_code_steps (int t) { code_steps_ = t < 1 ? 1 : t; }
   // = lh264_model_finish
   int finish() {
     if (!open_) return 0;
+    { const int rc = flush(); if (rc) return rc; }
     while (page_ptrs_.size() < (size_t)next_ + CT_COUNT) { pages_.emplace_back (PAGE_SIZE, 0); page_ptrs_.push_back (pages_.back().data()); }
     ArenaDev ar{ page_ptrs_.data(), &next_, (unsigned int)page_ptrs_.size() };
     MState* st = &st_;
@@ -81,6 +105,10 @@ class ModelEmu {
     return true;
   }
  private:
+  std::vector<CodeJob> jobs_;                          // pending: generated, not coded yet
+  unsigned long long pool_used_ = 0;
+  unsigned int pages_pending_ = 0;
+  int code_steps_ = getenv ("LH264_CODE_STEPS") ? atoi (getenv ("LH264_CODE_STEPS")) : 4;
   bool open_ = false;
   int max_mbs_ = 0;
   MState st_;

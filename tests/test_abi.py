@@ -60,7 +60,7 @@ def test_runtime_entry_points_are_exported():
     # the ctypes mirror of the structs has the C layout
     from losslessh264_b200.runtime import RtConfig, RtStats, RtStreamResult
 
-    assert C.sizeof(RtConfig) == 64 and C.sizeof(RtStreamResult) == 2 * 8 + 82 + 6 + 8 + 8 and C.sizeof(RtStats) == 16 * 8
+    assert C.sizeof(RtConfig) == 64 and C.sizeof(RtStreamResult) == 2 * 8 + 82 + 6 + 8 + 8 and C.sizeof(RtStats) == 18 * 8
 
 
 def test_record_layouts():
