@@ -94,15 +94,16 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": int(self.rows[0][1]) if self.rows[0][1].isdigit() else None, "reasons": reasons, "samples": len(self.rows)}
 
 
-def run_reference_once(k, tmp):
+def run_reference_once(k, tmp, streams=None):
     """k concurrent reference processes (the reference is single-threaded with process-global model
     state, one stream per process).  Returns (frames/s by the tool's own decode time, frames/s by wall)."""
     procs = []
+    streams = streams or STREAMS
     t0 = time.time()
     for i in range(k):
         d = os.path.join(tmp, f"p{i}")
         os.makedirs(d, exist_ok=True)
-        procs.append(subprocess.Popen([REF_DEC, STREAMS[i % len(STREAMS)], os.path.join(d, "o.pip"), os.path.join(d, "o.yuv")], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True))
+        procs.append(subprocess.Popen([REF_DEC, streams[i % len(streams)], os.path.join(d, "o.pip"), os.path.join(d, "o.yuv")], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True))
     fps_core, frames = 0.0, 0
     for p in procs:
         err = p.communicate()[1]
@@ -223,14 +224,14 @@ def ncu_traffic(kernel):
     return best
 
 
-def bench_runtime(streams_bytes, S, threads, loops, device, want_yuv, pipelines=1, verify=None):
+def bench_runtime(streams_bytes, S, threads, loops, device, want_yuv, pipelines=1, verify=None, stagger=True):
     """Bitstream-in leg through lh264_rt_* (include/lh264_runtime.h).  Returns the stats dict + pictures."""
     from losslessh264_b200.runtime import Runtime
 
     rt = Runtime(device=device, threads=threads, pipelines=pipelines, want_yuv=want_yuv, want_hash=verify is not None, want_pip=True, loops=loops)
     bufs = {}
     for i in range(S):
-        key = (i % len(streams_bytes), (i % N_SEQ_FRAMES) if verify is None else 0)
+        key = (i % len(streams_bytes), (i % N_SEQ_FRAMES) if (verify is None and stagger) else 0)
         if key not in bufs:
             rt.add(staggered_input(streams_bytes[key[0]], key[1]))
             bufs[key] = (rt._keep[-1], len(rt._keep[-1]) - 4)
@@ -321,6 +322,7 @@ def main():
     ap.add_argument("--e2e-pipelines", type=int, default=1)
     ap.add_argument("--no-records-leg", action="store_true", help="skip e2e_records (round 1's host-records figure)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-workloads", action="store_true", help="skip the extra legs for BASELINE configs 3 (720p) and 5 (4k multi-slice LTR)")
     ap.add_argument("--no-expand", action="store_true", help="skip the decompress-direction leg")
     ap.add_argument("--expand-streams", type=int, default=2048, help="streams of the decompress-direction leg (one warp each; throughput peaks near 2048, profiles/r1_summary.md)")
     args = ap.parse_args()
@@ -464,6 +466,18 @@ def main():
     }
     mb_per_frame = stream_bytes / n_frames / 1e6
 
+    # ---- make room: the host-buffer legs open their own contexts and device streams ------------------------------------
+    for b in batches:
+        ctx.free_batch(b)
+    for b in mbatches:
+        ctx.model_free_batch(b)
+    batches, mbatches = [], []
+    for h_ in streams:
+        ctx.close_stream(h_)
+    for h_ in mstreams:
+        ctx.model_close(h_)
+    mstreams = []
+
     # ---- e2e_records (round 1's figure): pre-parsed records in pinned host memory in, decoded pictures back -----------
     if not args.no_records_leg:
         T = 8
@@ -530,18 +544,6 @@ def main():
                                "path": "pre-parsed records in pinned host memory -> lh264_recon_submit + lh264_model_submit -> lh264_pictures_read_packed (parse NOT included)"}
         keep = []
 
-    # ---- make room: the bitstream-in legs open their own device streams ------------------------------------------------
-    for b in batches:
-        ctx.free_batch(b)
-    for b in mbatches:
-        ctx.model_free_batch(b)
-    batches, mbatches = [], []
-    for h_ in streams:
-        ctx.close_stream(h_)
-    for h_ in mstreams:
-        ctx.model_close(h_)
-    mstreams = []
-
     # ---- e2e: Annex-B bytes in host memory -> lh264_rt_run -> I420 in pinned host memory + `.pip` ---------------------
     cores = os.cpu_count() or 1
     threads = args.e2e_threads or max(1, cores // world)
@@ -581,6 +583,34 @@ def main():
                           "device_resident_mb_s": round(value_mod * mb_per_frame, 2),
                           "path": "bitstream in -> lh264_rt_run(want_yuv = 0): host parse + lh264_model_submit only (`h264dec in.264 out.pip`)"}
 
+    # ---- BASELINE configs 3 and 5 through the same bitstream-in path (extra keys; the headline stays config 4) -------------
+    if not args.no_workloads:
+        line["workloads"] = {}
+        for key, fname, Sw, loops_w, note in (
+                ("syn720p_8f", "syn720p_8f.264", 512, 4, "BASELINE config 3 shape: 1280x720, 8 pictures, decode + recompress"),
+                ("syn4k_8slices_ltr_4f", "syn4k_8slices_ltr_4f.264", 64, 4, "BASELINE config 5 shape: 4096x2304, 8 slices per picture, two long-term references, recompression corpus")):
+            path = os.path.join(ROOT, "tests", "golden", "streams", fname)
+            wdata = [open(path, "rb").read()]
+            barrier()
+            sw, _ = bench_runtime(wdata, Sw, threads, loops_w, local, True, pipelines=args.e2e_pipelines, stagger=False)
+            barrier()
+            sw2, _ = bench_runtime(wdata, Sw, threads, loops_w, local, False, pipelines=args.e2e_pipelines, stagger=False)
+            t1 = max_over_ranks(max(1e-9, sw["seconds"] - sw["setup_s"]) * 1000.0) / 1000.0
+            t2 = max_over_ranks(max(1e-9, sw2["seconds"] - sw2["setup_s"]) * 1000.0) / 1000.0
+            f1 = world * (sw["pictures"] - sw["setup_pictures"]) / t1
+            f2 = world * (sw2["pictures"] - sw2["setup_pictures"]) / t2
+            n_fr = sw["pictures"] // (Sw * loops_w)
+            w = {"note": note, "streams_per_gpu": Sw, "loops": loops_w, "pictures_per_stream": int(n_fr),
+                 "decode_recompress_frames_per_s": round(f1, 1), "recompress_only_frames_per_s": round(f2, 1),
+                 "recompress_only_input_mb_s": round(f2 * len(wdata[0]) / max(1, n_fr) / 1e6, 2), "path": "bitstream in -> lh264_rt_run (as e2e / recompress)"}
+            if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(REF_DEC):
+                k, _cores = reference_concurrency()
+                with tempfile.TemporaryDirectory() as tmp:
+                    core, wall, frames = run_reference_once(k, tmp, [path])
+                w["reference_frames_per_s"] = round(core, 2)
+                w["reference_note"] = f"{k} concurrent oracle/_ref/h264dec processes on the same stream (parse + model + reconstruction, tool-reported decode time)"
+            line["workloads"][key] = w
+
     if not args.no_expand:
         line["expand"] = bench_expand(ctx, parsed[0][1], args.expand_streams, world)
     if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(REF_DEC):
@@ -596,6 +626,22 @@ def main():
                     line["expand"]["reference_note"] = "reference decompress failed: " + str(e)[:200]
         line["cpu_baseline"] = {"value": round(core, 2), "unit": UNIT, "cores": k, "host_cores": cores, "kind": "reference",
                                 "sample": f"{k} concurrent oracle/_ref/h264dec processes x 16 frames, process i on bench stream i mod 8 (parse + model + reconstruction, tool-reported decode time; {wall:.2f} frames/s including the ~8 s start-up per process)"}
+    # ---- the drop-in CLI on ONE stream (one picture per submit, a device sync per picture: latency, not throughput) ---------
+    H264DEC = os.path.join(ROOT, "losslessh264_b200", "_lib", "h264dec_lh264")
+    if rank == 0 and world == 1 and os.path.exists(H264DEC):
+        ctx.close()
+        with tempfile.TemporaryDirectory() as tmp:
+            best = None
+            for _ in range(2):
+                r = subprocess.run([H264DEC, STREAM, os.path.join(tmp, "o.pip"), os.path.join(tmp, "o.yuv")], capture_output=True, text=True)
+                m = re.search(r"Frames:\s+(\d+)\s+decode time:\s+([\d.]+) sec", r.stderr)
+                if r.returncode == 0 and m:
+                    fps = int(m.group(1)) / max(1e-9, float(m.group(2)))
+                    best = fps if best is None else max(best, fps)
+        ref_core = line["cpu_baseline"]["value"] / line["cpu_baseline"]["cores"] if "cpu_baseline" in line else None
+        line["single_stream"] = {"h264dec_lh264_frames_per_s": round(best, 2) if best else None, "reference_frames_per_s_per_core": round(ref_core, 2) if ref_core else None,
+                                 "note": "`h264dec_lh264 in.264 out.pip out.yuv` on one bench stream through ISVCDecoder::DecodeFrameNoDelay (tool-reported decode time, "
+                                         "best of 2): one 1080p picture per launch cannot fill 148 SMs; throughput comes from batching streams (e2e)"}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

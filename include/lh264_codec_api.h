@@ -9,8 +9,11 @@
 #ifndef LH264_CODEC_API_H_
 #define LH264_CODEC_API_H_
 
+#include <stddef.h>
 #ifdef __cplusplus
 #define LH264_EXTAPI
+#else
+#include <stdbool.h>                      /* the C view (codec_api.h:482-520) uses bool in its structs, codec_app_def.h:43-47 */
 #endif
 
 /* codec_app_def.h:76-100 */

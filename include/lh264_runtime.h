@@ -91,6 +91,8 @@ int  lh264_rt_stream_result_get (const lh264_rt* rt, int stream, lh264_rt_stream
 long long lh264_rt_pip_read (const lh264_rt* rt, int stream, int tag, uint8_t* dst, size_t cap);
 int  lh264_rt_stats_get (const lh264_rt* rt, lh264_rt_stats* out);
 const char* lh264_rt_last_error (const lh264_rt* rt);
+/* The pinned staging memory of finished runs is kept for the next run of the process (pinning is slow); this gives it back.   */
+void lh264_rt_trim (void);
 
 #ifdef __cplusplus
 }

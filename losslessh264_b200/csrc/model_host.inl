@@ -353,9 +353,16 @@ static int model_launch (lh264_ctx* c, ModelCtx* m, MBatch& b, bool head, bool t
 static int model_grow_pool (lh264_ctx* c, ModelCtx* m, unsigned long long step_total) {
   (void)c;
   const size_t one = (size_t)step_total + (size_t)step_total / 4 + 64;
-  const size_t want = std::max (one, std::min (one * (size_t)m->code_steps, m->dec_cap_limit));
-  if (want > m->dec.cap) { CK (cudaStreamSynchronize (m->stream)); CK (m->dec.reserve (want)); }
-  return LH264_OK;
+  size_t want = std::max (one, std::min (one * (size_t)m->code_steps, m->dec_cap_limit));
+  if (want <= m->dec.cap) return LH264_OK;
+  CK (cudaStreamSynchronize (m->stream));
+  // room for code_steps steps is a wish, room for one step a need: halve the wish until the device has it
+  for (;;) {
+    if (m->dec.reserve (want) == cudaSuccess) return LH264_OK;
+    cudaGetLastError();
+    if (want == one) return fail (LH264_E_NOMEM, "out of device memory for the model's decision pool");
+    want = std::max (one, want / 2);
+  }
 }
 
 // blocking: runs a batch to completion, growing the decision list / output arena until it fits

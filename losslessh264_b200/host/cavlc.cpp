@@ -102,6 +102,9 @@ bool cavlc_selfcheck() {
   return ok;
 }
 
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__) && !defined(LH264_NO_CLONES)
+__attribute__ ((target_clones ("arch=x86-64-v3", "default")))       // see decoder.cpp LH264_HOT
+#endif
 int cavlc_residual_block (BitReader& br, int nC, int max_coeff, const uint8_t* scan, int scan_step, int scan_off, int16_t* out) {
   int total, t1;
   if (nC < 0) {

@@ -8,6 +8,18 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <algorithm>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
+// The slice-data parser is the host-side bottleneck of the bitstream-in path: its hot functions are compiled twice, for
+// x86-64-v3 (AVX2 / BMI1 / BMI2 / LZCNT / MOVBE: variable shifts, bit counts and the byte swap of the bit reader are single
+// instructions there) and for the baseline ISA; the loader picks per CPU.  Same source, same results.
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__) && !defined(LH264_NO_CLONES)
+#define LH264_HOT __attribute__ ((target_clones ("arch=x86-64-v3", "default")))
+#else
+#define LH264_HOT
+#endif
 
 namespace lh264host {
 
@@ -39,6 +51,26 @@ struct RefPic {
 };
 
 struct Nb { bool avail; int ref; int mvx, mvy; };
+
+// Records the parser never reads back (model records, coefficient pools) leave with non-temporal stores: no read-for-ownership
+// of ~180 bytes per macroblock of staging memory that is only written here and read by the DMA engine.  With sixteen parse
+// threads the host memory system, not the parse, sets the pace.
+inline void stream_copy (void* dst, const void* src, size_t bytes) {          // bytes: multiple of 16
+#if defined(__SSE2__)
+  if ((reinterpret_cast<uintptr_t> (dst) & 15) == 0) {
+    __m128i* d = static_cast<__m128i*> (dst);
+    const __m128i* q = static_cast<const __m128i*> (src);
+    for (size_t i = 0; i < bytes / 16; i++) _mm_stream_si128 (d + i, _mm_loadu_si128 (q + i));
+    return;
+  }
+#endif
+  memcpy (dst, src, bytes);
+}
+inline void stream_fence() {
+#if defined(__SSE2__)
+  _mm_sfence();
+#endif
+}
 
 // Growable array of hand-off records that lives either in heap memory of the decoder or in a RecordArena (decoder.h).  grow()
 // leaves the new elements uninitialised (the parser overwrites every one of them).
@@ -406,6 +438,7 @@ struct Decoder::Impl {
     if (!open) return 0;
     open = false;
     if (decoded < n_mbs) { for (int i = 0; i < n_mbs; i++) if (mb_slice[i] < 0) mbs[i].mb_type = LH264_MB_NONE; }
+    stream_fence();                                   // the streamed records are visible before anybody is told about them
     lh264_picture_desc d;
     d.stream = 0; d.cur_slot = cur_slot; d.n_slices = (int)slices.size(); d.n_coef_blocks = (int) (coefs.size() / 16);
     d.slices = slices.data(); d.mbs = mbs.data(); d.coefs = coefs.data();
@@ -523,7 +556,7 @@ void Decoder::Impl::resolve_intra (lh264_mb_rec& m, int mb_addr, const int8_t* m
 }
 
 // ---- residual( ) for CAVLC (7.3.5.3) --------------------------------------------------------------------
-int Decoder::Impl::parse_residual (BitReader& br, lh264_mb_rec& m, int mb_addr, int16_t* lev, uint32_t& coded, bool i16, int cbp) {
+LH264_HOT int Decoder::Impl::parse_residual (BitReader& br, lh264_mb_rec& m, int mb_addr, int16_t* lev, uint32_t& coded, bool i16, int cbp) {
   uint8_t* nz = &nzc[(size_t)mb_addr * 24];
   const bool t8 = m.flags & LH264_MBF_TRANSFORM8x8;
   if (i16) {                                        // Intra16x16DCLevel: 16 DC levels, zig-zag over the 4x4 DC matrix
@@ -568,7 +601,7 @@ int Decoder::Impl::parse_residual (BitReader& br, lh264_mb_rec& m, int mb_addr, 
 }
 
 // ---- macroblock_layer( ) (7.3.5) -----------------------------------------------------------------------
-int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_model_mb* mr) {
+LH264_HOT int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_model_mb* mr) {
   lh264_mb_rec& m = mbs[mb_addr];
   memset (&m, 0, sizeof (m));
   cur_mb = mb_addr;
@@ -813,7 +846,7 @@ int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped, lh264_mod
       m.coef_off = (uint32_t) (coefs.size() / 16);
       int16_t* o = coefs.grow (16 * (size_t)__builtin_popcount (coded));
       if (!o) { memset (lev_, 0, sizeof (lev_)); return -1; }
-      for (uint32_t mk = coded; mk; mk &= mk - 1) { const int k = __builtin_ctz (mk); memcpy (o, lev + 16 * k, 32); memset (lev + 16 * k, 0, 32); o += 16; }
+      for (uint32_t mk = coded; mk; mk &= mk - 1) { const int k = __builtin_ctz (mk); stream_copy (o, lev + 16 * k, 32); memset (lev + 16 * k, 0, 32); o += 16; }
     }
   } else {
     set_qp (m);
@@ -1135,7 +1168,7 @@ int Decoder::Impl::parse_slice_data_cabac (BitReader& br, Decoder* self) {
 }
 
 // ---- slice_data( ) (7.3.4), CAVLC --------------------------------------------------------------------------
-int Decoder::Impl::parse_slice_data (BitReader& br, Decoder* self) {
+LH264_HOT int Decoder::Impl::parse_slice_data (BitReader& br, Decoder* self) {
   int mb_addr = sh.first_mb;
   qp = sh.slice_qp;
   const int first = mb_addr;
@@ -1145,13 +1178,18 @@ int Decoder::Impl::parse_slice_data (BitReader& br, Decoder* self) {
   // model records: one per MB in slice-data order, with the reference's skip-run / stop-bit bookkeeping
   // (WelsDecodeMbCavlcPSlice decode_slice.cpp:3880-3960, WelsDecodeSliceForNonRecoding :2192-2252)
   const size_t rec0 = mrecs.size();
+  alignas (16) lh264_model_mb rec_local;              // assembled here, streamed out when the macroblock is done
   auto new_rec = [&] (int addr) -> lh264_model_mb* {
     if (!want_model) return nullptr;
-    lh264_model_mb* r = mrecs.grow (1);
-    if (!r) return nullptr;
-    memset (r, 0, sizeof (*r));
-    r->mb_addr = (uint32_t)addr; r->mb_in_slice = (uint16_t)std::min<size_t> (mrecs.size() - 1 - rec0, 65535);
-    return r;
+    memset (&rec_local, 0, sizeof (rec_local));
+    rec_local.mb_addr = (uint32_t)addr; rec_local.mb_in_slice = (uint16_t)std::min<size_t> (mrecs.size() - rec0, 65535);
+    return &rec_local;
+  };
+  auto commit_rec = [&] () -> bool {
+    lh264_model_mb* dst = mrecs.grow (1);
+    if (!dst) return false;
+    stream_copy (dst, &rec_local, sizeof (rec_local));
+    return true;
   };
   int m_cached_qp = 0, m_last_dqp = 0;                // uiCachedLumaQp / uiLastNonzeroDeltaLumaQp, decode_slice.cpp:3061-3062
   while (more && mb_addr < n_mbs) {
@@ -1166,9 +1204,11 @@ int Decoder::Impl::parse_slice_data (BitReader& br, Decoder* self) {
         if (mr) {
           if (i == 0) { mr->flags |= LH264_MM_EMIT_SKIP_RUN; mr->skip_run = (uint16_t)std::min<uint32_t> (run, 65535); }
           if (i + 1 == run) { mr->flags |= LH264_MM_STOP_IN_SKIP; if (!br.more_rbsp_data()) mr->flags |= LH264_MM_STOP_BIT; }
+          if (!commit_rec()) { rc = -1; break; }
         }
         mb_addr++;
       }
+      if (rc < 0) break;
       if (run > 0) { more = br.more_rbsp_data(); run_read = false; }
       if (!more || mb_addr >= n_mbs) break;
     }
@@ -1177,7 +1217,7 @@ int Decoder::Impl::parse_slice_data (BitReader& br, Decoder* self) {
       mr->flags |= LH264_MM_WRITE_BLOCK;
       if (run_read || sh.slice_type == SLICE_I) mr->flags |= LH264_MM_EMIT_SKIP_RUN;   // value 0
     }
-    if (parse_mb (br, mb_addr, false, mr) < 0) { rc = -1; self->stats_.errors++; if (mr) mrecs.pop_back(); break; }
+    if (parse_mb (br, mb_addr, false, mr) < 0) { rc = -1; self->stats_.errors++; break; }       // (its record is dropped)
     if (mr) {                                         // decode_slice.cpp:2267-2274
       const int d = (int)mr->luma_qp - m_cached_qp;
       mr->qp_delta = (int8_t)d;
@@ -1188,6 +1228,7 @@ int Decoder::Impl::parse_slice_data (BitReader& br, Decoder* self) {
     mb_addr++;
     more = br.more_rbsp_data();
     if (mr && !more) mr->flags |= LH264_MM_STOP_BIT;
+    if (mr && !commit_rec()) { rc = -1; break; }
   }
   lh264_slice_rec& sr = slices.back();
   sr.num_mbs = mb_addr - first;

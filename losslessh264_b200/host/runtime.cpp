@@ -23,6 +23,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <string>
@@ -39,21 +40,44 @@ namespace {
 
 double now() { return std::chrono::duration<double> (std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
+// Pinning memory is slow (cudaHostAlloc page-locks and maps every page: well under 1 GB/s when sixteen threads ask at once), and a
+// 1024-stream run stages ~8 GB.  Blocks are therefore kept for the life of the process and handed to the next run
+// (lh264_rt_trim() gives them back).
+class PinnedCache {
+ public:
+  uint8_t* get (size_t need, size_t* got) {
+    {
+      std::lock_guard<std::mutex> g (mu_);
+      auto it = free_.lower_bound (need);
+      if (it != free_.end() && it->first <= 2 * need + ((size_t)4 << 20)) { uint8_t* p = it->second; *got = it->first; free_.erase (it); return p; }
+    }
+    uint8_t* p = (uint8_t*)lh264_host_alloc (need);
+    *got = p ? need : 0;
+    return p;
+  }
+  void put (uint8_t* p, size_t cap) { if (!p) return; std::lock_guard<std::mutex> g (mu_); free_.emplace (cap, p); }
+  void trim() { std::lock_guard<std::mutex> g (mu_); for (auto& kv : free_) lh264_host_free (kv.second); free_.clear(); }
+ private:
+  std::mutex mu_;
+  std::multimap<size_t, uint8_t*> free_;
+};
+PinnedCache& pinned_cache() { static PinnedCache* c = new PinnedCache(); return *c; }   // (never destroyed: no CUDA calls at exit)
+
 struct PinRegion {                      // growable pinned buffer, bump-allocated within a step
   uint8_t* p = nullptr; size_t cap = 0, used = 0;
   double* alloc_s = nullptr;            // where the time spent in pinned allocation is accounted
-  ~PinRegion() { if (p) lh264_host_free (p); }
+  ~PinRegion() { pinned_cache().put (p, cap); }
   // returns the offset of n fresh bytes (contents so far are kept when the buffer has to grow), or (size_t)-1;
   // `room` = what the region is expected to hold in the end (pinning memory is slow: grow in few, large steps)
   size_t take (size_t n, size_t room = 0) {
     const size_t at = used, need = used + n;
     if (need > cap) {
       const double t0 = now();
-      const size_t ncap = std::max (std::max (need + need / 2, room), (size_t)1 << 16);
-      uint8_t* q = (uint8_t*)lh264_host_alloc (ncap);
+      size_t ncap = std::max (std::max (need + need / 2, room), (size_t)1 << 16);
+      uint8_t* q = pinned_cache().get (ncap, &ncap);
       if (!q) return (size_t) -1;
       if (used) memcpy (q, p, used);
-      if (p) lh264_host_free (p);
+      pinned_cache().put (p, cap);
       p = q; cap = ncap;
       if (alloc_s) *alloc_s += now() - t0;
     }
@@ -690,5 +714,7 @@ int lh264_rt_stats_get (const lh264_rt* rt, lh264_rt_stats* out) {
 }
 
 const char* lh264_rt_last_error (const lh264_rt* rt) { return rt ? rt->error.c_str() : "no runtime"; }
+
+void lh264_rt_trim (void) { pinned_cache().trim(); }
 
 } // extern "C"

@@ -55,8 +55,14 @@ def load_library():
     lib.lh264_rt_stats_get.argtypes = [C.c_void_p, C.POINTER(RtStats)]
     lib.lh264_rt_last_error.argtypes = [C.c_void_p]
     lib.lh264_rt_last_error.restype = C.c_char_p
+    lib.lh264_rt_trim.argtypes = []
     _LIB = lib
     return lib
+
+
+def trim():
+    """Gives the pinned staging memory kept from finished runs back to the system."""
+    load_library().lh264_rt_trim()
 
 
 class Runtime:

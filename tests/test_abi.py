@@ -54,7 +54,7 @@ def test_runtime_entry_points_are_exported():
     src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
     names = sorted(set(re.findall(r"\b(lh264_rt_[a-z0-9_]+)\s*\(", src)) - {"lh264_rt_picture_fn"})
     assert names == ["lh264_rt_add_stream", "lh264_rt_create", "lh264_rt_destroy", "lh264_rt_last_error", "lh264_rt_pip_read", "lh264_rt_run",
-                     "lh264_rt_stats_get", "lh264_rt_stream_result_get"]
+                     "lh264_rt_stats_get", "lh264_rt_stream_result_get", "lh264_rt_trim"]
     for n in names:
         assert hasattr(lib, n), f"{n} is declared in include/lh264_runtime.h but not exported"
     # the ctypes mirror of the structs has the C layout
