@@ -322,6 +322,7 @@ def main():
     ap.add_argument("--e2e-pipelines", type=int, default=1)
     ap.add_argument("--no-records-leg", action="store_true", help="skip e2e_records (round 1's host-records figure)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only-resident", action="store_true", help="kernel experiments: value / decode_only / model_only / roofline only")
     ap.add_argument("--no-workloads", action="store_true", help="skip the extra legs for BASELINE configs 3 (720p) and 5 (4k multi-slice LTR)")
     ap.add_argument("--no-expand", action="store_true", help="skip the decompress-direction leg")
     ap.add_argument("--expand-streams", type=int, default=2048, help="streams of the decompress-direction leg (one warp each; throughput peaks near 2048, profiles/r1_summary.md)")
@@ -465,6 +466,10 @@ def main():
         "gpu_launches": int(launches), "clocks": sampler.summary(),
     }
     mb_per_frame = stream_bytes / n_frames / 1e6
+    if args.only_resident:
+        if rank == 0:
+            print(json.dumps(line))
+        return
 
     # ---- make room: the host-buffer legs open their own contexts and device streams ------------------------------------
     for b in batches:

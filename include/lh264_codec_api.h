@@ -63,6 +63,7 @@ typedef struct TagBufferInfo {           /* codec_def.h:197-204 */
   unsigned long long uiInBsTimeStamp, uiOutYuvTimeStamp;
   union { SSysMEMBuffer sSystemBuffer; } UsrData;
 } SBufferInfo;
+typedef enum { FEEDBACK_NON_VCL_NAL = 0, FEEDBACK_VCL_NAL, FEEDBACK_UNKNOWN_NAL } FEEDBACK_VCL_NAL_IN_AU;   /* codec_app_def.h:184-188 */
 typedef struct TagDecoderCapability {    /* codec_app_def.h:590-600 */
   int iProfileIdc, iProfileIop, iLevelIdc, iMaxMbps, iMaxFs, iMaxCpb, iMaxDpb, iMaxBr;
   bool bRedPicCap;

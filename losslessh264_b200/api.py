@@ -83,7 +83,7 @@ def load_library():
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = library_path()
+    path = os.environ.get("LH264_B200_LIB") or library_path()      # (the override loads a kernel experiment build: development only)
     if not os.path.exists(path):
         raise LibraryMissing(f"{path} not built: run `python -c 'import __graft_entry__ as g; g.build()'` (there is no CPU fallback)")
     lib = C.CDLL(path)

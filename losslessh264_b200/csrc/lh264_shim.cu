@@ -97,7 +97,16 @@ struct lh264_ctx {
   PinBuf<PicDev> h_pics;
   cudaEvent_t staged = nullptr;              // h_pics consumed by the H2D copy
   bool staged_pending = false;
-  DevBuf<PackDev> pack_jobs; PinBuf<PackDev> h_pack_jobs; DevBuf<uint8_t> pack_out;
+  // packed read-back: job tables and output buffers alternate, so that a call neither waits for the kernels in front of it on the
+  // context stream nor holds them up until the previous call's copy to the host is over
+  DevBuf<PackDev> pack_jobs; PinBuf<PackDev> h_pack_jobs[2]; DevBuf<uint8_t> pack_out[2];
+  cudaEvent_t pack_copied[2] = {nullptr, nullptr}, pack_read[2] = {nullptr, nullptr};
+  bool pack_read_pending[2] = {false, false};
+  int pack_cur = 0;
+  // host-to-device copies of a submit run on a stream of their own: the records of step t+1 go up while step t's kernels run
+  cudaStream_t h2d_stream = nullptr;
+  cudaEvent_t uploaded = nullptr, decode_done[2] = {nullptr, nullptr};
+  bool decode_done_pending[2] = {false, false};
   DevBuf<uint8_t> scratch_a, scratch_b, scratch_c;
   uint64_t launches = 0;
   uint64_t batch_serial = 0;
@@ -153,6 +162,12 @@ int lh264_ctx_create (lh264_ctx** out, int device, void* cuda_stream) {
   CK (cudaEventCreateWithFlags (&c->staged, cudaEventDisableTiming));
   CK (cudaEventCreateWithFlags (&c->recon_staged, cudaEventDisableTiming));
   CK (cudaStreamCreateWithFlags (&c->d2h_stream, cudaStreamNonBlocking));
+  CK (cudaStreamCreateWithFlags (&c->h2d_stream, cudaStreamNonBlocking));
+  CK (cudaEventCreateWithFlags (&c->uploaded, cudaEventDisableTiming));
+  for (int i = 0; i < 2; i++) {
+    CK (cudaEventCreateWithFlags (&c->pack_copied[i], cudaEventDisableTiming)); CK (cudaEventCreateWithFlags (&c->pack_read[i], cudaEventDisableTiming));
+    CK (cudaEventCreateWithFlags (&c->decode_done[i], cudaEventDisableTiming));
+  }
   CK (cudaEventCreateWithFlags (&c->packed, cudaEventDisableTiming));
   CK (cudaEventCreateWithFlags (&c->d2h_done, cudaEventDisableTiming));
   for (int i = 0; i < 2; i++) CK (cudaEventCreateWithFlags (&c->batch_free[i], cudaEventDisableTiming));
@@ -171,7 +186,15 @@ void lh264_ctx_destroy (lh264_ctx* c) {
   if (c->d_error) cudaFree (c->d_error);
   c->batch[0].release(); c->batch[1].release(); c->h_pics.release();
   for (int i = 0; i < 2; i++) if (c->batch_free[i]) cudaEventDestroy (c->batch_free[i]);
-  c->pack_jobs.release(); c->h_pack_jobs.release(); c->pack_out.release();
+  c->pack_jobs.release();
+  for (int i = 0; i < 2; i++) {
+    c->h_pack_jobs[i].release(); c->pack_out[i].release();
+    if (c->pack_copied[i]) cudaEventDestroy (c->pack_copied[i]);
+    if (c->pack_read[i]) cudaEventDestroy (c->pack_read[i]);
+    if (c->decode_done[i]) cudaEventDestroy (c->decode_done[i]);
+  }
+  if (c->uploaded) cudaEventDestroy (c->uploaded);
+  if (c->h2d_stream) { cudaStreamSynchronize (c->h2d_stream); cudaStreamDestroy (c->h2d_stream); }
   c->scratch_a.release(); c->scratch_b.release(); c->scratch_c.release();
   if (c->staged) cudaEventDestroy (c->staged);
   if (c->recon_staged) cudaEventDestroy (c->recon_staged);
@@ -247,7 +270,7 @@ static int stage_batch (lh264_ctx* c, BatchDev& b, PinBuf<PicDev>& h_pics, const
   CK (h_pics.reserve (n));
   size_t o_mb = 0, o_blk = 0, o_sl = 0;
   b.n_pics = n; b.max_rows = 0;
-  CopyMerger cm_mb (c->stream), cm_co (c->stream), cm_sl (c->stream);
+  CopyMerger cm_mb (c->h2d_stream), cm_co (c->h2d_stream), cm_sl (c->h2d_stream);
   for (int i = 0; i < n; i++) {
     const lh264_picture_desc& p = pics[i];
     const StreamRec& s = c->streams[p.stream];
@@ -264,9 +287,11 @@ static int stage_batch (lh264_ctx* c, BatchDev& b, PinBuf<PicDev>& h_pics, const
   }
   cm_mb.flush(); cm_co.flush(); cm_sl.flush();
   CK (cm_mb.err); CK (cm_co.err); CK (cm_sl.err);
-  CK (cudaMemcpyAsync (b.pics.p, h_pics.p, n * sizeof (PicDev), cudaMemcpyHostToDevice, c->stream));
-  CK (cudaEventRecord (c->staged, c->stream));
+  CK (cudaMemcpyAsync (b.pics.p, h_pics.p, n * sizeof (PicDev), cudaMemcpyHostToDevice, c->h2d_stream));
+  CK (cudaEventRecord (c->staged, c->h2d_stream));
   c->staged_pending = true;
+  CK (cudaEventRecord (c->uploaded, c->h2d_stream));
+  CK (cudaStreamWaitEvent (c->stream, c->uploaded, 0));          // the kernels of this batch start when its records are in HBM
   CK (b.row_sync.reserve (4 + (size_t)n * b.max_rows));
   return LH264_OK;
 }
@@ -309,14 +334,20 @@ int lh264_recon_submit (lh264_ctx* c, const lh264_picture_desc* pics, int n_pics
     // space and waiting to be run again) before the pools are overwritten
     int rs = model_settle_sharer (c, k);
     if (rs) return rs;
-    CK (cudaStreamWaitEvent (c->stream, c->batch_free[k], 0));
+    CK (cudaStreamWaitEvent (c->h2d_stream, c->batch_free[k], 0));
     c->batch_shared[k] = false;
   }
+  // ... and so must the reconstruction kernel that read this staging buffer two submits ago
+  if (c->decode_done_pending[k]) { CK (cudaStreamWaitEvent (c->h2d_stream, c->decode_done[k], 0)); c->decode_done_pending[k] = false; }
   int rc = stage_batch (c, c->batch[k], c->h_pics, pics, n_pics);
   if (rc) return rc;
   for (int i = 0; i < n_pics; i++) if (pics[i].n_coef_blocks) c->staged_coefs.push_back (lh264_ctx::StagedPool{pics[i].coefs, c->h_pics.p[i].coefs, pics[i].n_coef_blocks});
-  CK (cudaEventRecord (c->recon_staged, c->stream));
-  return launch_recon (c, c->batch[k]);
+  CK (cudaEventRecord (c->recon_staged, c->h2d_stream));
+  rc = launch_recon (c, c->batch[k]);
+  if (rc) return rc;
+  CK (cudaEventRecord (c->decode_done[k], c->stream));
+  c->decode_done_pending[k] = true;
+  return LH264_OK;
 }
 
 int lh264_batch_upload (lh264_ctx* c, const lh264_picture_desc* pics, int n_pics, lh264_resident_batch** out) {
@@ -326,6 +357,7 @@ int lh264_batch_upload (lh264_ctx* c, const lh264_picture_desc* pics, int n_pics
   if (!rb) return fail (LH264_E_NOMEM, "out of host memory");
   int rc = stage_batch (c, rb->dev, c->h_pics, pics, n_pics);
   if (rc) { rb->dev.release(); delete rb; return rc; }
+  CK (cudaStreamSynchronize (c->h2d_stream));
   CK (cudaStreamSynchronize (c->stream));
   c->staged_pending = false;
   *out = rb;
@@ -421,7 +453,9 @@ int lh264_pictures_read_packed (lh264_ctx* c, const int* streams, const int* slo
   const int cw = (width + 1) >> 1, ch = (height + 1) >> 1;
   const size_t per = (size_t)width * height + 2 * (size_t)cw * ch;
   if (dst_bytes < per * n) return fail (LH264_E_INVALID, "destination too small");
-  CK (c->pack_jobs.reserve (3 * n)); CK (c->h_pack_jobs.reserve (3 * n)); CK (c->pack_out.reserve (per * n));
+  const int k = (c->pack_cur ^= 1);
+  CK (cudaEventSynchronize (c->pack_copied[k]));      // the job table of two calls ago has long gone up
+  CK (c->pack_jobs.reserve (3 * n)); CK (c->h_pack_jobs[k].reserve (3 * n)); CK (c->pack_out[k].reserve (per * n));
   for (int i = 0; i < n; i++) {
     const StreamRec* s;
     int rc = plane_geom (c, streams[i], slots[i], &s);
@@ -431,22 +465,24 @@ int lh264_pictures_read_packed (lh264_ctx* c, const int* streams, const int* slo
     const uint8_t* y = s->base + (size_t)slots[i] * s->slot_stride;
     const uint8_t* u = y + (size_t)W * H;
     const uint8_t* v = u + (size_t)W * H / 4;
-    PackDev* j = c->h_pack_jobs.p + 3 * i;
+    PackDev* j = c->h_pack_jobs[k].p + 3 * i;
     j[0] = PackDev{ y + (size_t)crop_y * W + crop_x, W, width, height, per * i };
     j[1] = PackDev{ u + (size_t) (crop_y >> 1) * (W >> 1) + (crop_x >> 1), W >> 1, cw, ch, per * i + (size_t)width * height };
     j[2] = PackDev{ v + (size_t) (crop_y >> 1) * (W >> 1) + (crop_x >> 1), W >> 1, cw, ch, per * i + (size_t)width * height + (size_t)cw * ch };
   }
-  if (c->d2h_pending) { CK (cudaStreamWaitEvent (c->stream, c->d2h_done, 0)); c->d2h_pending = false; }   // pack_out is free again
-  CK (cudaMemcpyAsync (c->pack_jobs.p, c->h_pack_jobs.p, 3 * n * sizeof (PackDev), cudaMemcpyHostToDevice, c->stream));
-  k_pack<<<dim3 (std::min (height, 64), 3 * n), 128, 0, c->stream>>> (c->pack_jobs.p, c->pack_out.p);
+  // pack_out[k] was read by the copy to the host of two calls ago
+  if (c->pack_read_pending[k]) { CK (cudaStreamWaitEvent (c->stream, c->pack_read[k], 0)); c->pack_read_pending[k] = false; }
+  CK (cudaMemcpyAsync (c->pack_jobs.p, c->h_pack_jobs[k].p, 3 * n * sizeof (PackDev), cudaMemcpyHostToDevice, c->stream));
+  CK (cudaEventRecord (c->pack_copied[k], c->stream));
+  k_pack<<<dim3 (std::min (height, 64), 3 * n), 128, 0, c->stream>>> (c->pack_jobs.p, c->pack_out[k].p);
   c->launches++;
   CK (cudaEventRecord (c->packed, c->stream));
   CK (cudaStreamWaitEvent (c->d2h_stream, c->packed, 0));
-  CK (cudaMemcpyAsync (dst, c->pack_out.p, per * n, cudaMemcpyDeviceToHost, c->d2h_stream));
+  CK (cudaMemcpyAsync (dst, c->pack_out[k].p, per * n, cudaMemcpyDeviceToHost, c->d2h_stream));
+  CK (cudaEventRecord (c->pack_read[k], c->d2h_stream));
+  c->pack_read_pending[k] = true;
   CK (cudaEventRecord (c->d2h_done, c->d2h_stream));
   c->d2h_pending = true;
-  // h_pack_jobs is reused by the next call: its H2D is on the context stream, wait for that part only
-  CK (cudaEventSynchronize (c->packed));
   if (sync) CK (cudaStreamSynchronize (c->d2h_stream));
   return LH264_OK;
 }
@@ -479,6 +515,7 @@ int lh264_sync (lh264_ctx* c) {
   CK (model_sync (c));
   unsigned int bad = 0;
   CK (cudaMemcpyAsync (&bad, c->d_error, sizeof (bad), cudaMemcpyDeviceToHost, c->stream));
+  CK (cudaStreamSynchronize (c->h2d_stream));
   CK (cudaStreamSynchronize (c->stream));
   CK (cudaStreamSynchronize (c->d2h_stream));
   c->staged_pending = false;
@@ -562,7 +599,7 @@ int lh264_k_expand_plane (lh264_ctx* c, const uint8_t* in, int w, int h, int pad
 static float model_ms (lh264_ctx* c, int which, bool reset) {
   ModelCtx* m = static_cast<ModelCtx*> (c->model);
   if (!m) return 0.f;
-  model_flush_coder (c, m);                           // steps still waiting for the coder are coded now (timed if timing is on)
+  model_coder_idle (c, m);                            // steps still waiting for the coder are coded now (timed if timing is on)
   if (reset) { m->ms_gen = m->ms_code = 0.f; return 0.f; }
   return which == 0 ? m->ms_gen : m->ms_code;
 }

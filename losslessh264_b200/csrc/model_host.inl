@@ -50,15 +50,25 @@ struct ModelCtx {
   std::vector<MBatch*> inflight;   // launched batches whose totals the host has not read yet, oldest first (at most 2)
   unsigned int* d_poison = nullptr;  // set by a batch that skipped its coding: later batches skip entirely (model_settle)
   cudaStream_t aux = nullptr;      // small D2H reads that must not queue behind running model kernels
-  DevBuf<uint32_t> dec;            // decision pool: the lists of the steps generated and not yet coded, back to back
+  // decision pool, in two halves: the generation kernels fill one while the coder (on code_stream) works through the other
+  DevBuf<uint32_t> dec[2];
   // deferred coding (model_kernels.cuh CodeJob): up to code_steps steps are generated before ONE k_model_code launch codes them
   int code_steps = 16;             // LH264_CODE_STEPS
   size_t dec_cap_limit = 0;        // decisions the pool may grow to for the sake of deferral (a single step may exceed it)
-  DevBuf<CodeJob> jobs; int job_stride = 0;        // [code_steps][job_stride]
+  DevBuf<CodeJob> jobs[2]; int job_stride = 0;     // per half: [code_steps][job_stride]
+  int cur = 0;                                     // the half being filled
+  cudaStream_t code_stream = nullptr;              // k_model_code runs here, beside the generation of the following steps
+  cudaEvent_t gen_done = nullptr, coder_done[2] = {nullptr, nullptr}, recon_idle = nullptr;
+  bool coder_pending[2] = {false, false};
+  // The coder launch (one block of two latency-bound warps per stream, resident for the whole window) and the persistent
+  // reconstruction kernel (two 256-thread blocks per SM: the whole register file) do not fit on an SM together: left to the
+  // block scheduler they starve each other (measured, profiles/r2_summary.md: 58 ms per step together, 52 ms one after the
+  // other).  LH264_CODE_EXCLUSIVE=0 lets them overlap again.
+  bool exclusive = true;
   int pend_steps = 0;
   std::vector<std::vector<int> > pend_streams;     // model stream of every job of a pending step
   std::vector<int> slot_of;                        // scratch: model stream -> block of the coder launch
-  unsigned long long* d_pool_used = nullptr; unsigned int* d_pages_pending = nullptr;
+  unsigned long long* d_pool_used = nullptr; unsigned int* d_pages_pending = nullptr;   // [2] each
   DevBuf<int> job_index; PinBuf<int> h_index[2]; cudaEvent_t index_copied[2] = {nullptr, nullptr}; int index_cur = 0;
   unsigned long long est_pool_used = 0, last_step_total = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -90,18 +100,22 @@ static ModelCtx* model_ctx (lh264_ctx* c) {
     cudaFuncSetAttribute (k_model_count, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (GEN_THREADS * sizeof (ThreadMb)));
     cudaFuncSetAttribute (k_model_emit, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) (GEN_THREADS * sizeof (ThreadMb)));
     cudaEventCreateWithFlags (&m->done, cudaEventDisableTiming);
-    cudaMalloc (&m->d_pool_used, sizeof (unsigned long long));
-    cudaMalloc (&m->d_pages_pending, sizeof (unsigned int));
-    cudaMemset (m->d_pool_used, 0, sizeof (unsigned long long));
-    cudaMemset (m->d_pages_pending, 0, sizeof (unsigned int));
-    for (int k = 0; k < 2; k++) cudaEventCreateWithFlags (&m->index_copied[k], cudaEventDisableTiming);
+    cudaMalloc (&m->d_pool_used, 2 * sizeof (unsigned long long));
+    cudaMalloc (&m->d_pages_pending, 2 * sizeof (unsigned int));
+    cudaMemset (m->d_pool_used, 0, 2 * sizeof (unsigned long long));
+    cudaMemset (m->d_pages_pending, 0, 2 * sizeof (unsigned int));
+    cudaStreamCreateWithFlags (&m->code_stream, cudaStreamNonBlocking);
+    cudaEventCreateWithFlags (&m->gen_done, cudaEventDisableTiming);
+    cudaEventCreateWithFlags (&m->recon_idle, cudaEventDisableTiming);
+    for (int k = 0; k < 2; k++) { cudaEventCreateWithFlags (&m->index_copied[k], cudaEventDisableTiming); cudaEventCreateWithFlags (&m->coder_done[k], cudaEventDisableTiming); }
+    if (const char* e = getenv ("LH264_CODE_EXCLUSIVE")) m->exclusive = atoi (e) != 0;
     if (const char* e = getenv ("LH264_CODE_STEPS")) m->code_steps = std::max (1, std::min (atoi (e), 64));
     {
       size_t free_b = 0, total_b = 0;
       cudaMemGetInfo (&free_b, &total_b);
       size_t limit_mb = 24576;                       // LH264_DEC_POOL_MB: memory the decision pool may take for deferral
       if (const char* e = getenv ("LH264_DEC_POOL_MB")) limit_mb = (size_t)std::max (1, atoi (e));
-      m->dec_cap_limit = std::min (limit_mb << 20, free_b / 4) / sizeof (uint32_t);
+      m->dec_cap_limit = std::min (limit_mb << 20, free_b / 4) / sizeof (uint32_t) / 2;     // per half
     }
     m->pend_streams.resize (m->code_steps);
     c->model = m;
@@ -126,7 +140,11 @@ static void model_destroy (lh264_ctx* c) {
   if (m->d_page_ptrs) cudaFree (m->d_page_ptrs);
   if (m->d_next) cudaFree (m->d_next);
   m->batch[0].release(); m->batch[1].release();
-  m->dec.release(); m->jobs.release(); m->job_index.release(); m->h_index[0].release(); m->h_index[1].release();
+  if (m->code_stream) { cudaStreamSynchronize (m->code_stream); cudaStreamDestroy (m->code_stream); }
+  for (int k = 0; k < 2; k++) { m->dec[k].release(); m->jobs[k].release(); if (m->coder_done[k]) cudaEventDestroy (m->coder_done[k]); }
+  if (m->gen_done) cudaEventDestroy (m->gen_done);
+  if (m->recon_idle) cudaEventDestroy (m->recon_idle);
+  m->job_index.release(); m->h_index[0].release(); m->h_index[1].release();
   if (m->d_pool_used) cudaFree (m->d_pool_used);
   if (m->d_pages_pending) cudaFree (m->d_pages_pending);
   for (int k = 0; k < 2; k++) if (m->index_copied[k]) cudaEventDestroy (m->index_copied[k]);
@@ -166,6 +184,7 @@ extern "C" {
 static int model_settle (lh264_ctx* c, ModelCtx* m);
 static int model_settle_batch (lh264_ctx* c, ModelCtx* m, MBatch* only);
 static int model_flush_coder (lh264_ctx* c, ModelCtx* m);
+static int model_coder_idle (lh264_ctx* c, ModelCtx* m);
 
 int lh264_model_open (lh264_ctx* c, int max_mbs, int with_8x8) {
   if (!c || max_mbs <= 0 || max_mbs > (1 << 20)) return fail (LH264_E_INVALID, "bad model stream geometry");
@@ -210,7 +229,7 @@ int lh264_model_close (lh264_ctx* c, int ms) {
   CK (cudaSetDevice (c->device));
   { int rs = model_settle (c, m); if (rs) return rs; }
   // pending jobs name the stream's state, and a coder launch may still be working on it
-  if ((rc = model_flush_coder (c, m))) return rc;
+  if ((rc = model_coder_idle (c, m))) return rc;
   CK (cudaStreamSynchronize (m->stream));
   // the stream's output pages stay in the arena until the context is destroyed (bump allocator)
   model_free_stream (m->streams[ms]);
@@ -283,31 +302,52 @@ static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_
 static int model_flush_coder (lh264_ctx* c, ModelCtx* m) {
   const int T = m->pend_steps;
   if (T == 0) return LH264_OK;
+  const int h = m->cur;
   m->slot_of.assign (m->streams.size(), -1);
   int nb = 0;
   for (int j = 0; j < T; j++) for (int s : m->pend_streams[j]) if (m->slot_of[s] < 0) m->slot_of[s] = nb++;
   const size_t n_idx = (size_t)nb * T;
   const int k = (m->index_cur ^= 1);
   CK (cudaEventSynchronize (m->index_copied[k]));      // (the copy of two flushes ago: long done)
-  CK (m->h_index[k].reserve (n_idx)); CK (m->job_index.reserve (n_idx));
+  CK (m->h_index[k].reserve (n_idx));
+  if (n_idx > m->job_index.cap) { CK (cudaStreamSynchronize (m->code_stream)); CK (m->job_index.reserve (n_idx)); }
   for (size_t i = 0; i < n_idx; i++) m->h_index[k].p[i] = -1;
   for (int j = 0; j < T; j++) for (size_t i = 0; i < m->pend_streams[j].size(); i++) m->h_index[k].p[(size_t)m->slot_of[m->pend_streams[j][i]] * T + j] = (int)i;
-  CK (cudaMemcpyAsync (m->job_index.p, m->h_index[k].p, n_idx * sizeof (int), cudaMemcpyHostToDevice, m->stream));
-  CK (cudaEventRecord (m->index_copied[k], m->stream));
+  // the coder starts when the generation kernels of its steps are through (and, in exclusive mode, when the reconstruction
+  // kernels submitted so far are)
+  CK (cudaEventRecord (m->gen_done, m->stream));
+  CK (cudaStreamWaitEvent (m->code_stream, m->gen_done, 0));
+  if (m->exclusive) { CK (cudaEventRecord (m->recon_idle, c->stream)); CK (cudaStreamWaitEvent (m->code_stream, m->recon_idle, 0)); }
+  CK (cudaMemcpyAsync (m->job_index.p, m->h_index[k].p, n_idx * sizeof (int), cudaMemcpyHostToDevice, m->code_stream));
+  CK (cudaEventRecord (m->index_copied[k], m->code_stream));
   ArenaDev ar{ m->d_page_ptrs, m->d_next, m->n_pages };
-  if (c->timing) CK (cudaEventRecord (m->ev[2], m->stream));
-  k_model_code<<<nb, 64, 0, m->stream>>> (m->jobs.p, m->job_index.p, T, m->job_stride, m->dec.p, ar);
+  if (c->timing) CK (cudaEventRecord (m->ev[2], m->code_stream));
+  k_model_code<<<nb, 64, 0, m->code_stream>>> (m->jobs[h].p, m->job_index.p, T, m->job_stride, m->dec[h].p, ar);
   c->launches++;
-  CK (cudaMemsetAsync (m->d_pool_used, 0, sizeof (unsigned long long), m->stream));
-  CK (cudaMemsetAsync (m->d_pages_pending, 0, sizeof (unsigned int), m->stream));
+  if (c->timing) CK (cudaEventRecord (m->ev[3], m->code_stream));
+  CK (cudaMemsetAsync (m->d_pool_used + h, 0, sizeof (unsigned long long), m->code_stream));
+  CK (cudaMemsetAsync (m->d_pages_pending + h, 0, sizeof (unsigned int), m->code_stream));
+  CK (cudaEventRecord (m->coder_done[h], m->code_stream));
+  m->coder_pending[h] = true;
+  if (m->exclusive) CK (cudaStreamWaitEvent (c->stream, m->coder_done[h], 0));
   m->pend_steps = 0; m->est_pool_used = 0;
+  // generation goes on in the other half, once the coder launch that read it (two flushes ago) is over
+  m->cur ^= 1;
+  if (m->coder_pending[m->cur]) { CK (cudaStreamWaitEvent (m->stream, m->coder_done[m->cur], 0)); m->coder_pending[m->cur] = false; }
   if (c->timing) {
-    CK (cudaEventRecord (m->ev[3], m->stream));
     CK (cudaEventSynchronize (m->ev[3]));
     float t = 0;
     cudaEventElapsedTime (&t, m->ev[2], m->ev[3]); m->ms_code += t;
   }
   CK (cudaGetLastError());
+  return LH264_OK;
+}
+
+// every coder launch is over: the stream states, priors and output pages are final
+static int model_coder_idle (lh264_ctx* c, ModelCtx* m) {
+  int rc = model_flush_coder (c, m);
+  if (rc) return rc;
+  CK (cudaStreamSynchronize (m->code_stream));
   return LH264_OK;
 }
 
@@ -320,13 +360,14 @@ static int model_launch (lh264_ctx* c, ModelCtx* m, MBatch& b, bool head, bool t
   if (n > m->job_stride) {                            // a wider step than any before: the job table is re-laid
     int rc = model_flush_coder (c, m);
     if (rc) return rc;
-    CK (cudaStreamSynchronize (m->stream));
+    CK (cudaStreamSynchronize (m->stream)); CK (cudaStreamSynchronize (m->code_stream));
     m->job_stride = n + n / 4 + 16;
-    CK (m->jobs.reserve ((size_t)m->job_stride * m->code_steps));
+    for (int k = 0; k < 2; k++) CK (m->jobs[k].reserve ((size_t)m->job_stride * m->code_steps));
   }
+  const int h = m->cur;
   ArenaDev ar{ m->d_page_ptrs, m->d_next, m->n_pages };
-  PoolDev pool{ m->d_pool_used, m->d_pages_pending };
-  CodeJob* row = m->jobs.p + (size_t)m->pend_steps * m->job_stride;
+  PoolDev pool{ m->d_pool_used + h, m->d_pages_pending + h, m->d_pages_pending + (h ^ 1) };
+  CodeJob* row = m->jobs[h].p + (size_t)m->pend_steps * m->job_stride;
   CK (cudaMemsetAsync (row, 0, (size_t)n * sizeof (CodeJob), m->stream));       // st == nullptr: a step that skips leaves no jobs
   if (head) {
     if (timed) CK (cudaEventRecord (m->ev[0], m->stream));
@@ -335,8 +376,8 @@ static int model_launch (lh264_ctx* c, ModelCtx* m, MBatch& b, bool head, bool t
     k_model_scan<<<n, 1024, 0, m->stream>>> (b.pics.p, n, b.pic_total.p, m->d_poison);
     c->launches += 3;
   }
-  k_model_plan<<<1, 1024, 0, m->stream>>> (n, b.pic_total.p, b.dec_base.p, b.ctl.p, (unsigned long long)m->dec.cap, ar, pool, m->d_poison);
-  k_model_emit<<<mb_blocks, GEN_THREADS, gen_smem, m->stream>>> (b.pics.p, n, total_recs, m->dec.p, b.dec_base.p, b.ctl.p);
+  k_model_plan<<<1, 1024, 0, m->stream>>> (n, b.pic_total.p, b.dec_base.p, b.ctl.p, (unsigned long long)m->dec[h].cap, ar, pool, m->d_poison);
+  k_model_emit<<<mb_blocks, GEN_THREADS, gen_smem, m->stream>>> (b.pics.p, n, total_recs, m->dec[h].p, b.dec_base.p, b.ctl.p);
   k_model_commit<<<n, 128, 0, m->stream>>> (b.pics.p, n, b.dec_base.p, b.pic_total.p, b.ctl.p, row);
   c->launches += 3;
   if (timed) CK (cudaEventRecord (m->ev[1], m->stream));
@@ -354,11 +395,12 @@ static int model_grow_pool (lh264_ctx* c, ModelCtx* m, unsigned long long step_t
   (void)c;
   const size_t one = (size_t)step_total + (size_t)step_total / 4 + 64;
   size_t want = std::max (one, std::min (one * (size_t)m->code_steps, m->dec_cap_limit));
-  if (want <= m->dec.cap) return LH264_OK;
-  CK (cudaStreamSynchronize (m->stream));
+  DevBuf<uint32_t>& dec = m->dec[m->cur];
+  if (want <= dec.cap) return LH264_OK;
+  CK (cudaStreamSynchronize (m->stream)); CK (cudaStreamSynchronize (m->code_stream));
   // room for code_steps steps is a wish, room for one step a need: halve the wish until the device has it
   for (;;) {
-    if (m->dec.reserve (want) == cudaSuccess) return LH264_OK;
+    if (dec.reserve (want) == cudaSuccess) return LH264_OK;
     cudaGetLastError();
     if (want == one) return fail (LH264_E_NOMEM, "out of device memory for the model's decision pool");
     want = std::max (one, want / 2);
@@ -442,9 +484,9 @@ static int model_run (lh264_ctx* c, ModelCtx* m, MBatch& b) {
   while (m->inflight.size() >= 2) if ((rc = model_settle_batch (c, m, m->inflight.front()))) return rc;
   for (int i = 0; i < n; i++) if (!m->streams[b.stream_of[i]].open) return fail (LH264_E_INVALID, "batch names a closed model stream");
   if (!m->d_page_ptrs && (rc = model_grow_arena (c, m, (unsigned int)n * CT_COUNT + 64))) return rc;
-  if (!m->dec.p && (rc = model_grow_pool (c, m, (unsigned long long)b.total_recs * 96 + 1024))) return rc;   // first guess; model_settle grows it when needed
+  if (!m->dec[m->cur].p && (rc = model_grow_pool (c, m, std::max<unsigned long long> ((unsigned long long)b.total_recs * 96 + 1024, m->last_step_total)))) return rc;   // first guess; model_settle grows it when needed
   // a step about as large as the last one would not fit behind the pending ones: code those first (saves a skip + re-run)
-  if (m->pend_steps > 0 && m->est_pool_used + m->last_step_total + m->last_step_total / 2 + 64 > m->dec.cap && (rc = model_flush_coder (c, m))) return rc;
+  if (m->pend_steps > 0 && m->est_pool_used + m->last_step_total + m->last_step_total / 2 + 64 > m->dec[m->cur].cap && (rc = model_flush_coder (c, m))) return rc;
   if ((rc = model_launch (c, m, b, true, c->timing))) return rc;
   b.pending = true; m->inflight.push_back (&b);
   if (c->timing) {
@@ -504,7 +546,7 @@ void lh264_model_batch_free (lh264_ctx* c, lh264_model_batch* b) {
 static int model_check_error (lh264_ctx* c, MStreamHost& s) {
   ModelCtx* m = static_cast<ModelCtx*> (c->model);
   { int rs = model_settle (c, m); if (rs) return rs; }
-  { int rs = model_flush_coder (c, m); if (rs) return rs; }
+  { int rs = model_coder_idle (c, m); if (rs) return rs; }
   int err = 0;
   CK (cudaMemcpyAsync (&err, &s.d_state->error, sizeof (int), cudaMemcpyDeviceToHost, m->stream));
   CK (cudaStreamSynchronize (m->stream));
@@ -520,7 +562,7 @@ int lh264_model_finish (lh264_ctx* c, int ms) {
   if (rc) return rc;
   CK (cudaSetDevice (c->device));
   if ((rc = model_settle (c, m))) return rc;
-  if ((rc = model_flush_coder (c, m))) return rc;
+  if ((rc = model_coder_idle (c, m))) return rc;
   unsigned int used = 0;
   if (m->d_next) { CK (cudaMemcpyAsync (&used, m->d_next, sizeof (used), cudaMemcpyDeviceToHost, m->stream)); CK (cudaStreamSynchronize (m->stream)); }
   if ((rc = model_grow_arena (c, m, used + CT_COUNT))) return rc;
@@ -575,7 +617,7 @@ unsigned long long lh264_model_decisions (lh264_ctx* c, int ms) {
 static cudaError_t model_sync (lh264_ctx* c) {
   ModelCtx* m = static_cast<ModelCtx*> (c->model);
   if (m && !m->inflight.empty() && model_settle (c, m) != LH264_OK) return cudaErrorUnknown;
-  if (m && model_flush_coder (c, m) != LH264_OK) return cudaErrorUnknown;
+  if (m && model_coder_idle (c, m) != LH264_OK) return cudaErrorUnknown;
   return m && m->stream ? cudaStreamSynchronize (m->stream) : cudaSuccess;
 }
 
@@ -585,7 +627,9 @@ static cudaError_t model_join (lh264_ctx* c) {
   if (!m || !m->stream) return cudaSuccess;
   if (model_flush_coder (c, m) != LH264_OK) return cudaErrorUnknown;
   cudaError_t e = cudaEventRecord (m->done, m->stream);
-  return e != cudaSuccess ? e : cudaStreamWaitEvent (c->stream, m->done, 0);
+  if (e == cudaSuccess) e = cudaStreamWaitEvent (c->stream, m->done, 0);
+  for (int k = 0; k < 2 && e == cudaSuccess; k++) if (m->coder_pending[k]) e = cudaStreamWaitEvent (c->stream, m->coder_done[k], 0);
+  return e;
 }
 
 static int model_settle_sharer (lh264_ctx* c, int k) {

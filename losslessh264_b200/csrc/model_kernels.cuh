@@ -85,7 +85,9 @@ struct ArenaDev { uint8_t** page_ptrs; unsigned int* next; unsigned int n_pages;
 // stream's pictures in step order.  (With one launch per step the slowest picture of the step - an I picture among P pictures -
 // set the step's time while every other stream's coder sat idle: streams whose I pictures fall in different steps now overlap.)
 struct CodeJob { MState* st; unsigned long long base; uint32_t n; uint32_t pad; };   // st == nullptr: nothing to code
-struct PoolDev { unsigned long long* used; unsigned int* pages_pending; };             // decisions in the pool; output pages promised to pending jobs
+// decisions in the pool half being filled; output pages promised to the jobs of this half and of the other half (whose coder may
+// still be running: the pages it has not taken yet are not in *ArenaDev::next)
+struct PoolDev { unsigned long long* used; unsigned int* pages_pending; const unsigned int* pages_pending_other; };
 
 // Written by k_model_plan, read by the host when it next touches the batch.  `skip` makes k_model_emit / k_model_code return
 // without touching any state, so that the host can grow what was too small and run the two kernels again.
@@ -630,7 +632,7 @@ __global__ void __launch_bounds__ (1024) k_model_plan (int n_pics, const uint32_
     // every decision shifts out at most 7 bits, and a tag needs at most one partly filled page more than its bytes
     const unsigned long long pages = total * 7 / 8 / PAGE_SIZE + (unsigned long long)n_pics * CT_COUNT + 1;
     // pages already promised to steps that are generated but not coded yet count as in use
-    const unsigned int in_use = *ar.next + *pool.pages_pending;
+    const unsigned int in_use = *ar.next + *pool.pages_pending + *pool.pages_pending_other;
     const unsigned long long base = *pool.used;
     ctl->total = total; ctl->pages_needed = (unsigned int)min (pages, 0xffffffffull); ctl->pages_in_use = in_use; ctl->pool_base = base;
     ctl->skip = (base + total + 32 > dec_capacity || in_use + pages > ar.n_pages) ? 1u : 0u;

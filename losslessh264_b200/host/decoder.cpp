@@ -162,12 +162,14 @@ struct Decoder::Impl {
   bool open = false;
   SliceHeader sh0;                       // first slice header of the picture
   int cur_slot = 0, decoded = 0;
+  bool ltr_marking = false; int ltr_marked_frame_num = 0;   // set by mark_current() for the picture being finished
   bool alloc_failed = false;             // record storage could not be had (RecordArena / heap): the picture is dropped
   // the reference holds its output back until the first IDR picture has been decoded (bFreezeOutput under the freeze error
   // concealment modes h264dec selects, decoder_core.cpp:56-217): pictures of a stream whose leading IDR was lost are parsed,
   // modelled and reconstructed, but marked `output = false` for the sink and not handed out
   bool frozen = true;
-  unsigned long long ts = 0;
+  unsigned long long ts = 0, ts_first = 0;
+  bool ref_lost = false, ref_lost_first = false;   // a reference picture of the current picture was never received (frame_num gap / no reference at all)
   RecBuf<lh264_mb_rec, RecordArena::MBS> mbs;      // n_mbs records while a picture is open
   RecBuf<int16_t, RecordArena::COEFS> coefs;
   std::vector<lh264_slice_rec> slices;
@@ -312,6 +314,7 @@ struct Decoder::Impl {
     (void)n;
   }
   void mark_current() {                                  // 8.2.5 after the picture is decoded
+    ltr_marking = false; ltr_marked_frame_num = 0;
     if (sh0.nal_ref_idc == 0) return;
     const int max_fn = 1 << S->log2_max_frame_num;
     RefPic cur;
@@ -340,7 +343,7 @@ struct Decoder::Impl {
         case 3: {
           const int pn = sh0.frame_num - ((int)m.a + 1);
           for (size_t i = 0; i < refs.size(); i++) if (refs[i].is_long && refs[i].long_idx == (int)m.b) { refs.erase (refs.begin() + i); break; }
-          for (RefPic& r : refs) if (!r.is_long && pic_num_of (r) == pn) { r.is_long = true; r.long_idx = (int)m.b; break; }
+          for (RefPic& r : refs) if (!r.is_long && pic_num_of (r) == pn) { r.is_long = true; r.long_idx = (int)m.b; ltr_marking = true; ltr_marked_frame_num = pn & (max_fn - 1); break; }
           break;
         }
         case 4:
@@ -351,6 +354,7 @@ struct Decoder::Impl {
         case 6:
           for (size_t i = 0; i < refs.size(); i++) if (refs[i].is_long && refs[i].long_idx == (int)m.b) { refs.erase (refs.begin() + i); break; }
           cur.is_long = true; cur.long_idx = (int)m.b; cur_long = true;
+          ltr_marking = true; ltr_marked_frame_num = sh0.frame_num;
           break;
         }
       }
@@ -407,6 +411,14 @@ struct Decoder::Impl {
   void start_picture (Decoder* self) {
     (void)self;
     open = true; sh0 = sh; decoded = 0; slice_no = 0;
+    ts_first = ts;
+    ref_lost_first = false;
+    if (sh.idr) ref_lost = false;
+    else {
+      const int max_fn0 = 1 << S->log2_max_frame_num;
+      const bool gap = !S->gaps_in_frame_num_allowed && sh.frame_num != prev_ref_frame_num && sh.frame_num != (prev_ref_frame_num + 1) % max_fn0;
+      if ((refs.empty() || gap) && !ref_lost) { ref_lost = true; ref_lost_first = true; }
+    }
     cur_mb = -2;                           // (cur_mbx / cur_mby are recomputed for the first macroblock)
     if (sh.idr) { /* refs dropped at marking time; lists are empty for an I picture anyway */ }
     else if (S->gaps_in_frame_num_allowed) {
@@ -447,7 +459,8 @@ struct Decoder::Impl {
     info.crop_x = S->crop_left; info.crop_y = S->crop_top;
     info.width = mb_w * 16 - S->crop_left - S->crop_right; info.height = mb_h * 16 - S->crop_top - S->crop_bottom;
     info.frame_num = sh0.frame_num; info.poc_lsb = sh0.poc_lsb; info.idr_pic_id = sh0.idr_pic_id; info.nal_ref_idc = sh0.nal_ref_idc;
-    info.slot = cur_slot; info.serial = serial++; info.complete = decoded >= n_mbs; info.timestamp = ts;
+    info.slot = cur_slot; info.serial = serial++; info.complete = decoded >= n_mbs; info.timestamp = ts; info.timestamp_first = ts_first;
+    info.ref_lost = ref_lost; info.ref_lost_first = ref_lost_first;
     int rc = 0;
     // ... and freezes it again at a picture with missing macroblocks (no concealment here: the reference's freeze modes do not
     // hand concealed pictures out either) until the next complete IDR picture
@@ -464,9 +477,11 @@ struct Decoder::Impl {
       if (!rc) rc = rm;
     }
     mark_current();
+    info.idr = sh0.idr; info.ltr_marking = ltr_marking; info.ltr_marked_frame_num = ltr_marked_frame_num;
     self->stats_.pictures++;
     self->stats_.coef_blocks += coefs.size() / 16;
     if (info.output) self->out_.push_back (info);
+    self->fin_.push_back (info);
     mbs.clear(); coefs.clear(); mrecs.clear();       // handed over: arena storage is the sink's now
     return rc;
   }
@@ -1322,7 +1337,7 @@ int Decoder::decode (const uint8_t* data, size_t len, unsigned long long timesta
         D.S = &D.sps[pps.sps_id]; D.P = &D.pps[sh.pps_id]; D.sh = sh; D.ts = timestamp;
         D.start_picture (this);
         if (!D.open) { last_err = -31; stats_.errors++; continue; }        // no storage for the picture's records
-      } else { D.S = &D.sps[pps.sps_id]; D.P = &D.pps[sh.pps_id]; D.sh = sh; }
+      } else { D.S = &D.sps[pps.sps_id]; D.P = &D.pps[sh.pps_id]; D.sh = sh; D.ts = timestamp; }   // (a picture carries the time stamp of its last slice's call)
       if (sh.first_mb >= D.n_mbs) { last_err = -1; stats_.errors++; continue; }
       D.slice_no = (int)D.slices.size();
       // slice record
@@ -1354,6 +1369,7 @@ int Decoder::decode (const uint8_t* data, size_t len, unsigned long long timesta
       br.seek (sh.header_bits);
       D.slice_rbsp.assign (D.rbsp.begin(), D.rbsp.begin() + std::min (D.rbsp.size(), (sh.header_bits + 7) / 8));   // for last_slice()
       last_slice_.decoded = true; last_slice_.cabac = pps.cabac; last_slice_.rbsp = D.slice_rbsp.data(); last_slice_.header_bits = sh.header_bits;
+      last_slice_.idr = sh.idr; last_slice_.idr_pic_id = sh.idr_pic_id; last_slice_.frame_num = sh.frame_num;
       if ((pps.cabac ? D.parse_slice_data_cabac (br, this) : D.parse_slice_data (br, this)) < 0) last_err = -40;
       if (D.decoded >= D.n_mbs) D.finish_picture (this);
     } else if (type == NAL_END_SEQ || type == NAL_END_STREAM) {

@@ -28,7 +28,12 @@ struct DecodedPictureInfo {
   int serial;
   bool complete;                         // every macroblock was decoded
   bool output = true;                    // false: decoded before the first IDR picture of the stream, held back (see decoder.cpp `frozen`)
-  unsigned long long timestamp;
+  bool idr = false;
+  bool ltr_marking = false;              // the picture's marking made a long-term reference (MMCO 3 / 6): manage_dec_ref.cpp:376-378, :405-407
+  int ltr_marked_frame_num = 0;
+  unsigned long long timestamp;          // of the call that brought the picture's last slice ...
+  unsigned long long timestamp_first = 0;// ... and its first one
+  bool ref_lost = false, ref_lost_first = false;   // decoded after a lost reference picture (until the next IDR); the first such picture
 };
 
 // Per-MB side record for the recompression model (filled by the parser; reference:
@@ -86,7 +91,9 @@ class Decoder {
   void enable_rewrite_check (bool on);
   // pictures completed by the last decode()/flush() call, in output order
   const std::vector<DecodedPictureInfo>& output() const { return out_; }
-  void clear_output() { out_.clear(); }
+  // every picture finished by the last decode()/flush() call, handed out or not (what the reference calls a decoded access unit)
+  const std::vector<DecodedPictureInfo>& finished() const { return fin_; }
+  void clear_output() { out_.clear(); fin_.clear(); }
   void enable_model (bool on);           // produce lh264_model_picture hand-offs (PictureSink::submit_model)
   // Switches record storage to `arena` (NULL = the decoder's own heap buffers) for the following pictures AND for a picture in
   // progress, whose records so far move over.  The pointers PictureSink::submit() sees then point into the arena.
@@ -94,7 +101,7 @@ class Decoder {
   bool picture_open() const;             // a picture has been started and not yet handed to the sink
   // the last slice NAL handled by the last decode() call (for the `.pip` default stream, pip_container.h); rbsp is valid
   // until the next decode() call
-  struct LastSlice { bool decoded = false, cabac = false; const uint8_t* rbsp = nullptr; size_t header_bits = 0; };
+  struct LastSlice { bool decoded = false, cabac = false; const uint8_t* rbsp = nullptr; size_t header_bits = 0; bool idr = false; int idr_pic_id = 0, frame_num = 0; };
   const LastSlice& last_slice() const { return last_slice_; }
   bool sps_seen() const { return sps_seen_; }
   bool keep_model_side = false;          // fill ModelMbSide records
@@ -104,7 +111,7 @@ class Decoder {
   struct Impl;
   std::unique_ptr<Impl> d_;
   DecoderStats stats_;
-  std::vector<DecodedPictureInfo> out_;
+  std::vector<DecodedPictureInfo> out_, fin_;
   LastSlice last_slice_;
   bool sps_seen_ = false;
 };

@@ -40,7 +40,7 @@ class CLh264Decoder : public ISVCDecoder {
     delete dec_; dec_ = nullptr;
     delete sink_; sink_ = nullptr;
     if (out_) { lh264_host_free (out_); out_ = nullptr; out_cap_ = 0; }
-    queue_.clear();
+    queue_.clear(); held_.clear();
     return cmResultSuccess;
   }
 
@@ -77,7 +77,7 @@ class CLh264Decoder : public ISVCDecoder {
     if (!opt) return cmInitParaError;
     switch (id) {
     case DECODER_OPTION_DATAFORMAT: return * (int*)opt == videoFormatI420 ? cmResultSuccess : cmInitParaError;
-    case DECODER_OPTION_END_OF_STREAM: eos_ = * (bool*)opt; return cmResultSuccess;
+    case DECODER_OPTION_END_OF_STREAM: eos_ = eos_opt_ = * (bool*)opt; return cmResultSuccess;
     case DECODER_OPTION_ERROR_CON_IDC: ec_idc_ = * (int*)opt; return cmResultSuccess;
     case DECODER_OPTION_TRACE_LEVEL: trace_level_ = * (int*)opt; return cmResultSuccess;
     case DECODER_OPTION_TRACE_CALLBACK: case DECODER_OPTION_TRACE_CALLBACK_CONTEXT: return cmResultSuccess;
@@ -90,11 +90,11 @@ class CLh264Decoder : public ISVCDecoder {
     case DECODER_OPTION_DATAFORMAT: * (int*)opt = videoFormatI420; return cmResultSuccess;
     case DECODER_OPTION_END_OF_STREAM: * (int*)opt = eos_; return cmResultSuccess;
     case DECODER_OPTION_VCL_NAL: * (int*)opt = last_vcl_; return cmResultSuccess;
-    case DECODER_OPTION_TEMPORAL_ID: * (int*)opt = 0; return cmResultSuccess;
+    case DECODER_OPTION_TEMPORAL_ID: * (int*)opt = tid_; return cmResultSuccess;
     case DECODER_OPTION_FRAME_NUM: * (int*)opt = last_frame_num_; return cmResultSuccess;
     case DECODER_OPTION_IDR_PIC_ID: * (int*)opt = last_idr_pic_id_; return cmResultSuccess;
-    case DECODER_OPTION_LTR_MARKING_FLAG: * (bool*)opt = false; return cmResultSuccess;
-    case DECODER_OPTION_LTR_MARKED_FRAME_NUM: * (int*)opt = 0; return cmResultSuccess;
+    case DECODER_OPTION_LTR_MARKING_FLAG: * (int*)opt = ltr_flag_ ? 1 : 0; return cmResultSuccess;      // (the reference stores an int, :370-373)
+    case DECODER_OPTION_LTR_MARKED_FRAME_NUM: * (int*)opt = ltr_frame_num_; return cmResultSuccess;
     case DECODER_OPTION_ERROR_CON_IDC: * (int*)opt = ec_idc_; return cmResultSuccess;
     case DECODER_OPTION_GET_STATISTICS: memcpy (opt, &stat_, sizeof (stat_)); return cmResultSuccess;
     default: return cmInitParaError;
@@ -102,7 +102,11 @@ class CLh264Decoder : public ISVCDecoder {
   }
 
  private:
-  DECODING_STATE decode (const unsigned char* src, int len, unsigned char** ppDst, SBufferInfo* info, bool no_delay) {
+  // One DecodeFrame2 call as an API client sees it (welsDecoderExt.cpp:431-571).  The reference decodes an access unit when the
+  // first NAL of the NEXT one arrives, or at once on the flush call DecodeFrame2 (NULL, 0) — which DecodeFrameNoDelay issues after
+  // every unit (:408-430).  The host decoder finishes a complete picture at its last slice, so DecodeFrame2 holds such a picture
+  // back until the next call: output timing, time stamps and the per-call feedback options then follow the reference.
+  DECODING_STATE decode_one (const unsigned char* src, int len, unsigned char** ppDst, SBufferInfo* info, bool second_half = false) {
     if (!dec_ || !sink_) return dsInitialOptExpected;
     if (!ppDst || !info) return dsInvalidArgument;
     const unsigned long long ts = info->uiInBsTimeStamp;       // welsDecoderExt.cpp:463-465
@@ -110,26 +114,36 @@ class CLh264Decoder : public ISVCDecoder {
     info->uiInBsTimeStamp = ts;
     ppDst[0] = ppDst[1] = ppDst[2] = nullptr;
     int state = dsErrorFree;
+    // feedback of this call (welsDecoderExt.cpp:461-473)
+    last_vcl_ = FEEDBACK_UNKNOWN_NAL; tid_ = -1; last_frame_num_ = -1; ltr_flag_ = false; ltr_frame_num_ = 0;
+    std::vector<DecodedPictureInfo> decoded_now;               // access units the reference would decode during this call
     dec_->clear_output();
     if (src && len > 0) {
-      if (pip_ && no_delay) {
-        if (len < 4) { pip_->raw (src, (size_t)len); return (DECODING_STATE)state; }     // h264dec.cpp:268-271
-        pip_->unit_begin (src, (size_t)len, dec_->sps_seen());
-      }
+      eos_ = false;
+      for (const DecodedPictureInfo& o : held_) decoded_now.push_back (o);     // the next access unit has arrived
+      held_.clear();
       const int rc = dec_->decode (src, (size_t)len, ts);
-      if (pip_ && no_delay) {
-        UnitSliceInfo u;
-        u.slice_decoded = dec_->last_slice().decoded; u.cabac = dec_->last_slice().cabac;
-        u.rbsp = dec_->last_slice().rbsp; u.header_bits = dec_->last_slice().header_bits;
-        pip_->unit_end (u);
-      }
+      if (dec_->last_slice().decoded && dec_->last_slice().idr) last_idr_pic_id_ = dec_->last_slice().idr_pic_id;
       if (rc == -2) state |= dsNoParamSets;
       else if (rc < 0) state |= dsBitstreamError;
-      last_vcl_ = 1;
-    } else if (eos_ || !no_delay) {
-      if (eos_) dec_->flush();                                   // end of stream: emit what is pending
+      // finished by its own last slice: the reference has not decoded it yet; finished by the arrival of this unit: it has
+      for (const DecodedPictureInfo& o : dec_->finished()) { if (o.complete) held_.push_back (o); else decoded_now.push_back (o); }
+    } else {
+      eos_ = true;                                               // :452-455: the flush call
+      // a picture still missing slices is only given up at the END of the stream (the client said so with DECODER_OPTION_END_OF_STREAM),
+      // not by the flush half of DecodeFrameNoDelay, which comes after every slice of a multi-slice picture
+      if (eos_opt_ && !second_half) dec_->flush();
+      for (const DecodedPictureInfo& o : held_) decoded_now.push_back (o);
+      held_.clear();
+      for (const DecodedPictureInfo& o : dec_->finished()) decoded_now.push_back (o);
     }
-    for (const DecodedPictureInfo& o : dec_->output()) queue_.push_back (o);
+    for (const DecodedPictureInfo& o : decoded_now) {
+      last_vcl_ = FEEDBACK_VCL_NAL; tid_ = 0; last_frame_num_ = o.frame_num;
+      if (o.ltr_marking) { ltr_flag_ = true; ltr_frame_num_ = o.ltr_marked_frame_num; }
+      if (o.output) queue_.push_back (o);
+      if (!o.complete || !o.output || o.ref_lost) state |= dsDataErrorConcealed;   // (incomplete, held back behind a lost IDR picture, or predicted from a lost one)
+      if (o.ref_lost_first) state |= dsRefLost;
+    }
     if (!queue_.empty()) {
       const DecodedPictureInfo o = queue_.front();
       queue_.pop_front();
@@ -145,16 +159,49 @@ class CLh264Decoder : public ISVCDecoder {
       if (sink_->read (o, y, o.width, u, v, cw) != LH264_OK) return (DECODING_STATE) (state | dsOutOfMemory);
       ppDst[0] = y; ppDst[1] = u; ppDst[2] = v;
       info->iBufferStatus = 1;
-      info->uiOutYuvTimeStamp = o.timestamp;
+      // the time stamp that came with the picture's own data: DecodeFrame2 decodes an access unit as a whole (its first unit's
+      // stamp), the flush half of DecodeFrameNoDelay slice by slice (the last one's)
+      info->uiOutYuvTimeStamp = nodelay_ ? o.timestamp : o.timestamp_first;
       info->UsrData.sSystemBuffer.iWidth = o.width; info->UsrData.sSystemBuffer.iHeight = o.height;
       info->UsrData.sSystemBuffer.iFormat = videoFormatI420;
       info->UsrData.sSystemBuffer.iStride[0] = o.width; info->UsrData.sSystemBuffer.iStride[1] = cw;
-      last_frame_num_ = o.frame_num; last_idr_pic_id_ = o.idr_pic_id;
       stat_.uiDecodedFrameCount++;
       if (stat_.uiWidth != (unsigned)o.width || stat_.uiHeight != (unsigned)o.height) { stat_.uiResolutionChangeTimes++; stat_.uiWidth = o.width; stat_.uiHeight = o.height; }
-      if (!o.complete) state |= dsDataErrorConcealed;
     }
     return (DECODING_STATE)state;
+  }
+
+  DECODING_STATE decode (const unsigned char* src, int len, unsigned char** ppDst, SBufferInfo* info, bool no_delay) {
+    nodelay_ = no_delay;
+    if (!no_delay) return decode_one (src, len, ppDst, info);
+    if (!dec_ || !sink_) return dsInitialOptExpected;
+    if (!ppDst || !info) return dsInvalidArgument;
+    if (pip_ && src && len > 0) {
+      if (len < 4) { pip_->raw (src, (size_t)len); return dsErrorFree; }     // h264dec.cpp:268-271
+      pip_->unit_begin (src, (size_t)len, dec_->sps_seen());
+    }
+    // DecodeFrame2 (src) then DecodeFrame2 (NULL, 0), return codes OR-ed; the caller sees the second call's output (:408-430)
+    int st = (int)decode_one (src, len, ppDst, info);
+    if (pip_ && src && len > 0) {
+      UnitSliceInfo u;
+      u.slice_decoded = dec_->last_slice().decoded; u.cabac = dec_->last_slice().cabac;
+      u.rbsp = dec_->last_slice().rbsp; u.header_bits = dec_->last_slice().header_bits;
+      pip_->unit_end (u);
+    }
+    unsigned char* first_planes[3] = {ppDst[0], ppDst[1], ppDst[2]};
+    const SBufferInfo first = *info;
+    const bool slice_here = src && len > 0 && dec_->last_slice().decoded;
+    const int slice_frame_num = dec_->last_slice().frame_num;
+    st |= (int)decode_one (nullptr, 0, ppDst, info, true);
+    // the flush half decodes what the unit brought at once: a slice unit reports its access unit even while the picture waits for
+    // more slices
+    if (slice_here && last_vcl_ != FEEDBACK_VCL_NAL) { last_vcl_ = FEEDBACK_VCL_NAL; tid_ = 0; last_frame_num_ = slice_frame_num; }
+    if (info->iBufferStatus == 0 && first.iBufferStatus == 1) {                // (a picture released by the first half: an incomplete one)
+      const unsigned long long ts = info->uiInBsTimeStamp;
+      *info = first; info->uiInBsTimeStamp = ts;
+      ppDst[0] = first_planes[0]; ppDst[1] = first_planes[1]; ppDst[2] = first_planes[2];
+    }
+    return (DECODING_STATE)st;
   }
 
   // writes the `.pip` file set: default stream + one file per tag that has a stream (MultiFileWriter, h264dec.cpp:79-104)
@@ -182,9 +229,12 @@ class CLh264Decoder : public ISVCDecoder {
   PipBoilerplate* pip_ = nullptr;
   std::string pip_path_;
   std::deque<DecodedPictureInfo> queue_;
+  std::vector<DecodedPictureInfo> held_;          // complete pictures the reference would only decode at the next call
+  int tid_ = -1, ltr_frame_num_ = 0;
+  bool ltr_flag_ = false, nodelay_ = false;
   unsigned char* out_ = nullptr;
   size_t out_cap_ = 0;
-  bool eos_ = false;
+  bool eos_ = false, eos_opt_ = false;
   int ec_idc_ = ERROR_CON_SLICE_COPY, trace_level_ = 0, device_ = 0;
   int last_vcl_ = 0, last_frame_num_ = -1, last_idr_pic_id_ = 0;
   SDecoderStatistics stat_;

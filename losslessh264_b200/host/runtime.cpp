@@ -23,6 +23,7 @@
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
+#include <deque>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -220,6 +221,14 @@ namespace {
 
 struct Pipeline;
 
+struct Out {                             // pictures on their way to the host
+  bool valid = false;
+  std::vector<Placed> pics;
+  size_t per = 0;
+  int idx = 0;
+};
+
+
 struct Worker {
   Pipeline* pl = nullptr;
   std::vector<int> streams;             // indices into rt->streams
@@ -247,6 +256,15 @@ struct Pipeline {
   unsigned long long launches = 0;
   lh264_rt_picture_fn fn = nullptr; void* user = nullptr;
   std::thread th;
+  // decoded pictures on their way to the host: the submit thread issues the packed reads, an output thread waits for each copy
+  // and delivers it (SHA-1 / callback), so that the next step's submit never waits behind a device-to-host copy
+  std::mutex out_mu;
+  std::condition_variable out_cv;
+  std::deque<Out> out_q;
+  int out_in_flight = 0;                // reads issued and not yet delivered
+  bool out_quit = false;
+  uint8_t* out_pin[2] = {nullptr, nullptr}; size_t out_cap[2] = {0, 0};   // (pinned: 3.2 GB each for 1024 1080p streams)
+  long out_issued = 0;
 };
 
 // Parses until the stream has placed one picture into `buf` (or ended).  h264dec's unit loop, h264dec.cpp:246-364.
@@ -352,20 +370,12 @@ void worker_main (Worker* w) {
   }
 }
 
-struct Out {                             // pictures on their way to the host
-  bool valid = false;
-  std::vector<Placed> pics;
-  size_t per = 0;
-  int idx = 0;
-};
-
 void pipeline_main (Pipeline* P) {
   lh264_rt* rt = P->rt;
   const lh264_rt_config& cfg = rt->cfg;
   const bool want_yuv = cfg.want_yuv != 0, want_hash = want_yuv && cfg.want_hash != 0, want_pip = cfg.want_pip != 0;
   lh264_ctx* ctx = P->ctx;
   const int D = (int)P->workers[0]->bufs.size();
-  uint8_t* out_pin[2] = {nullptr, nullptr}; size_t out_cap[2] = {0, 0};
   std::vector<uint8_t> out_host;
   std::vector<lh264_picture_desc> descs;
   std::vector<lh264_model_picture> mdescs;
@@ -373,25 +383,43 @@ void pipeline_main (Pipeline* P) {
   std::vector<Placed> step;
   std::vector<const StepBuf*> step_buf;
   std::vector<long> done_snapshot;
-  Out prev;
 #define FAIL(msg) do { rt->fail (std::string (msg) + ": " + lh264_last_error()); P->rc = -1; goto done; } while (0)
 
   auto deliver = [&] (const Out& o) {    // pictures of a finished step: SHA-1 + callback
     const int n = (int)o.pics.size();
+    const uint8_t* base = P->out_pin[o.idx];
     if (want_hash && n > 0) {
       const int T = std::min (n, std::max (1, std::min (8, (int)std::thread::hardware_concurrency())));
       std::atomic<int> next (0);
-      auto job = [&] { for (int i; (i = next.fetch_add (1)) < n;) if (o.pics[i].info.output) rt->streams[o.pics[i].stream]->yuv.update (out_pin[o.idx] + o.per * i, o.per); };
+      auto job = [&] { for (int i; (i = next.fetch_add (1)) < n;) if (o.pics[i].info.output) rt->streams[o.pics[i].stream]->yuv.update (base + o.per * i, o.per); };
       if (T <= 1) job();
       else { std::vector<std::thread> th; for (int t = 0; t < T; t++) th.emplace_back (job); for (auto& t : th) t.join(); }
     }
     for (int i = 0; i < n; i++) {
       Stream& s = *rt->streams[o.pics[i].stream];
       if (!o.pics[i].info.output) continue;
-      if (P->fn) P->fn (P->user, o.pics[i].stream, s.pictures_output, o.pics[i].info.width, o.pics[i].info.height, out_pin[o.idx] + o.per * i);
+      if (P->fn) P->fn (P->user, o.pics[i].stream, s.pictures_output, o.pics[i].info.width, o.pics[i].info.height, base + o.per * i);
       s.pictures_output++;
     }
   };
+  // the output thread: one packed read at a time, oldest first
+  std::thread out_thread ([&] {
+    for (;;) {
+      Out o;
+      {
+        std::unique_lock<std::mutex> g (P->out_mu);
+        P->out_cv.wait (g, [&] { return P->out_quit || !P->out_q.empty(); });
+        if (P->out_q.empty()) return;
+        o = std::move (P->out_q.front());
+        P->out_q.pop_front();
+      }
+      if (lh264_output_wait (ctx) != LH264_OK) { rt->fail (std::string ("lh264_output_wait: ") + lh264_last_error()); P->rc = -1; }   // (every read issued so far is on the host)
+      else deliver (o);
+      { std::lock_guard<std::mutex> g (P->out_mu); P->out_in_flight--; }
+      P->out_cv.notify_all();
+    }
+  });
+  auto drain_output = [&] { std::unique_lock<std::mutex> g (P->out_mu); P->out_cv.wait (g, [&] { return P->out_in_flight == 0; }); };
 
   for (long k = 0;; k++) {
     // ---- wait for step k of every parse thread ----
@@ -423,7 +451,7 @@ void pipeline_main (Pipeline* P) {
       bool reopen = false;
       for (const Placed& pl : step) if (rt->streams[pl.stream]->geo_seen != pl.geo_serial) reopen = true;
       if (reopen) {
-        if (want_yuv) { if (lh264_output_wait (ctx) != LH264_OK) FAIL ("lh264_output_wait"); if (prev.valid) { deliver (prev); prev.valid = false; } }
+        drain_output();
         if (lh264_sync (ctx) != LH264_OK) FAIL ("lh264_sync");
       }
       const double to0 = now();
@@ -479,27 +507,34 @@ void pipeline_main (Pipeline* P) {
       if (parse_only) { descs.clear(); mdescs.clear(); }
       if (!descs.empty() && lh264_recon_submit (ctx, descs.data(), (int)descs.size()) != LH264_OK) FAIL ("lh264_recon_submit");
       if (!mdescs.empty() && lh264_model_submit (ctx, mdescs.data(), (int)mdescs.size()) != LH264_OK) FAIL ("lh264_model_submit");
-      const double tg0 = now();
       if (want_yuv && !parse_only) {
-        // the pictures of step k - 1 were on their way to the host while step k's records went up: take them now, start this
-        // step's copy, then hash / hand out the previous pictures while it runs
-        if (lh264_output_wait (ctx) != LH264_OK) FAIL ("lh264_output_wait");
-        P->t_wait_gpu += now() - tg0;
         if (same_geometry) {
           const size_t per = (size_t)out_w * out_h + 2 * (size_t) ((out_w + 1) / 2) * ((out_h + 1) / 2);
-          const int oi = prev.valid ? prev.idx ^ 1 : 0;
-          if (per * step.size() > out_cap[oi]) {
-            if (out_pin[oi]) lh264_host_free (out_pin[oi]);
-            out_cap[oi] = per * step.size(); out_pin[oi] = (uint8_t*)lh264_host_alloc (out_cap[oi]);
-            if (!out_pin[oi]) { out_cap[oi] = 0; rt->fail ("cannot allocate pinned output memory"); P->rc = LH264_E_NOMEM; goto done; }
+          const int oi = (int) (P->out_issued % 2);
+          {                                                // output buffer oi is free once the read of two steps ago is delivered
+            const double tg0 = now();
+            std::unique_lock<std::mutex> g (P->out_mu);
+            P->out_cv.wait (g, [&] { return P->out_in_flight < 2; });
+            P->t_wait_gpu += now() - tg0;
           }
-          if (lh264_pictures_read_packed (ctx, rd_streams.data(), rd_slots.data(), (int)step.size(), crop_x, crop_y, out_w, out_h, out_pin[oi], out_cap[oi], 0) != LH264_OK)
+          if (per * step.size() > P->out_cap[oi]) {
+            pinned_cache().put (P->out_pin[oi], P->out_cap[oi]);
+            P->out_pin[oi] = pinned_cache().get (per * step.size(), &P->out_cap[oi]);
+            if (!P->out_pin[oi]) { P->out_cap[oi] = 0; rt->fail ("cannot allocate pinned output memory"); P->rc = LH264_E_NOMEM; goto done; }
+          }
+          if (lh264_pictures_read_packed (ctx, rd_streams.data(), rd_slots.data(), (int)step.size(), crop_x, crop_y, out_w, out_h, P->out_pin[oi], P->out_cap[oi], 0) != LH264_OK)
             FAIL ("lh264_pictures_read_packed");
           P->d2h += per * step.size();
-          if (prev.valid) deliver (prev);
-          prev.valid = true; prev.pics = step; prev.per = per; prev.idx = oi;
-        } else {                                           // mixed geometry in one step: picture by picture
-          if (prev.valid) { deliver (prev); prev.valid = false; }
+          P->out_issued++;
+          {
+            std::lock_guard<std::mutex> g (P->out_mu);
+            Out o; o.valid = true; o.pics = step; o.per = per; o.idx = oi;
+            P->out_q.push_back (std::move (o));
+            P->out_in_flight++;
+          }
+          P->out_cv.notify_all();
+        } else {                                           // mixed geometry in one step: picture by picture, after what is on its way
+          drain_output();
           for (const Placed& pl : step) {
             Stream& s = *rt->streams[pl.stream];
             const int w = pl.info.width, h = pl.info.height, cw = (w + 1) / 2, ch = (h + 1) / 2;
@@ -529,16 +564,19 @@ void pipeline_main (Pipeline* P) {
     P->cv_released.notify_all();
   }
   if (lh264_sync (ctx) != LH264_OK) FAIL ("lh264_sync");
-  if (prev.valid) { deliver (prev); prev.valid = false; }
 done:
 #undef FAIL
+  drain_output();
+  { std::lock_guard<std::mutex> g (P->out_mu); P->out_quit = true; }
+  P->out_cv.notify_all();
+  out_thread.join();
   P->t_end = now();
   {
     std::lock_guard<std::mutex> g (P->mu);
     P->abort = true;                     // (also the normal end: no parse thread is waiting any more)
   }
   P->cv_released.notify_all();
-  for (int k = 0; k < 2; k++) if (out_pin[k]) lh264_host_free (out_pin[k]);
+  for (int k = 0; k < 2; k++) { pinned_cache().put (P->out_pin[k], P->out_cap[k]); P->out_pin[k] = nullptr; P->out_cap[k] = 0; }
 }
 
 // the `.pip` file set of every stream of a pipeline: default stream (host) + tag side streams (GPU)

@@ -40,7 +40,7 @@ class ModelEmu {
     const int total_recs = pic.n_recs, blocks = (total_recs + GEN_THREADS - 1) / GEN_THREADS;
     const size_t gen_smem = (size_t)GEN_THREADS * sizeof (ThreadMb);
     if ((int)jobs_.size() >= code_steps_) { const int rc = flush(); if (rc) return rc; }
-    PoolDev pool{ &pool_used_, &pages_pending_ };
+    PoolDev pool{ &pool_used_, &pages_pending_, &pages_pending_other_ };
     emu::launch (1, 1, 32, [&] { k_model_frame (pd, 1, &poison); });
     emu::launch ((unsigned)blocks, 1, GEN_THREADS, [&] { k_model_count (pd, 1, total_recs, &poison); }, gen_smem);
     emu::launch (1, 1, 1024, [&] { k_model_scan (pd, 1, &pic_total, &poison); });
@@ -107,7 +107,7 @@ class ModelEmu {
  private:
   std::vector<CodeJob> jobs_;                          // pending: generated, not coded yet
   unsigned long long pool_used_ = 0;
-  unsigned int pages_pending_ = 0;
+  unsigned int pages_pending_ = 0, pages_pending_other_ = 0;
   int code_steps_ = getenv ("LH264_CODE_STEPS") ? atoi (getenv ("LH264_CODE_STEPS")) : 4;
   bool open_ = false;
   int max_mbs_ = 0;
