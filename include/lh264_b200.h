@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define LH264_ABI_VERSION 1
+#define LH264_ABI_VERSION 2
 
 /* ---- error codes ------------------------------------------------------------------------ */
 #define LH264_OK             0
@@ -403,6 +403,67 @@ typedef struct lh264_decode_job {
 
 /* Synchronous: uploads the jobs, runs one warp per job, downloads the bits.  Returns LH264_OK when every job decoded.    */
 int  lh264_model_decode(lh264_ctx* ctx, lh264_decode_job* jobs, int n_jobs);
+
+/* ---- compact transfer form of a picture's records -------------------------------------------------------------------------
+ * lh264_mb_rec and lh264_model_mb are laid out for the kernels (128 bytes, one warp-wide load); most of their bytes repeat
+ * (a 16x16 partition's motion vector sixteen times) or are unused by the macroblock's type.  Where the records cross PCIe at
+ * the rate of a thousand 1080p streams, host memory bandwidth - parser stores + DMA reads + the decoded pictures coming back -
+ * is what limits the path, so a host may hand them over in this form instead: 32 + 48 bytes per macroblock plus 16-byte
+ * "extra" units for the types that need more, expanded on the device into exactly the records above (lh264_expand_mb /
+ * lh264_expand_mm in losslessh264_b200/csrc/compact_records.h state the mapping, and its inverse for the host side).          */
+typedef struct lh264_cmb {            /* compact lh264_mb_rec, 32 bytes                                                          */
+  uint8_t  mb_type, flags, cbp, qp_y;
+  uint8_t  qp_c[2], i16_mode, chroma_mode;
+  uint16_t slice_idx;
+  uint8_t  nxn_avail;
+  uint8_t  kind;                      /* 0: mv below holds for all sixteen blocks (P16x16, P_Skip; intra without 4x4 modes: 0)
+                                         1: extra = intra_mode[16]                      (1 unit;  I4x4, I8x8)
+                                         2: extra = mv[16][2]                           (4 units; P16x8, P8x16)
+                                         3: extra = mv[16][2], sub_mb_type[4], 12 pad   (5 units; P8x8)                          */
+  uint32_t nz_mask, coded_mask, coef_off;
+  int8_t   ref_idx[4];
+  union { int16_t mv[2]; uint32_t extra_off; } u;   /* kind != 0: first unit of the extra data in the picture's mb extra array  */
+} lh264_cmb;
+
+typedef struct lh264_cmm {            /* compact lh264_model_mb, 48 bytes                                                        */
+  uint32_t mb_addr;
+  uint16_t flags, skip_run, mb_in_slice;
+  uint8_t  type_code, cbp;
+  uint8_t  luma_qp, chroma_mode, i16_mode;
+  int8_t   qp_delta;
+  uint8_t  sub_mb_type[4];
+  int8_t   ref_idx[4];
+  uint32_t coded_mask, coef_off;
+  uint8_t  kind;                      /* 0: mvd below: [0] the first partition's, [1] the second's (16x8: block 8, 8x16: block 2)
+                                         1: extra = pred_mode[16], pred_avail[16]      (2 units; I4x4, I8x8)
+                                         2: extra = mvd[16][2]                          (4 units; 8x8 types)                     */
+  uint8_t  reserved[3];
+  union { int16_t mvd[2][2]; uint32_t extra_off; } u;
+  uint32_t reserved2;
+} lh264_cmm;
+
+/* One picture in compact form: reconstruction and model hand-off together (they share the coefficient pool).                  */
+typedef struct lh264_compact_picture {
+  int32_t  stream;                    /* lh264_stream_open handle (ignored without LH264_COMPACT_RECON)                          */
+  int32_t  model_stream;              /* lh264_model_open handle  (ignored without LH264_COMPACT_MODEL)                          */
+  int32_t  cur_slot, mb_w, mb_h;
+  int32_t  n_slices, n_model_slices, n_recs, n_coef_blocks;
+  int32_t  n_mb_extra, n_mm_extra;    /* 16-byte units                                                                           */
+  int32_t  reserved;
+  const lh264_slice_rec*   slices;
+  const lh264_model_slice* model_slices;
+  const lh264_cmb*  cmbs;             /* mb_w * mb_h, raster order                                                               */
+  const lh264_cmm*  cmms;             /* n_recs, slice-data order                                                                */
+  const uint8_t*    mb_extra;
+  const uint8_t*    mm_extra;
+  const int16_t*    coefs;
+} lh264_compact_picture;
+#define LH264_COMPACT_RECON 1
+#define LH264_COMPACT_MODEL 2
+/* = lh264_recon_submit (flags & LH264_COMPACT_RECON) and lh264_model_submit (flags & LH264_COMPACT_MODEL) for a batch of pictures
+ * handed over in compact form: the records are expanded on the device (k_expand_mb / k_expand_mm) in front of the same kernels.
+ * Host buffers may be reused after lh264_inputs_consumed().                                                                   */
+int  lh264_submit_compact(lh264_ctx* ctx, const lh264_compact_picture* pics, int n_pics, int flags);
 
 #ifdef __cplusplus
 }

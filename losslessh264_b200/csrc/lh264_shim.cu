@@ -5,6 +5,7 @@
 // (SDqLayer, dec_frame.h:61-127) into HBM and issues the reconstruction launches that replace
 // WelsTargetSliceConstruction (decode_slice.cpp:110-206) for every picture of the batch.
 // There is no CPU fallback in this file: without a CUDA device every entry point fails.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>
@@ -18,6 +19,36 @@
 #include "recon_rows.cuh"
 #include "decode_rows.cuh"
 #include "model_kernels.cuh"
+#include "compact_records.h"
+
+// ---- expansion of compact records (include/lh264_b200.h: lh264_cmb / lh264_cmm) into the kernels' 128-byte records ------------
+struct ExpandJob { const void* src; const uint8_t* extra; void* dst; int n; int pad; };    // one picture
+__global__ void __launch_bounds__ (128) k_expand_mb (const ExpandJob* __restrict__ jobs) {
+  const ExpandJob j = jobs[blockIdx.y];
+  const lh264_cmb* src = static_cast<const lh264_cmb*> (j.src);
+  lh264_mb_rec* dst = static_cast<lh264_mb_rec*> (j.dst);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.n; i += gridDim.x * blockDim.x) {
+    lh264_mb_rec m;
+    lh264_expand_mb (src[i], j.extra, m);
+    const uint4* q = reinterpret_cast<const uint4*> (&m);
+    uint4* o = reinterpret_cast<uint4*> (dst + i);
+#pragma unroll
+    for (int k = 0; k < 8; k++) o[k] = q[k];
+  }
+}
+__global__ void __launch_bounds__ (128) k_expand_mm (const ExpandJob* __restrict__ jobs) {
+  const ExpandJob j = jobs[blockIdx.y];
+  const lh264_cmm* src = static_cast<const lh264_cmm*> (j.src);
+  lh264_model_mb* dst = static_cast<lh264_model_mb*> (j.dst);
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < j.n; i += gridDim.x * blockDim.x) {
+    lh264_model_mb m;
+    lh264_expand_mm (src[i], j.extra, m);
+    const uint4* q = reinterpret_cast<const uint4*> (&m);
+    uint4* o = reinterpret_cast<uint4*> (dst + i);
+#pragma unroll
+    for (int k = 0; k < 8; k++) o[k] = q[k];
+  }
+}
 
 using namespace lh264;
 
@@ -74,8 +105,10 @@ struct BatchDev {                            // device-resident batch
   DevBuf<lh264_slice_rec> slices;
   DevBuf<PicDev> pics;
   DevBuf<int> row_sync;                      // DecodeSync header + progress[n_pics][max_rows]
-  int n_pics = 0, max_rows = 0;
-  void release() { mbs.release(); coefs.release(); slices.release(); pics.release(); row_sync.release(); }
+  DevBuf<lh264_cmb> cmb; DevBuf<uint8_t> xmb; DevBuf<ExpandJob> xjobs;   // compact hand-off: staged here, expanded into mbs
+  int n_pics = 0, max_rows = 0, max_mbs = 0;
+  bool compact = false;
+  void release() { mbs.release(); coefs.release(); slices.release(); pics.release(); row_sync.release(); cmb.release(); xmb.release(); xjobs.release(); }
 };
 
 } // namespace
@@ -95,6 +128,7 @@ struct lh264_ctx {
   bool batch_shared[2] = {false, false};
   void* batch_sharer[2] = {nullptr, nullptr};   // the MBatch (model_host.inl) that shares batch[k]'s pools
   PinBuf<PicDev> h_pics;
+  PinBuf<ExpandJob> h_xjobs;                 // (same life cycle as h_pics: guarded by `staged`)
   cudaEvent_t staged = nullptr;              // h_pics consumed by the H2D copy
   bool staged_pending = false;
   // packed read-back: job tables and output buffers alternate, so that a call neither waits for the kernels in front of it on the
@@ -184,7 +218,7 @@ void lh264_ctx_destroy (lh264_ctx* c) {
   decode_destroy (c);
   for (auto& s : c->streams) { if (s.base) cudaFree (s.base); if (s.lines) cudaFree (s.lines); }
   if (c->d_error) cudaFree (c->d_error);
-  c->batch[0].release(); c->batch[1].release(); c->h_pics.release();
+  c->batch[0].release(); c->batch[1].release(); c->h_pics.release(); c->h_xjobs.release();
   for (int i = 0; i < 2; i++) if (c->batch_free[i]) cudaEventDestroy (c->batch_free[i]);
   c->pack_jobs.release();
   for (int i = 0; i < 2; i++) {
@@ -230,11 +264,11 @@ int lh264_stream_close (lh264_ctx* c, int stream) {
   return LH264_OK;
 }
 
-static int check_pic (lh264_ctx* c, const lh264_picture_desc& p) {
+static int check_pic (lh264_ctx* c, const lh264_picture_desc& p, bool need_mbs = true) {
   if (p.stream < 0 || p.stream >= (int)c->streams.size() || !c->streams[p.stream].open) return fail (LH264_E_INVALID, "picture names a closed stream");
   const StreamRec& s = c->streams[p.stream];
   if (p.cur_slot < 0 || p.cur_slot >= s.n_slots) return fail (LH264_E_INVALID, "cur_slot out of range");
-  if (p.n_slices <= 0 || !p.slices || !p.mbs || (p.n_coef_blocks > 0 && !p.coefs) || p.n_coef_blocks < 0) return fail (LH264_E_INVALID, "malformed picture_desc");
+  if (p.n_slices <= 0 || !p.slices || (need_mbs && !p.mbs) || (p.n_coef_blocks > 0 && !p.coefs) || p.n_coef_blocks < 0) return fail (LH264_E_INVALID, "malformed picture_desc");
   return LH264_OK;
 }
 
@@ -256,26 +290,41 @@ struct CopyMerger {
 };
 
 // Copies the records of a batch into HBM (async) and fills the device picture table.
-static int stage_batch (lh264_ctx* c, BatchDev& b, PinBuf<PicDev>& h_pics, const lh264_picture_desc* pics, int n) {
-  size_t tot_mbs = 0, tot_blk = 0, tot_sl = 0;
+static int stage_batch (lh264_ctx* c, BatchDev& b, PinBuf<PicDev>& h_pics, const lh264_picture_desc* pics, int n, const lh264_compact_picture* cp = nullptr) {
+  size_t tot_mbs = 0, tot_blk = 0, tot_sl = 0, tot_x = 0;
   for (int i = 0; i < n; i++) {
-    int rc = check_pic (c, pics[i]);
+    int rc = check_pic (c, pics[i], cp == nullptr);
     if (rc) return rc;
+    if (cp) {
+      if (!cp[i].cmbs || cp[i].n_mb_extra < 0 || (cp[i].n_mb_extra > 0 && !cp[i].mb_extra)) return fail (LH264_E_INVALID, "malformed compact picture");
+      tot_x += (size_t)cp[i].n_mb_extra;
+    }
     const StreamRec& s = c->streams[pics[i].stream];
     tot_mbs += (size_t)s.mb_w * s.mb_h; tot_blk += pics[i].n_coef_blocks; tot_sl += pics[i].n_slices;
   }
   CK (b.mbs.reserve (tot_mbs)); CK (b.coefs.reserve (tot_blk * 16 + 16)); CK (b.slices.reserve (tot_sl));
   CK (b.pics.reserve (n));
+  b.compact = cp != nullptr;
+  if (cp) { CK (b.cmb.reserve (tot_mbs)); CK (b.xmb.reserve (tot_x * 16 + 16)); CK (b.xjobs.reserve (n)); }
   if (c->staged_pending) { CK (cudaEventSynchronize (c->staged)); c->staged_pending = false; }
   CK (h_pics.reserve (n));
-  size_t o_mb = 0, o_blk = 0, o_sl = 0;
-  b.n_pics = n; b.max_rows = 0;
+  if (cp) CK (c->h_xjobs.reserve (n));
+  size_t o_mb = 0, o_blk = 0, o_sl = 0, o_x = 0;
+  b.n_pics = n; b.max_rows = 0; b.max_mbs = 0;
+  CopyMerger cm_cmb (c->h2d_stream), cm_x (c->h2d_stream);
   CopyMerger cm_mb (c->h2d_stream), cm_co (c->h2d_stream), cm_sl (c->h2d_stream);
   for (int i = 0; i < n; i++) {
     const lh264_picture_desc& p = pics[i];
     const StreamRec& s = c->streams[p.stream];
     const size_t nmb = (size_t)s.mb_w * s.mb_h;
-    cm_mb.add (b.mbs.p + o_mb, p.mbs, nmb * sizeof (lh264_mb_rec));
+    if (!cp) cm_mb.add (b.mbs.p + o_mb, p.mbs, nmb * sizeof (lh264_mb_rec));
+    else {
+      cm_cmb.add (b.cmb.p + o_mb, cp[i].cmbs, nmb * sizeof (lh264_cmb));
+      cm_x.add (b.xmb.p + o_x * 16, cp[i].mb_extra, (size_t)cp[i].n_mb_extra * 16);
+      c->h_xjobs.p[i] = ExpandJob{ b.cmb.p + o_mb, b.xmb.p + o_x * 16, b.mbs.p + o_mb, (int)nmb, 0 };
+      o_x += (size_t)cp[i].n_mb_extra;
+      b.max_mbs = std::max (b.max_mbs, (int)nmb);
+    }
     cm_co.add (b.coefs.p + o_blk * 16, p.coefs, (size_t)p.n_coef_blocks * 32);
     cm_sl.add (b.slices.p + o_sl, p.slices, (size_t)p.n_slices * sizeof (lh264_slice_rec));
     PicDev& d = h_pics.p[i];
@@ -285,8 +334,9 @@ static int stage_batch (lh264_ctx* c, BatchDev& b, PinBuf<PicDev>& h_pics, const
     b.max_rows = std::max (b.max_rows, s.mb_h);
     o_mb += nmb; o_blk += p.n_coef_blocks; o_sl += p.n_slices;
   }
-  cm_mb.flush(); cm_co.flush(); cm_sl.flush();
-  CK (cm_mb.err); CK (cm_co.err); CK (cm_sl.err);
+  cm_mb.flush(); cm_co.flush(); cm_sl.flush(); cm_cmb.flush(); cm_x.flush();
+  CK (cm_mb.err); CK (cm_co.err); CK (cm_sl.err); CK (cm_cmb.err); CK (cm_x.err);
+  if (cp) CK (cudaMemcpyAsync (b.xjobs.p, c->h_xjobs.p, n * sizeof (ExpandJob), cudaMemcpyHostToDevice, c->h2d_stream));
   CK (cudaMemcpyAsync (b.pics.p, h_pics.p, n * sizeof (PicDev), cudaMemcpyHostToDevice, c->h2d_stream));
   CK (cudaEventRecord (c->staged, c->h2d_stream));
   c->staged_pending = true;
@@ -303,6 +353,11 @@ static int launch_recon (lh264_ctx* c, BatchDev& b) {
   const long long rows = (long long)b.n_pics * b.max_rows;
   const int blocks = (int)std::max (1LL, std::min ((long long)c->n_sm * c->occ_recon, (rows + ROWS_WARPS - 1) / ROWS_WARPS));
   if (c->timing) CK (cudaEventRecord (c->ev[0], c->stream));
+  if (b.compact) {                            // the records arrived in compact form: expand them where the row kernel reads them
+    k_expand_mb<<<dim3 ((unsigned)std::min ((b.max_mbs + 127) / 128, 64), (unsigned)b.n_pics), 128, 0, c->stream>>> (b.xjobs.p);
+    c->launches++;
+    b.compact = false;
+  }
   CK (cudaMemsetAsync (b.row_sync.p, 0, sync_bytes, c->stream));
   k_decode_rows<<<blocks, ROWS_WARPS * 32, 0, c->stream>>> (b.pics.p, b.n_pics, b.max_rows, reinterpret_cast<DecodeSync*> (b.row_sync.p), c->d_error);
   c->launches++;
@@ -315,7 +370,7 @@ static int launch_recon (lh264_ctx* c, BatchDev& b) {
   return LH264_OK;
 }
 
-int lh264_recon_submit (lh264_ctx* c, const lh264_picture_desc* pics, int n_pics) {
+static int recon_submit_impl (lh264_ctx* c, const lh264_picture_desc* pics, int n_pics, const lh264_compact_picture* cp) {
   if (!c || (n_pics > 0 && !pics) || n_pics < 0) return fail (LH264_E_INVALID, "bad arguments");
   CK (cudaSetDevice (c->device));
   // two pictures of one stream in a batch would race on cur_slot (and on the stream's references): refuse, at every batch size
@@ -339,7 +394,7 @@ int lh264_recon_submit (lh264_ctx* c, const lh264_picture_desc* pics, int n_pics
   }
   // ... and so must the reconstruction kernel that read this staging buffer two submits ago
   if (c->decode_done_pending[k]) { CK (cudaStreamWaitEvent (c->h2d_stream, c->decode_done[k], 0)); c->decode_done_pending[k] = false; }
-  int rc = stage_batch (c, c->batch[k], c->h_pics, pics, n_pics);
+  int rc = stage_batch (c, c->batch[k], c->h_pics, pics, n_pics, cp);
   if (rc) return rc;
   for (int i = 0; i < n_pics; i++) if (pics[i].n_coef_blocks) c->staged_coefs.push_back (lh264_ctx::StagedPool{pics[i].coefs, c->h_pics.p[i].coefs, pics[i].n_coef_blocks});
   CK (cudaEventRecord (c->recon_staged, c->h2d_stream));
@@ -349,6 +404,8 @@ int lh264_recon_submit (lh264_ctx* c, const lh264_picture_desc* pics, int n_pics
   c->decode_done_pending[k] = true;
   return LH264_OK;
 }
+
+int lh264_recon_submit (lh264_ctx* c, const lh264_picture_desc* pics, int n_pics) { return recon_submit_impl (c, pics, n_pics, nullptr); }
 
 int lh264_batch_upload (lh264_ctx* c, const lh264_picture_desc* pics, int n_pics, lh264_resident_batch** out) {
   if (!c || !pics || n_pics <= 0 || !out) return fail (LH264_E_INVALID, "bad arguments");

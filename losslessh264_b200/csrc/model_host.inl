@@ -21,6 +21,8 @@ struct MStreamHost {
 struct MBatch {                    // one batch of model pictures in HBM
   DevBuf<lh264_model_mb> recs; DevBuf<lh264_model_slice> slices; DevBuf<int16_t> coefs;
   DevBuf<MPicDev> pics; PinBuf<MPicDev> h_pics;
+  DevBuf<lh264_cmm> cmm; DevBuf<uint8_t> xmm; DevBuf<ExpandJob> xjobs; PinBuf<ExpandJob> h_xjobs;   // compact hand-off, expanded into recs
+  bool compact = false; int max_recs = 0;
   DevBuf<uint32_t> rec_cnt; DevBuf<uint32_t> rec_off; DevBuf<uint32_t> pic_total; DevBuf<unsigned long long> dec_base;
   PinBuf<uint32_t> h_total; PinBuf<unsigned long long> h_base;
   DevBuf<BatchCtl> ctl; PinBuf<BatchCtl> h_ctl;
@@ -31,6 +33,7 @@ struct MBatch {                    // one batch of model pictures in HBM
   int n = 0, total_recs = 0;
   int shares_recon_batch = -1;     // index of the recon staging batch whose coefficient pools this batch reads
   void release() { recs.release(); slices.release(); coefs.release(); pics.release(); h_pics.release(); rec_cnt.release(); rec_off.release();
+                   cmm.release(); xmm.release(); xjobs.release(); h_xjobs.release();
                    pic_total.release(); dec_base.release(); h_total.release(); h_base.release(); ctl.release(); h_ctl.release();
                    if (done) { cudaEventDestroy (done); done = nullptr; }
                    if (staged) { cudaEventDestroy (staged); staged = nullptr; } }
@@ -65,6 +68,8 @@ struct ModelCtx {
   // block scheduler they starve each other (measured, profiles/r2_summary.md: 58 ms per step together, 52 ms one after the
   // other).  LH264_CODE_EXCLUSIVE=0 lets them overlap again.
   bool exclusive = true;
+  bool exclusive_gen = true;                       // ... and neither do the generation kernels of the following steps (LH264_CODE_EXCLUSIVE=1: they may)
+  bool partitioned = false;                        // code_stream belongs to an SM partition (model_partition_stream)
   int pend_steps = 0;
   std::vector<std::vector<int> > pend_streams;     // model stream of every job of a pending step
   std::vector<int> slot_of;                        // scratch: model stream -> block of the coder launch
@@ -88,6 +93,47 @@ int model_grow_arena (lh264_ctx* c, ModelCtx* m, unsigned int need_pages);
 
 struct lh264_model_batch { MBatch b; };
 
+// A CUDA stream whose kernels run on a partition of `n_sms` SMs only (driver green contexts, CUDA 12.4+; fetched through
+// cudaGetDriverEntryPoint, so nothing links against libcuda).  The deferred coder - one block of two latency-bound warps per stream,
+// resident for a whole window - is confined to a quarter of the GPU this way, and the reconstruction / generation kernels of the
+// following steps keep the other SMs to themselves instead of being starved SM by SM.  nullptr = not
+// available: the caller falls back to an ordinary stream and to running coder and reconstruction one after the other.
+static cudaStream_t model_partition_stream (int device, int n_sms) {
+  typedef CUresult (*fn_dev_get) (CUdevice*, int);
+  typedef CUresult (*fn_get_res) (CUdevice, CUdevResource*, CUdevResourceType);
+  typedef CUresult (*fn_split) (CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int);
+  typedef CUresult (*fn_desc) (CUdevResourceDesc*, CUdevResource*, unsigned int);
+  typedef CUresult (*fn_gctx) (CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int);
+  typedef CUresult (*fn_gstream) (CUstream*, CUgreenCtx, unsigned int, int);
+  auto drv = [] (const char* name) -> void* {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint (name, &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+  };
+  fn_dev_get dev_get = (fn_dev_get)drv ("cuDeviceGet");
+  fn_get_res get_res = (fn_get_res)drv ("cuDeviceGetDevResource");
+  fn_split split = (fn_split)drv ("cuDevSmResourceSplitByCount");
+  fn_desc gen_desc = (fn_desc)drv ("cuDevResourceGenerateDesc");
+  fn_gctx gctx_create = (fn_gctx)drv ("cuGreenCtxCreate");
+  fn_gstream gstream_create = (fn_gstream)drv ("cuGreenCtxStreamCreate");
+  if (!dev_get || !get_res || !split || !gen_desc || !gctx_create || !gstream_create) return nullptr;
+  CUdevice dev;
+  CUdevResource all, part, rest;
+  unsigned int groups = 1;
+  CUdevResourceDesc desc;
+  CUgreenCtx g;
+  CUstream st = nullptr;
+  if (dev_get (&dev, device) != CUDA_SUCCESS) return nullptr;
+  if (get_res (dev, &all, CU_DEV_RESOURCE_TYPE_SM) != CUDA_SUCCESS) return nullptr;
+  if (split (&part, &groups, &all, &rest, 0, (unsigned int)n_sms) != CUDA_SUCCESS || groups < 1) return nullptr;
+  if (gen_desc (&desc, &part, 1) != CUDA_SUCCESS) return nullptr;
+  if (gctx_create (&g, desc, dev, CU_GREEN_CTX_DEFAULT_STREAM) != CUDA_SUCCESS) return nullptr;
+  if (gstream_create (&st, g, CU_STREAM_NON_BLOCKING, 0) != CUDA_SUCCESS) return nullptr;
+  if (getenv ("LH264_DEBUG")) fprintf (stderr, "lh264: coder partition of %u SMs (asked for %d)\n", part.sm.smCount, n_sms);
+  return (cudaStream_t)st;                            // (the green context lives as long as the process)
+}
+
 static ModelCtx* model_ctx (lh264_ctx* c) {
   if (!c->model) {
     ModelCtx* m = new (std::nothrow) ModelCtx();
@@ -104,11 +150,17 @@ static ModelCtx* model_ctx (lh264_ctx* c) {
     cudaMalloc (&m->d_pages_pending, 2 * sizeof (unsigned int));
     cudaMemset (m->d_pool_used, 0, 2 * sizeof (unsigned long long));
     cudaMemset (m->d_pages_pending, 0, 2 * sizeof (unsigned int));
-    cudaStreamCreateWithFlags (&m->code_stream, cudaStreamNonBlocking);
+    // LH264_CODER_SMS=n: the coder gets a partition of n SMs and runs beside the other kernels (0 / unset: no partition)
+    if (const char* e = getenv ("LH264_CODER_SMS")) {
+      const int n = atoi (e);
+      if (n > 0) { m->code_stream = model_partition_stream (c->device, n); if (m->code_stream) { m->partitioned = true; m->exclusive = false; } }
+    }
+    if (!m->code_stream) cudaStreamCreateWithFlags (&m->code_stream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags (&m->gen_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags (&m->recon_idle, cudaEventDisableTiming);
     for (int k = 0; k < 2; k++) { cudaEventCreateWithFlags (&m->index_copied[k], cudaEventDisableTiming); cudaEventCreateWithFlags (&m->coder_done[k], cudaEventDisableTiming); }
-    if (const char* e = getenv ("LH264_CODE_EXCLUSIVE")) m->exclusive = atoi (e) != 0;
+    if (const char* e = getenv ("LH264_CODE_EXCLUSIVE")) { m->exclusive = atoi (e) != 0; m->exclusive_gen = atoi (e) >= 2; }
+    if (m->partitioned && !getenv ("LH264_CODE_EXCLUSIVE")) m->exclusive = false;
     if (const char* e = getenv ("LH264_CODE_STEPS")) m->code_steps = std::max (1, std::min (atoi (e), 64));
     {
       size_t free_b = 0, total_b = 0;
@@ -237,8 +289,8 @@ int lh264_model_close (lh264_ctx* c, int ms) {
 }
 
 // Validates a batch and copies its records into HBM (async); fills the device picture table.
-static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_picture* pics, int n, bool share_coefs) {
-  size_t tot_rec = 0, tot_sl = 0, tot_blk = 0;
+static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_picture* pics, int n, bool share_coefs, const lh264_compact_picture* cp = nullptr) {
+  size_t tot_rec = 0, tot_sl = 0, tot_blk = 0, tot_x = 0;
   m->batch_serial++;
   for (int i = 0; i < n; i++) {
     const lh264_model_picture& p = pics[i];
@@ -247,7 +299,11 @@ static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_
     if (rc) return rc;
     const MStreamHost& s = m->streams[p.model_stream];
     if (p.mb_w <= 0 || p.mb_h <= 0 || (long long)p.mb_w * p.mb_h > s.max_mbs) return fail (LH264_E_INVALID, "picture larger than the model stream was opened for");
-    if (p.n_slices <= 0 || p.n_recs <= 0 || !p.slices || !p.recs || p.n_coef_blocks < 0 || (p.n_coef_blocks > 0 && !p.coefs)) return fail (LH264_E_INVALID, "malformed model picture");
+    if (p.n_slices <= 0 || p.n_recs <= 0 || !p.slices || (!cp && !p.recs) || p.n_coef_blocks < 0 || (p.n_coef_blocks > 0 && !p.coefs)) return fail (LH264_E_INVALID, "malformed model picture");
+    if (cp) {
+      if (!cp[i].cmms || cp[i].n_mm_extra < 0 || (cp[i].n_mm_extra > 0 && !cp[i].mm_extra)) return fail (LH264_E_INVALID, "malformed compact picture");
+      tot_x += (size_t)cp[i].n_mm_extra;
+    }
     for (int k = 0; k < p.n_slices; k++) {
       const lh264_model_slice& sl = p.slices[k];
       if (sl.first_rec < 0 || sl.n_recs < 0 || sl.first_rec + sl.n_recs > p.n_recs) return fail (LH264_E_INVALID, "slice record range out of bounds");
@@ -262,14 +318,23 @@ static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_
   CK (b.pic_total.reserve (n)); CK (b.dec_base.reserve (n)); CK (b.ctl.reserve (1));
   { int rs = model_settle_batch (c, m, &b); if (rs) return rs; }   // the batch that used this staging before is done and read
   CK (b.h_pics.reserve (n)); CK (b.h_total.reserve (n + 1)); CK (b.h_base.reserve (n)); CK (b.h_ctl.reserve (1));
+  b.compact = cp != nullptr; b.max_recs = 0;
+  if (cp) { CK (b.cmm.reserve (tot_rec)); CK (b.xmm.reserve (tot_x * 16 + 16)); CK (b.xjobs.reserve (n)); CK (b.h_xjobs.reserve (n)); }
   b.stream_of.assign (n, 0);
   bool any_shared = false;
-  size_t o_rec = 0, o_sl = 0, o_blk = 0;
-  CopyMerger cm_rec (m->stream), cm_sl (m->stream), cm_co (m->stream);
+  size_t o_rec = 0, o_sl = 0, o_blk = 0, o_x = 0;
+  CopyMerger cm_rec (m->stream), cm_sl (m->stream), cm_co (m->stream), cm_x (m->stream);
   for (int i = 0; i < n; i++) {
     const lh264_model_picture& p = pics[i];
     const MStreamHost& s = m->streams[p.model_stream];
-    cm_rec.add (b.recs.p + o_rec, p.recs, (size_t)p.n_recs * sizeof (lh264_model_mb));
+    if (!cp) cm_rec.add (b.recs.p + o_rec, p.recs, (size_t)p.n_recs * sizeof (lh264_model_mb));
+    else {
+      cm_rec.add (b.cmm.p + o_rec, cp[i].cmms, (size_t)p.n_recs * sizeof (lh264_cmm));
+      cm_x.add (b.xmm.p + o_x * 16, cp[i].mm_extra, (size_t)cp[i].n_mm_extra * 16);
+      b.h_xjobs.p[i] = ExpandJob{ b.cmm.p + o_rec, b.xmm.p + o_x * 16, b.recs.p + o_rec, p.n_recs, 0 };
+      o_x += (size_t)cp[i].n_mm_extra;
+      b.max_recs = std::max (b.max_recs, p.n_recs);
+    }
     cm_sl.add (b.slices.p + o_sl, p.slices, (size_t)p.n_slices * sizeof (lh264_model_slice));
     const int16_t* dev_coefs = nullptr;
     // same host pool AND same length as a picture of the preceding recon submit: it is that picture's pool, read its device copy
@@ -284,8 +349,13 @@ static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_
     b.stream_of[i] = p.model_stream;
     o_rec += p.n_recs; o_sl += p.n_slices; o_blk += p.n_coef_blocks;
   }
-  cm_rec.flush(); cm_sl.flush(); cm_co.flush();
-  CK (cm_rec.err); CK (cm_sl.err); CK (cm_co.err);
+  cm_rec.flush(); cm_sl.flush(); cm_co.flush(); cm_x.flush();
+  CK (cm_rec.err); CK (cm_sl.err); CK (cm_co.err); CK (cm_x.err);
+  if (cp) {                                           // expanded right behind the copies, on the same stream: the generation kernels see full records
+    CK (cudaMemcpyAsync (b.xjobs.p, b.h_xjobs.p, n * sizeof (ExpandJob), cudaMemcpyHostToDevice, m->stream));
+    k_expand_mm<<<dim3 ((unsigned)std::min ((b.max_recs + 127) / 128, 64), (unsigned)n), 128, 0, m->stream>>> (b.xjobs.p);
+    c->launches++;
+  }
   CK (cudaMemcpyAsync (b.pics.p, b.h_pics.p, n * sizeof (MPicDev), cudaMemcpyHostToDevice, m->stream));
   if (!b.staged) CK (cudaEventCreateWithFlags (&b.staged, cudaEventDisableTiming));
   CK (cudaEventRecord (b.staged, m->stream));
@@ -329,7 +399,8 @@ static int model_flush_coder (lh264_ctx* c, ModelCtx* m) {
   CK (cudaMemsetAsync (m->d_pages_pending + h, 0, sizeof (unsigned int), m->code_stream));
   CK (cudaEventRecord (m->coder_done[h], m->code_stream));
   m->coder_pending[h] = true;
-  if (m->exclusive) CK (cudaStreamWaitEvent (c->stream, m->coder_done[h], 0));
+  // exclusive: neither the reconstruction kernels nor the generation kernels of the following steps start before the coder is through
+  if (m->exclusive) { CK (cudaStreamWaitEvent (c->stream, m->coder_done[h], 0)); if (m->exclusive_gen) CK (cudaStreamWaitEvent (m->stream, m->coder_done[h], 0)); }
   m->pend_steps = 0; m->est_pool_used = 0;
   // generation goes on in the other half, once the coder launch that read it (two flushes ago) is over
   m->cur ^= 1;
@@ -505,7 +576,7 @@ static int model_run (lh264_ctx* c, ModelCtx* m, MBatch& b) {
   return LH264_OK;
 }
 
-int lh264_model_submit (lh264_ctx* c, const lh264_model_picture* pics, int n) {
+static int model_submit_impl (lh264_ctx* c, const lh264_model_picture* pics, int n, const lh264_compact_picture* cp) {
   if (!c || (n > 0 && !pics) || n < 0) return fail (LH264_E_INVALID, "bad arguments");
   if (n == 0) return LH264_OK;
   CK (cudaSetDevice (c->device));
@@ -513,9 +584,37 @@ int lh264_model_submit (lh264_ctx* c, const lh264_model_picture* pics, int n) {
   if (!m) return fail (LH264_E_NOMEM, "out of host memory");
   m->batch_cur ^= 1;
   MBatch& b = m->batch[m->batch_cur];
-  int rc = model_stage (c, m, b, pics, n, true);
+  int rc = model_stage (c, m, b, pics, n, true, cp);
   if (rc) return rc;
   return model_run (c, m, b);
+}
+int lh264_model_submit (lh264_ctx* c, const lh264_model_picture* pics, int n) { return model_submit_impl (c, pics, n, nullptr); }
+
+int lh264_submit_compact (lh264_ctx* c, const lh264_compact_picture* pics, int n, int flags) {
+  if (!c || (n > 0 && !pics) || n < 0) return fail (LH264_E_INVALID, "bad arguments");
+  if (n == 0) return LH264_OK;
+  int rc = LH264_OK;
+  if (flags & LH264_COMPACT_RECON) {
+    std::vector<lh264_picture_desc> d (n);
+    for (int i = 0; i < n; i++) {
+      d[i].stream = pics[i].stream; d[i].cur_slot = pics[i].cur_slot; d[i].n_slices = pics[i].n_slices; d[i].n_coef_blocks = pics[i].n_coef_blocks;
+      d[i].slices = pics[i].slices; d[i].mbs = nullptr; d[i].coefs = pics[i].coefs;
+    }
+    if ((rc = recon_submit_impl (c, d.data(), n, pics))) return rc;
+  }
+  if (flags & LH264_COMPACT_MODEL) {
+    std::vector<lh264_model_picture> d;
+    std::vector<lh264_compact_picture> cp;
+    for (int i = 0; i < n; i++) {
+      if (pics[i].n_recs <= 0) continue;              // (a picture without model records: nothing to code)
+      lh264_model_picture q;
+      q.model_stream = pics[i].model_stream; q.mb_w = pics[i].mb_w; q.mb_h = pics[i].mb_h; q.n_slices = pics[i].n_model_slices; q.n_recs = pics[i].n_recs;
+      q.n_coef_blocks = pics[i].n_coef_blocks; q.slices = pics[i].model_slices; q.recs = nullptr; q.coefs = pics[i].coefs;
+      d.push_back (q); cp.push_back (pics[i]);
+    }
+    if (!d.empty() && (rc = model_submit_impl (c, d.data(), (int)d.size(), cp.data()))) return rc;
+  }
+  return rc;
 }
 
 int lh264_model_batch_upload (lh264_ctx* c, const lh264_model_picture* pics, int n, lh264_model_batch** out) {

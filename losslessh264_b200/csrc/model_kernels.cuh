@@ -748,7 +748,10 @@ __device__ __forceinline__ void coder_write (Coder& c, uint8_t*& page, MState* s
 // (probability, bit) to the shared-memory ring of the decision's tag.  Warp 1 (consumer): lane t owns compact tag t and
 // drains ring t through its bool coder.  The two serial chains (per prior, per tag) thus run concurrently and the coder
 // lanes never wait for each other.
-constexpr int CODE_RING = 256;               // entries per tag ring (power of two)
+#ifndef LH264_CODE_RING
+#define LH264_CODE_RING 256
+#endif
+constexpr int CODE_RING = LH264_CODE_RING;    // entries per tag ring (power of two)
 struct CodeShared {
   uint16_t ring[32][CODE_RING];
   volatile uint32_t prod[32];               // entries ever appended to ring t (producer writes)
@@ -780,7 +783,10 @@ __global__ void __launch_bounds__ (128) k_model_commit (const MPicDev* pics, int
 }
 
 // `index[b * n_steps + j]` = position of stream-block b's picture in step j's job row (jobs + j * stride), or -1.
-__global__ void __launch_bounds__ (64) k_model_code (const CodeJob* jobs, const int* index, int n_steps, int stride, const uint32_t* dec, ArenaDev ar) {
+#ifndef LH264_CODE_BOUNDS
+#define LH264_CODE_BOUNDS __launch_bounds__ (64)
+#endif
+__global__ void LH264_CODE_BOUNDS k_model_code (const CodeJob* jobs, const int* index, int n_steps, int stride, const uint32_t* dec, ArenaDev ar) {
   __shared__ CodeShared sh;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll 1

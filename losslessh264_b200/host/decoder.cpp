@@ -163,7 +163,8 @@ struct Decoder::Impl {
   SliceHeader sh0;                       // first slice header of the picture
   int cur_slot = 0, decoded = 0;
   bool ltr_marking = false; int ltr_marked_frame_num = 0;   // set by mark_current() for the picture being finished
-  bool alloc_failed = false;             // record storage could not be had (RecordArena / heap): the picture is dropped
+  bool alloc_failed = false;
+  bool stream_coefs = true, stream_mrecs = true;   // Decoder::set_streaming_stores             // record storage could not be had (RecordArena / heap): the picture is dropped
   // the reference holds its output back until the first IDR picture has been decoded (bFreezeOutput under the freeze error
   // concealment modes h264dec selects, decoder_core.cpp:56-217): pictures of a stream whose leading IDR was lost are parsed,
   // modelled and reconstructed, but marked `output = false` for the sink and not handed out
@@ -861,7 +862,7 @@ LH264_HOT int Decoder::Impl::parse_mb (BitReader& br, int mb_addr, bool skipped,
       m.coef_off = (uint32_t) (coefs.size() / 16);
       int16_t* o = coefs.grow (16 * (size_t)__builtin_popcount (coded));
       if (!o) { memset (lev_, 0, sizeof (lev_)); return -1; }
-      for (uint32_t mk = coded; mk; mk &= mk - 1) { const int k = __builtin_ctz (mk); stream_copy (o, lev + 16 * k, 32); memset (lev + 16 * k, 0, 32); o += 16; }
+      for (uint32_t mk = coded; mk; mk &= mk - 1) { const int k = __builtin_ctz (mk); if (stream_coefs) stream_copy (o, lev + 16 * k, 32); else memcpy (o, lev + 16 * k, 32); memset (lev + 16 * k, 0, 32); o += 16; }
     }
   } else {
     set_qp (m);
@@ -1203,7 +1204,7 @@ LH264_HOT int Decoder::Impl::parse_slice_data (BitReader& br, Decoder* self) {
   auto commit_rec = [&] () -> bool {
     lh264_model_mb* dst = mrecs.grow (1);
     if (!dst) return false;
-    stream_copy (dst, &rec_local, sizeof (rec_local));
+    if (stream_mrecs) stream_copy (dst, &rec_local, sizeof (rec_local)); else memcpy (dst, &rec_local, sizeof (rec_local));
     return true;
   };
   int m_cached_qp = 0, m_last_dqp = 0;                // uiCachedLumaQp / uiLastNonzeroDeltaLumaQp, decode_slice.cpp:3061-3062
@@ -1296,6 +1297,7 @@ void Decoder::enable_rewrite_check (bool on) { d_->check_rewrite = on; if (on) d
 
 int Decoder::flush() { return d_->finish_picture (this); }
 bool Decoder::picture_open() const { return d_->open; }
+void Decoder::set_streaming_stores (bool coefs, bool model_recs) { d_->stream_coefs = coefs; d_->stream_mrecs = model_recs; }
 bool Decoder::set_arena (RecordArena* a) {
   const bool ok = d_->mbs.set_arena (a) & d_->coefs.set_arena (a) & d_->mrecs.set_arena (a);
   if (!ok) d_->alloc_failed = true;

@@ -99,6 +99,9 @@ class Decoder {
   // progress, whose records so far move over.  The pointers PictureSink::submit() sees then point into the arena.
   bool set_arena (RecordArena* arena);
   bool picture_open() const;             // a picture has been started and not yet handed to the sink
+  // non-temporal stores for the coefficient pools / the model records (worth it when they go to memory the parser never reads
+  // back, e.g. pinned staging; not when the destination is cache-resident scratch).  Default: both on.
+  void set_streaming_stores (bool coefs, bool model_recs);
   // the last slice NAL handled by the last decode() call (for the `.pip` default stream, pip_container.h); rbsp is valid
   // until the next decode() call
   struct LastSlice { bool decoded = false, cabac = false; const uint8_t* rbsp = nullptr; size_t header_bits = 0; bool idr = false; int idr_pic_id = 0, frame_num = 0; };

@@ -34,6 +34,10 @@
 #include "decoder.h"
 #include "pip_container.h"
 #include "sha1.h"
+#include "../csrc/compact_records.h"
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 using namespace lh264host;
 
@@ -89,71 +93,114 @@ struct PinRegion {                      // growable pinned buffer, bump-allocate
 
 struct Placed {                         // one picture of a step: where its arrays sit in the thread's staging buffer
   int stream;
-  size_t o_sl, o_mb, o_co, o_msl, o_mr;
-  int n_slices, n_mbs, n_blocks, n_mslices, n_mrecs;
+  size_t o_sl, o_cmb, o_xmb, o_co, o_msl, o_cmm, o_xmm;
+  int n_slices, n_mbs, n_blocks, n_mslices, n_mrecs, n_xmb, n_xmm;      // (n_xmb / n_xmm: 16-byte units)
   int mb_w, mb_h, n_slots, geo_serial;
   DecodedPictureInfo info;
 };
 
+// Regions of a step buffer (pinned): compact MB records + their extra units, coefficient pools, compact model records + extra
+// units, slice records, model slice records.
+enum { R_CMB = 0, R_XMB, R_COEFS, R_CMM, R_XMM, R_SLICES, R_MSLICES, R_COUNT };
 struct StepBuf {
-  PinRegion mbs, coefs, mrecs, slices, mslices;
+  PinRegion r[R_COUNT];
   size_t expect = 1;                    // pictures a step of the owning thread usually holds (its number of streams)
   std::vector<Placed> placed;
   bool failed = false;                  // pinned allocation failed
-  void reset() { mbs.used = coefs.used = mrecs.used = slices.used = mslices.used = 0; placed.clear(); failed = false; }
+  void reset() { for (PinRegion& x : r) x.used = 0; placed.clear(); failed = false; }
 };
 
-// The parser writes MB records, coefficient pools and model records of the picture in progress straight into the step buffer
-// of the owning thread (decoder.h RecordArena): the open picture is the LAST allocation of each region and grows in place.
+// Where the parser writes the records of the picture in progress (decoder.h RecordArena).  Coefficient pools go STRAIGHT into the
+// pinned step buffer of the owning thread: the open picture is the last allocation of the region and grows in place.  The
+// 128-byte MB records and model records go into scratch memory of the thread (one picture at a time: it stays in the core's
+// cache, the parser reads its neighbours back from there) and are handed over in compact form when the picture is done
+// (StageSink): what crosses host memory and PCIe is 32 + 48 bytes per macroblock instead of 256.
 class StepArena : public RecordArena {
  public:
-  void bind (StepBuf* b) { buf_ = b; for (int k = 0; k < 3; k++) open_[k] = false; }
-  void picture_done() { for (int k = 0; k < 3; k++) open_[k] = false; }
-  PinRegion& region (int kind) { return kind == MBS ? buf_->mbs : (kind == COEFS ? buf_->coefs : buf_->mrecs); }
+  void bind (StepBuf* b) { buf_ = b; open_ = false; }
+  void picture_done() { open_ = false; }
   uint8_t* storage (int kind, size_t need, size_t* cap, const uint8_t* old, size_t keep) override {
-    PinRegion& r = region (kind);
-    const bool mine = open_[kind] && old == r.p + start_[kind];
+    if (kind != COEFS) {
+      std::vector<uint8_t>& sc = scratch_[kind == MBS ? 0 : 1];
+      if (old && old != sc.data() && keep) {          // records arriving from the decoder's own heap (a picture left open by the previous step)
+        if (sc.size() < need) sc.resize (need + need / 4);
+        memcpy (sc.data(), old, keep);
+      } else if (sc.size() < need) sc.resize (need + need / 2 + 4096);        // (vector::resize keeps the bytes so far)
+      *cap = sc.size();
+      return sc.data();
+    }
+    PinRegion& r = buf_->r[R_COEFS];
+    const bool mine = open_ && old == r.p + start_;
     // headroom: the parser asks again only when it runs out, so hand out generously (the sink trims to the final size)
-    const size_t want = need + (kind == MBS ? 0 : std::max<size_t> (need / 2, (size_t)64 << 10));
+    const size_t want = need + std::max<size_t> (need / 2, (size_t)64 << 10);
     size_t kept = 0;
-    if (mine) { kept = keep; r.used = start_[kind] + keep; }     // grow in place (a region that has to move takes its bytes along)
-    else { start_[kind] = r.used; open_[kind] = true; }          // a new picture, or records arriving from the heap
-    // room for the thread's whole step at this picture's size (coefficient pools: at what the parser reserves first)
-    const size_t room = start_[kind] + want * buf_->expect + want * buf_->expect / 8;
+    if (mine) { kept = keep; r.used = start_ + keep; }           // grow in place (a region that has to move takes its bytes along)
+    else { start_ = r.used; open_ = true; }                      // a new picture, or records arriving from the heap
+    const size_t room = start_ + want * buf_->expect + want * buf_->expect / 8;      // room for the thread's whole step
     if (want > kept && r.take (want - kept, room) == (size_t) -1) { buf_->failed = true; return nullptr; }
-    uint8_t* q = r.p + start_[kind];
+    uint8_t* q = r.p + start_;
     if (!mine && old && keep) memcpy (q, old, keep);
     *cap = want;
     return q;
   }
  private:
   StepBuf* buf_ = nullptr;
-  size_t start_[3] = {0, 0, 0};
-  bool open_[3] = {false, false, false};
+  size_t start_ = 0;
+  bool open_ = false;
+  std::vector<uint8_t> scratch_[2];
 };
 
-// Receives the pictures a Decoder completes; their bulky records already sit in the step buffer (StepArena), the small slice
-// records are copied behind them.
+inline void stream16 (void* dst, const void* src, size_t bytes) {   // non-temporal copy, multiples of 16 bytes to 16-byte aligned memory
+#if defined(__SSE2__)
+  if ((reinterpret_cast<uintptr_t> (dst) & 15) == 0) {
+    __m128i* d = static_cast<__m128i*> (dst);
+    const __m128i* q = static_cast<const __m128i*> (src);
+    for (size_t i = 0; i < bytes / 16; i++) _mm_stream_si128 (d + i, _mm_loadu_si128 (q + i));
+    return;
+  }
+#endif
+  memcpy (dst, src, bytes);
+}
+
+// Receives the pictures a Decoder completes: compacts their MB / model records into the step buffer (lh264_cmb / lh264_cmm,
+// include/lh264_b200.h; csrc/compact_records.h), notes where the coefficient pool sits (parsed in place) and copies the small
+// slice records behind them.
 class StageSink : public PictureSink {
  public:
   int stream = 0;
   int mb_w = 0, mb_h = 0, n_slots = 0, geo_serial = 0;
   StepBuf* buf = nullptr;               // where pictures completed now are placed
   int placed_now = 0;                   // pictures placed since the owner last looked
+  bool verify = false;                  // LH264_RT_VERIFY_COMPACT: expand every compact record again and compare with its source
   int configure (int w, int h, int slots) override { mb_w = w; mb_h = h; n_slots = slots; geo_serial++; return 0; }
   int submit (const lh264_picture_desc& pic, const DecodedPictureInfo& info) override {
     Placed pl = Placed();
     pl.stream = stream; pl.info = info;
     pl.n_slices = pic.n_slices; pl.n_mbs = mb_w * mb_h; pl.n_blocks = pic.n_coef_blocks;
     pl.mb_w = mb_w; pl.mb_h = mb_h; pl.n_slots = n_slots; pl.geo_serial = geo_serial;
-    const size_t b_sl = (size_t)pic.n_slices * sizeof (lh264_slice_rec), b_mb = (size_t)pl.n_mbs * sizeof (lh264_mb_rec), b_co = (size_t)pic.n_coef_blocks * 32;
-    pl.o_sl = buf->slices.take (b_sl);
-    if (inside (buf->mbs, pic.mbs)) { pl.o_mb = (size_t) ((const uint8_t*)pic.mbs - buf->mbs.p); buf->mbs.used = pl.o_mb + b_mb; }       // parsed in place
-    else { pl.o_mb = buf->mbs.take (b_mb); if (pl.o_mb != (size_t) -1) memcpy (buf->mbs.p + pl.o_mb, pic.mbs, b_mb); }
-    if (b_co && inside (buf->coefs, pic.coefs)) { pl.o_co = (size_t) ((const uint8_t*)pic.coefs - buf->coefs.p); buf->coefs.used = pl.o_co + b_co; }
-    else { pl.o_co = buf->coefs.take (b_co); if (pl.o_co != (size_t) -1 && b_co) memcpy (buf->coefs.p + pl.o_co, pic.coefs, b_co); }
-    if (pl.o_sl == (size_t) -1 || pl.o_mb == (size_t) -1 || pl.o_co == (size_t) -1) { buf->failed = true; return LH264_E_NOMEM; }
-    memcpy (buf->slices.p + pl.o_sl, pic.slices, b_sl);
+    const size_t b_sl = (size_t)pic.n_slices * sizeof (lh264_slice_rec), b_co = (size_t)pic.n_coef_blocks * 32, n = (size_t)pl.n_mbs;
+    PinRegion& rc = buf->r[R_COEFS];
+    pl.o_sl = buf->r[R_SLICES].take (b_sl);
+    if (b_co && inside (rc, pic.coefs)) { pl.o_co = (size_t) ((const uint8_t*)pic.coefs - rc.p); rc.used = pl.o_co + b_co; }      // parsed in place
+    else { pl.o_co = rc.take (b_co); if (pl.o_co != (size_t) -1 && b_co) memcpy (rc.p + pl.o_co, pic.coefs, b_co); }
+    pl.o_cmb = buf->r[R_CMB].take (n * sizeof (lh264_cmb), n * sizeof (lh264_cmb) * buf->expect * 9 / 8);
+    pl.o_xmb = buf->r[R_XMB].take (n * 80 + 16);                                  // worst case: five units per macroblock; trimmed below
+    if (pl.o_sl == (size_t) -1 || pl.o_co == (size_t) -1 || pl.o_cmb == (size_t) -1 || pl.o_xmb == (size_t) -1) { buf->failed = true; return LH264_E_NOMEM; }
+    memcpy (buf->r[R_SLICES].p + pl.o_sl, pic.slices, b_sl);
+    lh264_cmb* out = reinterpret_cast<lh264_cmb*> (buf->r[R_CMB].p + pl.o_cmb);
+    uint8_t* extra = buf->r[R_XMB].p + pl.o_xmb;
+    uint32_t nx = 0;
+    lh264_mb_rec none;
+    memset (&none, 0, sizeof (none));                                            // (LH264_MB_NONE: whatever the scratch record held is dropped)
+    for (size_t i = 0; i < n; i++) {
+      const lh264_mb_rec& m = pic.mbs[i].mb_type == LH264_MB_NONE ? none : pic.mbs[i];
+      lh264_cmb c;
+      lh264_compact_mb (m, c, extra, &nx);
+      stream16 (out + i, &c, sizeof (c));
+      if (verify) { lh264_mb_rec back; lh264_expand_mb (c, extra, back); if (memcmp (&back, &m, sizeof (m))) { fprintf (stderr, "compact MB record %zu does not expand to its source (type %d)\n", i, m.mb_type); abort(); } }
+    }
+    pl.n_xmb = (int)nx;
+    buf->r[R_XMB].used = pl.o_xmb + (size_t)nx * 16;
     if (arena) arena->picture_done();
     buf->placed.push_back (pl);
     placed_now++;
@@ -163,12 +210,23 @@ class StageSink : public PictureSink {
   int submit_model (const lh264_model_picture& pic, const DecodedPictureInfo&) override {
     if (cur_ < 0 || cur_ >= (int)buf->placed.size()) return 0;
     Placed& pl = buf->placed[cur_];
-    const size_t b_sl = (size_t)pic.n_slices * sizeof (lh264_model_slice), b_rc = (size_t)pic.n_recs * sizeof (lh264_model_mb);
-    pl.o_msl = buf->mslices.take (b_sl);
-    if (inside (buf->mrecs, pic.recs)) { pl.o_mr = (size_t) ((const uint8_t*)pic.recs - buf->mrecs.p); buf->mrecs.used = pl.o_mr + b_rc; }
-    else { pl.o_mr = buf->mrecs.take (b_rc); if (pl.o_mr != (size_t) -1) memcpy (buf->mrecs.p + pl.o_mr, pic.recs, b_rc); }
-    if (pl.o_msl == (size_t) -1 || pl.o_mr == (size_t) -1) { buf->failed = true; return LH264_E_NOMEM; }
-    memcpy (buf->mslices.p + pl.o_msl, pic.slices, b_sl);
+    const size_t b_sl = (size_t)pic.n_slices * sizeof (lh264_model_slice), n = (size_t)pic.n_recs;
+    pl.o_msl = buf->r[R_MSLICES].take (b_sl);
+    pl.o_cmm = buf->r[R_CMM].take (n * sizeof (lh264_cmm), n * sizeof (lh264_cmm) * buf->expect * 9 / 8);
+    pl.o_xmm = buf->r[R_XMM].take (n * 64 + 16);                                  // worst case: four units per record; trimmed below
+    if (pl.o_msl == (size_t) -1 || pl.o_cmm == (size_t) -1 || pl.o_xmm == (size_t) -1) { buf->failed = true; return LH264_E_NOMEM; }
+    memcpy (buf->r[R_MSLICES].p + pl.o_msl, pic.slices, b_sl);
+    lh264_cmm* out = reinterpret_cast<lh264_cmm*> (buf->r[R_CMM].p + pl.o_cmm);
+    uint8_t* extra = buf->r[R_XMM].p + pl.o_xmm;
+    uint32_t nx = 0;
+    for (size_t i = 0; i < n; i++) {
+      lh264_cmm c;
+      lh264_compact_mm (pic.recs[i], c, extra, &nx);
+      stream16 (out + i, &c, sizeof (c));
+      if (verify) { lh264_model_mb back; lh264_expand_mm (c, extra, back); if (memcmp (&back, &pic.recs[i], sizeof (back))) { fprintf (stderr, "compact model record %zu does not expand to its source (type code %d)\n", i, pic.recs[i].type_code); abort(); } }
+    }
+    pl.n_xmm = (int)nx;
+    buf->r[R_XMM].used = pl.o_xmm + (size_t)nx * 16;
     pl.n_mslices = pic.n_slices; pl.n_mrecs = pic.n_recs;
     return 0;
   }
@@ -178,6 +236,21 @@ class StageSink : public PictureSink {
   static bool inside (const PinRegion& r, const void* p) { return r.p && (const uint8_t*)p >= r.p && (const uint8_t*)p < r.p + r.cap; }
   int cur_ = -1;
 };
+
+// offset and size of a placed picture's part in region k of its step buffer (0 bytes: the picture has no such part)
+inline size_t part_off (const Placed& pl, int k) {
+  switch (k) { case R_CMB: return pl.o_cmb; case R_XMB: return pl.o_xmb; case R_COEFS: return pl.o_co; case R_CMM: return pl.o_cmm; case R_XMM: return pl.o_xmm;
+               case R_SLICES: return pl.o_sl; default: return pl.o_msl; }
+}
+inline size_t part_size (const Placed& pl, int k) {
+  switch (k) { case R_CMB: return (size_t)pl.n_mbs * sizeof (lh264_cmb); case R_XMB: return (size_t)pl.n_xmb * 16; case R_COEFS: return (size_t)pl.n_blocks * 32;
+               case R_CMM: return (size_t)pl.n_mrecs * sizeof (lh264_cmm); case R_XMM: return (size_t)pl.n_xmm * 16;
+               case R_SLICES: return (size_t)pl.n_slices * sizeof (lh264_slice_rec); default: return (size_t)pl.n_mslices * sizeof (lh264_model_slice); }
+}
+inline void set_part_off (Placed& pl, int k, size_t o) {
+  switch (k) { case R_CMB: pl.o_cmb = o; break; case R_XMB: pl.o_xmb = o; break; case R_COEFS: pl.o_co = o; break; case R_CMM: pl.o_cmm = o; break;
+               case R_XMM: pl.o_xmm = o; break; case R_SLICES: pl.o_sl = o; break; default: pl.o_msl = o; break; }
+}
 
 struct Stream {
   const uint8_t* data = nullptr;        // Annex-B bytes, followed by the 00 00 00 01 sentinel
@@ -192,7 +265,7 @@ struct Stream {
   int last_error = 0;
   // a damaged stream can complete more than one picture in one unit; a step takes one picture per stream, the others wait in
   // a private step buffer (heap, not pinned: the rare path) and are moved into the staging of the following steps
-  struct Spill { Placed pl; std::vector<uint8_t> sl, mb, co, msl, mr; };
+  struct Spill { Placed pl; std::vector<uint8_t> part[R_COUNT]; };
   std::vector<Spill> spill;
   // submit-thread side
   int gpu_stream = -1, model_stream = -1, model_mbs = 0, geo_seen = 0;
@@ -274,13 +347,12 @@ void advance (Stream& s, StepBuf* buf, StepArena* arena, bool want_pip, long max
   if (!s.spill.empty()) {                // a picture that was completed together with an earlier one
     Stream::Spill& sp = s.spill.front();
     Placed pl = sp.pl;
-    pl.o_sl = buf->slices.take (sp.sl.size()); pl.o_mb = buf->mbs.take (sp.mb.size()); pl.o_co = buf->coefs.take (sp.co.size());
-    pl.o_msl = buf->mslices.take (sp.msl.size()); pl.o_mr = buf->mrecs.take (sp.mr.size());
-    if (pl.o_sl == (size_t) -1 || pl.o_mb == (size_t) -1 || pl.o_co == (size_t) -1 || pl.o_msl == (size_t) -1 || pl.o_mr == (size_t) -1) { buf->failed = true; return; }
-    memcpy (buf->slices.p + pl.o_sl, sp.sl.data(), sp.sl.size()); memcpy (buf->mbs.p + pl.o_mb, sp.mb.data(), sp.mb.size());
-    if (!sp.co.empty()) memcpy (buf->coefs.p + pl.o_co, sp.co.data(), sp.co.size());
-    if (!sp.msl.empty()) memcpy (buf->mslices.p + pl.o_msl, sp.msl.data(), sp.msl.size());
-    if (!sp.mr.empty()) memcpy (buf->mrecs.p + pl.o_mr, sp.mr.data(), sp.mr.size());
+    for (int k = 0; k < R_COUNT; k++) {
+      const size_t o = buf->r[k].take (sp.part[k].size());
+      if (o == (size_t) -1) { buf->failed = true; return; }
+      if (!sp.part[k].empty()) memcpy (buf->r[k].p + o, sp.part[k].data(), sp.part[k].size());
+      set_part_off (pl, k, o);
+    }
     buf->placed.push_back (pl);
     s.spill.erase (s.spill.begin());
     s.parsed++;
@@ -289,7 +361,8 @@ void advance (Stream& s, StepBuf* buf, StepArena* arena, bool want_pip, long max
   arena->bind (buf);
   if (!s.dec->set_arena (arena)) { buf->failed = true; return; }   // (a picture left open by the previous step moves into this buffer)
   const size_t first = buf->placed.size();
-  const size_t m0[5] = {buf->slices.used, buf->mbs.used, buf->coefs.used, buf->mslices.used, buf->mrecs.used};
+  size_t m0[R_COUNT];
+  for (int k = 0; k < R_COUNT; k++) m0[k] = buf->r[k].used;
   while (s.sink.placed_now == 0 && !s.flushed) {
     if (s.pos >= s.size) {
       if (s.loops_left > 0) { s.loops_left--; s.pos = 0; continue; }
@@ -313,21 +386,12 @@ void advance (Stream& s, StepBuf* buf, StepArena* arena, bool want_pip, long max
       const Placed& pl = buf->placed[i];
       Stream::Spill sp;
       sp.pl = pl;
-      sp.sl.assign (buf->slices.p + pl.o_sl, buf->slices.p + pl.o_sl + (size_t)pl.n_slices * sizeof (lh264_slice_rec));
-      sp.mb.assign (buf->mbs.p + pl.o_mb, buf->mbs.p + pl.o_mb + (size_t)pl.n_mbs * sizeof (lh264_mb_rec));
-      sp.co.assign (buf->coefs.p + pl.o_co, buf->coefs.p + pl.o_co + (size_t)pl.n_blocks * 32);
-      if (pl.n_mrecs) {
-        sp.msl.assign (buf->mslices.p + pl.o_msl, buf->mslices.p + pl.o_msl + (size_t)pl.n_mslices * sizeof (lh264_model_slice));
-        sp.mr.assign (buf->mrecs.p + pl.o_mr, buf->mrecs.p + pl.o_mr + (size_t)pl.n_mrecs * sizeof (lh264_model_mb));
-      }
+      for (int k = 0; k < R_COUNT; k++) { const uint8_t* q = buf->r[k].p + part_off (pl, k); sp.part[k].assign (q, q + part_size (pl, k)); }
       s.spill.push_back (std::move (sp));
     }
     // give the bytes back: everything behind the first picture of this call
     const Placed& f = buf->placed[first];
-    buf->slices.used = f.o_sl + (size_t)f.n_slices * sizeof (lh264_slice_rec); buf->mbs.used = f.o_mb + (size_t)f.n_mbs * sizeof (lh264_mb_rec);
-    buf->coefs.used = f.o_co + (size_t)f.n_blocks * 32;
-    buf->mslices.used = f.n_mrecs ? f.o_msl + (size_t)f.n_mslices * sizeof (lh264_model_slice) : m0[3];
-    buf->mrecs.used = f.n_mrecs ? f.o_mr + (size_t)f.n_mrecs * sizeof (lh264_model_mb) : m0[4];
+    for (int k = 0; k < R_COUNT; k++) buf->r[k].used = part_size (f, k) ? part_off (f, k) + part_size (f, k) : m0[k];
     buf->placed.resize (first + 1);
   }
   // a picture still in progress (damaged streams: completed only by the arrival of the next one) must not stay in this buffer
@@ -377,8 +441,7 @@ void pipeline_main (Pipeline* P) {
   lh264_ctx* ctx = P->ctx;
   const int D = (int)P->workers[0]->bufs.size();
   std::vector<uint8_t> out_host;
-  std::vector<lh264_picture_desc> descs;
-  std::vector<lh264_model_picture> mdescs;
+  std::vector<lh264_compact_picture> cdescs;
   std::vector<int> rd_streams, rd_slots;
   std::vector<Placed> step;
   std::vector<const StepBuf*> step_buf;
@@ -473,30 +536,32 @@ void pipeline_main (Pipeline* P) {
       P->t_open += now() - to0;
     }
     // ---- descriptors ----
-    descs.clear(); mdescs.clear(); rd_streams.clear(); rd_slots.clear();
+    cdescs.clear(); rd_streams.clear(); rd_slots.clear();
     {
       int out_w = 0, out_h = 0, crop_x = 0, crop_y = 0;
-      bool same_geometry = true;
+      bool same_geometry = true, any_model = false;
       for (size_t pi = 0; pi < step.size(); pi++) {
         const Placed& pl = step[pi];
         const StepBuf* b = step_buf[pi];
         Stream& s = *rt->streams[pl.stream];
-        lh264_picture_desc d;
-        d.stream = s.gpu_stream; d.cur_slot = pl.info.slot; d.n_slices = pl.n_slices; d.n_coef_blocks = pl.n_blocks;
-        d.slices = reinterpret_cast<const lh264_slice_rec*> (b->slices.p + pl.o_sl);
-        d.mbs = reinterpret_cast<const lh264_mb_rec*> (b->mbs.p + pl.o_mb);
-        d.coefs = reinterpret_cast<const int16_t*> (b->coefs.p + pl.o_co);
-        if (want_yuv) { descs.push_back (d); P->h2d += (size_t)pl.n_slices * sizeof (lh264_slice_rec) + (size_t)pl.n_mbs * sizeof (lh264_mb_rec); }
-        P->h2d += (size_t)pl.n_blocks * 32;
+        lh264_compact_picture d;
+        memset (&d, 0, sizeof (d));
+        d.stream = s.gpu_stream; d.model_stream = s.model_stream; d.cur_slot = pl.info.slot; d.mb_w = pl.mb_w; d.mb_h = pl.mb_h;
+        d.n_slices = pl.n_slices; d.n_model_slices = pl.n_mslices; d.n_recs = want_pip ? pl.n_mrecs : 0; d.n_coef_blocks = pl.n_blocks;
+        d.n_mb_extra = pl.n_xmb; d.n_mm_extra = pl.n_xmm;
+        d.slices = reinterpret_cast<const lh264_slice_rec*> (b->r[R_SLICES].p + pl.o_sl);
+        d.model_slices = reinterpret_cast<const lh264_model_slice*> (b->r[R_MSLICES].p + pl.o_msl);
+        d.cmbs = reinterpret_cast<const lh264_cmb*> (b->r[R_CMB].p + pl.o_cmb);
+        d.cmms = reinterpret_cast<const lh264_cmm*> (b->r[R_CMM].p + pl.o_cmm);
+        d.mb_extra = b->r[R_XMB].p + pl.o_xmb; d.mm_extra = b->r[R_XMM].p + pl.o_xmm;
+        d.coefs = reinterpret_cast<const int16_t*> (b->r[R_COEFS].p + pl.o_co);
+        cdescs.push_back (d);
+        if (want_yuv) P->h2d += part_size (pl, R_SLICES) + part_size (pl, R_CMB) + part_size (pl, R_XMB);
+        P->h2d += part_size (pl, R_COEFS);
         if (want_pip && pl.n_mrecs > 0) {
           if (pl.mb_w * pl.mb_h > s.model_mbs) { rt->fail ("a stream's picture grew beyond level 5.2"); P->rc = LH264_E_UNSUPPORTED; goto done; }
-          lh264_model_picture m;
-          m.model_stream = s.model_stream; m.mb_w = pl.mb_w; m.mb_h = pl.mb_h; m.n_slices = pl.n_mslices; m.n_recs = pl.n_mrecs; m.n_coef_blocks = pl.n_blocks;
-          m.slices = reinterpret_cast<const lh264_model_slice*> (b->mslices.p + pl.o_msl);
-          m.recs = reinterpret_cast<const lh264_model_mb*> (b->mrecs.p + pl.o_mr);
-          m.coefs = d.coefs;
-          mdescs.push_back (m);
-          P->h2d += (size_t)pl.n_mslices * sizeof (lh264_model_slice) + (size_t)pl.n_mrecs * sizeof (lh264_model_mb);
+          any_model = true;
+          P->h2d += part_size (pl, R_MSLICES) + part_size (pl, R_CMM) + part_size (pl, R_XMM);
         }
         rd_streams.push_back (s.gpu_stream); rd_slots.push_back (pl.info.slot);
         if (out_w == 0) { out_w = pl.info.width; out_h = pl.info.height; crop_x = pl.info.crop_x; crop_y = pl.info.crop_y; }
@@ -504,9 +569,8 @@ void pipeline_main (Pipeline* P) {
       }
       // ---- the device ----
       static const bool parse_only = getenv ("LH264_RT_PARSE_ONLY") != nullptr;   // diagnostic: how fast the parse threads alone are
-      if (parse_only) { descs.clear(); mdescs.clear(); }
-      if (!descs.empty() && lh264_recon_submit (ctx, descs.data(), (int)descs.size()) != LH264_OK) FAIL ("lh264_recon_submit");
-      if (!mdescs.empty() && lh264_model_submit (ctx, mdescs.data(), (int)mdescs.size()) != LH264_OK) FAIL ("lh264_model_submit");
+      const int sflags = (want_yuv ? LH264_COMPACT_RECON : 0) | (any_model ? LH264_COMPACT_MODEL : 0);
+      if (!parse_only && sflags && lh264_submit_compact (ctx, cdescs.data(), (int)cdescs.size(), sflags) != LH264_OK) FAIL ("lh264_submit_compact");
       if (want_yuv && !parse_only) {
         if (same_geometry) {
           const size_t per = (size_t)out_w * out_h + 2 * (size_t) ((out_w + 1) / 2) * ((out_h + 1) / 2);
@@ -646,6 +710,8 @@ int lh264_rt_add_stream (lh264_rt* rt, const uint8_t* annexb, size_t len, int tr
   s->sink.stream = (int)rt->streams.size();
   s->dec.reset (new Decoder (&s->sink));
   s->dec->enable_model (rt->cfg.want_pip != 0);
+  s->dec->set_streaming_stores (true, false);         // coefficient pools go to pinned staging, model records to cache-resident scratch
+  s->sink.verify = getenv ("LH264_RT_VERIFY_COMPACT") != nullptr;
   rt->streams.push_back (std::move (s));
   return (int)rt->streams.size() - 1;
 }
@@ -676,7 +742,7 @@ int lh264_rt_run (lh264_rt* rt, lh264_rt_picture_fn fn, void* user) {
       for (int i = first + w; i < last; i += tw) W->streams.push_back (i);
       for (StepBuf& b : W->bufs) {
         b.expect = W->streams.size();
-        b.mbs.alloc_s = b.coefs.alloc_s = b.mrecs.alloc_s = b.slices.alloc_s = b.mslices.alloc_s = &W->alloc;
+        for (PinRegion& x : b.r) x.alloc_s = &W->alloc;
       }
       P->workers.push_back (std::move (W));
     }

@@ -8,6 +8,7 @@
 #include "../../losslessh264_b200/csrc/model_kernels.cuh"
 using namespace lh264m;
 #include "model_emu_core.h"
+#include "../../losslessh264_b200/csrc/compact_records.h"
 #include <memory>
 #include <mutex>
 
@@ -139,6 +140,38 @@ long long lh264_model_read (lh264_ctx* c, int m, int tag, uint8_t* dst, size_t o
   if (!c->models[m]->tag_bytes (tag, b)) return fail (LH264_E_INVALID, "broken page list");
   if (dst && offset < b.size()) memcpy (dst, b.data() + offset, std::min (cap, b.size() - offset));
   return (long long)b.size();
+}
+
+// = lh264_submit_compact (lh264_shim.cu / model_host.inl): the records are expanded with the very functions k_expand_mb / k_expand_mm
+// run (csrc/compact_records.h), then take the same path as full records
+int lh264_submit_compact (lh264_ctx* c, const lh264_compact_picture* pics, int n, int flags) {
+  std::vector<std::vector<lh264_mb_rec> > mbs (n);
+  std::vector<std::vector<lh264_model_mb> > recs (n);
+  std::vector<lh264_picture_desc> rd;
+  std::vector<lh264_model_picture> md;
+  for (int i = 0; i < n; i++) {
+    const lh264_compact_picture& p = pics[i];
+    if (flags & LH264_COMPACT_RECON) {
+      mbs[i].resize ((size_t)p.mb_w * p.mb_h);
+      for (size_t k = 0; k < mbs[i].size(); k++) lh264_expand_mb (p.cmbs[k], p.mb_extra, mbs[i][k]);
+      lh264_picture_desc d;
+      d.stream = p.stream; d.cur_slot = p.cur_slot; d.n_slices = p.n_slices; d.n_coef_blocks = p.n_coef_blocks;
+      d.slices = p.slices; d.mbs = mbs[i].data(); d.coefs = p.coefs;
+      rd.push_back (d);
+    }
+    if ((flags & LH264_COMPACT_MODEL) && p.n_recs > 0) {
+      recs[i].resize ((size_t)p.n_recs);
+      for (size_t k = 0; k < recs[i].size(); k++) lh264_expand_mm (p.cmms[k], p.mm_extra, recs[i][k]);
+      lh264_model_picture q;
+      q.model_stream = p.model_stream; q.mb_w = p.mb_w; q.mb_h = p.mb_h; q.n_slices = p.n_model_slices; q.n_recs = p.n_recs; q.n_coef_blocks = p.n_coef_blocks;
+      q.slices = p.model_slices; q.recs = recs[i].data(); q.coefs = p.coefs;
+      md.push_back (q);
+    }
+  }
+  int rc = LH264_OK;
+  if (!rd.empty()) rc = lh264_recon_submit (c, rd.data(), (int)rd.size());
+  if (rc == LH264_OK && !md.empty()) rc = lh264_model_submit (c, md.data(), (int)md.size());
+  return rc;
 }
 
 } // extern "C"

@@ -32,8 +32,9 @@ def batch_emu(tmp_path_factory):
 def run(exe, names, copies, threads, tmp_path, extra=()):
     d = os.path.join(str(tmp_path), "pip")
     os.makedirs(d, exist_ok=True)
+    # LH264_RT_VERIFY_COMPACT: every compact record the runtime hands over is expanded again on the spot and compared with its source
     r = subprocess.run([exe, "--copies", str(copies), "--threads", str(threads), "--pip-dir", d, *extra] + [os.path.join(STREAM_DIR, n) for n in names],
-                       capture_output=True, text=True, timeout=900)
+                       capture_output=True, text=True, timeout=900, env=dict(os.environ, LH264_RT_VERIFY_COMPACT="1"))
     assert r.returncode == 0, r.stdout[-400:] + r.stderr[-400:]
     lines = r.stdout.strip().splitlines()
     per = {}
