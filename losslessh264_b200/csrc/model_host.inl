@@ -27,6 +27,7 @@ struct MBatch {                    // one batch of model pictures in HBM
   PinBuf<uint32_t> h_total; PinBuf<unsigned long long> h_base;
   DevBuf<BatchCtl> ctl; PinBuf<BatchCtl> h_ctl;
   bool pending = false;            // launched, totals not yet read back (model_settle)
+  bool resident = false;           // staged once by lh264_model_batch_upload and replayed
   cudaEvent_t done = nullptr;      // recorded after the batch's last kernel
   cudaEvent_t staged = nullptr;    // recorded after the batch's host-to-device copies
   std::vector<int> stream_of;
@@ -67,8 +68,14 @@ struct ModelCtx {
   // reconstruction kernel (two 256-thread blocks per SM: the whole register file) do not fit on an SM together: left to the
   // block scheduler they starve each other (measured, profiles/r2_summary.md: 58 ms per step together, 52 ms one after the
   // other).  LH264_CODE_EXCLUSIVE=0 lets them overlap again.
+  // When the steps come from resident batches (nothing but the GPU sets the pace) the coder therefore runs alone: it waits for the
+  // kernels submitted so far and the kernels of the following steps wait for it.  When the steps are fed from host buffers the
+  // GPU has slack and a 330 ms bubble per window would only stall the host pipeline: there they share the GPU.
+  // LH264_CODE_EXCLUSIVE=0 / 1 (reconstruction waits) / 2 (reconstruction and generation wait) overrides.
+  int exclusive_env = -1;
+  bool last_resident = false;                      // the step submitted last came from a resident batch
   bool exclusive = true;
-  bool exclusive_gen = true;                       // ... and neither do the generation kernels of the following steps (LH264_CODE_EXCLUSIVE=1: they may)
+  bool exclusive_gen = true;
   bool partitioned = false;                        // code_stream belongs to an SM partition (model_partition_stream)
   int pend_steps = 0;
   std::vector<std::vector<int> > pend_streams;     // model stream of every job of a pending step
@@ -153,21 +160,20 @@ static ModelCtx* model_ctx (lh264_ctx* c) {
     // LH264_CODER_SMS=n: the coder gets a partition of n SMs and runs beside the other kernels (0 / unset: no partition)
     if (const char* e = getenv ("LH264_CODER_SMS")) {
       const int n = atoi (e);
-      if (n > 0) { m->code_stream = model_partition_stream (c->device, n); if (m->code_stream) { m->partitioned = true; m->exclusive = false; } }
+      if (n > 0) { m->code_stream = model_partition_stream (c->device, n); if (m->code_stream) m->partitioned = true; }
     }
     if (!m->code_stream) cudaStreamCreateWithFlags (&m->code_stream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags (&m->gen_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags (&m->recon_idle, cudaEventDisableTiming);
     for (int k = 0; k < 2; k++) { cudaEventCreateWithFlags (&m->index_copied[k], cudaEventDisableTiming); cudaEventCreateWithFlags (&m->coder_done[k], cudaEventDisableTiming); }
-    if (const char* e = getenv ("LH264_CODE_EXCLUSIVE")) { m->exclusive = atoi (e) != 0; m->exclusive_gen = atoi (e) >= 2; }
-    if (m->partitioned && !getenv ("LH264_CODE_EXCLUSIVE")) m->exclusive = false;
+    if (const char* e = getenv ("LH264_CODE_EXCLUSIVE")) m->exclusive_env = atoi (e);
     if (const char* e = getenv ("LH264_CODE_STEPS")) m->code_steps = std::max (1, std::min (atoi (e), 64));
     {
       size_t free_b = 0, total_b = 0;
       cudaMemGetInfo (&free_b, &total_b);
-      size_t limit_mb = 24576;                       // LH264_DEC_POOL_MB: memory the decision pool may take for deferral
+      size_t limit_mb = 65536;                       // LH264_DEC_POOL_MB: memory the decision pool (both halves) may take for deferral
       if (const char* e = getenv ("LH264_DEC_POOL_MB")) limit_mb = (size_t)std::max (1, atoi (e));
-      m->dec_cap_limit = std::min (limit_mb << 20, free_b / 4) / sizeof (uint32_t) / 2;     // per half
+      m->dec_cap_limit = std::min (limit_mb << 20, free_b / 3) / sizeof (uint32_t) / 2;     // per half
     }
     m->pend_streams.resize (m->code_steps);
     c->model = m;
@@ -373,6 +379,10 @@ static int model_flush_coder (lh264_ctx* c, ModelCtx* m) {
   const int T = m->pend_steps;
   if (T == 0) return LH264_OK;
   const int h = m->cur;
+  {
+    const int mode = m->partitioned ? 0 : (m->exclusive_env >= 0 ? m->exclusive_env : (m->last_resident ? 2 : 0));
+    m->exclusive = mode >= 1; m->exclusive_gen = mode >= 2;
+  }
   m->slot_of.assign (m->streams.size(), -1);
   int nb = 0;
   for (int j = 0; j < T; j++) for (int s : m->pend_streams[j]) if (m->slot_of[s] < 0) m->slot_of[s] = nb++;
@@ -558,6 +568,7 @@ static int model_run (lh264_ctx* c, ModelCtx* m, MBatch& b) {
   if (!m->dec[m->cur].p && (rc = model_grow_pool (c, m, std::max<unsigned long long> ((unsigned long long)b.total_recs * 96 + 1024, m->last_step_total)))) return rc;   // first guess; model_settle grows it when needed
   // a step about as large as the last one would not fit behind the pending ones: code those first (saves a skip + re-run)
   if (m->pend_steps > 0 && m->est_pool_used + m->last_step_total + m->last_step_total / 2 + 64 > m->dec[m->cur].cap && (rc = model_flush_coder (c, m))) return rc;
+  m->last_resident = b.resident;
   if ((rc = model_launch (c, m, b, true, c->timing))) return rc;
   b.pending = true; m->inflight.push_back (&b);
   if (c->timing) {
@@ -626,6 +637,7 @@ int lh264_model_batch_upload (lh264_ctx* c, const lh264_model_picture* pics, int
   if (!rb) return fail (LH264_E_NOMEM, "out of host memory");
   int rc = model_stage (c, m, rb->b, pics, n, false);
   if (rc) { rb->b.release(); delete rb; return rc; }
+  rb->b.resident = true;
   CK (cudaStreamSynchronize (m->stream));
   *out = rb;
   return LH264_OK;

@@ -169,6 +169,9 @@ struct Decoder::Impl {
   // concealment modes h264dec selects, decoder_core.cpp:56-217): pictures of a stream whose leading IDR was lost are parsed,
   // modelled and reconstructed, but marked `output = false` for the sink and not handed out
   bool frozen = true;
+  bool frozen_incomplete = false;        // ... the part of `frozen` that every error concealment mode keeps: behind a picture with missing macroblocks
+  uint32_t slots_touched = 0;            // picture slots that have been reconstructed into since the stream's storage was made
+  bool freeze_output = true;             // Decoder::set_freeze_output
   unsigned long long ts = 0, ts_first = 0;
   bool ref_lost = false, ref_lost_first = false;   // a reference picture of the current picture was never received (frame_num gap / no reference at all)
   RecBuf<lh264_mb_rec, RecordArena::MBS> mbs;      // n_mbs records while a picture is open
@@ -389,6 +392,7 @@ struct Decoder::Impl {
     mb_w = s.mb_w; mb_h = s.mb_h; n_mbs = mb_w * mb_h;
     n_slots = std::max (3, s.max_num_ref_frames + 2);
     refs.clear(); max_long_idx = -1;
+    slots_touched = 0;                     // (new picture storage: configure() below)
     mbs.clear();
     nzc.assign ((size_t)n_mbs * 24, 0);
     ipm.assign ((size_t)n_mbs * 16, 2);
@@ -440,6 +444,7 @@ struct Decoder::Impl {
       }
     }
     cur_slot = free_slot();
+    slots_touched |= 1u << (cur_slot & 31);
     slices.clear(); coefs.clear(); mrecs.clear(); mslices.clear(); mbs.clear();
     if (!mbs.grow (n_mbs)) { open = false; alloc_failed = true; return; }
     coefs.reserve ((size_t)n_mbs * 32);               // two coefficient blocks per macroblock to start with
@@ -465,9 +470,11 @@ struct Decoder::Impl {
     int rc = 0;
     // ... and freezes it again at a picture with missing macroblocks (no concealment here: the reference's freeze modes do not
     // hand concealed pictures out either) until the next complete IDR picture
-    if (!info.complete) frozen = true;
-    else if (sh0.idr) frozen = false;
-    info.output = !frozen;
+    if (!info.complete) frozen = frozen_incomplete = true;
+    else if (sh0.idr) frozen = frozen_incomplete = false;
+    // the FREEZE modes also hold back what precedes the stream's first IDR picture; the other modes hand those pictures out
+    // (predicted from the grey stand-in reference)
+    info.output = freeze_output ? !frozen : !frozen_incomplete;
     if (debug_trace()) fprintf (stderr, "picture: %dx%d idr %d frame_num %d decoded %d of %d slices %zu\n", mb_w, mb_h, (int)sh0.idr, sh0.frame_num, decoded, n_mbs, slices.size());
     if (!slices.empty()) rc = sink->submit (d, info);
     if (want_model && !mslices.empty()) {
@@ -1297,6 +1304,7 @@ void Decoder::enable_rewrite_check (bool on) { d_->check_rewrite = on; if (on) d
 
 int Decoder::flush() { return d_->finish_picture (this); }
 bool Decoder::picture_open() const { return d_->open; }
+void Decoder::set_freeze_output (bool on) { d_->freeze_output = on; }
 void Decoder::set_streaming_stores (bool coefs, bool model_recs) { d_->stream_coefs = coefs; d_->stream_mrecs = model_recs; }
 bool Decoder::set_arena (RecordArena* a) {
   const bool ok = d_->mbs.set_arena (a) & d_->coefs.set_arena (a) & d_->mrecs.set_arena (a);
@@ -1351,6 +1359,20 @@ int Decoder::decode (const uint8_t* data, size_t len, unsigned long long timesta
       sr.alpha_c0_offset = (int8_t)sh.alpha_c0_offset; sr.beta_offset = (int8_t)sh.beta_offset;
       sr.num_ref_idx_l0 = (uint8_t)sh.num_ref_idx_l0;
       if (sh.slice_type == SLICE_P) {
+        // No reference picture at all (the stream's IDR picture was lost): the reference puts a fresh grey picture with frame_num 0
+        // into its short-term list and predicts from it (WelsInitRefList, manage_dec_ref.cpp:112-150; the previous picture is
+        // copied instead only when there is one, which a stream without any reference does not have).  The slots of a stream
+        // start out grey (pic_queue.cpp:96); one that has been written since is filled again by the sink.
+        if (D.refs.empty()) {
+          int gs = -1;
+          for (int s2 = 0; s2 < D.n_slots && gs < 0; s2++) if (s2 != D.cur_slot) gs = s2;
+          if (gs >= 0) {
+            RefPic r;
+            r.slot = gs; r.frame_num = 0;
+            D.refs.push_back (r);
+            if ((D.slots_touched >> gs) & 1u) D.sink->fill_slot (gs, 128);
+          }
+        }
         D.build_list0();
         if (debug_trace()) { fprintf(stderr, "slice fn=%d nref=%d refs=%zu mods:", sh.frame_num, sh.num_ref_idx_l0, D.refs.size()); for (auto& mm : sh.mods) fprintf(stderr, " (%d,%u)", mm.op, mm.val); fprintf(stderr, " | refs:"); for (auto& r : D.refs) fprintf(stderr, " [slot %d fn %d long %d idx %d]", r.slot, r.frame_num, r.is_long, r.long_idx); fprintf(stderr, " | mmco:"); for (auto& mm : sh.mmcos) fprintf(stderr, " (%d,%u,%u)", mm.op, mm.a, mm.b); fprintf(stderr, "\n"); }
         const int fallback = D.list0[0] ? D.list0[0]->slot : (D.refs.empty() ? 0 : D.refs.back().slot);

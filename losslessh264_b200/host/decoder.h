@@ -69,6 +69,8 @@ class PictureSink {
   virtual int submit (const lh264_picture_desc& pic, const DecodedPictureInfo& info) = 0;
   // host-side error concealment: copy slot src -> dst (whole picture)
   virtual int copy_slot (int dst, int src) { (void)dst; (void)src; return 0; }
+  // fill every sample of a slot with `value` (the grey stand-in for a reference picture that was never received)
+  virtual int fill_slot (int slot, int value) { (void)slot; (void)value; return 0; }
   // the picture's recompression-model records (only when Decoder::enable_model(true)); pointers valid until return
   virtual int submit_model (const lh264_model_picture& pic, const DecodedPictureInfo& info) { (void)pic; (void)info; return 0; }
 };
@@ -102,6 +104,10 @@ class Decoder {
   // non-temporal stores for the coefficient pools / the model records (worth it when they go to memory the parser never reads
   // back, e.g. pinned staging; not when the destination is cache-resident scratch).  Default: both on.
   void set_streaming_stores (bool coefs, bool model_recs);
+  // The reference's FREEZE error-concealment modes (ERROR_CON_*_FREEZE_RES_CHANGE, what h264dec selects) hold the output back
+  // from a lost IDR picture / a picture with missing macroblocks until the next complete IDR picture; the other modes hand every
+  // picture out.  Default: freeze (the h264dec behaviour the YUV goldens pin).
+  void set_freeze_output (bool on);
   // the last slice NAL handled by the last decode() call (for the `.pip` default stream, pip_container.h); rbsp is valid
   // until the next decode() call
   struct LastSlice { bool decoded = false, cabac = false; const uint8_t* rbsp = nullptr; size_t header_bits = 0; bool idr = false; int idr_pic_id = 0, frame_num = 0; };

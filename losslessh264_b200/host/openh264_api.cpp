@@ -6,6 +6,8 @@
 #include <string.h>
 #include <stdlib.h>
 #include <deque>
+#include <map>
+#include <vector>
 #include <new>
 #include "../../include/lh264_codec_api.h"
 #include "decoder.h"
@@ -32,6 +34,7 @@ class CLh264Decoder : public ISVCDecoder {
     if (!sink_ || !sink_->ctx()) { delete sink_; sink_ = nullptr; return cmInitParaError; }   // no device: fail loudly
     dec_ = new (std::nothrow) Decoder (sink_);
     if (!dec_) return cmMallocMemeError;
+    apply_ec();
     memset (&stat_, 0, sizeof (stat_));
     return cmResultSuccess;
   }
@@ -40,7 +43,7 @@ class CLh264Decoder : public ISVCDecoder {
     delete dec_; dec_ = nullptr;
     delete sink_; sink_ = nullptr;
     if (out_) { lh264_host_free (out_); out_ = nullptr; out_cap_ = 0; }
-    queue_.clear(); held_.clear();
+    queue_.clear(); held_.clear(); saved_.clear();
     return cmResultSuccess;
   }
 
@@ -78,7 +81,7 @@ class CLh264Decoder : public ISVCDecoder {
     switch (id) {
     case DECODER_OPTION_DATAFORMAT: return * (int*)opt == videoFormatI420 ? cmResultSuccess : cmInitParaError;
     case DECODER_OPTION_END_OF_STREAM: eos_ = eos_opt_ = * (bool*)opt; return cmResultSuccess;
-    case DECODER_OPTION_ERROR_CON_IDC: ec_idc_ = * (int*)opt; return cmResultSuccess;
+    case DECODER_OPTION_ERROR_CON_IDC: ec_idc_ = * (int*)opt; apply_ec(); return cmResultSuccess;
     case DECODER_OPTION_TRACE_LEVEL: trace_level_ = * (int*)opt; return cmResultSuccess;
     case DECODER_OPTION_TRACE_CALLBACK: case DECODER_OPTION_TRACE_CALLBACK_CONTEXT: return cmResultSuccess;
     default: return cmInitParaError;
@@ -102,6 +105,11 @@ class CLh264Decoder : public ISVCDecoder {
   }
 
  private:
+  // the two FREEZE modes hold output back behind a lost IDR / an incomplete picture (decoder_core.cpp:56-217 bFreezeOutput); the
+  // others hand every picture out
+  void apply_ec() {
+    if (dec_) dec_->set_freeze_output (ec_idc_ == ERROR_CON_SLICE_COPY_CROSS_IDR_FREEZE_RES_CHANGE || ec_idc_ == ERROR_CON_SLICE_MV_COPY_CROSS_IDR_FREEZE_RES_CHANGE);
+  }
   // One DecodeFrame2 call as an API client sees it (welsDecoderExt.cpp:431-571).  The reference decodes an access unit when the
   // first NAL of the NEXT one arrives, or at once on the flush call DecodeFrame2 (NULL, 0) — which DecodeFrameNoDelay issues after
   // every unit (:408-430).  The host decoder finishes a complete picture at its last slice, so DecodeFrame2 holds such a picture
@@ -127,7 +135,19 @@ class CLh264Decoder : public ISVCDecoder {
       if (rc == -2) state |= dsNoParamSets;
       else if (rc < 0) state |= dsBitstreamError;
       // finished by its own last slice: the reference has not decoded it yet; finished by the arrival of this unit: it has
-      for (const DecodedPictureInfo& o : dec_->finished()) { if (o.complete) held_.push_back (o); else decoded_now.push_back (o); }
+      for (const DecodedPictureInfo& o : dec_->finished()) {
+        if (!o.complete) { decoded_now.push_back (o); continue; }
+        held_.push_back (o);
+        // the picture is handed out at a LATER call, after more data has been decoded: a picture that is no reference may have lost
+        // its slot to the next one by then, so its samples are taken now (DecodeFrame2 only; the flush half of DecodeFrameNoDelay
+        // releases it before anything else is decoded)
+        if (!nodelay_ && o.output) {
+          const int cw = (o.width + 1) >> 1, ch = (o.height + 1) >> 1;
+          std::vector<unsigned char>& px = saved_[o.serial];
+          px.resize ((size_t)o.width * o.height + 2 * (size_t)cw * ch);
+          if (sink_->read (o, px.data(), o.width, px.data() + (size_t)o.width * o.height, px.data() + (size_t)o.width * o.height + (size_t)cw * ch, cw) != LH264_OK) saved_.erase (o.serial);
+        }
+      }
     } else {
       eos_ = true;                                               // :452-455: the flush call
       // a picture still missing slices is only given up at the END of the stream (the client said so with DECODER_OPTION_END_OF_STREAM),
@@ -156,7 +176,9 @@ class CLh264Decoder : public ISVCDecoder {
         if (!out_) return (DECODING_STATE) (state | dsOutOfMemory);
       }
       unsigned char* y = out_, *u = y + (size_t)o.width * o.height, *v = u + (size_t)cw * ch;
-      if (sink_->read (o, y, o.width, u, v, cw) != LH264_OK) return (DECODING_STATE) (state | dsOutOfMemory);
+      auto sv = saved_.find (o.serial);
+      if (sv != saved_.end()) { memcpy (y, sv->second.data(), need); saved_.erase (sv); }
+      else if (sink_->read (o, y, o.width, u, v, cw) != LH264_OK) return (DECODING_STATE) (state | dsOutOfMemory);
       ppDst[0] = y; ppDst[1] = u; ppDst[2] = v;
       info->iBufferStatus = 1;
       // the time stamp that came with the picture's own data: DecodeFrame2 decodes an access unit as a whole (its first unit's
@@ -230,6 +252,7 @@ class CLh264Decoder : public ISVCDecoder {
   std::string pip_path_;
   std::deque<DecodedPictureInfo> queue_;
   std::vector<DecodedPictureInfo> held_;          // complete pictures the reference would only decode at the next call
+  std::map<int, std::vector<unsigned char> > saved_;   // ... and their samples (by DecodedPictureInfo::serial)
   int tid_ = -1, ltr_frame_num_ = 0;
   bool ltr_flag_ = false, nodelay_ = false;
   unsigned char* out_ = nullptr;

@@ -36,6 +36,7 @@ class GpuSink : public PictureSink {
   ~GpuSink() override;
   int configure (int mb_w, int mb_h, int n_slots) override;
   int submit (const lh264_picture_desc& pic, const DecodedPictureInfo& info) override;
+  int fill_slot (int slot, int value) override;
   // recompression model of the picture on the GPU (lh264_model_submit); the model stream is opened on first use
   int submit_model (const lh264_model_picture& pic, const DecodedPictureInfo& info) override;
   // ends the model's tag streams; bytes of one `.pip.<tag>` side stream (empty = the tag has no file)
@@ -51,6 +52,7 @@ class GpuSink : public PictureSink {
   bool own_ctx_;
   int stream_ = -1;
   int model_ = -1, model_mbs_ = 0;
+  int w_ = 0, h_ = 0;
 };
 
 } // namespace lh264host

@@ -17,6 +17,7 @@ int GpuSink::configure (int mb_w, int mb_h, int n_slots) {
   if (!ctx_) return LH264_E_NO_DEVICE;
   if (stream_ >= 0) lh264_stream_close (ctx_, stream_);
   stream_ = lh264_stream_open (ctx_, mb_w, mb_h, n_slots);
+  w_ = mb_w * 16; h_ = mb_h * 16;
   return stream_ < 0 ? stream_ : 0;
 }
 int GpuSink::submit (const lh264_picture_desc& pic, const DecodedPictureInfo&) {
@@ -26,6 +27,11 @@ int GpuSink::submit (const lh264_picture_desc& pic, const DecodedPictureInfo&) {
   int rc = lh264_recon_submit (ctx_, &d, 1);
   if (rc) return rc;
   return lh264_sync (ctx_);          // the decoder reuses its record buffers for the next picture
+}
+int GpuSink::fill_slot (int slot, int value) {
+  if (!ctx_ || stream_ < 0 || w_ <= 0) return LH264_E_NO_DEVICE;
+  std::vector<uint8_t> y ((size_t)w_ * h_, (uint8_t)value), c ((size_t)w_ * h_ / 4, (uint8_t)value);
+  return lh264_picture_write (ctx_, stream_, slot, y.data(), w_, c.data(), c.data(), w_ / 2);
 }
 int GpuSink::submit_model (const lh264_model_picture& pic, const DecodedPictureInfo&) {
   if (!ctx_) return LH264_E_NO_DEVICE;

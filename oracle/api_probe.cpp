@@ -68,7 +68,17 @@ int main (int argc, char** argv) {
     const int st = nodelay && src ? (int)dec->DecodeFrameNoDelay (src, len, planes, &bi) : (int)dec->DecodeFrame2 (src, len, planes, &bi);
     printf ("call %d: len %d state %d status %d", call, len, st, bi.iBufferStatus);
     // (strides are the library's business - the reference hands out its padded planes - and are not printed)
-    if (bi.iBufferStatus == 1) printf (" %dx%d format %d ts %llu", bi.UsrData.sSystemBuffer.iWidth, bi.UsrData.sSystemBuffer.iHeight, bi.UsrData.sSystemBuffer.iFormat, bi.uiOutYuvTimeStamp);
+    if (bi.iBufferStatus == 1) {
+      printf (" %dx%d format %d ts %llu", bi.UsrData.sSystemBuffer.iWidth, bi.UsrData.sSystemBuffer.iHeight, bi.UsrData.sSystemBuffer.iFormat, bi.uiOutYuvTimeStamp);
+      // FNV-1a over the cropped planes: the SAMPLES an API client receives (concealed pictures included)
+      unsigned long long h = 1469598103934665603ull;
+      const int w = bi.UsrData.sSystemBuffer.iWidth, hh = bi.UsrData.sSystemBuffer.iHeight;
+      for (int p = 0; p < 3; p++) {
+        const int pw = p ? w / 2 : w, ph = p ? hh / 2 : hh, st = bi.UsrData.sSystemBuffer.iStride[p ? 1 : 0];
+        for (int r = 0; r < ph; r++) for (int x = 0; x < pw; x++) { h ^= planes[p][(size_t)r * st + x]; h *= 1099511628211ull; }
+      }
+      printf (" samples %016llx", h);
+    }
     printf ("\n");
     options ("after");
     call++;

@@ -7,15 +7,19 @@ import subprocess
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 PROBE = os.path.join(ROOT, "oracle", "_ref", "api_probe_ref")
 OUT = os.path.join(ROOT, "tests", "golden", "api_probe")
-# error-free streams under BaseDecoderTest's ERROR_CON_SLICE_COPY; the damaged ones under the mode h264dec selects (7,
-# ERROR_CON_SLICE_MV_COPY_CROSS_IDR_FREEZE_RES_CHANGE, h264dec.cpp:156-157) - sample concealment is not built
-STREAMS = [("SVA_BA1_B.264", None), ("syn_cif_cabac_4slices_ltr_6f.264", None), ("MPS_MW_A.264", None), ("MR1_BT_A.h264", None), ("test_vd_rc.264", None),
-           ("BA_MW_D_IDR_LOST.264", 7), ("Error_I_P.264", 7), ("BA_MW_D_P_LOST.264", 7)]
+# error-free streams under BaseDecoderTest's ERROR_CON_SLICE_COPY (the probe's default); the damaged ones under every error
+# concealment mode that behaves differently on them: 2 ERROR_CON_SLICE_COPY (hands out what precedes a lost IDR picture, predicted
+# from a grey stand-in reference), 4 ERROR_CON_SLICE_COPY_CROSS_IDR, 7 ERROR_CON_SLICE_MV_COPY_CROSS_IDR_FREEZE_RES_CHANGE (what
+# h264dec selects, h264dec.cpp:156-157: output frozen until the first IDR picture)
+STREAMS = [("SVA_BA1_B.264", None), ("syn_cif_cabac_4slices_ltr_6f.264", None), ("MPS_MW_A.264", None), ("MR1_BT_A.h264", None), ("test_vd_rc.264", None)]
+for _n in ("BA_MW_D_IDR_LOST.264", "BA_MW_D_P_LOST.264", "Error_I_P.264"):
+    STREAMS += [(_n, 2), (_n, 4), (_n, 7)]
 
 os.makedirs(OUT, exist_ok=True)
 for name, ec in STREAMS:
     for mode in ("nodelay", "frame2"):
         r = subprocess.run([PROBE, mode, os.path.join(ROOT, "tests", "golden", "streams", name)] + ([str(ec)] if ec is not None else []), capture_output=True, text=True)
         lines = [ln for ln in r.stdout.splitlines() if ln.startswith(("call ", "after "))]      # (the reference also prints its billing table)
-        open(os.path.join(OUT, f"{name}.{mode}.txt"), "w").write("\n".join(lines) + "\n")
-        print(name, mode, len(lines) // 2, "calls")
+        tag = f".ec{ec}" if ec is not None else ""
+        open(os.path.join(OUT, f"{name}{tag}.{mode}.txt"), "w").write("\n".join(lines) + "\n")
+        print(name, ec, mode, len(lines) // 2, "calls")

@@ -117,6 +117,18 @@ int lh264_pictures_read_packed (lh264_ctx* c, const int* streams, const int* slo
   return LH264_OK;
 }
 
+int lh264_picture_write (lh264_ctx* c, int stream, int slot, const uint8_t* sy, int stride_y, const uint8_t* su, const uint8_t* sv, int stride_c) {
+  if (stream < 0 || stream >= (int)c->streams.size() || !c->streams[stream].open) return fail (LH264_E_INVALID, "bad stream");
+  StreamEmu& s = c->streams[stream];
+  const int W = s.mb_w * 16, H = s.mb_h * 16;
+  uint8_t* y = s.pool.data() + (size_t)slot * s.stride;
+  uint8_t* u = y + (size_t)W * H;
+  uint8_t* v = u + (size_t)W * H / 4;
+  for (int r = 0; r < H; r++) memcpy (y + (size_t)r * W, sy + (size_t)r * stride_y, W);
+  for (int r = 0; r < H / 2; r++) { memcpy (u + (size_t)r * (W / 2), su + (size_t)r * stride_c, W / 2); memcpy (v + (size_t)r * (W / 2), sv + (size_t)r * stride_c, W / 2); }
+  return LH264_OK;
+}
+
 int lh264_model_open (lh264_ctx* c, int, int) { c->models.emplace_back (new ModelEmu()); return (int)c->models.size() - 1; }
 int lh264_model_close (lh264_ctx* c, int m) { if (m < 0 || m >= (int)c->models.size()) return fail (LH264_E_INVALID, "bad model stream"); c->models[m].reset(); return LH264_OK; }
 int lh264_model_submit (lh264_ctx* c, const lh264_model_picture* pics, int n) {

@@ -48,6 +48,29 @@ def test_decoder_driven_from_c(api_driver):
     assert r.returncode == 0, r.stdout + r.stderr
 
 
+@pytest.fixture(scope="module")
+def api_driver_emu(tmp_path_factory):
+    """The same driver over the API layer linked against the CPU stand-in of the C ABI (tests/emu/mock_abi.cpp: the kernel sources
+    under the CUDA emulator), so that the DecodeFrame2 procedure is checked in the build container too."""
+    d = str(tmp_path_factory.mktemp("api_emu"))
+    host, emu = os.path.join(ROOT, "losslessh264_b200", "host"), os.path.join(ROOT, "tests", "emu")
+    obj, exe = os.path.join(d, "c_vtable_check.o"), os.path.join(d, "api_driver_emu")
+    subprocess.check_call(["gcc", "-std=c99", "-c", "-o", obj, os.path.join(API, "c_vtable_check.c")])
+    src = ["openh264_api.cpp", "sinks_gpu.cpp", "sinks_file.cpp", "decoder.cpp", "h264_syntax.cpp", "cavlc.cpp", "cavlc_writer.cpp", "pip_container.cpp", "pip_expand.cpp"]
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-w", "-I" + os.path.join(ROOT, "include"), "-o", exe, os.path.join(API, "api_driver.cpp"), obj]
+                          + [os.path.join(host, f) for f in src] + [os.path.join(emu, "mock_abi.cpp"), os.path.join(emu, "cuda_emu.cpp"), "-lpthread"])
+    return exe
+
+
+# NRF_MW_E: pictures that are no reference lose their slot to the next picture - DecodeFrame2 hands them out one call late
+@pytest.mark.parametrize("name", ["NRF_MW_E.264", "SVA_BA1_B.264", "test_vd_1d.264", "MIDR_MW_D.264"])
+def test_base_decoder_test_procedure_cpu(name, api_driver_emu):
+    r = subprocess.run([api_driver_emu, "decode", os.path.join(STREAM_DIR, name)], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-400:]
+    m = re.search(r"frames (\d+) sha1 (\w+) state_or (\d+)", r.stdout)
+    assert m and m.group(2) == SHA1[name]["sha1"] and int(m.group(1)) == SHA1[name]["frames"] and int(m.group(3)) == 0, r.stdout
+
+
 # streams of the reference's DecoderOutputTest (decoder_test.cpp:90-128); error-free ones: BaseDecoderTest asserts dsErrorFree per call
 API_STREAMS = ["BA_MW_D.264", "SVA_BA1_B.264", "MR1_BT_A.h264", "CI1_FT_B.264", "BAMQ1_JVC_C.264", "NRF_MW_E.264", "MIDR_MW_D.264", "test_vd_1d.264",
                "CVPCMNL1_SVA_C.264", "test_qcif_cabac.264"]
