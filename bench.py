@@ -496,6 +496,7 @@ def main():
             hp.append(p2)
             hm.append(q2)
         Ke = n_frames
+        os.environ["LH264_DEC_POOL_MB"] = "4096"          # eight contexts side by side: each keeps its decision pool small
         gate = threading.Barrier(T + 1)
         errors = []
 
@@ -548,6 +549,7 @@ def main():
         line["e2e_records"] = {"value": round(world * T * Se * Ke / (rec_ms / 1000.0), 1), "unit": UNIT, "pictures_per_step": T * Se, "host_threads": T,
                                "path": "pre-parsed records in pinned host memory -> lh264_recon_submit + lh264_model_submit -> lh264_pictures_read_packed (parse NOT included)"}
         keep = []
+        os.environ.pop("LH264_DEC_POOL_MB", None)
 
     # ---- e2e: Annex-B bytes in host memory -> lh264_rt_run -> I420 in pinned host memory + `.pip` ---------------------
     cores = os.cpu_count() or 1

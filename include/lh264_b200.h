@@ -228,6 +228,11 @@ int  lh264_pictures_read_packed(lh264_ctx* ctx, const int* streams, const int* s
                                 int crop_x, int crop_y, int width, int height,
                                 uint8_t* dst, size_t dst_bytes, int sync);
 int  lh264_output_wait(lh264_ctx* ctx);
+/* Finer grained: lh264_read_ticket() names the lh264_pictures_read_packed() call made last on this context (two may be in flight: the
+ * output buffers inside the library alternate), lh264_output_wait_ticket() waits for THAT call's copy only - a consumer thread can
+ * take the pictures of step t while the copy of step t+1 is still running.                                                    */
+int  lh264_read_ticket(const lh264_ctx* ctx);
+int  lh264_output_wait_ticket(lh264_ctx* ctx, int ticket);
 /* Pinned host memory for hand-off records and output pictures (async copies need it).       */
 void* lh264_host_alloc(size_t bytes);
 void  lh264_host_free(void* p);

@@ -28,7 +28,7 @@ EXPORTS = [
     "lh264_k_expand_plane",
     "lh264_model_open", "lh264_model_close", "lh264_model_submit", "lh264_model_finish", "lh264_model_read",
     "lh264_model_decisions", "lh264_model_batch_upload", "lh264_model_batch_run", "lh264_model_batch_free",
-    "lh264_model_decode", "lh264_submit_compact",
+    "lh264_model_decode", "lh264_submit_compact", "lh264_read_ticket", "lh264_output_wait_ticket",
 ]
 
 

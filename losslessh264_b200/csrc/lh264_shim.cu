@@ -551,6 +551,14 @@ int lh264_output_wait (lh264_ctx* c) {
   return LH264_OK;
 }
 
+int lh264_read_ticket (const lh264_ctx* c) { return c ? c->pack_cur : LH264_E_INVALID; }
+int lh264_output_wait_ticket (lh264_ctx* c, int ticket) {
+  if (!c || ticket < 0 || ticket > 1) return fail (LH264_E_INVALID, "bad ticket");
+  CK (cudaSetDevice (c->device));
+  CK (cudaEventSynchronize (c->pack_read[ticket]));
+  return LH264_OK;
+}
+
 int lh264_inputs_consumed (lh264_ctx* c) {
   if (!c) return fail (LH264_E_INVALID, "null ctx");
   CK (cudaSetDevice (c->device));

@@ -112,6 +112,7 @@ int main (int argc, char** argv) {
   param.eOutputColorFormat = videoFormatI420; param.uiTargetDqLayer = 255; param.eEcActiveIdc = ERROR_CON_SLICE_COPY;
   param.sVideoProperty.eVideoBsType = VIDEO_BITSTREAM_DEFAULT;
   if (dec->Initialize (&param)) { fprintf (stderr, "Initialize failed (no CUDA device? this build has no CPU fallback)\n"); return 1; }
+  { int ec = ERROR_CON_SLICE_MV_COPY_CROSS_IDR_FREEZE_RES_CHANGE; dec->SetOption (DECODER_OPTION_ERROR_CON_IDC, &ec); }   // h264dec.cpp:156-157
   if (compress && dec->SetOption (DECODER_OPTION_LH264_PIP_OUTPUT, (void*)set_path.c_str())) { fprintf (stderr, "cannot switch the recompressor on\n"); return 1; }
 
   int frames = 0, width = 0, height = 0;

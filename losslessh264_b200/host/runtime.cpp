@@ -296,6 +296,7 @@ struct Pipeline;
 
 struct Out {                             // pictures on their way to the host
   bool valid = false;
+  int ticket = 0;                       // lh264_read_ticket of the packed read
   std::vector<Placed> pics;
   size_t per = 0;
   int idx = 0;
@@ -476,7 +477,7 @@ void pipeline_main (Pipeline* P) {
         o = std::move (P->out_q.front());
         P->out_q.pop_front();
       }
-      if (lh264_output_wait (ctx) != LH264_OK) { rt->fail (std::string ("lh264_output_wait: ") + lh264_last_error()); P->rc = -1; }   // (every read issued so far is on the host)
+      if (lh264_output_wait_ticket (ctx, o.ticket) != LH264_OK) { rt->fail (std::string ("lh264_output_wait_ticket: ") + lh264_last_error()); P->rc = -1; }   // this read's copy only: the next one may still be running
       else deliver (o);
       { std::lock_guard<std::mutex> g (P->out_mu); P->out_in_flight--; }
       P->out_cv.notify_all();
@@ -592,7 +593,7 @@ void pipeline_main (Pipeline* P) {
           P->out_issued++;
           {
             std::lock_guard<std::mutex> g (P->out_mu);
-            Out o; o.valid = true; o.pics = step; o.per = per; o.idx = oi;
+            Out o; o.valid = true; o.pics = step; o.per = per; o.idx = oi; o.ticket = lh264_read_ticket (ctx);
             P->out_q.push_back (std::move (o));
             P->out_in_flight++;
           }
