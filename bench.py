@@ -482,6 +482,8 @@ def main():
     for h_ in mstreams:
         ctx.model_close(h_)
     mstreams = []
+    ctx.close()                                            # decision pool and output arena of the resident legs go back to the device
+    ctx = None
 
     # ---- e2e_records (round 1's figure): pre-parsed records in pinned host memory in, decoded pictures back -----------
     if not args.no_records_leg:
@@ -618,6 +620,7 @@ def main():
                 w["reference_note"] = f"{k} concurrent oracle/_ref/h264dec processes on the same stream (parse + model + reconstruction, tool-reported decode time)"
             line["workloads"][key] = w
 
+    ctx = Context(local)
     if not args.no_expand:
         line["expand"] = bench_expand(ctx, parsed[0][1], args.expand_streams, world)
     if rank == 0 and world == 1 and not args.no_cpu_baseline and os.path.exists(REF_DEC):

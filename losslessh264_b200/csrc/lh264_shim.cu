@@ -169,6 +169,7 @@ static cudaError_t model_sync (lh264_ctx* c);
 static cudaError_t model_join (lh264_ctx* c);
 static int model_settle_sharer (lh264_ctx* c, int k);
 static cudaError_t model_inputs_consumed (lh264_ctx* c);
+static cudaError_t model_order_recon (lh264_ctx* c);
 
 extern "C" {
 
@@ -352,6 +353,7 @@ static int launch_recon (lh264_ctx* c, BatchDev& b) {
   const size_t sync_bytes = (4 + (size_t)b.n_pics * b.max_rows) * sizeof (int);
   const long long rows = (long long)b.n_pics * b.max_rows;
   const int blocks = (int)std::max (1LL, std::min ((long long)c->n_sm * c->occ_recon, (rows + ROWS_WARPS - 1) / ROWS_WARPS));
+  CK (model_order_recon (c));
   if (c->timing) CK (cudaEventRecord (c->ev[0], c->stream));
   if (b.compact) {                            // the records arrived in compact form: expand them where the row kernel reads them
     k_expand_mb<<<dim3 ((unsigned)std::min ((b.max_mbs + 127) / 128, 64), (unsigned)b.n_pics), 128, 0, c->stream>>> (b.xjobs.p);

@@ -83,18 +83,21 @@ struct ModelCtx {
   unsigned long long* d_pool_used = nullptr; unsigned int* d_pages_pending = nullptr;   // [2] each
   DevBuf<int> job_index; PinBuf<int> h_index[2]; cudaEvent_t index_copied[2] = {nullptr, nullptr}; int index_cur = 0;
   unsigned long long est_pool_used = 0, last_step_total = 0;
+  unsigned long long pool_step_total = 0;   // the step size the pool was last sized for (model_grow_pool)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float ms_gen = 0, ms_code = 0;
   // The model runs on its own CUDA stream: it consumes syntax elements, not samples, so the model of picture t overlaps
   // the reconstruction of picture t.  `done` makes the context stream (and whoever records events on it) wait for it.
   cudaStream_t stream = nullptr;
   cudaEvent_t done = nullptr;
+  bool done_recorded = false;
 };
 
 constexpr unsigned int SEG_PAGES = 2048;         // 32 MB arena segments
 constexpr size_t MAX_ARENA_PAGES = 1u << 20;     // 16 GB of output pages (grown in segments on demand; the table of page pointers is 8 MB)
 
 int model_grow_arena (lh264_ctx* c, ModelCtx* m, unsigned int need_pages);
+int model_grow_pool (lh264_ctx* c, ModelCtx* m, unsigned long long step_total);
 
 } // namespace
 
@@ -222,10 +225,22 @@ int model_grow_arena (lh264_ctx* c, ModelCtx* m, unsigned int need_pages) {
     CK (cudaMalloc (&m->d_next, sizeof (unsigned int)));
     CK (cudaMemsetAsync (m->d_next, 0, sizeof (unsigned int), m->stream));
   }
+  bool pool_released = false;
   while (m->n_pages < need_pages) {
     if (m->n_pages + SEG_PAGES > MAX_ARENA_PAGES) return fail (LH264_E_NOMEM, "model output arena exhausted");
     uint8_t* seg = nullptr;
-    CK (cudaMalloc (&seg, (size_t)SEG_PAGES * PAGE_SIZE));
+    cudaError_t e = cudaMalloc (&seg, (size_t)SEG_PAGES * PAGE_SIZE);
+    if (e == cudaErrorMemoryAllocation && !pool_released && m->pend_steps == 0 && (m->dec[0].p || m->dec[1].p)) {
+      // output pages are a need, the decision pool's room for deferral is a wish: with no step waiting in the pool, hand the
+      // pool's memory back, take the pages, and let the pool come back as large as what is left allows (model_grow_pool)
+      cudaGetLastError();
+      CK (cudaStreamSynchronize (m->stream)); CK (cudaStreamSynchronize (m->code_stream));
+      m->dec[0].release(); m->dec[1].release();
+      pool_released = true;
+      if (getenv ("LH264_DEBUG")) fprintf (stderr, "lh264: output arena out of memory at %u pages: decision pool released\n", m->n_pages);
+      continue;
+    }
+    if (e != cudaSuccess) return fail (LH264_E_CUDA, "cudaMalloc of a model output segment: %s (%u pages of %u)", cudaGetErrorString (e), m->n_pages, need_pages);
     m->segments.push_back (seg);
     const size_t first = m->h_page_ptrs.size();
     for (unsigned int i = 0; i < SEG_PAGES; i++) m->h_page_ptrs.push_back (seg + (size_t)i * PAGE_SIZE);
@@ -233,6 +248,7 @@ int model_grow_arena (lh264_ctx* c, ModelCtx* m, unsigned int need_pages) {
     CK (cudaStreamSynchronize (m->stream));
     m->n_pages += SEG_PAGES;
   }
+  if (pool_released && m->pool_step_total) return model_grow_pool (c, m, m->pool_step_total);
   return LH264_OK;
 }
 } // namespace
@@ -375,6 +391,8 @@ static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_
 }
 
 // Codes every pending step with ONE launch: block b = one model stream, walking its pictures in step order.
+static bool model_serial (const ModelCtx* m) { return !m->partitioned && (m->exclusive_env >= 0 ? m->exclusive_env >= 2 : m->last_resident); }
+
 static int model_flush_coder (lh264_ctx* c, ModelCtx* m) {
   const int T = m->pend_steps;
   if (T == 0) return LH264_OK;
@@ -472,13 +490,29 @@ static int model_launch (lh264_ctx* c, ModelCtx* m, MBatch& b, bool head, bool t
 
 // The pool must hold one step of `step_total` decisions; for the sake of deferral it is given room for code_steps such steps
 // as long as that stays below dec_cap_limit.  Call with the pool empty (after model_flush_coder).
-static int model_grow_pool (lh264_ctx* c, ModelCtx* m, unsigned long long step_total) {
+extern "C++" {
+namespace {
+int model_grow_pool (lh264_ctx* c, ModelCtx* m, unsigned long long step_total) {
   (void)c;
+  m->pool_step_total = std::max (m->pool_step_total, step_total);
   const size_t one = (size_t)step_total + (size_t)step_total / 4 + 64;
-  size_t want = std::max (one, std::min (one * (size_t)m->code_steps, m->dec_cap_limit));
+  // what the device can spare NOW (other contexts, picture pools and output pages have come and gone since the context was
+  // made): both halves together leave a tenth of the device (at least 4 GB) free for output pages and staging
+  size_t budget = m->dec_cap_limit;
+  {
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo (&free_b, &total_b) == cudaSuccess) {
+      const size_t mine = (m->dec[0].cap + m->dec[1].cap) * sizeof (uint32_t);
+      const size_t keep = std::max (total_b / 10, (size_t)4 << 30);
+      const size_t avail = free_b + mine > keep ? free_b + mine - keep : 0;
+      budget = std::min (budget, avail / sizeof (uint32_t) / 2 * 4 / 5);     // per half; DevBuf::reserve adds a quarter
+    }
+  }
+  size_t want = std::max (one, std::min (one * (size_t)m->code_steps, budget));
   DevBuf<uint32_t>& dec = m->dec[m->cur];
   if (want <= dec.cap) return LH264_OK;
   CK (cudaStreamSynchronize (m->stream)); CK (cudaStreamSynchronize (m->code_stream));
+  if (getenv ("LH264_DEBUG")) fprintf (stderr, "lh264: decision pool half %d: %zu -> %zu M decisions (step %llu M, budget %zu M)\n", m->cur, dec.cap >> 20, want >> 20, step_total >> 20, budget >> 20);
   // room for code_steps steps is a wish, room for one step a need: halve the wish until the device has it
   for (;;) {
     if (dec.reserve (want) == cudaSuccess) return LH264_OK;
@@ -487,6 +521,8 @@ static int model_grow_pool (lh264_ctx* c, ModelCtx* m, unsigned long long step_t
     want = std::max (one, want / 2);
   }
 }
+} // namespace
+} // extern "C++"
 
 // blocking: runs a batch to completion, growing the decision list / output arena until it fits
 static int model_complete (lh264_ctx* c, ModelCtx* m, MBatch& b, bool head) {
@@ -569,6 +605,10 @@ static int model_run (lh264_ctx* c, ModelCtx* m, MBatch& b) {
   // a step about as large as the last one would not fit behind the pending ones: code those first (saves a skip + re-run)
   if (m->pend_steps > 0 && m->est_pool_used + m->last_step_total + m->last_step_total / 2 + 64 > m->dec[m->cur].cap && (rc = model_flush_coder (c, m))) return rc;
   m->last_resident = b.resident;
+  // resident steps: one in-order chain on the device - this step's generation behind the reconstruction kernels submitted so far,
+  // the next reconstruction behind this generation (model_order_recon) - because side by side the persistent reconstruction kernel
+  // and the generation kernels cost more than one after the other (measured: 33-53 ms per step together, 27.6 ms in a row)
+  if (model_serial (m)) { CK (cudaEventRecord (m->recon_idle, c->stream)); CK (cudaStreamWaitEvent (m->stream, m->recon_idle, 0)); }
   if ((rc = model_launch (c, m, b, true, c->timing))) return rc;
   b.pending = true; m->inflight.push_back (&b);
   if (c->timing) {
@@ -578,6 +618,7 @@ static int model_run (lh264_ctx* c, ModelCtx* m, MBatch& b) {
     if ((rc = model_settle (c, m))) return rc;     // (a retry after growth is not part of the timed figures)
   }
   CK (cudaEventRecord (m->done, m->stream));
+  m->done_recorded = true;
   if (b.shares_recon_batch >= 0) {                 // that staging batch may be overwritten once this run is over
     CK (cudaEventRecord (c->batch_free[b.shares_recon_batch], m->stream));
     c->batch_shared[b.shares_recon_batch] = true;
@@ -759,6 +800,13 @@ static int model_settle_sharer (lh264_ctx* c, int k) {
 }
 
 // the caller's host buffers of every model submit so far have been copied to the device
+// called in front of a reconstruction launch: in the in-order mode it waits for the model work submitted so far
+static cudaError_t model_order_recon (lh264_ctx* c) {
+  ModelCtx* m = static_cast<ModelCtx*> (c->model);
+  if (!m || !model_serial (m) || !m->done_recorded) return cudaSuccess;
+  return cudaStreamWaitEvent (c->stream, m->done, 0);
+}
+
 static cudaError_t model_inputs_consumed (lh264_ctx* c) {
   ModelCtx* m = static_cast<ModelCtx*> (c->model);
   if (!m) return cudaSuccess;
