@@ -41,7 +41,7 @@
 extern "C" {
 #endif
 
-#define LH264_ABI_VERSION 2
+#define LH264_ABI_VERSION 3
 
 /* ---- error codes ------------------------------------------------------------------------ */
 #define LH264_OK             0
@@ -147,7 +147,29 @@ typedef struct lh264_slice_rec {
   int16_t  luma_offset[LH264_MAX_REFS];
   int16_t  chroma_weight[LH264_MAX_REFS][2];
   int16_t  chroma_offset[LH264_MAX_REFS][2];
+  /* Scaling lists (High profile; WelsCalcDeqCoeffScalingList, decode_slice.cpp:1231-1277).  The
+   * lists are the ones IN FORCE for the slice after the SPS / PPS fall-back rules
+   * (ParseScalingList, au_parser.cpp:1502-1562), in raster position order.  The multiplier of a
+   * level is list[pos] * LevelScale(qp, pos), applied as the reference applies it:
+   * (level * m) >> 4 for 4x4 blocks (parse_mb_syn_cavlc.cpp:945,993), the 8x8 rounding formula
+   * (parse_mb_syn_cavlc.cpp:1088-1090) for 8x8 blocks, all zero at qp 51 (the reference fills
+   * its tables for qp 0..50 only).                                                           */
+  uint8_t  scaling_flags;           /* LH264_SLF_*                                            */
+  uint8_t  reserved[15];
+  uint8_t  scale4[6][16];           /* Y intra, Cb intra, Cr intra, Y inter, Cb inter, Cr inter */
+  uint8_t  scale8[2][64];           /* Y intra, Y inter                                       */
 } lh264_slice_rec;
+
+#define LH264_SLF_SCALING      0x01 /* scaling lists in use (bUseScalingList)                 */
+#define LH264_SLF_SCALING_CAVLC 0x02 /* CAVLC slice: the reference indexes its 8x8 multiplier
+                                       tables with the 4x4 residual property (decode_slice.cpp:3385,
+                                       :3782 pass LUMA_DC_AC_INTRA / _INTER to
+                                       WelsResidualBlockCavlc8x8, whose table index is property - 6),
+                                       i.e. it reads pDequant_coeff4x4[0] / [3] as a 64-wide table.
+                                       With this bit the 8x8 multiplier of (qp, pos) is element
+                                       base + qp * 64 + pos of the flat 4x4 tables [6][52][16]
+                                       followed by the flat 8x8 tables [6][52][64], base = 0 for an
+                                       intra and 3 * 52 * 16 for an inter macroblock.           */
 
 /* One picture to reconstruct (all of its slices).  All pointers are HOST pointers for
  * lh264_recon_submit(); the library copies what it needs before returning only if

@@ -50,6 +50,7 @@ struct __align__ (16) RowCtx : WarpCtx {
   // what the hot path reads of the current slice's record, refreshed when slice_idx changes (most pictures: once per row)
   int16_t sl_slot[LH264_MAX_REFS];              // picture slot of RefPicList0[i], clamped to the stream's pool
   uint8_t sl_wp, sl_idc; int8_t sl_aoff, sl_boff;
+  uint8_t sl_scal;                              // LH264_SLF_*: scaling lists in use (cold path: residual_block_scaled)
 };
 
 struct DecodeSync {          // device-resident, zeroed before every batch
@@ -267,7 +268,7 @@ __device__ LH264_NOINLINE void w_inter_general (RowCtx& s, const PicDev& pic, co
     if (res_done) return;
     res_done = true;
     w_store_levels (s, lane, lv);
-    if (lane < 24) residual_block (reinterpret_cast<MbShared&> (s), lane);
+    if (lane < 24) { if (s.sl_scal & LH264_SLF_SCALING) residual_block_scaled (reinterpret_cast<MbShared&> (s), lane, sl); else residual_block (reinterpret_cast<MbShared&> (s), lane); }
   };
   if (t == LH264_MB_P16x16 || t == LH264_MB_PSKIP) { w_inter_partition (s, pic, sl, mbx, mby, lane, 0, 0, 16, 16, 0, 0); residual(); }
   else if (t == LH264_MB_P16x8) { w_inter_partition (s, pic, sl, mbx, mby, lane, 0, 0, 16, 8, 0, 0); residual(); w_inter_partition (s, pic, sl, mbx, mby, lane, 0, 8, 16, 8, 8, 2); }
@@ -321,7 +322,7 @@ __device__ LH264_NOINLINE void w_intra_row (RowCtx& s, const PicDev& pic, int mb
       else s.cedge[p][1][k - 9] = s.ucol[16 + 8 * p + (k - 10)];
     }
   }
-  if (lane < 24) residual_block (reinterpret_cast<MbShared&> (s), lane);
+  if (lane < 24) { if (s.sl_scal & LH264_SLF_SCALING) residual_block_scaled (reinterpret_cast<MbShared&> (s), lane, pic.slices + s.mb.slice_idx); else residual_block (reinterpret_cast<MbShared&> (s), lane); }
   __syncwarp();
 
   // chroma prediction, WelsIChromaPred*_c: 32 quads, one per lane
@@ -589,7 +590,7 @@ __global__ void __launch_bounds__ (ROWS_WARPS * 32, 2) k_decode_rows (const PicD
         const lh264_slice_rec* sl = pic.slices + cached_slice;
         __syncwarp();
         if (lane < LH264_MAX_REFS) s.sl_slot[lane] = (int16_t)clip3i (__ldg (&sl->ref_slot[lane]), 0, pic.n_slots - 1);
-        else if (lane == 16) { s.sl_wp = __ldg (&sl->weighted_pred); s.sl_idc = __ldg (&sl->disable_deblocking_idc); s.sl_aoff = __ldg (&sl->alpha_c0_offset); s.sl_boff = __ldg (&sl->beta_offset); }
+        else if (lane == 16) { s.sl_wp = __ldg (&sl->weighted_pred); s.sl_idc = __ldg (&sl->disable_deblocking_idc); s.sl_aoff = __ldg (&sl->alpha_c0_offset); s.sl_boff = __ldg (&sl->beta_offset); s.sl_scal = __ldg (&sl->scaling_flags); }
         __syncwarp();
       }
       // the row above must have stored macroblock x (its final state but for the edge filtered here) and written the
@@ -614,7 +615,7 @@ __global__ void __launch_bounds__ (ROWS_WARPS * 32, 2) k_decode_rows (const PicD
       if (LH264_MB_IS_INTER (mb_type)) {
         const lh264_slice_rec* sl = pic.slices + s.mb.slice_idx;
         bool done = false;
-        if ((mb_type == LH264_MB_P16x16 || mb_type == LH264_MB_PSKIP) && ! (s.mb.flags & LH264_MBF_TRANSFORM8x8)) done = w_inter16_fast (s, pic, mbx, mby, lane);
+        if ((mb_type == LH264_MB_P16x16 || mb_type == LH264_MB_PSKIP) && ! (s.mb.flags & LH264_MBF_TRANSFORM8x8) && !s.sl_scal) done = w_inter16_fast (s, pic, mbx, mby, lane);
         if (!done) w_inter_general (s, pic, sl, mbx, mby, lane);
       } else if (LH264_MB_IS_INTRA (mb_type)) w_intra_row (s, pic, mbx, mby, lane);
       else {                                        // not decoded in this picture: the samples stay as they are

@@ -133,6 +133,101 @@ __device__ void residual_block (MbShared& s, int k) {
   }
 }
 
+// ---- the same with scaling lists (High profile), WelsCalcDeqCoeffScalingList decode_slice.cpp:1231-1277 -----------------------
+// multiplier of a level = list[pos] * LevelScale (qp, pos); the reference fills its tables for qp 0..50 only, so qp 51 gives 0
+__device__ __forceinline__ int sl_dq4 (const lh264_slice_rec* sl, int list, int qp, int pos) {
+  return qp < 51 ? ((int)__ldg (&sl->scale4[list][pos]) * dq4 (qp, pos)) & 0xffff : 0;      // the reference's tables are uint16_t
+}
+__device__ __forceinline__ int sl_dq8 (const lh264_slice_rec* sl, int list, int qp, int pos) {
+  return qp < 51 ? (int)__ldg (&sl->scale8[list][pos]) * (dq8 (qp % 6, pos) >> 4) : 0;
+}
+// 8x8 multiplier of a CAVLC slice: element base + qp * 64 + pos of the reference's flat tables (LH264_SLF_SCALING_CAVLC)
+__device__ __forceinline__ int sl_dq8_cavlc (const lh264_slice_rec* sl, bool intra, int qp, int pos) {
+  const int n = (intra ? 0 : 3 * 52 * 16) + qp * 64 + pos;
+  if (n < 6 * 52 * 16) return sl_dq4 (sl, n / (52 * 16), (n % (52 * 16)) >> 4, n & 15);
+  const int m = n - 6 * 52 * 16;
+  return sl_dq8 (sl, m / (52 * 64), (m % (52 * 64)) >> 6, m & 63);
+}
+// residual_block() for a slice with LH264_SLF_SCALING.  Cold path: kept out of line.
+#ifdef LH264_CPU_EMU
+#define LH264_COLD __attribute__ ((noinline))
+#else
+#define LH264_COLD __noinline__
+#endif
+__device__ LH264_COLD void residual_block_scaled (MbShared& s, int k, const lh264_slice_rec* sl) {
+  const bool i16 = s.mb.mb_type == LH264_MB_I16x16, intra = LH264_MB_IS_INTRA (s.mb.mb_type);
+  if (s.mb.mb_type == LH264_MB_IPCM) { residual_block (s, k); return; }
+  if (k < 16) {
+    const int qp = s.mb.qp_y;
+    if (s.mb.flags & LH264_MBF_TRANSFORM8x8) {
+      if (k & 3) return;
+      int16_t* res = s.res + blk_y (k) * 16 + blk_x (k);
+      if (((s.mb.coded_mask >> k) & 15u) == 0) {
+        for (int y = 0; y < 8; y++) for (int x = 0; x < 8; x += 4) *reinterpret_cast<uint2*> (res + 16 * y + x) = make_uint2 (0u, 0u);
+        return;
+      }
+      const bool cavlc = (__ldg (&sl->scaling_flags) & LH264_SLF_SCALING_CAVLC) != 0;
+      const int16_t* lev = s.lev + 16 * k;
+      int t[64];
+      const int sh = qp / 6;
+#pragma unroll 1
+      for (int i = 0; i < 8; i++) {
+        int p[8], o[8];
+        for (int j = 0; j < 8; j++) {
+          const int m = cavlc ? sl_dq8_cavlc (sl, intra, qp, 8 * i + j) : sl_dq8 (sl, intra ? 0 : 1, qp, 8 * i + j);
+          const int v = lev[8 * i + j] * m;
+          p[j] = S16 (qp >= 36 ? (v << (sh - 6)) : ((v + (1 << (5 - sh))) >> (6 - sh)));
+        }
+        idct8_1d (p, o);
+        for (int j = 0; j < 8; j++) t[8 * i + j] = o[j];
+      }
+#pragma unroll 1
+      for (int i = 0; i < 8; i++) {
+        int p[8], o[8];
+        for (int j = 0; j < 8; j++) p[j] = t[8 * j + i];
+        idct8_1d (p, o);
+        for (int j = 0; j < 8; j++) res[16 * j + i] = (int16_t) ((32 + o[j]) >> 6);
+      }
+      return;
+    }
+    const uint32_t mask = s.mb.coded_mask;
+    if (i16 ? (mask & 0xffffu) == 0 : ((mask >> k) & 1u) == 0) { residual_block (s, k); return; }     // writes the zeros
+    const int list = intra ? 0 : 3;
+    int c[16];
+    const int16_t* lev = s.lev + 16 * k;
+    for (int j = 0; j < 16; j++) c[j] = S16 ((lev[j] * sl_dq4 (sl, list, qp, j)) >> 4);
+    if (i16) {                                    // WelsLumaDcDequantIdct with kiQMul = table[0] >> 4 (decode_slice.cpp:272)
+      const int qmul = sl_dq4 (sl, 0, qp, 0) >> 4;
+      int m[16], t[16];
+      for (int i = 0; i < 4; i++)
+        for (int j = 0; j < 4; j++) m[4 * i + j] = s.lev[16 * (((i & 1) << 1) + ((i & 2) << 2) + (j & 1) + ((j & 2) << 1))];
+      for (int i = 0; i < 4; i++) {
+        const int a = m[4 * i], b = m[4 * i + 1], cc = m[4 * i + 2], d = m[4 * i + 3];
+        const int z0 = a + cc, z1 = a - cc, z2 = b - d, z3 = b + d;
+        t[4 * i] = z0 + z3; t[4 * i + 1] = z1 + z2; t[4 * i + 2] = z1 - z2; t[4 * i + 3] = z0 - z3;
+      }
+      const int col = (k & 1) + ((k & 4) >> 1), row = ((k & 2) >> 1) + ((k & 8) >> 2);
+      const int z0 = t[col] + t[8 + col], z1 = t[col] - t[8 + col], z2 = t[4 + col] - t[12 + col], z3 = t[4 + col] + t[12 + col];
+      const int v = row == 0 ? z0 + z3 : (row == 1 ? z1 + z2 : (row == 2 ? z1 - z2 : z0 - z3));
+      c[0] = S16 ((v * qmul + 2) >> 2);
+    }
+    idct4x4_res (c, s.res + blk_y (k) * 16 + blk_x (k), 16);
+  } else {
+    const int p = (k - 16) >> 2, b = (k - 16) & 3, qp = s.mb.qp_c[p];
+    if (((s.mb.coded_mask >> (16 + 4 * p)) & 15u) == 0) { residual_block (s, k); return; }
+    const int list = (intra ? 1 : 4) + p;
+    const int16_t* lev = s.lev + 16 * k;
+    int c[16];
+    for (int j = 1; j < 16; j++) c[j] = S16 ((lev[j] * sl_dq4 (sl, list, qp, j)) >> 4);
+    const int q0 = sl_dq4 (sl, list, qp, 0);
+    const int16_t* dc = s.lev + 16 * (16 + 4 * p);
+    int a = S16 ((dc[0] * q0) >> 4), bb = S16 ((dc[16] * q0) >> 4), cc = S16 ((dc[32] * q0) >> 4), d = S16 ((dc[48] * q0) >> 4);
+    const int e = a - bb; a += bb; bb = cc - d; cc += d;
+    c[0] = S16 (b == 0 ? (a + cc) >> 1 : (b == 1 ? (e + bb) >> 1 : (b == 2 ? (a - cc) >> 1 : (e - bb) >> 1)));
+    idct4x4_res (c, s.res + 256 + 64 * p + (b >> 1) * 32 + (b & 1) * 4, 8);
+  }
+}
+
 // =====================================================================================================
 // Intra wavefront.  WelsMbIntraPredictionConstruction (decode_slice.cpp:313-334), RecI4x4Mb / RecI8x8Mb /
 // RecI16x16Mb / RecChroma (rec_mb.cpp:64-219,:547-575), predictors get_intra_predictor.cpp:54-1155.

@@ -202,6 +202,10 @@ struct Decoder::Impl {
   CabacDecoder cab;
   int16_t lev_[384] = {0};               // residual scratch of parse_mb
   bool cabac_on = false, last_dqp_nz = false;
+  // scaling lists: what the reference's multiplier tables were last built from (see the slice record set-up)
+  bool scal_init = false, sps_late_pps = false;
+  int scal_ppsid = -1;
+  uint8_t scal4[6][16], scal8[2][64];
   std::vector<CabMb> cabmb;
   std::vector<uint8_t> mvd_abs;          // [mb][16][2] |mvd| per raster 4x4 block, saturated at 128
 
@@ -1333,14 +1337,13 @@ int Decoder::decode (const uint8_t* data, size_t len, unsigned long long timesta
       } else { last_err = -10; stats_.errors++; }
     } else if (type == NAL_PPS) {
       Pps p;
-      if (parse_pps (br, p, D.sps)) D.pps[p.id] = p; else { last_err = -11; stats_.errors++; }
+      if (parse_pps (br, p, D.sps)) { D.pps[p.id] = p; if (p.scaling_matrix_present && p.sps_was_missing) D.sps_late_pps = true; } else { last_err = -11; stats_.errors++; }
     } else if (type == NAL_SLICE || type == NAL_IDR) {
       SliceHeader sh;
       const int rc = parse_slice_header (br, ref_idc, type, D.sps, D.pps, sh);
       if (rc < 0) { last_err = rc; stats_.errors++; continue; }
       const Pps& pps = D.pps[sh.pps_id];
       const Sps& sps = D.sps[pps.sps_id];
-      if (sps.scaling_matrix_present || pps.scaling_matrix_present) { last_err = -21; stats_.errors++; continue; }
       if (D.open && D.is_new_picture (D.sh0, sh)) D.finish_picture (this);
       if (!D.open) {
         if (D.activate (sps) < 0) { last_err = -30; continue; }
@@ -1387,6 +1390,25 @@ int Decoder::decode (const uint8_t* data, size_t len, unsigned long long timesta
             for (int c = 0; c < 2; c++) { sr.chroma_weight[i][c] = (int16_t)sh.chroma_weight[i][c]; sr.chroma_offset[i][c] = (int16_t)sh.chroma_offset[i][c]; }
           }
         }
+      }
+      // Scaling lists in force (WelsCalcDeqCoeffScalingList, decode_slice.cpp:1231-1277, called once per slice): the reference
+      // rebuilds its multiplier tables only when the PPS id differs from the one they were built for, so a slice keeps the
+      // lists of the FIRST parameter sets seen under that id until another id comes by - reproduced here.
+      if (sps.scaling_matrix_present || pps.scaling_matrix_present) {
+        if (!D.scal_init || D.scal_ppsid != pps.id) {
+          Pps& wp = D.pps[sh.pps_id];
+          if (D.sps_late_pps)                        // a PPS parsed before its SPS: absent lists are patched from the SPS now
+            for (int i = 0; i < 12; i++) if (!wp.list_present[i]) {
+                if (i < 6) memcpy (wp.scale4[i], (i == 0 || i == 3) ? sps.scale4[i] : wp.scale4[i - 1], 16);
+                else memcpy (wp.scale8[i - 6], (i == 6 || i == 7) ? sps.scale8[i - 6] : wp.scale8[i - 8], 64);
+              }
+          for (int i = 0; i < 6; i++) memcpy (D.scal4[i], wp.scaling_matrix_present ? wp.scale4[i] : sps.scale4[i], 16);
+          for (int i = 0; i < 2; i++) memcpy (D.scal8[i], wp.scaling_matrix_present ? wp.scale8[i] : sps.scale8[i], 64);
+          D.scal_init = true; D.scal_ppsid = pps.id;
+        }
+        sr.scaling_flags = (uint8_t) (LH264_SLF_SCALING | (pps.cabac ? 0 : LH264_SLF_SCALING_CAVLC));
+        memcpy (sr.scale4, D.scal4, sizeof (sr.scale4));
+        memcpy (sr.scale8, D.scal8, sizeof (sr.scale8));
       }
       D.slices.push_back (sr);
       stats_.slices++;

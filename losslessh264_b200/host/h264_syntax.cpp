@@ -47,12 +47,70 @@ size_t unescape_nal (const uint8_t* p, size_t len, std::vector<uint8_t>& out) {
   return o;
 }
 
-static void skip_scaling_list (BitReader& br, int size) {
+// ---- scaling lists (7.3.2.1.1.1, fall-back rules of 7.4.2.1.1 / 7.4.2.2) as the reference applies them ------------------------
+// ParseScalingList / SetScalingListValue, au_parser.cpp:1475-1562.  Lists are kept in raster position order.
+static const uint8_t kZig4[16] = {0, 1, 4, 8, 5, 2, 3, 6, 9, 12, 13, 10, 7, 11, 14, 15};
+static uint8_t g_zig8[64];
+static uint8_t g_default4[2][16], g_default8[2][64];       // Default_4x4_Intra / _Inter, Default_8x8_Intra / _Inter (Tables 7-3, 7-4)
+static bool init_scaling_tables() {
+  // 8x8 frame zig-zag: walk the anti-diagonals
+  int n = 0;
+  for (int d = 0; d < 15; d++)
+    for (int k = 0; k <= d; k++) {
+      const int i = (d & 1) ? k : d - k, j = d - i;       // odd diagonals run down-left, even ones up-right
+      if (i < 8 && j < 8) g_zig8[n++] = (uint8_t) (8 * i + j);
+    }
+  static const uint8_t z4[2][16] = { {6, 13, 13, 20, 20, 20, 28, 28, 28, 28, 32, 32, 32, 37, 37, 42}, {10, 14, 14, 20, 20, 20, 24, 24, 24, 24, 27, 27, 27, 30, 30, 34} };
+  static const uint8_t z8[2][64] = {
+    {6, 10, 10, 13, 11, 13, 16, 16, 16, 16, 18, 18, 18, 18, 18, 23, 23, 23, 23, 23, 23, 25, 25, 25, 25, 25, 25, 25, 27, 27, 27, 27, 27, 27, 27, 27,
+     29, 29, 29, 29, 29, 29, 29, 31, 31, 31, 31, 31, 31, 33, 33, 33, 33, 33, 36, 36, 36, 36, 38, 38, 38, 40, 40, 42},
+    {9, 13, 13, 15, 13, 15, 17, 17, 17, 17, 19, 19, 19, 19, 19, 21, 21, 21, 21, 21, 21, 22, 22, 22, 22, 22, 22, 22, 24, 24, 24, 24, 24, 24, 24, 24,
+     25, 25, 25, 25, 25, 25, 25, 27, 27, 27, 27, 27, 27, 28, 28, 28, 28, 28, 30, 30, 30, 30, 32, 32, 32, 33, 33, 35} };
+  for (int t = 0; t < 2; t++) {
+    for (int k = 0; k < 16; k++) g_default4[t][kZig4[k]] = z4[t][k];
+    for (int k = 0; k < 64; k++) g_default8[t][g_zig8[k]] = z8[t][k];
+  }
+  return true;
+}
+static const bool g_scaling_tables_ready = init_scaling_tables();
+
+// one scaling_list(): returns true when the list asks for the default matrix (first delta brings next_scale to 0)
+static bool read_scaling_list (BitReader& br, uint8_t* list, int size, bool& bad) {
   int last = 8, next = 8;
   for (int j = 0; j < size; j++) {
-    if (next != 0) next = (last + br.se() + 256) % 256;
-    last = next == 0 ? last : next;
+    if (next != 0) {
+      const int delta = br.se();
+      if (delta < -128 || delta > 127) { bad = true; return false; }
+      next = (last + delta + 256) % 256;
+      if (j == 0 && next == 0) return true;
+    }
+    const int idx = size == 16 ? kZig4[j] : g_zig8[j];
+    list[idx] = (uint8_t) (next == 0 ? last : next);
+    last = list[idx];
   }
+  return false;
+}
+
+// n_lists = 8 (4:2:0) or 12; `sps` = the sequence parameter set whose lists are fall-back rule B for a PPS (nullptr: rule A)
+static bool parse_scaling_lists (BitReader& br, int n_lists, const Sps* sps, bool* present, uint8_t (*l4)[16], uint8_t (*l8)[64]) {
+  (void)g_scaling_tables_ready;
+  const uint8_t* fall[4] = { sps ? sps->scale4[0] : g_default4[0], sps ? sps->scale4[3] : g_default4[1],
+                             sps ? sps->scale8[0] : g_default8[0], sps ? sps->scale8[1] : g_default8[1] };
+  for (int i = 0; i < n_lists; i++) {
+    const bool here = br.u1();
+    if (present) present[i] = here;
+    bool bad = false;
+    if (here) {
+      if (i < 6) { if (read_scaling_list (br, l4[i], 16, bad)) memcpy (l4[i], g_default4[i / 3], 16); }
+      else if (read_scaling_list (br, l8[i - 6], 64, bad)) memcpy (l8[i - 6], g_default8[(i - 6) & 1], 64);
+      if (bad) return false;
+    } else if (i < 6) {
+      if (i != 0 && i != 3) memcpy (l4[i], l4[i - 1], 16); else memcpy (l4[i], fall[i / 3], 16);
+    } else {
+      if (i == 6 || i == 7) memcpy (l8[i - 6], fall[(i & 1) + 2], 64); else memcpy (l8[i - 6], l8[i - 8], 64);
+    }
+  }
+  return !br.overrun();
 }
 
 bool parse_sps (BitReader& br, Sps& s) {
@@ -70,7 +128,7 @@ bool parse_sps (BitReader& br, Sps& s) {
     br.u1();                                       // qpprime_y_zero_transform_bypass_flag
     if (br.u1()) {                                 // seq_scaling_matrix_present_flag
       s.scaling_matrix_present = true;
-      for (int i = 0; i < (s.chroma_format_idc != 3 ? 8 : 12); i++) if (br.u1()) skip_scaling_list (br, i < 6 ? 16 : 64);
+      if (!parse_scaling_lists (br, s.chroma_format_idc != 3 ? 8 : 12, nullptr, nullptr, s.scale4, s.scale8)) return false;
     }
     if (s.chroma_format_idc != 1 || bdl != 0 || bdc != 0) return false;   // 4:2:0 8-bit only
   }
@@ -143,12 +201,15 @@ bool parse_pps (BitReader& br, Pps& p, const Sps* sps_table) {
   if (br.more_rbsp_data()) {
     p.transform_8x8_mode = br.u1();
     if (br.u1()) {                                    // pic_scaling_matrix_present_flag
+      // ParsePps reads 8 lists (12 when the SPS has not arrived yet or is 4:4:4) whatever transform_8x8_mode_flag says, and
+      // falls back on the lists of an SPS that carries a matrix of its own (au_parser.cpp:1384-1395, :1512-1522)
       p.scaling_matrix_present = true;
-      for (int i = 0; i < 6 + (p.transform_8x8_mode ? 2 : 0); i++) if (br.u1()) skip_scaling_list (br, i < 6 ? 16 : 64);
+      const Sps* sps = sps_table && sps_table[p.sps_id].valid ? &sps_table[p.sps_id] : nullptr;
+      p.sps_was_missing = sps == nullptr;
+      if (!parse_scaling_lists (br, sps && sps->chroma_format_idc != 3 ? 8 : 12, sps && sps->scaling_matrix_present ? sps : nullptr, p.list_present, p.scale4, p.scale8)) return false;
     }
     p.second_chroma_qp_index_offset = br.se();
   }
-  (void)sps_table;
   if (br.overrun()) return false;
   p.valid = true;
   return true;

@@ -30,6 +30,8 @@ struct Sps {
   bool frame_mbs_only = true, direct_8x8_inference = false;
   int crop_left = 0, crop_right = 0, crop_top = 0, crop_bottom = 0;   // in luma samples
   bool scaling_matrix_present = false;
+  // scaling lists in raster position order, every list filled in by the fall-back rules (ParseScalingList, au_parser.cpp:1502-1562)
+  uint8_t scale4[6][16], scale8[6][64];
 };
 
 struct Pps {
@@ -45,6 +47,9 @@ struct Pps {
   int chroma_qp_index_offset = 0, second_chroma_qp_index_offset = 0;
   bool deblocking_filter_control_present = false, constrained_intra_pred = false, redundant_pic_cnt_present = false;
   bool transform_8x8_mode = false, scaling_matrix_present = false;
+  bool list_present[12] = {false, false, false, false, false, false, false, false, false, false, false, false};
+  uint8_t scale4[6][16], scale8[6][64];              // as in Sps; fall-back from the SPS known when the PPS arrived
+  bool sps_was_missing = false;                      // parsed before its SPS (the reference then reads 12 lists and patches later)
 };
 
 struct RefPicListMod { int op; uint32_t val; };

@@ -58,9 +58,24 @@ SLICE_REC = np.dtype(
         ("luma_offset", "<i2", (MAX_REFS,)),
         ("chroma_weight", "<i2", (MAX_REFS, 2)),
         ("chroma_offset", "<i2", (MAX_REFS, 2)),
+        ("scaling_flags", "u1"),
+        ("reserved", "u1", (15,)),
+        ("scale4", "u1", (6, 16)),
+        ("scale8", "u1", (2, 64)),
     ]
 )
-assert SLICE_REC.itemsize == 16 + 2 * MAX_REFS * 7
+assert SLICE_REC.itemsize == 16 + 2 * MAX_REFS * 7 + 240
+SLF_SCALING, SLF_SCALING_CAVLC = 1, 2
+
+
+def as_slice_recs(a):
+    """Slice records saved before the scaling-list fields existed (240-byte records) widened to the current layout."""
+    if a.dtype == SLICE_REC:
+        return a
+    out = np.zeros(len(a), SLICE_REC)
+    for name in a.dtype.names:
+        out[name] = a[name]
+    return out
 
 
 @dataclass
@@ -202,7 +217,7 @@ def load_fixture(path):
     for row in z["meta"]:
         mb_w, mb_h, slot, fn, poc, idr, ref_idc, serial, n_sl, n_co = (int(v) for v in row)
         p = Picture(mb_w, mb_h, slot, fn, poc, idr, ref_idc, serial)
-        p.slices = z["slices"][o_s : o_s + n_sl].copy()
+        p.slices = as_slice_recs(z["slices"][o_s : o_s + n_sl]).copy()
         p.mbs = z["mbs"][o_m : o_m + mb_w * mb_h].copy()
         p.coefs = z["coefs"][o_c : o_c + n_co].copy()
         ysz = mb_w * mb_h * 384

@@ -53,14 +53,32 @@ static inline int dq8 (int qp, int pos) {
   return 16 * kScale8[qp % 6][c];
 }
 
-/* parse_mb_syn_cavlc.cpp:989-993: pTCoeff[j] = level * dq[j & 7], stored as int16_t. */
-static void dequant_ac4x4 (int16_t* out, const int16_t* lev, int qp, int first) {
+/* Scaling lists (WelsCalcDeqCoeffScalingList, decode_slice.cpp:1231-1277): the reference's per-qp tables are
+ * list[pos] * g_kuiDequantCoeff[q][pos & 7] (4x4) and list[pos] * g_kuiMatrixV[q % 6][pos] (8x8), filled for q < 51 only
+ * (the q == 51 row keeps the zeros of the context's allocation).  `sc` = the slice record when LH264_SLF_SCALING is set. */
+static inline int sl_dq4 (const lh264_slice_rec* sc, int list, int q, int pos) { return q < 51 ? (uint16_t) (sc->scale4[list][pos] * dq4 (q, pos)) : 0; }   /* uint16_t tables */
+static inline int sl_dq8 (const lh264_slice_rec* sc, int list, int q, int pos) { return q < 51 ? sc->scale8[list][pos] * (dq8 (q % 6, pos) >> 4) : 0; }
+/* CAVLC slices: WelsResidualBlockCavlc8x8 is handed the 4x4 property (decode_slice.cpp:3385, :3782), so its table index
+ * (property - 6) is -6 / -3: pDequant_coeff8x8[-6] IS pDequant_coeff4x4[0] (adjacent pointer arrays, decoder_context.h:448-449),
+ * read as a 64-wide table over pDequant_coeff_buffer4x4[6][52][16] and, past its end, pDequant_coeff_buffer8x8[6][52][64]. */
+static inline int sl_dq8_cavlc (const lh264_slice_rec* sc, int intra, int qp, int pos) {
+  const int n = (intra ? 0 : 3 * 52 * 16) + qp * 64 + pos;
+  if (n < 6 * 52 * 16) return sl_dq4 (sc, n / (52 * 16), (n % (52 * 16)) / 16, n % 16);
+  const int m = n - 6 * 52 * 16;
+  return sl_dq8 (sc, m / (52 * 64), (m % (52 * 64)) / 64, m % 64);
+}
+
+/* parse_mb_syn_cavlc.cpp:989-993: pTCoeff[j] = level * dq[j & 7], stored as int16_t; with scaling lists
+ * (level * table[j]) >> 4 (same lines). */
+static void dequant_ac4x4 (int16_t* out, const int16_t* lev, int qp, int first, const lh264_slice_rec* sc, int list) {
+  if (sc) { for (int j = first; j < 16; j++) out[j] = (int16_t) ((lev[j] * sl_dq4 (sc, list, qp, j)) >> 4); return; }
   for (int j = first; j < 16; j++) out[j] = (int16_t) (lev[j] * dq4 (qp, j));
 }
 /* parse_mb_syn_cavlc.cpp:1088-1095 */
-static void dequant_8x8 (int16_t* out, const int16_t* lev, int qp) {
+static void dequant_8x8 (int16_t* out, const int16_t* lev, int qp, const lh264_slice_rec* sc, int intra) {
   for (int j = 0; j < 64; j++) {
-    int v = lev[j] * dq8 (qp, j);
+    const int mul = !sc ? dq8 (qp, j) : ((sc->scaling_flags & LH264_SLF_SCALING_CAVLC) ? sl_dq8_cavlc (sc, intra, qp, j) : sl_dq8 (sc, intra ? 0 : 1, qp, j));
+    int v = lev[j] * mul;
     out[j] = (int16_t) (qp >= 36 ? (v << (qp / 6 - 6)) : ((v + (1 << (5 - qp / 6))) >> (6 - qp / 6)));
   }
 }
@@ -111,9 +129,9 @@ static void idct8x8_add (uint8_t* p, int stride, const int16_t* c) {
 
 /* WelsLumaDcDequantIdct, decode_slice.cpp:271-311.  dc[z] = level in slot 0 of block z (z order);
  * result written back (int16) to slot 0 of each block. */
-static void luma_dc_dequant_idct (int16_t* blk /*[16][16]*/, int qp) {
+static void luma_dc_dequant_idct (int16_t* blk /*[16][16]*/, int qp, const lh264_slice_rec* sc) {
   static const int xoff[4] = {0, 1, 4, 5}, yoff[4] = {0, 2, 8, 10};   /* block index = yoff[i] + xoff[j] */
-  const int qmul = dq4 (qp, 0);
+  const int qmul = sc ? sl_dq4 (sc, 0, qp, 0) >> 4 : dq4 (qp, 0);      /* decode_slice.cpp:272 */
   int t[16];
   for (int i = 0; i < 4; i++) {
     int o = yoff[i];
@@ -501,7 +519,7 @@ static void gather_levels (const lh264_mb_rec* m, const int16_t* pool, int16_t l
   for (int k = 0; k < 24; k++) if (m->coded_mask & (1u << k)) { memcpy (lev + 16 * k, src, 32); src += 16; }
 }
 
-static void residual_chroma (const ora_picture* cur, const lh264_mb_rec* m, const int16_t* lev, int mbx, int mby) {
+static void residual_chroma (const ora_picture* cur, const lh264_mb_rec* m, const int16_t* lev, int mbx, int mby, const lh264_slice_rec* sc) {
   /* RecChroma (rec_mb.cpp:547-575) / WelsMbInterSampleConstruction chroma part (decode_slice.cpp:213-247) */
   const int cw = cur->w >> 1;
   for (int p = 0; p < 2; p++) {
@@ -509,8 +527,9 @@ static void residual_chroma (const ora_picture* cur, const lh264_mb_rec* m, cons
     const int qp = m->qp_c[p];
     for (int b = 0; b < 4; b++) {
       const int16_t* l = lev + 16 * (16 + 4 * p + b);
-      c[16 * b] = (int16_t) (l[0] * dq4 (qp, 0));           /* parse_mb_syn_cavlc.cpp:944 */
-      dequant_ac4x4 (c + 16 * b, l, qp, 1);
+      const int list = (LH264_MB_IS_INTRA (m->mb_type) ? 1 : 4) + p;
+      c[16 * b] = sc ? (int16_t) ((l[0] * sl_dq4 (sc, list, qp, 0)) >> 4) : (int16_t) (l[0] * dq4 (qp, 0));           /* parse_mb_syn_cavlc.cpp:944 */
+      dequant_ac4x4 (c + 16 * b, l, qp, 1, sc, list);
     }
     chroma_dc_idct (c);
     for (int b = 0; b < 4; b++) {
@@ -526,6 +545,7 @@ static void recon_mb (const ora_picture* cur, const ora_picture* slots, int n_sl
   uint8_t* py = cur->plane[0] + (size_t)mby * 16 * w + mbx * 16;
   int16_t lev[384], c[64];
   const int t8 = m->flags & LH264_MBF_TRANSFORM8x8;
+  const lh264_slice_rec* sc = (sl->scaling_flags & LH264_SLF_SCALING) ? sl : NULL;
   if (m->mb_type == LH264_MB_NONE) return;
   gather_levels (m, pool, lev);
   if (m->mb_type == LH264_MB_IPCM) {            /* decode_slice.cpp:3213-3263: samples copied at parse time */
@@ -538,18 +558,18 @@ static void recon_mb (const ora_picture* cur, const ora_picture* slots, int n_sl
     inter_pred (cur, slots, n_slots, sl, m, mbx, mby);
     if (m->cbp == 0) return;                    /* WelsMbInterPrediction only, decode_slice.cpp:362-364 */
     if (t8) {
-      for (int q = 0; q < 4; q++) { dequant_8x8 (c, lev + 64 * q, m->qp_y); idct8x8_add (py + kBlkY[4 * q] * w + kBlkX[4 * q], w, c); }
+      for (int q = 0; q < 4; q++) { dequant_8x8 (c, lev + 64 * q, m->qp_y, sc, 0); idct8x8_add (py + kBlkY[4 * q] * w + kBlkX[4 * q], w, c); }
     } else {
-      for (int z = 0; z < 16; z++) { dequant_ac4x4 (c, lev + 16 * z, m->qp_y, 0); idct4x4_add (py + kBlkY[z] * w + kBlkX[z], w, c); }
+      for (int z = 0; z < 16; z++) { dequant_ac4x4 (c, lev + 16 * z, m->qp_y, 0, sc, 3); idct4x4_add (py + kBlkY[z] * w + kBlkX[z], w, c); }
     }
-    residual_chroma (cur, m, lev, mbx, mby);
+    residual_chroma (cur, m, lev, mbx, mby, sc);
     return;
   }
   /* intra: WelsMbIntraPredictionConstruction, decode_slice.cpp:313-334 */
   if (m->mb_type == LH264_MB_I16x16) {          /* RecI16x16Mb, rec_mb.cpp:179-219 */
     int16_t blk[256];
-    for (int z = 0; z < 16; z++) { blk[16 * z] = lev[16 * z]; dequant_ac4x4 (blk + 16 * z, lev + 16 * z, m->qp_y, 1); }
-    luma_dc_dequant_idct (blk, m->qp_y);
+    for (int z = 0; z < 16; z++) { blk[16 * z] = lev[16 * z]; dequant_ac4x4 (blk + 16 * z, lev + 16 * z, m->qp_y, 1, sc, 0); }
+    luma_dc_dequant_idct (blk, m->qp_y, sc);
     pred16x16 (py, w, m->i16_mode);
     for (int z = 0; z < 16; z++) idct4x4_add (py + kBlkY[z] * w + kBlkX[z], w, blk + 16 * z);
   } else if (m->mb_type == LH264_MB_I8x8) {     /* RecI8x8Luma, rec_mb.cpp:70-115 */
@@ -558,20 +578,20 @@ static void recon_mb (const ora_picture* cur, const ora_picture* slots, int n_sl
     for (int q = 0; q < 4; q++) {
       uint8_t* d = py + kBlkY[4 * q] * w + kBlkX[4 * q];
       pred8x8l (d, w, m->intra_mode[4 * q], tl[q], tr[q]);
-      dequant_8x8 (c, lev + 64 * q, m->qp_y);
+      dequant_8x8 (c, lev + 64 * q, m->qp_y, sc, 1);
       idct8x8_add (d, w, c);
     }
   } else {                                      /* RecI4x4Luma, rec_mb.cpp:124-158 */
     for (int z = 0; z < 16; z++) {
       uint8_t* d = py + kBlkY[z] * w + kBlkX[z];
       pred4x4 (d, w, m->intra_mode[z]);
-      dequant_ac4x4 (c, lev + 16 * z, m->qp_y, 0);
+      dequant_ac4x4 (c, lev + 16 * z, m->qp_y, 0, sc, 0);
       idct4x4_add (d, w, c);
     }
   }
   pred_chroma (cur->plane[1] + (size_t)mby * 8 * cw + mbx * 8, cw, m->chroma_mode);
   pred_chroma (cur->plane[2] + (size_t)mby * 8 * cw + mbx * 8, cw, m->chroma_mode);
-  { int cc = m->cbp >> 4; if (cc == 1 || cc == 2) residual_chroma (cur, m, lev, mbx, mby); }
+  { int cc = m->cbp >> 4; if (cc == 1 || cc == 2) residual_chroma (cur, m, lev, mbx, mby, sc); }
 }
 
 /* ------------------------------------------------------------------------------------------------

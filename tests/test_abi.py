@@ -65,7 +65,7 @@ def test_runtime_entry_points_are_exported():
 
 def test_record_layouts():
     assert MB_REC.itemsize == 128 and MODEL_MB.itemsize == 128 and MODEL_SLICE.itemsize == 20
-    assert SLICE_REC.itemsize == 16 + 2 * 16 * 7
+    assert SLICE_REC.itemsize == 16 + 2 * 16 * 7 + 240          # + scaling lists (flags, 6 x 16, 2 x 64)
 
 
 def test_no_cpu_fallback():

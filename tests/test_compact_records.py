@@ -42,7 +42,7 @@ def test_struct_sizes():
     from losslessh264_b200.build import build_library
 
     lib = C.CDLL(build_library())
-    assert lib.lh264_abi_version() == 2
+    assert lib.lh264_abi_version() == 3
     src = open(os.path.join(ROOT, "include", "lh264_b200.h")).read()
     assert "typedef struct lh264_cmb" in src and "typedef struct lh264_cmm" in src
     # sizes are part of the ABI: checked where the structs are compiled
