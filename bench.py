@@ -397,6 +397,7 @@ def main():
             step_no += 1
 
     def timed(n, recon, model):
+        ctx.join()                                     # code what the steps before left pending: the timed region starts with an empty decision pool
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(tstream)

@@ -202,6 +202,32 @@ struct Decoder::Impl {
   CabacDecoder cab;
   int16_t lev_[384] = {0};               // residual scratch of parse_mb
   bool cabac_on = false, last_dqp_nz = false;
+  // FMO (slice groups, map types 0 and 1 - the ones the reference decodes, fmo.cpp:53-104): slice group of every macroblock of
+  // the picture for the slice being parsed; empty = one slice group, the walk is mb_addr + 1
+  std::vector<uint8_t> fmo_map;
+  void build_fmo_map (const Pps& pps) {
+    fmo_map.clear();
+    if (pps.num_slice_groups < 2) return;
+    fmo_map.assign ((size_t)n_mbs, 0);
+    const int g = pps.num_slice_groups;
+    if (pps.slice_group_map_type == 0) {             // interleaved: runs of run_length[group] macroblocks, group after group
+      int i = 0;
+      while (i < n_mbs)
+        for (int grp = 0; grp < g && i < n_mbs; grp++) {
+          const int run = pps.run_length[grp];
+          for (int j = 0; j < run && i + j < n_mbs; j++) fmo_map[(size_t) (i + j)] = (uint8_t)grp;
+          i += run;
+        }
+    } else                                            // dispersed (8.2.2.2)
+      for (int i = 0; i < n_mbs; i++) fmo_map[(size_t)i] = (uint8_t) (((i % mb_w) + (((i / mb_w) * g) >> 1)) % g);
+  }
+  // next macroblock of the slice: the next one of the same slice group (FmoNextMb, fmo.cpp:308-330); n_mbs = none
+  int next_mb (int a) const {
+    if (fmo_map.empty()) return a + 1;
+    const uint8_t grp = fmo_map[(size_t)a];
+    for (int n = a + 1; n < n_mbs; n++) if (fmo_map[(size_t)n] == grp) return n;
+    return n_mbs;
+  }
   // scaling lists: what the reference's multiplier tables were last built from (see the slice record set-up)
   bool scal_init = false, sps_late_pps = false;
   int scal_ppsid = -1;
@@ -1129,7 +1155,7 @@ int Decoder::Impl::parse_residual_cabac (lh264_mb_rec& m, int mb_addr, int16_t* 
 // ---- slice_data( ) (7.3.4), CABAC ----------------------------------------------------------------------------
 int Decoder::Impl::parse_slice_data_cabac (BitReader& br, Decoder* self) {
   int mb_addr = sh.first_mb;
-  const int first = mb_addr;
+  int n_done = 0;
   qp = sh.slice_qp;
   br.align();                                         // cabac_alignment_one_bit
   cab.init_contexts (sh.slice_type == SLICE_I ? 0 : 1 + sh.cabac_init_idc, sh.slice_qp);
@@ -1167,16 +1193,16 @@ int Decoder::Impl::parse_slice_data_cabac (BitReader& br, Decoder* self) {
       m_cached_qp = mr->luma_qp;
       if (d) m_last_dqp = d;
     }
-    mb_addr++;
+    mb_addr = next_mb (mb_addr); n_done++;
     const bool eos = cab.terminate();                 // end_of_slice_flag
     if (mr && eos) mr->flags |= LH264_MM_STOP_BIT;
     if (eos) break;
   }
   cabac_on = false;
   lh264_slice_rec& sr = slices.back();
-  sr.num_mbs = mb_addr - first;
-  decoded += mb_addr - first;
-  self->stats_.mbs += mb_addr - first;
+  sr.num_mbs = n_done;
+  decoded += n_done;
+  self->stats_.mbs += n_done;
   if (want_model) {
     lh264_model_slice ms;
     memset (&ms, 0, sizeof (ms));
@@ -1199,6 +1225,7 @@ LH264_HOT int Decoder::Impl::parse_slice_data (BitReader& br, Decoder* self) {
   int mb_addr = sh.first_mb;
   qp = sh.slice_qp;
   const int first = mb_addr;
+  int n_done = 0;
   const size_t data_begin = br.pos();
   bool more = true;
   int rc = 0;
@@ -1233,7 +1260,8 @@ LH264_HOT int Decoder::Impl::parse_slice_data (BitReader& br, Decoder* self) {
           if (i + 1 == run) { mr->flags |= LH264_MM_STOP_IN_SKIP; if (!br.more_rbsp_data()) mr->flags |= LH264_MM_STOP_BIT; }
           if (!commit_rec()) { rc = -1; break; }
         }
-        mb_addr++;
+        mb_addr = next_mb (mb_addr); n_done++;
+        if (mb_addr >= n_mbs && i + 1 < run) { rc = -1; break; }      // the run leaves the slice group
       }
       if (rc < 0) break;
       if (run > 0) { more = br.more_rbsp_data(); run_read = false; }
@@ -1252,15 +1280,15 @@ LH264_HOT int Decoder::Impl::parse_slice_data (BitReader& br, Decoder* self) {
       m_cached_qp = mr->luma_qp;
       if (d) m_last_dqp = d;
     }
-    mb_addr++;
+    mb_addr = next_mb (mb_addr); n_done++;
     more = br.more_rbsp_data();
     if (mr && !more) mr->flags |= LH264_MM_STOP_BIT;
     if (mr && !commit_rec()) { rc = -1; break; }
   }
   lh264_slice_rec& sr = slices.back();
-  sr.num_mbs = mb_addr - first;
-  decoded += mb_addr - first;
-  self->stats_.mbs += mb_addr - first;
+  sr.num_mbs = n_done;
+  decoded += n_done;
+  self->stats_.mbs += n_done;
   if (want_model) {
     lh264_model_slice ms;
     memset (&ms, 0, sizeof (ms));
@@ -1352,6 +1380,8 @@ int Decoder::decode (const uint8_t* data, size_t len, unsigned long long timesta
         if (!D.open) { last_err = -31; stats_.errors++; continue; }        // no storage for the picture's records
       } else { D.S = &D.sps[pps.sps_id]; D.P = &D.pps[sh.pps_id]; D.sh = sh; D.ts = timestamp; }   // (a picture carries the time stamp of its last slice's call)
       if (sh.first_mb >= D.n_mbs) { last_err = -1; stats_.errors++; continue; }
+      if (pps.num_slice_groups > 7) { last_err = -4; stats_.errors++; continue; }   // FmoGenerateMbAllocMapType0/1 refuse 8 groups (fmo.cpp:61, :92)
+      D.build_fmo_map (pps);
       D.slice_no = (int)D.slices.size();
       // slice record
       lh264_slice_rec sr;

@@ -292,7 +292,6 @@ int parse_slice_header (BitReader& br, int nal_ref_idc, int nal_type, const Sps*
     sh.disable_deblocking_idc = (int)idc;
     if (sh.disable_deblocking_idc != 1) { sh.alpha_c0_offset = 2 * br.se(); sh.beta_offset = 2 * br.se(); }
   }
-  if (pps.num_slice_groups > 1) return -4;            // FMO: "next" row N3
   if (br.overrun()) return -1;
   sh.header_bits = br.pos();
   return 0;

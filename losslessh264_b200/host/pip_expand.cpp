@@ -70,6 +70,7 @@ bool expand_plan (const uint8_t* def_in, size_t n, ExpandPlan& plan) {
       BitReader br (ext.data() + 1, plen - 1 + 8);
       SliceHeader sh;
       if (parse_slice_header (br, ref_idc, type, sps.data(), pps.data(), sh) < 0) { plan.error = "slice header does not parse"; return false; }
+      if (pps[sh.pps_id].num_slice_groups > 1) { plan.error = "slice groups (FMO): the decompress direction walks macroblocks in raster order"; return false; }
       const Pps& pp = pps[sh.pps_id];
       const Sps& sp = sps[pp.sps_id];
       const uint8_t* rb = ext.data() + 1;

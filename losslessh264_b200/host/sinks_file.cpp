@@ -1,5 +1,6 @@
 // sinks_file.cpp — LhfbSink, see sinks.h.
 #include "sinks.h"
+#include <vector>
 #include <string.h>
 
 namespace lh264host {
@@ -26,18 +27,22 @@ int LhfbSink::submit (const lh264_picture_desc& pic, const DecodedPictureInfo& i
     w32 (0x4246484c); w32 (1);
     w32 (mb_w_); w32 (mb_h_); w32 (pic.cur_slot); w32 (info.frame_num); w32 (info.poc_lsb); w32 (info.idr_pic_id); w32 (info.nal_ref_idc); w32 (info.serial);
     fwrite (&sl, sizeof (sl), 1, f_);
-    w32 (sl.num_mbs);
+    // the slice's macroblocks in address order (with slice groups they are not a contiguous range)
+    std::vector<int> addr;
+    for (int a = sl.first_mb; a < mb_w_ * mb_h_ && (int)addr.size() < sl.num_mbs; a++)
+      if (pic.mbs[a].mb_type != LH264_MB_NONE && pic.mbs[a].slice_idx == s) addr.push_back (a);
+    w32 ((int32_t)addr.size());
     uint32_t lo = 0xffffffffu, hi = 0;
-    for (int i = 0; i < sl.num_mbs; i++) {
-      const lh264_mb_rec& m = pic.mbs[sl.first_mb + i];
+    for (int a : addr) {
+      const lh264_mb_rec& m = pic.mbs[a];
       if (m.coded_mask) { lo = lo < m.coef_off ? lo : m.coef_off; const uint32_t e = m.coef_off + __builtin_popcount (m.coded_mask); hi = hi > e ? hi : e; }
     }
     if (lo == 0xffffffffu) lo = hi = 0;
-    for (int i = 0; i < sl.num_mbs; i++) {
-      lh264_mb_rec m = pic.mbs[sl.first_mb + i];
+    for (int a : addr) {
+      lh264_mb_rec m = pic.mbs[a];
       m.slice_idx = 0;
       if (m.coded_mask) m.coef_off -= lo; else m.coef_off = 0;
-      w32 (sl.first_mb + i);
+      w32 (a);
       fwrite (&m, sizeof (m), 1, f_);
     }
     w32 ((int32_t) (hi - lo));

@@ -788,14 +788,18 @@ int ora_recon_picture (const lh264_picture_desc* pd, int mb_w, int mb_h, ora_pic
   ora_picture* cur = &slots[pd->cur_slot];
   for (int s = 0; s < pd->n_slices; s++) {
     const lh264_slice_rec* sl = &pd->slices[s];
-    int first = sl->first_mb, last = first + sl->num_mbs;
-    if (first < 0 || last > mb_w * mb_h) return LH264_E_INVALID;
-    for (int xy = first; xy < last; xy++)
-      recon_mb (cur, slots, n_slots, sl, &pd->mbs[xy], pd->coefs, xy % mb_w, xy / mb_w);
+    /* the slice's macroblocks in address order; with slice groups (FMO) they are every n-th one, not a range (FmoNextMb,
+     * decode_slice.cpp:173-177) */
+    const int first = sl->first_mb, n = mb_w * mb_h;
+    if (first < 0 || first > n || sl->num_mbs < 0 || sl->num_mbs > n) return LH264_E_INVALID;
+    int done = 0;
+    for (int xy = first; xy < n && done < sl->num_mbs; xy++)
+      if (pd->mbs[xy].mb_type != LH264_MB_NONE && pd->mbs[xy].slice_idx == s) { recon_mb (cur, slots, n_slots, sl, &pd->mbs[xy], pd->coefs, xy % mb_w, xy / mb_w); done++; }
     if (sl->disable_deblocking_idc != 1) {
       dbk_ctx c = { sl, cur };
-      for (int xy = first; xy < last; xy++)
-        if (pd->mbs[xy].mb_type != LH264_MB_NONE) deblock_mb (&c, pd->mbs, mb_w, xy % mb_w, xy / mb_w);
+      done = 0;
+      for (int xy = first; xy < n && done < sl->num_mbs; xy++)
+        if (pd->mbs[xy].mb_type != LH264_MB_NONE && pd->mbs[xy].slice_idx == s) { deblock_mb (&c, pd->mbs, mb_w, xy % mb_w, xy / mb_w); done++; }
     }
   }
   return LH264_OK;

@@ -8,10 +8,10 @@ import subprocess
 
 import pytest
 
-from streams import CABAC, LIB_DIR, REFUSED, STREAM_DIR
+from streams import CABAC, LIB_DIR, PCM_SYNTH, REFUSED, STREAM_DIR
 
 TOOL = os.path.join(LIB_DIR, "lh264_parse_dump")
-PCM = {"CVPCMNL1_SVA_C.264"}          # I_PCM samples are not part of the model records (the reference does not model them either)
+PCM = {"CVPCMNL1_SVA_C.264"} | PCM_SYNTH          # I_PCM samples are not part of the model records (the reference does not model them either)
 NAMES = sorted(n for n in os.listdir(STREAM_DIR) if n.rsplit(".", 1)[-1] in ("264", "jsv", "h264") and n not in CABAC | PCM | REFUSED)
 
 

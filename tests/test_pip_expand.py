@@ -9,11 +9,11 @@ import subprocess
 import pytest
 
 from oracle import oracle
-from streams import LIB_DIR, STREAM_DIR
+from streams import FMO, LIB_DIR, PCM_SYNTH, STREAM_DIR
 from test_model_oracle import CPU_SET as MODEL_SET, TOOL
 
 # CAVLC and CABAC streams alike (the core re-serialises both); I_PCM macroblocks are not in the model, as in the reference
-CPU_SET = [s for s in MODEL_SET if s != "QCIF_2P_I_allIPCM.264"]
+CPU_SET = [s for s in MODEL_SET if s != "QCIF_2P_I_allIPCM.264" and s not in PCM_SYNTH | FMO]
 from losslessh264_b200.records import read_lhmd
 
 
@@ -59,6 +59,16 @@ def test_truncated_side_stream_is_not_silently_accepted(name, tmp_path, expand_c
     r = subprocess.run([expand_cpu, pip, out], capture_output=True, text=True)
     same = r.returncode == 0 and open(out, "rb").read() == open(os.path.join(STREAM_DIR, name), "rb").read()
     assert not same
+
+
+def test_slice_groups_are_refused_not_mangled(tmp_path, expand_cpu):
+    """The decompress direction walks macroblocks in raster order; a stream with slice groups is refused (the reference's own
+    decompressor aborts on it).  Arbitrary slice order alone is fine: aso_4slices_nopcm is in CPU_SET."""
+    d = str(tmp_path)
+    pip = write_pip_cpu("fmo_dispersed3_2slices_aso_nopcm.264", d)
+    r = subprocess.run([expand_cpu, pip, os.path.join(d, "out.264")], capture_output=True, text=True)
+    assert r.returncode != 0 and "slice groups" in r.stderr
+    assert "aso_4slices_nopcm.264" in CPU_SET
 
 
 def test_cabac_pcm_stream_is_refused_like_the_reference(tmp_path, expand_cpu):
