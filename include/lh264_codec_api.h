@@ -33,7 +33,12 @@ typedef enum {
    * reference's h264dec does when its OUTPUT name contains ".pip" (h264dec.cpp:167-169).  Units fed through
    * DecodeFrameNoDelay are then also modelled on the GPU; Uninitialize() (or a SetOption with NULL) writes `path` (the
    * default stream) and `path.<tag>` (one file per arithmetic-coded side stream), compression_stream.cpp:269-287.     */
-  DECODER_OPTION_LH264_PIP_OUTPUT = 1000
+  DECODER_OPTION_LH264_PIP_OUTPUT = 1000,
+  /* A `path` ending in ".pipx" selects the single-file container, written WHILE the stream is compressed: every N units
+   * (SetOption (DECODER_OPTION_LH264_PIP_FLUSH_UNITS, int* N), default 64, 0 = only at the end) the bytes of the default
+   * stream and of every side stream that can no longer change are appended as chunks (format: host/pip_container.h) -
+   * the reference keeps everything in memory until exit (FlushOnClose, h264dec.cpp:105-121).                           */
+  DECODER_OPTION_LH264_PIP_FLUSH_UNITS = 1001
 } DECODER_OPTION;
 
 /* codec_app_def.h:171-180 */

@@ -83,6 +83,7 @@ struct ModelCtx {
   unsigned long long* d_pool_used = nullptr; unsigned int* d_pages_pending = nullptr;   // [2] each
   DevBuf<int> job_index; PinBuf<int> h_index[2]; cudaEvent_t index_copied[2] = {nullptr, nullptr}; int index_cur = 0;
   unsigned long long est_pool_used = 0, last_step_total = 0;
+  unsigned long long max_step_total = 0;    // largest step seen: what a pool half is sized for (code_steps of them, memory permitting)
   unsigned long long pool_step_total = 0;   // the step size the pool was last sized for (model_grow_pool)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float ms_gen = 0, ms_code = 0;
@@ -496,6 +497,7 @@ int model_grow_pool (lh264_ctx* c, ModelCtx* m, unsigned long long step_total) {
   (void)c;
   m->pool_step_total = std::max (m->pool_step_total, step_total);
   const size_t one = (size_t)step_total + (size_t)step_total / 4 + 64;
+  if (m->dec[m->cur].cap >= one * (size_t)m->code_steps) return LH264_OK;      // room for a full window already
   // what the device can spare NOW (other contexts, picture pools and output pages have come and gone since the context was
   // made): both halves together leave a tenth of the device (at least 4 GB) free for output pages and staging
   size_t budget = m->dec_cap_limit;
@@ -547,6 +549,7 @@ static void model_account (ModelCtx* m, MBatch& b) {
   unsigned long long tot = 0;
   for (int i = 0; i < b.n; i++) { tot += b.h_total.p[i]; if (m->streams[b.stream_of[i]].open) m->streams[b.stream_of[i]].decisions += b.h_total.p[i]; }
   m->last_step_total = tot;
+  m->max_step_total = std::max (m->max_step_total, tot);
 }
 
 // Reads back what a launched batch reported (decision totals, capacity verdict); `only` = settle up to and including that
@@ -602,6 +605,10 @@ static int model_run (lh264_ctx* c, ModelCtx* m, MBatch& b) {
   for (int i = 0; i < n; i++) if (!m->streams[b.stream_of[i]].open) return fail (LH264_E_INVALID, "batch names a closed model stream");
   if (!m->d_page_ptrs && (rc = model_grow_arena (c, m, (unsigned int)n * CT_COUNT + 64))) return rc;
   if (!m->dec[m->cur].p && (rc = model_grow_pool (c, m, std::max<unsigned long long> ((unsigned long long)b.total_recs * 96 + 1024, m->last_step_total)))) return rc;   // first guess; model_settle grows it when needed
+  // An empty half that could not hold code_steps steps of the size seen so far is re-made larger (it was sized from an early,
+  // smaller step): a window cut short by the pool costs a coder launch that is as long as a full one (the longest picture sets
+  // its time), so short windows halve the coder's throughput.
+  if (m->pend_steps == 0 && m->dec[m->cur].p && m->max_step_total > 0 && (rc = model_grow_pool (c, m, m->max_step_total))) return rc;
   // a step about as large as the last one would not fit behind the pending ones: code those first (saves a skip + re-run)
   if (m->pend_steps > 0 && m->est_pool_used + m->last_step_total + m->last_step_total / 2 + 64 > m->dec[m->cur].cap && (rc = model_flush_coder (c, m))) return rc;
   m->last_resident = b.resident;

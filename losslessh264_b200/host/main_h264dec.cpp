@@ -89,9 +89,8 @@ int main (int argc, char** argv) {
   const bool compress = strstr (argv[2], ".pip") != nullptr;             // h264dec.cpp:167-169
   if (!compress && strstr (argv[1], ".pip")) return decompress (argv[1], argv[2]);                        // h264dec.cpp:170-173
   const char* yuv_path = compress ? (argc > 3 ? argv[3] : "/dev/null") : argv[2];
-  // `.pipx`: the file set is written next to the archive first, packed, and removed
-  const bool archive = compress && lh264host::is_pip_archive_name (argv[2]);
-  const std::string set_path = archive ? std::string (argv[2]) + ".tmp.pip" : std::string (argv[2]);
+  // `.pipx`: the decoder object writes the single-file container itself, chunk by chunk while it compresses
+  const std::string set_path = std::string (argv[2]);
   FILE* fi = fopen (argv[1], "rb");
   if (!fi) { perror (argv[1]); return 1; }
   std::vector<unsigned char> buf;
@@ -114,6 +113,7 @@ int main (int argc, char** argv) {
   if (dec->Initialize (&param)) { fprintf (stderr, "Initialize failed (no CUDA device? this build has no CPU fallback)\n"); return 1; }
   { int ec = ERROR_CON_SLICE_MV_COPY_CROSS_IDR_FREEZE_RES_CHANGE; dec->SetOption (DECODER_OPTION_ERROR_CON_IDC, &ec); }   // h264dec.cpp:156-157
   if (compress && dec->SetOption (DECODER_OPTION_LH264_PIP_OUTPUT, (void*)set_path.c_str())) { fprintf (stderr, "cannot switch the recompressor on\n"); return 1; }
+  if (const char* e = getenv ("LH264_PIP_FLUSH_UNITS")) { int n = atoi (e); dec->SetOption (DECODER_OPTION_LH264_PIP_FLUSH_UNITS, &n); }
 
   int frames = 0, width = 0, height = 0;
   double secs = 0;
@@ -148,12 +148,5 @@ int main (int argc, char** argv) {
   fprintf (stderr, "-------------------------------------------------------\n");
   dec->Uninitialize();
   WelsDestroyDecoder (dec);
-  if (archive) {
-    lh264host::PipFileSet fs;
-    const bool ok = lh264host::pip_set_read (set_path.c_str(), fs) && lh264host::pip_archive_write (argv[2], fs);
-    remove (set_path.c_str());
-    for (int t = 0; t < LH264_NUM_TAGS; t++) remove ((set_path + "." + std::to_string (t)).c_str());
-    if (!ok) { fprintf (stderr, "cannot write %s\n", argv[2]); return 1; }
-  }
   return 0;
 }

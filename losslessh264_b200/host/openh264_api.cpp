@@ -75,7 +75,16 @@ class CLh264Decoder : public ISVCDecoder {
       pip_path_ = (const char*)opt;
       pip_ = new (std::nothrow) PipBoilerplate();
       dec_->enable_model (true);
+      // `.pipx`: the single-file form, written while the stream is being compressed (see flush_chunks)
+      streaming_ = is_pip_archive_name (pip_path_.c_str());
+      def_sent_ = 0; tag_sent_.assign (LH264_NUM_TAGS, 0); since_flush_ = 0;
+      if (streaming_ && !arc_.open (pip_path_.c_str())) { delete pip_; pip_ = nullptr; return cmUnkonwReason; }
       return pip_ ? cmResultSuccess : cmMallocMemeError;
+    }
+    if (id == DECODER_OPTION_LH264_PIP_FLUSH_UNITS) {  // extension: units between two flushes of a `.pipx` (0: only at the end)
+      if (!opt) return cmInitParaError;
+      flush_units_ = * (int*)opt < 0 ? 0 : * (int*)opt;
+      return cmResultSuccess;
     }
     if (!opt) return cmInitParaError;
     switch (id) {
@@ -215,6 +224,7 @@ class CLh264Decoder : public ISVCDecoder {
     const bool slice_here = src && len > 0 && dec_->last_slice().decoded;
     const int slice_frame_num = dec_->last_slice().frame_num;
     st |= (int)decode_one (nullptr, 0, ppDst, info, true);
+    if (pip_ && streaming_ && flush_units_ > 0 && ++since_flush_ >= flush_units_) { since_flush_ = 0; flush_chunks (false); }
     // the flush half decodes what the unit brought at once: a slice unit reports its access unit even while the picture waits for
     // more slices
     if (slice_here && last_vcl_ != FEEDBACK_VCL_NAL) { last_vcl_ = FEEDBACK_VCL_NAL; tid_ = 0; last_frame_num_ = slice_frame_num; }
@@ -226,11 +236,40 @@ class CLh264Decoder : public ISVCDecoder {
     return (DECODING_STATE)st;
   }
 
+  // Streaming flush (the reference writes everything at exit, FlushOnClose h264dec.cpp:105-121): appends to the
+  // `.pipx` what has become FINAL since the last call.  The default stream only grows.  A tag stream is the output of a VP8 bool
+  // coder, whose pending carry can still add one to the number formed by the bytes written so far - that changes the last byte
+  // that is not 0xff and the 0xff bytes behind it, nothing in front of it - so everything in front of the last non-0xff byte
+  // goes out and the rest waits for the next call (`final`: the coders have been ended, everything goes).
+  bool flush_chunks (bool final) {
+    bool ok = true;
+    const std::vector<uint8_t>& d = final ? pip_->finish() : pip_->so_far();
+    if (d.size() > def_sent_) { ok = arc_.chunk (0xffffffffu, d.data() + def_sent_, d.size() - def_sent_) && ok; def_sent_ = d.size(); }
+    if (!final && sink_->sync() != LH264_OK) return false;        // the deferred coder has coded every picture submitted so far
+    std::vector<uint8_t> b;
+    for (int tag = 1; tag < LH264_NUM_TAGS && ok; tag++) {
+      if (sink_->model_tag_bytes_from (tag, tag_sent_[tag], b) != LH264_OK) return false;
+      size_t n = b.size();
+      if (!final) {
+        while (n > 0 && b[n - 1] == 0xff) n--;          // trailing 0xff bytes and ...
+        if (n > 0) n--;                                 // ... the byte in front of them may still change
+      }
+      if (n > 0) { ok = arc_.chunk ((uint32_t)tag, b.data(), n) && ok; tag_sent_[tag] += n; }
+    }
+    return ok;
+  }
+
   // writes the `.pip` file set: default stream + one file per tag that has a stream (MultiFileWriter, h264dec.cpp:79-104)
   bool write_pip() {
     if (!pip_ || !sink_ || !dec_) return true;
     dec_->flush();
     bool ok = sink_->model_finish() == LH264_OK;
+    if (streaming_) {
+      ok = flush_chunks (true) && ok;
+      ok = arc_.close() && ok;
+      delete pip_; pip_ = nullptr;
+      return ok;
+    }
     const std::vector<uint8_t>& d = pip_->finish();
     FILE* f = fopen (pip_path_.c_str(), "wb");
     if (f) { fwrite (d.data(), 1, d.size(), f); fclose (f); } else ok = false;
@@ -250,6 +289,11 @@ class CLh264Decoder : public ISVCDecoder {
   GpuSink* sink_ = nullptr;
   PipBoilerplate* pip_ = nullptr;
   std::string pip_path_;
+  bool streaming_ = false;                        // `.pipx` output: chunks go out every flush_units_ units
+  PipStreamWriter arc_;
+  size_t def_sent_ = 0;
+  std::vector<size_t> tag_sent_;
+  int flush_units_ = 64, since_flush_ = 0;
   std::deque<DecodedPictureInfo> queue_;
   std::vector<DecodedPictureInfo> held_;          // complete pictures the reference would only decode at the next call
   std::map<int, std::vector<unsigned char> > saved_;   // ... and their samples (by DecodedPictureInfo::serial)

@@ -124,9 +124,56 @@ bool pip_archive_write (const char* archive_path, const PipFileSet& in) {
   for (int t = 0; t < (int)in.tags.size(); t++) if (in.present[t]) o.insert (o.end(), in.tags[t].begin(), in.tags[t].end());
   return spill_file (archive_path, o);
 }
+bool PipStreamWriter::open (const char* path) {
+  if (f_) fclose (f_);
+  f_ = fopen (path, "wb");
+  if (!f_) return false;
+  std::vector<uint8_t> h = {'L', 'H', 'P', 'X'};
+  put32 (h, 2);
+  return fwrite (h.data(), 1, h.size(), f_) == h.size();
+}
+bool PipStreamWriter::chunk (uint32_t tag, const uint8_t* p, size_t n) {
+  if (!f_) return false;
+  while (n > 0) {                                      // (a chunk length is 32 bits)
+    const size_t part = n > 0x40000000u ? 0x40000000u : n;
+    std::vector<uint8_t> h;
+    put32 (h, tag); put32 (h, (uint32_t)part);
+    if (fwrite (h.data(), 1, h.size(), f_) != h.size() || fwrite (p, 1, part, f_) != part) return false;
+    p += part; n -= part;
+  }
+  return fflush (f_) == 0;
+}
+bool PipStreamWriter::close() {
+  if (!f_) return false;
+  std::vector<uint8_t> h;
+  put32 (h, 0xfffffffeu); put32 (h, 0);
+  const bool ok = fwrite (h.data(), 1, h.size(), f_) == h.size();
+  const bool ok2 = fclose (f_) == 0;
+  f_ = nullptr;
+  return ok && ok2;
+}
 bool pip_archive_read (const char* archive_path, PipFileSet& out) {
   std::vector<uint8_t> b;
-  if (!slurp_file (archive_path, b) || b.size() < 12 || memcmp (b.data(), "LHPX", 4) || get_le (b.data() + 4, 4) != 1) return false;
+  if (!slurp_file (archive_path, b) || b.size() < 12 || memcmp (b.data(), "LHPX", 4)) return false;
+  if (get_le (b.data() + 4, 4) == 2) {                 // chunked form (PipStreamWriter)
+    out.tags.assign (kNumTags, std::vector<uint8_t>());
+    out.present.assign (kNumTags, false);
+    out.def.clear();
+    size_t at = 8;
+    for (;;) {
+      if (b.size() - at < 8) return false;             // no closing chunk: the writer was cut off
+      const uint32_t tag = (uint32_t)get_le (b.data() + at, 4);
+      const uint64_t len = get_le (b.data() + at + 4, 4);
+      at += 8;
+      if (tag == 0xfffffffeu) return len == 0 && at == b.size();
+      if (len > b.size() - at) return false;
+      if (tag == 0xffffffffu) out.def.insert (out.def.end(), b.begin() + at, b.begin() + at + len);
+      else if (tag < (uint32_t)kNumTags) { out.present[tag] = true; out.tags[tag].insert (out.tags[tag].end(), b.begin() + at, b.begin() + at + len); }
+      else return false;
+      at += len;
+    }
+  }
+  if (get_le (b.data() + 4, 4) != 1) return false;
   const uint64_t n = get_le (b.data() + 8, 4);
   if (n < 1 || n > (uint64_t)kNumTags + 1 || b.size() < 12 + 12 * n) return false;
   out.tags.assign (kNumTags, std::vector<uint8_t>());

@@ -16,6 +16,7 @@
 // Host code: byte shuffling that follows the parse, not a hot path.
 #pragma once
 #include <stdint.h>
+#include <stdio.h>
 #include <stddef.h>
 #include <string.h>
 #include <vector>
@@ -58,6 +59,8 @@ class PipBoilerplate {
   // the flush half: slice header bits and stop bit of the slice decoded from this unit, then stopEscape
   void unit_end (const UnitSliceInfo& s);
   const std::vector<uint8_t>& finish() { def_.pad_to_byte(); return def_.bytes(); }
+  // the bytes written so far: the buffer only ever grows, so any prefix handed out stays valid (streaming flush)
+  const std::vector<uint8_t>& so_far() const { return def_.bytes(); }
  private:
   DefaultStream def_;
 };
@@ -75,6 +78,20 @@ struct PipFileSet {
 bool pip_set_read (const char* pip_path, PipFileSet& out);            // x.pip + x.pip.<tag>
 bool pip_set_write (const char* pip_path, const PipFileSet& in);
 bool pip_archive_read (const char* archive_path, PipFileSet& out);
+// Version 2 of the archive, written WHILE the stream is being compressed (streaming flush instead of the reference's exit-time
+// FlushOnClose, h264dec.cpp:105-121): "LHPX", u32 version (2), then chunks { u32 tag (0xffffffff = default stream), u32 length,
+// payload } in the order they became final, closed by the chunk { 0xfffffffe, 0 }.  The payloads of one tag, concatenated in file
+// order, are that tag's file of the set; an archive without the closing chunk is a stream that was cut off (refused).
+class PipStreamWriter {
+ public:
+  bool open (const char* path);
+  bool chunk (uint32_t tag, const uint8_t* p, size_t n);
+  bool close();                           // writes the closing chunk
+  bool is_open() const { return f_ != nullptr; }
+  ~PipStreamWriter() { if (f_) fclose (f_); }
+ private:
+  FILE* f_ = nullptr;
+};
 bool pip_archive_write (const char* archive_path, const PipFileSet& in);
 inline bool is_pip_archive_name (const char* path) { const char* d = strrchr (path, '.'); return d && !strcmp (d, ".pipx"); }
 

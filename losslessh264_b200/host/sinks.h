@@ -41,6 +41,8 @@ class GpuSink : public PictureSink {
   int submit_model (const lh264_model_picture& pic, const DecodedPictureInfo& info) override;
   // ends the model's tag streams; bytes of one `.pip.<tag>` side stream (empty = the tag has no file)
   int model_finish();
+  int sync();                              // everything submitted so far is done (deferred coding included)
+  int model_tag_bytes_from (int tag, size_t offset, std::vector<uint8_t>& out);   // the bytes of a tag stream from `offset` on
   int model_tag_bytes (int tag, std::vector<uint8_t>& out);
   // cropped I420 of a decoded picture into host memory (synchronous)
   int read (const DecodedPictureInfo& info, uint8_t* y, int stride_y, uint8_t* u, uint8_t* v, int stride_c);

@@ -49,6 +49,17 @@ int GpuSink::submit_model (const lh264_model_picture& pic, const DecodedPictureI
   p.model_stream = model_;
   return lh264_model_submit (ctx_, &p, 1);
 }
+int GpuSink::sync() { return ctx_ ? lh264_sync (ctx_) : LH264_OK; }
+int GpuSink::model_tag_bytes_from (int tag, size_t offset, std::vector<uint8_t>& out) {
+  out.clear();
+  if (!ctx_ || model_ < 0) return LH264_OK;
+  const long long n = lh264_model_read (ctx_, model_, tag, nullptr, 0, 0);
+  if (n < 0) return (int)n;
+  if ((size_t)n <= offset) return LH264_OK;
+  out.resize ((size_t)n - offset);
+  const long long m = lh264_model_read (ctx_, model_, tag, out.data(), offset, out.size());
+  return m < 0 ? (int)m : LH264_OK;
+}
 int GpuSink::model_finish() { return ctx_ && model_ >= 0 ? lh264_model_finish (ctx_, model_) : LH264_OK; }
 int GpuSink::model_tag_bytes (int tag, std::vector<uint8_t>& out) {
   out.clear();
