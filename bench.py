@@ -415,6 +415,11 @@ def main():
         ms = timed(K, True, True)
         launches = ctx.kernel_launches() - l0
         sampler.stop_flag = True
+        repeats = []
+        if os.environ.get("LH264_BENCH_REPEATS"):       # diagnosis: the same K steps again (not the reported figure)
+            for _ in range(int(os.environ["LH264_BENCH_REPEATS"])):
+                step_no = 0
+                repeats.append(round(timed(K, True, True) / K, 3))
         step_no = 0
         ms_dec = timed(K, True, False)                 # reconstruction alone (decode without the recompression model)
         step_no = 0
@@ -466,6 +471,8 @@ def main():
         "roofline": roofline,
         "gpu_launches": int(launches), "clocks": sampler.summary(),
     }
+    if repeats:
+        line["repeat_ms_per_step"] = repeats
     mb_per_frame = stream_bytes / n_frames / 1e6
     if args.only_resident:
         if rank == 0:

@@ -83,7 +83,9 @@ struct ModelCtx {
   unsigned long long* d_pool_used = nullptr; unsigned int* d_pages_pending = nullptr;   // [2] each
   DevBuf<int> job_index; PinBuf<int> h_index[2]; cudaEvent_t index_copied[2] = {nullptr, nullptr}; int index_cur = 0;
   unsigned long long est_pool_used = 0, last_step_total = 0;
-  unsigned long long max_step_total = 0;    // largest step seen: what a pool half is sized for (code_steps of them, memory permitting)
+  unsigned long long max_step_total = 0;
+  // LH264_STATS=1: one line per coder launch / pool change on stderr (how long the windows are is what sets the coder's cost)
+  bool stats = false; unsigned long long n_flush = 0, n_grow = 0, n_redo = 0;    // largest step seen: what a pool half is sized for (code_steps of them, memory permitting)
   unsigned long long pool_step_total = 0;   // the step size the pool was last sized for (model_grow_pool)
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   float ms_gen = 0, ms_code = 0;
@@ -95,9 +97,9 @@ struct ModelCtx {
 };
 
 constexpr unsigned int SEG_PAGES = 2048;         // 32 MB arena segments
-constexpr size_t MAX_ARENA_PAGES = 1u << 20;     // 16 GB of output pages (grown in segments on demand; the table of page pointers is 8 MB)
+constexpr size_t MAX_ARENA_PAGES = 1u << 21;     // 32 GB of output pages (grown in segments on demand; the table of page pointers is 16 MB)
 
-int model_grow_arena (lh264_ctx* c, ModelCtx* m, unsigned int need_pages);
+int model_grow_arena (lh264_ctx* c, ModelCtx* m, unsigned int need_pages, unsigned int wish_pages = 0);
 int model_grow_pool (lh264_ctx* c, ModelCtx* m, unsigned long long step_total);
 
 } // namespace
@@ -171,6 +173,7 @@ static ModelCtx* model_ctx (lh264_ctx* c) {
     cudaEventCreateWithFlags (&m->recon_idle, cudaEventDisableTiming);
     for (int k = 0; k < 2; k++) { cudaEventCreateWithFlags (&m->index_copied[k], cudaEventDisableTiming); cudaEventCreateWithFlags (&m->coder_done[k], cudaEventDisableTiming); }
     if (const char* e = getenv ("LH264_CODE_EXCLUSIVE")) m->exclusive_env = atoi (e);
+    if (const char* e = getenv ("LH264_STATS")) m->stats = atoi (e) != 0;
     if (const char* e = getenv ("LH264_CODE_STEPS")) m->code_steps = std::max (1, std::min (atoi (e), 64));
     {
       size_t free_b = 0, total_b = 0;
@@ -220,17 +223,20 @@ static void model_destroy (lh264_ctx* c) {
 }
 
 namespace {
-int model_grow_arena (lh264_ctx* c, ModelCtx* m, unsigned int need_pages) {
+int model_grow_arena (lh264_ctx* c, ModelCtx* m, unsigned int need_pages, unsigned int wish_pages) {
   if (!m->d_page_ptrs) {
     CK (cudaMalloc (&m->d_page_ptrs, MAX_ARENA_PAGES * sizeof (uint8_t*)));
     CK (cudaMalloc (&m->d_next, sizeof (unsigned int)));
     CK (cudaMemsetAsync (m->d_next, 0, sizeof (unsigned int), m->stream));
   }
   bool pool_released = false;
-  while (m->n_pages < need_pages) {
-    if (m->n_pages + SEG_PAGES > MAX_ARENA_PAGES) return fail (LH264_E_NOMEM, "model output arena exhausted");
+  // need_pages: what the step cannot do without; wish_pages: room for a whole window of promises (given up when memory is short)
+  const unsigned int target = std::max (need_pages, wish_pages);
+  while (m->n_pages < target) {
+    if (m->n_pages + SEG_PAGES > MAX_ARENA_PAGES) { if (m->n_pages >= need_pages) break; return fail (LH264_E_NOMEM, "model output arena exhausted"); }
     uint8_t* seg = nullptr;
     cudaError_t e = cudaMalloc (&seg, (size_t)SEG_PAGES * PAGE_SIZE);
+    if (e == cudaErrorMemoryAllocation && m->n_pages >= need_pages) { cudaGetLastError(); break; }
     if (e == cudaErrorMemoryAllocation && !pool_released && m->pend_steps == 0 && (m->dec[0].p || m->dec[1].p)) {
       // output pages are a need, the decision pool's room for deferral is a wish: with no step waiting in the pool, hand the
       // pool's memory back, take the pages, and let the pool come back as large as what is left allows (model_grow_pool)
@@ -398,6 +404,8 @@ static int model_flush_coder (lh264_ctx* c, ModelCtx* m) {
   const int T = m->pend_steps;
   if (T == 0) return LH264_OK;
   const int h = m->cur;
+  m->n_flush++;
+  if (m->stats) fprintf (stderr, "lh264 stats: coder launch %llu: %d steps, half %d (cap %zu M, est used %llu M, last step %llu M)\n", m->n_flush, T, h, m->dec[h].cap >> 20, m->est_pool_used >> 20, m->last_step_total >> 20);
   {
     const int mode = m->partitioned ? 0 : (m->exclusive_env >= 0 ? m->exclusive_env : (m->last_resident ? 2 : 0));
     m->exclusive = mode >= 1; m->exclusive_gen = mode >= 2;
@@ -514,7 +522,8 @@ int model_grow_pool (lh264_ctx* c, ModelCtx* m, unsigned long long step_total) {
   DevBuf<uint32_t>& dec = m->dec[m->cur];
   if (want <= dec.cap) return LH264_OK;
   CK (cudaStreamSynchronize (m->stream)); CK (cudaStreamSynchronize (m->code_stream));
-  if (getenv ("LH264_DEBUG")) fprintf (stderr, "lh264: decision pool half %d: %zu -> %zu M decisions (step %llu M, budget %zu M)\n", m->cur, dec.cap >> 20, want >> 20, step_total >> 20, budget >> 20);
+  m->n_grow++;
+  if (m->stats || getenv ("LH264_DEBUG")) fprintf (stderr, "lh264: decision pool half %d: %zu -> %zu M decisions (step %llu M, budget %zu M)\n", m->cur, dec.cap >> 20, want >> 20, step_total >> 20, budget >> 20);
   // room for code_steps steps is a wish, room for one step a need: halve the wish until the device has it
   for (;;) {
     if (dec.reserve (want) == cudaSuccess) return LH264_OK;
@@ -525,6 +534,35 @@ int model_grow_pool (lh264_ctx* c, ModelCtx* m, unsigned long long step_total) {
 }
 } // namespace
 } // extern "C++"
+
+// Output pages are PROMISED to a step when it is generated (worst case: 7 bits per decision plus a page per tag and picture) and
+// the promise is released when the coder has run, so a window of code_steps pending steps needs code_steps promises at once.
+// Growing by one or two steps' worth at a time cut every window short until the arena had crept up to that size (fifteen
+// re-runs and as many short coder launches at 1024 streams): ask for the whole window the first time a step does not fit.
+static unsigned int model_arena_want (const ModelCtx* m, unsigned int in_use, unsigned int needed) {
+  const unsigned long long must = (unsigned long long)in_use + 2ull * needed;
+  const unsigned long long window = (unsigned long long)in_use + (unsigned long long)std::max (2, m->code_steps + 1) * needed;
+  const unsigned long long room = MAX_ARENA_PAGES - SEG_PAGES;                     // (segments are added whole)
+  return (unsigned int)std::max (must, std::min (window, (unsigned long long)room));
+}
+
+// A step skipped itself because the decision pool or the promised output pages did not fit; the pending steps have been handed
+// to the coder (model_flush_coder).  Pool and arena are made large enough for it - and, memory permitting, for a whole window.
+static int model_make_room (lh264_ctx* c, ModelCtx* m, const BatchCtl& ctl) {
+  int rc = model_grow_pool (c, m, ctl.total);
+  if (rc) return rc;
+  unsigned int in_use = ctl.pages_in_use;
+  if ((unsigned long long)in_use + 2ull * ctl.pages_needed > MAX_ARENA_PAGES - SEG_PAGES) {
+    // the arena cannot grow that far: the promises counted in `in_use` are released as the coder runs, so wait for it and count
+    // the pages that really hold output
+    CK (cudaStreamSynchronize (m->code_stream));
+    unsigned int used = 0;
+    CK (cudaMemcpyAsync (&used, m->d_next, sizeof (used), cudaMemcpyDeviceToHost, m->stream));
+    CK (cudaStreamSynchronize (m->stream));
+    in_use = used;
+  }
+  return model_grow_arena (c, m, in_use + 2 * ctl.pages_needed, model_arena_want (m, in_use, ctl.pages_needed));
+}
 
 // blocking: runs a batch to completion, growing the decision list / output arena until it fits
 static int model_complete (lh264_ctx* c, ModelCtx* m, MBatch& b, bool head) {
@@ -539,8 +577,7 @@ static int model_complete (lh264_ctx* c, ModelCtx* m, MBatch& b, bool head) {
     head = false;                                   // frame / count / scan did run: the batch itself was the one that did not fit
     CK (cudaMemsetAsync (m->d_poison, 0, sizeof (unsigned int), m->stream));
     if ((rc = model_flush_coder (c, m))) return rc;  // empties the pool (the step that skipped left no jobs)
-    if ((rc = model_grow_pool (c, m, ctl.total))) return rc;
-    if ((rc = model_grow_arena (c, m, ctl.pages_in_use + 2 * ctl.pages_needed))) return rc;
+    if ((rc = model_make_room (c, m, ctl))) return rc;
   }
   return fail (LH264_E_NOMEM, "model batch does not fit after growing its buffers");
 }
@@ -567,6 +604,9 @@ static int model_settle_batch (lh264_ctx* c, ModelCtx* m, MBatch* only) {
     if (b.h_ctl.p->skip) {
       CK (cudaStreamSynchronize (m->stream));       // the later batches have skipped themselves too by now
       std::vector<MBatch*> redo = m->inflight;
+      m->n_redo++;
+      if (m->stats) fprintf (stderr, "lh264 stats: arena %u pages; ", m->n_pages);
+      if (m->stats) fprintf (stderr, "lh264 stats: a step did not fit (skip %d, total %llu M): %zu step(s) run again\n", (int)b.h_ctl.p->skip, (unsigned long long)b.h_ctl.p->total >> 20, redo.size());
       m->inflight.clear();
       bool head = b.h_ctl.p->skip == 2;             // 2 cannot be first in the list, but be safe
       CK (cudaMemsetAsync (m->d_poison, 0, sizeof (unsigned int), m->stream));
@@ -574,8 +614,7 @@ static int model_settle_batch (lh264_ctx* c, ModelCtx* m, MBatch* only) {
         const BatchCtl ctl = *b.h_ctl.p;
         int rc = model_flush_coder (c, m);           // the steps generated before it are coded; the pool is empty again
         if (rc) return rc;
-        if ((rc = model_grow_pool (c, m, ctl.total))) return rc;
-        if ((rc = model_grow_arena (c, m, ctl.pages_in_use + 2 * ctl.pages_needed))) return rc;
+        if ((rc = model_make_room (c, m, ctl))) return rc;
       }
       for (MBatch* r : redo) {
         int rc = model_complete (c, m, *r, head);

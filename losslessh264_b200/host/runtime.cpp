@@ -325,6 +325,7 @@ struct Pipeline {
   int rc = 0;
   long pictures = 0;
   double t_wait_parse = 0, t_wait_gpu = 0, t_end = 0, t_first = 0, t_open = 0;
+  double t_submit = 0, t_read = 0, t_desc = 0;     // LH264_STATS: where the submit thread's own time goes
   long first_pictures = 0;
   size_t h2d = 0, d2h = 0;
   unsigned long long launches = 0;
@@ -571,7 +572,9 @@ void pipeline_main (Pipeline* P) {
       // ---- the device ----
       static const bool parse_only = getenv ("LH264_RT_PARSE_ONLY") != nullptr;   // diagnostic: how fast the parse threads alone are
       const int sflags = (want_yuv ? LH264_COMPACT_RECON : 0) | (any_model ? LH264_COMPACT_MODEL : 0);
+      const double ts0 = now();
       if (!parse_only && sflags && lh264_submit_compact (ctx, cdescs.data(), (int)cdescs.size(), sflags) != LH264_OK) FAIL ("lh264_submit_compact");
+      P->t_submit += now() - ts0;
       if (want_yuv && !parse_only) {
         if (same_geometry) {
           const size_t per = (size_t)out_w * out_h + 2 * (size_t) ((out_w + 1) / 2) * ((out_h + 1) / 2);
@@ -587,8 +590,10 @@ void pipeline_main (Pipeline* P) {
             P->out_pin[oi] = pinned_cache().get (per * step.size(), &P->out_cap[oi]);
             if (!P->out_pin[oi]) { P->out_cap[oi] = 0; rt->fail ("cannot allocate pinned output memory"); P->rc = LH264_E_NOMEM; goto done; }
           }
+          const double tr0 = now();
           if (lh264_pictures_read_packed (ctx, rd_streams.data(), rd_slots.data(), (int)step.size(), crop_x, crop_y, out_w, out_h, P->out_pin[oi], P->out_cap[oi], 0) != LH264_OK)
             FAIL ("lh264_pictures_read_packed");
+          P->t_read += now() - tr0;
           P->d2h += per * step.size();
           P->out_issued++;
           {
@@ -631,6 +636,7 @@ void pipeline_main (Pipeline* P) {
   if (lh264_sync (ctx) != LH264_OK) FAIL ("lh264_sync");
 done:
 #undef FAIL
+  if (getenv ("LH264_STATS")) fprintf (stderr, "lh264 stats: submit thread: lh264_submit_compact %.3f s, lh264_pictures_read_packed %.3f s, waiting for parse %.3f s, for the device %.3f s, opening streams %.3f s\n", P->t_submit, P->t_read, P->t_wait_parse, P->t_wait_gpu, P->t_open);
   drain_output();
   { std::lock_guard<std::mutex> g (P->out_mu); P->out_quit = true; }
   P->out_cv.notify_all();
