@@ -168,8 +168,21 @@ struct Decoder::Impl {
   // the reference holds its output back until the first IDR picture has been decoded (bFreezeOutput under the freeze error
   // concealment modes h264dec selects, decoder_core.cpp:56-217): pictures of a stream whose leading IDR was lost are parsed,
   // modelled and reconstructed, but marked `output = false` for the sink and not handed out
-  bool frozen = true;
-  bool frozen_incomplete = false;        // ... the part of `frozen` that every error concealment mode keeps: behind a picture with missing macroblocks
+  // Error concealment (error_concealment.cpp:43-471, DecodeFrameConstruction decoder_core.cpp:56-217).  `ec_mode` = ERROR_CON_IDC;
+  // `freeze` = bFreezeOutput as h264dec leaves it (Initialize with ERROR_CON_SLICE_COPY clears it, the SetOption that follows
+  // does not set it again): set by the two FREEZE_RES_CHANGE modes when a picture with an error changes the output size, cleared
+  // by a complete error-free IDR picture.  `slot_incomplete` = !bIsComplete per picture slot (concealed, or predicted from such
+  // a picture); `prev_slot` = pPreviousDecodedPictureInDpb.
+  int ec_mode = 7;
+  bool freeze = false;
+  int last_out_w = 0, last_out_h = 0;
+  uint32_t slot_incomplete = 0;
+  int prev_slot = -1;
+  int slot_poc[32];
+  // DecodeFrameNoDelay (what h264dec calls) loses a picture that is only given up - concealed - when the NEXT access unit arrives:
+  // its second DecodeFrame2 clears the output structure of the first (welsDecoderExt.cpp:408-430).  On for users of this class
+  // that stand in for h264dec (lh264_rt_*, lh264_parse_dump); the API layer does the two halves itself and switches it off.
+  bool nodelay_output = true, by_flush = false;
   uint32_t slots_touched = 0;            // picture slots that have been reconstructed into since the stream's storage was made
   bool freeze_output = true;             // Decoder::set_freeze_output
   unsigned long long ts = 0, ts_first = 0;
@@ -485,7 +498,13 @@ struct Decoder::Impl {
   int finish_picture (Decoder* self) {
     if (!open) return 0;
     open = false;
-    if (decoded < n_mbs) { for (int i = 0; i < n_mbs; i++) if (mb_slice[i] < 0) mbs[i].mb_type = LH264_MB_NONE; }
+    const bool all_decoded = decoded >= n_mbs;
+    bool concealed = false;
+    if (!all_decoded) {
+      // ImplementErrorCon runs for a picture that has SOME macroblocks (decoder_core.cpp:2352, :2497: iTotalNumMbRec != 0)
+      if (ec_mode != 0 && decoded > 0 && !slices.empty()) concealed = conceal();
+      if (!concealed) for (int i = 0; i < n_mbs; i++) if (mb_slice[i] < 0) mbs[i].mb_type = LH264_MB_NONE;
+    }
     stream_fence();                                   // the streamed records are visible before anybody is told about them
     lh264_picture_desc d;
     d.stream = 0; d.cur_slot = cur_slot; d.n_slices = (int)slices.size(); d.n_coef_blocks = (int) (coefs.size() / 16);
@@ -495,16 +514,36 @@ struct Decoder::Impl {
     info.crop_x = S->crop_left; info.crop_y = S->crop_top;
     info.width = mb_w * 16 - S->crop_left - S->crop_right; info.height = mb_h * 16 - S->crop_top - S->crop_bottom;
     info.frame_num = sh0.frame_num; info.poc_lsb = sh0.poc_lsb; info.idr_pic_id = sh0.idr_pic_id; info.nal_ref_idc = sh0.nal_ref_idc;
-    info.slot = cur_slot; info.serial = serial++; info.complete = decoded >= n_mbs; info.timestamp = ts; info.timestamp_first = ts_first;
+    info.slot = cur_slot; info.serial = serial++; info.complete = all_decoded; info.timestamp = ts; info.timestamp_first = ts_first;
     info.ref_lost = ref_lost; info.ref_lost_first = ref_lost_first;
     int rc = 0;
-    // ... and freezes it again at a picture with missing macroblocks (no concealment here: the reference's freeze modes do not
-    // hand concealed pictures out either) until the next complete IDR picture
-    if (!info.complete) frozen = frozen_incomplete = true;
-    else if (sh0.idr) frozen = frozen_incomplete = false;
-    // the FREEZE modes also hold back what precedes the stream's first IDR picture; the other modes hand those pictures out
-    // (predicted from the grey stand-in reference)
-    info.output = freeze_output ? !frozen : !frozen_incomplete;
+    // bIsComplete: every macroblock decoded AND every picture it predicts from complete (CheckRefPicturesComplete,
+    // decoder_core.cpp:2529-2565: the reference index of every partition of every inter macroblock)
+    bool ref_incomplete = false;
+    if (slot_incomplete && !sh0.idr)
+      for (int i = 0; i < n_mbs && !ref_incomplete; i++) {
+        const lh264_mb_rec& m = mbs[i];
+        if (mb_slice[i] < 0 || !LH264_MB_IS_INTER (m.mb_type) || (int)m.slice_idx >= (int)slices.size()) continue;
+        const lh264_slice_rec& sl = slices[m.slice_idx];
+        const int nq = (m.mb_type == LH264_MB_P16x16 || m.mb_type == LH264_MB_PSKIP) ? 1 : 4;
+        for (int q = 0; q < nq; q++) if (m.ref_idx[q] >= 0 && ((slot_incomplete >> (sl.ref_slot[m.ref_idx[q] & 15] & 31)) & 1u)) ref_incomplete = true;
+      }
+    const bool pic_error = !all_decoded || ref_incomplete || ref_lost;
+    info.error = pic_error;
+    if (pic_error) slot_incomplete |= 1u << (cur_slot & 31); else slot_incomplete &= ~(1u << (cur_slot & 31));
+    slot_poc[cur_slot & 31] = sh0.poc_lsb;
+    if (all_decoded && sh0.idr && !pic_error) freeze = false;          // complete non-ECed IDR frame done (decoder_core.cpp:163-166)
+    if (!all_decoded && !concealed) info.output = false;               // nothing to hand out (EC disabled, or no macroblock at all)
+    else {
+      const bool res_change = last_out_w != info.width || last_out_h != info.height;
+      last_out_w = info.width; last_out_h = info.height;
+      if (ec_mode == 0) info.output = !pic_error;                      // decoder_core.cpp:192-194
+      else {
+        if ((ec_mode == 5 || ec_mode == 7) && pic_error && res_change) freeze = true;   // :195-198
+        info.output = !freeze;
+      }
+      if (concealed && nodelay_output && !by_flush) info.output = false;   // (constructed in the first half of DecodeFrameNoDelay: lost)
+    }
     if (debug_trace()) fprintf (stderr, "picture: %dx%d idr %d frame_num %d decoded %d of %d slices %zu\n", mb_w, mb_h, (int)sh0.idr, sh0.frame_num, decoded, n_mbs, slices.size());
     if (!slices.empty()) rc = sink->submit (d, info);
     if (want_model && !mslices.empty()) {
@@ -515,6 +554,7 @@ struct Decoder::Impl {
       if (!rc) rc = rm;
     }
     mark_current();
+    if (!slices.empty()) prev_slot = cur_slot;           // pPreviousDecodedPictureInDpb (decoder_core.cpp:2365, :2505)
     info.idr = sh0.idr; info.ltr_marking = ltr_marking; info.ltr_marked_frame_num = ltr_marked_frame_num;
     self->stats_.pictures++;
     self->stats_.coef_blocks += coefs.size() / 16;
@@ -522,6 +562,99 @@ struct Decoder::Impl {
     self->fin_.push_back (info);
     mbs.clear(); coefs.clear(); mrecs.clear();       // handed over: arena storage is the sink's now
     return rc;
+  }
+
+  // ---- error concealment inside a picture (ImplementErrorCon, error_concealment.cpp:443-471) ---------------------------
+  // The macroblocks no slice brought are handed to the reconstruction kernel as ordinary records of a synthetic slice without
+  // deblocking: a 16x16 motion-compensated block from the previous decoded picture (zero vector = DoErrorConSliceCopy, the
+  // average vector of the picture's inter macroblocks = DoErrorConSliceMVCopy), I_PCM grey when there is no such picture; the
+  // FRAME_COPY modes replace every macroblock.  (A decoded macroblock whose left / top neighbour is missing was deblocked by the
+  // reference against whatever the buffer held there before; that is not reproduced - see DESIGN.md.)
+  bool conceal() {
+    if (slices.size() >= 65535) return false;
+    int src = prev_slot;
+    if ((ec_mode == 1 || ec_mode == 2) && sh0.idr) src = -1;           // no cross-IDR copy: fill
+    const bool frame_copy = ec_mode == 1 || ec_mode == 3;
+    const bool same_buffer = src >= 0 && src == cur_slot;             // (the reference copies a buffer onto itself / skips the MC)
+    // GetAvilInfoFromCorrectMb: mean motion vector of the correctly decoded inter partitions that use reference index 0
+    int mvx = 0, mvy = 0;
+    bool use_mv = false;
+    if ((ec_mode == 6 || ec_mode == 7) && src >= 0 && !sh0.idr) {
+      long long sx = 0, sy = 0; int cnt = 0;
+      auto add = [&] (const lh264_mb_rec& m, int q, int idx) { if (m.ref_idx[q] == 0) { sx += m.mv[idx][0]; sy += m.mv[idx][1]; cnt++; } };
+      for (int i = 0; i < n_mbs; i++) {
+        if (mb_slice[i] < 0) continue;
+        const lh264_mb_rec& m = mbs[i];
+        switch (m.mb_type) {
+        case LH264_MB_PSKIP: case LH264_MB_P16x16: add (m, 0, 0); break;
+        case LH264_MB_P16x8: add (m, 0, 0); add (m, 2, 8); break;
+        case LH264_MB_P8x16: add (m, 0, 0); add (m, 1, 2); break;
+        case LH264_MB_P8x8:
+          for (int q = 0; q < 4; q++) {
+            const int b = ((q >> 1) << 3) + ((q & 1) << 1);
+            switch (m.sub_mb_type[q]) {
+            case LH264_SUB_8x8: add (m, q, b); break;
+            case LH264_SUB_8x4: add (m, q, b); add (m, q, b + 4); break;
+            case LH264_SUB_4x8: add (m, q, b); add (m, q, b + 1); break;
+            default: add (m, q, b); add (m, q, b + 1); add (m, q, b + 4); add (m, q, b + 5); break;
+            }
+          }
+          break;
+        default: break;
+        }
+      }
+      if (cnt > 0) {
+        mvx = (int) (sx / cnt); mvy = (int) (sy / cnt);
+        use_mv = true;
+        const int ref0 = slices.back().ref_slot[0];                   // pECRefPic[0]: entry 0 of the list in force (the last slice's)
+        if (ref0 != src) {                                            // scaled by the distance in iFramePoc (= pic_order_cnt_lsb)
+          const int s0 = slot_poc[ref0 & 31] - sh0.poc_lsb, s1 = slot_poc[src & 31] - sh0.poc_lsb;
+          mvx = s0 == 0 ? 0 : mvx * s1 / s0; mvy = s0 == 0 ? 0 : mvy * s1 / s0;
+        }
+      }
+    }
+    lh264_slice_rec sr;
+    memset (&sr, 0, sizeof (sr));
+    sr.slice_type = SLICE_P; sr.disable_deblocking_idc = 1; sr.num_ref_idx_l0 = 1;
+    for (int i = 0; i < LH264_MAX_REFS; i++) sr.ref_slot[i] = (int16_t) (src >= 0 ? src : cur_slot);
+    const int sidx = (int)slices.size();
+    int first = -1, count = 0;
+    const int W = mb_w * 16, H = mb_h * 16;
+    for (int i = 0; i < n_mbs; i++) {
+      if (!frame_copy && mb_slice[i] >= 0) continue;
+      if (first < 0) first = i;
+      count++;
+      lh264_mb_rec& m = mbs[i];
+      memset (&m, 0, sizeof (m));
+      m.slice_idx = (uint16_t)sidx;
+      if (same_buffer) { m.mb_type = LH264_MB_NONE; continue; }
+      if (src < 0) {                                                  // memset 128 (error_concealment.cpp:139-156)
+        m.mb_type = LH264_MB_IPCM; m.coded_mask = 0xffffffu; m.cbp = 0x2f; m.nz_mask = 0xffffffu;
+        m.coef_off = (uint32_t) (coefs.size() / 16);
+        int16_t* o = coefs.grow (384);
+        if (!o) { m.mb_type = LH264_MB_NONE; m.coded_mask = 0; continue; }
+        for (int k = 0; k < 384; k++) o[k] = 128;
+        continue;
+      }
+      m.mb_type = LH264_MB_P16x16;
+      int vx = 0, vy = 0;
+      if (use_mv) {                                                   // DoMbECMvCopy: the block stays inside the (cropped) picture
+        const int px = (i % mb_w) << 4, py = (i / mb_w) << 4;
+        int fx = (px << 2) + mvx, fy = (py << 2) + mvy;
+        int l = 0, t = 0, r = W, b = H;
+        if (S->crop_left || S->crop_right || S->crop_top || S->crop_bottom) { l = S->crop_left; r = W - S->crop_right; t = S->crop_top; b = H - S->crop_top; }
+        if (fx < ((l + 2) << 2)) { fx = (fx >> 2) << 2; fx = std::max (l, fx); }
+        else if (fx > ((r - 19) << 2)) { fx = (fx >> 2) << 2; fx = std::min ((r - 17) << 2, fx); }
+        if (fy < ((t + 2) << 2)) { fy = (fy >> 2) << 2; fy = std::max (t, fy); }
+        else if (fy > ((b - 19) << 2)) { fy = (fy >> 2) << 2; fy = std::min ((b - 17) << 2, fy); }
+        vx = fx - (px << 2); vy = fy - (py << 2);
+      }
+      for (int k = 0; k < 16; k++) { m.mv[k][0] = (int16_t)vx; m.mv[k][1] = (int16_t)vy; }
+    }
+    if (count == 0) return false;
+    sr.first_mb = first; sr.num_mbs = count;
+    slices.push_back (sr);
+    return true;
   }
 
   // ---- slice data ------------------------------------------------------------------------------------
@@ -1334,9 +1467,26 @@ const std::vector<ModelMbSide>& Decoder::model_side() const { return d_->side; }
 void Decoder::enable_model (bool on) { d_->want_model = on; }
 void Decoder::enable_rewrite_check (bool on) { d_->check_rewrite = on; if (on) d_->want_model = true; }
 
-int Decoder::flush() { return d_->finish_picture (this); }
+int Decoder::flush() { d_->by_flush = true; const int rc = d_->finish_picture (this); d_->by_flush = false; return rc; }
+void Decoder::set_nodelay_output (bool on) { d_->nodelay_output = on; }
 bool Decoder::picture_open() const { return d_->open; }
 void Decoder::set_freeze_output (bool on) { d_->freeze_output = on; }
+// InitErrorCon (error_concealment.cpp:43-52): the three non-freezing slice modes clear bFreezeOutput, nothing sets it here
+bool Decoder::open_picture_error() const {
+  const Impl& D = *d_;
+  if (!D.open || D.sh0.idr) return false;
+  if (D.ref_lost) return true;
+  if (!D.slot_incomplete || D.slices.empty()) return false;
+  const lh264_slice_rec& sl = D.slices.back();
+  if (sl.slice_type != SLICE_P) return false;
+  for (int i = 0; i < sl.num_ref_idx_l0 && i < LH264_MAX_REFS; i++) if ((D.slot_incomplete >> (sl.ref_slot[i] & 31)) & 1u) return true;
+  return false;
+}
+void Decoder::set_ec_mode (int idc, bool at_initialize) {
+  if (at_initialize) d_->freeze = true;                // WelsDecoderDefaults, decoder.cpp:300
+  d_->ec_mode = idc;
+  if (idc == 2 || idc == 4 || idc == 6) d_->freeze = false;
+}
 void Decoder::set_streaming_stores (bool coefs, bool model_recs) { d_->stream_coefs = coefs; d_->stream_mrecs = model_recs; }
 bool Decoder::set_arena (RecordArena* a) {
   const bool ok = d_->mbs.set_arena (a) & d_->coefs.set_arena (a) & d_->mrecs.set_arena (a);

@@ -34,6 +34,7 @@ struct DecodedPictureInfo {
   unsigned long long timestamp;          // of the call that brought the picture's last slice ...
   unsigned long long timestamp_first = 0;// ... and its first one
   bool ref_lost = false, ref_lost_first = false;   // decoded after a lost reference picture (until the next IDR); the first such picture
+  bool error = false;                    // concealed, or predicted from a picture that is not complete (!bIsComplete)
 };
 
 // Per-MB side record for the recompression model (filled by the parser; reference:
@@ -108,6 +109,13 @@ class Decoder {
   // from a lost IDR picture / a picture with missing macroblocks until the next complete IDR picture; the other modes hand every
   // picture out.  Default: freeze (the h264dec behaviour the YUV goldens pin).
   void set_freeze_output (bool on);
+  // ERROR_CON_IDC as SDecodingParam::eEcActiveIdc (at_initialize) or DECODER_OPTION_ERROR_CON_IDC sets it; default: what h264dec
+  // ends up with (Initialize with ERROR_CON_SLICE_COPY, then SetOption ERROR_CON_SLICE_MV_COPY_CROSS_IDR_FREEZE_RES_CHANGE)
+  void set_ec_mode (int idc, bool at_initialize);
+  // the picture being decoded predicts from a picture that is not complete (concealed / lost reference): bAllRefComplete false
+  bool open_picture_error() const;
+  // false: hand out every concealed picture (DecodeFrame2 semantics); true (default): as DecodeFrameNoDelay / h264dec does
+  void set_nodelay_output (bool on);
   // the last slice NAL handled by the last decode() call (for the `.pip` default stream, pip_container.h); rbsp is valid
   // until the next decode() call
   struct LastSlice { bool decoded = false, cabac = false; const uint8_t* rbsp = nullptr; size_t header_bits = 0; bool idr = false; int idr_pic_id = 0, frame_num = 0; };

@@ -34,6 +34,8 @@ class CLh264Decoder : public ISVCDecoder {
     if (!sink_ || !sink_->ctx()) { delete sink_; sink_ = nullptr; return cmInitParaError; }   // no device: fail loudly
     dec_ = new (std::nothrow) Decoder (sink_);
     if (!dec_) return cmMallocMemeError;
+    dec_->set_nodelay_output (false);                 // the two halves of DecodeFrameNoDelay are played out in decode()
+    ec_applied_ = false;                              // the first mode comes with Initialize (InitErrorCon on a fresh context)
     apply_ec();
     memset (&stat_, 0, sizeof (stat_));
     return cmResultSuccess;
@@ -117,7 +119,7 @@ class CLh264Decoder : public ISVCDecoder {
   // the two FREEZE modes hold output back behind a lost IDR / an incomplete picture (decoder_core.cpp:56-217 bFreezeOutput); the
   // others hand every picture out
   void apply_ec() {
-    if (dec_) dec_->set_freeze_output (ec_idc_ == ERROR_CON_SLICE_COPY_CROSS_IDR_FREEZE_RES_CHANGE || ec_idc_ == ERROR_CON_SLICE_MV_COPY_CROSS_IDR_FREEZE_RES_CHANGE);
+    if (dec_) { dec_->set_ec_mode (ec_idc_, !ec_applied_); ec_applied_ = true; }
   }
   // One DecodeFrame2 call as an API client sees it (welsDecoderExt.cpp:431-571).  The reference decodes an access unit when the
   // first NAL of the NEXT one arrives, or at once on the flush call DecodeFrame2 (NULL, 0) — which DecodeFrameNoDelay issues after
@@ -170,7 +172,7 @@ class CLh264Decoder : public ISVCDecoder {
       last_vcl_ = FEEDBACK_VCL_NAL; tid_ = 0; last_frame_num_ = o.frame_num;
       if (o.ltr_marking) { ltr_flag_ = true; ltr_frame_num_ = o.ltr_marked_frame_num; }
       if (o.output) queue_.push_back (o);
-      if (!o.complete || !o.output || o.ref_lost) state |= dsDataErrorConcealed;   // (incomplete, held back behind a lost IDR picture, or predicted from a lost one)
+      if (!o.complete || !o.output || o.ref_lost || o.error) state |= dsDataErrorConcealed;   // (incomplete, held back behind a lost IDR picture, or predicted from a lost one)
       if (o.ref_lost_first) state |= dsRefLost;
     }
     if (!queue_.empty()) {
@@ -228,11 +230,12 @@ class CLh264Decoder : public ISVCDecoder {
     // the flush half decodes what the unit brought at once: a slice unit reports its access unit even while the picture waits for
     // more slices
     if (slice_here && last_vcl_ != FEEDBACK_VCL_NAL) { last_vcl_ = FEEDBACK_VCL_NAL; tid_ = 0; last_frame_num_ = slice_frame_num; }
-    if (info->iBufferStatus == 0 && first.iBufferStatus == 1) {                // (a picture released by the first half: an incomplete one)
-      const unsigned long long ts = info->uiInBsTimeStamp;
-      *info = first; info->uiInBsTimeStamp = ts;
-      ppDst[0] = first_planes[0]; ppDst[1] = first_planes[1]; ppDst[2] = first_planes[2];
-    }
+    // A picture released by the FIRST half (a concealed one, given up when the next access unit arrived) is lost to the caller:
+    // the second DecodeFrame2 clears the output structure again (welsDecoderExt.cpp:408-430; the lines that would have kept it are
+    // commented out in the reference) - `first` is not looked at.
+    (void)first; (void)first_planes;
+    // a slice decoded at once (flush half) from a picture that is not complete reports the concealment state with every call
+    if (slice_here && dec_->open_picture_error()) st |= dsDataErrorConcealed;
     return (DECODING_STATE)st;
   }
 
@@ -303,6 +306,7 @@ class CLh264Decoder : public ISVCDecoder {
   size_t out_cap_ = 0;
   bool eos_ = false, eos_opt_ = false;
   int ec_idc_ = ERROR_CON_SLICE_COPY, trace_level_ = 0, device_ = 0;
+  bool ec_applied_ = false;
   int last_vcl_ = 0, last_frame_num_ = -1, last_idr_pic_id_ = 0;
   SDecoderStatistics stat_;
 };

@@ -20,12 +20,15 @@ int LhfbSink::submit_model (const lh264_model_picture& pic, const DecodedPicture
 int LhfbSink::configure (int mb_w, int mb_h, int) { mb_w_ = mb_w; mb_h_ = mb_h; return 0; }
 int LhfbSink::submit (const lh264_picture_desc& pic, const DecodedPictureInfo& info) {
   if (!f_) return -1;
-  if (!info.output) return 0;                        // held back by the decoder: not part of the decoded sequence
+  // A picture that is not handed out is still written when it was concealed (info.error with every macroblock present): later
+  // pictures predict from it.  Bit 8 of the nal_ref_idc word marks "decoded, not output".  (A picture held back behind a lost IDR
+  // picture is left out as before: nothing that is output depends on it.)
+  if (!info.output && ! (info.error && !info.complete)) return 0;
   auto w32 = [&] (int32_t v) { fwrite (&v, 4, 1, f_); };
   for (int s = 0; s < pic.n_slices; s++) {
     const lh264_slice_rec& sl = pic.slices[s];
     w32 (0x4246484c); w32 (1);
-    w32 (mb_w_); w32 (mb_h_); w32 (pic.cur_slot); w32 (info.frame_num); w32 (info.poc_lsb); w32 (info.idr_pic_id); w32 (info.nal_ref_idc); w32 (info.serial);
+    w32 (mb_w_); w32 (mb_h_); w32 (pic.cur_slot); w32 (info.frame_num); w32 (info.poc_lsb); w32 (info.idr_pic_id); w32 (info.nal_ref_idc | (info.output ? 0 : 0x100)); w32 (info.serial);
     fwrite (&sl, sizeof (sl), 1, f_);
     // the slice's macroblocks in address order (with slice groups they are not a contiguous range)
     std::vector<int> addr;

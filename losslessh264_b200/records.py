@@ -94,6 +94,7 @@ class Picture:
     mbs: np.ndarray = field(default_factory=lambda: np.zeros(0, MB_REC))
     coefs: np.ndarray = field(default_factory=lambda: np.zeros((0, 16), np.int16))
     scaled: np.ndarray | None = None  # reference-dequantised coefficients (dump only)
+    output: bool = True  # False: decoded (a reference for later pictures) but not part of the output sequence
     pix_pre: list | None = None  # per slice: picture before that slice's deblocking
     pix_post: list | None = None  # per slice: picture after it
 
@@ -143,7 +144,8 @@ def read_lhfb(path, max_pictures=None):
             if cur is None or key != cur_key:
                 if max_pictures is not None and len(pics) >= max_pictures:
                     break
-                cur = Picture(mb_w, mb_h, slot, frame_num, poc, idr_id, ref_idc, serial)
+                cur = Picture(mb_w, mb_h, slot, frame_num, poc, idr_id, ref_idc & 0xFF, serial)
+                cur.output = not (ref_idc & 0x100)      # a concealed picture DecodeFrameNoDelay does not hand out: reconstruct, do not emit
                 cur.mbs = np.zeros(mb_w * mb_h, MB_REC)
                 cur.scaled = np.zeros((0, 16), np.int16)
                 cur.pix_pre, cur.pix_post = [], []

@@ -15,6 +15,13 @@ STREAMS = [("SVA_BA1_B.264", None), ("syn_cif_cabac_4slices_ltr_6f.264", None), 
 for _n in ("BA_MW_D_IDR_LOST.264", "BA_MW_D_P_LOST.264", "Error_I_P.264"):
     STREAMS += [(_n, 2), (_n, 4), (_n, 7)]
 
+# streams with lost slices (tests/golden/streams/ec_*: the last slice of some pictures taken out of a four-slice stream) under the
+# modes that conceal differently: 1 frame copy, 2 slice copy, 4 slice copy across IDR, 6 motion-vector copy, 7 the same with the
+# freeze on a change of resolution.  DecodeFrame2 hands the concealed pictures out; DecodeFrameNoDelay loses them (its second
+# half clears the output of the first)
+for _n in ("ec_qcif_4slices_tail_lost.264", "ec_qcif_4slices_idr_tail_lost.264", "ec_cif_cabac_ltr_tail_lost.264"):
+    STREAMS += [(_n, 1), (_n, 2), (_n, 4), (_n, 6), (_n, 7)]
+
 os.makedirs(OUT, exist_ok=True)
 for name, ec in STREAMS:
     for mode in ("nodelay", "frame2"):

@@ -16,7 +16,7 @@ NOT_YET = {}
 # one-macroblock skip runs and end_of_slice stop bits; the decompress core has a CABAC slice-data writer).  The set is only
 # needed where a test is about CAVLC itself (the host CAVLC writer check).
 CABAC = {"QCIF_2P_I_allIPCM.264", "test_qcif_cabac.264", "tibbycabac.264", "syn_cif_cabac_4slices_ltr_6f.264", "syn_qcif_cabac_qp38_8f.264",
-         "test_cif_I_CABAC_slice.264", "test_cif_P_CABAC_slice.264", "sl_cabac_sps_pps.264"}
+         "test_cif_I_CABAC_slice.264", "test_cif_P_CABAC_slice.264", "sl_cabac_sps_pps.264", "ec_cif_cabac_ltr_tail_lost.264"}
 
 
 # Streams the reference itself refuses: it hands out 0 frames and a `.pip` that holds only the default stream.

@@ -17,13 +17,16 @@ HOST = os.path.join(ROOT, "losslessh264_b200", "host")
 EMU = os.path.join(ROOT, "tests", "emu")
 GOLD = os.path.join(ROOT, "tests", "golden", "api_probe")
 # (stream, error concealment idc): error-free streams under BaseDecoderTest's ERROR_CON_SLICE_COPY (the probe's default), damaged ones
-# under the mode h264dec selects (7: freeze) - sample concealment for the other modes is SURVEY 8f N3, not built
+# under the modes that behave differently on them
 CASES = [("SVA_BA1_B.264", None), ("syn_cif_cabac_4slices_ltr_6f.264", None), ("MPS_MW_A.264", None), ("MR1_BT_A.h264", None), ("test_vd_rc.264", None)]
 # the damaged streams under three error concealment modes: 2 and 4 hand out the pictures in front of a lost IDR picture (their
 # SAMPLES - predicted from the grey stand-in reference the reference decoder fabricates - are part of the comparison: the probe
 # prints a checksum of every picture it receives), 7 (h264dec's) freezes the output until the first IDR picture
 for _n in ("BA_MW_D_IDR_LOST.264", "BA_MW_D_P_LOST.264", "Error_I_P.264"):
     CASES += [(_n, 2), (_n, 4), (_n, 7)]
+# pictures with lost slices: concealed inside the picture (error_concealment.cpp) - frame copy, slice copy, grey fill, motion-vector copy
+for _n in ("ec_qcif_4slices_tail_lost.264", "ec_qcif_4slices_idr_tail_lost.264", "ec_cif_cabac_ltr_tail_lost.264"):
+    CASES += [(_n, 1), (_n, 2), (_n, 4), (_n, 6), (_n, 7)]
 # Error_I_P ends in a picture with missing macroblocks: the reference reports it at the slice that reveals the gap, this library at
 # the end of the stream - the last two calls are left out of the comparison
 TRIM = {"Error_I_P.264": 2}
