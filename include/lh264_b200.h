@@ -257,6 +257,10 @@ int  lh264_read_ticket(const lh264_ctx* ctx);
 int  lh264_output_wait_ticket(lh264_ctx* ctx, int ticket);
 /* Pinned host memory for hand-off records and output pictures (async copies need it).       */
 void* lh264_host_alloc(size_t bytes);
+/* The same, write-combined: for staging memory the host only WRITES (record arrays on their way to lh264_recon_submit /
+ * lh264_submit_compact).  Stores stream out without read-for-ownership and the DMA reads do not snoop the caches; host reads
+ * of such memory are uncached and very slow.  Freed with lh264_host_free.                                                  */
+void* lh264_host_alloc_wc(size_t bytes);
 void  lh264_host_free(void* p);
 
 /* ---- kernel-level entry points (parity tests against the reference kernel tables) ---------- */

@@ -490,7 +490,7 @@ __device__ __forceinline__ bool w_deblock_tile (RowCtx& s, int mbx, int mby, int
         bs = nz ? 2 : mv_differs (m, t8 ? rc8 : rc, nb, n8 ? rn8 : rn);
       }
     }
-  } else if (mb_type != LH264_MB_PSKIP && ! (t8 && e != 2)) {
+  } else if (mb_type != LH264_MB_PSKIP && ! (mb_type == LH264_MB_P16x16 && m->nz_mask == 0) && ! (t8 && e != 2)) {      // (one vector, no coefficients: no inner edge)
     const uint32_t nzc = m->nz_mask;
     const int a = dir ? 4 * e + i : 4 * i + e, b = dir ? a - 4 : a - 1;
     const int nz = t8 ? (nz8 (nzc, a) | nz8 (nzc, b)) : (nzb (nzc, a) | nzb (nzc, b));
@@ -661,8 +661,9 @@ __global__ void __launch_bounds__ (ROWS_WARPS * 32, 2) k_decode_rows (const PicD
         py[0] = n0; py[1] = n1; pc[0] = nc;
       }
       __syncwarp();
-      // progress = macroblocks of this row stored so far; consumers need x + 2 -> publish every second macroblock
-      if (lane == 0 && mbx > 0 && (mbx & 1) == 0) st_release (my, mbx);
+      // progress = macroblocks of this row stored so far; a consumer at macroblock x needs x + 1.  A release store is a fence:
+      // every fourth macroblock is often enough (rows of one picture are picked up ~n_pics tickets apart)
+      if (lane == 0 && mbx > 0 && (mbx & 3) == 0) st_release (my, mbx);
     }
     // the last macroblock of the row
     __syncwarp();

@@ -593,12 +593,8 @@ int lh264_sync (lh264_ctx* c) {
   return LH264_OK;
 }
 
-void* lh264_host_alloc (size_t bytes) {
-  void* p = nullptr;
-  static const bool wc = getenv ("LH264_HOST_WC") != nullptr;      // experiment: write-combined staging (CPU writes stream out, DMA reads do not snoop)
-  if (wc) return cudaHostAlloc (&p, bytes, cudaHostAllocWriteCombined) == cudaSuccess ? p : nullptr;
-  return cudaMallocHost (&p, bytes) == cudaSuccess ? p : nullptr;
-}
+void* lh264_host_alloc (size_t bytes) { void* p = nullptr; return cudaMallocHost (&p, bytes) == cudaSuccess ? p : nullptr; }
+void* lh264_host_alloc_wc (size_t bytes) { void* p = nullptr; return cudaHostAlloc (&p, bytes, cudaHostAllocWriteCombined) == cudaSuccess ? p : nullptr; }
 void lh264_host_free (void* p) { if (p) cudaFreeHost (p); }
 
 // ---- kernel-level entry points ---------------------------------------------------------------------------

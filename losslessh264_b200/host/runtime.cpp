@@ -50,28 +50,39 @@ double now() { return std::chrono::duration<double> (std::chrono::steady_clock::
 // (lh264_rt_trim() gives them back).
 class PinnedCache {
  public:
+  explicit PinnedCache (bool wc) : wc_ (wc) {}
   uint8_t* get (size_t need, size_t* got) {
     {
       std::lock_guard<std::mutex> g (mu_);
       auto it = free_.lower_bound (need);
       if (it != free_.end() && it->first <= 2 * need + ((size_t)4 << 20)) { uint8_t* p = it->second; *got = it->first; free_.erase (it); return p; }
     }
-    uint8_t* p = (uint8_t*)lh264_host_alloc (need);
+    uint8_t* p = (uint8_t*) (wc_ ? lh264_host_alloc_wc (need) : lh264_host_alloc (need));
     *got = p ? need : 0;
     return p;
   }
   void put (uint8_t* p, size_t cap) { if (!p) return; std::lock_guard<std::mutex> g (mu_); free_.emplace (cap, p); }
   void trim() { std::lock_guard<std::mutex> g (mu_); for (auto& kv : free_) lh264_host_free (kv.second); free_.clear(); }
  private:
+  bool wc_;
   std::mutex mu_;
   std::multimap<size_t, uint8_t*> free_;
 };
-PinnedCache& pinned_cache() { static PinnedCache* c = new PinnedCache(); return *c; }   // (never destroyed: no CUDA calls at exit)
+PinnedCache& pinned_cache() { static PinnedCache* c = new PinnedCache (false); return *c; }   // (never destroyed: no CUDA calls at exit)
+// Staging memory - what the parse threads fill and the copy engine reads - is write-combined: the parser only ever WRITES it
+// (compact records and coefficient pools leave the cache-resident scratch for good), so its stores need no read-for-ownership
+// and the DMA reads need not snoop sixteen cores' caches.  Measured on the pool's box, 1024 1080p streams: 3.5 k -> 5.7 k
+// pictures/s with pictures coming back, 6.5 k -> 8.2 k without (LH264_RT_NO_WC=1 switches it off).  Output buffers stay cacheable:
+// the client reads them.
+PinnedCache& staging_cache() {
+  static PinnedCache* c = new PinnedCache (getenv ("LH264_RT_NO_WC") == nullptr);
+  return *c;
+}
 
 struct PinRegion {                      // growable pinned buffer, bump-allocated within a step
   uint8_t* p = nullptr; size_t cap = 0, used = 0;
   double* alloc_s = nullptr;            // where the time spent in pinned allocation is accounted
-  ~PinRegion() { pinned_cache().put (p, cap); }
+  ~PinRegion() { staging_cache().put (p, cap); }
   // returns the offset of n fresh bytes (contents so far are kept when the buffer has to grow), or (size_t)-1;
   // `room` = what the region is expected to hold in the end (pinning memory is slow: grow in few, large steps)
   size_t take (size_t n, size_t room = 0) {
@@ -79,10 +90,10 @@ struct PinRegion {                      // growable pinned buffer, bump-allocate
     if (need > cap) {
       const double t0 = now();
       size_t ncap = std::max (std::max (need + need / 2, room), (size_t)1 << 16);
-      uint8_t* q = pinned_cache().get (ncap, &ncap);
+      uint8_t* q = staging_cache().get (ncap, &ncap);
       if (!q) return (size_t) -1;
-      if (used) memcpy (q, p, used);
-      pinned_cache().put (p, cap);
+      if (used) memcpy (q, p, used);                   // (a read of write-combined memory: slow, and rare - regions grow in few, large steps)
+      staging_cache().put (p, cap);
       p = q; cap = ncap;
       if (alloc_s) *alloc_s += now() - t0;
     }
@@ -826,6 +837,6 @@ int lh264_rt_stats_get (const lh264_rt* rt, lh264_rt_stats* out) {
 
 const char* lh264_rt_last_error (const lh264_rt* rt) { return rt ? rt->error.c_str() : "no runtime"; }
 
-void lh264_rt_trim (void) { pinned_cache().trim(); }
+void lh264_rt_trim (void) { pinned_cache().trim(); staging_cache().trim(); }
 
 } // extern "C"
