@@ -5,11 +5,16 @@
 // compression_stream.cpp:18-30); its driver is h264dec's unit loop (h264dec.cpp:246-364).  This is the host runtime the B200
 // path wants instead (SURVEY.md §7 "host thread per stream", §8f N2):
 //
-//   parse threads ── thread w owns streams w, w + T, w + 2T, ...: the unit loop of h264dec → host decoder (NAL / slice /
-//        │           CAVLC / CABAC parse).  Step k of a thread = the next picture of each of its streams; the hand-off records
-//        │           go into the thread's pinned staging buffer k mod D (five tightly packed regions: MB records, coefficient
-//        │           pools, model records, slice records, model slice records), so the records of a step leave for the device
-//        │           with a handful of H2D copies per thread.  A thread runs up to D - 1 steps ahead of the device.
+//   parse threads ── the unit loop of h264dec → host decoder (NAL / slice / CAVLC / CABAC parse).  Step k = the next picture
+//        │           of every stream; the threads DRAW (step, stream) tickets from one counter per pipeline, so an intra
+//        │           picture (several times the parse work of a P picture) delays nobody but the thread that drew it - with
+//        │           streams owned by threads (w, w + T, ...) any period in the streams that divides T put all the intra
+//        │           pictures of a step on one thread (measured: parse threads idle 57 % of a 1024-stream run).  A stream's
+//        │           pictures are parsed in order (a ticket waits for the stream's previous one).  The hand-off records of the
+//        │           tickets a thread draws for step k go into ITS pinned staging buffer k mod D (tightly packed regions: MB
+//        │           records, coefficient pools, model records, slice records, model slice records), so the records of a step
+//        │           leave for the device with a handful of H2D copies per thread.  A thread runs up to D - 1 steps ahead of
+//        │           the device.
 //   submit thread ── per pipeline: waits until every parse thread has finished step k, hands the step's pictures to the GPU
 //                    with ONE lh264_recon_submit + ONE lh264_model_submit, starts the packed D2H copy of the decoded pictures,
 //                    delivers the pictures of step k - 1 (callback / SHA-1) while step k runs, and releases staging buffer
@@ -274,6 +279,8 @@ struct Stream {
   int loops_left = 0;
   long parsed = 0;                      // pictures placed so far
   int last_error = 0;
+  std::atomic<long> steps_parsed {0};   // steps this stream has been taken through (its tickets are served in order)
+  bool live = true;                     // more pictures may come (touched by the holder of the stream's current ticket only)
   // a damaged stream can complete more than one picture in one unit; a step takes one picture per stream, the others wait in
   // a private step buffer (heap, not pinned: the rare path) and are moved into the staging of the following steps
   struct Spill { Placed pl; std::vector<uint8_t> part[R_COUNT]; };
@@ -316,7 +323,6 @@ struct Out {                             // pictures on their way to the host
 
 struct Worker {
   Pipeline* pl = nullptr;
-  std::vector<int> streams;             // indices into rt->streams
   std::vector<StepBuf> bufs;
   long steps_done = 0;                  // guarded by Pipeline::mu
   bool finished = false;                // no picture after step steps_done - 1
@@ -329,10 +335,13 @@ struct Pipeline {
   int index = 0;
   lh264_ctx* ctx = nullptr;
   std::vector<std::unique_ptr<Worker> > workers;
+  std::vector<int> streams;             // indices into rt->streams
+  std::atomic<long> ticket {0};         // next (step, stream) pair to parse: step = ticket / n, stream = streams[ticket % n]
+  std::atomic<int> live {0};            // streams that may still bring pictures
   std::mutex mu;
   std::condition_variable cv_parsed, cv_released;
   long released = 0;                    // steps whose staging buffers may be overwritten again
-  bool abort = false;
+  std::atomic<bool> abort {false};
   int rc = 0;
   long pictures = 0;
   double t_wait_parse = 0, t_wait_gpu = 0, t_end = 0, t_first = 0, t_open = 0;
@@ -417,33 +426,51 @@ void worker_main (Worker* w) {
   Pipeline* P = w->pl;
   lh264_rt* rt = P->rt;
   const int D = (int)w->bufs.size();
+  const long n = (long)P->streams.size();
   const bool want_pip = rt->cfg.want_pip != 0;
   StepArena arena;
-  for (long k = 0;; k++) {
-    {
-      const double t0 = now();
-      std::unique_lock<std::mutex> g (P->mu);
-      P->cv_released.wait (g, [&] { return P->abort || k < P->released + D; });
-      w->wait += now() - t0;
-      if (P->abort) { w->finished = true; w->steps_done = k; P->cv_parsed.notify_all(); return; }
-    }
-    const double t0 = now();
-    StepBuf& b = w->bufs[k % D];
-    b.reset();
-    bool more = false;
-    for (int si : w->streams) {
-      Stream& s = *rt->streams[si];
-      advance (s, &b, &arena, want_pip, rt->cfg.max_pictures);
-      if (!s.spill.empty() || (!s.flushed && !(rt->cfg.max_pictures > 0 && s.parsed >= rt->cfg.max_pictures))) more = true;
-    }
-    w->busy += now() - t0;
-    {
-      std::lock_guard<std::mutex> g (P->mu);
-      w->steps_done = k + 1;
-      if (!more) w->finished = true;
-    }
+  long cur = -1;                         // the step whose staging buffer this thread is filling
+  auto leave = [&] {                     // nothing behind steps 0 .. cur from this thread
+    { std::lock_guard<std::mutex> g (P->mu); w->steps_done = cur + 1; w->finished = true; }
     P->cv_parsed.notify_all();
-    if (!more) return;
+  };
+  for (;;) {
+    const long t = P->ticket.fetch_add (1, std::memory_order_relaxed);
+    const long k = t / n;
+    if (P->live.load (std::memory_order_acquire) == 0 || P->abort.load()) { leave(); return; }
+    // close the steps in front of the ticket's (a step this thread drew nothing of leaves an empty buffer) and take buffer k mod D
+    while (cur < k) {
+      if (cur >= 0) {
+        { std::lock_guard<std::mutex> g (P->mu); w->steps_done = cur + 1; }
+        P->cv_parsed.notify_all();
+      }
+      const double t0 = now();
+      {
+        std::unique_lock<std::mutex> g (P->mu);
+        P->cv_released.wait (g, [&] { return P->abort.load() || cur + 1 < P->released + D; });
+      }
+      w->wait += now() - t0;
+      if (P->abort.load()) { leave(); return; }
+      cur++;
+      w->bufs[cur % D].reset();
+    }
+    Stream& s = *rt->streams[P->streams[t % n]];
+    if (s.steps_parsed.load (std::memory_order_acquire) < k) {          // the stream's previous picture is still being parsed
+      const double t0 = now();
+      while (s.steps_parsed.load (std::memory_order_acquire) < k && !P->abort.load()) std::this_thread::yield();
+      w->wait += now() - t0;
+      if (P->abort.load()) { leave(); return; }
+    }
+    if (s.live) {
+      const double t0 = now();
+      advance (s, &w->bufs[k % D], &arena, want_pip, rt->cfg.max_pictures);
+      w->busy += now() - t0;
+      if (!(!s.spill.empty() || (!s.flushed && !(rt->cfg.max_pictures > 0 && s.parsed >= rt->cfg.max_pictures)))) {
+        s.live = false;
+        P->live.fetch_sub (1, std::memory_order_acq_rel);
+      }
+    }
+    s.steps_parsed.store (k + 1, std::memory_order_release);
   }
 }
 
@@ -664,7 +691,7 @@ done:
 // the `.pip` file set of every stream of a pipeline: default stream (host) + tag side streams (GPU)
 void collect_pip (Pipeline* P) {
   lh264_rt* rt = P->rt;
-  for (auto& w : P->workers) for (int si : w->streams) {
+  for (int si : P->streams) {
     Stream& s = *rt->streams[si];
     Sha1 h;
     s.pip_default = s.pip.finish();
@@ -753,13 +780,14 @@ int lh264_rt_run (lh264_rt* rt, lh264_rt_picture_fn fn, void* user) {
     }
     const int first = (int) ((long long)S * g / G), last = (int) ((long long)S * (g + 1) / G);
     const int tw = std::max (1, std::min (last - first, T * (g + 1) / G - T * g / G));
+    for (int i = first; i < last; i++) P->streams.push_back (i);
+    P->live.store (last - first);
     for (int w = 0; w < tw; w++) {
       std::unique_ptr<Worker> W (new Worker());
       W->pl = P.get();
       W->bufs.resize (rt->cfg.depth);
-      for (int i = first + w; i < last; i += tw) W->streams.push_back (i);
       for (StepBuf& b : W->bufs) {
-        b.expect = W->streams.size();
+        b.expect = (size_t) ((last - first + tw - 1) / tw);
         for (PinRegion& x : b.r) x.alloc_s = &W->alloc;
       }
       P->workers.push_back (std::move (W));
@@ -797,7 +825,7 @@ int lh264_rt_run (lh264_rt* rt, lh264_rt_picture_fn fn, void* user) {
     if (rt->cfg.want_hash) s.yuv_hex = s.yuv.hex();
   }
   for (auto& P : pipes) {
-    for (auto& w : P->workers) for (int si : w->streams) {
+    for (int si : P->streams) {
       Stream& s = *rt->streams[si];
       if (s.model_stream >= 0) lh264_model_close (P->ctx, s.model_stream);
       if (s.gpu_stream >= 0) lh264_stream_close (P->ctx, s.gpu_stream);
