@@ -62,17 +62,23 @@ struct ModelCtx {
   DevBuf<CodeJob> jobs[2]; int job_stride = 0;     // per half: [code_steps][job_stride]
   int cur = 0;                                     // the half being filled
   cudaStream_t code_stream = nullptr;              // k_model_code runs here, beside the generation of the following steps
-  cudaEvent_t gen_done = nullptr, coder_done[2] = {nullptr, nullptr}, recon_idle = nullptr;
+  cudaEvent_t gen_done = nullptr, coder_done[2] = {nullptr, nullptr}, recon_idle = nullptr, coder_start = nullptr;
   bool coder_pending[2] = {false, false};
   // The coder launch (one block of two latency-bound warps per stream, resident for the whole window) and the persistent
   // reconstruction kernel (two 256-thread blocks per SM: the whole register file) do not fit on an SM together: left to the
   // block scheduler they starve each other (measured, profiles/r2_summary.md: 58 ms per step together, 52 ms one after the
   // other).  LH264_CODE_EXCLUSIVE=0 lets them overlap again.
-  // When the steps come from resident batches (nothing but the GPU sets the pace) the coder therefore runs alone: it waits for the
-  // kernels submitted so far and the kernels of the following steps wait for it.  When the steps are fed from host buffers the
+  // When the steps come from resident batches (nothing but the GPU sets the pace) the coder therefore never shares the GPU with
+  // the reconstruction kernel: it waits for the reconstruction kernels submitted so far and those of the following steps wait for it
+  // (the generation kernels of the following window run beside it: mode 3 below).  When the steps are fed from host buffers the
   // GPU has slack and a 330 ms bubble per window would only stall the host pipeline: there they share the GPU.
-  // LH264_CODE_EXCLUSIVE=0 / 1 (reconstruction waits) / 2 (reconstruction and generation wait) overrides.
+  // LH264_CODE_EXCLUSIVE=0 / 1 (reconstruction waits) / 2 (reconstruction and generation wait) / 3 (reconstruction waits; the
+  // generation kernels of the NEXT window wait for the coder to START and run beside it - they are HBM-bound, the coder is a
+  // dependency chain, and neither reads what the other writes - so a window costs reconstruction + max (coder, generation)
+  // instead of the sum of the three) overrides.
   int exclusive_env = -1;
+  bool gen_with_coder = false;
+  bool beside_coder = false;                       // mode 3: a coder launch is in front of the window being generated (else the window is chained as in mode 2)
   bool last_resident = false;                      // the step submitted last came from a resident batch
   bool exclusive = true;
   bool exclusive_gen = true;
@@ -171,6 +177,7 @@ static ModelCtx* model_ctx (lh264_ctx* c) {
     if (!m->code_stream) cudaStreamCreateWithFlags (&m->code_stream, cudaStreamNonBlocking);
     cudaEventCreateWithFlags (&m->gen_done, cudaEventDisableTiming);
     cudaEventCreateWithFlags (&m->recon_idle, cudaEventDisableTiming);
+    cudaEventCreateWithFlags (&m->coder_start, cudaEventDisableTiming);
     for (int k = 0; k < 2; k++) { cudaEventCreateWithFlags (&m->index_copied[k], cudaEventDisableTiming); cudaEventCreateWithFlags (&m->coder_done[k], cudaEventDisableTiming); }
     if (const char* e = getenv ("LH264_CODE_EXCLUSIVE")) m->exclusive_env = atoi (e);
     if (const char* e = getenv ("LH264_STATS")) m->stats = atoi (e) != 0;
@@ -209,6 +216,7 @@ static void model_destroy (lh264_ctx* c) {
   for (int k = 0; k < 2; k++) { m->dec[k].release(); m->jobs[k].release(); if (m->coder_done[k]) cudaEventDestroy (m->coder_done[k]); }
   if (m->gen_done) cudaEventDestroy (m->gen_done);
   if (m->recon_idle) cudaEventDestroy (m->recon_idle);
+  if (m->coder_start) cudaEventDestroy (m->coder_start);
   m->job_index.release(); m->h_index[0].release(); m->h_index[1].release();
   if (m->d_pool_used) cudaFree (m->d_pool_used);
   if (m->d_pages_pending) cudaFree (m->d_pages_pending);
@@ -398,7 +406,11 @@ static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_
 }
 
 // Codes every pending step with ONE launch: block b = one model stream, walking its pictures in step order.
-static bool model_serial (const ModelCtx* m) { return !m->partitioned && (m->exclusive_env >= 0 ? m->exclusive_env >= 2 : m->last_resident); }
+#ifndef LH264_RESIDENT_MODE
+#define LH264_RESIDENT_MODE 3      // measured, 1024 staggered 1080p streams: 43.7 ms per step in mode 2, 40.2 in mode 3 (profiles/r2_summary.md section 11)
+#endif
+static int model_mode (const ModelCtx* m) { return m->partitioned ? 0 : (m->exclusive_env >= 0 ? m->exclusive_env : (m->last_resident ? LH264_RESIDENT_MODE : 0)); }
+static bool model_serial (const ModelCtx* m) { const int mode = model_mode (m); return mode == 2 || (mode == 3 && !m->beside_coder); }
 
 static int model_flush_coder (lh264_ctx* c, ModelCtx* m) {
   const int T = m->pend_steps;
@@ -407,8 +419,8 @@ static int model_flush_coder (lh264_ctx* c, ModelCtx* m) {
   m->n_flush++;
   if (m->stats) fprintf (stderr, "lh264 stats: coder launch %llu: %d steps, half %d (cap %zu M, est used %llu M, last step %llu M)\n", m->n_flush, T, h, m->dec[h].cap >> 20, m->est_pool_used >> 20, m->last_step_total >> 20);
   {
-    const int mode = m->partitioned ? 0 : (m->exclusive_env >= 0 ? m->exclusive_env : (m->last_resident ? 2 : 0));
-    m->exclusive = mode >= 1; m->exclusive_gen = mode >= 2;
+    const int mode = model_mode (m);
+    m->exclusive = mode >= 1; m->exclusive_gen = mode == 2; m->gen_with_coder = mode == 3;
   }
   m->slot_of.assign (m->streams.size(), -1);
   int nb = 0;
@@ -428,6 +440,7 @@ static int model_flush_coder (lh264_ctx* c, ModelCtx* m) {
   CK (cudaMemcpyAsync (m->job_index.p, m->h_index[k].p, n_idx * sizeof (int), cudaMemcpyHostToDevice, m->code_stream));
   CK (cudaEventRecord (m->index_copied[k], m->code_stream));
   ArenaDev ar{ m->d_page_ptrs, m->d_next, m->n_pages };
+  if (m->gen_with_coder) CK (cudaEventRecord (m->coder_start, m->code_stream));    // everything this launch waits for is through
   if (c->timing) CK (cudaEventRecord (m->ev[2], m->code_stream));
   k_model_code<<<nb, 64, 0, m->code_stream>>> (m->jobs[h].p, m->job_index.p, T, m->job_stride, m->dec[h].p, ar);
   c->launches++;
@@ -438,6 +451,9 @@ static int model_flush_coder (lh264_ctx* c, ModelCtx* m) {
   m->coder_pending[h] = true;
   // exclusive: neither the reconstruction kernels nor the generation kernels of the following steps start before the coder is through
   if (m->exclusive) { CK (cudaStreamWaitEvent (c->stream, m->coder_done[h], 0)); if (m->exclusive_gen) CK (cudaStreamWaitEvent (m->stream, m->coder_done[h], 0)); }
+  // the generation kernels of the following window run BESIDE this coder launch, not beside the reconstruction kernels in front of it
+  if (m->gen_with_coder) CK (cudaStreamWaitEvent (m->stream, m->coder_start, 0));
+  m->beside_coder = m->gen_with_coder;
   m->pend_steps = 0; m->est_pool_used = 0;
   // generation goes on in the other half, once the coder launch that read it (two flushes ago) is over
   m->cur ^= 1;
@@ -456,6 +472,7 @@ static int model_coder_idle (lh264_ctx* c, ModelCtx* m) {
   int rc = model_flush_coder (c, m);
   if (rc) return rc;
   CK (cudaStreamSynchronize (m->code_stream));
+  m->beside_coder = false;
   return LH264_OK;
 }
 
@@ -541,7 +558,9 @@ int model_grow_pool (lh264_ctx* c, ModelCtx* m, unsigned long long step_total) {
 // re-runs and as many short coder launches at 1024 streams): ask for the whole window the first time a step does not fit.
 static unsigned int model_arena_want (const ModelCtx* m, unsigned int in_use, unsigned int needed) {
   const unsigned long long must = (unsigned long long)in_use + 2ull * needed;
-  const unsigned long long window = (unsigned long long)in_use + (unsigned long long)std::max (2, m->code_steps + 1) * needed;
+  // (mode 3 generates a window while the coder works on the one before: two windows' promises are out at once)
+  const int steps = model_mode (m) == 3 ? 2 * m->code_steps + 1 : m->code_steps + 1;
+  const unsigned long long window = (unsigned long long)in_use + (unsigned long long)std::max (2, steps) * needed;
   const unsigned long long room = MAX_ARENA_PAGES - SEG_PAGES;                     // (segments are added whole)
   return (unsigned int)std::max (must, std::min (window, (unsigned long long)room));
 }
@@ -824,6 +843,7 @@ static cudaError_t model_join (lh264_ctx* c) {
   ModelCtx* m = static_cast<ModelCtx*> (c->model);
   if (!m || !m->stream) return cudaSuccess;
   if (model_flush_coder (c, m) != LH264_OK) return cudaErrorUnknown;
+  m->beside_coder = false;             // what follows a join is ordered behind it: the next window is chained, not run beside the launch in front of the join
   cudaError_t e = cudaEventRecord (m->done, m->stream);
   if (e == cudaSuccess) e = cudaStreamWaitEvent (c->stream, m->done, 0);
   for (int k = 0; k < 2 && e == cudaSuccess; k++) if (m->coder_pending[k]) e = cudaStreamWaitEvent (c->stream, m->coder_done[k], 0);
