@@ -410,7 +410,7 @@ static int model_stage (lh264_ctx* c, ModelCtx* m, MBatch& b, const lh264_model_
 #define LH264_RESIDENT_MODE 3      // measured, 1024 staggered 1080p streams: 43.7 ms per step in mode 2, 40.2 in mode 3 (profiles/r2_summary.md section 11)
 #endif
 static int model_mode (const ModelCtx* m) { return m->partitioned ? 0 : (m->exclusive_env >= 0 ? m->exclusive_env : (m->last_resident ? LH264_RESIDENT_MODE : 0)); }
-static bool model_serial (const ModelCtx* m) { const int mode = model_mode (m); return mode == 2 || (mode == 3 && !m->beside_coder); }
+static bool model_serial (const ModelCtx* m) { const int mode = model_mode (m); return mode == 2 || (mode >= 3 && !m->beside_coder); }
 
 static int model_flush_coder (lh264_ctx* c, ModelCtx* m) {
   const int T = m->pend_steps;
@@ -420,7 +420,7 @@ static int model_flush_coder (lh264_ctx* c, ModelCtx* m) {
   if (m->stats) fprintf (stderr, "lh264 stats: coder launch %llu: %d steps, half %d (cap %zu M, est used %llu M, last step %llu M)\n", m->n_flush, T, h, m->dec[h].cap >> 20, m->est_pool_used >> 20, m->last_step_total >> 20);
   {
     const int mode = model_mode (m);
-    m->exclusive = mode >= 1; m->exclusive_gen = mode == 2; m->gen_with_coder = mode == 3;
+    m->exclusive = mode >= 1 && mode <= 3; m->exclusive_gen = mode == 2; m->gen_with_coder = mode >= 3;     // (4: experiment - as 3, but the reconstruction kernels do not wait either)
   }
   m->slot_of.assign (m->streams.size(), -1);
   int nb = 0;
@@ -559,7 +559,7 @@ int model_grow_pool (lh264_ctx* c, ModelCtx* m, unsigned long long step_total) {
 static unsigned int model_arena_want (const ModelCtx* m, unsigned int in_use, unsigned int needed) {
   const unsigned long long must = (unsigned long long)in_use + 2ull * needed;
   // (mode 3 generates a window while the coder works on the one before: two windows' promises are out at once)
-  const int steps = model_mode (m) == 3 ? 2 * m->code_steps + 1 : m->code_steps + 1;
+  const int steps = model_mode (m) >= 3 ? 2 * m->code_steps + 1 : m->code_steps + 1;
   const unsigned long long window = (unsigned long long)in_use + (unsigned long long)std::max (2, steps) * needed;
   const unsigned long long room = MAX_ARENA_PAGES - SEG_PAGES;                     // (segments are added whole)
   return (unsigned int)std::max (must, std::min (window, (unsigned long long)room));
