@@ -10,6 +10,7 @@
 #include <stdio.h>
 #include <string.h>
 #include <stdarg.h>
+#include <map>
 #include <vector>
 #include <algorithm>
 #include <utility>
@@ -115,8 +116,46 @@ struct BatchDev {                            // device-resident batch
 
 struct lh264_resident_batch { BatchDev dev; };
 
+// Device memory of the per-stream buffers (picture slots, line buffers, priors, context records ...).  Opening a stream used to cost
+// seven cudaMalloc calls - a millisecond or so each for the multi-megabyte ones: 4 s for the 1024 streams of a batch run before
+// the first picture moved.  Slabs are taken 1 GB at a time and handed out by a bump pointer; a block given back is kept on a
+// free list by size and reused by the next stream of the same geometry (streams of one run mostly have one geometry); the
+// slabs go back to the driver when the context is destroyed.
+struct DevSlabs {
+  static constexpr size_t SLAB = (size_t)1 << 30, ALIGN = 512;
+  struct Slab { char* p; size_t cap, used; };
+  std::vector<Slab> slabs;
+  std::multimap<size_t, void*> free_;
+  std::vector<void*> big;                    // requests that do not fit a slab: their own cudaMalloc
+  cudaError_t take (void** out, size_t bytes) {
+    const size_t n = (bytes + ALIGN - 1) / ALIGN * ALIGN;
+    auto it = free_.find (n);
+    if (it != free_.end()) { *out = it->second; free_.erase (it); return cudaSuccess; }
+    if (n > SLAB / 4) { cudaError_t e = cudaMalloc (out, n); if (e == cudaSuccess) big.push_back (*out); return e; }
+    if (slabs.empty() || slabs.back().used + n > slabs.back().cap) {
+      char* q = nullptr;
+      size_t cap = SLAB;
+      cudaError_t e = cudaMalloc (&q, cap);
+      while (e != cudaSuccess && cap / 2 >= n && cap > ((size_t)32 << 20)) { cudaGetLastError(); cap /= 2; e = cudaMalloc (&q, cap); }   // memory is short: smaller slabs
+      if (e != cudaSuccess) return e;
+      slabs.push_back (Slab{q, cap, 0});
+    }
+    *out = slabs.back().p + slabs.back().used;
+    slabs.back().used += n;
+    return cudaSuccess;
+  }
+  void give (void* p, size_t bytes) {
+    if (!p) return;
+    const size_t n = (bytes + ALIGN - 1) / ALIGN * ALIGN;
+    for (size_t i = 0; i < big.size(); i++) if (big[i] == p) { cudaFree (p); big.erase (big.begin() + (long)i); return; }
+    free_.emplace (n, p);
+  }
+  void release() { for (auto& sl : slabs) cudaFree (sl.p); for (void* q : big) cudaFree (q); slabs.clear(); big.clear(); free_.clear(); }
+};
+
 struct lh264_ctx {
   int device = 0, n_sm = 148, occ_recon = 2;
+  DevSlabs slabs;
   unsigned int* d_error = nullptr;           // records that failed validation on the device (sticky until lh264_sync reports it)
   cudaStream_t stream = nullptr;
   bool own_stream = false;
@@ -217,7 +256,7 @@ void lh264_ctx_destroy (lh264_ctx* c) {
   cudaStreamSynchronize (c->stream);
   model_destroy (c);
   decode_destroy (c);
-  for (auto& s : c->streams) { if (s.base) cudaFree (s.base); if (s.lines) cudaFree (s.lines); }
+  c->slabs.release();                        // (picture slots, line buffers and the model streams' buffers live there)
   if (c->d_error) cudaFree (c->d_error);
   c->batch[0].release(); c->batch[1].release(); c->h_pics.release(); c->h_xjobs.release();
   for (int i = 0; i < 2; i++) if (c->batch_free[i]) cudaEventDestroy (c->batch_free[i]);
@@ -248,9 +287,9 @@ int lh264_stream_open (lh264_ctx* c, int mb_w, int mb_h, int n_slots) {
   s.open = true; s.mb_w = mb_w; s.mb_h = mb_h; s.n_slots = n_slots;
   s.slot_stride = (size_t)mb_w * mb_h * 384;
   // + 64: the aligned word loads of the reconstruction kernel may touch up to 3 bytes past the last row of the last plane
-  CK (cudaMalloc (&s.base, s.slot_stride * n_slots + 64));
+  CK (c->slabs.take ((void**)&s.base, s.slot_stride * n_slots + 64));
   CK (cudaMemsetAsync (s.base, 128, s.slot_stride * n_slots + 64, c->stream));   // pic_queue.cpp:96
-  if (cudaMalloc (&s.lines, (size_t)mb_h * 2 * mb_w * 16) != cudaSuccess) { cudaFree (s.base); return fail (LH264_E_NOMEM, "out of device memory (line buffer)"); }
+  if (c->slabs.take ((void**)&s.lines, (size_t)mb_h * 2 * mb_w * 16) != cudaSuccess) { cudaGetLastError(); c->slabs.give (s.base, s.slot_stride * n_slots + 64); return fail (LH264_E_NOMEM, "out of device memory (line buffer)"); }
   for (size_t i = 0; i < c->streams.size(); i++) if (!c->streams[i].open) { c->streams[i] = s; return (int)i; }
   c->streams.push_back (s);
   return (int)c->streams.size() - 1;
@@ -259,8 +298,11 @@ int lh264_stream_open (lh264_ctx* c, int mb_w, int mb_h, int n_slots) {
 int lh264_stream_close (lh264_ctx* c, int stream) {
   if (!c || stream < 0 || stream >= (int)c->streams.size() || !c->streams[stream].open) return fail (LH264_E_INVALID, "bad stream");
   CK (cudaStreamSynchronize (c->stream));
-  cudaFree (c->streams[stream].base);
-  if (c->streams[stream].lines) cudaFree (c->streams[stream].lines);
+  {
+    const StreamRec& s = c->streams[stream];
+    c->slabs.give (s.base, s.slot_stride * s.n_slots + 64);
+    c->slabs.give (s.lines, (size_t)s.mb_h * 2 * s.mb_w * 16);
+  }
   c->streams[stream] = StreamRec();
   return LH264_OK;
 }

@@ -195,19 +195,21 @@ static ModelCtx* model_ctx (lh264_ctx* c) {
   return static_cast<ModelCtx*> (c->model);
 }
 
-static void model_free_stream (MStreamHost& s) {
-  if (s.d_state) cudaFree (s.d_state);
-  if (s.d_priors) cudaFree (s.d_priors);
-  if (s.d_frames) cudaFree (s.d_frames);
-  if (s.d_order) cudaFree (s.d_order);
-  if (s.d_pagelist) cudaFree (s.d_pagelist);
+// the buffers of a model stream come from the context's slabs (DevSlabs, lh264_shim.cu): sizes as lh264_model_open asked for them
+static size_t model_priors_bytes (const MStreamHost& s) { return (s.with_8x8 ? P_END : P_END_NO8) * sizeof (uint32_t); }
+static void model_free_stream (lh264_ctx* c, MStreamHost& s) {
+  c->slabs.give (s.d_state, sizeof (MState));
+  c->slabs.give (s.d_priors, model_priors_bytes (s));
+  c->slabs.give (s.d_frames, (size_t)3 * s.max_mbs * sizeof (CtxRec));
+  c->slabs.give (s.d_order, (size_t)s.max_mbs * sizeof (int));
+  c->slabs.give (s.d_pagelist, (size_t)CT_COUNT * MAX_PAGES_PER_TAG * sizeof (uint32_t));
   s = MStreamHost();
 }
 
 static void model_destroy (lh264_ctx* c) {
   ModelCtx* m = static_cast<ModelCtx*> (c->model);
   if (!m) return;
-  for (auto& s : m->streams) if (s.open) model_free_stream (s);
+  for (auto& s : m->streams) if (s.open) model_free_stream (c, s);
   for (uint8_t* p : m->segments) cudaFree (p);
   if (m->d_page_ptrs) cudaFree (m->d_page_ptrs);
   if (m->d_next) cudaFree (m->d_next);
@@ -283,11 +285,13 @@ int lh264_model_open (lh264_ctx* c, int max_mbs, int with_8x8) {
   MStreamHost s;
   s.open = true; s.max_mbs = max_mbs; s.with_8x8 = with_8x8 ? 1 : 0;
   const size_t n_priors = with_8x8 ? P_END : P_END_NO8;
-  CK (cudaMalloc (&s.d_state, sizeof (MState)));
-  CK (cudaMalloc (&s.d_priors, n_priors * sizeof (uint32_t)));
-  CK (cudaMalloc (&s.d_frames, (size_t)3 * max_mbs * sizeof (CtxRec)));
-  CK (cudaMalloc (&s.d_order, (size_t)max_mbs * sizeof (int)));
-  CK (cudaMalloc (&s.d_pagelist, (size_t)CT_COUNT * MAX_PAGES_PER_TAG * sizeof (uint32_t)));
+  if (c->slabs.take ((void**)&s.d_state, sizeof (MState)) != cudaSuccess || c->slabs.take ((void**)&s.d_priors, n_priors * sizeof (uint32_t)) != cudaSuccess ||
+      c->slabs.take ((void**)&s.d_frames, (size_t)3 * max_mbs * sizeof (CtxRec)) != cudaSuccess || c->slabs.take ((void**)&s.d_order, (size_t)max_mbs * sizeof (int)) != cudaSuccess ||
+      c->slabs.take ((void**)&s.d_pagelist, (size_t)CT_COUNT * MAX_PAGES_PER_TAG * sizeof (uint32_t)) != cudaSuccess) {
+    cudaGetLastError();
+    model_free_stream (c, s);                        // (gives back what was had: give() ignores null pointers)
+    return fail (LH264_E_NOMEM, "out of device memory (model stream)");
+  }
   CK (cudaMemsetAsync (s.d_priors, 0, n_priors * sizeof (uint32_t), m->stream));          // fresh DynProb = all zero bits
   CK (cudaMemsetAsync (s.d_frames, 0, (size_t)3 * max_mbs * sizeof (CtxRec), m->stream));
   CK (cudaMemsetAsync (s.d_pagelist, 0, (size_t)CT_COUNT * MAX_PAGES_PER_TAG * sizeof (uint32_t), m->stream));
@@ -321,7 +325,7 @@ int lh264_model_close (lh264_ctx* c, int ms) {
   if ((rc = model_coder_idle (c, m))) return rc;
   CK (cudaStreamSynchronize (m->stream));
   // the stream's output pages stay in the arena until the context is destroyed (bump allocator)
-  model_free_stream (m->streams[ms]);
+  model_free_stream (c, m->streams[ms]);
   return LH264_OK;
 }
 
