@@ -262,6 +262,10 @@ void* lh264_host_alloc(size_t bytes);
  * of such memory are uncached and very slow.  Freed with lh264_host_free.                                                  */
 void* lh264_host_alloc_wc(size_t bytes);
 void  lh264_host_free(void* p);
+/* Makes `device` the calling THREAD's CUDA device.  The allocators above work on the calling thread's device: a helper thread
+ * of a process that drives GPU n > 0 (one process per GPU) binds itself first, or its first allocation would open a context on
+ * GPU 0.  Returns LH264_OK or LH264_E_NO_DEVICE.                                                                              */
+int   lh264_thread_bind(int device);
 
 /* ---- kernel-level entry points (parity tests against the reference kernel tables) ---------- */
 /* n independent 4x4 blocks: pred/out u8[n][16], levels int16[n][16] already dequantised.

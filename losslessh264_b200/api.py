@@ -23,7 +23,7 @@ EXPORTS = [
     "lh264_stream_open", "lh264_stream_close", "lh264_recon_submit", "lh264_batch_upload",
     "lh264_batch_recon", "lh264_batch_free", "lh264_kernel_launches", "lh264_kernel_ms",
     "lh264_picture_read", "lh264_picture_write", "lh264_picture_device_ptrs", "lh264_sync", "lh264_join", "lh264_inputs_consumed",
-    "lh264_pictures_read_packed", "lh264_output_wait", "lh264_host_alloc", "lh264_host_alloc_wc", "lh264_host_free",
+    "lh264_pictures_read_packed", "lh264_output_wait", "lh264_host_alloc", "lh264_host_alloc_wc", "lh264_host_free", "lh264_thread_bind",
     "lh264_k_idct4x4_add", "lh264_k_idct8x8_add", "lh264_k_mc_luma", "lh264_k_mc_chroma",
     "lh264_k_expand_plane",
     "lh264_model_open", "lh264_model_close", "lh264_model_submit", "lh264_model_finish", "lh264_model_read",

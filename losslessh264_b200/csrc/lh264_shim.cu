@@ -638,6 +638,7 @@ int lh264_sync (lh264_ctx* c) {
 void* lh264_host_alloc (size_t bytes) { void* p = nullptr; return cudaMallocHost (&p, bytes) == cudaSuccess ? p : nullptr; }
 void* lh264_host_alloc_wc (size_t bytes) { void* p = nullptr; return cudaHostAlloc (&p, bytes, cudaHostAllocWriteCombined) == cudaSuccess ? p : nullptr; }
 void lh264_host_free (void* p) { if (p) cudaFreeHost (p); }
+int lh264_thread_bind (int device) { return cudaSetDevice (device) == cudaSuccess ? LH264_OK : fail (LH264_E_NO_DEVICE, "cudaSetDevice failed"); }
 
 // ---- kernel-level entry points ---------------------------------------------------------------------------
 static int up (lh264_ctx* c, DevBuf<uint8_t>& b, const void* src, size_t bytes) {

@@ -29,6 +29,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <deque>
+#include <future>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -359,6 +360,7 @@ struct Pipeline {
   int out_in_flight = 0;                // reads issued and not yet delivered
   bool out_quit = false;
   uint8_t* out_pin[2] = {nullptr, nullptr}; size_t out_cap[2] = {0, 0};   // (pinned: 3.2 GB each for 1024 1080p streams)
+  std::future<std::pair<uint8_t*, size_t> > out_prefetch;                  // out_pin[1] on its way (helper thread)
   long out_issued = 0;
 };
 
@@ -425,6 +427,7 @@ void advance (Stream& s, StepBuf* buf, StepArena* arena, bool want_pip, long max
 void worker_main (Worker* w) {
   Pipeline* P = w->pl;
   lh264_rt* rt = P->rt;
+  lh264_thread_bind (rt->cfg.device);    // this thread page-locks staging memory: on the pipeline's GPU, not on GPU 0
   const int D = (int)w->bufs.size();
   const long n = (long)P->streams.size();
   const bool want_pip = rt->cfg.want_pip != 0;
@@ -477,6 +480,7 @@ void worker_main (Worker* w) {
 void pipeline_main (Pipeline* P) {
   lh264_rt* rt = P->rt;
   const lh264_rt_config& cfg = rt->cfg;
+  lh264_thread_bind (cfg.device);
   const bool want_yuv = cfg.want_yuv != 0, want_hash = want_yuv && cfg.want_hash != 0, want_pip = cfg.want_pip != 0;
   lh264_ctx* ctx = P->ctx;
   const int D = (int)P->workers[0]->bufs.size();
@@ -623,6 +627,16 @@ void pipeline_main (Pipeline* P) {
             P->out_cv.wait (g, [&] { return P->out_in_flight < 2; });
             P->t_wait_gpu += now() - tg0;
           }
+          if (P->out_prefetch.valid() && oi == 1) {          // the second output buffer, page-locked by the helper thread since step 0
+            const std::pair<uint8_t*, size_t> got = P->out_prefetch.get();
+            if (got.first) { pinned_cache().put (P->out_pin[1], P->out_cap[1]); P->out_pin[1] = got.first; P->out_cap[1] = got.second; }
+          }
+          if (P->out_issued == 0 && per * step.size() > P->out_cap[1] && !P->out_prefetch.valid()) {
+            // page-locking 3 GB takes about a second: the buffer of step 1 is made beside step 0 instead of inside step 1
+            const size_t want = per * step.size();
+            const int dev = cfg.device;
+            P->out_prefetch = std::async (std::launch::async, [want, dev] { lh264_thread_bind (dev); size_t cap = 0; uint8_t* q = pinned_cache().get (want, &cap); return std::make_pair (q, q ? cap : (size_t)0); });
+          }
           if (per * step.size() > P->out_cap[oi]) {
             pinned_cache().put (P->out_pin[oi], P->out_cap[oi]);
             P->out_pin[oi] = pinned_cache().get (per * step.size(), &P->out_cap[oi]);
@@ -685,6 +699,7 @@ done:
     P->abort = true;                     // (also the normal end: no parse thread is waiting any more)
   }
   P->cv_released.notify_all();
+  if (P->out_prefetch.valid()) { const std::pair<uint8_t*, size_t> got = P->out_prefetch.get(); pinned_cache().put (got.first, got.second); }   // (a run that ended after one step)
   for (int k = 0; k < 2; k++) { pinned_cache().put (P->out_pin[k], P->out_cap[k]); P->out_pin[k] = nullptr; P->out_cap[k] = 0; }
 }
 

@@ -89,6 +89,7 @@ int lh264_output_wait_ticket (lh264_ctx*, int) { return LH264_OK; }
 uint64_t lh264_kernel_launches (const lh264_ctx* c) { return c->launches; }
 void* lh264_host_alloc (size_t n) { return malloc (n ? n : 1); }
 void* lh264_host_alloc_wc (size_t n) { return malloc (n ? n : 1); }
+int lh264_thread_bind (int) { return LH264_OK; }
 void lh264_host_free (void* p) { free (p); }
 
 int lh264_picture_read (lh264_ctx* c, int stream, int slot, int crop_x, int crop_y, int width, int height,
