@@ -11,7 +11,11 @@ void split_annexb (const uint8_t* d, size_t len, std::vector<NalSpan>& out) {
   // find first start code
   auto find_sc = [&] (size_t from, size_t& sc_len) -> size_t {
     for (size_t k = from; k + 3 <= len; k++) {
-      if (d[k] == 0 && d[k + 1] == 0) {
+      // entropy-coded bytes are rarely zero: jump from zero byte to zero byte (memchr runs at tens of bytes per cycle)
+      const uint8_t* z = static_cast<const uint8_t*> (memchr (d + k, 0, len - 2 - k));
+      if (!z) break;
+      k = (size_t) (z - d);
+      if (d[k + 1] == 0) {
         if (d[k + 2] == 1) { sc_len = 3; return k; }
         if (k + 4 <= len && d[k + 2] == 0 && d[k + 3] == 1) { sc_len = 4; return k; }
       }
@@ -33,16 +37,24 @@ void split_annexb (const uint8_t* d, size_t len, std::vector<NalSpan>& out) {
 }
 
 size_t unescape_nal (const uint8_t* p, size_t len, std::vector<uint8_t>& out) {
-  out.resize (len + 8);
-  size_t o = 0;
+  if (out.size() < len + 8) out.resize (len + 8);       // (a reused vector is not cleared again: every byte up to o + 8 is written below)
+  uint8_t* dst = out.data();
+  size_t o = 0, i = 0;
   int zeros = 0;
-  for (size_t i = 0; i < len; i++) {
-    const uint8_t b = p[i];
+  while (i < len) {
+    if (zeros == 0) {                                    // no zero run open: everything up to the next zero byte is copied as it is
+      const uint8_t* z = static_cast<const uint8_t*> (memchr (p + i, 0, len - i));
+      const size_t n = z ? (size_t) (z - (p + i)) : len - i;
+      memcpy (dst + o, p + i, n);
+      o += n; i += n;
+      if (i >= len) break;
+    }
+    const uint8_t b = p[i++];
     if (zeros >= 2 && b == 3) { zeros = 0; continue; }   // emulation_prevention_three_byte
-    out[o++] = b;
+    dst[o++] = b;
     zeros = b == 0 ? zeros + 1 : 0;
   }
-  memset (out.data() + o, 0, 8);
+  memset (dst + o, 0, 8);
   out.resize (o + 8);
   return o;
 }

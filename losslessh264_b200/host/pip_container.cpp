@@ -36,8 +36,21 @@ void DefaultStream::stop_escape() {                    // compression_stream.h:7
 }
 
 size_t PipBoilerplate::next_unit (const uint8_t* b, size_t pos, size_t file_size) {
-  size_t i;
-  for (i = 0; i < file_size; i++) {
+  size_t i = 0;
+  // the unit ends at the next start code - at the latest the sentinel behind the last byte (b[file_size ..]): jump from zero byte
+  // to zero byte inside that range, and fall back to the plain walk only if nothing was found there
+  if (file_size > pos) {
+    const size_t limit = file_size - pos;               // candidates i = 1 .. limit
+    for (size_t k = 1; k <= limit; k++) {
+      const uint8_t* z = static_cast<const uint8_t*> (memchr (b + pos + k, 0, limit - k + 1));
+      if (!z) break;
+      k = (size_t) (z - (b + pos));
+      const uint8_t* q = z;
+      if (q[1] == 0 && ((q[2] == 0 && q[3] == 1) || q[2] == 1)) return k;
+    }
+    i = limit + 1;
+  }
+  for (; i < file_size; i++) {
     const uint8_t* q = b + pos + i;
     if (i > 0 && q[0] == 0 && q[1] == 0 && ((q[2] == 0 && q[3] == 1) || q[2] == 1)) break;   // at the latest: the sentinel
   }
@@ -50,7 +63,7 @@ void PipBoilerplate::unit_begin (const uint8_t* u, size_t len, bool sps_seen) {
   for (size_t k = 0; k + 3 <= len; k++) if (u[k] == 0 && u[k + 1] == 0 && u[k + 2] == 1) { off = k + 3; break; }
   if (off == 0) return;                                // no start code: the reference rejects the buffer
   def_.append_bytes (u, off);
-  std::vector<uint8_t> nal;
+  std::vector<uint8_t>& nal = nal_scratch_;            // (reused: no allocation and no clearing per unit)
   const size_t n = unescape_nal (u + off, len - off, nal);
   def_.escape_on();
   if (n == 0) return;

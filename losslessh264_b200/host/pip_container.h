@@ -63,6 +63,7 @@ class PipBoilerplate {
   const std::vector<uint8_t>& so_far() const { return def_.bytes(); }
  private:
   DefaultStream def_;
+  std::vector<uint8_t> nal_scratch_;   // unit_begin: the unescaped unit
 };
 
 // ---- single-file container (not in the reference, which writes <= ~35 side files per stream) -----------------
