@@ -51,6 +51,11 @@ struct __align__ (16) RowCtx : WarpCtx {
   int16_t sl_slot[LH264_MAX_REFS];              // picture slot of RefPicList0[i], clamped to the stream's pool
   uint8_t sl_wp, sl_idc; int8_t sl_aoff, sl_boff;
   uint8_t sl_scal;                              // LH264_SLF_*: scaling lists in use (cold path: residual_block_scaled)
+  // Per-lane addresses of the row being decoded, for macroblock 0 (a lane adds mbx * 16 or mbx * 8): kept here because the
+  // compiler, short of registers, recomputed them from the picture descriptor at every use (a tenth of the kernel's instructions
+  // were loop invariants).  [0] luma store (row lane / 2, half lane & 1), [1] chroma store, [2] the words of the rows above
+  // (lanes 0..15 luma rows -4..-1, lanes 16..23 chroma rows -2..-1), [3] line-buffer words (lanes 0..3 luma, 4..7 chroma)
+  unsigned long long lp[4][32];
 };
 
 struct DecodeSync {          // device-resident, zeroed before every batch
@@ -563,6 +568,21 @@ __global__ void __launch_bounds__ (ROWS_WARPS * 32, 2) k_decode_rows (const PicD
     uint32_t recw = __ldg (row + lane), topw = __ldg (row_top + lane);   // the records of the next MB are always in flight
     uint8_t* Y = plane_ptr (pic, pic.cur_slot, 0) + (size_t)mby * 16 * W;
     uint8_t* C = plane_ptr (pic, pic.cur_slot, 1 + cp) + (size_t)mby * 8 * CW;
+    {
+      __syncwarp();
+      s.lp[0][lane] = reinterpret_cast<unsigned long long> (Y + (size_t)r * W + 8 * h);
+      s.lp[1][lane] = reinterpret_cast<unsigned long long> (C + (size_t)cr * CW + 4 * h);
+      uint8_t* tp = Y;
+      if (mby > 0) {
+        if (lane < 16) tp = Y - (size_t) (4 - (lane >> 2)) * W + 4 * (lane & 3);
+        else if (lane < 24) { const int q = lane - 16; tp = plane_ptr (pic, pic.cur_slot, 1 + (q >> 2)) + ((size_t)mby * 8 - 2 + ((q >> 1) & 1)) * CW + 4 * (q & 1); }
+      }
+      s.lp[2][lane] = reinterpret_cast<unsigned long long> (tp);
+      uint8_t* lb = line_ptr (pic, mby, 0) + 4 * (lane & 3);
+      if (lane >= 4) { const int q = (lane - 4) & 3; lb = line_ptr (pic, mby, 1 + (q >> 1)) + 4 * (q & 1); }
+      s.lp[3][lane] = reinterpret_cast<unsigned long long> (lb);
+      __syncwarp();
+    }
 #pragma unroll 1
     for (int mbx = 0; mbx < mb_w; mbx++) {
       __syncwarp();
@@ -604,13 +624,7 @@ __global__ void __launch_bounds__ (ROWS_WARPS * 32, 2) k_decode_rows (const PicD
       }
       // rows 12..15 (6..7) of the macroblock above, for the top edge: issued now, parked in the tile arrays after reconstruction
       uint32_t tw = 0;
-      if (mby > 0) {
-        if (lane < 16) tw = __ldcg (reinterpret_cast<const uint32_t*> (Y - (size_t) (4 - (lane >> 2)) * W + mbx * 16) + (lane & 3));
-        else if (lane < 24) {
-          const int q = lane - 16, tp = q >> 2, trow = (q >> 1) & 1;
-          tw = __ldcg (reinterpret_cast<const uint32_t*> (plane_ptr (pic, pic.cur_slot, 1 + tp) + ((size_t)mby * 8 - 2 + trow) * CW + mbx * 8) + (q & 1));
-        }
-      }
+      if (mby > 0 && lane < 24) tw = __ldcg (reinterpret_cast<const uint32_t*> (reinterpret_cast<const uint8_t*> (s.lp[2][lane]) + mbx * (lane < 16 ? 16 : 8)));
       // ---- unfiltered reconstruction into the cur tile ----
       if (LH264_MB_IS_INTER (mb_type)) {
         const lh264_slice_rec* sl = pic.slices + s.mb.slice_idx;
@@ -632,10 +646,10 @@ __global__ void __launch_bounds__ (ROWS_WARPS * 32, 2) k_decode_rows (const PicD
       // ---- what the neighbours' intra prediction needs of U(x, y): right column (shared), bottom row (line buffer) ----
       if (lane < 16) s.ucol[lane] = s.ry[(RY_TOP + lane) * RY + 31];
       else s.ucol[lane] = s.rc[(lane - 16) >> 3][(RC_TOP + (lane & 7)) * RC + 15];
-      if (lane < 4) __stcg (reinterpret_cast<uint32_t*> (line_ptr (pic, mby, 0) + mbx * 16) + lane, *reinterpret_cast<const uint32_t*> (s.ry + (RY_TOP + 15) * RY + 16 + 4 * lane));
+      if (lane < 4) __stcg (reinterpret_cast<uint32_t*> (reinterpret_cast<uint8_t*> (s.lp[3][lane]) + mbx * 16), *reinterpret_cast<const uint32_t*> (s.ry + (RY_TOP + 15) * RY + 16 + 4 * lane));
       else if (lane < 8) {
         const int q = lane - 4;
-        __stcg (reinterpret_cast<uint32_t*> (line_ptr (pic, mby, 1 + (q >> 1)) + mbx * 8) + (q & 1), *reinterpret_cast<const uint32_t*> (s.rc[q >> 1] + (RC_TOP + 7) * RC + 8 + 4 * (q & 1)));
+        __stcg (reinterpret_cast<uint32_t*> (reinterpret_cast<uint8_t*> (s.lp[3][lane]) + mbx * 8), *reinterpret_cast<const uint32_t*> (s.rc[q >> 1] + (RC_TOP + 7) * RC + 8 + 4 * (q & 1)));
       }
       __syncwarp();
       // ---- deblocking of macroblock x: left edge across prev | cur, top edge across the rows above | cur ----
@@ -646,14 +660,16 @@ __global__ void __launch_bounds__ (ROWS_WARPS * 32, 2) k_decode_rows (const PicD
         uint32_t* py = reinterpret_cast<uint32_t*> (s.ry + (RY_TOP + r) * RY + 8 * h);
         uint32_t* pc = reinterpret_cast<uint32_t*> (s.rc[cp] + (RC_TOP + cr) * RC + 4 * h);
         if (mbx > 0) {
-          *reinterpret_cast<uint2*> (Y + (size_t)r * W + (mbx - 1) * 16 + 8 * h) = make_uint2 (py[0], py[1]);
-          *reinterpret_cast<uint32_t*> (C + (size_t)cr * CW + (mbx - 1) * 8 + 4 * h) = pc[0];
+          *reinterpret_cast<uint2*> (reinterpret_cast<uint8_t*> (s.lp[0][lane]) + (mbx - 1) * 16) = make_uint2 (py[0], py[1]);
+          *reinterpret_cast<uint32_t*> (reinterpret_cast<uint8_t*> (s.lp[1][lane]) + (mbx - 1) * 8) = pc[0];
         }
         if (top_done) {
-          if (lane < 12) { const int tr = 1 + (lane >> 2); *(reinterpret_cast<uint32_t*> (Y - (size_t) (4 - tr) * W + mbx * 16) + (lane & 3)) = *reinterpret_cast<const uint32_t*> (s.ry + tr * RY + 16 + 4 * (lane & 3)); }
+          // the words of the rows above go back where they were read from: luma rows -3..-1 = the loads of lanes 4..15, chroma row -1
+          // of plane q >> 1 = the loads of lanes 16 + 4 (q >> 1) + 2 + (q & 1)
+          if (lane < 12) { const int tr = 1 + (lane >> 2); *reinterpret_cast<uint32_t*> (reinterpret_cast<uint8_t*> (s.lp[2][lane + 4]) + mbx * 16) = *reinterpret_cast<const uint32_t*> (s.ry + tr * RY + 16 + 4 * (lane & 3)); }
           else if (lane < 16) {
             const int q = lane - 12;
-            *(reinterpret_cast<uint32_t*> (plane_ptr (pic, pic.cur_slot, 1 + (q >> 1)) + ((size_t)mby * 8 - 1) * CW + mbx * 8) + (q & 1)) = *reinterpret_cast<const uint32_t*> (s.rc[q >> 1] + 1 * RC + 8 + 4 * (q & 1));
+            *reinterpret_cast<uint32_t*> (reinterpret_cast<uint8_t*> (s.lp[2][16 + 4 * (q >> 1) + 2 + (q & 1)]) + mbx * 8) = *reinterpret_cast<const uint32_t*> (s.rc[q >> 1] + 1 * RC + 8 + 4 * (q & 1));
           }
         }
         const uint32_t n0 = py[4], n1 = py[5], nc = pc[2];      // cur = prev + 16 bytes (luma) / + 8 bytes (chroma)
@@ -670,8 +686,8 @@ __global__ void __launch_bounds__ (ROWS_WARPS * 32, 2) k_decode_rows (const PicD
     {
       const uint32_t* py = reinterpret_cast<const uint32_t*> (s.ry + (RY_TOP + r) * RY + 8 * h);
       const uint32_t* pc = reinterpret_cast<const uint32_t*> (s.rc[cp] + (RC_TOP + cr) * RC + 4 * h);
-      *reinterpret_cast<uint2*> (Y + (size_t)r * W + (mb_w - 1) * 16 + 8 * h) = make_uint2 (py[0], py[1]);
-      *reinterpret_cast<uint32_t*> (C + (size_t)cr * CW + (mb_w - 1) * 8 + 4 * h) = pc[0];
+      *reinterpret_cast<uint2*> (reinterpret_cast<uint8_t*> (s.lp[0][lane]) + (mb_w - 1) * 16) = make_uint2 (py[0], py[1]);
+      *reinterpret_cast<uint32_t*> (reinterpret_cast<uint8_t*> (s.lp[1][lane]) + (mb_w - 1) * 8) = pc[0];
     }
     __syncwarp();
     if (lane == 0) st_release (my, mb_w);
