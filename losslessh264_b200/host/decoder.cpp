@@ -643,10 +643,10 @@ struct Decoder::Impl {
         int fx = (px << 2) + mvx, fy = (py << 2) + mvy;
         int l = 0, t = 0, r = W, b = H;
         if (S->crop_left || S->crop_right || S->crop_top || S->crop_bottom) { l = S->crop_left; r = W - S->crop_right; t = S->crop_top; b = H - S->crop_top; }
-        if (fx < ((l + 2) << 2)) { fx = (fx >> 2) << 2; fx = std::max (l, fx); }
-        else if (fx > ((r - 19) << 2)) { fx = (fx >> 2) << 2; fx = std::min ((r - 17) << 2, fx); }
-        if (fy < ((t + 2) << 2)) { fy = (fy >> 2) << 2; fy = std::max (t, fy); }
-        else if (fy > ((b - 19) << 2)) { fy = (fy >> 2) << 2; fy = std::min ((b - 17) << 2, fy); }
+        if (fx < ((l + 2) << 2)) { fx &= ~3; fx = std::max (l, fx); }
+        else if (fx > ((r - 19) << 2)) { fx &= ~3; fx = std::min ((r - 17) << 2, fx); }
+        if (fy < ((t + 2) << 2)) { fy &= ~3; fy = std::max (t, fy); }
+        else if (fy > ((b - 19) << 2)) { fy &= ~3; fy = std::min ((b - 17) << 2, fy); }
         vx = fx - (px << 2); vy = fy - (py << 2);
       }
       for (int k = 0; k < 16; k++) { m.mv[k][0] = (int16_t)vx; m.mv[k][1] = (int16_t)vy; }

@@ -12,8 +12,8 @@ int LhfbSink::submit_model (const lh264_model_picture& pic, const DecodedPicture
   if (!fm_) return 0;
   const int32_t hdr[6] = {0x444d484c, pic.mb_w, pic.mb_h, pic.n_slices, pic.n_recs, pic.n_coef_blocks};
   fwrite (hdr, 4, 6, fm_);
-  fwrite (pic.slices, sizeof (lh264_model_slice), pic.n_slices, fm_);
-  fwrite (pic.recs, sizeof (lh264_model_mb), pic.n_recs, fm_);
+  if (pic.n_slices) fwrite (pic.slices, sizeof (lh264_model_slice), pic.n_slices, fm_);     // (a damaged picture may bring none: no null pointer to fwrite)
+  if (pic.n_recs) fwrite (pic.recs, sizeof (lh264_model_mb), pic.n_recs, fm_);
   if (pic.n_coef_blocks) fwrite (pic.coefs, 32, pic.n_coef_blocks, fm_);
   return 0;
 }
