@@ -78,6 +78,7 @@ struct ModelCtx {
   // instead of the sum of the three) overrides.
   int exclusive_env = -1;
   bool gen_with_coder = false;
+  size_t max_inflight_resident = 2;
   bool beside_coder = false;                       // mode 3: a coder launch is in front of the window being generated (else the window is chained as in mode 2)
   bool last_resident = false;                      // the step submitted last came from a resident batch
   bool exclusive = true;
@@ -180,6 +181,7 @@ static ModelCtx* model_ctx (lh264_ctx* c) {
     cudaEventCreateWithFlags (&m->coder_start, cudaEventDisableTiming);
     for (int k = 0; k < 2; k++) { cudaEventCreateWithFlags (&m->index_copied[k], cudaEventDisableTiming); cudaEventCreateWithFlags (&m->coder_done[k], cudaEventDisableTiming); }
     if (const char* e = getenv ("LH264_CODE_EXCLUSIVE")) m->exclusive_env = atoi (e);
+    if (const char* e = getenv ("LH264_MODEL_INFLIGHT")) m->max_inflight_resident = (size_t)std::max (2, std::min (atoi (e), 12));
     if (const char* e = getenv ("LH264_STATS")) m->stats = atoi (e) != 0;
     if (const char* e = getenv ("LH264_CODE_STEPS")) m->code_steps = std::max (1, std::min (atoi (e), 64));
     {
@@ -663,7 +665,9 @@ static int model_run (lh264_ctx* c, ModelCtx* m, MBatch& b) {
   if (n == 0) return LH264_OK;
   int rc = model_settle_batch (c, m, &b);          // a resident batch that is run again while still pending
   if (rc) return rc;
-  while (m->inflight.size() >= 2) if ((rc = model_settle_batch (c, m, m->inflight.front()))) return rc;
+  // (LH264_MODEL_INFLIGHT: how many steps of RESIDENT batches the host may run ahead of the device before it settles the oldest;
+  //  default 2.  An experiment hook for the schedule outlier of profiles/r2_summary.md section 15 - not measured yet)
+  while (m->inflight.size() >= (b.resident ? m->max_inflight_resident : (size_t)2)) if ((rc = model_settle_batch (c, m, m->inflight.front()))) return rc;
   for (int i = 0; i < n; i++) if (!m->streams[b.stream_of[i]].open) return fail (LH264_E_INVALID, "batch names a closed model stream");
   if (!m->d_page_ptrs && (rc = model_grow_arena (c, m, (unsigned int)n * CT_COUNT + 64))) return rc;
   if (!m->dec[m->cur].p && (rc = model_grow_pool (c, m, std::max<unsigned long long> ((unsigned long long)b.total_recs * 96 + 1024, m->last_step_total)))) return rc;   // first guess; model_settle grows it when needed
