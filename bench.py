@@ -613,8 +613,8 @@ def main():
     if not args.no_workloads:
         line["workloads"] = {}
         for key, fname, Sw, loops_w, note in (
-                ("syn720p_8f", "syn720p_8f.264", 512, 4, "BASELINE config 3 shape: 1280x720, 8 pictures, decode + recompress"),
-                ("syn4k_8slices_ltr_4f", "syn4k_8slices_ltr_4f.264", 64, 4, "BASELINE config 5 shape: 4096x2304, 8 slices per picture, two long-term references, recompression corpus")):
+                ("syn720p_8f", "syn720p_8f.264", 512, 8, "BASELINE config 3 shape: 1280x720, 8 pictures, decode + recompress"),
+                ("syn4k_8slices_ltr_4f", "syn4k_8slices_ltr_4f.264", 64, 8, "BASELINE config 5 shape: 4096x2304, 8 slices per picture, two long-term references, recompression corpus")):
             path = os.path.join(ROOT, "tests", "golden", "streams", fname)
             wdata = [open(path, "rb").read()]
             barrier()
